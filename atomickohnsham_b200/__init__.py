@@ -1,0 +1,11 @@
+"""atomickohnsham_b200: B200-native SCF inner loop for radial Kohn-Sham atoms.
+
+Host-side mirror of the AtomicKohnSham.jl public API for the hot path
+(`KSEModel`, `KSEDiscretization`, `P1IntLegendreBasis` on exp/geometric meshes,
+`ODA`, `groundstate`) over a C-ABI CUDA library (`include/aks_b200.h`).
+"""
+from .mesh import (Mesh, expmesh, geometricmesh, linmesh, polynomialmesh, explinmesh,  # noqa: F401
+                   findindex)
+from .basis import P1IntLegendreBasis, FEMBasis  # noqa: F401
+from .quadrature import GaussLegendre  # noqa: F401
+from .femops import FEMOperators, build_femops  # noqa: F401

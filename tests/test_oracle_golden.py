@@ -1,0 +1,156 @@
+"""Pin the CPU oracle against every golden value the reference commits for the
+hot path.  CPU only."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, make_oracle, package_tables
+
+
+def _cm(M):  # column-major flattening, as stored by Julia/JLD2
+    return np.asarray(M).transpose(*reversed(range(np.ndim(M)))).reshape(-1)
+
+
+def test_fem_matrices_golden():
+    """test/fem.jl:147-174 -- M0, M(1/x), M(1/x^2), A, T0, T(1/x), T(1/x^2), atol 1e-12."""
+    from atomickohnsham_b200.mesh import polynomialmesh
+    from oracle.fem_reference import ReferenceTables
+    g = load_golden("fem_matrices.json")
+    rt = ReferenceTables(polynomialmesh(0.0, 1.0, 3, s=0.9).points, 2, 8)
+    tol = 1e-12
+    assert np.allclose(_cm(rt.M0), g["M0"], atol=tol, rtol=0)
+    assert np.allclose(_cm(rt.A), g["A"], atol=tol, rtol=0)
+    assert np.allclose(_cm(rt.Mm1), g["M1"], atol=tol, rtol=0)
+    assert np.allclose(_cm(rt.Mm2), g["M2"], atol=tol, rtol=0)
+    assert np.allclose(_cm(rt.plain_tensor_dense()), g["T0"], atol=tol, rtol=0)
+    assert np.allclose(_cm(rt.weighted_tensor_dense(1)), g["T1"], atol=tol, rtol=0)
+    assert np.allclose(_cm(rt.weighted_tensor_dense(2)), g["T2"], atol=tol, rtol=0)
+
+
+def test_package_tables_match_fem_golden():
+    """The package's stable (quadrature) builder reproduces the same fixture."""
+    g = load_golden("fem_matrices.json")
+    basis, ops, _ = package_tables(["poly", 0.0, 1.0, 3, 0.9], 2, 8)
+    for key, M in (("M0", ops.M0), ("A", ops.A), ("M1", ops.Mm1), ("M2", ops.Mm2)):
+        assert np.allclose(_cm(M), g[key], atol=1e-12, rtol=0), key
+    i, j, m, v = ops.F_coo()
+    T1 = np.zeros((3, 3, 3))
+    T1[i, j, m] = v
+    assert np.allclose(_cm(T1), g["T1"], atol=1e-12, rtol=0)
+
+
+def test_stable_vs_monomial_tables_p10():
+    """At order 10 the two builders agree to the monomial noise level."""
+    from oracle.fem_reference import ReferenceTables
+    basis, ops, quad = package_tables(["exp", 0, 30, 8, 1.3], 10, 64)
+    rt = ReferenceTables(basis.mesh.points, 10, 64)
+    for a, b in ((ops.M0, rt.M0), (ops.A, rt.A), (ops.Mm1, rt.Mm1), (ops.Mm2, rt.Mm2)):
+        d = np.sqrt(np.abs(np.diag(a)))
+        assert np.max(np.abs(a - b) / np.outer(d, d)) < 5e-9
+    assert np.max(np.abs(quad.Pgenx - rt.Pgenx)) < 1e-11
+    assert np.max(np.abs(quad.x - rt.x)) < 1e-15
+
+
+def test_brent_first_point_and_boundary():
+    """examples/basic_example/log.txt: a monotone objective ends at t = 0.999999999991612."""
+    from oracle.brent import brent_minimize
+    tol = 1e4 * np.finfo(float).eps
+    seen = []
+
+    def f(t):
+        seen.append(t)
+        return -t
+
+    t, _, _ = brent_minimize(f, 0.0, 1.0, abs_tol=tol, rel_tol=tol)
+    assert seen[0] == 0.3819660112501051
+    assert t == 0.999999999991612
+
+
+@pytest.mark.parametrize("name", ["hydrogen_rhf", "hydrogen_slater", "hydrogen_bare"])
+@pytest.mark.parametrize("tables", ["package", "reference"])
+def test_hydrogen_goldens(name, tables):
+    """test/hydrogen.jl:55-116,138-171."""
+    g = load_golden("scf_goldens.json")[name]
+    o = make_oracle(g["setup"], tables=tables)
+    st, _ = o.groundstate(maxiter=g["setup"].get("maxiter", 100))
+    assert st.stop < g["setup"]["scftol"]
+    e = st.energies
+    for k in ("Ekin", "Ecou", "Ehar", "Eexc", "Etot"):
+        if k in g:
+            assert abs(getattr(e, k) - g[k]) < g["tol"], k
+    if "eps_1s" in g:
+        assert abs(st.eps[0, 0, 0] - g["eps_1s"]) < g["eps_tol"]
+        assert st.n[0, 0, 0] == 1.0
+    if "eps" in g:
+        for key, val in g["eps"].items():
+            l, k = map(int, key.split(","))
+            assert abs(st.eps[l, k, 0] - val) < g["tol"]
+
+
+def test_readme_hydrogen_c1():
+    """README.md:57-84 (config C1): eps_1s to 9 digits; iteration count is reported,
+    not asserted to +-1 (chaotic Brent tail)."""
+    g = load_golden("scf_goldens.json")["readme_hydrogen"]
+    st, _ = make_oracle(g["setup"]).groundstate()
+    assert abs(st.eps[0, 0, 0] - g["eps_1s"]) < 1e-9
+    assert abs(st.niter - g["niter"]) <= 4
+    assert st.n[0, 0, 0] == 1.0
+
+
+def test_sodium_trajectory():
+    """examples/basic_example/log.txt:35-57 -- iteration 0 to 1e-12 relative, boundary `t`
+    values digit for digit, final Etot to 1e-12 relative, occupations."""
+    g = load_golden("trajectories.json")["sodium_slater"]
+    st, hist = make_oracle(g["setup"]).groundstate()
+    ref = g["log"]
+    for k in ("Etot", "Ekin", "Ecou", "Ehar", "Eexc"):
+        assert abs(hist[0][k] - ref[0][k]) < 1e-12 * abs(ref[0][k]) + 1e-12, k
+    for i in (2, 5, 7):
+        assert hist[i]["t"] == ref[i]["t"] == 0.999999999991612
+    assert abs(hist[9]["t"] - ref[9]["t"]) < 1e-12
+    for i in range(10):
+        assert abs(hist[i]["Etot"] - ref[i]["Etot"]) < 2e-9 * abs(ref[i]["Etot"])
+    r = g["results"]
+    assert abs(st.energies.Etot - r["Etot"]) < 1e-12 * abs(r["Etot"])
+    assert abs(st.niter - r["niter"]) <= 3
+    gold = {lab: (e, n) for lab, e, n in r["orbitals"]}
+    got = {"1s": (0, 0), "2s": (0, 1), "3s": (0, 2), "2p": (1, 0), "3p": (1, 1)}
+    for lab, (l, k) in got.items():
+        # scftol = 1e-9 converges eps to ~1e-8 absolute only
+        assert abs(st.eps[l, k, 0] - gold[lab][0]) < 5e-8 * max(1.0, abs(gold[lab][0])), lab
+        assert abs(st.n[l, k, 0] - gold[lab][1]) < 1e-9, lab
+
+
+def test_oxygen_lda():
+    """examples/functional comparison/lda/results.txt (builtin lda_x + PW92)."""
+    g = load_golden("trajectories.json")["oxygen_lda"]
+    st, _ = make_oracle(g["setup"]).groundstate()
+    r = g["results"]
+    assert abs(st.energies.Etot - r["Etot"]) < 1e-11 * abs(r["Etot"])
+    assert abs(st.niter - r["niter"]) <= 3
+    gold = {lab: (e, n) for lab, e, n in r["orbitals"]}
+    for lab, (l, k) in {"1s": (0, 0), "2s": (0, 1), "2p": (1, 0)}.items():
+        assert abs(st.eps[l, k, 0] - gold[lab][0]) < 1e-8 * abs(gold[lab][0]), lab
+        assert st.n[l, k, 0] == gold[lab][1]
+
+
+def test_scandium_rhf_twofold_degeneracy():
+    """test/scandium.jl:38-107: Etot to 1e-9, eps to 1e-5, n(3d)/5 ~ 0.0056."""
+    g = load_golden("scf_goldens.json")["scandium_rhf"]
+    st, _ = make_oracle(g["setup"]).groundstate()
+    assert abs(st.energies.Etot - g["Etot"]) < g["tol"]
+    lab = {"1s": (0, 0), "2s": (0, 1), "3s": (0, 2), "4s": (0, 3), "2p": (1, 0), "3p": (1, 1),
+           "4p": (1, 2), "3d": (2, 0)}
+    for name, (l, k) in lab.items():
+        assert abs(st.eps[l, k, 0] - g["eps"][name]) < g["eps_tol"], name
+    assert abs(st.n[2, 0, 0] / 5 - g["n3d_over_5"]) < g["n3d_tol"]
+    assert list(st.n[0, :4, 0]) == [2.0, 2.0, 2.0, 2.0] and list(st.n[1, :2, 0]) == [6.0, 6.0]
+    assert abs(st.n.sum() - 21) < 1e-12
+
+
+def test_sqrtinv_route_matches_generalized():
+    """S = sqrt(inv(M0)) route vs Cholesky route, same pencil."""
+    g = load_golden("scf_goldens.json")["hydrogen_slater"]
+    a, _ = make_oracle(g["setup"], eig="sqrtinv").groundstate()
+    b, _ = make_oracle(g["setup"], eig="generalized").groundstate()
+    assert abs(a.energies.Etot - b.energies.Etot) < 1e-11
+    assert abs(a.eps[0, 0, 0] - b.eps[0, 0, 0]) < 1e-9
