@@ -9,3 +9,16 @@ from .mesh import (Mesh, expmesh, geometricmesh, linmesh, polynomialmesh, explin
 from .basis import P1IntLegendreBasis, FEMBasis  # noqa: F401
 from .quadrature import GaussLegendre  # noqa: F401
 from .femops import FEMOperators, build_femops  # noqa: F401
+
+
+def __getattr__(name):
+    """Device-facing API (needs the built CUDA library; no CPU fallback)."""
+    _dev = {"KSEModel": "model", "NoFunctional": "model", "BuiltinFunctional": "model", "Functional": "model",
+            "RHF": "model", "Slater": "model", "LDA": "model", "ODA": "algorithms",
+            "OptimizedAufbau": "algorithms", "KSEDiscretization": "discretization",
+            "groundstate": "solver", "KSESolver": "solver", "KSESolution": "solver", "Batch": "solver",
+            "CallbackSet": "solver", "LogFileCallback": "solver", "LogBook": "solver"}
+    if name in _dev:
+        import importlib
+        return getattr(importlib.import_module(f".{_dev[name]}", __name__), name)
+    raise AttributeError(name)

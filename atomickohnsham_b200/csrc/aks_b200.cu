@@ -1,0 +1,820 @@
+// Host side of the C ABI (include/aks_b200.h): table preprocessing, device memory, the
+// per-iteration launch sequence.  No CPU fallback: every numerical step of the SCF loop runs
+// in the kernels of k_*.cuh; the host only splits the caller's (reference-built) global
+// tables into per-cell blocks once, at aks_disc_create.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/aks_b200.h"
+#include "aks_device.cuh"
+#include "aks_types.cuh"
+#include "k_aux.cuh"
+#include "k_eig.cuh"
+#include "k_potential.cuh"
+#include "k_scf.cuh"
+
+struct aks_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+};
+
+struct aks_disc {
+  aks_ctx* ctx = nullptr;
+  DiscDev dev{};
+  std::vector<void*> allocs;
+  std::vector<int> l2g;  // host copy [C][n]
+  int nmax_tpl = 32;     // template NMAX for the density kernels
+};
+
+struct aks_batch {
+  aks_disc* disc = nullptr;
+  BatchDev dev{};
+  std::vector<void*> allocs;
+  int B = 0;
+  bool fac_in_smem = true;
+  double* fac_global = nullptr;
+  size_t smem_pot = 0, smem_eig = 0, smem_dens = 0, smem_poisson = 0;
+  std::vector<double> hZ, hN, hHar;
+  std::vector<int> hLp, hnhp;
+  aks_iter_record* h_rec = nullptr;  // pinned
+  bool timers = false;
+  cudaEvent_t ev[9];
+  double phase_ms[8] = {0};
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      char buf_[512];                                                                         \
+      snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #call,                \
+               cudaGetErrorString(e_));                                                       \
+      ctx->err = buf_;                                                                        \
+      return AKS_ECUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+template <class T>
+static int dev_upload(aks_ctx* ctx, std::vector<void*>& allocs, const std::vector<T>& h, const T** out) {
+  void* p = nullptr;
+  const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  CK(cudaMalloc(&p, bytes));
+  allocs.push_back(p);
+  if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = (const T*)p;
+  return AKS_OK;
+}
+template <class T>
+static int dev_zeros(aks_ctx* ctx, std::vector<void*>& allocs, size_t count, T** out) {
+  void* p = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  CK(cudaMalloc(&p, bytes));
+  allocs.push_back(p);
+  CK(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+  *out = (T*)p;
+  return AKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ context
+extern "C" int aks_ctx_create(int device, aks_ctx** out) {
+  if (!out) return AKS_EINVAL;
+  aks_ctx* ctx = new aks_ctx();
+  ctx->device = device;
+  *out = ctx;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { ctx->err = "no such CUDA device"; return AKS_ECUDA; }
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  XcConsts xc;
+  xc.cx = std::pow(3.0 / M_PI, 1.0 / 3.0);
+  xc.cx34 = 0.75 * xc.cx;
+  xc.cx6_34 = 0.75 * std::pow(6.0 / M_PI, 1.0 / 3.0);
+  xc.fourpi = 4.0 * M_PI;
+  xc.inv4pi = 1.0 / (4.0 * M_PI);
+  xc.f2p0 = 4.0 / (9.0 * (std::pow(2.0, 1.0 / 3.0) - 1.0));
+  xc.two43m2 = std::pow(2.0, 4.0 / 3.0) - 2.0;
+  xc.third = 1.0 / 3.0;
+  xc.four3 = 4.0 / 3.0;
+  CK(cudaMemcpyToSymbol(c_xc, &xc, sizeof xc));
+  return AKS_OK;
+}
+extern "C" void aks_ctx_destroy(aks_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+extern "C" const char* aks_last_error(const aks_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+extern "C" void* aks_ctx_stream(const aks_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int64_t aks_launch_count(const aks_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------ disc
+// small dense helpers (setup only)
+static bool chol_inverse(std::vector<double>& A, int m) {
+  // in-place inverse of an SPD m x m matrix (row-major) via Gauss-Jordan with no pivoting
+  std::vector<double> I(m * m, 0.0);
+  for (int i = 0; i < m; ++i) I[i * m + i] = 1.0;
+  for (int j = 0; j < m; ++j) {
+    const double piv = A[j * m + j];
+    if (!(piv > 0.0)) return false;
+    const double inv = 1.0 / piv;
+    for (int k = 0; k < m; ++k) { A[j * m + k] *= inv; I[j * m + k] *= inv; }
+    for (int i = 0; i < m; ++i) {
+      if (i == j) continue;
+      const double f = A[i * m + j];
+      if (f == 0.0) continue;
+      for (int k = 0; k < m; ++k) { A[i * m + k] -= f * A[j * m + k]; I[i * m + k] -= f * I[j * m + k]; }
+    }
+  }
+  A = I;
+  return true;
+}
+
+extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** out) {
+  if (!ctx || !D || !out) return AKS_EINVAL;
+  *out = nullptr;
+  if (D->dtype == 1) { ctx->err = "dtype=1 (Double64) is not built in this round"; return AKS_ENOSYS; }
+  if (D->dtype != 0) { ctx->err = "bad dtype"; return AKS_EINVAL; }
+  const int p = D->p, C = D->C, Nh = D->Nh, Q = D->Q, G = D->G, n = p + 1, nb = p - 1;
+  if (p < 2 || p > 29 || C < 2 || Nh != p * C - 1 || Q < 1 || G < 1 || D->lh < 0 || D->nh < 1 ||
+      (D->nspin != 1 && D->nspin != 2)) {
+    ctx->err = "aks_disc_create: need 2 <= p <= 29, C >= 2, Nh == p*C-1, Q,G >= 1, nspin in {1,2}";
+    return AKS_EINVAL;
+  }
+  if ((D->lh + 1) * D->nh * D->nspin > AKS_MAXORB) { ctx->err = "(lh+1)*nh*nspin exceeds AKS_MAXORB"; return AKS_EINVAL; }
+  if (!D->mesh || !D->invshifts || !D->x || !D->w || !D->Pgenx || !D->y || !D->wy || !D->ycell ||
+      !D->Pgeny || !D->M0 || !D->A || !D->Mm1 || !D->cell_len || !D->cell_indices || !D->cell_generators) {
+    ctx->err = "aks_disc_create: NULL table";
+    return AKS_EINVAL;
+  }
+  if (D->lh > 0 && !D->Mm2) { ctx->err = "Mm2 required when lh > 0"; return AKS_EINVAL; }
+  aks_disc* disc = new aks_disc();
+  disc->ctx = ctx;
+  DiscDev& dv = disc->dev;
+  dv.p = p; dv.n = n; dv.nb = nb; dv.npk = n * (n + 1) / 2; dv.C = C; dv.Nh = Nh; dv.Q = Q;
+  dv.Qs = ((Q + 3) / 4) * 4; dv.G = G; dv.L = D->lh + 1; dv.nh = D->nh; dv.nspin = D->nspin;
+  dv.Rmax = D->mesh[C];
+  disc->nmax_tpl = (n <= 12) ? 12 : (n <= 24 ? 24 : 32);
+
+  // local-to-global map
+  std::vector<int>& l2g = disc->l2g;
+  l2g.assign((size_t)C * n, -1);
+  for (int c = 0; c < C; ++c) {
+    const int len = (int)D->cell_len[c];
+    if (len < 1 || len > n) { ctx->err = "bad cell_len"; delete disc; return AKS_EINVAL; }
+    for (int j = 0; j < len; ++j) {
+      const int64_t I = D->cell_indices[(size_t)c * n + j], g = D->cell_generators[(size_t)c * n + j];
+      if (I < 1 || I > Nh || g < 1 || g > n) { ctx->err = "bad cell index/generator"; delete disc; return AKS_EINVAL; }
+      l2g[(size_t)c * n + (g - 1)] = (int)(I - 1);
+    }
+  }
+  // structural check: right hat of cell c == left hat of cell c+1, ends are Dirichlet
+  for (int c = 0; c + 1 < C; ++c)
+    if (l2g[(size_t)c * n] < 0 || l2g[(size_t)c * n] != l2g[(size_t)(c + 1) * n + 1]) {
+      ctx->err = "cell maps are not a P1+bubble chain"; delete disc; return AKS_EINVAL;
+    }
+  if (l2g[1] != -1 || l2g[(size_t)(C - 1) * n] != -1) { ctx->err = "expected Dirichlet ends"; delete disc; return AKS_EINVAL; }
+
+  // split global symmetric matrices into cell-owned blocks (first cell containing both indices)
+  auto split = [&](const double* Gm, std::vector<double>& loc) {
+    loc.assign((size_t)C * n * n, 0.0);
+    if (!Gm) return;
+    std::vector<char> owned((size_t)Nh * Nh, 0);
+    for (int c = 0; c < C; ++c)
+      for (int a = 0; a < n; ++a) {
+        const int I = l2g[(size_t)c * n + a];
+        if (I < 0) continue;
+        for (int bq = 0; bq < n; ++bq) {
+          const int J = l2g[(size_t)c * n + bq];
+          if (J < 0) continue;
+          if (owned[(size_t)I * Nh + J]) continue;
+          owned[(size_t)I * Nh + J] = 1;
+          loc[((size_t)c * n + a) * n + bq] = 0.5 * (Gm[(size_t)I + (size_t)Nh * J] + Gm[(size_t)J + (size_t)Nh * I]);
+        }
+      }
+  };
+  std::vector<double> M0l, Al, M1l, M2l;
+  split(D->M0, M0l);
+  split(D->A, Al);
+  split(D->Mm1, M1l);
+  split(D->Mm2, M2l);
+  // packed M0
+  std::vector<double> M0pk((size_t)C * dv.npk, 0.0);
+  for (int c = 0; c < C; ++c)
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) M0pk[(size_t)c * dv.npk + pk_index(i, j, nb)] = M0l[((size_t)c * n + i) * n + j];
+  // mass tensor: COO -> per-cell [m][ij], owner = first cell that holds all three indices
+  std::vector<double> Fl((size_t)C * n * n * n, 0.0);
+  if (D->nF > 0) {
+    if (!D->Fi || !D->Fj || !D->Fm || !D->Fv) { ctx->err = "NULL F arrays"; delete disc; return AKS_EINVAL; }
+    std::vector<int> cell_of((size_t)Nh * 2, -1), loc_of((size_t)Nh * 2, -1);
+    for (int c = 0; c < C; ++c)
+      for (int a = 0; a < n; ++a) {
+        const int I = l2g[(size_t)c * n + a];
+        if (I < 0) continue;
+        const int slot = (cell_of[2 * I] < 0) ? 0 : 1;
+        cell_of[2 * I + slot] = c;
+        loc_of[2 * I + slot] = a;
+      }
+    for (int64_t t = 0; t < D->nF; ++t) {
+      const int I = (int)D->Fi[t] - 1, J = (int)D->Fj[t] - 1, M = (int)D->Fm[t] - 1;
+      if (I < 0 || J < 0 || M < 0 || I >= Nh || J >= Nh || M >= Nh) { ctx->err = "bad F index"; delete disc; return AKS_EINVAL; }
+      int owner = -1, la = 0, lb = 0, lm = 0;
+      for (int si = 0; si < 2 && owner < 0; ++si) {
+        const int c = cell_of[2 * I + si];
+        if (c < 0) continue;
+        int fj = -1, fm = -1;
+        for (int sj = 0; sj < 2; ++sj) if (cell_of[2 * J + sj] == c) fj = loc_of[2 * J + sj];
+        for (int sm2 = 0; sm2 < 2; ++sm2) if (cell_of[2 * M + sm2] == c) fm = loc_of[2 * M + sm2];
+        if (fj >= 0 && fm >= 0) { owner = c; la = loc_of[2 * I + si]; lb = fj; lm = fm; }
+      }
+      if (owner < 0) continue;  // not a cell-local triple: cannot carry weight in this basis
+      // symmetrise in (i,j): half to (a,b), half to (b,a)
+      Fl[(((size_t)owner * n + lm) * n + la) * n + lb] += 0.5 * D->Fv[t];
+      Fl[(((size_t)owner * n + lm) * n + lb) * n + la] += 0.5 * D->Fv[t];
+    }
+  }
+  // Poisson prefactor: static condensation of the stiffness operator
+  std::vector<double> Abbinv((size_t)C * nb * nb), XA((size_t)C * 2 * nb), triD(C, 1.0), triL(C, 0.0);
+  {
+    std::vector<double> S00(C), S10(C), S11(C);
+    for (int c = 0; c < C; ++c) {
+      std::vector<double> bbm((size_t)nb * nb);
+      for (int i = 0; i < nb; ++i)
+        for (int j = 0; j < nb; ++j) bbm[(size_t)i * nb + j] = Al[((size_t)c * n + 2 + i) * n + 2 + j];
+      if (!chol_inverse(bbm, nb)) { ctx->err = "stiffness bubble block not positive definite"; delete disc; return AKS_EINVAL; }
+      std::copy(bbm.begin(), bbm.end(), Abbinv.begin() + (size_t)c * nb * nb);
+      for (int g = 0; g < 2; ++g)
+        for (int i = 0; i < nb; ++i) {
+          double acc = 0.0;
+          for (int j = 0; j < nb; ++j) acc += bbm[(size_t)i * nb + j] * Al[((size_t)c * n + 2 + j) * n + g];
+          XA[((size_t)c * 2 + g) * nb + i] = acc;
+        }
+      auto hb = [&](int g, int i) { return Al[((size_t)c * n + 2 + i) * n + g]; };
+      double t00 = 0, t10 = 0, t11 = 0;
+      for (int i = 0; i < nb; ++i) {
+        t00 += hb(0, i) * XA[((size_t)c * 2 + 0) * nb + i];
+        t10 += hb(1, i) * XA[((size_t)c * 2 + 0) * nb + i];
+        t11 += hb(1, i) * XA[((size_t)c * 2 + 1) * nb + i];
+      }
+      S00[c] = Al[((size_t)c * n + 0) * n + 0] - t00;
+      S10[c] = Al[((size_t)c * n + 1) * n + 0] - t10;
+      S11[c] = Al[((size_t)c * n + 1) * n + 1] - t11;
+    }
+    double dprev = 0, offprev = 0;
+    for (int j = 0; j < C - 1; ++j) {
+      const double diag = S00[j] + S11[j + 1];
+      double l = 0, dj = diag;
+      if (j > 0) { l = offprev / dprev; dj = diag - l * offprev; }
+      if (!(dj > 0.0)) { ctx->err = "stiffness Schur complement not positive definite"; delete disc; return AKS_EINVAL; }
+      triD[j] = dj;
+      if (j > 0) triL[j - 1] = l;
+      dprev = dj;
+      offprev = (j + 1 < C - 1) ? S10[j + 1] : 0.0;
+    }
+  }
+  // Gauss tables
+  std::vector<double> Pg((size_t)n * dv.Qs, 0.0), Pgy((size_t)n * G, 0.0), inv1(C), inv2(C);
+  for (int g = 0; g < n; ++g) {
+    for (int q = 0; q < Q; ++q) Pg[(size_t)g * dv.Qs + q] = D->Pgenx[(size_t)g + (size_t)n * q];
+    for (int q = 0; q < G; ++q) Pgy[(size_t)g * G + q] = D->Pgeny[(size_t)g + (size_t)n * q];
+  }
+  for (int c = 0; c < C; ++c) { inv1[c] = D->invshifts[2 * c]; inv2[c] = D->invshifts[2 * c + 1]; }
+  std::vector<int> ycell(G);
+  for (int q = 0; q < G; ++q) {
+    const int64_t c = D->ycell[q];
+    if (c < 1 || c > C) { ctx->err = "ycell out of range"; delete disc; return AKS_EINVAL; }
+    ycell[q] = (int)c - 1;
+  }
+  std::vector<double> xv(D->x, D->x + Q), wv(D->w, D->w + Q), yv(D->y, D->y + G), wyv(D->wy, D->wy + G);
+  int rc;
+#define UP(vec, field)                                                                          \
+  if ((rc = dev_upload(ctx, disc->allocs, vec, &dv.field)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
+  UP(Pg, Pg) UP(wv, w) UP(xv, x) UP(inv1, inv1) UP(inv2, inv2) UP(Al, A_loc) UP(M0l, M0_loc) UP(M1l, Mm1_loc)
+  UP(M2l, Mm2_loc) UP(M0pk, M0pk) UP(Fl, F_loc) UP(l2g, l2g) UP(yv, y) UP(wyv, wy) UP(ycell, ycell) UP(Pgy, Pgy)
+  UP(Abbinv, Abb_inv) UP(XA, XA) UP(triD, triA_d) UP(triL, triA_l)
+#undef UP
+  *out = disc;
+  return AKS_OK;
+}
+
+extern "C" void aks_disc_destroy(aks_disc* disc) {
+  if (!disc) return;
+  for (void* p : disc->allocs) cudaFree(p);
+  delete disc;
+}
+
+// ------------------------------------------------------------------------------------ batch
+extern "C" int aks_batch_reset(aks_batch* bt);
+
+extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const double* N,
+                                const double* hartree, const int32_t* ex_id, const int32_t* ec_id,
+                                const int32_t* lh_p, const int32_t* nh_p, aks_batch** out) {
+  if (!disc || !out || nprob < 1 || !Z || !N) return AKS_EINVAL;
+  aks_ctx* ctx = disc->ctx;
+  *out = nullptr;
+  const DiscDev& dv = disc->dev;
+  aks_batch* bt = new aks_batch();
+  bt->disc = disc;
+  bt->B = nprob;
+  BatchDev& b = bt->dev;
+  b.B = nprob; b.s = dv.nspin; b.Lmax = dv.L; b.nhmax = dv.nh;
+  b.ntile = (dv.Nh + MIX_TS - 1) / MIX_TS;
+  bt->hZ.assign(Z, Z + nprob);
+  bt->hN.assign(N, N + nprob);
+  bt->hHar.assign(nprob, 1.0);
+  if (hartree) bt->hHar.assign(hartree, hartree + nprob);
+  std::vector<int> ex(nprob, 0), ec(nprob, 0);
+  bt->hLp.assign(nprob, dv.L);
+  bt->hnhp.assign(nprob, dv.nh);
+  for (int i = 0; i < nprob; ++i) {
+    if (ex_id) ex[i] = ex_id[i];
+    if (ec_id) ec[i] = ec_id[i];
+    if (lh_p) bt->hLp[i] = lh_p[i] + 1;
+    if (nh_p) bt->hnhp[i] = nh_p[i];
+    if ((ex[i] != AKS_XC_NONE && ex[i] != AKS_LDA_X) || (ec[i] != AKS_XC_NONE && ec[i] != AKS_LDA_C_PW)) {
+      ctx->err = "unsupported functional id (LDA only: ex in {0,1}, ec in {0,12})"; delete bt; return AKS_EINVAL;
+    }
+    if (bt->hLp[i] < 1 || bt->hLp[i] > dv.L || bt->hnhp[i] < 1 || bt->hnhp[i] > dv.nh || !(N[i] > 0) || !(Z[i] > 0)) {
+      ctx->err = "bad per-problem lh/nh/Z/N"; delete bt; return AKS_EINVAL;
+    }
+  }
+  int rc;
+#define UPB(vec, field) if ((rc = dev_upload(ctx, bt->allocs, vec, &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
+  UPB(bt->hZ, Z) UPB(bt->hN, N) UPB(bt->hHar, hartree) UPB(ex, ex) UPB(ec, ec) UPB(bt->hLp, Lp) UPB(bt->hnhp, nhp)
+#undef UPB
+  const size_t B = nprob, s = b.s, Nh = dv.Nh, C = dv.C, Q = dv.Q, G = dv.G, L = b.Lmax, nh = b.nhmax, n = dv.n;
+#define ZB(T, field, count) if ((rc = dev_zeros<T>(ctx, bt->allocs, (count), &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
+  ZB(double, Dd, B * s * Nh * Nh) ZB(double, rho_q, B * s * C * Q) ZB(double, rho_y, B * s * G)
+  ZB(double, Bv, B * Nh) ZB(double, Wv, B * Nh) ZB(double, E, B * 5) ZB(double, t, B) ZB(double, stop, B)
+  ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk)
+  ZB(double, eps, B * s * L * nh) ZB(double, eps_new, B * s * L * nh) ZB(double, U, B * s * L * nh * Nh)
+  ZB(int, eig_info, B * s * L * nh) ZB(int, warm, B) ZB(double, ekin_orb, B * s * L * nh)
+  ZB(double, ecou_orb, B * s * L * nh) ZB(double, occ, B * 2 * s * L * nh) ZB(int, degen, B)
+  ZB(int, degen_idx, B * 2) ZB(double, degen_n, B * 4) ZB(double, rho_q_new, B * 2 * s * C * Q)
+  ZB(double, rho_y_new, B * 2 * s * G) ZB(double, corr_part, B * 2 * C) ZB(double, Bloc_new, B * 2 * C * n)
+  ZB(double, B_new, B * 2 * Nh) ZB(double, W_new, B * 2 * Nh) ZB(double, scal, B * 2 * 4) ZB(double, td, B)
+  ZB(double, tmix, B) ZB(double, norm_part, B * s * b.ntile * b.ntile) ZB(aks_iter_record, rec, B)
+  ZB(double, Enew, B * 5)
+#undef ZB
+  // ODA defaults (oda/types.jl:38-44, optimized.jl:23-26)
+  b.scftol = 1e-10; b.tinit = 0.6; b.frozen_t = 0; b.maxiter_ls = 100;
+  b.abstol_ls = b.reltol_ls = 1e4 * 2.220446049250313e-16;
+  b.max_degen = 2; b.degen_tol = 1e-3; b.handle_spin = 1;
+  // launch configuration
+  bt->smem_pot = potential_smem_bytes(dv.n, dv.Q, b.s);
+  bt->smem_eig = eig_smem_bytes(dv.C, dv.npk, dv.Nh, true);
+  bt->fac_in_smem = bt->smem_eig <= 110 * 1024;  // two CTAs per SM; else one big CTA or global scratch
+  if (!bt->fac_in_smem && bt->smem_eig <= 220 * 1024) bt->fac_in_smem = true;
+  if (!bt->fac_in_smem) {
+    bt->smem_eig = eig_smem_bytes(dv.C, dv.npk, dv.Nh, false);
+    const size_t cnt = (size_t)B * s * L * nh * C * dv.npk;
+    if ((rc = dev_zeros<double>(ctx, bt->allocs, cnt, &bt->fac_global)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
+  }
+  bt->smem_dens = sizeof(double) * ((size_t)AKS_MAXORB * disc->nmax_tpl + (size_t)std::max<int>(dv.n * dv.n * b.s, dv.n * dv.n) + AKS_NW + 8);
+  bt->smem_poisson = sizeof(double) * ((size_t)2 * dv.Nh + 3 * dv.C + 16);
+  if (bt->smem_pot > 220 * 1024 || bt->smem_eig > 220 * 1024 || bt->smem_dens > 220 * 1024) {
+    ctx->err = "discretization too large for the shared-memory tiling of this build"; aks_batch_destroy(bt); return AKS_EINVAL;
+  }
+  CK(cudaFuncSetAttribute(k_potential, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
+  CK(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
+  CK(cudaFuncSetAttribute(k_eig_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
+  CK(cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_poisson));
+  CK(cudaFuncSetAttribute(k_dens_cells<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
+  CK(cudaFuncSetAttribute(k_dens_cells<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
+  CK(cudaFuncSetAttribute(k_dens_cells<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
+  CK(cudaFuncSetAttribute(k_cells_from_dense<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
+  CK(cudaFuncSetAttribute(k_cells_from_dense<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
+  CK(cudaFuncSetAttribute(k_cells_from_dense<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
+  CK(cudaMallocHost((void**)&bt->h_rec, sizeof(aks_iter_record) * B));
+  const char* tenv = getenv("AKS_PHASE_TIMERS");
+  bt->timers = tenv && tenv[0] == '1';
+  if (bt->timers) for (auto& e : bt->ev) CK(cudaEventCreate(&e));
+  *out = bt;
+  return aks_batch_reset(bt);
+}
+
+extern "C" void aks_batch_destroy(aks_batch* bt) {
+  if (!bt) return;
+  for (void* p : bt->allocs) cudaFree(p);
+  if (bt->h_rec) cudaFreeHost(bt->h_rec);
+  if (bt->timers) for (auto& e : bt->ev) cudaEventDestroy(e);
+  delete bt;
+}
+
+extern "C" int aks_batch_set_oda(aks_batch* bt, double scftol, double tinit, int32_t frozen_t,
+                                 int32_t maxiter_ls, double abstol_ls, double reltol_ls, int32_t max_degen,
+                                 double degen_tol, int32_t handle_degen_spin_1iter) {
+  if (!bt) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  if (!(scftol > 0) || !(tinit >= 0 && tinit <= 1) || maxiter_ls < 1 || max_degen < 1 || !(degen_tol >= 0)) {
+    ctx->err = "aks_batch_set_oda: bad option"; return AKS_EINVAL;
+  }
+  BatchDev& b = bt->dev;
+  b.scftol = scftol; b.tinit = tinit; b.frozen_t = frozen_t; b.maxiter_ls = maxiter_ls;
+  b.abstol_ls = abstol_ls; b.reltol_ls = reltol_ls; b.max_degen = max_degen; b.degen_tol = degen_tol;
+  b.handle_spin = handle_degen_spin_1iter;
+  std::vector<double> tv(bt->B, tinit);
+  CK(cudaMemcpyAsync(b.t, tv.data(), sizeof(double) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
+extern "C" int aks_batch_reset(aks_batch* bt) {
+  if (!bt) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  BatchDev& b = bt->dev;
+  const DiscDev& dv = bt->disc->dev;
+  const size_t B = bt->B, s = b.s;
+  CK(cudaMemsetAsync(b.Dd, 0, sizeof(double) * B * s * dv.Nh * dv.Nh, ctx->stream));
+  CK(cudaMemsetAsync(b.rho_q, 0, sizeof(double) * B * s * dv.C * dv.Q, ctx->stream));
+  CK(cudaMemsetAsync(b.rho_y, 0, sizeof(double) * B * s * dv.G, ctx->stream));
+  CK(cudaMemsetAsync(b.Bv, 0, sizeof(double) * B * dv.Nh, ctx->stream));
+  CK(cudaMemsetAsync(b.Wv, 0, sizeof(double) * B * dv.Nh, ctx->stream));
+  CK(cudaMemsetAsync(b.E, 0, sizeof(double) * B * 5, ctx->stream));
+  CK(cudaMemsetAsync(b.stop, 0, sizeof(double) * B, ctx->stream));
+  CK(cudaMemsetAsync(b.niter, 0, sizeof(int) * B, ctx->stream));
+  CK(cudaMemsetAsync(b.status, 0, sizeof(int) * B, ctx->stream));
+  CK(cudaMemsetAsync(b.warm, 0, sizeof(int) * B, ctx->stream));
+  CK(cudaMemsetAsync(b.degen, 0, sizeof(int) * B, ctx->stream));
+  std::vector<double> tv(B, b.tinit);
+  CK(cudaMemcpyAsync(b.t, tv.data(), sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ SCF step
+#define LAUNCH_CHECK()                                                                        \
+  do {                                                                                        \
+    ctx->launches += 1;                                                                       \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess) {                                                                  \
+      char buf_[256];                                                                         \
+      snprintf(buf_, sizeof buf_, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      ctx->err = buf_;                                                                        \
+      return AKS_ECUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+static int launch_potential(aks_batch* bt, double* vxc_out, double* har_out) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  k_potential<<<dim3(dv.C, bt->B), AKS_NT, bt->smem_pot, ctx->stream>>>(dv, bt->dev, vxc_out, har_out, 0, 0);
+  LAUNCH_CHECK();
+  return AKS_OK;
+}
+static int launch_eig(aks_batch* bt) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const BatchDev& b = bt->dev;
+  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_eig, ctx->stream>>>(dv, b, bt->fac_global,
+                                                                                     bt->fac_in_smem ? 1 : 0);
+  LAUNCH_CHECK();
+  return AKS_OK;
+}
+static int launch_dens_cells(aks_batch* bt) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const dim3 grid(dv.C, bt->B, 2);
+  switch (bt->disc->nmax_tpl) {
+    case 12: k_dens_cells<12><<<grid, AKS_NT, bt->smem_dens, ctx->stream>>>(dv, bt->dev); break;
+    case 24: k_dens_cells<24><<<grid, AKS_NT, bt->smem_dens, ctx->stream>>>(dv, bt->dev); break;
+    default: k_dens_cells<32><<<grid, AKS_NT, bt->smem_dens, ctx->stream>>>(dv, bt->dev); break;
+  }
+  LAUNCH_CHECK();
+  const dim3 g2((dv.G + AKS_NT - 1) / AKS_NT, bt->B, 2);
+  switch (bt->disc->nmax_tpl) {
+    case 12: k_dens_grid<12><<<g2, AKS_NT, 0, ctx->stream>>>(dv, bt->dev); break;
+    case 24: k_dens_grid<24><<<g2, AKS_NT, 0, ctx->stream>>>(dv, bt->dev); break;
+    default: k_dens_grid<32><<<g2, AKS_NT, 0, ctx->stream>>>(dv, bt->dev); break;
+  }
+  LAUNCH_CHECK();
+  return AKS_OK;
+}
+
+static int step_launch(aks_batch* bt) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const BatchDev& b = bt->dev;
+  int rc;
+  int ei = 0;
+#define TICK() do { if (bt->timers) CK(cudaEventRecord(bt->ev[ei++], ctx->stream)); } while (0)
+  TICK();
+  if ((rc = launch_potential(bt, nullptr, nullptr)) != AKS_OK) return rc;
+  TICK();
+  if ((rc = launch_eig(bt)) != AKS_OK) return rc;
+  TICK();
+  k_aufbau<<<(bt->B + 63) / 64, 64, 0, ctx->stream>>>(dv, b);
+  LAUNCH_CHECK();
+  k_orb_energy<<<dim3(b.s * b.Lmax * b.nhmax, bt->B), 32, 0, ctx->stream>>>(dv, b);
+  LAUNCH_CHECK();
+  TICK();
+  if ((rc = launch_dens_cells(bt)) != AKS_OK) return rc;
+  TICK();
+  k_poisson<<<dim3(bt->B, 2), 128, bt->smem_poisson, ctx->stream>>>(dv, b, 0, 0);
+  LAUNCH_CHECK();
+  TICK();
+  k_linesearch<<<bt->B, AKS_NT, 0, ctx->stream>>>(dv, b);
+  LAUNCH_CHECK();
+  TICK();
+  {
+    const size_t total = (size_t)b.s * dv.C * dv.Q + (size_t)b.s * dv.G + 2 * (size_t)dv.Nh;
+    const int gx = (int)std::min<size_t>((total + 255) / 256, 1024);
+    k_mix_state<<<dim3(gx, bt->B), 256, 0, ctx->stream>>>(dv, b);
+    LAUNCH_CHECK();
+  }
+  k_mix_dense<<<dim3(b.ntile * b.ntile, b.s, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b);
+  LAUNCH_CHECK();
+  k_finalize<<<(bt->B + 127) / 128, 128, 0, ctx->stream>>>(dv, b);
+  LAUNCH_CHECK();
+  TICK();
+#undef TICK
+  return AKS_OK;
+}
+
+static int fetch_records(aks_batch* bt, aks_iter_record* out) {
+  aks_ctx* ctx = bt->disc->ctx;
+  CK(cudaMemcpyAsync(bt->h_rec, bt->dev.rec, sizeof(aks_iter_record) * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (bt->timers) {
+    for (int i = 0; i < 7; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, bt->ev[i], bt->ev[i + 1]);
+      bt->phase_ms[i] = ms;
+    }
+  }
+  if (out) memcpy(out, bt->h_rec, sizeof(aks_iter_record) * bt->B);
+  return AKS_OK;
+}
+
+extern "C" int aks_scf_step(aks_batch* bt, aks_iter_record* out) {
+  if (!bt) return AKS_EINVAL;
+  int rc = step_launch(bt);
+  if (rc != AKS_OK) return rc;
+  return fetch_records(bt, out);
+}
+
+extern "C" int aks_scf_run(aks_batch* bt, int32_t maxiter, aks_iter_record* history, aks_iter_record* final_records) {
+  if (!bt || maxiter < 1) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  std::vector<aks_iter_record> last(bt->B);
+  // records persist on the device between steps; start from the current ones
+  int rc = fetch_records(bt, last.data());
+  if (rc != AKS_OK) return rc;
+  bool any_error = false;
+  for (int it = 0; it < maxiter; ++it) {
+    if ((rc = step_launch(bt)) != AKS_OK) return rc;
+    if ((rc = fetch_records(bt, nullptr)) != AKS_OK) return rc;
+    bool running = false;
+    for (int i = 0; i < bt->B; ++i) {
+      // a problem that was not running this step keeps its old record
+      const aks_iter_record& r = bt->h_rec[i];
+      if (r.niter != last[i].niter || r.status != last[i].status) last[i] = r;
+      if (history) history[(size_t)it * bt->B + i] = last[i];
+      if (last[i].status == AKS_RUNNING) running = true;
+      if (last[i].status < 0) any_error = true;
+    }
+    if (!running) break;
+  }
+  // problems still running have exhausted maxiter
+  std::vector<int> st(bt->B);
+  CK(cudaMemcpyAsync(st.data(), bt->dev.status, sizeof(int) * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  bool notconv = false;
+  for (int i = 0; i < bt->B; ++i)
+    if (st[i] == AKS_RUNNING) { st[i] = AKS_MAXITERS; last[i].status = AKS_MAXITERS; notconv = true; }
+  if (notconv) {
+    CK(cudaMemcpyAsync(bt->dev.status, st.data(), sizeof(int) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (final_records) memcpy(final_records, last.data(), sizeof(aks_iter_record) * bt->B);
+  if (any_error) {
+    for (int i = 0; i < bt->B; ++i) if (last[i].status < 0) return last[i].status;
+  }
+  return notconv ? AKS_ENOTCONV : AKS_OK;
+}
+
+extern "C" int aks_last_phase_ms(aks_batch* bt, double out[8]) {
+  if (!bt || !out) return AKS_EINVAL;
+  for (int i = 0; i < 8; ++i) out[i] = bt->phase_ms[i];
+  return bt->timers ? AKS_OK : AKS_EINVAL;
+}
+
+// ------------------------------------------------------------------------------------ state I/O
+extern "C" int aks_get_state(aks_batch* bt, int32_t prob, double* D, double* U, double* eps, double* nocc, double* W) {
+  if (!bt || prob < 0 || prob >= bt->B) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const BatchDev& b = bt->dev;
+  const size_t s = b.s, Nh = dv.Nh, L = b.Lmax, nh = b.nhmax;
+  if (D) CK(cudaMemcpyAsync(D, b.Dd + (size_t)prob * s * Nh * Nh, sizeof(double) * s * Nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  if (U) CK(cudaMemcpyAsync(U, b.U + (size_t)prob * s * L * nh * Nh, sizeof(double) * s * L * nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<double> he(s * L * nh), hn(s * L * nh), hw(Nh);
+  if (eps) CK(cudaMemcpyAsync(he.data(), b.eps + (size_t)prob * s * L * nh, sizeof(double) * s * L * nh, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nocc) CK(cudaMemcpyAsync(hn.data(), b.occ + (size_t)prob * 2 * s * L * nh, sizeof(double) * s * L * nh, cudaMemcpyDeviceToHost, ctx->stream));
+  if (W) CK(cudaMemcpyAsync(hw.data(), b.Wv + (size_t)prob * Nh, sizeof(double) * Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  // device [s][L][nh]  ->  Julia (L, nh[, s]) column-major
+  for (size_t e = 0; e < s; ++e)
+    for (size_t l = 0; l < L; ++l)
+      for (size_t k = 0; k < nh; ++k) {
+        if (eps) eps[l + L * (k + nh * e)] = he[(e * L + l) * nh + k];
+        if (nocc) nocc[l + L * (k + nh * e)] = hn[(e * L + l) * nh + k];
+      }
+  if (W) for (size_t i = 0; i < Nh; ++i) W[i] = hw[i] * bt->hHar[prob];
+  return AKS_OK;
+}
+
+static int launch_state_from_dense(aks_batch* bt, int prob) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const BatchDev& b = bt->dev;
+  switch (bt->disc->nmax_tpl) {
+    case 12: k_cells_from_dense<12><<<dv.C, AKS_NT, bt->smem_dens, ctx->stream>>>(dv, b, prob); break;
+    case 24: k_cells_from_dense<24><<<dv.C, AKS_NT, bt->smem_dens, ctx->stream>>>(dv, b, prob); break;
+    default: k_cells_from_dense<32><<<dv.C, AKS_NT, bt->smem_dens, ctx->stream>>>(dv, b, prob); break;
+  }
+  LAUNCH_CHECK();
+  k_grid_from_dense<<<(dv.G + AKS_NT - 1) / AKS_NT, AKS_NT, 0, ctx->stream>>>(dv, b, prob);
+  LAUNCH_CHECK();
+  return AKS_OK;
+}
+
+extern "C" int aks_set_density(aks_batch* bt, int32_t prob, const double* D, const double* eprev, int32_t niter) {
+  if (!bt || prob < 0 || prob >= bt->B || !D || niter < 0) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  BatchDev& b = bt->dev;
+  const size_t s = b.s, Nh = dv.Nh;
+  CK(cudaMemcpyAsync(b.Dd + (size_t)prob * s * Nh * Nh, D, sizeof(double) * s * Nh * Nh, cudaMemcpyHostToDevice, ctx->stream));
+  double e5[5] = {0, 0, 0, 0, 0};
+  if (eprev) memcpy(e5, eprev, sizeof e5);
+  CK(cudaMemcpyAsync(b.E + (size_t)prob * 5, e5, sizeof e5, cudaMemcpyHostToDevice, ctx->stream));
+  const int zero = 0, nit = niter;
+  CK(cudaMemcpyAsync(b.status + prob, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.degen + prob, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.warm + prob, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.niter + prob, &nit, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  int rc = launch_state_from_dense(bt, prob);
+  if (rc != AKS_OK) return rc;
+  // Poisson solve of slot 0 for this problem only, then commit B, W
+  k_poisson<<<dim3(1, 1), 128, bt->smem_poisson, ctx->stream>>>(dv, b, prob, 1);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(b.Bv + (size_t)prob * Nh, b.B_new + ((size_t)prob * 2) * Nh, sizeof(double) * Nh, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.Wv + (size_t)prob * Nh, b.W_new + ((size_t)prob * 2) * Nh, sizeof(double) * Nh, cudaMemcpyDeviceToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ hooks
+static void assemble_global(const aks_disc* disc, const std::vector<double>& loc, double* out /*Nh x Nh*/) {
+  const DiscDev& dv = disc->dev;
+  const int n = dv.n, Nh = dv.Nh;
+  std::fill(out, out + (size_t)Nh * Nh, 0.0);
+  for (int c = 0; c < dv.C; ++c)
+    for (int a = 0; a < n; ++a) {
+      const int I = disc->l2g[(size_t)c * n + a];
+      if (I < 0) continue;
+      for (int bq = 0; bq < n; ++bq) {
+        const int J = disc->l2g[(size_t)c * n + bq];
+        if (J < 0) continue;
+        out[(size_t)I + (size_t)Nh * J] += loc[((size_t)c * n + a) * n + bq];
+      }
+    }
+}
+
+static int potential_hook(aks_batch* bt, int prob, double* vxc, double* har) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const BatchDev& b = bt->dev;
+  const size_t cn2 = (size_t)dv.C * dv.n * dv.n;
+  double *dvxc = nullptr, *dhar = nullptr;
+  CK(cudaMalloc((void**)&dvxc, sizeof(double) * b.s * cn2));
+  CK(cudaMalloc((void**)&dhar, sizeof(double) * cn2));
+  // run the kernel for this problem only
+  k_potential<<<dim3(dv.C, 1), AKS_NT, bt->smem_pot, ctx->stream>>>(dv, b, dvxc, dhar, prob, 1);
+  LAUNCH_CHECK();
+  std::vector<double> hv(b.s * cn2), hh(cn2);
+  CK(cudaMemcpyAsync(hv.data(), dvxc, sizeof(double) * b.s * cn2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(hh.data(), dhar, sizeof(double) * cn2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dvxc);
+  cudaFree(dhar);
+  if (vxc)
+    for (int e = 0; e < b.s; ++e) {
+      std::vector<double> one(hv.begin() + (size_t)e * cn2, hv.begin() + (size_t)(e + 1) * cn2);
+      assemble_global(bt->disc, one, vxc + (size_t)e * dv.Nh * dv.Nh);
+    }
+  if (har) assemble_global(bt->disc, hh, har);
+  return AKS_OK;
+}
+
+extern "C" int aks_assemble_hartree(aks_batch* bt, int32_t prob, double* Har) {
+  if (!bt || prob < 0 || prob >= bt->B || !Har) return AKS_EINVAL;
+  return potential_hook(bt, prob, nullptr, Har);
+}
+extern "C" int aks_assemble_vxc(aks_batch* bt, int32_t prob, double* Vxc) {
+  if (!bt || prob < 0 || prob >= bt->B || !Vxc) return AKS_EINVAL;
+  return potential_hook(bt, prob, Vxc, nullptr);
+}
+
+extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* U, double* residuals) {
+  if (!bt || prob < 0 || prob >= bt->B) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const BatchDev& b = bt->dev;
+  int rc;
+  if ((rc = launch_potential(bt, nullptr, nullptr)) != AKS_OK) return rc;
+  if ((rc = launch_eig(bt)) != AKS_OK) return rc;
+  const size_t s = b.s, L = b.Lmax, nh = b.nhmax, Nh = dv.Nh;
+  std::vector<double> he(s * L * nh), hr(s * L * nh, 0.0);
+  CK(cudaMemcpyAsync(he.data(), b.eps_new + (size_t)prob * s * L * nh, sizeof(double) * s * L * nh, cudaMemcpyDeviceToHost, ctx->stream));
+  if (U) CK(cudaMemcpyAsync(U, b.U + (size_t)prob * s * L * nh * Nh, sizeof(double) * s * L * nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  if (residuals) {
+    double* dres = nullptr;
+    CK(cudaMalloc((void**)&dres, sizeof(double) * s * L * nh));
+    CK(cudaMemsetAsync(dres, 0, sizeof(double) * s * L * nh, ctx->stream));
+    k_eig_residual<<<dim3(nh, L * s), AKS_NT, bt->smem_eig, ctx->stream>>>(dv, b, prob, dres);
+    LAUNCH_CHECK();
+    CK(cudaMemcpyAsync(hr.data(), dres, sizeof(double) * s * L * nh, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dres);
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t e = 0; e < s; ++e)
+    for (size_t l = 0; l < L; ++l)
+      for (size_t k = 0; k < nh; ++k) {
+        if (eps) eps[l + L * (k + nh * e)] = he[(e * L + l) * nh + k];
+        if (residuals) residuals[l + L * (k + nh * e)] = hr[(e * L + l) * nh + k];
+      }
+  return AKS_OK;
+}
+
+extern "C" int aks_exc_energy(aks_batch* bt, int32_t prob, double* Exc) {
+  if (!bt || prob < 0 || prob >= bt->B || !Exc) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  double* dout = nullptr;
+  CK(cudaMalloc((void**)&dout, sizeof(double)));
+  k_exc_state<<<1, AKS_NT, 0, ctx->stream>>>(bt->disc->dev, bt->dev, prob, dout);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(Exc, dout, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dout);
+  return AKS_OK;
+}
+
+extern "C" int aks_hartree_energy(aks_batch* bt, int32_t prob, double* Ehar) {
+  if (!bt || prob < 0 || prob >= bt->B || !Ehar) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  if (bt->hHar[prob] == 0.0) { *Ehar = 0.0; return AKS_OK; }
+  std::vector<double> hb(dv.Nh), hw(dv.Nh);
+  CK(cudaMemcpyAsync(hb.data(), bt->dev.Bv + (size_t)prob * dv.Nh, sizeof(double) * dv.Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(hw.data(), bt->dev.Wv + (size_t)prob * dv.Nh, sizeof(double) * dv.Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  double acc = 0.0;
+  for (int i = 0; i < dv.Nh; ++i) acc += hb[i] * hw[i];
+  *Ehar = (acc + bt->hN[prob] * bt->hN[prob] / dv.Rmax) / 2.0;
+  return AKS_OK;
+}
+
+// ------------------------------------------------------------------------------------ FP64 peak
+extern "C" int aks_measure_fp64_peak(aks_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return AKS_EINVAL;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double* dout = nullptr;
+  CK(cudaMalloc((void**)&dout, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0, ctx->stream));
+    k_fp64_peak<<<blocks, threads, 0, ctx->stream>>>(dout, iters);
+    LAUNCH_CHECK();
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dout);
+  *tflops = best;
+  return AKS_OK;
+}

@@ -1,0 +1,94 @@
+// Device-side views of a discretization and of a batch of problems.
+//
+// Data layout in HBM (DESIGN.md "layout"): every operator is kept UNASSEMBLED, one
+// (p+1)x(p+1) block per cell in generator order (g = 0: right hat 1+x, g = 1: left hat
+// 1-x, g >= 2: bubbles), because every step of the hot path is cell-local.  Global
+// vectors (orbitals U, Poisson rhs/solution) use the reference numbering
+// (src/fem/generators.jl:79-138) and are reached through `l2g`.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/aks_b200.h"
+
+struct DiscDev {
+  int p, n, nb, npk, C, Nh, Q, Qs, G, L, nh, nspin;
+  double Rmax;
+  const double* Pg;      // [n][Qs]   generator g at Gauss node q (row stride Qs)
+  const double* w;       // [Q]
+  const double* x;       // [Q]   Gauss nodes on [-1,1]
+  const double* inv1;    // [C]  h/2
+  const double* inv2;    // [C]  midpoint
+  const double* A_loc;   // [C][n][n]
+  const double* M0_loc;  // [C][n][n]
+  const double* Mm1_loc; // [C][n][n]
+  const double* Mm2_loc; // [C][n][n]
+  const double* M0pk;    // [C][npk]  packed (hh | hb | bb lower), see pk_index()
+  const double* F_loc;   // [C][n (m)][n*n (ij)], symmetric in ij
+  const int* l2g;        // [C][n]   global index or -1
+  const double* y;       // [G]
+  const double* wy;      // [G]
+  const int* ycell;      // [G]   0-based cell
+  const double* Pgy;     // [n][G]
+  // prefactored radial Poisson operator (stiffness A): static condensation
+  const double* Abb_inv; // [C][nb][nb]  inverse of the bubble block
+  const double* XA;      // [C][2][nb]   A_bb^{-1} A_bh
+  const double* triA_d;  // [C-1] LDL^T of the hat Schur complement
+  const double* triA_l;  // [C-1]
+};
+
+struct BatchDev {
+  int B, s, Lmax, nhmax;
+  // model parameters
+  const double *Z, *N, *hartree;
+  const int *ex, *ec, *Lp, *nhp;
+  // ODA / aufbau options
+  double scftol, tinit, abstol_ls, reltol_ls, degen_tol;
+  int frozen_t, maxiter_ls, max_degen, handle_spin;
+  // persistent state (mixed density, in every representation the path needs)
+  double* Dd;     // [B][s][Nh][Nh]  dense density matrix (stopping norm, output)
+  double* rho_q;  // [B][s][C][Q]    rho at the Gauss nodes of every cell
+  double* rho_y;  // [B][s][G]       rho on the global energy grid
+  double* Bv;     // [B][Nh]         Hartree rhs  F:D
+  double* Wv;     // [B][Nh]         A^{-1} B
+  double* E;      // [B][5]          Etot,Ekin,Ecou,Ehar,Eexc
+  double* t;      // [B]
+  double* stop;   // [B]
+  int* niter;     // [B]
+  int* status;    // [B]
+  // per-iteration work
+  double* fxc;       // [B][s][C][Q]   w_q * vxc_sigma(rho(q))
+  double* Hpk;       // [B][s][Lmax][C][npk]
+  double* eps;       // [B][s][Lmax][nhmax]
+  double* eps_new;   // [B][s][Lmax][nhmax]  written by k_eig, committed by k_aufbau
+  double* U;         // [B][s][Lmax][nhmax][Nh]
+  int* eig_info;     // [B][s][Lmax][nhmax]  (counts<<8 | rqi its) diagnostics
+  int* warm;         // [B]  1 once eps/U hold a previous solution
+  double* ekin_orb;  // [B][s][Lmax][nhmax]
+  double* ecou_orb;  // [B][s][Lmax][nhmax]
+  double* occ;       // [B][2][s][Lmax][nhmax]  slot 0: final / first extreme, slot 1: second extreme
+  int* degen;        // [B]  1 when the two-fold branch is active this iteration
+  int* degen_idx;    // [B][2]  orbital offsets (into [s][Lmax][nhmax]) of the block
+  double* degen_n;   // [B][4]  n1_0, n2_0, n1_1, n2_1
+  double* rho_q_new; // [B][2][s][C][Q]
+  double* rho_y_new; // [B][2][s][G]
+  double* corr_part; // [B][2][C]
+  double* Bloc_new;  // [B][2][C][n]
+  double* B_new;     // [B][2][Nh]
+  double* W_new;     // [B][2][Nh]
+  double* scal;      // [B][2][4]   B.W self, Bprev.W, -, -
+  double* td;        // [B]  weight of slot 0 in the trial density (1 if not degenerate)
+  double* tmix;      // [B]  ODA t of this step
+  double* norm_part; // [B][ntile_total]
+  int ntile;         // tiles per spin side (ceil(Nh/32))
+  aks_iter_record* rec; // [B]
+  double* Enew;      // [B][5] energies of the trial density (before mixing)
+};
+
+// packed index of local pair (i >= j), generator order
+__host__ __device__ inline int pk_index(int i, int j, int nb) {
+  if (i < 2) return (i == 0) ? 0 : (j == 0 ? 1 : 2);
+  const int a = i - 2;
+  if (j < 2) return 3 + j * nb + a;
+  const int bj = j - 2;
+  return 3 + 2 * nb + a * (a + 1) / 2 + bj;
+}

@@ -1,0 +1,153 @@
+// Auxiliary kernels: state from a dense density matrix (restart / "identical input D"
+// parity hooks), eigen-residuals, Exc of the current state, FP64 peak probe.
+#pragma once
+#include "aks_device.cuh"
+#include "aks_types.cuh"
+#include "k_eig.cuh"
+#include "k_scf.cuh"
+
+// rho at the Gauss nodes of cell c and the cell's share of B = F:D from a DENSE D:
+//   rho_sigma(r_q) = (g_q^T D_loc g_q) / r_q^2 / (4 pi)     (optimized_eval_density!,
+//   src/discretization/assemble.jl:91-125, in factored form)
+template <int NMAX>
+__global__ void __launch_bounds__(AKS_NT) k_cells_from_dense(DiscDev d, BatchDev b, int p) {
+  const int c = blockIdx.x;
+  extern __shared__ double sm[];
+  const int n = d.n, Q = d.Q, C = d.C, s = b.s, Nh = d.Nh;
+  double* Dl = sm;  // [s][n*n]
+  for (int idx = threadIdx.x; idx < s * n * n; idx += AKS_NT) {
+    const int e = idx / (n * n), r = idx - e * n * n, i = r / n, j = r - i * n;
+    const int gi = d.l2g[c * n + i], gj = d.l2g[c * n + j];
+    Dl[idx] = (gi >= 0 && gj >= 0) ? b.Dd[((size_t)p * s + e) * Nh * Nh + (size_t)gi * Nh + gj] : 0.0;
+  }
+  __syncthreads();
+  const double inv1 = d.inv1[c], inv2 = d.inv2[c];
+  for (int q = threadIdx.x; q < Q; q += AKS_NT) {
+    double g[NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) g[i] = (i < n) ? d.Pg[(size_t)i * d.Qs + q] : 0.0;
+    const double X = inv1 * d.x[q] + inv2;
+    for (int e = 0; e < s; ++e) {
+      double acc = 0.0;
+      for (int j = 0; j < n; ++j) {
+        double col = 0.0;
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i)
+          if (i < n) col = fma(Dl[e * n * n + i * n + j], g[i], col);
+        // g[j] with a runtime index: read it back from global (L1 hit)
+        acc = fma(col, d.Pg[(size_t)j * d.Qs + q], acc);
+      }
+      b.rho_q[((size_t)(p * s + e) * C + c) * Q + q] = (acc / (X * X)) * c_xc.inv4pi;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* Fc = d.F_loc + (size_t)c * n * n * n;
+  for (int m = warp; m < n; m += AKS_NW) {
+    double acc = 0.0;
+    for (int idx = lane; idx < n * n; idx += 32) {
+      double dsum = Dl[idx];
+      if (s == 2) dsum += Dl[n * n + idx];
+      acc = fma(dsum, Fc[(size_t)m * n * n + idx], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) b.Bloc_new[(((size_t)p * 2 + 0) * C + c) * n + m] = acc;
+  }
+}
+
+// rho on the global energy grid from a DENSE D (eval_density!, density.jl:97-126)
+__global__ void __launch_bounds__(AKS_NT) k_grid_from_dense(DiscDev d, BatchDev b, int p) {
+  const int q = blockIdx.x * AKS_NT + threadIdx.x;
+  if (q >= d.G) return;
+  const int n = d.n, c = d.ycell[q], s = b.s, Nh = d.Nh;
+  const double yq = d.y[q];
+  for (int e = 0; e < s; ++e) {
+    const double* D = b.Dd + ((size_t)p * s + e) * Nh * Nh;
+    double acc = 0.0;
+    for (int a = 0; a < n; ++a) {
+      const int ga = d.l2g[c * n + a];
+      if (ga < 0) continue;
+      const double ea = d.Pgy[(size_t)a * d.G + q];
+      for (int bb = 0; bb < n; ++bb) {
+        const int gb = d.l2g[c * n + bb];
+        if (gb < 0) continue;
+        acc += ea * D[(size_t)ga * Nh + gb] * d.Pgy[(size_t)bb * d.G + q];
+      }
+    }
+    b.rho_y[((size_t)p * s + e) * d.G + q] = acc / (c_xc.fourpi * (yq * yq));
+  }
+}
+
+// Exc of the current (mixed) state of problem p -> out[0]
+__global__ void __launch_bounds__(AKS_NT) k_exc_state(DiscDev d, BatchDev b, int p, double* out) {
+  __shared__ double red[AKS_NW + 2];
+  const bool has_xc = (b.ex[p] != 0) || (b.ec[p] != 0);
+  const double v = has_xc ? exc_grid(d, b, p, 0.0, 0.0, 1.0, false, red) : 0.0;
+  if (threadIdx.x == 0) out[0] = v;
+}
+
+// ||(H - eps M0) u||_2 for every eigenpair of problem p (diagnostic of aks_eig_lowest)
+__global__ void __launch_bounds__(AKS_NT) k_eig_residual(DiscDev d, BatchDev b, int p, double* out) {
+  const int k = blockIdx.x, ch = blockIdx.y;
+  const int e = ch / b.Lmax, l = ch - e * b.Lmax;
+  if (l >= b.Lp[p] || k >= b.nhp[p]) return;
+  extern __shared__ double sm[];
+  const int C = d.C, npk = d.npk, Nh = d.Nh, n = d.n, nb = d.nb;
+  EigShared S;
+  double* ptr = sm;
+  S.fac = nullptr;
+  S.vx = ptr; ptr += Nh;
+  S.vr = ptr; ptr += Nh;
+  S.vy = ptr; ptr += Nh;
+  S.hatpart = ptr; ptr += 2 * C;
+  S.tri_d = ptr; ptr += C;
+  S.tri_l = ptr; ptr += C;
+  S.xh = ptr; ptr += C;
+  S.red = ptr; ptr += AKS_NW + 8;
+  S.negc = (int*)ptr;
+  const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
+  const double* Hpk = b.Hpk + chan * C * npk;
+  const double* u = b.U + (chan * b.nhmax + k) * Nh;
+  const double lam = b.eps_new[chan * b.nhmax + k];
+  for (int i = threadIdx.x; i < Nh; i += blockDim.x) S.vx[i] = u[i];
+  __syncthreads();
+  eig_apply(d, S, d.M0_loc, S.vx, S.vr);  // vr = M u
+  // vy = H u with the packed blocks
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < C; c += AKS_NW) {
+    const int gi = (lane < n) ? d.l2g[c * n + lane] : -1;
+    const double xl = (gi >= 0) ? S.vx[gi] : 0.0;
+    const double* Hc = Hpk + (size_t)c * npk;
+    double r = 0.0;
+    for (int a = 0; a < n; ++a) {
+      const double xa = __shfl_sync(0xffffffffu, xl, a);
+      if (lane < n) {
+        const int hi = (lane >= a) ? lane : a, lo = (lane >= a) ? a : lane;
+        r = fma(Hc[pk_index(hi, lo, nb)], xa, r);
+      }
+    }
+    if (lane >= 2 && gi >= 0) S.vy[gi] = r;
+    if (lane < 2) S.hatpart[2 * c + lane] = r;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < C - 1; j += blockDim.x)
+    S.vy[d.l2g[j * n + 0]] = S.hatpart[2 * j] + S.hatpart[2 * (j + 1) + 1];
+  __syncthreads();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < Nh; i += blockDim.x) {
+    const double r = S.vy[i] - lam * S.vr[i];
+    acc = fma(r, r, acc);
+  }
+  acc = block_sum(acc, S.red);
+  if (threadIdx.x == 0) out[(size_t)ch * b.nhmax + k] = sqrt(acc);
+}
+
+// FP64 FMA throughput probe: 8 independent register chains per thread
+__global__ void k_fp64_peak(double* out, int iters) {
+  double a0 = 1.0 + threadIdx.x * 1e-9, a1 = 1.1, a2 = 1.2, a3 = 1.3, a4 = 1.4, a5 = 1.5, a6 = 1.6, a7 = 1.7;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}

@@ -1,0 +1,218 @@
+// k_potential: density-dependent potential blocks of one (problem, cell).
+//
+// Replaces, for all spins at once,
+//   assemble_exc!  (src/discretization/assemble.jl:277-319) with its per-cell body
+//                  fill_local_matrix!(K, ::GaussLegendre, ::FunWeight, ...)
+//                  (src/fem/local matrix.jl:129-155) and evaluate_vrho!
+//                  (src/physics/models.jl:97-105),
+//   the F.W contraction + N/Rmax M0 shift of assemble_hartree! (assemble.jl:78-81),
+//   assemble_hamiltonian! (assemble.jl:334-358): H_l = Hfix_l + Vxc + Hartree.
+//
+// The XC block is the factored contraction K = B^T diag(w v) B with B = generator values at
+// the Gauss nodes (north star), not the reference's Qgenx mat-vec: rho at the nodes is part of
+// the device state (it mixes linearly with D), so only the second GEMM-like half remains:
+//   K[i][j] = inv1 * sum_q g_i(q) (w_q v(rho_q)) g_j(q)          2 n^2 Q flop per cell and spin.
+// One warp owns a q-slice; each lane owns 3x3 register tiles of the symmetric K (upper tile
+// triangle only), generator values are staged per 256-node chunk in shared memory with a row
+// stride = 1 (mod 16) doubles so that the 7 distinct rows a warp touches hit distinct banks.
+#pragma once
+#include "aks_device.cuh"
+#include "aks_types.cuh"
+
+#define POT_QC 256
+#define POT_QCS 257
+
+__host__ __device__ inline size_t potential_smem_bytes(int n, int Q, int s) {
+  const int T = (n + 2) / 3, n3 = 3 * T;
+  const int Qpad = ((Q + POT_QC - 1) / POT_QC) * POT_QC;
+  return sizeof(double) * ((size_t)s * Qpad + (size_t)n3 * POT_QCS + (size_t)AKS_NW * n3 * n3 +
+                           (size_t)(s + 1) * n * n + n + 8);
+}
+
+__global__ void __launch_bounds__(AKS_NT)
+k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __restrict__ har_loc_out,
+            int p0, int force) {
+  const int c = blockIdx.x, p = blockIdx.y + p0;
+  if (!force && b.status[p] != 0) return;
+  extern __shared__ double sm[];
+  const int n = d.n, nb = d.nb, Q = d.Q, s = b.s, C = d.C;
+  const int T = (n + 2) / 3, n3 = 3 * T, ntile = T * (T + 1) / 2;
+  const int Qpad = ((Q + POT_QC - 1) / POT_QC) * POT_QC;
+  double* fs = sm;                           // [s][Qpad]
+  double* Gs = fs + (size_t)s * Qpad;        // [n3][POT_QCS]
+  double* Kp = Gs + (size_t)n3 * POT_QCS;    // [NW][n3*n3]
+  double* Ks = Kp + (size_t)AKS_NW * n3 * n3;  // [s][n*n]   XC block per spin
+  double* Hs = Ks + (size_t)s * n * n;       // [n*n]      Hartree block
+  double* wl = Hs + n * n;                   // [n]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ex = b.ex[p], ec = b.ec[p];
+  const bool has_xc = (ex != 0) || (ec != 0);
+  const double inv1 = d.inv1[c];
+
+  // ---- 1. pointwise XC potential at the Gauss nodes: f_sigma[q] = w_q v_sigma(rho(q))
+  if (has_xc) {
+    const double* r0 = b.rho_q + ((size_t)(p * s + 0) * C + c) * Q;
+    const double* r1 = (s == 2) ? b.rho_q + ((size_t)(p * s + 1) * C + c) * Q : nullptr;
+    double* fo0 = b.fxc + ((size_t)(p * s + 0) * C + c) * Q;
+    double* fo1 = (s == 2) ? b.fxc + ((size_t)(p * s + 1) * C + c) * Q : nullptr;
+    for (int q = tid; q < Qpad; q += AKS_NT) {
+      double f0 = 0.0, f1 = 0.0;
+      if (q < Q) {
+        const double wq = d.w[q];
+        if (s == 1) {
+          f0 = xc_vrho_unpol(fmax(r0[q], 0.0), ex, ec) * wq;
+          fo0[q] = f0;
+        } else {
+          double vu, vd;
+          xc_vrho_pol(fmax(r0[q], 0.0), fmax(r1[q], 0.0), ex, ec, vu, vd);
+          f0 = vu * wq;
+          f1 = vd * wq;
+          fo0[q] = f0;
+          fo1[q] = f1;
+        }
+      }
+      fs[q] = f0;
+      if (s == 2) fs[Qpad + q] = f1;
+    }
+  }
+
+  // ---- 2. K_sigma = sum_q f_sigma[q] g g^T, 3x3 register tiles
+  int ti[2], tj[2];
+  for (int ts = 0; ts < 2; ++ts) {
+    int tile = lane + 32 * ts;
+    ti[ts] = -1;
+    tj[ts] = -1;
+    if (tile < ntile) {
+      int a = 0, rem = tile;
+      while (rem >= T - a) { rem -= (T - a); ++a; }  // row a holds tiles (a, a..T-1)
+      ti[ts] = a;
+      tj[ts] = a + rem;
+    }
+  }
+  double acc[2][2][9];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[a][e][k] = 0.0;
+
+  if (has_xc) {
+    for (int q0 = 0; q0 < Qpad; q0 += POT_QC) {
+      __syncthreads();
+      for (int idx = tid; idx < n3 * POT_QC; idx += AKS_NT) {
+        const int g = idx / POT_QC, j = idx - g * POT_QC;
+        double v = 0.0;
+        if (g < n && q0 + j < Q) v = d.Pg[(size_t)g * d.Qs + q0 + j];
+        Gs[g * POT_QCS + j] = v;
+      }
+      __syncthreads();
+      const int jq0 = warp * (POT_QC / AKS_NW);
+      for (int jq = jq0; jq < jq0 + POT_QC / AKS_NW; ++jq) {
+#pragma unroll
+        for (int ts = 0; ts < 2; ++ts) {
+          if (ti[ts] < 0) continue;
+          const double* gi = Gs + (3 * ti[ts]) * POT_QCS + jq;
+          const double* gj = Gs + (3 * tj[ts]) * POT_QCS + jq;
+          const double a0 = gi[0], a1 = gi[POT_QCS], a2 = gi[2 * POT_QCS];
+          const double b0 = gj[0], b1 = gj[POT_QCS], b2 = gj[2 * POT_QCS];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (e >= s) break;
+            const double fq = fs[e * Qpad + q0 + jq];
+            const double t0 = fq * b0, t1 = fq * b1, t2 = fq * b2;
+            double* A = acc[ts][e];
+            A[0] = fma(a0, t0, A[0]); A[1] = fma(a0, t1, A[1]); A[2] = fma(a0, t2, A[2]);
+            A[3] = fma(a1, t0, A[3]); A[4] = fma(a1, t1, A[4]); A[5] = fma(a1, t2, A[5]);
+            A[6] = fma(a2, t0, A[6]); A[7] = fma(a2, t1, A[7]); A[8] = fma(a2, t2, A[8]);
+          }
+        }
+      }
+    }
+  }
+  // cross-warp reduction, fixed order; symmetrise diagonal tiles; scale by inv1
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (e >= s) break;
+    __syncthreads();
+    if (has_xc) {
+#pragma unroll
+      for (int ts = 0; ts < 2; ++ts) {
+        if (ti[ts] < 0) continue;
+        double* K = Kp + (size_t)warp * n3 * n3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 3; ++bb)
+            K[(3 * ti[ts] + a) * n3 + 3 * tj[ts] + bb] = acc[ts][e][3 * a + bb];
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += AKS_NT) {
+      const int i = idx / n, j = idx - i * n;
+      double v = 0.0;
+      if (has_xc) {
+        const int ii = (i / 3 <= j / 3) ? i : j, jj = (i / 3 <= j / 3) ? j : i;
+        double s1 = 0.0, s2 = 0.0;
+        for (int wv = 0; wv < AKS_NW; ++wv) {
+          s1 += Kp[(size_t)wv * n3 * n3 + ii * n3 + jj];
+          if (i / 3 == j / 3) s2 += Kp[(size_t)wv * n3 * n3 + jj * n3 + ii];
+        }
+        v = (i / 3 == j / 3) ? 0.5 * (s1 + s2) : s1;
+        v *= inv1;
+      }
+      Ks[e * n * n + idx] = v;
+    }
+  }
+
+  // ---- 3. Hartree block: coeff * (sum_m W_m F[ij][m] + N/Rmax M0)
+  const double coeff = b.hartree[p];
+  if (tid < n) {
+    const int gi = d.l2g[c * n + tid];
+    wl[tid] = (gi >= 0 && coeff != 0.0) ? b.Wv[(size_t)p * d.Nh + gi] : 0.0;
+  }
+  __syncthreads();
+  {
+    const double shift = b.N[p] / d.Rmax;
+    const double* Fc = d.F_loc + (size_t)c * n * n * n;
+    const double* M0c = d.M0_loc + (size_t)c * n * n;
+    for (int idx = tid; idx < n * n; idx += AKS_NT) {
+      double v = 0.0;
+      if (coeff != 0.0) {
+        double fw = 0.0;
+        for (int m = 0; m < n; ++m) fw = fma(wl[m], Fc[(size_t)m * n * n + idx], fw);
+        v = (fw + shift * M0c[idx]) * coeff;
+      }
+      Hs[idx] = v;
+    }
+  }
+  __syncthreads();
+
+  // optional local outputs for the step-level hooks
+  if (vxc_loc_out)
+    for (int e = 0; e < s; ++e)
+      for (int idx = tid; idx < n * n; idx += AKS_NT)
+        vxc_loc_out[((size_t)e * C + c) * n * n + idx] = Ks[e * n * n + idx];
+  if (har_loc_out)
+    for (int idx = tid; idx < n * n; idx += AKS_NT) har_loc_out[(size_t)c * n * n + idx] = Hs[idx];
+
+  // ---- 4. H_l = (Kin_l + Coulomb) + Vxc + Hartree, packed per (sigma, l, cell)
+  const double Zp = b.Z[p];
+  const int Lp = b.Lp[p];
+  const double* Ac = d.A_loc + (size_t)c * n * n;
+  const double* M1c = d.Mm1_loc + (size_t)c * n * n;
+  const double* M2c = d.Mm2_loc + (size_t)c * n * n;
+  for (int e = 0; e < s; ++e) {
+    for (int l = 0; l < Lp; ++l) {
+      double* out = b.Hpk + ((((size_t)p * s + e) * b.Lmax + l) * C + c) * d.npk;
+      const double ll = (double)(l * (l + 1));
+      for (int idx = tid; idx < n * n; idx += AKS_NT) {
+        const int i = idx / n, j = idx - i * n;
+        if (j > i) continue;
+        const double kin = (Ac[idx] + ll * M2c[idx]) / 2.0;
+        const double cou = -Zp * M1c[idx];
+        out[pk_index(i, j, nb)] = ((kin + cou) + Ks[e * n * n + idx]) + Hs[idx];
+      }
+    }
+  }
+}

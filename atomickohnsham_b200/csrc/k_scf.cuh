@@ -1,0 +1,669 @@
+// Remaining kernels of one SCF step: aufbau, orbital energies, trial density in every
+// representation the path needs, radial Poisson solve, energies + ODA line search, mixing
+// and the stopping rule.  Reference functions replaced are cited per kernel.
+#pragma once
+#include "aks_device.cuh"
+#include "aks_types.cuh"
+
+__device__ __forceinline__ size_t orb_off(const BatchDev& b, int p, int e, int l, int k) {
+  return (((size_t)p * b.s + e) * b.Lmax + l) * b.nhmax + k;
+}
+__device__ __forceinline__ size_t occ_off(const BatchDev& b, int p, int slot, int e, int l, int k) {
+  return ((((size_t)p * 2 + slot) * b.s + e) * b.Lmax + l) * b.nhmax + k;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_aufbau: aufbau!(n, eps, ..., ::OptimizedAufbauCache, niter)  (src/algorithms/aufbau/
+// optimized.jl:99-222) -- stable sort of all eps, greedy filling by blocks of <= max_degen
+// levels within `tol` of the block head; a partially filled two-fold block only records the
+// two extreme fillings here (slot 0 / slot 1), the energy minimisation between them
+// (optimized.jl:228-306) happens in k_linesearch.  One thread per problem.
+__global__ void k_aufbau(DiscDev d, BatchDev b) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= b.B || b.status[p] != 0) return;
+  const int Lp = b.Lp[p], nhp = b.nhp[p], s = b.s;
+  const int norb = Lp * nhp * s;
+  double ev[AKS_MAXORB];
+  int ord[AKS_MAXORB];
+  // flat index f = l + Lp*k + Lp*nhp*e  (convert_index, discretization.jl:379-392)
+  for (int f = 0; f < norb; ++f) {
+    const int e = f / (Lp * nhp), r = f - e * Lp * nhp, k = r / Lp, l = r - k * Lp;
+    const double v = b.eps_new[orb_off(b, p, e, l, k)];
+    b.eps[orb_off(b, p, e, l, k)] = v;
+    ev[f] = v;
+    ord[f] = f;
+  }
+  for (int i = 1; i < norb; ++i) {  // stable insertion sort (sortperm!)
+    const int oi = ord[i];
+    const double vi = ev[oi];
+    int j = i - 1;
+    while (j >= 0 && ev[ord[j]] > vi) { ord[j + 1] = ord[j]; --j; }
+    ord[j + 1] = oi;
+  }
+  for (int slot = 0; slot < 2; ++slot)
+    for (int e = 0; e < s; ++e)
+      for (int l = 0; l < b.Lmax; ++l)
+        for (int k = 0; k < b.nhmax; ++k) b.occ[occ_off(b, p, slot, e, l, k)] = 0.0;
+  double Nleft = b.N[p];
+  const int niter = b.niter[p];
+  int i = 0, degen = 0;
+  int blk[8];
+  const int maxd = b.max_degen < 8 ? b.max_degen : 8;
+  while (Nleft > 0.0 && i < norb) {
+    blk[0] = ord[i];
+    int nbd = 1;
+    const double e0 = ev[blk[0]];
+    int j = i + 1;
+    while (j < norb && fabs(ev[ord[j]] - e0) < b.degen_tol && nbd < maxd) { blk[nbd++] = ord[j]; ++j; }
+    i += nbd;
+    int degs[8], tot = 0, ee[8], ll[8], kk[8];
+    for (int m = 0; m < nbd; ++m) {
+      const int f = blk[m];
+      ee[m] = f / (Lp * nhp);
+      const int r = f - ee[m] * Lp * nhp;
+      kk[m] = r / Lp;
+      ll[m] = r - kk[m] * Lp;
+      degs[m] = (s == 1) ? 4 * ll[m] + 2 : 2 * ll[m] + 1;
+      tot += degs[m];
+    }
+    if (Nleft >= (double)tot) {
+      for (int m = 0; m < nbd; ++m) {
+        b.occ[occ_off(b, p, 0, ee[m], ll[m], kk[m])] = (double)degs[m];
+        b.occ[occ_off(b, p, 1, ee[m], ll[m], kk[m])] = (double)degs[m];
+      }
+      Nleft -= (double)tot;
+    } else if (nbd == 1) {
+      b.occ[occ_off(b, p, 0, ee[0], ll[0], kk[0])] = Nleft;
+      break;
+    } else if (nbd == 2) {
+      if (b.handle_spin && niter == 0 && ll[0] == ll[1] && kk[0] == kk[1] && ee[0] != ee[1]) {
+        b.occ[occ_off(b, p, 0, ee[0], ll[0], kk[0])] = Nleft / 2.0;
+        b.occ[occ_off(b, p, 0, ee[1], ll[1], kk[1])] = Nleft / 2.0;
+        break;
+      }
+      degen = 1;
+      const double n10 = ((double)degs[0] >= Nleft) ? Nleft : (double)degs[0];
+      const double n20 = Nleft - n10;
+      const double n21 = ((double)degs[1] >= Nleft) ? Nleft : (double)degs[1];
+      const double n11 = Nleft - n21;
+      b.occ[occ_off(b, p, 0, ee[0], ll[0], kk[0])] = n10;
+      b.occ[occ_off(b, p, 0, ee[1], ll[1], kk[1])] = n20;
+      b.occ[occ_off(b, p, 1, ee[0], ll[0], kk[0])] = n11;
+      b.occ[occ_off(b, p, 1, ee[1], ll[1], kk[1])] = n21;
+      b.degen_idx[2 * p] = (ee[0] * b.Lmax + ll[0]) * b.nhmax + kk[0];
+      b.degen_idx[2 * p + 1] = (ee[1] * b.Lmax + ll[1]) * b.nhmax + kk[1];
+      b.degen_n[4 * p] = n10; b.degen_n[4 * p + 1] = n20;
+      b.degen_n[4 * p + 2] = n11; b.degen_n[4 * p + 3] = n21;
+      break;
+    } else {
+      b.status[p] = AKS_EDEGEN3;
+      break;
+    }
+  }
+  b.degen[p] = degen;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_orb_energy: u^T Kin_l u and u^T Coulomb u per occupied orbital
+// (compute_kinetic_energy / compute_coulomb_energy, src/discretization/energies.jl:47-87).
+// One warp per orbital, unassembled operators.
+__global__ void k_orb_energy(DiscDev d, BatchDev b) {
+  const int p = blockIdx.y;
+  if (b.status[p] != 0) return;
+  const int o = blockIdx.x;  // (e*Lmax + l)*nhmax + k
+  const int k = o % b.nhmax, l = (o / b.nhmax) % b.Lmax, e = o / (b.nhmax * b.Lmax);
+  if (l >= b.Lp[p] || k >= b.nhp[p]) return;
+  const double n0 = b.occ[occ_off(b, p, 0, e, l, k)], n1 = b.occ[occ_off(b, p, 1, e, l, k)];
+  if (n0 == 0.0 && !(b.degen[p] && n1 != 0.0)) return;
+  const int lane = threadIdx.x, n = d.n, C = d.C;
+  const double* u = b.U + orb_off(b, p, e, l, k) * d.Nh;
+  const double ll = (double)(l * (l + 1));
+  double akin = 0.0, acou = 0.0;
+  for (int c = 0; c < C; ++c) {
+    const int gi = (lane < n) ? d.l2g[c * n + lane] : -1;
+    const double xl = (gi >= 0) ? u[gi] : 0.0;
+    const double* Ar = d.A_loc + ((size_t)c * n + lane) * n;
+    const double* M2r = d.Mm2_loc + ((size_t)c * n + lane) * n;
+    const double* M1r = d.Mm1_loc + ((size_t)c * n + lane) * n;
+    double rk = 0.0, rc = 0.0;
+    for (int a = 0; a < n; ++a) {
+      const double xa = __shfl_sync(0xffffffffu, xl, a);
+      if (lane < n) {
+        rk = fma((Ar[a] + ll * M2r[a]) / 2.0, xa, rk);
+        rc = fma(M1r[a], xa, rc);
+      }
+    }
+    akin = fma(rk, xl, akin);
+    acou = fma(rc, xl, acou);
+  }
+  akin = warp_sum(akin);
+  acou = warp_sum(acou);
+  if (lane == 0) {
+    b.ekin_orb[orb_off(b, p, e, l, k)] = akin;
+    b.ecou_orb[orb_off(b, p, e, l, k)] = -b.Z[p] * acou;
+  }
+}
+
+// occupied-orbital list of (problem, slot) in the reference's density! order (sigma, k, l)
+struct OccList {
+  int count;
+  int e[AKS_MAXORB], l[AKS_MAXORB], k[AKS_MAXORB];
+  double n[AKS_MAXORB];
+};
+__device__ inline void build_occ_list(const BatchDev& b, int p, int slot, OccList* L) {
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    for (int e = 0; e < b.s; ++e)
+      for (int k = 0; k < b.nhp[p]; ++k)
+        for (int l = 0; l < b.Lp[p]; ++l) {
+          const double nn = b.occ[occ_off(b, p, slot, e, l, k)];
+          if (nn != 0.0 && cnt < AKS_MAXORB) { L->e[cnt] = e; L->l[cnt] = l; L->k[cnt] = k; L->n[cnt] = nn; ++cnt; }
+        }
+    L->count = cnt;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// k_dens_cells: trial density of one (cell, problem, slot) straight from the orbitals:
+//   rho_sigma(r_q) = sum_k n_k (sum_i u_ik g_i(q))^2 / r_q^2 / (4 pi)
+// (what optimized_eval_density!, assemble.jl:91-125, yields for D = sum n u u^T), the energy
+// correction <Vxc[D_prev], D_new> (energies.jl:15-24) as sum_q fxc(q) q_new(q), and the cell's
+// share of the Hartree rhs B = F:D (tensor_matrix_dict!, src/utils/free allocation.jl:17-36).
+template <int NMAX>
+__global__ void __launch_bounds__(AKS_NT) k_dens_cells(DiscDev d, BatchDev b) {
+  const int c = blockIdx.x, p = blockIdx.y, slot = blockIdx.z;
+  if (b.status[p] != 0) return;
+  if (slot == 1 && !b.degen[p]) return;
+  __shared__ OccList L;
+  extern __shared__ double sm[];
+  const int n = d.n, Q = d.Q, C = d.C, s = b.s;
+  double* us = sm;                              // [count][NMAX]
+  double* Dl = us + (size_t)AKS_MAXORB * NMAX;  // [n*n]
+  double* red = Dl + n * n;                     // [NW]
+  build_occ_list(b, p, slot, &L);
+  const int cnt = L.count;
+  for (int idx = threadIdx.x; idx < cnt * NMAX; idx += AKS_NT) {
+    const int o = idx / NMAX, i = idx - o * NMAX;
+    double v = 0.0;
+    if (i < n) {
+      const int gi = d.l2g[c * n + i];
+      if (gi >= 0) v = b.U[orb_off(b, p, L.e[o], L.l[o], L.k[o]) * d.Nh + gi];
+    }
+    us[idx] = v;
+  }
+  __syncthreads();
+  const double inv1 = d.inv1[c], inv2 = d.inv2[c];
+  const bool has_xc = (b.ex[p] != 0) || (b.ec[p] != 0);
+  double corr = 0.0;
+  for (int q = threadIdx.x; q < Q; q += AKS_NT) {
+    double g[NMAX];
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i) g[i] = (i < n) ? d.Pg[(size_t)i * d.Qs + q] : 0.0;
+    double r0 = 0.0, r1 = 0.0;
+    for (int o = 0; o < cnt; ++o) {
+      const double* uo = us + (size_t)o * NMAX;
+      double psi = 0.0;
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) psi = fma(uo[i], g[i], psi);
+      const double t = L.n[o] * psi * psi;
+      if (L.e[o] == 0) r0 += t; else r1 += t;
+    }
+    const double X = inv1 * d.x[q] + inv2;
+    double* out0 = b.rho_q_new + ((((size_t)p * 2 + slot) * s + 0) * C + c) * Q;
+    out0[q] = (r0 / (X * X)) * c_xc.inv4pi;
+    if (has_xc) corr = fma(b.fxc[((size_t)(p * s + 0) * C + c) * Q + q], r0, corr);
+    if (s == 2) {
+      double* out1 = b.rho_q_new + ((((size_t)p * 2 + slot) * s + 1) * C + c) * Q;
+      out1[q] = (r1 / (X * X)) * c_xc.inv4pi;
+      if (has_xc) corr = fma(b.fxc[((size_t)(p * s + 1) * C + c) * Q + q], r1, corr);
+    }
+  }
+  corr = block_sum(corr, red);
+  if (threadIdx.x == 0) b.corr_part[((size_t)p * 2 + slot) * C + c] = corr * inv1;
+  // local density block (both spins summed) and its contraction with the mass tensor
+  if (b.hartree[p] != 0.0) {
+    for (int idx = threadIdx.x; idx < n * n; idx += AKS_NT) {
+      const int i = idx / n, j = idx - i * n;
+      double v = 0.0;
+      for (int o = 0; o < cnt; ++o) v = fma(L.n[o] * us[(size_t)o * NMAX + i], us[(size_t)o * NMAX + j], v);
+      Dl[idx] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* Fc = d.F_loc + (size_t)c * n * n * n;
+    for (int m = warp; m < n; m += AKS_NW) {
+      double acc = 0.0;
+      for (int idx = lane; idx < n * n; idx += 32) acc = fma(Dl[idx], Fc[(size_t)m * n * n + idx], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) b.Bloc_new[(((size_t)p * 2 + slot) * C + c) * n + m] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_dens_grid: trial density on the global energy grid (eval_density!, density.jl:97-126)
+template <int NMAX>
+__global__ void __launch_bounds__(AKS_NT) k_dens_grid(DiscDev d, BatchDev b) {
+  const int p = blockIdx.y, slot = blockIdx.z;
+  if (b.status[p] != 0) return;
+  if (slot == 1 && !b.degen[p]) return;
+  __shared__ OccList L;
+  build_occ_list(b, p, slot, &L);
+  const int q = blockIdx.x * AKS_NT + threadIdx.x;
+  if (q >= d.G) return;
+  const int n = d.n, c = d.ycell[q], s = b.s;
+  double g[NMAX];
+  int gi[NMAX];
+#pragma unroll
+  for (int i = 0; i < NMAX; ++i) {
+    g[i] = (i < n) ? d.Pgy[(size_t)i * d.G + q] : 0.0;
+    gi[i] = (i < n) ? d.l2g[c * n + i] : -1;
+  }
+  double r0 = 0.0, r1 = 0.0;
+  for (int o = 0; o < L.count; ++o) {
+    const double* u = b.U + orb_off(b, p, L.e[o], L.l[o], L.k[o]) * d.Nh;
+    double psi = 0.0;
+#pragma unroll
+    for (int i = 0; i < NMAX; ++i)
+      if (gi[i] >= 0) psi = fma(u[gi[i]], g[i], psi);
+    const double t = L.n[o] * psi * psi;
+    if (L.e[o] == 0) r0 += t; else r1 += t;
+  }
+  const double yq = d.y[q];
+  const double den = c_xc.fourpi * (yq * yq);
+  b.rho_y_new[(((size_t)p * 2 + slot) * s + 0) * d.G + q] = r0 / den;
+  if (s == 2) b.rho_y_new[(((size_t)p * 2 + slot) * s + 1) * d.G + q] = r1 / den;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_poisson: assemble B = F:D_new from the cell shares and solve A W = B with the prefactored
+// statically condensed stiffness operator (the reference calls CHOLMOD on the sparse A every
+// time: assemble.jl:71,76; energies.jl:105,111,128,137).  Also B.W and B_prev.W.
+__global__ void __launch_bounds__(128) k_poisson(DiscDev d, BatchDev b, int p0, int force) {
+  const int p = blockIdx.x + p0, slot = blockIdx.y;
+  if (!force && b.status[p] != 0) return;
+  if (slot == 1 && !b.degen[p]) return;
+  extern __shared__ double sm[];
+  const int C = d.C, n = d.n, nb = d.nb, Nh = d.Nh;
+  double* Bs = sm;          // [Nh]
+  double* Ws = Bs + Nh;     // [Nh]
+  double* hp = Ws + Nh;     // [2C]
+  double* xh = hp + 2 * C;  // [C]
+  double* red = xh + C;     // [8]
+  double* Bout = b.B_new + ((size_t)p * 2 + slot) * Nh;
+  double* Wout = b.W_new + ((size_t)p * 2 + slot) * Nh;
+  double* sc = b.scal + ((size_t)p * 2 + slot) * 4;
+  if (b.hartree[p] == 0.0) {
+    for (int i = threadIdx.x; i < Nh; i += blockDim.x) { Bout[i] = 0.0; Wout[i] = 0.0; }
+    if (threadIdx.x == 0) { sc[0] = 0.0; sc[1] = 0.0; }
+    return;
+  }
+  const double* Bl = b.Bloc_new + ((size_t)p * 2 + slot) * C * n;
+  for (int idx = threadIdx.x; idx < C * n; idx += blockDim.x) {
+    const int c = idx / n, m = idx - c * n;
+    const int gi = d.l2g[idx];
+    if (gi < 0) continue;
+    if (m >= 2) Bs[gi] = Bl[idx];
+    else if (m == 0) Bs[gi] = Bl[idx] + Bl[(c + 1) * n + 1];  // right hat of c == left hat of c+1
+  }
+  __syncthreads();
+  // hat rhs: rh_j = B[hat j] - XA_j[0].B_b(j) - XA_{j+1}[1].B_b(j+1)
+  for (int idx = threadIdx.x; idx < 2 * C; idx += blockDim.x) {
+    const int c = idx >> 1, g = idx & 1;
+    const double* X = d.XA + ((size_t)c * 2 + g) * nb;
+    double acc = 0.0;
+    for (int i = 0; i < nb; ++i) acc = fma(X[i], Bs[d.l2g[c * n + 2 + i]], acc);
+    hp[idx] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int m = C - 1;
+    double zprev = 0.0;
+    for (int j = 0; j < m; ++j) {
+      double rh = Bs[d.l2g[j * n]] - hp[2 * j] - hp[2 * (j + 1) + 1];
+      if (j > 0) rh -= d.triA_l[j - 1] * zprev;
+      xh[j] = rh;
+      zprev = rh;
+    }
+    double xnext = 0.0;
+    for (int j = m - 1; j >= 0; --j) {
+      double v = xh[j] / d.triA_d[j];
+      if (j < m - 1) v -= d.triA_l[j] * xnext;
+      xh[j] = v;
+      xnext = v;
+      Ws[d.l2g[j * n]] = v;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < C * nb; idx += blockDim.x) {
+    const int c = idx / nb, i = idx - c * nb;
+    const double* Ai = d.Abb_inv + ((size_t)c * nb + i) * nb;
+    double acc = 0.0;
+    for (int j = 0; j < nb; ++j) acc = fma(Ai[j], Bs[d.l2g[c * n + 2 + j]], acc);
+    const double xh0 = (c < C - 1) ? xh[c] : 0.0, xh1 = (c > 0) ? xh[c - 1] : 0.0;
+    acc -= d.XA[((size_t)c * 2 + 0) * nb + i] * xh0 + d.XA[((size_t)c * 2 + 1) * nb + i] * xh1;
+    Ws[d.l2g[c * n + 2 + i]] = acc;
+  }
+  __syncthreads();
+  double bw = 0.0, bpw = 0.0;
+  const double* Bp = b.Bv + (size_t)p * Nh;
+  for (int i = threadIdx.x; i < Nh; i += blockDim.x) {
+    bw = fma(Bs[i], Ws[i], bw);
+    bpw = fma(Bp[i], Ws[i], bpw);
+    Bout[i] = Bs[i];
+    Wout[i] = Ws[i];
+  }
+  bw = block_sum(bw, red);
+  bpw = block_sum(bpw, red);
+  if (threadIdx.x == 0) { sc[0] = bw; sc[1] = bpw; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Exc on the global grid for rho = a*new0 + bq*new1 + cq*prev (compute_exc_energy,
+// energies.jl:217-233 with evaluate_zk!, models.jl:107-116).  rho is linear in D, so the
+// reference's F(t) = Exc[t D + (1-t) D_prev] (oda/types.jl:96-100) costs O(G) per evaluation.
+__device__ double exc_grid(const DiscDev& d, const BatchDev& b, int p, double a, double bq, double cq,
+                           bool use1, double* red) {
+  const int G = d.G, s = b.s;
+  const int ex = b.ex[p], ec = b.ec[p];
+  const double* n0 = b.rho_y_new + (((size_t)p * 2 + 0) * s) * G;
+  const double* n1 = b.rho_y_new + (((size_t)p * 2 + 1) * s) * G;
+  const double* pr = b.rho_y + ((size_t)p * s) * G;
+  double acc = 0.0;
+  for (int q = threadIdx.x; q < G; q += blockDim.x) {
+    double ru = a * n0[q] + cq * pr[q];
+    if (use1) ru += bq * n1[q];
+    double val;
+    if (s == 1) {
+      val = ru * xc_zk_unpol(fmax(ru, 0.0), ex, ec);
+    } else {
+      double rd = a * n0[G + q] + cq * pr[G + q];
+      if (use1) rd += bq * n1[G + q];
+      val = (ru + rd) * xc_zk_pol(fmax(ru, 0.0), fmax(rd, 0.0), ex, ec);
+    }
+    const double yq = d.y[q];
+    acc = fma(d.wy[q], val * (yq * yq), acc);
+  }
+  return c_xc.fourpi * block_sum(acc, red);
+}
+
+// minimise a t^2 + b t + c + F(t) on [0,1] (line_search_energy, line_search.jl:45-80);
+// F(t) = Exc[t*rhoA + (1-t)*rhoB] where (A,B) = (new0,new1) [degenerate aufbau] or
+// (trial, prev) [ODA].  All threads of the CTA call this; returns (tmin, fmin) to all.
+struct LsShared { double t; double f; int go; };
+__device__ void line_search(const DiscDev& d, const BatchDev& b, int p, double qa, double qb, double qc,
+                            bool has_xc, int mode /*0: new0 vs new1, 1: trial(td) vs prev*/, double td,
+                            bool degen, double abstol, double reltol, int maxit, LsShared* ls,
+                            double* red, double& t_out, double& f_out) {
+  if (!has_xc) {
+    double t;
+    if (qa > 0.0) t = fmin(fmax(-qb / (2.0 * qa), 0.0), 1.0);
+    else t = (qc <= qc + qb + qa) ? 0.0 : 1.0;
+    t_out = t;
+    f_out = qc + qb * t + qa * t * t;
+    return;
+  }
+  BrentState st;
+  if (threadIdx.x == 0) { brent_init(st, 0.0, 1.0, abstol, reltol, maxit); ls->t = st.next; ls->go = 1; }
+  __syncthreads();
+  bool first = true;
+  while (true) {
+    const double t = ls->t;
+    double F;
+    if (mode == 0) F = exc_grid(d, b, p, t, 1.0 - t, 0.0, true, red);
+    else F = exc_grid(d, b, p, t * td, t * (1.0 - td), 1.0 - t, degen, red);
+    if (threadIdx.x == 0) {
+      const double fv = qa * (t * t) + qb * t + qc + F;
+      if (first) brent_first(st, fv); else brent_update(st, fv);
+      ls->go = brent_propose(st) ? 1 : 0;
+      ls->t = st.next;
+      if (!ls->go) { ls->t = st.x; ls->f = st.fx; }
+    }
+    first = false;
+    __syncthreads();
+    const int go = ls->go;
+    __syncthreads();
+    if (!go) break;
+  }
+  t_out = ls->t;
+  f_out = ls->f;
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// k_linesearch: energies of the trial density (compute_total_energy & co, energies.jl:7-141),
+// two-fold degeneracy resolution (optimized.jl:228-306) and the ODA line search
+// (line_search_density!, oda/loop.jl:79-116).  One CTA per problem.
+__global__ void __launch_bounds__(AKS_NT) k_linesearch(DiscDev d, BatchDev b) {
+  const int p = blockIdx.x;
+  if (b.status[p] != 0) return;
+  __shared__ double red[AKS_NW + 2];
+  __shared__ LsShared ls;
+  __shared__ double sh[16];
+  const int s = b.s, C = d.C, Nh = d.Nh;
+  const bool has_xc = (b.ex[p] != 0) || (b.ec[p] != 0);
+  const bool har_on = b.hartree[p] != 0.0;
+  const bool degen = b.degen[p] != 0;
+  const double Np = b.N[p], Rmax = d.Rmax;
+  const double n2r = Np * Np / Rmax;
+  const double eps64 = 2.220446049250313e-16;
+  // orbital sums for both slots (thread 0, fixed order sigma, l, k as in energies.jl:52-61)
+  if (threadIdx.x == 0) {
+    for (int slot = 0; slot < 2; ++slot) {
+      double sne = 0.0, ek = 0.0, ecs = 0.0;
+      if (slot == 0 || degen)
+        for (int e = 0; e < s; ++e)
+          for (int l = 0; l < b.Lp[p]; ++l)
+            for (int k = 0; k < b.nhp[p]; ++k) {
+              const double nn = b.occ[occ_off(b, p, slot, e, l, k)];
+              if (nn != 0.0) {
+                sne += nn * b.eps[orb_off(b, p, e, l, k)];
+                ek += nn * b.ekin_orb[orb_off(b, p, e, l, k)];
+                ecs += nn * b.ecou_orb[orb_off(b, p, e, l, k)];
+              }
+            }
+      double corr = 0.0;
+      if (has_xc && (slot == 0 || degen))
+        for (int c = 0; c < C; ++c) corr += b.corr_part[((size_t)p * 2 + slot) * C + c];
+      sh[4 * slot + 0] = sne; sh[4 * slot + 1] = ek; sh[4 * slot + 2] = ecs; sh[4 * slot + 3] = corr;
+    }
+  }
+  __syncthreads();
+  const double* sc0 = b.scal + ((size_t)p * 2 + 0) * 4;
+  const double* sc1 = b.scal + ((size_t)p * 2 + 1) * 4;
+  double Ekin, Ecou, Ehar, Eexc, Etot, td = 1.0;
+  if (degen) {
+    // energies of the two extreme fillings and their Hartree cross term
+    const double k0 = sh[1], c0 = sh[2], k1 = sh[5], c1 = sh[6];
+    const double h0 = har_on ? (sc0[0] + n2r) / 2.0 : 0.0;
+    const double h1 = har_on ? (sc1[0] + n2r) / 2.0 : 0.0;
+    double h01 = 0.0;
+    if (har_on) {
+      const double* B1 = b.B_new + ((size_t)p * 2 + 1) * Nh;
+      const double* W0 = b.W_new + ((size_t)p * 2 + 0) * Nh;
+      double acc = 0.0;
+      for (int i = threadIdx.x; i < Nh; i += blockDim.x) acc = fma(B1[i], W0[i], acc);
+      h01 = (block_sum(acc, red) + n2r) / 2.0;
+    }
+    const double A0 = k0 + c0, A1 = k1 + c1;
+    const double qa = h0 + h1 - 2.0 * h01, qb = (A0 - A1) + 2.0 * (h01 - h1), qc = A1 + h1;
+    double emin;
+    line_search(d, b, p, qa, qb, qc, has_xc, 0, 1.0, true, 1e4 * eps64, 1e4 * eps64, 100, &ls, red, td, emin);
+    Etot = emin;
+    Ekin = td * k0 + (1.0 - td) * k1;
+    Ecou = td * c0 + (1.0 - td) * c1;
+    Ehar = td * td * h0 + (1.0 - td) * (1.0 - td) * h1 + 2.0 * td * (1.0 - td) * h01;
+    Eexc = Etot - Ekin - Ecou - Ehar;
+    if (threadIdx.x == 0) {
+      const int o0 = b.degen_idx[2 * p], o1 = b.degen_idx[2 * p + 1];
+      const double* dn = b.degen_n + 4 * p;
+      const size_t base = ((size_t)p * 2 + 0) * s * b.Lmax * b.nhmax;
+      b.occ[base + o0] = td * dn[0] + (1.0 - td) * dn[2];
+      b.occ[base + o1] = td * dn[1] + (1.0 - td) * dn[3];
+    }
+  } else {
+    Ekin = sh[1];
+    Ecou = sh[2];
+    Ehar = har_on ? (sc0[0] + n2r) / 2.0 : 0.0;
+    Eexc = has_xc ? exc_grid(d, b, p, 1.0, 0.0, 0.0, false, red) : 0.0;
+    Etot = has_xc ? (sh[0] - Ehar + Eexc - sh[3]) : (sh[0] - Ehar);
+  }
+  // ---- ODA relaxation (niter > 0)
+  const int niter = b.niter[p];
+  const double* Ep = b.E + (size_t)p * 5;  // previous: Etot,Ekin,Ecou,Ehar,Eexc
+  double t = b.t[p], tmix = 1.0;
+  if (niter > 0) {
+    double h01 = 0.0;
+    if (har_on) {
+      const double bpw = degen ? (td * sc0[1] + (1.0 - td) * sc1[1]) : sc0[1];
+      h01 = (bpw + n2r) / 2.0;
+    }
+    double ekin_m, ecou_m, ehar_m, eexc_m, etot_m;
+    if (b.frozen_t) {
+      ekin_m = t * Ekin + (1.0 - t) * Ep[1];
+      ecou_m = t * Ecou + (1.0 - t) * Ep[2];
+      ehar_m = (t * t) * Ehar + ((1.0 - t) * (1.0 - t)) * Ep[3] + 2.0 * t * (1.0 - t) * h01;
+      eexc_m = has_xc ? exc_grid(d, b, p, t * td, t * (1.0 - td), 1.0 - t, degen, red) : 0.0;
+      etot_m = ekin_m + ecou_m + ehar_m + eexc_m;
+    } else {
+      const double A0 = Ekin + Ecou, A1 = Ep[1] + Ep[2];
+      const double qa = Ehar + Ep[3] - 2.0 * h01, qb = (A0 - A1) + 2.0 * (h01 - Ep[3]), qc = A1 + Ep[3];
+      line_search(d, b, p, qa, qb, qc, has_xc, 1, td, degen, b.abstol_ls, b.reltol_ls, b.maxiter_ls, &ls,
+                  red, t, etot_m);
+      ekin_m = t * Ekin + (1.0 - t) * Ep[1];
+      ecou_m = t * Ecou + (1.0 - t) * Ep[2];
+      ehar_m = t * t * Ehar + (1.0 - t) * (1.0 - t) * Ep[3] + 2.0 * t * (1.0 - t) * h01;
+      eexc_m = etot_m - ekin_m - ecou_m - ehar_m;
+    }
+    Ekin = ekin_m; Ecou = ecou_m; Ehar = ehar_m; Eexc = eexc_m; Etot = etot_m;
+    tmix = t;
+  }
+  if (threadIdx.x == 0) {
+    double* En = b.Enew + (size_t)p * 5;
+    En[0] = Etot; En[1] = Ekin; En[2] = Ecou; En[3] = Ehar; En[4] = Eexc;
+    b.t[p] = t;
+    b.tmix[p] = tmix;
+    b.td[p] = td;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_mix_state: D <- t D_new + (1-t) D_prev applied to the linear images of D the next step
+// reads (rho at the Gauss nodes, rho on the energy grid, Hartree rhs and solution).
+__global__ void k_mix_state(DiscDev d, BatchDev b) {
+  const int p = blockIdx.y;
+  if (b.status[p] != 0) return;
+  const double t = b.tmix[p], td = b.td[p];
+  const bool degen = b.degen[p] != 0;
+  const size_t nq = (size_t)b.s * d.C * d.Q, ny = (size_t)b.s * d.G, nv = d.Nh;
+  const size_t total = nq + ny + 2 * nv;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    double *dst;
+    const double *a0, *a1;
+    if (idx < nq) {
+      dst = b.rho_q + (size_t)p * nq + idx;
+      a0 = b.rho_q_new + ((size_t)p * 2 + 0) * nq + idx; a1 = b.rho_q_new + ((size_t)p * 2 + 1) * nq + idx;
+    } else if (idx < nq + ny) {
+      const size_t i = idx - nq;
+      dst = b.rho_y + (size_t)p * ny + i;
+      a0 = b.rho_y_new + ((size_t)p * 2 + 0) * ny + i; a1 = b.rho_y_new + ((size_t)p * 2 + 1) * ny + i;
+    } else if (idx < nq + ny + nv) {
+      const size_t i = idx - nq - ny;
+      dst = b.Bv + (size_t)p * nv + i;
+      a0 = b.B_new + ((size_t)p * 2 + 0) * nv + i; a1 = b.B_new + ((size_t)p * 2 + 1) * nv + i;
+    } else {
+      const size_t i = idx - nq - ny - nv;
+      dst = b.Wv + (size_t)p * nv + i;
+      a0 = b.W_new + ((size_t)p * 2 + 0) * nv + i; a1 = b.W_new + ((size_t)p * 2 + 1) * nv + i;
+    }
+    double v = *a0;
+    if (degen) v = td * v + (1.0 - td) * (*a1);
+    *dst = t * v + (1.0 - t) * (*dst);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_mix_dense: the dense density matrix D = sum n u u^T (density!, density.jl:15-41), mixed in
+// place, and the Frobenius norm of the update (stopping rule, oda/loop.jl:43-45).  Pure HBM
+// streaming: read D, write D; the trial D is never materialised.  32x32 tile per CTA.
+#define MIX_TS 32
+#define MIX_MAXOCC 48
+__global__ void __launch_bounds__(AKS_NT) k_mix_dense(DiscDev d, BatchDev b) {
+  const int p = blockIdx.z, e = blockIdx.y;
+  if (b.status[p] != 0) return;
+  __shared__ double Ui[MIX_TS][MIX_MAXOCC + 1];
+  __shared__ double Uj[MIX_TS][MIX_MAXOCC + 1];
+  __shared__ double nk[MIX_MAXOCC];
+  __shared__ int ol[MIX_MAXOCC], okk[MIX_MAXOCC];
+  __shared__ int cnt_s;
+  __shared__ double red[AKS_NW];
+  const int Nh = d.Nh, nt = b.ntile;
+  const int tr = blockIdx.x / nt, tc = blockIdx.x - tr * nt;
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    for (int k = 0; k < b.nhp[p]; ++k)
+      for (int l = 0; l < b.Lp[p]; ++l) {
+        const double nn = b.occ[occ_off(b, p, 0, e, l, k)];
+        if (nn != 0.0 && cnt < MIX_MAXOCC) { nk[cnt] = nn; ol[cnt] = l; okk[cnt] = k; ++cnt; }
+      }
+    cnt_s = cnt;
+  }
+  __syncthreads();
+  const int cnt = cnt_s;
+  for (int idx = threadIdx.x; idx < MIX_TS * cnt; idx += AKS_NT) {
+    const int o = idx / MIX_TS, r = idx - o * MIX_TS;
+    const double* u = b.U + orb_off(b, p, e, ol[o], okk[o]) * Nh;
+    const int gi = tr * MIX_TS + r, gj = tc * MIX_TS + r;
+    Ui[r][o] = (gi < Nh) ? u[gi] : 0.0;
+    Uj[r][o] = (gj < Nh) ? u[gj] : 0.0;
+  }
+  __syncthreads();
+  const double t = b.tmix[p];
+  double* D = b.Dd + ((size_t)p * b.s + e) * Nh * Nh;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (int rr = ry; rr < MIX_TS; rr += AKS_NW) {
+    const int gi = tr * MIX_TS + rr, gj = tc * MIX_TS + cx;
+    if (gi < Nh && gj < Nh) {
+      double dn = 0.0;
+      for (int o = 0; o < cnt; ++o) dn = fma(nk[o] * Ui[rr][o], Uj[cx][o], dn);
+      const size_t at = (size_t)gi * Nh + gj;
+      const double old = D[at];
+      const double nv = t * dn + (1.0 - t) * old;
+      D[at] = nv;
+      const double df = nv - old;
+      acc = fma(df, df, acc);
+    }
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) b.norm_part[((size_t)p * b.s + e) * nt * nt + blockIdx.x] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// k_finalize: stopping criterion max(||D - D_prev||_F, |Etot - Etot_prev|) < scftol
+// (oda/loop.jl:43-49), iteration counter, per-iteration record for LogBook / callbacks.
+__global__ void k_finalize(DiscDev d, BatchDev b) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= b.B || b.status[p] != 0) return;
+  const int npart = b.s * b.ntile * b.ntile;
+  double ss = 0.0;
+  for (int i = 0; i < npart; ++i) ss += b.norm_part[(size_t)p * npart + i];
+  const double* En = b.Enew + (size_t)p * 5;
+  double* E = b.E + (size_t)p * 5;
+  const double stop = fmax(sqrt(ss), fabs(En[0] - E[0]));
+  for (int i = 0; i < 5; ++i) E[i] = En[i];
+  b.stop[p] = stop;
+  b.niter[p] += 1;
+  b.warm[p] = 1;
+  int st = 0;
+  if (!(isfinite(En[0]) && isfinite(stop))) st = AKS_ENAN;
+  else if (stop < b.scftol) st = AKS_SUCCESS;
+  b.status[p] = st;
+  aks_iter_record r;
+  r.niter = b.niter[p]; r.status = st; r.stop = stop;
+  r.Etot = En[0]; r.Ekin = En[1]; r.Ecou = En[2]; r.Ehar = En[3]; r.Eexc = En[4];
+  r.t = b.t[p];
+  b.rec[p] = r;
+}

@@ -1,0 +1,86 @@
+"""KSEDiscretization: tables of one radial discretization, host- and device-side.
+
+Mirrors `KSEDiscretization(basis, model; lh, nh=10, fem_integration_method=GaussLegendre(basis))`
++ `init_cache!` (`src/discretization/discretization.jl:270-341`).  The density-independent
+tables are built once on the host (`femops.py`, `quadrature.py`) and handed to the CUDA
+library through `aks_disc_create`; everything density-dependent lives on the device.
+One discretization serves any number of models (a batch) with the same spin count.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .basis import FEMBasis
+from .femops import FEMOperators, build_femops
+from .quadrature import GaussLegendre
+
+
+class KSEDiscretization:
+    def __init__(self, basis: FEMBasis, model=None, *, lh: int, nh: int = 10, nspin: int | None = None,
+                 fem_integration_method: GaussLegendre | None = None, femops: FEMOperators | None = None,
+                 device: int = 0):
+        self.basis = basis
+        self.lh, self.nh = int(lh), int(nh)
+        self.nspin = int(nspin if nspin is not None else (model.nspin if model is not None else 1))
+        self.Nh = basis.size
+        self.Rmax = basis.mesh.last
+        self.fem_integration_method = fem_integration_method or GaussLegendre(basis)
+        self.femops = femops or build_femops(basis)
+        self.device = device
+        self._handle = None
+        self._ctx = None
+        self._keep = None
+
+    # ---- device side -------------------------------------------------------------------
+    @property
+    def ctx(self) -> _capi.Context:
+        if self._ctx is None:
+            self._ctx = _capi.default_context(self.device)
+        return self._ctx
+
+    def handle(self):
+        """aks_disc* of this discretization (created on first use)."""
+        if self._handle is not None:
+            return self._handle
+        b, ops, q = self.basis, self.femops, self.fem_integration_method
+        n, Cn = b.nloc, b.ncells
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        cell_len = i64([len(v) for v in b.cells_to_indices])
+        cidx = np.zeros((Cn, n), dtype=np.int64)
+        cgen = np.zeros((Cn, n), dtype=np.int64)
+        for c in range(Cn):
+            L = len(b.cells_to_indices[c])
+            cidx[c, :L] = np.asarray(b.cells_to_indices[c]) + 1
+            cgen[c, :L] = np.asarray(b.cells_to_generators[c]) + 1
+        Fi, Fj, Fm, Fv = ops.F_coo()
+        keep = dict(
+            mesh=f64(b.mesh.points), invshifts=f64(b.invshifts.reshape(-1)), x=f64(q.x), w=f64(q.w),
+            Pgenx=f64(q.Pgenx.T.reshape(-1)),          # column-major (p+1, Q)
+            y=f64(q.y), wy=f64(q.wy), ycell=i64(q.ycell + 1), Pgeny=f64(q.Pgeny.T.reshape(-1)),
+            M0=f64(ops.M0.T.reshape(-1)), A=f64(ops.A.T.reshape(-1)), Mm1=f64(ops.Mm1.T.reshape(-1)),
+            Mm2=f64(ops.Mm2.T.reshape(-1)), Fi=i64(Fi + 1), Fj=i64(Fj + 1), Fm=i64(Fm + 1), Fv=f64(Fv),
+            cell_len=cell_len, cidx=i64(cidx.reshape(-1)), cgen=i64(cgen.reshape(-1)))
+        d = _capi.DiscDesc()
+        d.dtype, d.p, d.C, d.Nh = 0, b.ordermax, Cn, b.size
+        d.Q, d.G, d.lh, d.nh, d.nspin = q.npoints, q.npoints, self.lh, self.nh, self.nspin
+        for name in ("mesh", "invshifts", "x", "w", "Pgenx", "y", "wy", "Pgeny", "M0", "A", "Mm1", "Mm2", "Fv"):
+            setattr(d, name, _capi.dptr(keep[name]))
+        d.ycell = _capi.iptr(keep["ycell"])
+        d.nF = len(Fv)
+        d.Fi, d.Fj, d.Fm = _capi.iptr(keep["Fi"]), _capi.iptr(keep["Fj"]), _capi.iptr(keep["Fm"])
+        d.cell_len = _capi.iptr(keep["cell_len"])
+        d.cell_indices = _capi.iptr(keep["cidx"])
+        d.cell_generators = _capi.iptr(keep["cgen"])
+        h = C.c_void_p()
+        self.ctx.check(_capi.lib.aks_disc_create(self.ctx.h, C.byref(d), C.byref(h)))
+        self._handle = h
+        return h
+
+    def close(self):
+        if self._handle is not None:
+            _capi.lib.aks_disc_destroy(self._handle)
+            self._handle = None

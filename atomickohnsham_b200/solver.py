@@ -1,0 +1,321 @@
+"""groundstate / KSESolver / KSESolution on top of the CUDA library.
+
+Mirrors `groundstate(model, discretization, alg; maxiter=100, callback=nothing)`,
+`KSESolver`, `solve!`, `register!`, `LogBook`, `CallbackSet`, `LogFileCallback`
+(`src/solver/{groundstate,solver,logbook,callback,logging}.jl`) and the fields of
+`KSESolution` the hot path produces (`src/solution/types.jl:74-140`).  The SCF loop body
+`scf_step!` is one `aks_scf_step` call on the device for the whole batch; the host only
+keeps the reference's bookkeeping (logbook, callbacks, status strings).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _capi
+from ._capi import AKS_ENOTCONV, AKS_MAXITERS, AKS_OK, AKS_RUNNING, AKS_SUCCESS, IterRecord
+from .algorithms import ODA
+from .discretization import KSEDiscretization
+from .model import KSEModel
+
+ATOMIC_NAMES = ("Hydrogen Helium Lithium Beryllium Boron Carbon Nitrogen Oxygen Fluorine Neon Sodium "
+                "Magnesium Aluminium Silicon Phosphorus Sulfur Chlorine Argon Potassium Calcium Scandium "
+                "Titanium Vanadium Chromium Manganese Iron Cobalt Nickel Copper Zinc Gallium Germanium "
+                "Arsenic Selenium Bromine Krypton Rubidium Strontium Yttrium Zirconium Niobium Molybdenum "
+                "Technetium Ruthenium Rhodium Palladium Silver Cadmium Indium Tin Antimony Tellurium Iodine "
+                "Xenon Caesium Barium Lanthanum Cerium Praseodymium Neodymium Promethium Samarium Europium "
+                "Gadolinium Terbium Dysprosium Holmium Erbium Thulium Ytterbium Lutetium Hafnium Tantalum "
+                "Tungsten Rhenium Osmium Iridium Platinum Gold Mercury Thallium Lead Bismuth Polonium "
+                "Astatine Radon").split()
+
+
+@dataclass
+class Energies:
+    Etot: float = 0.0
+    Ekin: float = 0.0
+    Ecou: float = 0.0
+    Ehar: float = 0.0
+    Eexc: float = 0.0
+
+
+@dataclass
+class LogBook:
+    stopping_criteria: list = field(default_factory=list)
+    Etot: list = field(default_factory=list)
+
+
+class CallbackSet:
+    def __init__(self, callbacks=()):
+        self.callbacks = tuple(callbacks)
+
+    def __call__(self, solver):
+        for cb in self.callbacks:
+            cb(solver)
+
+
+class LogFileCallback:
+    """One line per iteration: iter, stop, Etot, Ekin, Ecou, Ehar, Eexc, t (logging.jl:26-37)."""
+
+    def __init__(self, io):
+        self.io = io
+
+    def __call__(self, solver):
+        e = solver.energies
+        self.io.write(f"iter = {solver.niter}   stop = {solver.stopping_criteria!r}   Etot = {e.Etot!r}   "
+                      f"Ekin = {e.Ekin!r}   Ecou = {e.Ecou!r}   Ehar = {e.Ehar!r}   Eexc = {e.Eexc!r}   "
+                      f"t = {solver.t!r}\n")
+
+
+def solution_name(Z, N):
+    """groundstate.jl:24-34."""
+    if float(Z).is_integer():
+        d = Z - N
+        base = ATOMIC_NAMES[int(Z) - 1] if 1 <= int(Z) <= len(ATOMIC_NAMES) else f"Z={Z}"
+        if d == 0:
+            return base
+        return f"{base}{abs(d)}{'+' if d > 0 else '-'}"
+    return f"Z={Z}, N={N}"
+
+
+class Batch:
+    """A batch of models sharing one discretization, resident on the device (aks_batch)."""
+
+    def __init__(self, models, discretization: KSEDiscretization, alg: ODA, *, lh=None, nh=None):
+        self.models = list(models)
+        self.disc = discretization
+        self.alg = alg
+        nprob = len(self.models)
+        for m in self.models:
+            if m.nspin != discretization.nspin:
+                raise ValueError("all models of a batch must have the discretization's spin count")
+        f64 = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+        i32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        self._Z = f64([m.Z for m in self.models])
+        self._N = f64([m.N for m in self.models])
+        self._har = f64([m.hartree for m in self.models])
+        self._ex = i32([m.exchange.xc_id for m in self.models])
+        self._ec = i32([m.correlation.xc_id for m in self.models])
+        self._lh = None if lh is None else i32(lh)
+        self._nh = None if nh is None else i32(nh)
+        self.ctx = discretization.ctx
+        h = C.c_void_p()
+        self.ctx.check(_capi.lib.aks_batch_create(
+            discretization.handle(), nprob, _capi.dptr(self._Z), _capi.dptr(self._N), _capi.dptr(self._har),
+            _capi.i32ptr(self._ex), _capi.i32ptr(self._ec), _capi.i32ptr(self._lh), _capi.i32ptr(self._nh),
+            C.byref(h)))
+        self.h = h
+        self.nprob = nprob
+        a = alg.aufbau
+        self.ctx.check(_capi.lib.aks_batch_set_oda(h, alg.scftol, alg.tinit, int(alg.frozen_t), alg.maxiter_ls,
+                                                   alg.abstol_ls, alg.reltol_ls, a.max_degen, a.tol,
+                                                   int(a.handle_degen_spin_1iter)))
+        self._rec = (IterRecord * nprob)()
+
+    def reset(self):
+        self.ctx.check(_capi.lib.aks_batch_reset(self.h))
+
+    def step(self):
+        """One scf_step! for every running problem; returns the list of records."""
+        self.ctx.check(_capi.lib.aks_scf_step(self.h, self._rec))
+        return [r.asdict() for r in self._rec]
+
+    def run(self, maxiter=100, history=False):
+        """solve!: returns (final records, history or None)."""
+        hist = (IterRecord * (maxiter * self.nprob))() if history else None
+        rc = _capi.lib.aks_scf_run(self.h, maxiter, hist, self._rec)
+        self.ctx.check(rc, ok=(AKS_OK, AKS_ENOTCONV))
+        final = [r.asdict() for r in self._rec]
+        if not history:
+            return final, None
+        out = [[] for _ in range(self.nprob)]
+        for k in range(maxiter):
+            for i in range(self.nprob):
+                r = hist[k * self.nprob + i]
+                if r.niter == k + 1 and (not out[i] or out[i][-1]["niter"] != r.niter):
+                    out[i].append(r.asdict())
+        return final, out
+
+    def state(self, prob=0, *, want_D=True, want_U=True):
+        d = self.disc
+        s, Nh, L, nh = d.nspin, d.Nh, d.lh + 1, d.nh
+        D = np.zeros((s, Nh, Nh)) if want_D else None
+        U = np.zeros((s, L, nh, Nh)) if want_U else None
+        eps = np.zeros(s * L * nh)
+        n = np.zeros(s * L * nh)
+        W = np.zeros(Nh)
+        self.ctx.check(_capi.lib.aks_get_state(self.h, prob, _capi.dptr(D), _capi.dptr(U), _capi.dptr(eps),
+                                               _capi.dptr(n), _capi.dptr(W)))
+        # Julia layouts -> numpy [l, k, sigma] / [i, k, l, sigma] / [i, j, sigma]
+        eps = eps.reshape((L, nh, s), order="F")
+        n = n.reshape((L, nh, s), order="F")
+        out = dict(eps=eps, n=n, W=W)
+        if want_D:
+            out["D"] = np.transpose(D, (1, 2, 0))
+        if want_U:
+            out["U"] = np.transpose(U, (3, 2, 1, 0))
+        return out
+
+    def set_density(self, prob, D, energies_prev=None, niter=1):
+        """Restart / step-level parity: D is (Nh, Nh, nspin) (or (Nh, Nh))."""
+        D = np.asarray(D, dtype=np.float64)
+        if D.ndim == 2:
+            D = D[:, :, None]
+        Dd = np.ascontiguousarray(np.transpose(D, (2, 0, 1)))
+        e = None if energies_prev is None else np.ascontiguousarray(energies_prev, dtype=np.float64)
+        self.ctx.check(_capi.lib.aks_set_density(self.h, prob, _capi.dptr(Dd), _capi.dptr(e), niter))
+
+    # ---- step-level hooks ------------------------------------------------------------
+    def assemble_hartree(self, prob=0):
+        out = np.zeros((self.disc.Nh, self.disc.Nh))
+        self.ctx.check(_capi.lib.aks_assemble_hartree(self.h, prob, _capi.dptr(out)))
+        return out.T.copy()
+
+    def assemble_vxc(self, prob=0):
+        s, Nh = self.disc.nspin, self.disc.Nh
+        out = np.zeros((s, Nh, Nh))
+        self.ctx.check(_capi.lib.aks_assemble_vxc(self.h, prob, _capi.dptr(out)))
+        return np.transpose(out, (2, 1, 0)).copy()
+
+    def eig_lowest(self, prob=0):
+        d = self.disc
+        s, Nh, L, nh = d.nspin, d.Nh, d.lh + 1, d.nh
+        eps = np.zeros(s * L * nh)
+        res = np.zeros(s * L * nh)
+        U = np.zeros((s, L, nh, Nh))
+        self.ctx.check(_capi.lib.aks_eig_lowest(self.h, prob, _capi.dptr(eps), _capi.dptr(U), _capi.dptr(res)))
+        return (eps.reshape((L, nh, s), order="F"), np.transpose(U, (3, 2, 1, 0)),
+                res.reshape((L, nh, s), order="F"))
+
+    def exc_energy(self, prob=0):
+        v = C.c_double()
+        self.ctx.check(_capi.lib.aks_exc_energy(self.h, prob, C.byref(v)))
+        return v.value
+
+    def hartree_energy(self, prob=0):
+        v = C.c_double()
+        self.ctx.check(_capi.lib.aks_hartree_energy(self.h, prob, C.byref(v)))
+        return v.value
+
+    def phase_ms(self):
+        out = (C.c_double * 8)()
+        rc = _capi.lib.aks_last_phase_ms(self.h, out)
+        return list(out) if rc == AKS_OK else None
+
+    def close(self):
+        if self.h:
+            _capi.lib.aks_batch_destroy(self.h)
+            self.h = None
+
+
+class KSESolver:
+    """Single-problem solver state with the reference's fields (solver.jl:41-88)."""
+
+    def __init__(self, model: KSEModel, discretization: KSEDiscretization, alg: ODA, *, maxiter=100,
+                 callback=None):
+        self.model, self.discretization, self.alg = model, discretization, alg
+        self.maxiter = int(maxiter)
+        self.callback = callback
+        self.niter = 0
+        self.stopping_criteria = 0.0
+        self.energies = Energies()
+        self.logbook = LogBook()
+        self.t = alg.tinit
+        self.status = AKS_RUNNING
+        self.batch = Batch([model], discretization, alg)
+
+    def scf_step(self):
+        r = self.batch.step()[0]
+        self.stopping_criteria = r["stop"]
+        self.energies = Energies(r["Etot"], r["Ekin"], r["Ecou"], r["Ehar"], r["Eexc"])
+        self.t = r["t"]
+        self.status = r["status"]
+        return r["stop"]
+
+    def solve(self):
+        """solve! (groundstate.jl:53-62)."""
+        while self.niter < self.maxiter:
+            self.scf_step()
+            self.logbook.stopping_criteria.append(self.stopping_criteria)
+            self.logbook.Etot.append(self.energies.Etot)
+            if self.callback is not None:
+                self.callback(self)
+            self.niter += 1
+            if self.status < 0:
+                raise _capi.AKSError(self.status, "SCF step failed")
+            if self.stopping_criteria < self.alg.scftol:
+                break
+        return self
+
+
+@dataclass
+class KSESolution:
+    """The outputs of the hot path in the reference's naming (solution/types.jl:74-140)."""
+    name: str
+    success: str
+    niter: int
+    stopping_criteria: float
+    energies: Energies
+    ϵ: np.ndarray
+    n: np.ndarray
+    U: np.ndarray | None
+    D: np.ndarray | None
+    W: np.ndarray
+    logbook: LogBook | None = None
+
+    @property
+    def eps(self):
+        return self.ϵ
+
+    @property
+    def occupied(self):
+        """[(label, eps, n)] sorted by energy (solution/types.jl `occupied`)."""
+        out = []
+        L, nh, s = self.n.shape
+        for sg in range(s):
+            for l in range(L):
+                for k in range(nh):
+                    if self.n[l, k, sg] != 0:
+                        lab = f"{k + l + 1}{'spdfgh'[l]}" + ("" if s == 1 else "↑↓"[sg])
+                        out.append((lab, float(self.ϵ[l, k, sg]), float(self.n[l, k, sg])))
+        return sorted(out, key=lambda v: v[1])
+
+
+def _solution(batch: Batch, i: int, rec: dict, logbook=None, want_arrays=True):
+    st = batch.state(i, want_D=want_arrays, want_U=want_arrays)
+    m = batch.models[i]
+    succ = "SUCCESS" if rec["status"] == AKS_SUCCESS else ("MAXITERS" if rec["status"] in (AKS_MAXITERS, AKS_RUNNING)
+                                                            else f"ERROR({rec['status']})")
+    return KSESolution(solution_name(m.Z, m.N), succ, rec["niter"], rec["stop"],
+                       Energies(rec["Etot"], rec["Ekin"], rec["Ecou"], rec["Ehar"], rec["Eexc"]),
+                       st["eps"], st["n"], st.get("U"), st.get("D"), st["W"], logbook)
+
+
+def groundstate(model, discretization: KSEDiscretization, alg: ODA, *, maxiter: int = 100, callback=None,
+                lh=None, nh=None, want_arrays=True):
+    """Ground state of one model (-> KSESolution) or of a list of models (-> list), on the B200.
+
+    With a callback the loop runs one `aks_scf_step` per iteration so that `register!` and
+    the callback fire exactly as in the reference; without one the whole loop is a single
+    `aks_scf_run`.
+    """
+    if isinstance(model, KSEModel):
+        if callback is not None:
+            solver = KSESolver(model, discretization, alg, maxiter=maxiter, callback=callback).solve()
+            rec = dict(niter=solver.niter, status=solver.status, stop=solver.stopping_criteria,
+                       **solver.energies.__dict__)
+            sol = _solution(solver.batch, 0, rec, solver.logbook, want_arrays)
+            solver.batch.close()
+            return sol
+        models, single = [model], True
+    else:
+        models, single = list(model), False
+    batch = Batch(models, discretization, alg, lh=lh, nh=nh)
+    final, hist = batch.run(maxiter, history=True)
+    sols = []
+    for i, rec in enumerate(final):
+        lb = LogBook([h["stop"] for h in hist[i]], [h["Etot"] for h in hist[i]])
+        sols.append(_solution(batch, i, rec, lb, want_arrays))
+    batch.close()
+    return sols[0] if single else sols

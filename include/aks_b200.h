@@ -1,0 +1,169 @@
+/*
+ * aks_b200.h -- C ABI of the B200-native SCF inner loop for radial Kohn-Sham atoms.
+ *
+ * Drop-in boundary for ONE hot path of Theozeud/AtomicKohnSham (Julia): the body of
+ * `solve!`'s while loop, i.e. `scf_step!(::ODA, ::KSESolver)`
+ * (reference src/solver/groundstate.jl:53-62, src/algorithms/oda/loop.jl:1-116), for a
+ * BATCH of independent problems (atoms / ions / functionals) that share one
+ * discretization.  The reference has no FFI: these entry points are what a Julia
+ * `ccall` shim binds behind `groundstate(...; backend = :b200)`.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (AKS_OK == 0).
+ *   - all host arrays are caller-owned and copied at *_create; outputs are written into
+ *     caller-allocated buffers in the reference's (Julia, column-major) layouts.
+ *   - integer index tables are 1-based, as Julia holds them.
+ *   - a ctx is bound to one CUDA device and one stream; calls return after the work
+ *     they name has completed; a ctx is not thread-safe, different ctxs are independent.
+ */
+#ifndef AKS_B200_H
+#define AKS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define AKS_OK 0
+#define AKS_EINVAL (-1)   /* bad argument                                              */
+#define AKS_ECUDA (-2)    /* CUDA runtime error (see aks_last_error)                   */
+#define AKS_ENOTCONV (-3) /* aks_scf_run: at least one problem hit maxiter             */
+#define AKS_EDEGEN3 (-4)  /* >2-fold degeneracy (reference error(), optimized.jl:139)   */
+#define AKS_ENAN (-5)     /* non-finite value in a problem's energies                   */
+#define AKS_ENOSYS (-6)   /* feature not built (e.g. dtype = double-double)             */
+
+/* per-problem status word in aks_iter_record.status */
+#define AKS_RUNNING 0
+#define AKS_SUCCESS 1  /* reference "SUCCESS"  (src/solution/types.jl:123) */
+#define AKS_MAXITERS 2 /* reference "MAXITERS"                              */
+
+/* exchange / correlation ids (Libxc numbering for the functionals the reference uses) */
+#define AKS_XC_NONE 0
+#define AKS_LDA_X 1     /* Slater exchange, src/physics/exchange correlation/SlaterXa.jl */
+#define AKS_LDA_C_PW 12 /* PW92 correlation, .../PerdewWang.jl                           */
+
+typedef struct aks_ctx aks_ctx;
+typedef struct aks_disc aks_disc;
+typedef struct aks_batch aks_batch;
+
+/* ---- context ----------------------------------------------------------------------- */
+int aks_ctx_create(int device, aks_ctx** out);
+void aks_ctx_destroy(aks_ctx* ctx);
+const char* aks_last_error(const aks_ctx* ctx);
+/* the CUDA stream (cudaStream_t) all work of this ctx is launched on */
+void* aks_ctx_stream(const aks_ctx* ctx);
+
+/* ---- discretization: replaces KSEDiscretization + init_cache! tables --------------------
+ * (src/discretization/discretization.jl:270-341, src/fem/integration methods.jl:30-70,
+ *  src/fem/generators.jl:79-138).  Sizes: n = p+1 generators, C cells, Nh = p*C-1.       */
+typedef struct aks_disc_desc {
+  int32_t dtype;  /* 0 = Float64; 1 = Double64 (hi,lo) pairs -> AKS_ENOSYS in this build    */
+  int32_t p;      /* ordermax                                                             */
+  int32_t C;      /* number of cells = length(mesh)-1                                     */
+  int32_t Nh;     /* basis size                                                           */
+  int32_t Q;      /* Gauss points per cell  (GaussLegendre.npoints)                       */
+  int32_t G;      /* points of the global energy grid (== Q in the reference)             */
+  int32_t lh;     /* max angular momentum; L = lh+1 channels                              */
+  int32_t nh;     /* eigenpairs per channel                                               */
+  int32_t nspin;  /* 1 or 2                                                               */
+  const double* mesh;      /* [C+1]                                                       */
+  const double* invshifts; /* [2*C]  (c1,c0) per cell: r = c1*x + c0  (basis.invshifts)   */
+  const double* x;         /* [Q]    GaussLegendre.x                                      */
+  const double* w;         /* [Q]    GaussLegendre.w                                      */
+  const double* Pgenx;     /* [(p+1)*Q] column-major (p+1,Q): generator g at node q       */
+  const double* y;         /* [G]    GaussLegendre.y                                      */
+  const double* wy;        /* [G]    GaussLegendre.wy                                     */
+  const int64_t* ycell;    /* [G]    findindex(mesh, y[q]) (1-based cell)                 */
+  const double* Pgeny;     /* [(p+1)*G] column-major (p+1,G): generators at phi(y[q])     */
+  const double* M0;        /* [Nh*Nh] dense, symmetric (femops.M0)                        */
+  const double* A;         /* [Nh*Nh] dense (Matrix(femops.A))                            */
+  const double* Mm1;       /* [Nh*Nh] dense (Matrix(femops.M₋₁))                          */
+  const double* Mm2;       /* [Nh*Nh] dense or NULL when lh == 0                          */
+  int64_t nF;              /* entries of the mass tensor Dict femops.F (0 if no Hartree)  */
+  const int64_t* Fi;       /* [nF] 1-based (i,j,m) keys                                   */
+  const int64_t* Fj;
+  const int64_t* Fm;
+  const double* Fv;        /* [nF]                                                        */
+  const int64_t* cell_len;        /* [C]   length(cells_to_indices[c])                    */
+  const int64_t* cell_indices;    /* [C*(p+1)] row c: cells_to_indices[c], 1-based, 0-padded   */
+  const int64_t* cell_generators; /* [C*(p+1)] row c: cells_to_generators[c], 1-based, 0-padded */
+} aks_disc_desc;
+
+int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* desc, aks_disc** out);
+void aks_disc_destroy(aks_disc* disc);
+
+/* ---- batch of models: replaces KSEModel + KSESolver/ODACache state ----------------------
+ * (src/physics/models.jl:19-58, src/algorithms/oda/types.jl:58-107).
+ * lh_p / nh_p may be NULL (every problem uses the disc's lh, nh) or give per-problem
+ * values <= the disc's (a sweep where basis_size depends on Z).                          */
+int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const double* N,
+                     const double* hartree, const int32_t* ex_id, const int32_t* ec_id,
+                     const int32_t* lh_p, const int32_t* nh_p, aks_batch** out);
+void aks_batch_destroy(aks_batch* batch);
+
+/* ODA(...) + OptimizedAufbau(...) options (oda/types.jl:29-45, aufbau/optimized.jl:18-27) */
+int aks_batch_set_oda(aks_batch* batch, double scftol, double tinit, int32_t frozen_t,
+                      int32_t maxiter_ls, double abstol_ls, double reltol_ls,
+                      int32_t max_degen, double degen_tol, int32_t handle_degen_spin_1iter);
+
+/* back to niter = 0, D = 0 (KSESolver constructor, src/solver/solver.jl:61-88) */
+int aks_batch_reset(aks_batch* batch);
+
+/* what LogBook / LogFileCallback read after every iteration (src/solver/logging.jl:26-37) */
+typedef struct aks_iter_record {
+  int32_t niter;  /* iterations completed                                  */
+  int32_t status; /* AKS_RUNNING / AKS_SUCCESS / AKS_MAXITERS / <0 error   */
+  double stop;    /* stopping criterion of the last step                   */
+  double Etot, Ekin, Ecou, Ehar, Eexc;
+  double t;       /* ODA mixing parameter of the last step                 */
+} aks_iter_record;
+
+/* one scf_step! for every problem still running; out[nprob] may be NULL */
+int aks_scf_step(aks_batch* batch, aks_iter_record* out);
+
+/* solve!: iterate until every problem converged or reached maxiter.  history may be NULL
+ * or [maxiter*nprob] (record of problem i after iteration k at history[k*nprob+i]);
+ * final[nprob] receives the last record of each problem.                                  */
+int aks_scf_run(aks_batch* batch, int32_t maxiter, aks_iter_record* history,
+                aks_iter_record* final_records);
+
+/* copy one problem's state out, Julia layouts; any pointer may be NULL:
+ *   D (Nh,Nh[,2])  U (Nh,nh,L[,2])  eps,n (L,nh[,2])  W (Nh) = A\B of the final D
+ *   (postcomputations!, oda/loop.jl:51-54; multiplied by the model's hartree coefficient) */
+int aks_get_state(aks_batch* batch, int32_t prob, double* D, double* U, double* eps, double* n,
+                  double* W);
+/* overwrite one problem's density state from a dense D (Nh,Nh[,2]) -- restart / step-level
+ * parity tests ("identical input D").  Energies of the previous step are set from
+ * `energies_prev` = {Etot,Ekin,Ecou,Ehar,Eexc} and niter from `niter`.                    */
+int aks_set_density(aks_batch* batch, int32_t prob, const double* D, const double* energies_prev,
+                    int32_t niter);
+
+/* ---- step-level hooks (same device code as aks_scf_step; used by the parity tests) ------ */
+/* assemble_hartree!  (assemble.jl:63-83):   Har (Nh,Nh) of the problem's current D        */
+int aks_assemble_hartree(aks_batch* batch, int32_t prob, double* Har);
+/* assemble_exc!      (assemble.jl:277-319): Vxc (Nh,Nh[,2]) of the current D              */
+int aks_assemble_vxc(aks_batch* batch, int32_t prob, double* Vxc);
+/* find_orbital!      (oda/loop.jl:65-77):   lowest nh eigenpairs of every (l,sigma) channel
+ * of H[D]; eps (L,nh[,2]), U (Nh,nh,L[,2]); residuals (L,nh[,2]) = ||(H-eps M0)u||_2 or NULL */
+int aks_eig_lowest(aks_batch* batch, int32_t prob, double* eps, double* U, double* residuals);
+/* compute_exc_energy (energies.jl:217-233) of the current D                               */
+int aks_exc_energy(aks_batch* batch, int32_t prob, double* Exc);
+/* compute_hartree_energy (energies.jl:96-114) of the current D                            */
+int aks_hartree_energy(aks_batch* batch, int32_t prob, double* Ehar);
+
+/* ---- measurement aids --------------------------------------------------------------------*/
+/* number of kernels launched by this ctx so far (bench.py "gpu_launches")                 */
+int64_t aks_launch_count(const aks_ctx* ctx);
+/* sustained FP64 FMA throughput of the device in TFLOP/s (register-resident DFMA chains);
+ * the FP64 roofline denominator, which MEASURED_PEAKS.json does not carry                 */
+int aks_measure_fp64_peak(aks_ctx* ctx, double* tflops);
+/* per-phase device time of the LAST aks_scf_step in ms: {potential, eigensolve, aufbau,
+ * density, poisson, linesearch, mix}; valid only if AKS_PHASE_TIMERS=1 in the environment  */
+int aks_last_phase_ms(aks_batch* batch, double out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AKS_B200_H */
