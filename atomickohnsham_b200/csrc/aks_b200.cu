@@ -417,7 +417,7 @@ extern "C" int aks_batch_set_oda(aks_batch* bt, double scftol, double tinit, int
                                  double degen_tol, int32_t handle_degen_spin_1iter) {
   if (!bt) return AKS_EINVAL;
   aks_ctx* ctx = bt->disc->ctx;
-  if (!(scftol > 0) || !(tinit >= 0 && tinit <= 1) || maxiter_ls < 1 || max_degen < 1 || !(degen_tol >= 0)) {
+  if (!(scftol >= 0) || !(tinit >= 0 && tinit <= 1) || maxiter_ls < 1 || max_degen < 1 || !(degen_tol >= 0)) {
     ctx->err = "aks_batch_set_oda: bad option"; return AKS_EINVAL;
   }
   BatchDev& b = bt->dev;
@@ -561,6 +561,7 @@ extern "C" int aks_scf_step(aks_batch* bt, aks_iter_record* out) {
   if (!bt) return AKS_EINVAL;
   int rc = step_launch(bt);
   if (rc != AKS_OK) return rc;
+  if (!out && !bt->timers) return AKS_OK;  // enqueue only: the caller synchronises the ctx stream
   return fetch_records(bt, out);
 }
 

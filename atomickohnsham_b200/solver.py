@@ -121,6 +121,10 @@ class Batch:
         self.ctx.check(_capi.lib.aks_scf_step(self.h, self._rec))
         return [r.asdict() for r in self._rec]
 
+    def step_async(self):
+        """Enqueue one scf_step! on the ctx stream without reading anything back."""
+        self.ctx.check(_capi.lib.aks_scf_step(self.h, None))
+
     def run(self, maxiter=100, history=False):
         """solve!: returns (final records, history or None)."""
         hist = (IterRecord * (maxiter * self.nprob))() if history else None

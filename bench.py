@@ -1,0 +1,350 @@
+"""bench.py -- SCF-iteration throughput of the B200 hot path (and the CPU reference arm).
+
+Workload (config.workload): ONE periodic-table sweep per GPU on the Argon/C2 discretization of
+BASELINE.json (expmesh(0,300,41;s=1.5) = 40 elements, ordermax 20, Nh = 799, 1000 Gauss points per
+element, LDA = lda_x + lda_c_pw, Float64): 86 independent atoms Z = 1..86 with the reference's
+Z-dependent (lh, nh) rule.  A "step" is one `scf_step!` (assembly + eigensolve + aufbau + density +
+line search + mixing) of every atom of the batch; `scftol` is set to 0 for the timed steps so
+that every atom does every step (fixed work).  metric = atom-SCF-iterations per second.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+C2 = {"mesh": ["exp", 0, 300, 41, 1.5], "p": 20, "npoints": 1000, "lh": 3, "nh": 10}
+METRIC, UNIT = "scf_iterations_per_s", "atom-iterations/s"
+# rank -> (exchange, correlation, ionic charge): independent atoms, ions and functionals
+RANK_SWEEPS = [("lda_x", "lda_c_pw", 0), ("lda_x", "lda_c_pw", 1), ("lda_x", None, 0), ("lda_x", None, 1),
+               ("lda_x", "lda_c_pw", 2), ("lda_x", None, 2), ("lda_x", "lda_c_pw", 3), ("lda_x", None, 3)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_disc(device):
+    from helpers import package_tables
+    import atomickohnsham_b200 as aks
+    basis, ops, quad = package_tables(C2["mesh"], C2["p"], C2["npoints"])
+    disc = aks.KSEDiscretization(basis, None, lh=C2["lh"], nh=C2["nh"], nspin=1, fem_integration_method=quad,
+                                 femops=ops, device=device)
+    return disc
+
+
+def b200_arm(args):
+    import torch
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.solver import Batch
+    from atomickohnsham_b200.sweep import periodic_table_models
+
+    disc = build_disc(local)
+    ctx = disc.ctx
+    disc.handle()
+    ex, ec, charge = RANK_SWEEPS[rank % len(RANK_SWEEPS)]
+    models, lhs, nhs = periodic_table_models(range(1, 87), ex=ex, ec=ec, charge=charge)
+    if args.sweeps > 1:
+        models, lhs, nhs = models * args.sweeps, lhs * args.sweeps, nhs * args.sweeps
+    B = len(models)
+    alg_fixed = aks.ODA(scftol=0.0, tinit=0.6, aufbau=aks.OptimizedAufbau(tol=1e-3))
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(local)
+
+    # ---------------- device-resident throughput (`value`)
+    bt = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs)
+    for _ in range(args.warmup):
+        bt.step_async()
+    launches0 = ctx.launches
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        bt.step_async()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - launches0
+    recs = bt.step()  # sanity: energies finite
+    assert all(r["status"] >= 0 for r in recs), "a problem failed"
+    units = torch.tensor([float(B * args.steps), ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        import torch.distributed as dist
+        tot = units.clone()
+        dist.all_reduce(tot[0:1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(tot[1:2], op=dist.ReduceOp.MAX)
+        units = tot
+    total_units, max_ms = float(units[0]), float(units[1])
+    value = total_units / (max_ms * 1e-3)
+
+    # ---------------- per-phase device time + roofline of the dominant kernel (rank 0)
+    roof, phases = None, None
+    if rank == 0:
+        os.environ["AKS_PHASE_TIMERS"] = "1"
+        bt2 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs)
+        del os.environ["AKS_PHASE_TIMERS"]
+        for _ in range(max(args.warmup, 3)):
+            bt2.step()
+        acc = [0.0] * 7
+        nrep = 5
+        for _ in range(nrep):
+            bt2.step()
+            ph = bt2.phase_ms()
+            acc = [a + b for a, b in zip(acc, ph[:7])]
+        names = ["potential", "eigensolve", "aufbau+orbital_energies", "density", "poisson", "linesearch", "mix+stop"]
+        phases = {n: a / nrep for n, a in zip(names, acc)}
+        bt2.close()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fp64_peak = ctx.fp64_peak_tflops()
+        n, Q, Cc, Nh = C2["p"] + 1, C2["npoints"], 40, 799
+        dom = max(phases, key=phases.get)
+        # k_potential: 2 n^2 Q flop per cell and spin (second half of W_xc) + C Q XC points
+        pot_flops = B * Cc * 2.0 * n * n * Q
+        # k_mix_dense: read D + write D, 16 B per entry (SURVEY 8d W_dens bytes, in-place form)
+        mix_bytes = B * 16.0 * Nh * Nh
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roof_all = {
+            "potential": {"bound": "fp64", "achieved": pot_flops / (phases["potential"] * 1e-3) / 1e12,
+                          "peak": fp64_peak, "unit": "TFLOP/s"},
+            "mix+stop": {"bound": "hbm", "achieved": mix_bytes / (phases["mix+stop"] * 1e-3) / 1e9,
+                         "peak": hbm_peak, "unit": "GB/s"},
+        }
+        for v in roof_all.values():
+            v["frac"] = v["achieved"] / v["peak"]
+            v["traffic"] = None
+        roof = dict(roof_all["potential"])
+        roof["kernel"] = "k_potential"
+        roof["peak_source"] = "aks_measure_fp64_peak (DFMA chains, same run); MEASURED_PEAKS.json has no FP64 figure"
+        roof["dominant_phase"] = dom
+        roof["other"] = {"k_mix_dense": roof_all["mix+stop"],
+                         "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
+
+    # ---------------- end to end through the public API with host buffers (`e2e`)
+    barrier()
+    t0 = time.perf_counter()
+    bt3 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs)       # H2D: model parameters
+    for _ in range(args.steps):
+        bt3.step()                                             # D2H: one record per atom, every step
+    outs = [bt3.state(i, want_D=False, want_U=False) for i in range(B)]  # D2H: eps, n, W per atom
+    torch.cuda.synchronize(local)
+    t_e2e = time.perf_counter() - t0
+    bt3.close()
+    assert len(outs) == B
+    h2d = B * (3 * 8 + 4 * 4)
+    d2h_total = args.steps * B * 72 + B * (2 * 4 * 10 * 8 + Nh_bytes())
+    e2e_units = torch.tensor([float(B * args.steps), t_e2e], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(e2e_units[0:1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(e2e_units[1:2], op=dist.ReduceOp.MAX)
+    e2e_val = float(e2e_units[0]) / float(e2e_units[1])
+
+    # ---------------- full sweep to convergence (atoms/s), informational
+    sweep = None
+    if rank == 0:
+        alg = aks.ODA(scftol=1e-10, tinit=0.6, aufbau=aks.OptimizedAufbau(tol=1e-3))
+        btc = Batch(models, disc, alg, lh=lhs, nh=nhs)
+        t0 = time.perf_counter()
+        final, _ = btc.run(100)
+        dt = time.perf_counter() - t0
+        sweep = {"atoms": B, "seconds": dt, "atoms_per_s": B / dt,
+                 "converged": sum(1 for r in final if r["status"] == 1),
+                 "iterations_total": sum(r["niter"] for r in final),
+                 "iterations_max": max(r["niter"] for r in final)}
+        btc.close()
+
+    # ---------------- CPU baseline (rank 0, N = 1 only): the oracle on one host core
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_single(budget_s=15.0)
+
+    bt.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C5 periodic-table sweep Z=1..86 (one sweep per GPU; rank r: functional/charge "
+                                   "variant r) on the C2 Argon discretization: expmesh(0,300,41;s=1.5), ordermax=20, "
+                                   "Nh=799, 1000 Gauss points/element, LDA, lh=min(ceil(Z/20),3), nh=clamp(Z,2,10)",
+                       "atoms_per_gpu": B, "scftol": "0 during timed steps (fixed work per step)",
+                       "l2": "state per GPU (dense D: %.0f MB) exceeds the 126 MB L2; no explicit flush" % (B * 8 * 799 * 799 / 1e6),
+                       "tables": "resident before the timed regions (setup is outside the reference's loop too)"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+                    "d2h_bytes_per_step": d2h_total / args.steps,
+                    "what": "Batch() + K x aks_scf_step with host records + aks_get_state(eps,n,W) of every atom"},
+            "roofline": roof, "phases_ms": phases, "cpu_baseline": cpu, "sweep_to_convergence": sweep,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def Nh_bytes():
+    return 799 * 8
+
+
+# ------------------------------------------------------------------------------------------- CPU side
+def _oracle_for(Z):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    from helpers import make_oracle
+    from atomickohnsham_b200.sweep import basis_size
+    lh, nh = basis_size(Z)
+    setup = {"Z": Z, "N": Z, "mesh": C2["mesh"], "p": C2["p"], "npoints": C2["npoints"], "lh": lh, "nh": nh,
+             "ex": "lda_x", "ec": "lda_c_pw", "scftol": 1e-300}
+    return make_oracle(setup)
+
+
+def cpu_baseline_single(budget_s=15.0):
+    """Oracle (CPU restatement of the reference; Julia is unavailable) on ONE core: Argon, C2."""
+    o = _oracle_for(18)
+    st = o.initial_state()
+    o.scf_step(st)  # warm-up (includes first-use costs)
+    t0 = time.perf_counter()
+    k = 0
+    while time.perf_counter() - t0 < budget_s:
+        o.scf_step(st)
+        k += 1
+    dt = time.perf_counter() - t0
+    return {"value": k / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{k} SCF iterations of Argon (Z=18, C2 discretization) with the numpy/LAPACK oracle, 1 thread"}
+
+
+_W = {}
+
+
+def _worker_init(Z):
+    _W["o"] = _oracle_for(Z)
+    _W["st"] = _W["o"].initial_state()
+    _W["o"].scf_step(_W["st"])
+    return Z
+
+
+def _worker_step(_):
+    _W["o"].scf_step(_W["st"])
+    return 1
+
+
+def reference_arm(args):
+    """The reference's CPU implementation of the path = the oracle (Julia cannot run here), one
+    atom per host core, every step = one SCF iteration of each core's atom."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    ncore = os.cpu_count() or 1
+    Zs = [18, 36, 54, 86, 10, 26, 47, 79][:ncore] if ncore <= 8 else [(7 * i) % 86 + 1 for i in range(ncore)]
+    ctx = mp.get_context("spawn")
+    pools = [ctx.Pool(1) for _ in Zs]
+    for p, Z in zip(pools, Zs):
+        p.apply_async(_worker_init, (Z,)).get()
+    for _ in range(args.warmup):
+        for r in [p.apply_async(_worker_step, (0,)) for p in pools]:
+            r.get()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for r in [p.apply_async(_worker_step, (0,)) for p in pools]:
+            r.get()
+    dt = time.perf_counter() - t0
+    for p in pools:
+        p.terminate()
+    val = len(Zs) * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "same C2 discretization and LDA model; one atom per host core, Z in %s" % Zs},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": len(Zs), "kind": "port",
+                             "sample": f"{args.steps} steps x {len(Zs)} atoms, numpy/LAPACK oracle (Julia reference cannot run: no julia in the image)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--sweeps", type=int, default=1, help="periodic-table sweeps per GPU (default 1)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,7 +120,8 @@ typedef struct aks_iter_record {
   double t;       /* ODA mixing parameter of the last step                 */
 } aks_iter_record;
 
-/* one scf_step! for every problem still running; out[nprob] may be NULL */
+/* one scf_step! for every problem still running.  With out == NULL the step is only enqueued
+ * on the ctx stream (no host synchronisation); otherwise out[nprob] receives the records.  */
 int aks_scf_step(aks_batch* batch, aks_iter_record* out);
 
 /* solve!: iterate until every problem converged or reached maxiter.  history may be NULL
