@@ -42,7 +42,7 @@ struct aks_batch {
   int B = 0;
   bool fac_in_smem = true;
   double* fac_global = nullptr;
-  size_t smem_pot = 0, smem_eig = 0, smem_dens = 0, smem_poisson = 0;
+  size_t smem_pot = 0, smem_eig = 0, smem_red = 0, smem_dens = 0, smem_poisson = 0;
   std::vector<double> hZ, hN, hHar;
   std::vector<int> hLp, hnhp;
   aks_iter_record* h_rec = nullptr;  // pinned
@@ -184,6 +184,12 @@ extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** 
       ctx->err = "cell maps are not a P1+bubble chain"; delete disc; return AKS_EINVAL;
     }
   if (l2g[1] != -1 || l2g[(size_t)(C - 1) * n] != -1) { ctx->err = "expected Dirichlet ends"; delete disc; return AKS_EINVAL; }
+  for (int c = 0; c < C; ++c)
+    for (int i = 0; i < nb; ++i)
+      if (l2g[(size_t)c * n + 2 + i] != l2g[(size_t)c * n + 2] + i) {
+        ctx->err = "bubble indices of a cell must be contiguous"; delete disc; return AKS_EINVAL;
+      }
+  if (C > 8 * AKS_NW) { ctx->err = "at most 64 cells in this build"; delete disc; return AKS_EINVAL; }
 
   // split global symmetric matrices into cell-owned blocks (first cell containing both indices)
   auto split = [&](const double* Gm, std::vector<double>& loc) {
@@ -283,6 +289,28 @@ extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** 
       offprev = (j + 1 < C - 1) ? S10[j + 1] : 0.0;
     }
   }
+  // inverse Cholesky factor of the bubble mass block of every cell (for k_reduce)
+  std::vector<double> Linv((size_t)C * nb * nb, 0.0);
+  for (int c = 0; c < C; ++c) {
+    std::vector<double> Lm((size_t)nb * nb, 0.0);
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double acc = M0l[((size_t)c * n + 2 + i) * n + 2 + j];
+        for (int k = 0; k < j; ++k) acc -= Lm[(size_t)i * nb + k] * Lm[(size_t)j * nb + k];
+        if (i == j) {
+          if (!(acc > 0.0)) { ctx->err = "mass bubble block not positive definite"; delete disc; return AKS_EINVAL; }
+          Lm[(size_t)i * nb + i] = std::sqrt(acc);
+        } else Lm[(size_t)i * nb + j] = acc / Lm[(size_t)j * nb + j];
+      }
+    double* Lc = Linv.data() + (size_t)c * nb * nb;
+    for (int j = 0; j < nb; ++j) {  // column j of the inverse by forward substitution
+      for (int i = j; i < nb; ++i) {
+        double acc = (i == j) ? 1.0 : 0.0;
+        for (int k = j; k < i; ++k) acc -= Lm[(size_t)i * nb + k] * Lc[(size_t)k * nb + j];
+        Lc[(size_t)i * nb + j] = acc / Lm[(size_t)i * nb + i];
+      }
+    }
+  }
   // Gauss tables
   std::vector<double> Pg((size_t)n * dv.Qs, 0.0), Pgy((size_t)n * G, 0.0), inv1(C), inv2(C);
   for (int g = 0; g < n; ++g) {
@@ -302,7 +330,7 @@ extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** 
   if ((rc = dev_upload(ctx, disc->allocs, vec, &dv.field)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
   UP(Pg, Pg) UP(wv, w) UP(xv, x) UP(inv1, inv1) UP(inv2, inv2) UP(Al, A_loc) UP(M0l, M0_loc) UP(M1l, Mm1_loc)
   UP(M2l, Mm2_loc) UP(M0pk, M0pk) UP(Fl, F_loc) UP(l2g, l2g) UP(yv, y) UP(wyv, wy) UP(ycell, ycell) UP(Pgy, Pgy)
-  UP(Abbinv, Abb_inv) UP(XA, XA) UP(triD, triA_d) UP(triL, triA_l)
+  UP(Abbinv, Abb_inv) UP(XA, XA) UP(triD, triA_d) UP(triL, triA_l) UP(Linv, Linv)
 #undef UP
   *out = disc;
   return AKS_OK;
@@ -359,7 +387,8 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   ZB(double, Bv, B * Nh) ZB(double, Wv, B * Nh) ZB(double, E, B * 5) ZB(double, t, B) ZB(double, stop, B)
   ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk)
   ZB(double, eps, B * s * L * nh) ZB(double, eps_new, B * s * L * nh) ZB(double, U, B * s * L * nh * Nh)
-  ZB(int, eig_info, B * s * L * nh) ZB(int, warm, B) ZB(double, ekin_orb, B * s * L * nh)
+  ZB(int, eig_info, B * s * L * nh) ZB(double, red, B * s * L * C * (6 * (n - 2) + 4))
+  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(int, warm, B) ZB(double, ekin_orb, B * s * L * nh)
   ZB(double, ecou_orb, B * s * L * nh) ZB(double, occ, B * 2 * s * L * nh) ZB(int, degen, B)
   ZB(int, degen_idx, B * 2) ZB(double, degen_n, B * 4) ZB(double, rho_q_new, B * 2 * s * C * Q)
   ZB(double, rho_y_new, B * 2 * s * G) ZB(double, corr_part, B * 2 * C) ZB(double, Bloc_new, B * 2 * C * n)
@@ -373,14 +402,8 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   b.max_degen = 2; b.degen_tol = 1e-3; b.handle_spin = 1;
   // launch configuration
   bt->smem_pot = potential_smem_bytes(dv.n, dv.Q, b.s);
-  bt->smem_eig = eig_smem_bytes(dv.C, dv.npk, dv.Nh, true);
-  bt->fac_in_smem = bt->smem_eig <= 110 * 1024;  // two CTAs per SM; else one big CTA or global scratch
-  if (!bt->fac_in_smem && bt->smem_eig <= 220 * 1024) bt->fac_in_smem = true;
-  if (!bt->fac_in_smem) {
-    bt->smem_eig = eig_smem_bytes(dv.C, dv.npk, dv.Nh, false);
-    const size_t cnt = (size_t)B * s * L * nh * C * dv.npk;
-    if ((rc = dev_zeros<double>(ctx, bt->allocs, cnt, &bt->fac_global)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
-  }
+  bt->smem_eig = eig_smem_bytes(dv.C, dv.nb, dv.Nh);
+  bt->smem_red = reduce_smem_bytes(dv.nb);
   bt->smem_dens = sizeof(double) * ((size_t)AKS_MAXORB * disc->nmax_tpl + (size_t)std::max<int>(dv.n * dv.n * b.s, dv.n * dv.n) + AKS_NW + 8);
   bt->smem_poisson = sizeof(double) * ((size_t)2 * dv.Nh + 3 * dv.C + 16);
   if (bt->smem_pot > 220 * 1024 || bt->smem_eig > 220 * 1024 || bt->smem_dens > 220 * 1024) {
@@ -388,6 +411,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   }
   CK(cudaFuncSetAttribute(k_potential, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
   CK(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
+  CK(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
   CK(cudaFuncSetAttribute(k_eig_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
   CK(cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_poisson));
   CK(cudaFuncSetAttribute(k_dens_cells<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
@@ -477,8 +501,9 @@ static int launch_eig(aks_batch* bt) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   const BatchDev& b = bt->dev;
-  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_eig, ctx->stream>>>(dv, b, bt->fac_global,
-                                                                                     bt->fac_in_smem ? 1 : 0);
+  k_reduce<<<dim3((dv.C + AKS_NW - 1) / AKS_NW, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_red, ctx->stream>>>(dv, b);
+  LAUNCH_CHECK();
+  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_eig, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
   return AKS_OK;
 }
@@ -787,6 +812,16 @@ extern "C" int aks_hartree_energy(aks_batch* bt, int32_t prob, double* Ehar) {
   double acc = 0.0;
   for (int i = 0; i < dv.Nh; ++i) acc += hb[i] * hw[i];
   *Ehar = (acc + bt->hN[prob] * bt->hN[prob] / dv.Rmax) / 2.0;
+  return AKS_OK;
+}
+
+extern "C" int aks_debug_eig_info(aks_batch* bt, int32_t* info) {
+  if (!bt || !info) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  const BatchDev& b = bt->dev;
+  const size_t cnt = (size_t)bt->B * b.s * b.Lmax * b.nhmax;
+  CK(cudaMemcpyAsync(info, b.eig_info, sizeof(int) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
 }
 

@@ -34,6 +34,7 @@ struct DiscDev {
   const double* XA;      // [C][2][nb]   A_bb^{-1} A_bh
   const double* triA_d;  // [C-1] LDL^T of the hat Schur complement
   const double* triA_l;  // [C-1]
+  const double* Linv;    // [C][nb][nb] inverse Cholesky factor of the bubble mass block (lower, row-major)
 };
 
 struct BatchDev {
@@ -62,6 +63,9 @@ struct BatchDev {
   double* eps_new;   // [B][s][Lmax][nhmax]  written by k_eig, committed by k_aufbau
   double* U;         // [B][s][Lmax][nhmax][Nh]
   int* eig_info;     // [B][s][Lmax][nhmax]  (counts<<8 | rqi its) diagnostics
+  double* red;       // [B][s][Lmax][C][red_stride]  per-cell tridiagonal reduction of the pencil
+  double* Pm;        // [B][s][Lmax][C][nb*nb]  P = Q^T L^-1
+  double* Pt;        // [B][s][Lmax][C][nb*nb]  P^T
   int* warm;         // [B]  1 once eps/U hold a previous solution
   double* ekin_orb;  // [B][s][Lmax][nhmax]
   double* ecou_orb;  // [B][s][Lmax][nhmax]

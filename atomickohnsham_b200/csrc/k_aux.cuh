@@ -93,24 +93,15 @@ __global__ void __launch_bounds__(AKS_NT) k_eig_residual(DiscDev d, BatchDev b, 
   extern __shared__ double sm[];
   const int C = d.C, npk = d.npk, Nh = d.Nh, n = d.n, nb = d.nb;
   EigShared S;
-  double* ptr = sm;
-  S.fac = nullptr;
-  S.vx = ptr; ptr += Nh;
-  S.vr = ptr; ptr += Nh;
-  S.vy = ptr; ptr += Nh;
-  S.hatpart = ptr; ptr += 2 * C;
-  S.tri_d = ptr; ptr += C;
-  S.tri_l = ptr; ptr += C;
-  S.xh = ptr; ptr += C;
-  S.red = ptr; ptr += AKS_NW + 8;
-  S.negc = (int*)ptr;
+  eig_carve(d, sm, S);
+  __syncthreads();
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
   const double* Hpk = b.Hpk + chan * C * npk;
   const double* u = b.U + (chan * b.nhmax + k) * Nh;
   const double lam = b.eps_new[chan * b.nhmax + k];
   for (int i = threadIdx.x; i < Nh; i += blockDim.x) S.vx[i] = u[i];
   __syncthreads();
-  eig_apply(d, S, d.M0_loc, S.vx, S.vr);  // vr = M u
+  eig_apply(d.n, C, S.hatg, S.bub0, S.hatpart, d.M0_loc, S.vx, S.vr);  // vr = M u
   // vy = H u with the packed blocks
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int c = warp; c < C; c += AKS_NW) {
@@ -130,14 +121,14 @@ __global__ void __launch_bounds__(AKS_NT) k_eig_residual(DiscDev d, BatchDev b, 
   }
   __syncthreads();
   for (int j = threadIdx.x; j < C - 1; j += blockDim.x)
-    S.vy[d.l2g[j * n + 0]] = S.hatpart[2 * j] + S.hatpart[2 * (j + 1) + 1];
+    S.vy[S.hatg[j]] = S.hatpart[2 * j] + S.hatpart[2 * (j + 1) + 1];
   __syncthreads();
   double acc = 0.0;
   for (int i = threadIdx.x; i < Nh; i += blockDim.x) {
     const double r = S.vy[i] - lam * S.vr[i];
     acc = fma(r, r, acc);
   }
-  acc = block_sum(acc, S.red);
+  acc = block_sum(acc, S.red8);
   if (threadIdx.x == 0) out[(size_t)ch * b.nhmax + k] = sqrt(acc);
 }
 

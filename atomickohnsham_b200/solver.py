@@ -202,6 +202,14 @@ class Batch:
         self.ctx.check(_capi.lib.aks_hartree_energy(self.h, prob, C.byref(v)))
         return v.value
 
+    def eig_info(self):
+        """(counts, rqi_its, not_converged) arrays of shape (nprob, nspin, L, nh) for the last step."""
+        d = self.disc
+        info = np.zeros(self.nprob * d.nspin * (d.lh + 1) * d.nh, dtype=np.int32)
+        self.ctx.check(_capi.lib.aks_debug_eig_info(self.h, _capi.i32ptr(info)))
+        info = info.reshape(self.nprob, d.nspin, d.lh + 1, d.nh)
+        return info >> 8, info & 0x7f, (info & 0x80) != 0
+
     def phase_ms(self):
         out = (C.c_double * 8)()
         rc = _capi.lib.aks_last_phase_ms(self.h, out)

@@ -154,6 +154,10 @@ int aks_exc_energy(aks_batch* batch, int32_t prob, double* Exc);
 /* compute_hartree_energy (energies.jl:96-114) of the current D                            */
 int aks_hartree_energy(aks_batch* batch, int32_t prob, double* Ehar);
 
+/* eigensolver diagnostics of the last step: info[nprob*nspin*L*nh], device order [prob][sigma][l][k];
+ * each word = (inertia counts << 8) | (0x80 if RQI did not converge) | RQI iterations       */
+int aks_debug_eig_info(aks_batch* batch, int32_t* info);
+
 /* ---- measurement aids --------------------------------------------------------------------*/
 /* number of kernels launched by this ctx so far (bench.py "gpu_launches")                 */
 int64_t aks_launch_count(const aks_ctx* ctx);

@@ -56,7 +56,8 @@ def test_step_level_parity_identical_D(name):
     eps_g, U_g, res = bt.eig_lowest(0)                            # find_orbital!
     U_o, eps_o = o.find_orbital(Har_o, Vxc_o)
     scale = max(1.0, float(np.max(np.abs(eps_o))))
-    assert res.max() < 1e-12 * scale, "GPU eigen-residual"
+    # eigenvector error = reduction error / relative gap: residual allowance 1e-10
+    assert res.max() < 1e-10 * scale, "GPU eigen-residual"
     # LAPACK allowance: eps * ||M0^-1 H|| ~ 1e-8 absolute at order 20
     assert np.max(np.abs(eps_g - eps_o)) < 5e-8
     M0 = o.tb.M0
@@ -88,9 +89,9 @@ def test_trajectory_parity(name):
     assert f["status"] == 1
     # total energy within 1e-10 relative (north star)
     assert abs(f["Etot"] - so.energies.Etot) <= 1e-10 * abs(so.energies.Etot)
-    # iteration 0 has no line search: every energy to 1e-11 relative
+    # iteration 0 has no line search: every energy to 1e-10 relative (sum n*eps carries LAPACK's error)
     for k in ("Etot", "Ekin", "Ecou", "Ehar", "Eexc"):
-        assert abs(hist[0][0][k] - ho[0][k]) <= 1e-11 * max(1.0, abs(ho[0][k])), k
+        assert abs(hist[0][0][k] - ho[0][k]) <= 1e-10 * max(1.0, abs(ho[0][k])), k
     # iteration count: reported against the oracle; the Brent tail is chaotic
     assert abs(f["niter"] - so.niter) <= 8
     sg = bt.state(0, want_D=False, want_U=False)
