@@ -57,7 +57,7 @@ EXPORTS = ["aks_ctx_create", "aks_ctx_destroy", "aks_last_error", "aks_ctx_strea
            "aks_batch_set_oda", "aks_batch_reset", "aks_scf_step", "aks_scf_run", "aks_get_state",
            "aks_set_density", "aks_assemble_hartree", "aks_assemble_vxc", "aks_eig_lowest",
            "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak",
-           "aks_last_phase_ms", "aks_debug_eig_info"]
+           "aks_last_phase_ms", "aks_debug_eig_info", "aks_debug_eig_cycles"]
 
 
 def _load():
@@ -96,6 +96,7 @@ def _load():
     lib.aks_measure_fp64_peak.argtypes = [vp, _dp]
     lib.aks_last_phase_ms.argtypes = [vp, _dp]
     lib.aks_debug_eig_info.argtypes = [vp, _i32p]
+    lib.aks_debug_eig_cycles.argtypes = [vp, _ip]
     return lib
 
 

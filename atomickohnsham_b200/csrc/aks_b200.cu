@@ -42,7 +42,7 @@ struct aks_batch {
   int B = 0;
   bool fac_in_smem = true;
   double* fac_global = nullptr;
-  size_t smem_pot = 0, smem_eig = 0, smem_red = 0, smem_dens = 0, smem_poisson = 0;
+  size_t smem_pot = 0, smem_eig = 0, smem_red = 0, smem_chan = 0, smem_dens = 0, smem_poisson = 0;
   std::vector<double> hZ, hN, hHar;
   std::vector<int> hLp, hnhp;
   aks_iter_record* h_rec = nullptr;  // pinned
@@ -385,11 +385,11 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
 #define ZB(T, field, count) if ((rc = dev_zeros<T>(ctx, bt->allocs, (count), &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
   ZB(double, Dd, B * s * Nh * Nh) ZB(double, rho_q, B * s * C * Q) ZB(double, rho_y, B * s * G)
   ZB(double, Bv, B * Nh) ZB(double, Wv, B * Nh) ZB(double, E, B * 5) ZB(double, t, B) ZB(double, stop, B)
-  ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk)
+  ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk) ZB(double, Hfull, B * s * L * C * n * n)
   ZB(double, eps, B * s * L * nh) ZB(double, eps_new, B * s * L * nh) ZB(double, U, B * s * L * nh * Nh)
-  ZB(int, eig_info, B * s * L * nh) ZB(double, red, B * s * L * C * (6 * (n - 2) + 4))
-  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(int, warm, B) ZB(double, ekin_orb, B * s * L * nh)
-  ZB(double, ecou_orb, B * s * L * nh) ZB(double, occ, B * 2 * s * L * nh) ZB(int, degen, B)
+  ZB(int, eig_info, B * s * L * nh) ZB(long long, eig_dbg, B * s * L * nh * 8) ZB(double, red, B * s * L * C * (6 * (n - 2) + 4))
+  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * ((C + EIGC_CHUNK - 1) / EIGC_CHUNK) * 4) ZB(int, warm, B) ZB(double, ekin_orb, B * s * L * nh)
+  ZB(double, ecou_orb, B * s * L * nh) ZB(double, occ, B * 2 * s * L * nh) ZB(int, degen, B) ZB(int, occ_cnt, B * 2) ZB(int, occ_elk, B * 2 * AKS_MAXORB) ZB(double, occ_n, B * 2 * AKS_MAXORB)
   ZB(int, degen_idx, B * 2) ZB(double, degen_n, B * 4) ZB(double, rho_q_new, B * 2 * s * C * Q)
   ZB(double, rho_y_new, B * 2 * s * G) ZB(double, corr_part, B * 2 * C) ZB(double, Bloc_new, B * 2 * C * n)
   ZB(double, B_new, B * 2 * Nh) ZB(double, W_new, B * 2 * Nh) ZB(double, scal, B * 2 * 4) ZB(double, td, B)
@@ -404,6 +404,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   bt->smem_pot = potential_smem_bytes(dv.n, dv.Q, b.s);
   bt->smem_eig = eig_smem_bytes(dv.C, dv.nb, dv.Nh);
   bt->smem_red = reduce_smem_bytes(dv.nb);
+  bt->smem_chan = eig_chan_smem_bytes(dv.n, dv.nb);
   bt->smem_dens = sizeof(double) * ((size_t)AKS_MAXORB * disc->nmax_tpl + (size_t)std::max<int>(dv.n * dv.n * b.s, dv.n * dv.n) + AKS_NW + 8);
   bt->smem_poisson = sizeof(double) * ((size_t)2 * dv.Nh + 3 * dv.C + 16);
   if (bt->smem_pot > 220 * 1024 || bt->smem_eig > 220 * 1024 || bt->smem_dens > 220 * 1024) {
@@ -412,7 +413,8 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   CK(cudaFuncSetAttribute(k_potential, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
   CK(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
   CK(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
-  CK(cudaFuncSetAttribute(k_eig_residual, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
+  CK(cudaFuncSetAttribute(k_eig_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_chan));
+  CK(cudaFuncSetAttribute(k_eig_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_chan));
   CK(cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_poisson));
   CK(cudaFuncSetAttribute(k_dens_cells<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
   CK(cudaFuncSetAttribute(k_dens_cells<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
@@ -503,7 +505,14 @@ static int launch_eig(aks_batch* bt) {
   const BatchDev& b = bt->dev;
   k_reduce<<<dim3((dv.C + AKS_NW - 1) / AKS_NW, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_red, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
+  k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b);
+  LAUNCH_CHECK();
   k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_eig, ctx->stream>>>(dv, b);
+  LAUNCH_CHECK();
+  const int nchunk = (dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK;
+  k_eig_final<<<dim3(nchunk, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b);
+  LAUNCH_CHECK();
+  k_eig_scale<<<dim3(b.Lmax * b.s, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b, nchunk);
   LAUNCH_CHECK();
   return AKS_OK;
 }
@@ -539,7 +548,7 @@ static int step_launch(aks_batch* bt) {
   TICK();
   if ((rc = launch_eig(bt)) != AKS_OK) return rc;
   TICK();
-  k_aufbau<<<(bt->B + 63) / 64, 64, 0, ctx->stream>>>(dv, b);
+  k_aufbau<<<bt->B, 32, 0, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
   k_orb_energy<<<dim3(b.s * b.Lmax * b.nhmax, bt->B), 32, 0, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
@@ -549,7 +558,7 @@ static int step_launch(aks_batch* bt) {
   k_poisson<<<dim3(bt->B, 2), 128, bt->smem_poisson, ctx->stream>>>(dv, b, 0, 0);
   LAUNCH_CHECK();
   TICK();
-  k_linesearch<<<bt->B, AKS_NT, 0, ctx->stream>>>(dv, b);
+  k_linesearch<<<bt->B, LS_NT, 0, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
   TICK();
   {
@@ -771,7 +780,7 @@ extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* 
     double* dres = nullptr;
     CK(cudaMalloc((void**)&dres, sizeof(double) * s * L * nh));
     CK(cudaMemsetAsync(dres, 0, sizeof(double) * s * L * nh, ctx->stream));
-    k_eig_residual<<<dim3(nh, L * s), AKS_NT, bt->smem_eig, ctx->stream>>>(dv, b, prob, dres);
+    k_eig_residual<<<dim3(nh, L * s), AKS_NT, sizeof(double) * (3 * Nh + 2 * dv.C + AKS_NW + 8) + sizeof(int) * 2 * dv.C, ctx->stream>>>(dv, b, prob, dres);
     LAUNCH_CHECK();
     CK(cudaMemcpyAsync(hr.data(), dres, sizeof(double) * s * L * nh, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -812,6 +821,16 @@ extern "C" int aks_hartree_energy(aks_batch* bt, int32_t prob, double* Ehar) {
   double acc = 0.0;
   for (int i = 0; i < dv.Nh; ++i) acc += hb[i] * hw[i];
   *Ehar = (acc + bt->hN[prob] * bt->hN[prob] / dv.Rmax) / 2.0;
+  return AKS_OK;
+}
+
+extern "C" int aks_debug_eig_cycles(aks_batch* bt, int64_t* out) {
+  if (!bt || !out) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  const BatchDev& b = bt->dev;
+  const size_t cnt = (size_t)bt->B * b.s * b.Lmax * b.nhmax * 8;
+  CK(cudaMemcpyAsync(out, b.eig_dbg, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
 }
 

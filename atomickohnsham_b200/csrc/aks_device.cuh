@@ -4,6 +4,8 @@
 //   src/physics/exchange correlation/SlaterXa.jl:11-30   (Slater exchange)
 //   src/physics/exchange correlation/PerdewWang.jl:15-101 (PW92 correlation)
 //   src/physics/exchange correlation/BuiltinFunctional.jl:74-142 (clamp at 0, zero at rho = 0)
+// x^(1/3), x^(3/2), x^(4/3) are evaluated as cbrt(x), x*sqrt(x), x*cbrt(x) (the reference calls pow);
+// the results differ by <= 1-2 ulp, far inside the 1e-10 parity tolerance.
 // Brent follows Optim.jl's `Brent()` as called from
 //   src/algorithms/optimization/line_search.jl:59-67.
 #pragma once
@@ -60,7 +62,7 @@ __device__ __forceinline__ PwPar pw_pa() { return {0.016887, 0.11125, 10.357, 3.
 // G(rs) and dG/drs (PerdewWang.jl:15-27)
 __device__ __forceinline__ void pw_G(double rs, const PwPar& P, double& G, double& dG) {
   const double sq = sqrt(rs);
-  const double rs32 = pow(rs, 1.5);
+  const double rs32 = rs * sq;
   const double Q0 = -2.0 * P.A * (1.0 + P.a1 * rs);
   const double dQ0 = -2.0 * P.A * P.a1;
   const double Q1 = 2.0 * P.A * (P.b1 * sq + P.b2 * rs + P.b3 * rs32 + P.b4 * (rs * rs));
@@ -71,7 +73,7 @@ __device__ __forceinline__ void pw_G(double rs, const PwPar& P, double& G, doubl
 }
 
 __device__ __forceinline__ double rs_of_rho(double rho) {
-  return pow(3.0 / (c_xc.fourpi * rho), c_xc.third);
+  return cbrt(3.0 / (c_xc.fourpi * rho));
 }
 
 // ---------------------------------------------------------------- unpolarised
@@ -85,7 +87,7 @@ __device__ __forceinline__ double xc_vrho_unpol(double rho, int ex, int ec) {
     pw_G(rs, pw_p0(), G, dG);
     v += G - rs / 3.0 * dG;
   }
-  if (ex == 1) v += -c_xc.cx * pow(rho, c_xc.third);
+  if (ex == 1) v += -c_xc.cx * cbrt(rho);
   return v;
 }
 // exc per particle = ex + ec
@@ -97,16 +99,16 @@ __device__ __forceinline__ double xc_zk_unpol(double rho, int ex, int ec) {
     pw_G(rs_of_rho(rho), pw_p0(), G, dG);
     e += G;
   }
-  if (ex == 1) e += -c_xc.cx34 * pow(rho, c_xc.third);
+  if (ex == 1) e += -c_xc.cx34 * cbrt(rho);
   return e;
 }
 
 // ---------------------------------------------------------------- polarised
 __device__ __forceinline__ double pw_fz(double z) {
-  return (pow(1.0 + z, c_xc.four3) + pow(1.0 - z, c_xc.four3) - 2.0) / c_xc.two43m2;
+  return ((1.0 + z) * cbrt(1.0 + z) + (1.0 - z) * cbrt(1.0 - z) - 2.0) / c_xc.two43m2;
 }
 __device__ __forceinline__ double pw_dfz(double z) {
-  return c_xc.four3 * (pow(1.0 + z, c_xc.third) - pow(1.0 - z, c_xc.third)) / c_xc.two43m2;
+  return c_xc.four3 * (cbrt(1.0 + z) - cbrt(1.0 - z)) / c_xc.two43m2;
 }
 
 __device__ __forceinline__ void xc_vrho_pol(double ru, double rd, int ex, int ec, double& vu,
@@ -133,8 +135,8 @@ __device__ __forceinline__ void xc_vrho_pol(double ru, double rd, int ex, int ec
     vd += common - (1.0 + z) * decdz;
   }
   if (ex == 1) {
-    vu += (ru > 0.0) ? -c_xc.cx * pow(2.0 * ru, c_xc.third) : 0.0;
-    vd += (rd > 0.0) ? -c_xc.cx * pow(2.0 * rd, c_xc.third) : 0.0;
+    vu += (ru > 0.0) ? -c_xc.cx * cbrt(2.0 * ru) : 0.0;
+    vd += (rd > 0.0) ? -c_xc.cx * cbrt(2.0 * rd) : 0.0;
   }
 }
 
@@ -153,7 +155,7 @@ __device__ __forceinline__ double xc_zk_pol(double ru, double rd, int ex, int ec
     const double z4 = z * z * z * z;
     e += e0 + (-ea) * (f / c_xc.f2p0) * (1.0 - z4) + (e1 - e0) * f * z4;
   }
-  if (ex == 1) e += -c_xc.cx6_34 * (pow(ru, c_xc.four3) + pow(rd, c_xc.four3)) / rho;
+  if (ex == 1) e += -c_xc.cx6_34 * (ru * cbrt(ru) + rd * cbrt(rd)) / rho;
   return e;
 }
 

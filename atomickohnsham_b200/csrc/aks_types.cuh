@@ -58,19 +58,26 @@ struct BatchDev {
   int* status;    // [B]
   // per-iteration work
   double* fxc;       // [B][s][C][Q]   w_q * vxc_sigma(rho(q))
-  double* Hpk;       // [B][s][Lmax][C][npk]
+  double* Hpk;       // [B][s][Lmax][C][npk]  packed lower blocks (k_reduce)
+  double* Hfull;     // [B][s][Lmax][C][n*n]  the same blocks, full symmetric (mat-vecs in k_eig)
   double* eps;       // [B][s][Lmax][nhmax]
   double* eps_new;   // [B][s][Lmax][nhmax]  written by k_eig, committed by k_aufbau
   double* U;         // [B][s][Lmax][nhmax][Nh]
   int* eig_info;     // [B][s][Lmax][nhmax]  (counts<<8 | rqi its) diagnostics
+  long long* eig_dbg; // [B][s][Lmax][nhmax][8] cycle counters (filled only with -DAKS_EIG_TIMING)
   double* red;       // [B][s][Lmax][C][red_stride]  per-cell tridiagonal reduction of the pencil
   double* Pm;        // [B][s][Lmax][C][nb*nb]  P = Q^T L^-1
   double* Pt;        // [B][s][Lmax][C][nb*nb]  P^T
+  double* eig_part;  // [B][s][Lmax][nhmax][nchunk][4]  per-chunk x^T M x, x^T H x, sign sum
+  double* Xt;        // [B][s][Lmax][nhmax][nb*C + C]  eigenvectors in reduced coordinates (t | h)
   int* warm;         // [B]  1 once eps/U hold a previous solution
   double* ekin_orb;  // [B][s][Lmax][nhmax]
   double* ecou_orb;  // [B][s][Lmax][nhmax]
   double* occ;       // [B][2][s][Lmax][nhmax]  slot 0: final / first extreme, slot 1: second extreme
   int* degen;        // [B]  1 when the two-fold branch is active this iteration
+  int* occ_cnt;      // [B][2]            number of occupied orbitals per slot
+  int* occ_elk;      // [B][2][MAXORB]    packed (e<<16 | l<<8 | k), density! order (sigma, k, l)
+  double* occ_n;     // [B][2][MAXORB]    their occupations
   int* degen_idx;    // [B][2]  orbital offsets (into [s][Lmax][nhmax]) of the block
   double* degen_n;   // [B][4]  n1_0, n2_0, n1_1, n2_1
   double* rho_q_new; // [B][2][s][C][Q]

@@ -85,50 +85,54 @@ __global__ void __launch_bounds__(AKS_NT) k_exc_state(DiscDev d, BatchDev b, int
   if (threadIdx.x == 0) out[0] = v;
 }
 
-// ||(H - eps M0) u||_2 for every eigenpair of problem p (diagnostic of aks_eig_lowest)
+// out = (unassembled SYMMETRIC operator [C][n][n]) * in   (vectors in the original numbering)
+__device__ __noinline__ void dense_apply(int n, int C, const int* hatg, const int* bub0, double* hatpart,
+                                         const double* __restrict__ mat, const double* in, double* out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < C; c += AKS_NW) {
+    int gi = -1;
+    if (lane >= 2 && lane < n) gi = bub0[c] + lane - 2;
+    else if (lane == 0 && c < C - 1) gi = hatg[c];
+    else if (lane == 1 && c > 0) gi = hatg[c - 1];
+    const double xl = (gi >= 0) ? in[gi] : 0.0;
+    const double r = warp_colmatvec(mat + (size_t)c * n * n, n, n, lane, lane < n, xl);
+    if (lane >= 2 && gi >= 0) out[gi] = r;
+    if (lane < 2) hatpart[2 * c + lane] = r;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < C - 1; j += blockDim.x) out[hatg[j]] = hatpart[2 * j] + hatpart[2 * (j + 1) + 1];
+  __syncthreads();
+}
+
+// ||(H - eps M0) u||_2 for every eigenpair of problem p (diagnostic of aks_eig_lowest), original blocks
 __global__ void __launch_bounds__(AKS_NT) k_eig_residual(DiscDev d, BatchDev b, int p, double* out) {
   const int k = blockIdx.x, ch = blockIdx.y;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
   if (l >= b.Lp[p] || k >= b.nhp[p]) return;
   extern __shared__ double sm[];
-  const int C = d.C, npk = d.npk, Nh = d.Nh, n = d.n, nb = d.nb;
-  EigShared S;
-  eig_carve(d, sm, S);
-  __syncthreads();
+  const int C = d.C, Nh = d.Nh, n = d.n;
+  double* vu = sm;            // [Nh]
+  double* vm = vu + Nh;       // [Nh]
+  double* vh = vm + Nh;       // [Nh]
+  double* hatpart = vh + Nh;  // [2C]
+  double* red8 = hatpart + 2 * C;
+  int* hatg = (int*)(red8 + AKS_NW + 8);
+  int* bub0 = hatg + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { hatg[c] = (c < C - 1) ? d.l2g[c * n] : 0; bub0[c] = d.l2g[c * n + 2]; }
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
-  const double* Hpk = b.Hpk + chan * C * npk;
+  const double* Hfull = b.Hfull + chan * C * (size_t)n * n;
   const double* u = b.U + (chan * b.nhmax + k) * Nh;
   const double lam = b.eps_new[chan * b.nhmax + k];
-  for (int i = threadIdx.x; i < Nh; i += blockDim.x) S.vx[i] = u[i];
+  for (int i = threadIdx.x; i < Nh; i += blockDim.x) vu[i] = u[i];
   __syncthreads();
-  eig_apply(d.n, C, S.hatg, S.bub0, S.hatpart, d.M0_loc, S.vx, S.vr);  // vr = M u
-  // vy = H u with the packed blocks
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c = warp; c < C; c += AKS_NW) {
-    const int gi = (lane < n) ? d.l2g[c * n + lane] : -1;
-    const double xl = (gi >= 0) ? S.vx[gi] : 0.0;
-    const double* Hc = Hpk + (size_t)c * npk;
-    double r = 0.0;
-    for (int a = 0; a < n; ++a) {
-      const double xa = __shfl_sync(0xffffffffu, xl, a);
-      if (lane < n) {
-        const int hi = (lane >= a) ? lane : a, lo = (lane >= a) ? a : lane;
-        r = fma(Hc[pk_index(hi, lo, nb)], xa, r);
-      }
-    }
-    if (lane >= 2 && gi >= 0) S.vy[gi] = r;
-    if (lane < 2) S.hatpart[2 * c + lane] = r;
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < C - 1; j += blockDim.x)
-    S.vy[S.hatg[j]] = S.hatpart[2 * j] + S.hatpart[2 * (j + 1) + 1];
-  __syncthreads();
+  dense_apply(n, C, hatg, bub0, hatpart, d.M0_loc, vu, vm);
+  dense_apply(n, C, hatg, bub0, hatpart, Hfull, vu, vh);
   double acc = 0.0;
   for (int i = threadIdx.x; i < Nh; i += blockDim.x) {
-    const double r = S.vy[i] - lam * S.vr[i];
+    const double r = vh[i] - lam * vm[i];
     acc = fma(r, r, acc);
   }
-  acc = block_sum(acc, S.red8);
+  acc = block_sum(acc, red8);
   if (threadIdx.x == 0) out[(size_t)ch * b.nhmax + k] = sqrt(acc);
 }
 

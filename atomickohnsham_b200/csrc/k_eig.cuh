@@ -18,6 +18,10 @@
 //         the visited shifts are kept as witnesses and the converged pair is CERTIFIED as
 //         eigenvalue number k (count == k just below, == k+1 just above);
 //       cold path / failed certificate: bracket, bisect until isolated and narrow, same RQI.
+//     The whole iteration runs in the reduced coordinates (hats, x~): M~ = [M_hh m~^T; m~ I] and
+//     H~ = [H_hh h~^T; h~ T] act in O(nb) per cell too, so a factorisation, a solve and a mass
+//     product are all thread-per-cell sweeps over shared memory.  Dense (nb x nb) products with P
+//     appear only twice per eigenpair: x~ = P M_bb x_b for the warm start, x_b = P^T x~ at the end.
 //     The returned eigenvalue is the Rayleigh quotient with the ORIGINAL blocks (second-order
 //     accurate in the vector), so the O(eps*cond(M_bb)) error of the reduction does not reach it;
 //     eigenvectors carry that error divided by the relative gap (~1e-13).
@@ -168,14 +172,15 @@ k_reduce(DiscDev d, BatchDev b) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Vectors in reduced coordinates: hats h[C] (h[j] = hat node j, j < C-1) and bubbles t[nb][C]
+// (field-major: t[j*C + c] = j-th transformed bubble coefficient of cell c).
+struct RedVec { double* h; double* t; };
+
 struct EigShared {
   double* red;      // [red_stride][C]  reduced cell data (field-major)
   double* mhh;      // [3][C]           M hat-hat blocks
   double* fac;      // [4 nb][C]        dinv[nb] | l[nb] | W0[nb] | W1[nb]
-  double* zt;       // [nb][C]          transformed bubble vectors
-  double* vx;       // [Nh]
-  double* vr;       // [Nh]  r = M x
-  double* vy;       // [Nh]
+  RedVec x, r, y;   // iterate, r = M~ x, solve output
   double* hatpart;  // [2C]
   double* sc;       // [3C]  Schur blocks of the current factorisation
   double* tri_di;   // [C]   reciprocal pivots of the hat system
@@ -188,7 +193,7 @@ struct EigShared {
 };
 
 __host__ __device__ inline size_t eig_smem_bytes(int C, int nb, int Nh) {
-  size_t nd = (size_t)red_stride(nb) * C + 3 * C + (size_t)4 * nb * C + (size_t)nb * C + 3 * (size_t)Nh +
+  size_t nd = (size_t)red_stride(nb) * C + 3 * C + (size_t)4 * nb * C + 3 * ((size_t)nb * C + C) +
               2 * C + 3 * C + 3 * C + AKS_NW + 8;
   return nd * sizeof(double) + (size_t)(3 * C + 8) * sizeof(int);
 }
@@ -249,65 +254,86 @@ __device__ __forceinline__ int eig_factor(const EigShared& S, int C, int nb, dou
     S.negc[c] = neg;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int neg = 0;
-    for (int cc = 0; cc < C; ++cc) neg += S.negc[cc];
-    // hat node j sits between cell j (its right hat, g=0) and cell j+1 (its left hat, g=1)
-    double dinvp = 0.0, offprev = 0.0, scale = 0.0;
-    for (int j = 0; j < C - 1; ++j) {
-      const double diag = S.sc[3 * j] + S.sc[3 * (j + 1) + 2];
-      scale = fmax(scale, fabs(diag));
-      double l = 0.0, dj = diag;
-      if (j > 0) { l = offprev * dinvp; dj = diag - l * offprev; }
-      const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
-      if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
-      neg += (dj < 0.0);
-      dinvp = 1.0 / dj;
-      S.tri_di[j] = dinvp;
-      if (j > 0) S.tri_l[j - 1] = l;
-      offprev = (j + 1 < C - 1) ? S.sc[3 * (j + 1) + 1] : 0.0;
+  // hat node j sits between cell j (its right hat, g=0) and cell j+1 (its left hat, g=1).
+  // Twisted factorisation: thread 0 eliminates downwards j = 0..tw-1, thread 32 upwards j = m-1..tw+1,
+  // they meet at the twist index tw; inertia = negatives of both sweeps + sign of the twist pivot.
+  {
+    const int m = C - 1, tw = m / 2;
+    if (threadIdx.x == 0) {
+      int neg = 0;
+      for (int cc = 0; cc < C; ++cc) neg += S.negc[cc];
+      double dinvp = 0.0, offprev = 0.0, scale = 0.0;
+      for (int j = 0; j < tw; ++j) {
+        const double diag = S.sc[3 * j] + S.sc[3 * (j + 1) + 2];
+        scale = fmax(scale, fabs(diag));
+        double l = 0.0, dj = diag;
+        if (j > 0) { l = offprev * dinvp; dj = diag - l * offprev; }
+        const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
+        if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
+        neg += (dj < 0.0);
+        dinvp = 1.0 / dj;
+        S.tri_di[j] = dinvp;
+        if (j > 0) S.tri_l[j - 1] = l;
+        offprev = S.sc[3 * (j + 1) + 1];
+      }
+      S.xh[0] = (tw > 0) ? offprev * dinvp * offprev : 0.0;
+      if (tw > 0) S.tri_l[tw - 1] = offprev * dinvp;
+      S.negc[C] = neg;
+    } else if (threadIdx.x == 32) {
+      int neg = 0;
+      double dinvn = 0.0, offnext = 0.0, scale = 0.0;
+      for (int j = m - 1; j > tw; --j) {
+        const double diag = S.sc[3 * j] + S.sc[3 * (j + 1) + 2];
+        scale = fmax(scale, fabs(diag));
+        double u = 0.0, dj = diag;
+        if (j < m - 1) { u = offnext * dinvn; dj = diag - u * offnext; }
+        const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
+        if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
+        neg += (dj < 0.0);
+        dinvn = 1.0 / dj;
+        S.tri_di[j] = dinvn;
+        if (j < m - 1) S.tri_l[j] = u;
+        offnext = S.sc[3 * j + 1];
+      }
+      S.xh[1] = (tw < m - 1) ? offnext * dinvn * offnext : 0.0;
+      if (tw < m - 1) S.tri_l[tw] = offnext * dinvn;
+      S.negc[C + 1] = neg;
     }
-    S.negc[C] = neg;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const double diag = S.sc[3 * tw] + S.sc[3 * (tw + 1) + 2];
+      double g = diag - S.xh[0] - S.xh[1];
+      const double pivmin = fmax(fabs(diag) * 4.9e-32, DBL_MIN * 1e8);
+      if (fabs(g) < pivmin) g = (g < 0.0) ? -pivmin : pivmin;
+      S.tri_di[tw] = 1.0 / g;
+      S.negc[C] += S.negc[C + 1] + (g < 0.0);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   return S.negc[C];
 }
 
-// ---- y = T(sigma)^{-1} r with the stored factors (r in S.vr, y to S.vy)
-__device__ __forceinline__ void eig_solve(const EigShared& S, int C, int nb, const double* __restrict__ Pm,
-                                          const double* __restrict__ Pt) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // A. r~ = P r_b  (warp per cell; P^T storage makes lane i's reads contiguous)
-  for (int c = warp; c < C; c += AKS_NW) {
-    const double rb = (lane < nb) ? S.vr[S.bub0[c] + lane] : 0.0;
-    const double* Ptc = Pt + (size_t)c * nb * nb;
-    double acc = 0.0;
-    for (int j = 0; j < nb; ++j) {
-      const double rj = __shfl_sync(0xffffffffu, rb, j);
-      if (lane < nb) acc = fma(Ptc[j * nb + lane], rj, acc);
-    }
-    if (lane < nb) S.zt[lane * C + c] = acc;
-  }
-  __syncthreads();
-  // B. thread per cell: z = (T - sI)^-1 r~ ; hat partials W^T r~
+// ---- y = T~(sigma)^{-1} r in reduced coordinates with the stored factors
+__device__ __forceinline__ void eig_solve(const EigShared& S, int C, int nb) {
+  // B. thread per cell: z = (T - sI)^-1 r_b ; hat partials W^T r_b
   {
     const int c = threadIdx.x;
     if (c < C) {
       const double* F = S.fac;
       double t0 = 0.0, t1 = 0.0, zp = 0.0;
       for (int j = 0; j < nb; ++j) {
-        const double rj = S.zt[j * C + c];
+        const double rj = S.r.t[j * C + c];
         t0 = fma(F[(2 * nb + j) * C + c], rj, t0);
         t1 = fma(F[(3 * nb + j) * C + c], rj, t1);
         const double z = rj - F[(nb + j) * C + c] * zp;
-        S.zt[j * C + c] = z;
+        S.y.t[j * C + c] = z;
         zp = z;
       }
       double zn = 0.0;
       for (int j = nb - 1; j >= 0; --j) {
-        double z = S.zt[j * C + c] * F[j * C + c];
+        double z = S.y.t[j * C + c] * F[j * C + c];
         if (j < nb - 1) z -= F[(nb + j + 1) * C + c] * zn;
-        S.zt[j * C + c] = z;
+        S.y.t[j * C + c] = z;
         zn = z;
       }
       S.hatpart[2 * c] = t0;
@@ -315,114 +341,123 @@ __device__ __forceinline__ void eig_solve(const EigShared& S, int C, int nb, con
     }
   }
   __syncthreads();
-  // C. hat system
-  if (threadIdx.x == 0) {
-    const int m = C - 1;
-    double zprev = 0.0;
-    for (int j = 0; j < m; ++j) {
-      double rh = S.vr[S.hatg[j]] - S.hatpart[2 * j] - S.hatpart[2 * (j + 1) + 1];
-      if (j > 0) rh -= S.tri_l[j - 1] * zprev;
-      S.xh[j] = rh;
-      zprev = rh;
+  // C. hat system, twisted substitution (thread 0 from the top, thread 32 from the bottom)
+  {
+    const int m = C - 1, tw = m / 2;
+    if (threadIdx.x == 0) {
+      double zprev = 0.0;
+      for (int j = 0; j <= tw; ++j) {
+        double rh = S.r.h[j] - S.hatpart[2 * j] - S.hatpart[2 * (j + 1) + 1];
+        if (j > 0) rh -= S.tri_l[j - 1] * zprev;
+        if (j < tw) { S.xh[j] = rh; zprev = rh; } else S.red8[AKS_NW] = rh;
+      }
+    } else if (threadIdx.x == 32) {
+      double znext = 0.0;
+      for (int j = m - 1; j > tw; --j) {
+        double rh = S.r.h[j] - S.hatpart[2 * j] - S.hatpart[2 * (j + 1) + 1];
+        if (j < m - 1) rh -= S.tri_l[j] * znext;
+        S.xh[j] = rh;
+        znext = rh;
+      }
+      S.red8[AKS_NW + 1] = (tw < m - 1) ? S.tri_l[tw] * znext : 0.0;
     }
-    double xnext = 0.0;
-    for (int j = m - 1; j >= 0; --j) {
-      double v = S.xh[j] * S.tri_di[j];
-      if (j < m - 1) v -= S.tri_l[j] * xnext;
-      S.xh[j] = v;
-      xnext = v;
-      S.vy[S.hatg[j]] = v;
-    }
-  }
-  __syncthreads();
-  // D+E. y~ = z - W y_h ;  y_b = P^T y~   (warp per cell, lane = column of P)
-  for (int c = warp; c < C; c += AKS_NW) {
-    const double xh0 = (c < C - 1) ? S.xh[c] : 0.0;
-    const double xh1 = (c > 0) ? S.xh[c - 1] : 0.0;
-    double yt = 0.0;
-    if (lane < nb)
-      yt = S.zt[lane * C + c] - S.fac[(2 * nb + lane) * C + c] * xh0 - S.fac[(3 * nb + lane) * C + c] * xh1;
-    const double* Pc = Pm + (size_t)c * nb * nb;
-    double acc = 0.0;
-    for (int i = 0; i < nb; ++i) {
-      const double yi = __shfl_sync(0xffffffffu, yt, i);
-      if (lane < nb) acc = fma(Pc[i * nb + lane], yi, acc);
-    }
-    if (lane < nb) S.vy[S.bub0[c] + lane] = acc;
-  }
-  __syncthreads();
-}
-
-// ---- out = (unassembled SYMMETRIC operator [C][n][n]) * in   (shared vectors, global numbering)
-__device__ __noinline__ void eig_apply(int n, int C, const int* hatg, const int* bub0, double* hatpart,
-                                       const double* __restrict__ mat, const double* in, double* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c = warp; c < C; c += AKS_NW) {
-    int gi = -1;
-    if (lane >= 2 && lane < n) gi = bub0[c] + lane - 2;
-    else if (lane == 0 && c < C - 1) gi = hatg[c];
-    else if (lane == 1 && c > 0) gi = hatg[c - 1];
-    const double xl = (gi >= 0) ? in[gi] : 0.0;
-    const double* Mc = mat + (size_t)c * n * n;
-    double r = 0.0;
-    for (int a = 0; a < n; ++a) {
-      const double xa = __shfl_sync(0xffffffffu, xl, a);
-      if (lane < n) r = fma(Mc[a * n + lane], xa, r);   // symmetric: column access is coalesced
-    }
-    if (lane >= 2 && gi >= 0) out[gi] = r;
-    if (lane < 2) hatpart[2 * c + lane] = r;
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < C - 1; j += blockDim.x)
-    out[hatg[j]] = hatpart[2 * j] + hatpart[2 * (j + 1) + 1];
-  __syncthreads();
-}
-
-// ---- out = H * in with the packed per-channel blocks
-__device__ __noinline__ void eig_apply_pk(int n, int C, int nb, int npk, const int* hatg, const int* bub0,
-                                          double* hatpart, const double* __restrict__ Hpk, const double* in,
-                                          double* out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int c = warp; c < C; c += AKS_NW) {
-    int gi = -1;
-    if (lane >= 2 && lane < n) gi = bub0[c] + lane - 2;
-    else if (lane == 0 && c < C - 1) gi = hatg[c];
-    else if (lane == 1 && c > 0) gi = hatg[c - 1];
-    const double xl = (gi >= 0) ? in[gi] : 0.0;
-    const double* Hc = Hpk + (size_t)c * npk;
-    double r = 0.0;
-    for (int a = 0; a < n; ++a) {
-      const double xa = __shfl_sync(0xffffffffu, xl, a);
-      if (lane < n) {
-        const int hi = (lane >= a) ? lane : a, lo = (lane >= a) ? a : lane;
-        r = fma(Hc[pk_index(hi, lo, nb)], xa, r);
+    __syncthreads();
+    if (threadIdx.x == 0 || threadIdx.x == 32) {
+      const double xt = (S.red8[AKS_NW] - S.red8[AKS_NW + 1]) * S.tri_di[tw];
+      if (threadIdx.x == 0) {
+        S.y.h[tw] = xt;
+        double xn = xt;
+        for (int j = tw - 1; j >= 0; --j) {
+          const double v = S.xh[j] * S.tri_di[j] - S.tri_l[j] * xn;
+          xn = v;
+          S.y.h[j] = v;
+        }
+      } else {
+        double xp = xt;
+        for (int j = tw + 1; j < m; ++j) {
+          const double v = S.xh[j] * S.tri_di[j] - S.tri_l[j - 1] * xp;
+          xp = v;
+          S.y.h[j] = v;
+        }
       }
     }
-    if (lane >= 2 && gi >= 0) out[gi] = r;
-    if (lane < 2) hatpart[2 * c + lane] = r;
+    __syncthreads();
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < C - 1; j += blockDim.x)
-    out[hatg[j]] = hatpart[2 * j] + hatpart[2 * (j + 1) + 1];
+  // D. y_b = z - W y_h
+  for (int idx = threadIdx.x; idx < nb * C; idx += blockDim.x) {
+    const int j = idx / C, c = idx - j * C;
+    const double xh0 = (c < C - 1) ? S.y.h[c] : 0.0;
+    const double xh1 = (c > 0) ? S.y.h[c - 1] : 0.0;
+    S.y.t[idx] -= S.fac[(2 * nb + j) * C + c] * xh0 + S.fac[(3 * nb + j) * C + c] * xh1;
+  }
   __syncthreads();
 }
 
-__device__ __noinline__ double eig_dot(double* red, const double* a, const double* bvec, int Nh) {
+// ---- out = M~ in  (which = 0)  or  out = H~ in  (which = 1), reduced coordinates, O(nb) per cell
+__device__ __forceinline__ void eig_apply_red(const EigShared& S, int C, int nb, int which, const RedVec& in,
+                                              const RedVec& out) {
+  const int c = threadIdx.x;
+  if (c < C) {
+    const double* R = S.red;
+    const double xR = (c < C - 1) ? in.h[c] : 0.0, xL = (c > 0) ? in.h[c - 1] : 0.0;
+    const int o0 = which ? 2 * nb : 4 * nb, o1 = which ? 3 * nb : 5 * nb;
+    double p0 = 0.0, p1 = 0.0, xprev = 0.0, xj = in.t[c];
+    for (int j = 0; j < nb; ++j) {
+      const double xnext = (j + 1 < nb) ? in.t[(j + 1) * C + c] : 0.0;
+      const double c0 = R[(o0 + j) * C + c], c1 = R[(o1 + j) * C + c];
+      double v;
+      if (which) {
+        v = R[j * C + c] * xj;
+        if (j > 0) v = fma(R[(nb + j - 1) * C + c], xprev, v);
+        if (j + 1 < nb) v = fma(R[(nb + j) * C + c], xnext, v);
+      } else v = xj;
+      out.t[j * C + c] = v + c0 * xR + c1 * xL;
+      p0 = fma(c0, xj, p0);
+      p1 = fma(c1, xj, p1);
+      xprev = xj; xj = xnext;
+    }
+    double h00, h10, h11;
+    if (which) { h00 = R[(6 * nb) * C + c]; h10 = R[(6 * nb + 1) * C + c]; h11 = R[(6 * nb + 2) * C + c]; }
+    else { h00 = S.mhh[c]; h10 = S.mhh[C + c]; h11 = S.mhh[2 * C + c]; }
+    S.hatpart[2 * c] = p0 + h00 * xR + h10 * xL;
+    S.hatpart[2 * c + 1] = p1 + h10 * xR + h11 * xL;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < C - 1; j += blockDim.x) out.h[j] = S.hatpart[2 * j] + S.hatpart[2 * (j + 1) + 1];
+  __syncthreads();
+}
+
+__device__ __forceinline__ double eig_dot_red(const EigShared& S, int C, int nb, const RedVec& a, const RedVec& bv) {
   double acc = 0.0;
-  for (int i = threadIdx.x; i < Nh; i += blockDim.x) acc = fma(a[i], bvec[i], acc);
-  return block_sum(acc, red);
+  for (int i = threadIdx.x; i < nb * C; i += blockDim.x) acc = fma(a.t[i], bv.t[i], acc);
+  for (int i = threadIdx.x; i < C - 1; i += blockDim.x) acc = fma(a.h[i], bv.h[i], acc);
+  return block_sum(acc, S.red8);
+}
+
+#define EIG_NBMAX 32
+// sum_j base[j*ld + lane] * x_j with x_j held by lane j: all loads are issued before the first use
+// (they are L2 hits of ~500 cycles each; a dependent load-FMA loop would expose every one of them)
+__device__ __forceinline__ double warp_colmatvec(const double* __restrict__ base, int rows, int ld, int lane,
+                                                 bool act, double xl) {
+  double pv[EIG_NBMAX];
+#pragma unroll
+  for (int j = 0; j < EIG_NBMAX; ++j) pv[j] = (j < rows && act) ? base[j * ld + lane] : 0.0;
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < EIG_NBMAX; ++j)
+    if (j < rows) acc = fma(pv[j], __shfl_sync(0xffffffffu, xl, j), acc);
+  return acc;
 }
 
 __device__ inline void eig_carve(const DiscDev& d, double* sm, EigShared& S) {
-  const int C = d.C, Nh = d.Nh, n = d.n, nb = d.nb;
+  const int C = d.C, n = d.n, nb = d.nb;
   double* ptr = sm;
   S.red = ptr; ptr += (size_t)red_stride(nb) * C;
   S.mhh = ptr; ptr += 3 * C;
   S.fac = ptr; ptr += (size_t)4 * nb * C;
-  S.zt = ptr; ptr += (size_t)nb * C;
-  S.vx = ptr; ptr += Nh;
-  S.vr = ptr; ptr += Nh;
-  S.vy = ptr; ptr += Nh;
+  S.x.t = ptr; ptr += (size_t)nb * C; S.x.h = ptr; ptr += C;
+  S.r.t = ptr; ptr += (size_t)nb * C; S.r.h = ptr; ptr += C;
+  S.y.t = ptr; ptr += (size_t)nb * C; S.y.h = ptr; ptr += C;
   S.hatpart = ptr; ptr += 2 * C;
   S.sc = ptr; ptr += 3 * C;
   S.tri_di = ptr; ptr += C;
@@ -441,25 +476,29 @@ __device__ inline void eig_carve(const DiscDev& d, double* sm, EigShared& S) {
   }
 }
 
-enum { EST_BRACKET_LO = 0, EST_BRACKET_HI, EST_BISECT, EST_RQI, EST_CERT_LO, EST_CERT_HI, EST_REFINE, EST_DONE };
+enum { EST_BRACKET_LO = 0, EST_BRACKET_HI, EST_BISECT, EST_RQI, EST_CERT_LO, EST_CERT_HI, EST_FINAL, EST_DONE };
 
-__global__ void __launch_bounds__(AKS_NT)
+__global__ void __launch_bounds__(AKS_NT, 2)
 k_eig(DiscDev d, BatchDev b) {
   const int k = blockIdx.x, ch = blockIdx.y, p = blockIdx.z;
   if (b.status[p] != 0) return;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
   if (l >= b.Lp[p] || k >= b.nhp[p]) return;
   extern __shared__ double sm[];
-  const int C = d.C, npk = d.npk, Nh = d.Nh, nb = d.nb, n = d.n;
+  const int C = d.C, nb = d.nb;
+#ifdef AKS_EIG_TIMING
+  long long t_set = 0, t_fac = 0, t_sol = 0, t_app = 0, t_fin = 0, t_all = clock64(), t0_ = clock64();
+#define TSTART() t0_ = clock64()
+#define TADD(v) v += clock64() - t0_
+#else
+#define TSTART()
+#define TADD(v)
+#endif
   EigShared S;
   eig_carve(d, sm, S);
 
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
-  const double* Hpk = b.Hpk + chan * C * npk;
-  const double* Pm = b.Pm + chan * C * (size_t)nb * nb;
-  const double* Pt = b.Pt + chan * C * (size_t)nb * nb;
   const double* eps_ch = b.eps + chan * b.nhmax;
-  double* Uout = b.U + (chan * b.nhmax + k) * Nh;
   const int nhp = b.nhp[p];
   const bool have_prev = b.warm[p] != 0;
   {  // reduced data of this channel, transposed to field-major
@@ -478,6 +517,16 @@ k_eig(DiscDev d, BatchDev b) {
   int clo = -1, chi = -1;
   int state, nfac = 0, its = 0, its_cap = 12, ncount = 0;
   bool from_warm = false, need_start = false, certified = false, converged = false, refined = false;
+  // distance to the neighbouring levels of the previous step: RQI converges cubically, so an
+  // eigenvalue update below 1e-10 of it means the current vector is already converged
+  double gap_est = 0.0;
+  if (have_prev) {
+    const double ep = eps_ch[k];
+    gap_est = DBL_MAX;
+    if (k > 0) gap_est = fmin(gap_est, fabs(ep - eps_ch[k - 1]));
+    if (k + 1 < nhp) gap_est = fmin(gap_est, fabs(eps_ch[k + 1] - ep));
+    if (!(gap_est < 1e300)) gap_est = 0.0;
+  }
 
   auto cold_init = [&]() {
     from_warm = false;
@@ -504,23 +553,32 @@ k_eig(DiscDev d, BatchDev b) {
     if (clo < 0) { lo = blo; hi = (chi >= 0) ? hi : bhi; state = EST_BRACKET_LO; sigma = blo; }
     else { hi = bhi; state = EST_BRACKET_HI; sigma = bhi; }
   };
-
-  if (have_prev && b.stop[p] < 0.3) {
-    // ---- warm start: previous eigenvector, Rayleigh quotient with the new H as first shift
-    for (int i = threadIdx.x; i < Nh; i += blockDim.x) S.vx[i] = Uout[i];
-    __syncthreads();
-    eig_apply(n, C, S.hatg, S.bub0, S.hatpart, d.M0_loc, S.vx, S.vr);
-    const double xmx = eig_dot(S.red8, S.vx, S.vr, Nh);
+  // M~-normalise x, r = M~ x
+  auto normalise = [&]() {
+    eig_apply_red(S, C, nb, 0, S.x, S.r);
+    const double xmx = eig_dot_red(S, C, nb, S.x, S.r);
     const double sc = 1.0 / sqrt(xmx);
-    for (int i = threadIdx.x; i < Nh; i += blockDim.x) { S.vx[i] *= sc; S.vr[i] *= sc; }
+    for (int i = threadIdx.x; i < nb * C; i += blockDim.x) { S.x.t[i] *= sc; S.r.t[i] *= sc; }
+    for (int i = threadIdx.x; i < C - 1; i += blockDim.x) { S.x.h[i] *= sc; S.r.h[i] *= sc; }
     __syncthreads();
-    eig_apply_pk(n, C, nb, npk, S.hatg, S.bub0, S.hatpart, Hpk, S.vx, S.vy);
-    sigma = eig_dot(S.red8, S.vx, S.vy, Nh);
+  };
+
+  double* Xt = b.Xt + (chan * b.nhmax + k) * (size_t)(nb * C + C);
+  if (have_prev && b.stop[p] < 0.3) {
+    // ---- warm start: previous eigenvector, already in reduced coordinates (k_eig_init);
+    // its Rayleigh quotient with the new H~ is the first shift
+    for (int i = threadIdx.x; i < nb * C; i += blockDim.x) S.x.t[i] = Xt[i];
+    for (int i = threadIdx.x; i < C - 1; i += blockDim.x) S.x.h[i] = Xt[nb * C + i];
+    __syncthreads();
+    normalise();
+    eig_apply_red(S, C, nb, 1, S.x, S.y);
+    sigma = eig_dot_red(S, C, nb, S.x, S.y);
     state = EST_RQI; from_warm = true; its_cap = 6;
     if (!isfinite(sigma)) cold_init();
   } else {
     cold_init();
   }
+  TADD(t_set);
 
   auto narrow = [&]() { return clo == k && chi == k + 1 && (hi - lo) <= 0.05 * fmax(fmax(fabs(lo), fabs(hi)), 1e-12); };
   auto fail = [&]() {
@@ -534,27 +592,17 @@ k_eig(DiscDev d, BatchDev b) {
 
   while (state != EST_DONE && nfac < 600) {
     if (state == EST_RQI && need_start) {
-      for (int i = threadIdx.x; i < Nh; i += blockDim.x) S.vx[i] = 1.0 + 0.37 * (double)((i * 7 + 3 * k) % 11) / 11.0;
+      for (int i = threadIdx.x; i < nb * C; i += blockDim.x) S.x.t[i] = 1.0 + 0.37 * (double)((i * 7 + 3 * k) % 11) / 11.0;
+      for (int i = threadIdx.x; i < C - 1; i += blockDim.x) S.x.h[i] = 1.0 + 0.21 * (double)((i * 5 + k) % 7) / 7.0;
       __syncthreads();
-      eig_apply(n, C, S.hatg, S.bub0, S.hatpart, d.M0_loc, S.vx, S.vr);
-      const double xmx = eig_dot(S.red8, S.vx, S.vr, Nh);
-      const double sc = 1.0 / sqrt(xmx);
-      for (int i = threadIdx.x; i < Nh; i += blockDim.x) { S.vx[i] *= sc; S.vr[i] *= sc; }
-      __syncthreads();
+      normalise();
       need_start = false;
     }
-    if (state == EST_REFINE) {
-      // eigenvalue = Rayleigh quotient with the ORIGINAL blocks (x is M-normalised): second-order
-      // accurate in the eigenvector, so the reduction's O(eps cond(M_bb)) error does not reach it
-      eig_apply_pk(n, C, nb, npk, S.hatg, S.bub0, S.hatpart, Hpk, S.vx, S.vy);
-      const double rq = eig_dot(S.red8, S.vx, S.vy, Nh);
-      if (isfinite(rq)) rho = rq;
-      refined = true;
-      state = EST_DONE;
-      break;
-    }
+    if (state == EST_FINAL) break;
     const int store = (state == EST_RQI) ? 1 : 0;
+    TSTART();
     const int cnt = eig_factor(S, C, nb, sigma, store);
+    TADD(t_fac);
     ++nfac;
     if (!store) ++ncount;
     if (state == EST_BRACKET_LO) {
@@ -574,23 +622,29 @@ k_eig(DiscDev d, BatchDev b) {
       sigma = mid;
     } else if (state == EST_RQI) {
       witness(sigma, cnt);
-      eig_solve(S, C, nb, Pm, Pt);                                          // y = (H - sigma M)^{-1} M x
-      const double yr = eig_dot(S.red8, S.vy, S.vr, Nh);                    // y^T M x
-      eig_apply(n, C, S.hatg, S.bub0, S.hatpart, d.M0_loc, S.vy, S.vr);     // r <- M y
-      const double ymy = eig_dot(S.red8, S.vy, S.vr, Nh);
+      TSTART();
+      eig_solve(S, C, nb);                                        // y = (H~ - sigma M~)^{-1} M~ x
+      TADD(t_sol);
+      TSTART();
+      const double yr = eig_dot_red(S, C, nb, S.y, S.r);          // y^T M~ x
+      eig_apply_red(S, C, nb, 0, S.y, S.r);                       // r <- M~ y
+      const double ymy = eig_dot_red(S, C, nb, S.y, S.r);
       rho = sigma + yr / ymy;
       const double sc = 1.0 / sqrt(ymy);
-      for (int i = threadIdx.x; i < Nh; i += blockDim.x) { S.vx[i] = S.vy[i] * sc; S.vr[i] *= sc; }
+      for (int i = threadIdx.x; i < nb * C; i += blockDim.x) { S.x.t[i] = S.y.t[i] * sc; S.r.t[i] *= sc; }
+      for (int i = threadIdx.x; i < C - 1; i += blockDim.x) { S.x.h[i] = S.y.h[i] * sc; S.r.h[i] *= sc; }
       __syncthreads();
+      TADD(t_app);
       ++its;
       const double upd = fabs(rho - sigma);
       if (!isfinite(rho)) { fail(); continue; }
-      if (upd <= 1e-13 * fabs(rho) || (its >= 3 && upd >= 0.25 * prev_upd && upd <= 1e-9 * fmax(fabs(rho), 1e-6))) {
+      if (upd <= 1e-13 * fabs(rho) || upd <= 1e-10 * gap_est ||
+          (its >= 3 && upd >= 0.25 * prev_upd && upd <= 1e-9 * fmax(fabs(rho), 1e-6))) {
         converged = true;
         const double dl = fmax(1e-8 * fabs(rho), 1e-13);
         if (!(clo == k && lo < rho)) { state = EST_CERT_LO; sigma = rho - dl; }
         else if (!(chi == k + 1 && hi > rho)) { state = EST_CERT_HI; sigma = rho + dl; }
-        else { state = EST_REFINE; certified = true; }
+        else { state = EST_FINAL; certified = true; }
         continue;
       }
       prev_upd = upd;
@@ -602,21 +656,180 @@ k_eig(DiscDev d, BatchDev b) {
       if (cnt == k) {
         lo = sigma; clo = k;
         if (!(chi == k + 1 && hi > rho)) { state = EST_CERT_HI; sigma = rho + fmax(1e-8 * fabs(rho), 1e-13); }
-        else { state = EST_REFINE; certified = true; }
+        else { state = EST_FINAL; certified = true; }
       } else { witness(sigma, cnt); fail(); }
     } else if (state == EST_CERT_HI) {
-      if (cnt == k + 1) { state = EST_REFINE; certified = true; }
+      if (cnt == k + 1) { state = EST_FINAL; certified = true; }
       else { witness(sigma, cnt); fail(); }
     }
   }
-  // ---- write back: eigenvalue, vector with a fixed sign convention
-  double big = 0.0;
-  for (int i = threadIdx.x; i < Nh; i += blockDim.x) big += S.vx[i];
-  big = block_sum(big, S.red8);
-  const double sgn = (big < 0.0) ? -1.0 : 1.0;
-  for (int i = threadIdx.x; i < Nh; i += blockDim.x) Uout[i] = sgn * S.vx[i];
+  // ---- hand the converged reduced vector to k_eig_final (back-transform, exact M0 normalisation,
+  // Rayleigh quotient with the ORIGINAL blocks)
+  TSTART();
+  refined = (state == EST_FINAL);
+  for (int i = threadIdx.x; i < nb * C; i += blockDim.x) Xt[i] = S.x.t[i];
+  for (int i = threadIdx.x; i < C - 1; i += blockDim.x) Xt[nb * C + i] = S.x.h[i];
   if (threadIdx.x == 0) {
     b.eps_new[chan * b.nhmax + k] = rho;
     b.eig_info[chan * b.nhmax + k] = (ncount << 8) | ((nfac - ncount) & 0x7f) | ((certified && converged && refined) ? 0 : 0x80);
+#ifdef AKS_EIG_TIMING
+    TADD(t_fin);
+    long long* dbg = b.eig_dbg + (chan * b.nhmax + k) * 8;
+    dbg[0] = t_set; dbg[1] = t_fac; dbg[2] = t_sol; dbg[3] = t_app; dbg[4] = t_fin; dbg[5] = clock64() - t_all;
+#endif
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_eig_init: previous eigenvectors of a channel into the reduced coordinates of the NEW reduction,
+//   x~_b = P (M_bb x_b)   (exact inverse of x_b = P^T x~_b because P M_bb P^T = I),  hats unchanged.
+// One CTA per (cell chunk, channel): the cell's M_bb and P are staged once in shared memory and
+// reused by all nh vectors (one warp per vector).
+#define EIGC_CHUNK 8
+__host__ __device__ inline size_t eig_chan_smem_bytes(int n, int nb) {
+  return sizeof(double) * ((size_t)nb * nb + 2 * (size_t)n * n + 8);
+}
+
+__global__ void __launch_bounds__(AKS_NT)
+k_eig_init(DiscDev d, BatchDev b) {
+  const int p = blockIdx.z, ch = blockIdx.y;
+  if (b.status[p] != 0 || b.warm[p] == 0 || !(b.stop[p] < 0.3)) return;
+  const int e = ch / b.Lmax, l = ch - e * b.Lmax;
+  if (l >= b.Lp[p]) return;
+  extern __shared__ double sm[];
+  const int C = d.C, nb = d.nb, n = d.n, Nh = d.Nh, nhp = b.nhp[p];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* Ps = sm;              // [nb][nb]  P^T (Ps[j*nb+i] = P[i][j])
+  double* Ms = Ps + nb * nb;    // [nb][nb]  M_bb
+  const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
+  const size_t xs = (size_t)(nb * C + C);
+  for (int c = blockIdx.x * EIGC_CHUNK; c < min(C, (blockIdx.x + 1) * EIGC_CHUNK); ++c) {
+    __syncthreads();
+    const double* Ptc = b.Pt + (chan * C + c) * (size_t)nb * nb;
+    const double* Mc = d.M0_loc + (size_t)c * n * n;
+    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
+      Ps[idx] = Ptc[idx];
+      const int r = idx / nb, cc = idx - r * nb;
+      Ms[idx] = Mc[(2 + r) * n + 2 + cc];
+    }
+    __syncthreads();
+    const int g0 = d.l2g[c * n + 2];
+    for (int k = warp; k < nhp; k += AKS_NW) {
+      const double* u = b.U + (chan * b.nhmax + k) * Nh;
+      const double xb = (lane < nb) ? u[g0 + lane] : 0.0;
+      double mb = 0.0;
+      for (int j = 0; j < nb; ++j) {
+        const double xj = __shfl_sync(0xffffffffu, xb, j);
+        if (lane < nb) mb = fma(Ms[j * nb + lane], xj, mb);
+      }
+      double xt = 0.0;
+      for (int j = 0; j < nb; ++j) {
+        const double mj = __shfl_sync(0xffffffffu, mb, j);
+        if (lane < nb) xt = fma(Ps[j * nb + lane], mj, xt);
+      }
+      if (lane < nb) b.Xt[(chan * b.nhmax + k) * xs + (size_t)lane * C + c] = xt;
+    }
+  }
+  if (blockIdx.x == 0)
+    for (int idx = threadIdx.x; idx < nhp * (C - 1); idx += blockDim.x) {
+      const int k = idx / (C - 1), j = idx - k * (C - 1);
+      b.Xt[(chan * b.nhmax + k) * xs + (size_t)nb * C + j] = b.U[(chan * b.nhmax + k) * Nh + d.l2g[j * n]];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_eig_final: one CTA per (cell chunk, channel), one warp per eigenvector, cell by cell with the cell's
+// P, M_c and H_c staged in shared memory: x_b = P^T x~_b written to U (unnormalised), and the chunk's
+// share of x^T M0 x, x^T H x (ORIGINAL blocks, unassembled sums) and of the sign sum.
+// k_eig_scale then adds the shares in a fixed order: U = x / sqrt(x^T M0 x) with a fixed sign,
+// eps = x^T H x / x^T M0 x.
+__global__ void __launch_bounds__(AKS_NT)
+k_eig_final(DiscDev d, BatchDev b) {
+  const int p = blockIdx.z, ch = blockIdx.y, chunk = blockIdx.x;
+  if (b.status[p] != 0) return;
+  const int e = ch / b.Lmax, l = ch - e * b.Lmax;
+  if (l >= b.Lp[p]) return;
+  extern __shared__ double sm[];
+  const int C = d.C, nb = d.nb, n = d.n, Nh = d.Nh, nhp = b.nhp[p];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* Ps = sm;              // [nb][nb]  P   (Ps[i*nb+j] = P[i][j])
+  double* Ms = Ps + nb * nb;    // [n][n]
+  double* Hs = Ms + n * n;      // [n][n]
+  const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
+  const size_t xs = (size_t)(nb * C + C);
+  double xmx[2] = {0.0, 0.0}, xhx[2] = {0.0, 0.0}, ssum[2] = {0.0, 0.0};
+  for (int c = chunk * EIGC_CHUNK; c < min(C, (chunk + 1) * EIGC_CHUNK); ++c) {
+    __syncthreads();
+    const double* Pc = b.Pm + (chan * C + c) * (size_t)nb * nb;
+    const double* Mc = d.M0_loc + (size_t)c * n * n;
+    const double* Hc = b.Hfull + (chan * C + c) * (size_t)n * n;
+    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) Ps[idx] = Pc[idx];
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) { Ms[idx] = Mc[idx]; Hs[idx] = Hc[idx]; }
+    __syncthreads();
+    const int g0 = d.l2g[c * n + 2];
+    const int gR = (c < C - 1) ? d.l2g[c * n] : -1;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int k = warp + t * AKS_NW;
+      if (k < nhp) {
+        const double* X = b.Xt + (chan * b.nhmax + k) * xs;
+        double* u = b.U + (chan * b.nhmax + k) * Nh;
+        const double xt = (lane < nb) ? X[(size_t)lane * C + c] : 0.0;
+        double xb = 0.0;   // x_b[lane] = sum_i P[i][lane] x~_i
+        for (int i = 0; i < nb; ++i) {
+          const double xi = __shfl_sync(0xffffffffu, xt, i);
+          if (lane < nb) xb = fma(Ps[i * nb + lane], xi, xb);
+        }
+        // local vector in generator order: lane 0 right hat, lane 1 left hat, lanes 2.. bubbles
+        double xl = __shfl_up_sync(0xffffffffu, xb, 2);
+        if (lane == 0) xl = (c < C - 1) ? X[(size_t)nb * C + c] : 0.0;
+        if (lane == 1) xl = (c > 0) ? X[(size_t)nb * C + c - 1] : 0.0;
+        if (lane >= n) xl = 0.0;
+        double mx = 0.0, hx = 0.0;
+        for (int a = 0; a < n; ++a) {
+          const double xa = __shfl_sync(0xffffffffu, xl, a);
+          if (lane < n) { mx = fma(Ms[a * n + lane], xa, mx); hx = fma(Hs[a * n + lane], xa, hx); }
+        }
+        xmx[t] = fma(mx, xl, xmx[t]);
+        xhx[t] = fma(hx, xl, xhx[t]);
+        if (lane >= 2 && lane < n) { u[g0 + lane - 2] = xl; ssum[t] += xl; }
+        if (lane == 0 && gR >= 0) { u[gR] = xl; ssum[t] += xl; }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int k = warp + t * AKS_NW;
+    if (k < nhp) {
+      const double m = warp_sum(xmx[t]), h = warp_sum(xhx[t]), sg = warp_sum(ssum[t]);
+      if (lane == 0) {
+        double* part = b.eig_part + ((chan * b.nhmax + k) * gridDim.x + chunk) * 4;
+        part[0] = m; part[1] = h; part[2] = sg;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AKS_NT)
+k_eig_scale(DiscDev d, BatchDev b, int nchunk) {
+  const int p = blockIdx.y, ch = blockIdx.x;
+  if (b.status[p] != 0) return;
+  const int e = ch / b.Lmax, l = ch - e * b.Lmax;
+  if (l >= b.Lp[p]) return;
+  const int Nh = d.Nh, nhp = b.nhp[p];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
+  for (int k = warp; k < nhp; k += AKS_NW) {
+    const double* part = b.eig_part + ((chan * b.nhmax + k) * nchunk) * 4;
+    double m = 0.0, h = 0.0, sg = 0.0;
+    for (int q = 0; q < nchunk; ++q) { m += part[4 * q]; h += part[4 * q + 1]; sg += part[4 * q + 2]; }
+    double* u = b.U + (chan * b.nhmax + k) * Nh;
+    const double sc = ((sg < 0.0) ? -1.0 : 1.0) / sqrt(m);
+    for (int i = lane; i < Nh; i += 32) u[i] *= sc;
+    if (lane == 0) {
+      const double rq = h / m;
+      const int info = b.eig_info[chan * b.nhmax + k];
+      if (isfinite(rq) && !(info & 0x80)) b.eps_new[chan * b.nhmax + k] = rq;
+    }
   }
 }

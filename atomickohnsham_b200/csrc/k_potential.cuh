@@ -205,13 +205,16 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
   for (int e = 0; e < s; ++e) {
     for (int l = 0; l < Lp; ++l) {
       double* out = b.Hpk + ((((size_t)p * s + e) * b.Lmax + l) * C + c) * d.npk;
+      double* outf = b.Hfull + ((((size_t)p * s + e) * b.Lmax + l) * C + c) * (size_t)n * n;
       const double ll = (double)(l * (l + 1));
       for (int idx = tid; idx < n * n; idx += AKS_NT) {
         const int i = idx / n, j = idx - i * n;
-        if (j > i) continue;
-        const double kin = (Ac[idx] + ll * M2c[idx]) / 2.0;
-        const double cou = -Zp * M1c[idx];
-        out[pk_index(i, j, nb)] = ((kin + cou) + Ks[e * n * n + idx]) + Hs[idx];
+        const int lo_idx = (j > i) ? j * n + i : idx;   // read the lower triangle: exactly symmetric output
+        const double kin = (Ac[lo_idx] + ll * M2c[lo_idx]) / 2.0;
+        const double cou = -Zp * M1c[lo_idx];
+        const double h = ((kin + cou) + Ks[e * n * n + lo_idx]) + Hs[lo_idx];
+        outf[idx] = h;
+        if (j <= i) out[pk_index(i, j, nb)] = h;
       }
     }
   }

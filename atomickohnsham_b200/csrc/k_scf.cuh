@@ -12,95 +12,133 @@ __device__ __forceinline__ size_t occ_off(const BatchDev& b, int p, int slot, in
   return ((((size_t)p * 2 + slot) * b.s + e) * b.Lmax + l) * b.nhmax + k;
 }
 
+// compact list of the occupied orbitals of (problem, slot), density! order (sigma, k, l); written by
+// one thread of k_aufbau (both slots) and again by k_linesearch (slot 0, final occupations)
+__device__ inline void write_occ_list(const BatchDev& b, int p, int slot) {
+  int cnt = 0;
+  int* elk = b.occ_elk + ((size_t)p * 2 + slot) * AKS_MAXORB;
+  double* nn = b.occ_n + ((size_t)p * 2 + slot) * AKS_MAXORB;
+  for (int e = 0; e < b.s; ++e)
+    for (int k = 0; k < b.nhp[p]; ++k)
+      for (int l = 0; l < b.Lp[p]; ++l) {
+        const double v = b.occ[occ_off(b, p, slot, e, l, k)];
+        if (v != 0.0 && cnt < AKS_MAXORB) { elk[cnt] = (e << 16) | (l << 8) | k; nn[cnt] = v; ++cnt; }
+      }
+  b.occ_cnt[2 * p + slot] = cnt;
+}
+
 // ------------------------------------------------------------------------------------------
 // k_aufbau: aufbau!(n, eps, ..., ::OptimizedAufbauCache, niter)  (src/algorithms/aufbau/
 // optimized.jl:99-222) -- stable sort of all eps, greedy filling by blocks of <= max_degen
 // levels within `tol` of the block head; a partially filled two-fold block only records the
 // two extreme fillings here (slot 0 / slot 1), the energy minimisation between them
 // (optimized.jl:228-306) happens in k_linesearch.  One thread per problem.
-__global__ void k_aufbau(DiscDev d, BatchDev b) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b) {
+  const int p = blockIdx.x;
   if (p >= b.B || b.status[p] != 0) return;
   const int Lp = b.Lp[p], nhp = b.nhp[p], s = b.s;
   const int norb = Lp * nhp * s;
-  double ev[AKS_MAXORB];
-  int ord[AKS_MAXORB];
+  // stage everything the serial logic touches in shared memory (one warp per problem): the
+  // sort / fill below then never waits on global memory
+  __shared__ double ev[AKS_MAXORB];
+  __shared__ double occ_s[2][AKS_MAXORB];
+  __shared__ int ord[AKS_MAXORB];
+  const int lane = threadIdx.x;
   // flat index f = l + Lp*k + Lp*nhp*e  (convert_index, discretization.jl:379-392)
-  for (int f = 0; f < norb; ++f) {
+  for (int f = lane; f < norb; f += 32) {
     const int e = f / (Lp * nhp), r = f - e * Lp * nhp, k = r / Lp, l = r - k * Lp;
     const double v = b.eps_new[orb_off(b, p, e, l, k)];
     b.eps[orb_off(b, p, e, l, k)] = v;
     ev[f] = v;
     ord[f] = f;
+    occ_s[0][f] = 0.0;
+    occ_s[1][f] = 0.0;
   }
-  for (int i = 1; i < norb; ++i) {  // stable insertion sort (sortperm!)
-    const int oi = ord[i];
-    const double vi = ev[oi];
-    int j = i - 1;
-    while (j >= 0 && ev[ord[j]] > vi) { ord[j + 1] = ord[j]; --j; }
-    ord[j + 1] = oi;
-  }
-  for (int slot = 0; slot < 2; ++slot)
-    for (int e = 0; e < s; ++e)
-      for (int l = 0; l < b.Lmax; ++l)
-        for (int k = 0; k < b.nhmax; ++k) b.occ[occ_off(b, p, slot, e, l, k)] = 0.0;
-  double Nleft = b.N[p];
-  const int niter = b.niter[p];
-  int i = 0, degen = 0;
-  int blk[8];
-  const int maxd = b.max_degen < 8 ? b.max_degen : 8;
-  while (Nleft > 0.0 && i < norb) {
-    blk[0] = ord[i];
-    int nbd = 1;
-    const double e0 = ev[blk[0]];
-    int j = i + 1;
-    while (j < norb && fabs(ev[ord[j]] - e0) < b.degen_tol && nbd < maxd) { blk[nbd++] = ord[j]; ++j; }
-    i += nbd;
-    int degs[8], tot = 0, ee[8], ll[8], kk[8];
-    for (int m = 0; m < nbd; ++m) {
-      const int f = blk[m];
-      ee[m] = f / (Lp * nhp);
-      const int r = f - ee[m] * Lp * nhp;
-      kk[m] = r / Lp;
-      ll[m] = r - kk[m] * Lp;
-      degs[m] = (s == 1) ? 4 * ll[m] + 2 : 2 * ll[m] + 1;
-      tot += degs[m];
+  __syncwarp();
+  int degen = 0;
+  if (lane == 0) {
+    for (int i = 1; i < norb; ++i) {  // stable insertion sort (sortperm!)
+      const int oi = ord[i];
+      const double vi = ev[oi];
+      int j = i - 1;
+      while (j >= 0 && ev[ord[j]] > vi) { ord[j + 1] = ord[j]; --j; }
+      ord[j + 1] = oi;
     }
-    if (Nleft >= (double)tot) {
+    double Nleft = b.N[p];
+    const int niter = b.niter[p];
+    int i = 0;
+    int blk[8];
+    const int maxd = b.max_degen < 8 ? b.max_degen : 8;
+    while (Nleft > 0.0 && i < norb) {
+      blk[0] = ord[i];
+      int nbd = 1;
+      const double e0 = ev[blk[0]];
+      int j = i + 1;
+      while (j < norb && fabs(ev[ord[j]] - e0) < b.degen_tol && nbd < maxd) { blk[nbd++] = ord[j]; ++j; }
+      i += nbd;
+      int degs[8], tot = 0, ee[8], ll[8], kk[8];
       for (int m = 0; m < nbd; ++m) {
-        b.occ[occ_off(b, p, 0, ee[m], ll[m], kk[m])] = (double)degs[m];
-        b.occ[occ_off(b, p, 1, ee[m], ll[m], kk[m])] = (double)degs[m];
+        const int f = blk[m];
+        ee[m] = f / (Lp * nhp);
+        const int r = f - ee[m] * Lp * nhp;
+        kk[m] = r / Lp;
+        ll[m] = r - kk[m] * Lp;
+        degs[m] = (s == 1) ? 4 * ll[m] + 2 : 2 * ll[m] + 1;
+        tot += degs[m];
       }
-      Nleft -= (double)tot;
-    } else if (nbd == 1) {
-      b.occ[occ_off(b, p, 0, ee[0], ll[0], kk[0])] = Nleft;
-      break;
-    } else if (nbd == 2) {
-      if (b.handle_spin && niter == 0 && ll[0] == ll[1] && kk[0] == kk[1] && ee[0] != ee[1]) {
-        b.occ[occ_off(b, p, 0, ee[0], ll[0], kk[0])] = Nleft / 2.0;
-        b.occ[occ_off(b, p, 0, ee[1], ll[1], kk[1])] = Nleft / 2.0;
+      if (Nleft >= (double)tot) {
+        for (int m = 0; m < nbd; ++m) { occ_s[0][blk[m]] = (double)degs[m]; occ_s[1][blk[m]] = (double)degs[m]; }
+        Nleft -= (double)tot;
+      } else if (nbd == 1) {
+        occ_s[0][blk[0]] = Nleft;
+        break;
+      } else if (nbd == 2) {
+        if (b.handle_spin && niter == 0 && ll[0] == ll[1] && kk[0] == kk[1] && ee[0] != ee[1]) {
+          occ_s[0][blk[0]] = Nleft / 2.0;
+          occ_s[0][blk[1]] = Nleft / 2.0;
+          break;
+        }
+        degen = 1;
+        const double n10 = ((double)degs[0] >= Nleft) ? Nleft : (double)degs[0];
+        const double n20 = Nleft - n10;
+        const double n21 = ((double)degs[1] >= Nleft) ? Nleft : (double)degs[1];
+        const double n11 = Nleft - n21;
+        occ_s[0][blk[0]] = n10; occ_s[0][blk[1]] = n20;
+        occ_s[1][blk[0]] = n11; occ_s[1][blk[1]] = n21;
+        b.degen_idx[2 * p] = (ee[0] * b.Lmax + ll[0]) * b.nhmax + kk[0];
+        b.degen_idx[2 * p + 1] = (ee[1] * b.Lmax + ll[1]) * b.nhmax + kk[1];
+        b.degen_n[4 * p] = n10; b.degen_n[4 * p + 1] = n20;
+        b.degen_n[4 * p + 2] = n11; b.degen_n[4 * p + 3] = n21;
+        break;
+      } else {
+        b.status[p] = AKS_EDEGEN3;
         break;
       }
-      degen = 1;
-      const double n10 = ((double)degs[0] >= Nleft) ? Nleft : (double)degs[0];
-      const double n20 = Nleft - n10;
-      const double n21 = ((double)degs[1] >= Nleft) ? Nleft : (double)degs[1];
-      const double n11 = Nleft - n21;
-      b.occ[occ_off(b, p, 0, ee[0], ll[0], kk[0])] = n10;
-      b.occ[occ_off(b, p, 0, ee[1], ll[1], kk[1])] = n20;
-      b.occ[occ_off(b, p, 1, ee[0], ll[0], kk[0])] = n11;
-      b.occ[occ_off(b, p, 1, ee[1], ll[1], kk[1])] = n21;
-      b.degen_idx[2 * p] = (ee[0] * b.Lmax + ll[0]) * b.nhmax + kk[0];
-      b.degen_idx[2 * p + 1] = (ee[1] * b.Lmax + ll[1]) * b.nhmax + kk[1];
-      b.degen_n[4 * p] = n10; b.degen_n[4 * p + 1] = n20;
-      b.degen_n[4 * p + 2] = n11; b.degen_n[4 * p + 3] = n21;
-      break;
-    } else {
-      b.status[p] = AKS_EDEGEN3;
-      break;
+    }
+    b.degen[p] = degen;
+    // compact occupied lists, density! order (sigma, k, l)
+    for (int slot = 0; slot < 2; ++slot) {
+      int cnt = 0;
+      int* elk = b.occ_elk + ((size_t)p * 2 + slot) * AKS_MAXORB;
+      double* nn = b.occ_n + ((size_t)p * 2 + slot) * AKS_MAXORB;
+      if (slot == 0 || degen)
+        for (int e = 0; e < s; ++e)
+          for (int k = 0; k < nhp; ++k)
+            for (int l = 0; l < Lp; ++l) {
+              const double v = occ_s[slot][l + Lp * k + Lp * nhp * e];
+              if (v != 0.0) { elk[cnt] = (e << 16) | (l << 8) | k; nn[cnt] = v; ++cnt; }
+            }
+      b.occ_cnt[2 * p + slot] = cnt;
     }
   }
-  b.degen[p] = degen;
+  __syncwarp();
+  // occupations back to the [slot][sigma][Lmax][nhmax] layout (zero where a problem has no orbital)
+  for (int idx = lane; idx < 2 * s * b.Lmax * b.nhmax; idx += 32) {
+    const int k = idx % b.nhmax, l = (idx / b.nhmax) % b.Lmax, e = (idx / (b.nhmax * b.Lmax)) % s, slot = idx / (b.nhmax * b.Lmax * s);
+    double v = 0.0;
+    if (l < Lp && k < nhp) v = occ_s[slot][l + Lp * k + Lp * nhp * e];
+    b.occ[occ_off(b, p, slot, e, l, k)] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -122,15 +160,16 @@ __global__ void k_orb_energy(DiscDev d, BatchDev b) {
   for (int c = 0; c < C; ++c) {
     const int gi = (lane < n) ? d.l2g[c * n + lane] : -1;
     const double xl = (gi >= 0) ? u[gi] : 0.0;
-    const double* Ar = d.A_loc + ((size_t)c * n + lane) * n;
-    const double* M2r = d.Mm2_loc + ((size_t)c * n + lane) * n;
-    const double* M1r = d.Mm1_loc + ((size_t)c * n + lane) * n;
+    // symmetric blocks: column access (a*n + lane) is coalesced
+    const double* Ar = d.A_loc + (size_t)c * n * n + lane;
+    const double* M2r = d.Mm2_loc + (size_t)c * n * n + lane;
+    const double* M1r = d.Mm1_loc + (size_t)c * n * n + lane;
     double rk = 0.0, rc = 0.0;
     for (int a = 0; a < n; ++a) {
       const double xa = __shfl_sync(0xffffffffu, xl, a);
       if (lane < n) {
-        rk = fma((Ar[a] + ll * M2r[a]) / 2.0, xa, rk);
-        rc = fma(M1r[a], xa, rc);
+        rk = fma((Ar[a * n] + ll * M2r[a * n]) / 2.0, xa, rk);
+        rc = fma(M1r[a * n], xa, rc);
       }
     }
     akin = fma(rk, xl, akin);
@@ -151,16 +190,14 @@ struct OccList {
   double n[AKS_MAXORB];
 };
 __device__ inline void build_occ_list(const BatchDev& b, int p, int slot, OccList* L) {
-  if (threadIdx.x == 0) {
-    int cnt = 0;
-    for (int e = 0; e < b.s; ++e)
-      for (int k = 0; k < b.nhp[p]; ++k)
-        for (int l = 0; l < b.Lp[p]; ++l) {
-          const double nn = b.occ[occ_off(b, p, slot, e, l, k)];
-          if (nn != 0.0 && cnt < AKS_MAXORB) { L->e[cnt] = e; L->l[cnt] = l; L->k[cnt] = k; L->n[cnt] = nn; ++cnt; }
-        }
-    L->count = cnt;
+  const int cnt = b.occ_cnt[2 * p + slot];
+  const int* elk = b.occ_elk + ((size_t)p * 2 + slot) * AKS_MAXORB;
+  const double* nn = b.occ_n + ((size_t)p * 2 + slot) * AKS_MAXORB;
+  for (int o = threadIdx.x; o < cnt; o += blockDim.x) {
+    const int v = elk[o];
+    L->e[o] = v >> 16; L->l[o] = (v >> 8) & 0xff; L->k[o] = v & 0xff; L->n[o] = nn[o];
   }
+  if (threadIdx.x == 0) L->count = cnt;
   __syncthreads();
 }
 
@@ -435,10 +472,11 @@ __device__ void line_search(const DiscDev& d, const BatchDev& b, int p, double q
 // k_linesearch: energies of the trial density (compute_total_energy & co, energies.jl:7-141),
 // two-fold degeneracy resolution (optimized.jl:228-306) and the ODA line search
 // (line_search_density!, oda/loop.jl:79-116).  One CTA per problem.
-__global__ void __launch_bounds__(AKS_NT) k_linesearch(DiscDev d, BatchDev b) {
+#define LS_NT 1024
+__global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
   const int p = blockIdx.x;
   if (b.status[p] != 0) return;
-  __shared__ double red[AKS_NW + 2];
+  __shared__ double red[LS_NT / 32 + 2];
   __shared__ LsShared ls;
   __shared__ double sh[16];
   const int s = b.s, C = d.C, Nh = d.Nh;
@@ -501,6 +539,7 @@ __global__ void __launch_bounds__(AKS_NT) k_linesearch(DiscDev d, BatchDev b) {
       const size_t base = ((size_t)p * 2 + 0) * s * b.Lmax * b.nhmax;
       b.occ[base + o0] = td * dn[0] + (1.0 - td) * dn[2];
       b.occ[base + o1] = td * dn[1] + (1.0 - td) * dn[3];
+      write_occ_list(b, p, 0);
     }
   } else {
     Ekin = sh[1];
@@ -601,16 +640,24 @@ __global__ void __launch_bounds__(AKS_NT) k_mix_dense(DiscDev d, BatchDev b) {
   __shared__ double red[AKS_NW];
   const int Nh = d.Nh, nt = b.ntile;
   const int tr = blockIdx.x / nt, tc = blockIdx.x - tr * nt;
-  if (threadIdx.x == 0) {
-    int cnt = 0;
-    for (int k = 0; k < b.nhp[p]; ++k)
-      for (int l = 0; l < b.Lp[p]; ++l) {
-        const double nn = b.occ[occ_off(b, p, 0, e, l, k)];
-        if (nn != 0.0 && cnt < MIX_MAXOCC) { nk[cnt] = nn; ol[cnt] = l; okk[cnt] = k; ++cnt; }
-      }
-    cnt_s = cnt;
+  {
+    // the list is ordered by spin: entries of spin e are contiguous; one ballot finds them
+    const int tot = b.occ_cnt[2 * p];
+    const int* elk = b.occ_elk + ((size_t)p * 2) * AKS_MAXORB;
+    const double* nn = b.occ_n + ((size_t)p * 2) * AKS_MAXORB;
+    __shared__ int first_s;
+    if (threadIdx.x == 0) { cnt_s = 0; first_s = AKS_MAXORB; }
+    __syncthreads();
+    const int o = threadIdx.x;
+    int v = 0;
+    const bool mine = (o < tot) && (((v = elk[o]) >> 16) == e);
+    if (mine) { atomicMin(&first_s, o); atomicAdd(&cnt_s, 1); }
+    __syncthreads();
+    if (mine && o - first_s < MIX_MAXOCC) { nk[o - first_s] = nn[o]; ol[o - first_s] = (v >> 8) & 0xff; okk[o - first_s] = v & 0xff; }
+    __syncthreads();
+    if (threadIdx.x == 0 && cnt_s > MIX_MAXOCC) cnt_s = MIX_MAXOCC;
+    __syncthreads();
   }
-  __syncthreads();
   const int cnt = cnt_s;
   for (int idx = threadIdx.x; idx < MIX_TS * cnt; idx += AKS_NT) {
     const int o = idx / MIX_TS, r = idx - o * MIX_TS;

@@ -157,6 +157,9 @@ int aks_hartree_energy(aks_batch* batch, int32_t prob, double* Ehar);
 /* eigensolver diagnostics of the last step: info[nprob*nspin*L*nh], device order [prob][sigma][l][k];
  * each word = (inertia counts << 8) | (0x80 if RQI did not converge) | RQI iterations       */
 int aks_debug_eig_info(aks_batch* batch, int32_t* info);
+/* per-eigenpair cycle counters [nprob*nspin*L*nh][8] = {setup, factor, solve, apply+dots, final, total,
+ * 0, 0}; zeros unless the library was built with -DAKS_EIG_TIMING                              */
+int aks_debug_eig_cycles(aks_batch* batch, int64_t* cycles);
 
 /* ---- measurement aids --------------------------------------------------------------------*/
 /* number of kernels launched by this ctx so far (bench.py "gpu_launches")                 */
