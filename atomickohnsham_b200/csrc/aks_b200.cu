@@ -550,7 +550,7 @@ static int step_launch(aks_batch* bt) {
   TICK();
   k_aufbau<<<bt->B, 32, 0, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
-  k_orb_energy<<<dim3(b.s * b.Lmax * b.nhmax, bt->B), 32, 0, ctx->stream>>>(dv, b);
+  k_orb_energy<<<dim3(b.s * b.Lmax * b.nhmax, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
   TICK();
   if ((rc = launch_dens_cells(bt)) != AKS_OK) return rc;

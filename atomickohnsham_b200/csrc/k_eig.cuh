@@ -182,28 +182,33 @@ struct EigShared {
   double* fac;      // [4 nb][C]        dinv[nb] | l[nb] | W0[nb] | W1[nb]
   RedVec x, r, y;   // iterate, r = M~ x, solve output
   double* hatpart;  // [2C]
-  double* sc;       // [3C]  Schur blocks of the current factorisation
+  double* sc;       // [EIG_NG][3C]  Schur blocks of the current factorisation(s)
   double* tri_di;   // [C]   reciprocal pivots of the hat system
   double* tri_l;    // [C]
   double* xh;       // [C]
   double* red8;     // [NW + 8]
-  int* negc;        // [C + 2]
+  int* negc;        // [EIG_NG][C + 2]
+  int* cntg;        // [EIG_NG + 2] inertia counts of the shifts of the last eig_factor call
   int* hatg;        // [C]   global index of hat j (right hat of cell j)
   int* bub0;        // [C]   global index of the first bubble of cell c (bubbles are contiguous)
 };
 
 __host__ __device__ inline size_t eig_smem_bytes(int C, int nb, int Nh) {
   size_t nd = (size_t)red_stride(nb) * C + 3 * C + (size_t)4 * nb * C + 3 * ((size_t)nb * C + C) +
-              2 * C + 3 * C + 3 * C + AKS_NW + 8;
-  return nd * sizeof(double) + (size_t)(3 * C + 8) * sizeof(int);
+              2 * C + 6 * 3 * C + 3 * C + AKS_NW + 8;
+  return nd * sizeof(double) + (size_t)(6 * (C + 2) + 2 * C + 16) * sizeof(int);
 }
 
-// ---- factor T(sigma): thread c handles cell c; returns the inertia count
-__device__ __forceinline__ int eig_factor(const EigShared& S, int C, int nb, double sigma, int store) {
-  const int c = threadIdx.x;
-  if (c < C) {
+#define EIG_NG 6   // shifts evaluated concurrently in the count-only states (groups of C threads)
+
+// ---- factor T(sigma) for up to EIG_NG shifts at once: thread t = g*C + c handles cell c of shift g.
+// store != 0 (only with ng == 1): keep the factors of shift 0 for eig_solve.  Inertia counts -> S.cntg[g].
+__device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, int ng, double sigma, int store) {
+  const int g = threadIdx.x / C, c = threadIdx.x - g * C;
+  if (g < ng) {
     const double* R = S.red;
     double* F = S.fac;
+    double* sc = S.sc + (size_t)g * 3 * C;
     const double pivmin0 = DBL_MIN * 1e8;
     double scale = 0.0;
     int neg = 0;
@@ -248,23 +253,25 @@ __device__ __forceinline__ int eig_factor(const EigShared& S, int C, int nb, dou
         w0n = w0; w1n = w1;
       }
     }
-    S.sc[3 * c] = (R[(6 * nb) * C + c] - sigma * S.mhh[c]) - s00;
-    S.sc[3 * c + 1] = (R[(6 * nb + 1) * C + c] - sigma * S.mhh[C + c]) - s10;
-    S.sc[3 * c + 2] = (R[(6 * nb + 2) * C + c] - sigma * S.mhh[2 * C + c]) - s11;
-    S.negc[c] = neg;
+    sc[3 * c] = (R[(6 * nb) * C + c] - sigma * S.mhh[c]) - s00;
+    sc[3 * c + 1] = (R[(6 * nb + 1) * C + c] - sigma * S.mhh[C + c]) - s10;
+    sc[3 * c + 2] = (R[(6 * nb + 2) * C + c] - sigma * S.mhh[2 * C + c]) - s11;
+    S.negc[g * (C + 2) + c] = neg;
   }
   __syncthreads();
   // hat node j sits between cell j (its right hat, g=0) and cell j+1 (its left hat, g=1).
-  // Twisted factorisation: thread 0 eliminates downwards j = 0..tw-1, thread 32 upwards j = m-1..tw+1,
-  // they meet at the twist index tw; inertia = negatives of both sweeps + sign of the twist pivot.
-  {
-    const int m = C - 1, tw = m / 2;
+  // Twisted factorisation of the (C-1) tridiagonal: a sweep down from the top and a sweep up from the
+  // bottom meet at the twist index tw; inertia = negatives of both sweeps + sign of the twist pivot.
+  const int m = C - 1, tw = m / 2;
+  if (store) {
+    // shift 0, factors kept: thread 0 runs the top sweep, thread 32 the bottom sweep
+    const double* sc = S.sc;
     if (threadIdx.x == 0) {
       int neg = 0;
       for (int cc = 0; cc < C; ++cc) neg += S.negc[cc];
       double dinvp = 0.0, offprev = 0.0, scale = 0.0;
       for (int j = 0; j < tw; ++j) {
-        const double diag = S.sc[3 * j] + S.sc[3 * (j + 1) + 2];
+        const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
         scale = fmax(scale, fabs(diag));
         double l = 0.0, dj = diag;
         if (j > 0) { l = offprev * dinvp; dj = diag - l * offprev; }
@@ -274,7 +281,7 @@ __device__ __forceinline__ int eig_factor(const EigShared& S, int C, int nb, dou
         dinvp = 1.0 / dj;
         S.tri_di[j] = dinvp;
         if (j > 0) S.tri_l[j - 1] = l;
-        offprev = S.sc[3 * (j + 1) + 1];
+        offprev = sc[3 * (j + 1) + 1];
       }
       S.xh[0] = (tw > 0) ? offprev * dinvp * offprev : 0.0;
       if (tw > 0) S.tri_l[tw - 1] = offprev * dinvp;
@@ -283,7 +290,7 @@ __device__ __forceinline__ int eig_factor(const EigShared& S, int C, int nb, dou
       int neg = 0;
       double dinvn = 0.0, offnext = 0.0, scale = 0.0;
       for (int j = m - 1; j > tw; --j) {
-        const double diag = S.sc[3 * j] + S.sc[3 * (j + 1) + 2];
+        const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
         scale = fmax(scale, fabs(diag));
         double u = 0.0, dj = diag;
         if (j < m - 1) { u = offnext * dinvn; dj = diag - u * offnext; }
@@ -293,7 +300,7 @@ __device__ __forceinline__ int eig_factor(const EigShared& S, int C, int nb, dou
         dinvn = 1.0 / dj;
         S.tri_di[j] = dinvn;
         if (j < m - 1) S.tri_l[j] = u;
-        offnext = S.sc[3 * j + 1];
+        offnext = sc[3 * j + 1];
       }
       S.xh[1] = (tw < m - 1) ? offnext * dinvn * offnext : 0.0;
       if (tw < m - 1) S.tri_l[tw] = offnext * dinvn;
@@ -301,16 +308,54 @@ __device__ __forceinline__ int eig_factor(const EigShared& S, int C, int nb, dou
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      const double diag = S.sc[3 * tw] + S.sc[3 * (tw + 1) + 2];
-      double g = diag - S.xh[0] - S.xh[1];
+      const double diag = sc[3 * tw] + sc[3 * (tw + 1) + 2];
+      double gam = diag - S.xh[0] - S.xh[1];
       const double pivmin = fmax(fabs(diag) * 4.9e-32, DBL_MIN * 1e8);
-      if (fabs(g) < pivmin) g = (g < 0.0) ? -pivmin : pivmin;
-      S.tri_di[tw] = 1.0 / g;
-      S.negc[C] += S.negc[C + 1] + (g < 0.0);
+      if (fabs(gam) < pivmin) gam = (gam < 0.0) ? -pivmin : pivmin;
+      S.tri_di[tw] = 1.0 / gam;
+      S.cntg[0] = S.negc[C] + S.negc[C + 1] + (gam < 0.0);
     }
-    __syncthreads();
+  } else if (c == 0 && g < ng) {
+    // count only: one thread per shift runs both sweeps interleaved (two independent dependency chains)
+    const double* sc = S.sc + (size_t)g * 3 * C;
+    const int* ngc = S.negc + g * (C + 2);
+    int neg = 0;
+    for (int cc = 0; cc < C; ++cc) neg += ngc[cc];
+    double dinvp = 0.0, offprev = 0.0, dinvn = 0.0, offnext = 0.0, scale = 0.0;
+    const int nup = m - 1 - tw;  // rows of the bottom sweep
+    for (int q = 0; q < max(tw, nup); ++q) {
+      if (q < tw) {
+        const int j = q;
+        const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
+        scale = fmax(scale, fabs(diag));
+        double dj = diag;
+        if (j > 0) dj = diag - (offprev * dinvp) * offprev;
+        const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
+        if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
+        neg += (dj < 0.0);
+        dinvp = 1.0 / dj;
+        offprev = sc[3 * (j + 1) + 1];
+      }
+      if (q < nup) {
+        const int j = m - 1 - q;
+        const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
+        scale = fmax(scale, fabs(diag));
+        double dj = diag;
+        if (j < m - 1) dj = diag - (offnext * dinvn) * offnext;
+        const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
+        if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
+        neg += (dj < 0.0);
+        dinvn = 1.0 / dj;
+        offnext = sc[3 * j + 1];
+      }
+    }
+    const double diag = sc[3 * tw] + sc[3 * (tw + 1) + 2];
+    double gam = diag;
+    if (tw > 0) gam -= offprev * dinvp * offprev;
+    if (tw < m - 1) gam -= offnext * dinvn * offnext;
+    S.cntg[g] = neg + (gam < 0.0);
   }
-  return S.negc[C];
+  __syncthreads();
 }
 
 // ---- y = T~(sigma)^{-1} r in reduced coordinates with the stored factors
@@ -459,13 +504,14 @@ __device__ inline void eig_carve(const DiscDev& d, double* sm, EigShared& S) {
   S.r.t = ptr; ptr += (size_t)nb * C; S.r.h = ptr; ptr += C;
   S.y.t = ptr; ptr += (size_t)nb * C; S.y.h = ptr; ptr += C;
   S.hatpart = ptr; ptr += 2 * C;
-  S.sc = ptr; ptr += 3 * C;
+  S.sc = ptr; ptr += EIG_NG * 3 * C;
   S.tri_di = ptr; ptr += C;
   S.tri_l = ptr; ptr += C;
   S.xh = ptr; ptr += C;
   S.red8 = ptr; ptr += AKS_NW + 8;
   S.negc = (int*)ptr;
-  S.hatg = S.negc + C + 2;
+  S.cntg = S.negc + EIG_NG * (C + 2);
+  S.hatg = S.cntg + EIG_NG + 2;
   S.bub0 = S.hatg + C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     S.hatg[c] = (c < C - 1) ? d.l2g[c * n + 0] : 0;
@@ -600,23 +646,59 @@ k_eig(DiscDev d, BatchDev b) {
     }
     if (state == EST_FINAL) break;
     const int store = (state == EST_RQI) ? 1 : 0;
+    // shifts of this round: one (RQI) or a ladder / partition / certificate pair evaluated concurrently
+    const int ngmax = min(EIG_NG, (int)blockDim.x / C);
+    int ng = 1;
+    const int gme = threadIdx.x / C;
+    double sg_mine = sigma;
+    auto shift_of = [&](int g) -> double {
+      if (state == EST_BRACKET_LO) return sigma - step * (double)((1 << g) - 1);
+      if (state == EST_BRACKET_HI) return sigma + step * (double)((1 << g) - 1);
+      if (state == EST_BISECT) return lo + (hi - lo) * (double)(g + 1) / (double)(ng + 1);
+      if (state == EST_CERT_LO) return (g == 0) ? sigma : rho + fmax(1e-8 * fabs(rho), 1e-13);
+      return sigma;
+    };
+    if (state == EST_BRACKET_LO || state == EST_BRACKET_HI || state == EST_BISECT) ng = ngmax;
+    else if (state == EST_CERT_LO) ng = min(2, ngmax);
+    sg_mine = shift_of(min(gme, ng - 1));
     TSTART();
-    const int cnt = eig_factor(S, C, nb, sigma, store);
+    eig_factor(S, C, nb, ng, sg_mine, store);
     TADD(t_fac);
-    ++nfac;
-    if (!store) ++ncount;
+    nfac += 1;
+    if (!store) ncount += 1;   // count-only rounds (each evaluates up to EIG_NG shifts)
+    const int cnt = S.cntg[0];
     if (state == EST_BRACKET_LO) {
-      if (cnt > k) { hi = sigma; chi = cnt; lo = sigma - step; step *= 2.0; sigma = lo; }
-      else {
-        lo = sigma; clo = cnt;
-        if (chi >= 0) { state = narrow() ? EST_RQI : EST_BISECT; sigma = 0.5 * (lo + hi); }
-        else { state = EST_BRACKET_HI; sigma = hi; }
+      // ladder going down: first rung with count <= k closes the bracket from below
+      int gfound = -1;
+      for (int g = 0; g < ng; ++g) {
+        const int cg = S.cntg[g];
+        const double sgv = shift_of(g);
+        if (cg <= k) { gfound = g; lo = sgv; clo = cg; break; }
+        hi = sgv; chi = cg;
       }
+      if (gfound < 0) { sigma = shift_of(ng - 1) - step * (double)(1 << (ng - 1)); step *= (double)(1 << ng); }
+      else if (chi >= 0) { state = narrow() ? EST_RQI : EST_BISECT; sigma = 0.5 * (lo + hi); }
+      else { state = EST_BRACKET_HI; sigma = hi; }
     } else if (state == EST_BRACKET_HI) {
-      if (cnt < k + 1) { lo = sigma; clo = cnt; hi = sigma + step; step *= 2.0; sigma = hi; }
-      else { hi = sigma; chi = cnt; state = narrow() ? EST_RQI : EST_BISECT; sigma = 0.5 * (lo + hi); }
+      int gfound = -1;
+      for (int g = 0; g < ng; ++g) {
+        const int cg = S.cntg[g];
+        const double sgv = shift_of(g);
+        if (cg >= k + 1) { gfound = g; hi = sgv; chi = cg; break; }
+        lo = sgv; clo = cg;
+      }
+      if (gfound < 0) { sigma = shift_of(ng - 1) + step * (double)(1 << (ng - 1)); step *= (double)(1 << ng); }
+      else { state = narrow() ? EST_RQI : EST_BISECT; sigma = 0.5 * (lo + hi); }
     } else if (state == EST_BISECT) {
-      if (cnt <= k) { lo = sigma; clo = cnt; } else { hi = sigma; chi = cnt; }
+      double nlo = lo, nhi = hi;
+      int nclo = clo, nchi = chi;
+      for (int g = 0; g < ng; ++g) {
+        const int cg = S.cntg[g];
+        const double sgv = shift_of(g);
+        if (cg <= k) { if (sgv > nlo) { nlo = sgv; nclo = cg; } }
+        else if (sgv < nhi) { nhi = sgv; nchi = cg; }
+      }
+      lo = nlo; hi = nhi; clo = nclo; chi = nchi;
       const double mid = 0.5 * (lo + hi);
       if (narrow() || !(mid > lo && mid < hi)) state = EST_RQI;
       sigma = mid;
@@ -642,8 +724,7 @@ k_eig(DiscDev d, BatchDev b) {
           (its >= 3 && upd >= 0.25 * prev_upd && upd <= 1e-9 * fmax(fabs(rho), 1e-6))) {
         converged = true;
         const double dl = fmax(1e-8 * fabs(rho), 1e-13);
-        if (!(clo == k && lo < rho)) { state = EST_CERT_LO; sigma = rho - dl; }
-        else if (!(chi == k + 1 && hi > rho)) { state = EST_CERT_HI; sigma = rho + dl; }
+        if (!(clo == k && lo < rho) || !(chi == k + 1 && hi > rho)) { state = EST_CERT_LO; sigma = rho - dl; }
         else { state = EST_FINAL; certified = true; }
         continue;
       }
@@ -653,11 +734,19 @@ k_eig(DiscDev d, BatchDev b) {
       else if (from_warm) { fail(); continue; }
       else sigma = 0.5 * (lo + hi);
     } else if (state == EST_CERT_LO) {
-      if (cnt == k) {
-        lo = sigma; clo = k;
-        if (!(chi == k + 1 && hi > rho)) { state = EST_CERT_HI; sigma = rho + fmax(1e-8 * fabs(rho), 1e-13); }
-        else { state = EST_FINAL; certified = true; }
-      } else { witness(sigma, cnt); fail(); }
+      // sigma = rho - dl (shift 0); with two groups the upper certificate rho + dl rides along (shift 1)
+      bool ok = true;
+      if (!(clo == k && lo < rho)) {
+        if (cnt == k) { lo = sigma; clo = k; } else { witness(sigma, cnt); ok = false; }
+      }
+      if (ok && !(chi == k + 1 && hi > rho)) {
+        if (ng >= 2) {
+          const int c2 = S.cntg[1];
+          const double s2 = shift_of(1);
+          if (c2 == k + 1) { hi = s2; chi = c2; } else { witness(s2, c2); ok = false; }
+        } else { state = EST_CERT_HI; sigma = rho + fmax(1e-8 * fabs(rho), 1e-13); continue; }
+      }
+      if (ok) { state = EST_FINAL; certified = true; } else fail();
     } else if (state == EST_CERT_HI) {
       if (cnt == k + 1) { state = EST_FINAL; certified = true; }
       else { witness(sigma, cnt); fail(); }

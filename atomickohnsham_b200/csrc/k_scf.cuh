@@ -144,8 +144,9 @@ __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b) {
 // ------------------------------------------------------------------------------------------
 // k_orb_energy: u^T Kin_l u and u^T Coulomb u per occupied orbital
 // (compute_kinetic_energy / compute_coulomb_energy, src/discretization/energies.jl:47-87).
-// One warp per orbital, unassembled operators.
-__global__ void k_orb_energy(DiscDev d, BatchDev b) {
+// One CTA per orbital; its warps split the cells of the unassembled operators, every warp issues
+// the 3 x n column loads of a cell before using them; fixed-order block reduction.
+__global__ void __launch_bounds__(AKS_NT) k_orb_energy(DiscDev d, BatchDev b) {
   const int p = blockIdx.y;
   if (b.status[p] != 0) return;
   const int o = blockIdx.x;  // (e*Lmax + l)*nhmax + k
@@ -153,11 +154,12 @@ __global__ void k_orb_energy(DiscDev d, BatchDev b) {
   if (l >= b.Lp[p] || k >= b.nhp[p]) return;
   const double n0 = b.occ[occ_off(b, p, 0, e, l, k)], n1 = b.occ[occ_off(b, p, 1, e, l, k)];
   if (n0 == 0.0 && !(b.degen[p] && n1 != 0.0)) return;
-  const int lane = threadIdx.x, n = d.n, C = d.C;
+  __shared__ double red[AKS_NW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = d.n, C = d.C;
   const double* u = b.U + orb_off(b, p, e, l, k) * d.Nh;
   const double ll = (double)(l * (l + 1));
   double akin = 0.0, acou = 0.0;
-  for (int c = 0; c < C; ++c) {
+  for (int c = warp; c < C; c += AKS_NW) {
     const int gi = (lane < n) ? d.l2g[c * n + lane] : -1;
     const double xl = (gi >= 0) ? u[gi] : 0.0;
     // symmetric blocks: column access (a*n + lane) is coalesced
@@ -165,19 +167,29 @@ __global__ void k_orb_energy(DiscDev d, BatchDev b) {
     const double* M2r = d.Mm2_loc + (size_t)c * n * n + lane;
     const double* M1r = d.Mm1_loc + (size_t)c * n * n + lane;
     double rk = 0.0, rc = 0.0;
-    for (int a = 0; a < n; ++a) {
-      const double xa = __shfl_sync(0xffffffffu, xl, a);
-      if (lane < n) {
-        rk = fma((Ar[a * n] + ll * M2r[a * n]) / 2.0, xa, rk);
-        rc = fma(M1r[a * n], xa, rc);
+#pragma unroll
+    for (int a0 = 0; a0 < 32; a0 += 16) {
+      double ka[16], ca[16];
+#pragma unroll
+      for (int a = 0; a < 16; ++a) {
+        const bool on = (a0 + a < n) && (lane < n);
+        ka[a] = on ? (Ar[(a0 + a) * n] + ll * M2r[(a0 + a) * n]) / 2.0 : 0.0;
+        ca[a] = on ? M1r[(a0 + a) * n] : 0.0;
       }
+#pragma unroll
+      for (int a = 0; a < 16; ++a)
+        if (a0 + a < n) {
+          const double xa = __shfl_sync(0xffffffffu, xl, a0 + a);
+          rk = fma(ka[a], xa, rk);
+          rc = fma(ca[a], xa, rc);
+        }
     }
     akin = fma(rk, xl, akin);
     acou = fma(rc, xl, acou);
   }
-  akin = warp_sum(akin);
-  acou = warp_sum(acou);
-  if (lane == 0) {
+  akin = block_sum(akin, red);
+  acou = block_sum(acou, red);
+  if (threadIdx.x == 0) {
     b.ekin_orb[orb_off(b, p, e, l, k)] = akin;
     b.ecou_orb[orb_off(b, p, e, l, k)] = -b.Z[p] * acou;
   }
@@ -626,26 +638,35 @@ __global__ void k_mix_state(DiscDev d, BatchDev b) {
 // ------------------------------------------------------------------------------------------
 // k_mix_dense: the dense density matrix D = sum n u u^T (density!, density.jl:15-41), mixed in
 // place, and the Frobenius norm of the update (stopping rule, oda/loop.jl:43-45).  Pure HBM
-// streaming: read D, write D; the trial D is never materialised.  32x32 tile per CTA.
-#define MIX_TS 32
-#define MIX_MAXOCC 48
-__global__ void __launch_bounds__(AKS_NT) k_mix_dense(DiscDev d, BatchDev b) {
+// streaming: read D, write D; the trial D is never materialised.  One CTA per 64x64 tile, 16 entries
+// per thread whose old values are all requested before the rank-n_occ update is accumulated.
+#define MIX_TS 64
+#define MIX_OCH 16   // orbitals per staging chunk
+__global__ void __launch_bounds__(AKS_NT, 3) k_mix_dense(DiscDev d, BatchDev b) {
   const int p = blockIdx.z, e = blockIdx.y;
   if (b.status[p] != 0) return;
-  __shared__ double Ui[MIX_TS][MIX_MAXOCC + 1];
-  __shared__ double Uj[MIX_TS][MIX_MAXOCC + 1];
-  __shared__ double nk[MIX_MAXOCC];
-  __shared__ int ol[MIX_MAXOCC], okk[MIX_MAXOCC];
-  __shared__ int cnt_s;
+  __shared__ double Ui[MIX_OCH][MIX_TS + 1];
+  __shared__ double Uj[MIX_OCH][MIX_TS + 1];
+  __shared__ double nk[AKS_MAXORB];
+  __shared__ int oidx[AKS_MAXORB];
+  __shared__ int cnt_s, first_s;
   __shared__ double red[AKS_NW];
   const int Nh = d.Nh, nt = b.ntile;
   const int tr = blockIdx.x / nt, tc = blockIdx.x - tr * nt;
+  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;   // 4 row groups x 64 columns
+  double* D = b.Dd + ((size_t)p * b.s + e) * Nh * Nh;
+  // request the old tile first: these loads overlap the staging and the update below
+  double old[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int gi = tr * MIX_TS + ry + 4 * r, gj = tc * MIX_TS + cx;
+    old[r] = (gi < Nh && gj < Nh) ? D[(size_t)gi * Nh + gj] : 0.0;
+  }
   {
-    // the list is ordered by spin: entries of spin e are contiguous; one ballot finds them
+    // the list is ordered by spin: entries of spin e are contiguous
     const int tot = b.occ_cnt[2 * p];
     const int* elk = b.occ_elk + ((size_t)p * 2) * AKS_MAXORB;
     const double* nn = b.occ_n + ((size_t)p * 2) * AKS_MAXORB;
-    __shared__ int first_s;
     if (threadIdx.x == 0) { cnt_s = 0; first_s = AKS_MAXORB; }
     __syncthreads();
     const int o = threadIdx.x;
@@ -653,34 +674,40 @@ __global__ void __launch_bounds__(AKS_NT) k_mix_dense(DiscDev d, BatchDev b) {
     const bool mine = (o < tot) && (((v = elk[o]) >> 16) == e);
     if (mine) { atomicMin(&first_s, o); atomicAdd(&cnt_s, 1); }
     __syncthreads();
-    if (mine && o - first_s < MIX_MAXOCC) { nk[o - first_s] = nn[o]; ol[o - first_s] = (v >> 8) & 0xff; okk[o - first_s] = v & 0xff; }
-    __syncthreads();
-    if (threadIdx.x == 0 && cnt_s > MIX_MAXOCC) cnt_s = MIX_MAXOCC;
+    if (mine) { nk[o - first_s] = nn[o]; oidx[o - first_s] = (((v >> 8) & 0xff) * b.nhmax) + (v & 0xff); }
     __syncthreads();
   }
   const int cnt = cnt_s;
-  for (int idx = threadIdx.x; idx < MIX_TS * cnt; idx += AKS_NT) {
-    const int o = idx / MIX_TS, r = idx - o * MIX_TS;
-    const double* u = b.U + orb_off(b, p, e, ol[o], okk[o]) * Nh;
-    const int gi = tr * MIX_TS + r, gj = tc * MIX_TS + r;
-    Ui[r][o] = (gi < Nh) ? u[gi] : 0.0;
-    Uj[r][o] = (gj < Nh) ? u[gj] : 0.0;
-  }
-  __syncthreads();
   const double t = b.tmix[p];
-  double* D = b.Dd + ((size_t)p * b.s + e) * Nh * Nh;
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const double* Ubase = b.U + (((size_t)p * b.s + e) * b.Lmax * b.nhmax) * Nh;
+  double dn[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) dn[r] = 0.0;
+  for (int o0 = 0; o0 < cnt; o0 += MIX_OCH) {
+    const int oc = min(MIX_OCH, cnt - o0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < oc * MIX_TS; idx += AKS_NT) {
+      const int o = idx / MIX_TS, r = idx - o * MIX_TS;
+      const double* u = Ubase + (size_t)oidx[o0 + o] * Nh;
+      const int gi = tr * MIX_TS + r, gj = tc * MIX_TS + r;
+      Ui[o][r] = (gi < Nh) ? u[gi] : 0.0;
+      Uj[o][r] = (gj < Nh) ? u[gj] : 0.0;
+    }
+    __syncthreads();
+    for (int o = 0; o < oc; ++o) {
+      const double ujc = nk[o0 + o] * Uj[o][cx];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) dn[r] = fma(Ui[o][ry + 4 * r], ujc, dn[r]);
+    }
+  }
   double acc = 0.0;
-  for (int rr = ry; rr < MIX_TS; rr += AKS_NW) {
-    const int gi = tr * MIX_TS + rr, gj = tc * MIX_TS + cx;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const int gi = tr * MIX_TS + ry + 4 * r, gj = tc * MIX_TS + cx;
     if (gi < Nh && gj < Nh) {
-      double dn = 0.0;
-      for (int o = 0; o < cnt; ++o) dn = fma(nk[o] * Ui[rr][o], Uj[cx][o], dn);
-      const size_t at = (size_t)gi * Nh + gj;
-      const double old = D[at];
-      const double nv = t * dn + (1.0 - t) * old;
-      D[at] = nv;
-      const double df = nv - old;
+      const double nv = t * dn[r] + (1.0 - t) * old[r];
+      D[(size_t)gi * Nh + gj] = nv;
+      const double df = nv - old[r];
       acc = fma(df, df, acc);
     }
   }
