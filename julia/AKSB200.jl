@@ -1,0 +1,112 @@
+# AKSB200.jl -- ccall shim: AtomicKohnSham.jl's SCF loop on libaks_b200.so (include/aks_b200.h).
+#
+# NOT EXECUTABLE IN THIS REPOSITORY'S ENVIRONMENT (no Julia in the image or on the GPU box); it is the
+# reference-side binding a maintainer would add.  It keeps the public API: the caller builds
+# KSEModel / KSEDiscretization / ODA exactly as today and passes `backend = :b200`.
+module AKSB200
+
+using AtomicKohnSham
+using AtomicKohnSham: KSESolver, KSESolution, init_cache!, register!, callback!, findindex
+using LinearAlgebra, SparseArrays
+
+const LIB = get(ENV, "AKS_B200_LIB", "libaks_b200.so")
+
+struct IterRecord              # aks_iter_record
+    niter::Int32; status::Int32
+    stop::Float64; Etot::Float64; Ekin::Float64; Ecou::Float64; Ehar::Float64; Eexc::Float64; t::Float64
+end
+
+struct DiscDesc                # aks_disc_desc (field order must match the header)
+    dtype::Int32; p::Int32; C::Int32; Nh::Int32; Q::Int32; G::Int32; lh::Int32; nh::Int32; nspin::Int32
+    mesh::Ptr{Float64}; invshifts::Ptr{Float64}; x::Ptr{Float64}; w::Ptr{Float64}; Pgenx::Ptr{Float64}
+    y::Ptr{Float64}; wy::Ptr{Float64}; ycell::Ptr{Int64}; Pgeny::Ptr{Float64}
+    M0::Ptr{Float64}; A::Ptr{Float64}; Mm1::Ptr{Float64}; Mm2::Ptr{Float64}
+    nF::Int64; Fi::Ptr{Int64}; Fj::Ptr{Int64}; Fm::Ptr{Int64}; Fv::Ptr{Float64}
+    cell_len::Ptr{Int64}; cell_indices::Ptr{Int64}; cell_generators::Ptr{Int64}
+end
+
+check(ctx, rc) = rc == 0 || rc == -3 ||   # AKS_ENOTCONV is reported through the status words
+    error("aks_b200: status $rc: " * unsafe_string(ccall((:aks_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx)))
+
+xc_id(f) = f isa AtomicKohnSham.NoFunctional ? Int32(0) :
+           f.identifier == :lda_x ? Int32(1) : f.identifier == :lda_c_pw ? Int32(12) :
+           error("backend :b200 supports lda_x / lda_c_pw only")
+
+"""
+    groundstate_b200(models, disc, alg; maxiter = 100, callback = nothing, device = 0)
+
+Drop-in for `groundstate` on one model or a vector of models sharing `disc`.  The tables are the ones
+`init_cache!` / `GaussLegendre` build on the host; every SCF iteration is one `aks_scf_step`.
+"""
+function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, callback = nothing, device = 0)
+    basis, q = disc.basis, disc.fem_integration_method
+    init_cache!(disc, first(models))                      # A, M0, M-1, M-2, F (host, once)
+    ops = disc.femops
+    p = basis.generators.ordermax; C = length(basis.mesh) - 1; n = p + 1
+    # tables the reference recomputes on the fly, built once here
+    ycell = Int64[findindex(basis.mesh, yy) for yy in q.y]
+    Pgeny = hcat((begin ϕ = basis.shifts[c]; AtomicKohnSham.evaluate(basis.generators.polynomials, ϕ[1]*yy + ϕ[2]) end
+                  for (c, yy) in zip(ycell, q.y))...)
+    cell_len = Int64[length(v) for v in basis.cells_to_indices]
+    cidx = zeros(Int64, n, C); cgen = zeros(Int64, n, C)   # column c = cell c  (== row-major [C][p+1] in C)
+    for c in 1:C
+        cidx[1:cell_len[c], c] .= basis.cells_to_indices[c]; cgen[1:cell_len[c], c] .= basis.cells_to_generators[c]
+    end
+    invsh = Float64[v for s in basis.invshifts for v in s]
+    Fk = collect(keys(ops.F)); Fi = Int64[k[1] for k in Fk]; Fj = Int64[k[2] for k in Fk]; Fm = Int64[k[3] for k in Fk]
+    Fv = Float64[ops.F[k] for k in Fk]
+    A = Matrix(ops.A); Mm1 = Matrix(ops.M₋₁); Mm2 = Matrix(ops.M₋₂); mesh = collect(Float64, basis.mesh.points)
+    ctx = Ref{Ptr{Cvoid}}(); dh = Ref{Ptr{Cvoid}}(); bh = Ref{Ptr{Cvoid}}()
+    check(C_NULL, ccall((:aks_ctx_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ctx))
+    GC.@preserve mesh invsh q ops A Mm1 Mm2 Fi Fj Fm Fv cell_len cidx cgen ycell Pgeny begin
+        desc = DiscDesc(0, p, C, disc.Nₕ, q.npoints, q.npoints, disc.lₕ, disc.nₕ, disc.nspin,
+            pointer(mesh), pointer(invsh), pointer(q.x), pointer(q.w), pointer(q.Pgenx), pointer(q.y), pointer(q.wy),
+            pointer(ycell), pointer(Pgeny), pointer(ops.M₀), pointer(A), pointer(Mm1), pointer(Mm2),
+            length(Fv), pointer(Fi), pointer(Fj), pointer(Fm), pointer(Fv), pointer(cell_len), pointer(cidx), pointer(cgen))
+        check(ctx[], ccall((:aks_disc_create, LIB), Cint, (Ptr{Cvoid}, Ref{DiscDesc}, Ref{Ptr{Cvoid}}), ctx[], desc, dh))
+    end
+    nprob = length(models)
+    Z = Float64[m.Z for m in models]; N = Float64[m.N for m in models]; har = Float64[m.hartree for m in models]
+    ex = Int32[xc_id(m.exchange) for m in models]; ec = Int32[xc_id(m.correlation) for m in models]
+    check(ctx[], ccall((:aks_batch_create, LIB), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+        dh[], nprob, Z, N, har, ex, ec, C_NULL, C_NULL, bh))
+    a = alg.aufbau
+    check(ctx[], ccall((:aks_batch_set_oda, LIB), Cint,
+        (Ptr{Cvoid}, Float64, Float64, Int32, Int32, Float64, Float64, Int32, Float64, Int32),
+        bh[], alg.scftol, alg.tinit, alg.frozen_t, alg.maxiter_ls, alg.abstol_ls, alg.reltol_ls,
+        a.max_degen, a.tol, a.handle_degen_spin_1iter))
+    # solve!: one ccall per iteration so that register!/callback! fire as in groundstate.jl:55-57
+    solvers = [KSESolver(m, disc, alg; maxiter = maxiter, callback = callback) for m in models]
+    recs = Vector{IterRecord}(undef, nprob)
+    for it in 1:maxiter
+        check(ctx[], ccall((:aks_scf_step, LIB), Cint, (Ptr{Cvoid}, Ptr{IterRecord}), bh[], recs))
+        running = false
+        for (s, r) in zip(solvers, recs)
+            r.niter == it || continue                       # this problem had already stopped
+            s.stopping_criteria = r.stop
+            e = s.energies; e.Etot, e.Ekin, e.Ecou, e.Ehar, e.Eexc = r.Etot, r.Ekin, r.Ecou, r.Ehar, r.Eexc
+            s.algcache.t = r.t
+            register!(s); callback!(s.callback, s); s.niter += 1
+            running |= r.status == 0
+        end
+        running || break
+    end
+    # copy D, U, ϵ, n, W back into the ODACache so that KSESolution(solver, name) works untouched
+    sols = map(enumerate(solvers)) do (i, s)
+        c = s.algcache
+        W = disc.cache.hartw.W
+        check(ctx[], ccall((:aks_get_state, LIB), Cint,
+            (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            bh[], i - 1, c.D, c.U, c.ϵ, c.n, isempty(W) ? C_NULL : W))
+        KSESolution(s, AtomicKohnSham.solution_name(models[i]))
+    end
+    ccall((:aks_batch_destroy, LIB), Cvoid, (Ptr{Cvoid},), bh[])
+    ccall((:aks_disc_destroy, LIB), Cvoid, (Ptr{Cvoid},), dh[])
+    ccall((:aks_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
+    sols
+end
+
+groundstate_b200(model::KSEModel, disc, alg; kw...) = only(groundstate_b200([model], disc, alg; kw...))
+
+end # module
