@@ -324,13 +324,19 @@ extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** 
     if (c < 1 || c > C) { ctx->err = "ycell out of range"; delete disc; return AKS_EINVAL; }
     ycell[q] = (int)c - 1;
   }
+  std::vector<int> lo_tab((size_t)n * n), pk_tab((size_t)n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      lo_tab[(size_t)i * n + j] = (j > i) ? j * n + i : i * n + j;
+      pk_tab[(size_t)i * n + j] = (j <= i) ? pk_index(i, j, nb) : -1;
+    }
   std::vector<double> xv(D->x, D->x + Q), wv(D->w, D->w + Q), yv(D->y, D->y + G), wyv(D->wy, D->wy + G);
   int rc;
 #define UP(vec, field)                                                                          \
   if ((rc = dev_upload(ctx, disc->allocs, vec, &dv.field)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
   UP(Pg, Pg) UP(wv, w) UP(xv, x) UP(inv1, inv1) UP(inv2, inv2) UP(Al, A_loc) UP(M0l, M0_loc) UP(M1l, Mm1_loc)
   UP(M2l, Mm2_loc) UP(M0pk, M0pk) UP(Fl, F_loc) UP(l2g, l2g) UP(yv, y) UP(wyv, wy) UP(ycell, ycell) UP(Pgy, Pgy)
-  UP(Abbinv, Abb_inv) UP(XA, XA) UP(triD, triA_d) UP(triL, triA_l) UP(Linv, Linv)
+  UP(lo_tab, lo_tab) UP(pk_tab, pk_tab) UP(Abbinv, Abb_inv) UP(XA, XA) UP(triD, triA_d) UP(triL, triA_l) UP(Linv, Linv)
 #undef UP
   *out = disc;
   return AKS_OK;

@@ -25,6 +25,8 @@ struct DiscDev {
   const double* M0pk;    // [C][npk]  packed (hh | hb | bb lower), see pk_index()
   const double* F_loc;   // [C][n (m)][n*n (ij)], symmetric in ij
   const int* l2g;        // [C][n]   global index or -1
+  const int* lo_tab;     // [n*n]    idx -> index of its lower-triangle twin
+  const int* pk_tab;     // [n*n]    idx -> packed index (pk_index) or -1 above the diagonal
   const double* y;       // [G]
   const double* wy;      // [G]
   const int* ycell;      // [G]   0-based cell

@@ -213,12 +213,15 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
     double scale = 0.0;
     int neg = 0;
     double dprev_inv = 0.0, y0p = 0.0, y1p = 0.0, s00 = 0.0, s10 = 0.0, s11 = 0.0;
-    for (int j = 0; j < nb; ++j) {
-      const double tdj = R[j * C + c] - sigma;
+    const int nbC = nb * C;
+    const double* Rj = R + c;      // field td, advanced by C per step
+    double* Fj = F + c;
+    for (int j = 0; j < nb; ++j, Rj += C, Fj += C) {
+      const double tdj = Rj[0] - sigma;
       scale = fmax(scale, fabs(tdj));
       double lj = 0.0, dj = tdj;
       if (j > 0) {
-        const double te = R[(nb + j - 1) * C + c];
+        const double te = Rj[nbC - C];
         lj = te * dprev_inv;
         dj = tdj - lj * te;
       }
@@ -226,17 +229,17 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
       if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
       neg += (dj < 0.0);
       const double dinv = 1.0 / dj;
-      const double g0 = R[(2 * nb + j) * C + c] - sigma * R[(4 * nb + j) * C + c];
-      const double g1 = R[(3 * nb + j) * C + c] - sigma * R[(5 * nb + j) * C + c];
+      const double g0 = Rj[2 * nbC] - sigma * Rj[4 * nbC];
+      const double g1 = Rj[3 * nbC] - sigma * Rj[5 * nbC];
       const double y0 = g0 - lj * y0p, y1 = g1 - lj * y1p;
       s00 = fma(y0 * dinv, y0, s00);
       s10 = fma(y1 * dinv, y0, s10);
       s11 = fma(y1 * dinv, y1, s11);
       if (store) {
-        F[j * C + c] = dinv;
-        F[(nb + j) * C + c] = lj;
-        F[(2 * nb + j) * C + c] = y0 * dinv;
-        F[(3 * nb + j) * C + c] = y1 * dinv;
+        Fj[0] = dinv;
+        Fj[nbC] = lj;
+        Fj[2 * nbC] = y0 * dinv;
+        Fj[3 * nbC] = y1 * dinv;
       }
       dprev_inv = dinv; y0p = y0; y1p = y1;
     }
