@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(AKS_NT) k_dens_cells(DiscDev d, BatchDev b) {
   if (b.status[p] != 0) return;
   if (slot == 1 && !b.degen[p]) return;
   __shared__ OccList L;
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm_dc[];
+  double* sm = sm_dc;
   const int n = d.n, Q = d.Q, C = d.C, s = b.s;
   double* us = sm;                              // [count][NMAX]
   double* Dl = us + (size_t)AKS_MAXORB * NMAX;  // [n*n]
@@ -251,10 +252,15 @@ __global__ void __launch_bounds__(AKS_NT) k_dens_cells(DiscDev d, BatchDev b) {
     for (int i = 0; i < NMAX; ++i) g[i] = (i < n) ? d.Pg[(size_t)i * d.Qs + q] : 0.0;
     double r0 = 0.0, r1 = 0.0;
     for (int o = 0; o < cnt; ++o) {
-      const double* uo = us + (size_t)o * NMAX;
-      double psi = 0.0;
+      const double2* uo = reinterpret_cast<const double2*>(us + (size_t)o * NMAX);   // broadcast LDS.128
+      double psa = 0.0, psb = 0.0;
 #pragma unroll
-      for (int i = 0; i < NMAX; ++i) psi = fma(uo[i], g[i], psi);
+      for (int i = 0; i < NMAX / 2; ++i) {
+        const double2 u2 = uo[i];
+        psa = fma(u2.x, g[2 * i], psa);
+        psb = fma(u2.y, g[2 * i + 1], psb);
+      }
+      const double psi = psa + psb;
       const double t = L.n[o] * psi * psi;
       if (L.e[o] == 0) r0 += t; else r1 += t;
     }
@@ -638,30 +644,31 @@ __global__ void k_mix_state(DiscDev d, BatchDev b) {
 // ------------------------------------------------------------------------------------------
 // k_mix_dense: the dense density matrix D = sum n u u^T (density!, density.jl:15-41), mixed in
 // place, and the Frobenius norm of the update (stopping rule, oda/loop.jl:43-45).  Pure HBM
-// streaming: read D, write D; the trial D is never materialised.  One CTA per 64x64 tile, 16 entries
-// per thread whose old values are all requested before the rank-n_occ update is accumulated.
+// streaming: read D, write D; the trial D is never materialised.  One CTA per 64x64 tile; each thread
+// owns a 4x4 block (8 shared loads per 16 FMAs of the rank-n_occ update), whose old values are all
+// requested before the update is accumulated.
 #define MIX_TS 64
 #define MIX_OCH 16   // orbitals per staging chunk
-__global__ void __launch_bounds__(AKS_NT, 3) k_mix_dense(DiscDev d, BatchDev b) {
+__global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) {
   const int p = blockIdx.z, e = blockIdx.y;
   if (b.status[p] != 0) return;
-  __shared__ double Ui[MIX_OCH][MIX_TS + 1];
-  __shared__ double Uj[MIX_OCH][MIX_TS + 1];
+  __shared__ double Ui[MIX_OCH][MIX_TS];
+  __shared__ double Uj[MIX_OCH][MIX_TS];
   __shared__ double nk[AKS_MAXORB];
   __shared__ int oidx[AKS_MAXORB];
   __shared__ int cnt_s, first_s;
   __shared__ double red[AKS_NW];
   const int Nh = d.Nh, nt = b.ntile;
   const int tr = blockIdx.x / nt, tc = blockIdx.x - tr * nt;
-  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;   // 4 row groups x 64 columns
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 entries each
+  const int r0 = tr * MIX_TS + 4 * ty, c0 = tc * MIX_TS + 4 * tx;
   double* D = b.Dd + ((size_t)p * b.s + e) * Nh * Nh;
-  // request the old tile first: these loads overlap the staging and the update below
-  double old[16];
+  double old[4][4];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int gi = tr * MIX_TS + ry + 4 * r, gj = tc * MIX_TS + cx;
-    old[r] = (gi < Nh && gj < Nh) ? D[(size_t)gi * Nh + gj] : 0.0;
-  }
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      old[a][c] = (r0 + a < Nh && c0 + c < Nh) ? D[(size_t)(r0 + a) * Nh + c0 + c] : 0.0;
   {
     // the list is ordered by spin: entries of spin e are contiguous
     const int tot = b.occ_cnt[2 * p];
@@ -680,9 +687,11 @@ __global__ void __launch_bounds__(AKS_NT, 3) k_mix_dense(DiscDev d, BatchDev b) 
   const int cnt = cnt_s;
   const double t = b.tmix[p];
   const double* Ubase = b.U + (((size_t)p * b.s + e) * b.Lmax * b.nhmax) * Nh;
-  double dn[16];
+  double dn[4][4];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) dn[r] = 0.0;
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dn[a][c] = 0.0;
   for (int o0 = 0; o0 < cnt; o0 += MIX_OCH) {
     const int oc = min(MIX_OCH, cnt - o0);
     __syncthreads();
@@ -690,27 +699,30 @@ __global__ void __launch_bounds__(AKS_NT, 3) k_mix_dense(DiscDev d, BatchDev b) 
       const int o = idx / MIX_TS, r = idx - o * MIX_TS;
       const double* u = Ubase + (size_t)oidx[o0 + o] * Nh;
       const int gi = tr * MIX_TS + r, gj = tc * MIX_TS + r;
-      Ui[o][r] = (gi < Nh) ? u[gi] : 0.0;
+      Ui[o][r] = (gi < Nh) ? nk[o0 + o] * u[gi] : 0.0;   // occupation folded into the row factor
       Uj[o][r] = (gj < Nh) ? u[gj] : 0.0;
     }
     __syncthreads();
     for (int o = 0; o < oc; ++o) {
-      const double ujc = nk[o0 + o] * Uj[o][cx];
-#pragma unroll
-      for (int r = 0; r < 16; ++r) dn[r] = fma(Ui[o][ry + 4 * r], ujc, dn[r]);
+      const double a0 = Ui[o][4 * ty], a1 = Ui[o][4 * ty + 1], a2 = Ui[o][4 * ty + 2], a3 = Ui[o][4 * ty + 3];
+      const double b0 = Uj[o][4 * tx], b1 = Uj[o][4 * tx + 1], b2 = Uj[o][4 * tx + 2], b3 = Uj[o][4 * tx + 3];
+      dn[0][0] = fma(a0, b0, dn[0][0]); dn[0][1] = fma(a0, b1, dn[0][1]); dn[0][2] = fma(a0, b2, dn[0][2]); dn[0][3] = fma(a0, b3, dn[0][3]);
+      dn[1][0] = fma(a1, b0, dn[1][0]); dn[1][1] = fma(a1, b1, dn[1][1]); dn[1][2] = fma(a1, b2, dn[1][2]); dn[1][3] = fma(a1, b3, dn[1][3]);
+      dn[2][0] = fma(a2, b0, dn[2][0]); dn[2][1] = fma(a2, b1, dn[2][1]); dn[2][2] = fma(a2, b2, dn[2][2]); dn[2][3] = fma(a2, b3, dn[2][3]);
+      dn[3][0] = fma(a3, b0, dn[3][0]); dn[3][1] = fma(a3, b1, dn[3][1]); dn[3][2] = fma(a3, b2, dn[3][2]); dn[3][3] = fma(a3, b3, dn[3][3]);
     }
   }
   double acc = 0.0;
 #pragma unroll
-  for (int r = 0; r < 16; ++r) {
-    const int gi = tr * MIX_TS + ry + 4 * r, gj = tc * MIX_TS + cx;
-    if (gi < Nh && gj < Nh) {
-      const double nv = t * dn[r] + (1.0 - t) * old[r];
-      D[(size_t)gi * Nh + gj] = nv;
-      const double df = nv - old[r];
-      acc = fma(df, df, acc);
-    }
-  }
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (r0 + a < Nh && c0 + c < Nh) {
+        const double nv = t * dn[a][c] + (1.0 - t) * old[a][c];
+        D[(size_t)(r0 + a) * Nh + c0 + c] = nv;
+        const double df = nv - old[a][c];
+        acc = fma(df, df, acc);
+      }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) b.norm_part[((size_t)p * b.s + e) * nt * nt + blockIdx.x] = acc;
 }

@@ -30,6 +30,9 @@ RANK_SWEEPS = [("lda_x", "lda_c_pw", 0), ("lda_x", "lda_c_pw", 1), ("lda_x", Non
                ("lda_x", "lda_c_pw", 2), ("lda_x", None, 2), ("lda_x", "lda_c_pw", 3), ("lda_x", None, 3)]
 
 
+_RESULT_LINE = []   # the single JSON record, printed by main() on the real stdout
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -41,7 +44,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -245,7 +248,7 @@ def b200_arm(args):
                     "what": "Batch() + K x aks_scf_step with host records + aks_get_state(eps,n,W) of every atom"},
             "roofline": roof, "phases_ms": phases, "cpu_baseline": cpu, "sweep_to_convergence": sweep,
         }
-        print(json.dumps(line))
+        _RESULT_LINE.append(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -328,7 +331,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": len(Zs), "kind": "port",
                              "sample": f"{args.steps} steps x {len(Zs)} atoms, numpy/LAPACK oracle (Julia reference cannot run: no julia in the image)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _RESULT_LINE.append(json.dumps(line))
 
 
 def main():
@@ -340,10 +343,22 @@ def main():
     ap.add_argument("--sweeps", type=int, default=1, help="periodic-table sweeps per GPU (default 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
-        reference_arm(args)
-    else:
-        b200_arm(args)
+    # stdout carries exactly ONE line (the JSON record): anything libraries print there (e.g. NCCL's version
+    # banner under torchrun) is sent to stderr instead.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            reference_arm(args)
+        else:
+            b200_arm(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _RESULT_LINE:
+        print(_RESULT_LINE[0], flush=True)
 
 
 if __name__ == "__main__":

@@ -99,7 +99,7 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, 
         check(ctx[], ccall((:aks_get_state, LIB), Cint,
             (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
             bh[], i - 1, c.D, c.U, c.ϵ, c.n, isempty(W) ? C_NULL : W))
-        KSESolution(s, AtomicKohnSham.solution_name(models[i]))
+        KSESolution(s, _solution_name(models[i]))
     end
     ccall((:aks_batch_destroy, LIB), Cvoid, (Ptr{Cvoid},), bh[])
     ccall((:aks_disc_destroy, LIB), Cvoid, (Ptr{Cvoid},), dh[])
@@ -108,5 +108,15 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, 
 end
 
 groundstate_b200(model::KSEModel, disc, alg; kw...) = only(groundstate_b200([model], disc, alg; kw...))
+
+
+# same naming as groundstate (src/solver/groundstate.jl:24-34)
+function _solution_name(model)
+    Z, N = model.Z, model.N
+    floor(Z) == Z || return "Z=$Z, N=$N"
+    sym = AtomicKohnSham.ATOMIC_NUMBER_TO_NAME[Int(Z)]
+    dq = Z - N
+    iszero(dq) ? sym : sym * string(abs(dq)) * (dq > 0 ? "+" : "-")
+end
 
 end # module
