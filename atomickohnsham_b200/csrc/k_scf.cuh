@@ -645,7 +645,7 @@ __global__ void k_mix_state(DiscDev d, BatchDev b) {
 // k_mix_dense: the dense density matrix D = sum n u u^T (density!, density.jl:15-41), mixed in
 // place, and the Frobenius norm of the update (stopping rule, oda/loop.jl:43-45).  Pure HBM
 // streaming: read D, write D; the trial D is never materialised.  One CTA per 64x64 tile; each thread
-// owns a 4x4 block (8 shared loads per 16 FMAs of the rank-n_occ update), whose old values are all
+// owns 4 rows x 4 strided columns (8 shared loads per 16 FMAs of the rank-n_occ update), whose old values are all
 // requested before the update is accumulated.
 #define MIX_TS 64
 #define MIX_OCH 16   // orbitals per staging chunk
@@ -661,14 +661,14 @@ __global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) 
   const int Nh = d.Nh, nt = b.ntile;
   const int tr = blockIdx.x / nt, tc = blockIdx.x - tr * nt;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 entries each
-  const int r0 = tr * MIX_TS + 4 * ty, c0 = tc * MIX_TS + 4 * tx;
+  const int r0 = tr * MIX_TS + 4 * ty, c0 = tc * MIX_TS + tx;   // columns c0 + 16 c: coalesced rows
   double* D = b.Dd + ((size_t)p * b.s + e) * Nh * Nh;
   double old[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      old[a][c] = (r0 + a < Nh && c0 + c < Nh) ? D[(size_t)(r0 + a) * Nh + c0 + c] : 0.0;
+      old[a][c] = (r0 + a < Nh && c0 + 16 * c < Nh) ? D[(size_t)(r0 + a) * Nh + c0 + 16 * c] : 0.0;
   {
     // the list is ordered by spin: entries of spin e are contiguous
     const int tot = b.occ_cnt[2 * p];
@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) 
     __syncthreads();
     for (int o = 0; o < oc; ++o) {
       const double a0 = Ui[o][4 * ty], a1 = Ui[o][4 * ty + 1], a2 = Ui[o][4 * ty + 2], a3 = Ui[o][4 * ty + 3];
-      const double b0 = Uj[o][4 * tx], b1 = Uj[o][4 * tx + 1], b2 = Uj[o][4 * tx + 2], b3 = Uj[o][4 * tx + 3];
+      const double b0 = Uj[o][tx], b1 = Uj[o][tx + 16], b2 = Uj[o][tx + 32], b3 = Uj[o][tx + 48];
       dn[0][0] = fma(a0, b0, dn[0][0]); dn[0][1] = fma(a0, b1, dn[0][1]); dn[0][2] = fma(a0, b2, dn[0][2]); dn[0][3] = fma(a0, b3, dn[0][3]);
       dn[1][0] = fma(a1, b0, dn[1][0]); dn[1][1] = fma(a1, b1, dn[1][1]); dn[1][2] = fma(a1, b2, dn[1][2]); dn[1][3] = fma(a1, b3, dn[1][3]);
       dn[2][0] = fma(a2, b0, dn[2][0]); dn[2][1] = fma(a2, b1, dn[2][1]); dn[2][2] = fma(a2, b2, dn[2][2]); dn[2][3] = fma(a2, b3, dn[2][3]);
@@ -717,9 +717,9 @@ __global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) 
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      if (r0 + a < Nh && c0 + c < Nh) {
+      if (r0 + a < Nh && c0 + 16 * c < Nh) {
         const double nv = t * dn[a][c] + (1.0 - t) * old[a][c];
-        D[(size_t)(r0 + a) * Nh + c0 + c] = nv;
+        D[(size_t)(r0 + a) * Nh + c0 + 16 * c] = nv;
         const double df = nv - old[a][c];
         acc = fma(df, df, acc);
       }
