@@ -418,7 +418,10 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   }
   CK(cudaFuncSetAttribute(k_potential, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
   CK(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
-  CK(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
+  CK(cudaFuncSetAttribute(k_reduce<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
+  CK(cudaFuncSetAttribute(k_reduce<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
+  CK(cudaFuncSetAttribute(k_reduce<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
+  CK(cudaFuncSetAttribute(k_reduce<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
   CK(cudaFuncSetAttribute(k_eig_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_chan));
   CK(cudaFuncSetAttribute(k_eig_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_chan));
   CK(cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_poisson));
@@ -509,7 +512,15 @@ static int launch_eig(aks_batch* bt) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   const BatchDev& b = bt->dev;
-  k_reduce<<<dim3((dv.C + AKS_NW - 1) / AKS_NW, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_red, ctx->stream>>>(dv, b);
+  {
+    const dim3 grid((dv.C + RED_NW - 1) / RED_NW, b.Lmax * b.s, bt->B);
+    switch (reduce_nbm(dv.nb)) {
+      case 8: k_reduce<8><<<grid, RED_NT, bt->smem_red, ctx->stream>>>(dv, b); break;
+      case 12: k_reduce<12><<<grid, RED_NT, bt->smem_red, ctx->stream>>>(dv, b); break;
+      case 20: k_reduce<20><<<grid, RED_NT, bt->smem_red, ctx->stream>>>(dv, b); break;
+      default: k_reduce<28><<<grid, RED_NT, bt->smem_red, ctx->stream>>>(dv, b); break;
+    }
+  }
   LAUNCH_CHECK();
   k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();

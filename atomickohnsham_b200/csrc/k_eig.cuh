@@ -39,135 +39,217 @@
 __host__ __device__ inline int red_stride(int nb) { return 6 * nb + 4; }
 
 // ------------------------------------------------------------------------------------------
-// k_reduce: one warp per (problem, channel, cell)
+// k_reduce: one warp per (problem, channel, cell); lane i owns ROW i of the symmetric block C and
+// COLUMN i of P, both in registers (NBM = nb rounded up, zero padded; every register index is a
+// compile-time constant).  Shared memory holds only what all lanes read at the same address
+// (H_bb, L^-1, the Householder vectors v and w: broadcast 128-bit loads) and the final P.
+#define RED_NT 128
+#define RED_NW (RED_NT / 32)
+__host__ __device__ inline int reduce_nbm(int nb) { return nb <= 8 ? 8 : nb <= 12 ? 12 : nb <= 20 ? 20 : 28; }
 __host__ __device__ inline size_t reduce_smem_bytes(int nb) {
-  const int ld = nb | 1;
-  return sizeof(double) * (size_t)AKS_NW * (2 * nb * ld + 8);
+  const int nbm = reduce_nbm(nb);
+  return sizeof(double) * (size_t)RED_NW * (3 * nbm * nbm + nbm + 2 * 32);
 }
 
-__global__ void __launch_bounds__(AKS_NT)
+template <int NBM>
+__global__ void __launch_bounds__(RED_NT)
 k_reduce(DiscDev d, BatchDev b) {
   const int p = blockIdx.z, ch = blockIdx.y;
   if (b.status[p] != 0) return;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
   if (l >= b.Lp[p]) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * AKS_NW + warp;
-  const int nb = d.nb, npk = d.npk, C = d.C, ld = nb | 1;
+  const int c = blockIdx.x * RED_NW + warp;
+  const int nb = d.nb, npk = d.npk, C = d.C;
   if (c >= C) return;
-  extern __shared__ double sm[];
-  double* Cs = sm + (size_t)warp * (2 * nb * ld + 8);
-  double* Ps = Cs + nb * ld;
+  constexpr int LDP = NBM | 1;
+  extern __shared__ __align__(16) double sm_red[];
+  double* Hs = sm_red + (size_t)warp * (3 * NBM * NBM + NBM + 64);   // [NBM][NBM]  H_bb (zero padded)
+  double* Ls = Hs + NBM * NBM;                                       // [NBM][NBM]  L^-1 (lower, zero padded)
+  double* Ps = Ls + NBM * NBM;                                       // [NBM][LDP]  final P
+  double* vs = Hs + 3 * NBM * NBM + NBM;                             // [32], 16-byte aligned (NBM is even)
+  double* ws = vs + 32;
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
   const double* Hc = b.Hpk + (chan * C + c) * npk;
   const double* Mc = d.M0pk + (size_t)c * npk;
   const double* Li = d.Linv + (size_t)c * nb * nb;
   const int off = 3 + 2 * nb;
   const int i = lane;
-  // 1. H_bb, full symmetric
-  for (int idx = lane; idx < nb * nb; idx += 32) {
-    const int r = idx / nb, cc = idx - r * nb;
+  // 1. stage H_bb (full symmetric) and L^-1
+  for (int idx = lane; idx < NBM * NBM; idx += 32) {
+    const int r = idx / NBM, cc = idx - r * NBM;
     const int hi = r >= cc ? r : cc, lo = r >= cc ? cc : r;
-    Cs[r * ld + cc] = Hc[off + hi * (hi + 1) / 2 + lo];
+    const bool in = (r < nb) && (cc < nb);
+    Hs[idx] = in ? Hc[off + hi * (hi + 1) / 2 + lo] : 0.0;
+    Ls[idx] = (in && cc <= r) ? Li[r * nb + cc] : 0.0;
   }
   __syncwarp();
-  // 2. A = Linv * H  (row i per lane) -> Ps
-  if (i < nb)
-    for (int j = 0; j < nb; ++j) {
-      double acc = 0.0;
-      for (int k = 0; k <= i; ++k) acc = fma(Li[i * nb + k], Cs[k * ld + j], acc);
-      Ps[i * ld + j] = acc;
+  const int ir = (i < NBM) ? i : 0;   // padded lanes compute on row 0 and are masked at the stores
+  const bool act = i < nb;
+  // 2. A = L^-1 H : row i in registers
+  double row[NBM];
+#pragma unroll
+  for (int j = 0; j < NBM; ++j) row[j] = 0.0;
+  {
+    double lrow[NBM];
+#pragma unroll
+    for (int k = 0; k < NBM; ++k) lrow[k] = act ? Ls[ir * NBM + k] : 0.0;
+#pragma unroll
+    for (int k = 0; k < NBM; ++k) {
+      const double a = lrow[k];
+      const double2* h2 = reinterpret_cast<const double2*>(Hs + k * NBM);
+#pragma unroll
+      for (int j = 0; j < NBM / 2; ++j) {
+        const double2 h = h2[j];
+        row[2 * j] = fma(a, h.x, row[2 * j]);
+        row[2 * j + 1] = fma(a, h.y, row[2 * j + 1]);
+      }
     }
-  __syncwarp();
-  // 3. C = A * Linv^T (lower triangle computed, mirrored)
-  if (i < nb)
-    for (int j = 0; j <= i; ++j) {
-      double acc = 0.0;
-      for (int k = 0; k <= j; ++k) acc = fma(Ps[i * ld + k], Li[j * nb + k], acc);
-      Cs[i * ld + j] = acc;
+  }
+  // 3. C = A L^-T : C[i][j] = sum_k A[i][k] Linv[j][k]  (row i stays in registers)
+  {
+    double crow[NBM];
+#pragma unroll
+    for (int j = 0; j < NBM; ++j) {
+      const double2* l2 = reinterpret_cast<const double2*>(Ls + j * NBM);
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < (j + 2) / 2; ++k) {   // Linv[j][k] = 0 for k > j
+        const double2 lv = l2[k];
+        a0 = fma(row[2 * k], lv.x, a0);
+        a1 = fma(row[2 * k + 1], lv.y, a1);
+      }
+      crow[j] = a0 + a1;
     }
+#pragma unroll
+    for (int j = 0; j < NBM; ++j) row[j] = crow[j];
+  }
+  // symmetrise exactly: C[i][j] for j > i is taken from lane j's C[j][i]
+#pragma unroll
+  for (int j = 0; j < NBM; ++j) {
+    // value C[j][i] lives in lane j as row[i] (runtime index there): exchange through shared memory
+    if (i < NBM) Ps[i * LDP + j] = row[j];
+  }
   __syncwarp();
-  if (i < nb)
-    for (int j = 0; j < i; ++j) Cs[j * ld + i] = Cs[i * ld + j];
-  // 4. P = Linv
-  if (i < nb)
-    for (int j = 0; j < nb; ++j) Ps[i * ld + j] = (j <= i) ? Li[i * nb + j] : 0.0;
+#pragma unroll
+  for (int j = 0; j < NBM; ++j)
+    if (j > i) row[j] = Ps[j * LDP + ir];
   __syncwarp();
+  // 4. P = L^-1 : column i in registers
+  double pcol[NBM];
+#pragma unroll
+  for (int m = 0; m < NBM; ++m) pcol[m] = act ? Ls[m * NBM + ir] : 0.0;
   double* red = b.red + (chan * C + c) * red_stride(nb);
-  // 5. Householder tridiagonalisation, P <- H_k P
-  for (int k = 0; k + 2 < nb; ++k) {
-    const double x = (i > k && i < nb) ? Cs[i * ld + k] : 0.0;
-    const double sig2 = warp_sum((i > k + 1) ? x * x : 0.0);
-    const double xk1 = __shfl_sync(0xffffffffu, x, k + 1);
-    if (lane == 0) red[k] = Cs[k * ld + k];
-    if (sig2 == 0.0) {  // already tridiagonal in this column (warp-uniform)
-      if (lane == 0) red[nb + k] = xk1;
-      continue;
+  // 5. Householder tridiagonalisation C <- H_k C H_k, P <- H_k P
+#pragma unroll
+  for (int k = 0; k + 2 < NBM; ++k) {
+    if (k + 2 < nb) {
+      const double x = (i > k && act) ? row[k] : 0.0;
+      const double sig2 = warp_sum((i > k + 1) ? x * x : 0.0);
+      const double xk1 = __shfl_sync(0xffffffffu, x, k + 1);
+      const double dk = __shfl_sync(0xffffffffu, row[k], k);
+      if (lane == 0) red[k] = dk;
+      if (sig2 == 0.0) {  // already tridiagonal in this column (warp-uniform)
+        if (lane == 0) red[nb + k] = xk1;
+      } else {
+        const double alpha = -copysign(sqrt(xk1 * xk1 + sig2), xk1);
+        const double vk1 = xk1 - alpha;
+        const double v = (i == k + 1) ? vk1 : ((i > k + 1) ? x : 0.0);
+        const double tau = 2.0 / (sig2 + vk1 * vk1);
+        if (lane == 0) red[nb + k] = alpha;
+        vs[lane] = v;
+        __syncwarp();
+        const int j0 = (k + 1) / 2;   // v[j] = 0 for j <= k: start at the even index below k+1
+        const double2* v2 = reinterpret_cast<const double2*>(vs);
+        double pa = 0.0, pb = 0.0;
+#pragma unroll
+        for (int j = 0; j < NBM / 2; ++j) {
+          if (j < j0) continue;   // folds after unrolling
+          const double2 vv = v2[j];
+          pa = fma(row[2 * j], vv.x, pa);
+          pb = fma(row[2 * j + 1], vv.y, pb);
+        }
+        const double pacc = (i > k && act) ? (pa + pb) * tau : 0.0;
+        const double K = 0.5 * tau * warp_sum(pacc * v);
+        const double w = pacc - K * v;
+        ws[lane] = w;
+        __syncwarp();
+        const double2* w2 = reinterpret_cast<const double2*>(ws);
+#pragma unroll
+        for (int j = 0; j < NBM / 2; ++j) {
+          if (j < j0) continue;
+          const double2 vv = v2[j], ww = w2[j];
+          row[2 * j] -= v * ww.x + w * vv.x;
+          row[2 * j + 1] -= v * ww.y + w * vv.y;
+        }
+        // P <- (I - tau v v^T) P, lane = column
+        double ta = 0.0, tb = 0.0;
+#pragma unroll
+        for (int m = 0; m < NBM / 2; ++m) {
+          if (m < j0) continue;
+          const double2 vv = v2[m];
+          ta = fma(vv.x, pcol[2 * m], ta);
+          tb = fma(vv.y, pcol[2 * m + 1], tb);
+        }
+        const double t = (ta + tb) * tau;
+#pragma unroll
+        for (int m = 0; m < NBM / 2; ++m) {
+          if (m < j0) continue;
+          const double2 vv = v2[m];
+          pcol[2 * m] -= vv.x * t;
+          pcol[2 * m + 1] -= vv.y * t;
+        }
+        __syncwarp();
+      }
     }
-    const double alpha = -copysign(sqrt(xk1 * xk1 + sig2), xk1);
-    const double v = (i == k + 1) ? xk1 - alpha : ((i > k + 1) ? x : 0.0);
-    const double vk1 = xk1 - alpha;
-    const double tau = 2.0 / (sig2 + vk1 * vk1);
-    if (lane == 0) red[nb + k] = alpha;
-    double pacc = 0.0;
-    for (int j = k + 1; j < nb; ++j) {
-      const double vj = __shfl_sync(0xffffffffu, v, j);
-      if (i > k && i < nb) pacc = fma(Cs[i * ld + j], vj, pacc);
-    }
-    pacc *= tau;
-    const double K = 0.5 * tau * warp_sum(pacc * v);
-    const double w = pacc - K * v;
-    for (int j = k + 1; j < nb; ++j) {
-      const double vj = __shfl_sync(0xffffffffu, v, j), wj = __shfl_sync(0xffffffffu, w, j);
-      if (i > k && i < nb) Cs[i * ld + j] -= v * wj + w * vj;
-    }
-    // P <- (I - tau v v^T) P, lane = column
-    double t = 0.0;
-    for (int m = k + 1; m < nb; ++m) {
-      const double vm = __shfl_sync(0xffffffffu, v, m);
-      if (i < nb) t = fma(vm, Ps[m * ld + i], t);
-    }
-    t *= tau;
-    for (int m = k + 1; m < nb; ++m) {
-      const double vm = __shfl_sync(0xffffffffu, v, m);
-      if (i < nb) Ps[m * ld + i] -= vm * t;
+  }
+  // trailing 2x2 of T, the hat-hat block
+  {
+    // row[nb-2], row[nb-1] have runtime indices: go through shared memory once
+#pragma unroll
+    for (int j = 0; j < NBM; ++j)
+      if (i < NBM) Ps[i * LDP + j] = row[j];
+    __syncwarp();
+    if (lane == 0) {
+      if (nb >= 2) {
+        red[nb - 2] = Ps[(nb - 2) * LDP + nb - 2];
+        red[nb + nb - 2] = Ps[(nb - 1) * LDP + nb - 2];
+      }
+      red[nb - 1] = Ps[(nb - 1) * LDP + nb - 1];
+      red[nb + nb - 1] = 0.0;
+      red[6 * nb + 0] = Hc[0];
+      red[6 * nb + 1] = Hc[1];
+      red[6 * nb + 2] = Hc[2];
+      red[6 * nb + 3] = 0.0;
     }
     __syncwarp();
   }
+  // P to shared memory: Ps[m][i] = pcol[m]
+#pragma unroll
+  for (int m = 0; m < NBM; ++m)
+    if (i < NBM) Ps[m * LDP + i] = pcol[m];
   __syncwarp();
-  if (lane == 0) {
-    if (nb >= 2) {
-      red[nb - 2] = Cs[(nb - 2) * ld + nb - 2];
-      red[nb + nb - 2] = Cs[(nb - 1) * ld + nb - 2];
-    }
-    red[nb - 1] = Cs[(nb - 1) * ld + nb - 1];
-    red[nb + nb - 1] = 0.0;
-    red[6 * nb + 0] = Hc[0];
-    red[6 * nb + 1] = Hc[1];
-    red[6 * nb + 2] = Hc[2];
-    red[6 * nb + 3] = 0.0;
-  }
   // 6. h~ = P H_bh, m~ = P M_bh
   {
-    const double h0 = (i < nb) ? Hc[3 + i] : 0.0, h1 = (i < nb) ? Hc[3 + nb + i] : 0.0;
-    const double m0 = (i < nb) ? Mc[3 + i] : 0.0, m1 = (i < nb) ? Mc[3 + nb + i] : 0.0;
+    const double h0 = act ? Hc[3 + i] : 0.0, h1 = act ? Hc[3 + nb + i] : 0.0;
+    const double m0 = act ? Mc[3 + i] : 0.0, m1 = act ? Mc[3 + nb + i] : 0.0;
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (int j = 0; j < nb; ++j) {
-      const double pj = (i < nb) ? Ps[i * ld + j] : 0.0;
+      const double pj = Ps[ir * LDP + j];
       a0 = fma(pj, __shfl_sync(0xffffffffu, h0, j), a0);
       a1 = fma(pj, __shfl_sync(0xffffffffu, h1, j), a1);
       a2 = fma(pj, __shfl_sync(0xffffffffu, m0, j), a2);
       a3 = fma(pj, __shfl_sync(0xffffffffu, m1, j), a3);
     }
-    if (i < nb) { red[2 * nb + i] = a0; red[3 * nb + i] = a1; red[4 * nb + i] = a2; red[5 * nb + i] = a3; }
+    if (act) { red[2 * nb + i] = a0; red[3 * nb + i] = a1; red[4 * nb + i] = a2; red[5 * nb + i] = a3; }
   }
   // 7. P (row-major) and P^T
   double* Pm = b.Pm + (chan * C + c) * (size_t)nb * nb;
   double* Pt = b.Pt + (chan * C + c) * (size_t)nb * nb;
   for (int idx = lane; idx < nb * nb; idx += 32) {
     const int r = idx / nb, cc = idx - r * nb;
-    Pm[idx] = Ps[r * ld + cc];
-    Pt[idx] = Ps[cc * ld + r];
+    Pm[idx] = Ps[r * LDP + cc];
+    Pt[idx] = Ps[cc * LDP + r];
   }
 }
 
