@@ -47,6 +47,7 @@ struct aks_batch {
   std::vector<int> hLp, hnhp;
   aks_iter_record* h_rec = nullptr;  // pinned
   bool timers = false;
+  bool eig_dirty = false;   // levels outside the eigenpair window are stale (k_eig)
   cudaEvent_t ev[9];
   double phase_ms[8] = {0};
 };
@@ -350,6 +351,8 @@ extern "C" void aks_disc_destroy(aks_disc* disc) {
 
 // ------------------------------------------------------------------------------------ batch
 extern "C" int aks_batch_reset(aks_batch* bt);
+static int window_full(aks_batch* bt, int p0, int np);
+static int ensure_complete(aks_batch* bt);
 
 extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const double* N,
                                 const double* hartree, const int32_t* ex_id, const int32_t* ec_id,
@@ -394,7 +397,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk) ZB(double, Hfull, B * s * L * C * n * n)
   ZB(double, eps, B * s * L * nh) ZB(double, eps_new, B * s * L * nh) ZB(double, U, B * s * L * nh * Nh)
   ZB(int, eig_info, B * s * L * nh) ZB(long long, eig_dbg, B * s * L * nh * 8) ZB(double, red, B * s * L * C * (6 * (n - 2) + 4))
-  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * ((C + EIGC_CHUNK - 1) / EIGC_CHUNK) * 4) ZB(int, warm, B) ZB(double, ekin_orb, B * s * L * nh)
+  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * ((C + EIGC_CHUNK - 1) / EIGC_CHUNK) * 4) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, redo_cnt, B) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
   ZB(double, ecou_orb, B * s * L * nh) ZB(double, occ, B * 2 * s * L * nh) ZB(int, degen, B) ZB(int, occ_cnt, B * 2) ZB(int, occ_elk, B * 2 * AKS_MAXORB) ZB(double, occ_n, B * 2 * AKS_MAXORB)
   ZB(int, degen_idx, B * 2) ZB(double, degen_n, B * 4) ZB(double, rho_q_new, B * 2 * s * C * Q)
   ZB(double, rho_y_new, B * 2 * s * G) ZB(double, corr_part, B * 2 * C) ZB(double, Bloc_new, B * 2 * C * n)
@@ -406,6 +409,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   b.scftol = 1e-10; b.tinit = 0.6; b.frozen_t = 0; b.maxiter_ls = 100;
   b.abstol_ls = b.reltol_ls = 1e4 * 2.220446049250313e-16;
   b.max_degen = 2; b.degen_tol = 1e-3; b.handle_spin = 1;
+  b.eig_margin = 1;
   // launch configuration
   bt->smem_pot = potential_smem_bytes(dv.n, dv.Q, b.s);
   bt->smem_eig = eig_smem_bytes(dv.C, dv.nb, dv.Nh);
@@ -484,8 +488,19 @@ extern "C" int aks_batch_reset(aks_batch* bt) {
   CK(cudaMemsetAsync(b.degen, 0, sizeof(int) * B, ctx->stream));
   std::vector<double> tv(B, b.tinit);
   CK(cudaMemcpyAsync(b.t, tv.data(), sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = window_full(bt, 0, bt->B);
+  if (rc != AKS_OK) return rc;
+  bt->eig_dirty = false;
   CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
+}
+
+extern "C" int aks_batch_set_eig_window(aks_batch* bt, int32_t margin) {
+  if (!bt) return AKS_EINVAL;
+  int rc = ensure_complete(bt);
+  if (rc != AKS_OK) return rc;
+  bt->dev.eig_margin = margin;
+  return window_full(bt, 0, bt->B);
 }
 
 // ------------------------------------------------------------------------------------ SCF step
@@ -508,6 +523,22 @@ static int launch_potential(aks_batch* bt, double* vxc_out, double* har_out) {
   LAUNCH_CHECK();
   return AKS_OK;
 }
+// one pass of the eigensolver over the levels its mode selects (k_eig: 0 window, 1 refill, 2 completion)
+static int launch_eig_pass(aks_batch* bt, int mode) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const BatchDev& b = bt->dev;
+  k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b, mode);
+  LAUNCH_CHECK();
+  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_eig, ctx->stream>>>(dv, b, mode);
+  LAUNCH_CHECK();
+  const int nchunk = (dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK;
+  k_eig_final<<<dim3(nchunk, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b, mode);
+  LAUNCH_CHECK();
+  k_eig_scale<<<dim3(b.Lmax * b.s, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b, nchunk, mode);
+  LAUNCH_CHECK();
+  return AKS_OK;
+}
 static int launch_eig(aks_batch* bt) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
@@ -522,14 +553,24 @@ static int launch_eig(aks_batch* bt) {
     }
   }
   LAUNCH_CHECK();
-  k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b);
+  return launch_eig_pass(bt, 0);
+}
+// every level current again (the reference returns all nh eigenpairs of the last Hamiltonian)
+static int ensure_complete(aks_batch* bt) {
+  if (!bt->eig_dirty) return AKS_OK;
+  aks_ctx* ctx = bt->disc->ctx;
+  k_set_redo<<<(bt->B + 127) / 128, 128, 0, ctx->stream>>>(bt->dev, 1);
   LAUNCH_CHECK();
-  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_eig, ctx->stream>>>(dv, b);
+  int rc = launch_eig_pass(bt, 2);
+  if (rc != AKS_OK) return rc;
+  k_set_redo<<<(bt->B + 127) / 128, 128, 0, ctx->stream>>>(bt->dev, 0);
   LAUNCH_CHECK();
-  const int nchunk = (dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK;
-  k_eig_final<<<dim3(nchunk, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b);
-  LAUNCH_CHECK();
-  k_eig_scale<<<dim3(b.Lmax * b.s, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b, nchunk);
+  bt->eig_dirty = false;
+  return AKS_OK;
+}
+static int window_full(aks_batch* bt, int p0, int np) {
+  aks_ctx* ctx = bt->disc->ctx;
+  k_window_full<<<(np * bt->dev.s * bt->dev.Lmax + 127) / 128, 128, 0, ctx->stream>>>(bt->dev, p0, np);
   LAUNCH_CHECK();
   return AKS_OK;
 }
@@ -565,8 +606,14 @@ static int step_launch(aks_batch* bt) {
   TICK();
   if ((rc = launch_eig(bt)) != AKS_OK) return rc;
   TICK();
-  k_aufbau<<<bt->B, 32, 0, ctx->stream>>>(dv, b);
+  k_aufbau<<<bt->B, 32, 0, ctx->stream>>>(dv, b, 0);
   LAUNCH_CHECK();
+  if (b.eig_margin >= 0) {   // problems whose window could not be certified: solve the rest, repeat
+    if ((rc = launch_eig_pass(bt, 1)) != AKS_OK) return rc;
+    k_aufbau<<<bt->B, 32, 0, ctx->stream>>>(dv, b, 1);
+    LAUNCH_CHECK();
+    bt->eig_dirty = true;
+  }
   k_orb_energy<<<dim3(b.s * b.Lmax * b.nhmax, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
   TICK();
@@ -669,6 +716,7 @@ extern "C" int aks_get_state(aks_batch* bt, int32_t prob, double* D, double* U, 
   const DiscDev& dv = bt->disc->dev;
   const BatchDev& b = bt->dev;
   const size_t s = b.s, Nh = dv.Nh, L = b.Lmax, nh = b.nhmax;
+  if (U || eps) { int rc = ensure_complete(bt); if (rc != AKS_OK) return rc; }
   if (D) CK(cudaMemcpyAsync(D, b.Dd + (size_t)prob * s * Nh * Nh, sizeof(double) * s * Nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
   if (U) CK(cudaMemcpyAsync(U, b.U + (size_t)prob * s * L * nh * Nh, sizeof(double) * s * L * nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<double> he(s * L * nh), hn(s * L * nh), hw(Nh);
@@ -718,8 +766,10 @@ extern "C" int aks_set_density(aks_batch* bt, int32_t prob, const double* D, con
   CK(cudaMemcpyAsync(b.warm + prob, &zero, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(b.niter + prob, &nit, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  int rc = launch_state_from_dense(bt, prob);
+  int rc = ensure_complete(bt);   // the other problems keep a complete set of eigenpairs
   if (rc != AKS_OK) return rc;
+  if ((rc = window_full(bt, prob, 1)) != AKS_OK) return rc;
+  if ((rc = launch_state_from_dense(bt, prob)) != AKS_OK) return rc;
   // Poisson solve of slot 0 for this problem only, then commit B, W
   k_poisson<<<dim3(1, 1), 128, bt->smem_poisson, ctx->stream>>>(dv, b, prob, 1);
   LAUNCH_CHECK();
@@ -787,6 +837,8 @@ extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* 
   const DiscDev& dv = bt->disc->dev;
   const BatchDev& b = bt->dev;
   int rc;
+  if ((rc = window_full(bt, 0, bt->B)) != AKS_OK) return rc;
+  bt->eig_dirty = false;
   if ((rc = launch_potential(bt, nullptr, nullptr)) != AKS_OK) return rc;
   if ((rc = launch_eig(bt)) != AKS_OK) return rc;
   const size_t s = b.s, L = b.Lmax, nh = b.nhmax, Nh = dv.Nh;
@@ -847,6 +899,14 @@ extern "C" int aks_debug_eig_cycles(aks_batch* bt, int64_t* out) {
   const BatchDev& b = bt->dev;
   const size_t cnt = (size_t)bt->B * b.s * b.Lmax * b.nhmax * 8;
   CK(cudaMemcpyAsync(out, b.eig_dbg, sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
+extern "C" int aks_debug_eig_refills(aks_batch* bt, int32_t* counts) {
+  if (!bt || !counts) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  CK(cudaMemcpyAsync(counts, bt->dev.redo_cnt, sizeof(int) * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
 }

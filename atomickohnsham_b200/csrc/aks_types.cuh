@@ -39,6 +39,9 @@ struct DiscDev {
   const double* Linv;    // [C][nb][nb] inverse Cholesky factor of the bubble mass block (lower, row-major)
 };
 
+#define AKS_KHIST 4             // steps over which the eigenpair window remembers occupied levels
+#define AKS_EPS_MISSING 1e300   // eps_new of a level outside the eigenpair window (k_eig)
+
 struct BatchDev {
   int B, s, Lmax, nhmax;
   // model parameters
@@ -73,6 +76,12 @@ struct BatchDev {
   double* eig_part;  // [B][s][Lmax][nhmax][nchunk][4]  per-chunk x^T M x, x^T H x, sign sum
   double* Xt;        // [B][s][Lmax][nhmax][nb*C + C]  eigenvectors in reduced coordinates (t | h)
   int* warm;         // [B]  1 once eps/U hold a previous solution
+  int* kact;         // [B][s][Lmax]  eigenpairs per channel solved in the first pass of the next step
+  int* kdone;        // [B][s][Lmax]  eigenpairs per channel that are current (solved for the last H)
+  int* redo;         // [B]  aufbau could not be certified on the window: solve the rest, repeat
+  int* redo_cnt;     // [B]  how often that happened (diagnostic)
+  int* khist;        // [B][s][Lmax][AKS_KHIST]  occupied levels per channel of the last steps
+  int eig_margin;    // window = occupied levels + margin per channel; < 0: always all nh
   double* ekin_orb;  // [B][s][Lmax][nhmax]
   double* ecou_orb;  // [B][s][Lmax][nhmax]
   double* occ;       // [B][2][s][Lmax][nhmax]  slot 0: final / first extreme, slot 1: second extreme

@@ -136,6 +136,20 @@ __global__ void __launch_bounds__(AKS_NT) k_eig_residual(DiscDev d, BatchDev b, 
   if (threadIdx.x == 0) out[(size_t)ch * b.nhmax + k] = sqrt(acc);
 }
 
+// eigenpair window (k_eig): [p0, p0+np) back to "solve every level", nothing pending
+__global__ void k_window_full(BatchDev b, int p0, int np) {
+  const int per = b.s * b.Lmax;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np * per; i += gridDim.x * blockDim.x) {
+    b.kact[(size_t)p0 * per + i] = b.nhmax;
+    b.kdone[(size_t)p0 * per + i] = b.nhmax;
+    for (int h = 0; h < AKS_KHIST; ++h) b.khist[((size_t)p0 * per + i) * AKS_KHIST + h] = 0;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) b.redo[p0 + i] = 0;
+}
+__global__ void k_set_redo(BatchDev b, int v) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < b.B; i += gridDim.x * blockDim.x) b.redo[i] = v;
+}
+
 // FP64 FMA throughput probe: 8 independent register chains per thread
 __global__ void k_fp64_peak(double* out, int iters) {
   double a0 = 1.0 + threadIdx.x * 1e-9, a1 = 1.1, a2 = 1.2, a3 = 1.3, a4 = 1.4, a5 = 1.5, a6 = 1.6, a7 = 1.7;

@@ -607,14 +607,41 @@ __device__ inline void eig_carve(const DiscDev& d, double* sm, EigShared& S) {
   }
 }
 
+// levels [klo, khi) of a channel handled by a pass (see k_eig)
+__device__ __forceinline__ bool eig_window(const BatchDev& b, int p, size_t chan, int mode, int& klo, int& khi) {
+  if (mode != 2 && b.status[p] != 0) return false;
+  const int nhp = b.nhp[p];
+  if (mode == 0) { klo = 0; khi = min(nhp, b.kact[chan]); }
+  else {
+    if (b.redo[p] == 0) return false;
+    klo = b.kdone[chan]; khi = nhp;
+  }
+  return klo < khi;
+}
+
 enum { EST_BRACKET_LO = 0, EST_BRACKET_HI, EST_BISECT, EST_RQI, EST_CERT_LO, EST_CERT_HI, EST_FINAL, EST_DONE };
 
+// Eigenpair window.  Only levels that can influence the aufbau have to be current in every SCF step:
+// mode 0 solves the first kact[channel] levels of each channel (occupied levels of the previous step
+// + margin; the others get the sentinel AKS_EPS_MISSING and sort last); k_aufbau then CERTIFIES that
+// every unsolved level lies above everything it examined, and otherwise raises redo[p], for which
+// mode 1 solves the remaining levels (cold) before the aufbau is repeated.  Mode 2 is the same fill
+// pass on request of the host (aks_get_state / end of a run: the reference returns all nh pairs).
 __global__ void __launch_bounds__(AKS_NT, 2)
-k_eig(DiscDev d, BatchDev b) {
+k_eig(DiscDev d, BatchDev b, int mode) {
   const int k = blockIdx.x, ch = blockIdx.y, p = blockIdx.z;
-  if (b.status[p] != 0) return;
+  if (mode != 2 && b.status[p] != 0) return;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
   if (l >= b.Lp[p] || k >= b.nhp[p]) return;
+  {
+    const size_t chan0 = ((size_t)p * b.s + e) * b.Lmax + l;
+    if (mode == 0) {
+      if (k >= b.kact[chan0]) {
+        if (threadIdx.x == 0) b.eps_new[chan0 * b.nhmax + k] = AKS_EPS_MISSING;
+        return;
+      }
+    } else if (b.redo[p] == 0 || k < b.kdone[chan0]) return;
+  }
   extern __shared__ double sm[];
   const int C = d.C, nb = d.nb;
 #ifdef AKS_EIG_TIMING
@@ -631,6 +658,8 @@ k_eig(DiscDev d, BatchDev b) {
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
   const double* eps_ch = b.eps + chan * b.nhmax;
   const int nhp = b.nhp[p];
+  // eps / U of a level outside the last windows are older than one step: still a start, never trusted
+  // (every result is certified by inertia counts)
   const bool have_prev = b.warm[p] != 0;
   {  // reduced data of this channel, transposed to field-major
     const int rs = red_stride(nb);
@@ -865,17 +894,19 @@ __host__ __device__ inline size_t eig_chan_smem_bytes(int n, int nb) {
 }
 
 __global__ void __launch_bounds__(AKS_NT)
-k_eig_init(DiscDev d, BatchDev b) {
+k_eig_init(DiscDev d, BatchDev b, int mode) {
   const int p = blockIdx.z, ch = blockIdx.y;
-  if (b.status[p] != 0 || b.warm[p] == 0 || !(b.stop[p] < 0.3)) return;
+  if (b.warm[p] == 0 || !(b.stop[p] < 0.3)) return;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
   if (l >= b.Lp[p]) return;
   extern __shared__ double sm[];
-  const int C = d.C, nb = d.nb, n = d.n, Nh = d.Nh, nhp = b.nhp[p];
+  const int C = d.C, nb = d.nb, n = d.n, Nh = d.Nh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* Ps = sm;              // [nb][nb]  P^T (Ps[j*nb+i] = P[i][j])
   double* Ms = Ps + nb * nb;    // [nb][nb]  M_bb
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
+  int klo, nhp;                                  // only the levels of this pass are warm-started
+  if (!eig_window(b, p, chan, mode, klo, nhp)) return;
   const size_t xs = (size_t)(nb * C + C);
   for (int c = blockIdx.x * EIGC_CHUNK; c < min(C, (blockIdx.x + 1) * EIGC_CHUNK); ++c) {
     __syncthreads();
@@ -888,7 +919,7 @@ k_eig_init(DiscDev d, BatchDev b) {
     }
     __syncthreads();
     const int g0 = d.l2g[c * n + 2];
-    for (int k = warp; k < nhp; k += AKS_NW) {
+    for (int k = klo + warp; k < nhp; k += AKS_NW) {
       const double* u = b.U + (chan * b.nhmax + k) * Nh;
       const double xb = (lane < nb) ? u[g0 + lane] : 0.0;
       double mb = 0.0;
@@ -905,8 +936,8 @@ k_eig_init(DiscDev d, BatchDev b) {
     }
   }
   if (blockIdx.x == 0)
-    for (int idx = threadIdx.x; idx < nhp * (C - 1); idx += blockDim.x) {
-      const int k = idx / (C - 1), j = idx - k * (C - 1);
+    for (int idx = threadIdx.x; idx < (nhp - klo) * (C - 1); idx += blockDim.x) {
+      const int k = klo + idx / (C - 1), j = idx - (k - klo) * (C - 1);
       b.Xt[(chan * b.nhmax + k) * xs + (size_t)nb * C + j] = b.U[(chan * b.nhmax + k) * Nh + d.l2g[j * n]];
     }
 }
@@ -918,18 +949,19 @@ k_eig_init(DiscDev d, BatchDev b) {
 // k_eig_scale then adds the shares in a fixed order: U = x / sqrt(x^T M0 x) with a fixed sign,
 // eps = x^T H x / x^T M0 x.
 __global__ void __launch_bounds__(AKS_NT)
-k_eig_final(DiscDev d, BatchDev b) {
+k_eig_final(DiscDev d, BatchDev b, int mode) {
   const int p = blockIdx.z, ch = blockIdx.y, chunk = blockIdx.x;
-  if (b.status[p] != 0) return;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
   if (l >= b.Lp[p]) return;
   extern __shared__ double sm[];
-  const int C = d.C, nb = d.nb, n = d.n, Nh = d.Nh, nhp = b.nhp[p];
+  const int C = d.C, nb = d.nb, n = d.n, Nh = d.Nh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* Ps = sm;              // [nb][nb]  P   (Ps[i*nb+j] = P[i][j])
   double* Ms = Ps + nb * nb;    // [n][n]
   double* Hs = Ms + n * n;      // [n][n]
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
+  int klo, nhp;
+  if (!eig_window(b, p, chan, mode, klo, nhp)) return;
   const size_t xs = (size_t)(nb * C + C);
   double xmx[2] = {0.0, 0.0}, xhx[2] = {0.0, 0.0}, ssum[2] = {0.0, 0.0};
   for (int c = chunk * EIGC_CHUNK; c < min(C, (chunk + 1) * EIGC_CHUNK); ++c) {
@@ -944,7 +976,7 @@ k_eig_final(DiscDev d, BatchDev b) {
     const int gR = (c < C - 1) ? d.l2g[c * n] : -1;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
-      const int k = warp + t * AKS_NW;
+      const int k = klo + warp + t * AKS_NW;
       if (k < nhp) {
         const double* X = b.Xt + (chan * b.nhmax + k) * xs;
         double* u = b.U + (chan * b.nhmax + k) * Nh;
@@ -973,7 +1005,7 @@ k_eig_final(DiscDev d, BatchDev b) {
   }
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
-    const int k = warp + t * AKS_NW;
+    const int k = klo + warp + t * AKS_NW;
     if (k < nhp) {
       const double m = warp_sum(xmx[t]), h = warp_sum(xhx[t]), sg = warp_sum(ssum[t]);
       if (lane == 0) {
@@ -985,15 +1017,18 @@ k_eig_final(DiscDev d, BatchDev b) {
 }
 
 __global__ void __launch_bounds__(AKS_NT)
-k_eig_scale(DiscDev d, BatchDev b, int nchunk) {
+k_eig_scale(DiscDev d, BatchDev b, int nchunk, int mode) {
   const int p = blockIdx.y, ch = blockIdx.x;
-  if (b.status[p] != 0) return;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
   if (l >= b.Lp[p]) return;
-  const int Nh = d.Nh, nhp = b.nhp[p];
+  const int Nh = d.Nh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
-  for (int k = warp; k < nhp; k += AKS_NW) {
+  int klo, nhp;
+  if (!eig_window(b, p, chan, mode, klo, nhp)) return;
+  __syncthreads();   // every thread has read kdone before it is advanced
+  if (threadIdx.x == 0) b.kdone[chan] = nhp;
+  for (int k = klo + warp; k < nhp; k += AKS_NW) {
     const double* part = b.eig_part + ((chan * b.nhmax + k) * nchunk) * 4;
     double m = 0.0, h = 0.0, sg = 0.0;
     for (int q = 0; q < nchunk; ++q) { m += part[4 * q]; h += part[4 * q + 1]; sg += part[4 * q + 2]; }
@@ -1004,6 +1039,7 @@ k_eig_scale(DiscDev d, BatchDev b, int nchunk) {
       const double rq = h / m;
       const int info = b.eig_info[chan * b.nhmax + k];
       if (isfinite(rq) && !(info & 0x80)) b.eps_new[chan * b.nhmax + k] = rq;
+      if (mode == 2) b.eps[chan * b.nhmax + k] = b.eps_new[chan * b.nhmax + k];   // no aufbau follows
     }
   }
 }

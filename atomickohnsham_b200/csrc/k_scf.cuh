@@ -33,9 +33,13 @@ __device__ inline void write_occ_list(const BatchDev& b, int p, int slot) {
 // levels within `tol` of the block head; a partially filled two-fold block only records the
 // two extreme fillings here (slot 0 / slot 1), the energy minimisation between them
 // (optimized.jl:228-306) happens in k_linesearch.  One thread per problem.
-__global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b) {
+// mode 0: all running problems, on the eigenpair window (k_eig); the result is kept only if it is
+// certified: every level outside the window lies above everything the fill examined.  mode 1: the
+// problems whose certificate failed, after their remaining levels were solved.
+__global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b, int mode) {
   const int p = blockIdx.x;
   if (p >= b.B || b.status[p] != 0) return;
+  if (mode == 1 && b.redo[p] == 0) return;
   const int Lp = b.Lp[p], nhp = b.nhp[p], s = b.s;
   const int norb = Lp * nhp * s;
   // stage everything the serial logic touches in shared memory (one warp per problem): the
@@ -48,7 +52,7 @@ __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b) {
   for (int f = lane; f < norb; f += 32) {
     const int e = f / (Lp * nhp), r = f - e * Lp * nhp, k = r / Lp, l = r - k * Lp;
     const double v = b.eps_new[orb_off(b, p, e, l, k)];
-    b.eps[orb_off(b, p, e, l, k)] = v;
+    if (v < 0.5 * AKS_EPS_MISSING) b.eps[orb_off(b, p, e, l, k)] = v;   // unsolved levels keep their last value
     ev[f] = v;
     ord[f] = f;
     occ_s[0][f] = 0.0;
@@ -69,10 +73,13 @@ __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b) {
     int i = 0;
     int blk[8];
     const int maxd = b.max_degen < 8 ? b.max_degen : 8;
+    double e_last = -1e300;   // level of the last block the fill looked at
+    bool degen3 = false;
     while (Nleft > 0.0 && i < norb) {
       blk[0] = ord[i];
       int nbd = 1;
       const double e0 = ev[blk[0]];
+      e_last = e0;
       int j = i + 1;
       while (j < norb && fabs(ev[ord[j]] - e0) < b.degen_tol && nbd < maxd) { blk[nbd++] = ord[j]; ++j; }
       i += nbd;
@@ -111,9 +118,42 @@ __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b) {
         b.degen_n[4 * p + 2] = n11; b.degen_n[4 * p + 3] = n21;
         break;
       } else {
-        b.status[p] = AKS_EDEGEN3;
+        degen3 = true;
         break;
       }
+    }
+    // certificate of the window: the highest solved level of every truncated channel must lie above
+    // e_last + degen_tol (levels are ordered within a channel, so the unsolved ones lie higher still)
+    bool redo = false;
+    if (mode == 0) {
+      if (!(e_last < 0.5 * 1e300)) redo = true;
+      for (int e = 0; e < s && !redo; ++e)
+        for (int l = 0; l < Lp; ++l) {
+          const int kd = b.kdone[((size_t)p * s + e) * b.Lmax + l];
+          if (kd < nhp && !(ev[l + Lp * (kd - 1) + Lp * nhp * e] > e_last + b.degen_tol)) { redo = true; break; }
+        }
+    }
+    b.redo[p] = redo ? 1 : 0;
+    if (redo) b.redo_cnt[p] += 1;
+    if (!redo) {
+      if (degen3) b.status[p] = AKS_EDEGEN3;
+      // window of the next step: occupied levels (either slot) + margin
+      for (int e = 0; e < s; ++e)
+        for (int l = 0; l < Lp; ++l) {
+          int top = 0;
+          for (int k = 0; k < nhp; ++k) {
+            const int f = l + Lp * k + Lp * nhp * e;
+            if (occ_s[0][f] != 0.0 || occ_s[1][f] != 0.0) top = k + 1;
+          }
+          // highest need of the last AKS_KHIST steps: configurations that alternate between steps
+          // (open d / f shells) would otherwise fail the certificate every other step
+          const size_t chn = ((size_t)p * s + e) * b.Lmax + l;
+          int* hist = b.khist + chn * AKS_KHIST;
+          hist[niter % AKS_KHIST] = top;
+          int need = top;
+          for (int h = 0; h < AKS_KHIST; ++h) need = max(need, hist[h]);
+          b.kact[chn] = (b.eig_margin < 0) ? b.nhmax : max(1, min(nhp, need + b.eig_margin));
+        }
     }
     b.degen[p] = degen;
     // compact occupied lists, density! order (sigma, k, l)

@@ -82,7 +82,7 @@ def solution_name(Z, N):
 class Batch:
     """A batch of models sharing one discretization, resident on the device (aks_batch)."""
 
-    def __init__(self, models, discretization: KSEDiscretization, alg: ODA, *, lh=None, nh=None):
+    def __init__(self, models, discretization: KSEDiscretization, alg: ODA, *, lh=None, nh=None, eig_margin=None):
         self.models = list(models)
         self.disc = discretization
         self.alg = alg
@@ -111,7 +111,20 @@ class Batch:
         self.ctx.check(_capi.lib.aks_batch_set_oda(h, alg.scftol, alg.tinit, int(alg.frozen_t), alg.maxiter_ls,
                                                    alg.abstol_ls, alg.reltol_ls, a.max_degen, a.tol,
                                                    int(a.handle_degen_spin_1iter)))
+        if eig_margin is not None:
+            self.set_eig_window(eig_margin)
         self._rec = (IterRecord * nprob)()
+
+    def set_eig_window(self, margin):
+        """Eigenpair window (aks_batch_set_eig_window): levels solved per channel and step = occupied +
+        margin, certified on the device; margin < 0 solves all nh eigenpairs in every step."""
+        self.ctx.check(_capi.lib.aks_batch_set_eig_window(self.h, int(margin)))
+
+    def eig_refills(self):
+        """Per problem: number of steps whose eigenpair window had to be refilled (diagnostic)."""
+        out = np.zeros(self.nprob, dtype=np.int32)
+        self.ctx.check(_capi.lib.aks_debug_eig_refills(self.h, _capi.i32ptr(out)))
+        return out
 
     def reset(self):
         self.ctx.check(_capi.lib.aks_batch_reset(self.h))

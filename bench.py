@@ -117,7 +117,7 @@ def b200_arm(args):
         torch.cuda.synchronize(local)
 
     # ---------------- device-resident throughput (`value`)
-    bt = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs)
+    bt = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)
     for _ in range(args.warmup):
         bt.step_async()
     launches0 = ctx.launches
@@ -133,6 +133,7 @@ def b200_arm(args):
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
+    refills = int(bt.eig_refills().sum())
     recs = bt.step()  # sanity: energies finite
     assert all(r["status"] >= 0 for r in recs), "a problem failed"
     units = torch.tensor([float(B * args.steps), ms], dtype=torch.float64, device=f"cuda:{local}")
@@ -149,7 +150,7 @@ def b200_arm(args):
     roof, phases = None, None
     if rank == 0:
         os.environ["AKS_PHASE_TIMERS"] = "1"
-        bt2 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs)
+        bt2 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)
         del os.environ["AKS_PHASE_TIMERS"]
         for _ in range(max(args.warmup, 3)):
             bt2.step()
@@ -194,7 +195,7 @@ def b200_arm(args):
     # ---------------- end to end through the public API with host buffers (`e2e`)
     barrier()
     t0 = time.perf_counter()
-    bt3 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs)       # H2D: model parameters
+    bt3 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)   # H2D: model parameters
     for _ in range(args.steps):
         bt3.step()                                             # D2H: one record per atom, every step
     outs = [bt3.state(i, want_D=False, want_U=False) for i in range(B)]  # D2H: eps, n, W per atom
@@ -215,7 +216,7 @@ def b200_arm(args):
     sweep = None
     if rank == 0:
         alg = aks.ODA(scftol=1e-10, tinit=0.6, aufbau=aks.OptimizedAufbau(tol=1e-3))
-        btc = Batch(models, disc, alg, lh=lhs, nh=nhs)
+        btc = Batch(models, disc, alg, lh=lhs, nh=nhs, eig_margin=args.eig_margin)
         t0 = time.perf_counter()
         final, _ = btc.run(100)
         dt = time.perf_counter() - t0
@@ -239,7 +240,8 @@ def b200_arm(args):
             "config": {"workload": "C5 periodic-table sweep Z=1..86 (one sweep per GPU; rank r: functional/charge "
                                    "variant r) on the C2 Argon discretization: expmesh(0,300,41;s=1.5), ordermax=20, "
                                    "Nh=799, 1000 Gauss points/element, LDA, lh=min(ceil(Z/20),3), nh=clamp(Z,2,10)",
-                       "atoms_per_gpu": B, "scftol": "0 during timed steps (fixed work per step)",
+                       "atoms_per_gpu": B, "eig_window_margin": args.eig_margin,
+                       "eig_window_refills_in_run": refills, "scftol": "0 during timed steps (fixed work per step)",
                        "l2": "state per GPU (dense D: %.0f MB) exceeds the 126 MB L2; no explicit flush" % (B * 8 * 799 * 799 / 1e6),
                        "tables": "resident before the timed regions (setup is outside the reference's loop too)"},
             "clocks": clocks, "gpu_launches": launches,
@@ -341,6 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sweeps", type=int, default=1, help="periodic-table sweeps per GPU (default 1)")
+    ap.add_argument("--eig-margin", type=int, default=1, help="eigenpair window margin (-1: all nh every step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON record): anything libraries print there (e.g. NCCL's version

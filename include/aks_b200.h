@@ -108,6 +108,15 @@ int aks_batch_set_oda(aks_batch* batch, double scftol, double tinit, int32_t fro
                       int32_t maxiter_ls, double abstol_ls, double reltol_ls,
                       int32_t max_degen, double degen_tol, int32_t handle_degen_spin_1iter);
 
+/* Eigenpair window (no reference counterpart; the results are the reference's).  The reference solves
+ * all nh eigenpairs of every channel in every iteration (oda/loop.jl:65-77) although only the levels
+ * the aufbau can reach matter for the iteration.  With margin >= 0 a step solves, per channel, the
+ * levels occupied in the previous step + margin, certifies on the device that no unsolved level could
+ * have been occupied (else solves the rest and repeats the aufbau within the same step), and the
+ * remaining eigenpairs of the last Hamiltonian are solved when aks_get_state asks for eps / U.
+ * margin < 0: every step solves all nh eigenpairs.  Default 1.                                  */
+int aks_batch_set_eig_window(aks_batch* batch, int32_t margin);
+
 /* back to niter = 0, D = 0 (KSESolver constructor, src/solver/solver.jl:61-88) */
 int aks_batch_reset(aks_batch* batch);
 
@@ -157,6 +166,9 @@ int aks_hartree_energy(aks_batch* batch, int32_t prob, double* Ehar);
 /* eigensolver diagnostics of the last step: info[nprob*nspin*L*nh], device order [prob][sigma][l][k];
  * each word = (inertia counts << 8) | (0x80 if RQI did not converge) | RQI iterations       */
 int aks_debug_eig_info(aks_batch* batch, int32_t* info);
+/* counts[nprob]: steps in which the eigenpair window of a problem had to be refilled (see
+ * aks_batch_set_eig_window) since the batch was created                                     */
+int aks_debug_eig_refills(aks_batch* batch, int32_t* counts);
 /* per-eigenpair cycle counters [nprob*nspin*L*nh][8] = {setup, factor, solve, apply+dots, final, total,
  * 0, 0}; zeros unless the library was built with -DAKS_EIG_TIMING                              */
 int aks_debug_eig_cycles(aks_batch* batch, int64_t* cycles);
