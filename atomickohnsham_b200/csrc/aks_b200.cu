@@ -68,7 +68,7 @@ template <class T>
 static int dev_upload(aks_ctx* ctx, std::vector<void*>& allocs, const std::vector<T>& h, const T** out) {
   void* p = nullptr;
   const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
-  CK(cudaMalloc(&p, bytes));
+  CK(cudaMallocAsync(&p, bytes, ctx->stream));   // stream-ordered pool: see aks_ctx_create
   allocs.push_back(p);
   if (!h.empty()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -79,7 +79,7 @@ template <class T>
 static int dev_zeros(aks_ctx* ctx, std::vector<void*>& allocs, size_t count, T** out) {
   void* p = nullptr;
   const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-  CK(cudaMalloc(&p, bytes));
+  CK(cudaMallocAsync(&p, bytes, ctx->stream));
   allocs.push_back(p);
   CK(cudaMemsetAsync(p, 0, bytes, ctx->stream));
   *out = (T*)p;
@@ -97,6 +97,14 @@ extern "C" int aks_ctx_create(int device, aks_ctx** out) {
   if (device < 0 || device >= ndev) { ctx->err = "no such CUDA device"; return AKS_ECUDA; }
   CK(cudaSetDevice(device));
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  {
+    // batches come and go (one per sweep / restart): their device arrays are taken from the device's
+    // stream-ordered pool, which keeps freed memory instead of returning it to the OS
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   XcConsts xc;
   xc.cx = std::pow(3.0 / M_PI, 1.0 / 3.0);
   xc.cx34 = 0.75 * xc.cx;
@@ -345,7 +353,8 @@ extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** 
 
 extern "C" void aks_disc_destroy(aks_disc* disc) {
   if (!disc) return;
-  for (void* p : disc->allocs) cudaFree(p);
+  for (void* p : disc->allocs) cudaFreeAsync(p, disc->ctx->stream);
+  cudaStreamSynchronize(disc->ctx->stream);
   delete disc;
 }
 
@@ -445,7 +454,9 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
 
 extern "C" void aks_batch_destroy(aks_batch* bt) {
   if (!bt) return;
-  for (void* p : bt->allocs) cudaFree(p);
+  cudaStream_t st = bt->disc->ctx->stream;
+  for (void* p : bt->allocs) cudaFreeAsync(p, st);
+  cudaStreamSynchronize(st);
   if (bt->h_rec) cudaFreeHost(bt->h_rec);
   if (bt->timers) for (auto& e : bt->ev) cudaEventDestroy(e);
   delete bt;
