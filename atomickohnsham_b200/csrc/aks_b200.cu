@@ -376,6 +376,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   BatchDev& b = bt->dev;
   b.B = nprob; b.s = dv.nspin; b.Lmax = dv.L; b.nhmax = dv.nh;
   b.ntile = (dv.Nh + MIX_TS - 1) / MIX_TS;
+  b.ntri = b.ntile * (b.ntile + 1) / 2;
   bt->hZ.assign(Z, Z + nprob);
   bt->hN.assign(N, N + nprob);
   bt->hHar.assign(nprob, 1.0);
@@ -406,12 +407,12 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk) ZB(double, Hfull, B * s * L * C * n * n)
   ZB(double, eps, B * s * L * nh) ZB(double, eps_new, B * s * L * nh) ZB(double, U, B * s * L * nh * Nh)
   ZB(int, eig_info, B * s * L * nh) ZB(long long, eig_dbg, B * s * L * nh * 8) ZB(double, red, B * s * L * C * (6 * (n - 2) + 4))
-  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * ((C + EIGC_CHUNK - 1) / EIGC_CHUNK) * 4) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, redo_cnt, B) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
+  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * ((C + EIGC_CHUNK - 1) / EIGC_CHUNK) * 6) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, redo_cnt, B) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
   ZB(double, ecou_orb, B * s * L * nh) ZB(double, occ, B * 2 * s * L * nh) ZB(int, degen, B) ZB(int, occ_cnt, B * 2) ZB(int, occ_elk, B * 2 * AKS_MAXORB) ZB(double, occ_n, B * 2 * AKS_MAXORB)
   ZB(int, degen_idx, B * 2) ZB(double, degen_n, B * 4) ZB(double, rho_q_new, B * 2 * s * C * Q)
   ZB(double, rho_y_new, B * 2 * s * G) ZB(double, corr_part, B * 2 * C) ZB(double, Bloc_new, B * 2 * C * n)
   ZB(double, B_new, B * 2 * Nh) ZB(double, W_new, B * 2 * Nh) ZB(double, scal, B * 2 * 4) ZB(double, td, B)
-  ZB(double, tmix, B) ZB(double, norm_part, B * s * b.ntile * b.ntile) ZB(aks_iter_record, rec, B)
+  ZB(double, tmix, B) ZB(double, norm_part, B * s * b.ntri) ZB(aks_iter_record, rec, B)
   ZB(double, Enew, B * 5)
 #undef ZB
   // ODA defaults (oda/types.jl:38-44, optimized.jl:23-26)
@@ -625,8 +626,6 @@ static int step_launch(aks_batch* bt) {
     LAUNCH_CHECK();
     bt->eig_dirty = true;
   }
-  k_orb_energy<<<dim3(b.s * b.Lmax * b.nhmax, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b);
-  LAUNCH_CHECK();
   TICK();
   if ((rc = launch_dens_cells(bt)) != AKS_OK) return rc;
   TICK();
@@ -642,7 +641,7 @@ static int step_launch(aks_batch* bt) {
     k_mix_state<<<dim3(gx, bt->B), 256, 0, ctx->stream>>>(dv, b);
     LAUNCH_CHECK();
   }
-  k_mix_dense<<<dim3(b.ntile * b.ntile, b.s, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b);
+  k_mix_dense<<<dim3(b.ntri, b.s, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
   k_finalize<<<(bt->B + 127) / 128, 128, 0, ctx->stream>>>(dv, b);
   LAUNCH_CHECK();
@@ -728,6 +727,11 @@ extern "C" int aks_get_state(aks_batch* bt, int32_t prob, double* D, double* U, 
   const BatchDev& b = bt->dev;
   const size_t s = b.s, Nh = dv.Nh, L = b.Lmax, nh = b.nhmax;
   if (U || eps) { int rc = ensure_complete(bt); if (rc != AKS_OK) return rc; }
+  if (D) {   // the iterations keep only the lower triangle of D current
+    const int nb32 = (int)((Nh + 31) / 32);
+    k_mirror_dense<<<dim3(nb32, nb32, (unsigned)s), AKS_NT, 0, ctx->stream>>>(dv, b, prob);
+    LAUNCH_CHECK();
+  }
   if (D) CK(cudaMemcpyAsync(D, b.Dd + (size_t)prob * s * Nh * Nh, sizeof(double) * s * Nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
   if (U) CK(cudaMemcpyAsync(U, b.U + (size_t)prob * s * L * nh * Nh, sizeof(double) * s * L * nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<double> he(s * L * nh), hn(s * L * nh), hw(Nh);

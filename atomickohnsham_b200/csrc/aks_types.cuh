@@ -100,8 +100,9 @@ struct BatchDev {
   double* scal;      // [B][2][4]   B.W self, Bprev.W, -, -
   double* td;        // [B]  weight of slot 0 in the trial density (1 if not degenerate)
   double* tmix;      // [B]  ODA t of this step
-  double* norm_part; // [B][ntile_total]
-  int ntile;         // tiles per spin side (ceil(Nh/32))
+  double* norm_part; // [B][s][ntri]
+  int ntile;         // tiles per side of D (ceil(Nh/MIX_TS))
+  int ntri;          // ntile (ntile + 1) / 2: tiles on and below the diagonal
   aks_iter_record* rec; // [B]
   double* Enew;      // [B][5] energies of the trial density (before mixing)
 };

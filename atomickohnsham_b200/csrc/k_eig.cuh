@@ -890,7 +890,7 @@ k_eig(DiscDev d, BatchDev b, int mode) {
 // reused by all nh vectors (one warp per vector).
 #define EIGC_CHUNK 8
 __host__ __device__ inline size_t eig_chan_smem_bytes(int n, int nb) {
-  return sizeof(double) * ((size_t)nb * nb + 2 * (size_t)n * n + 8);
+  return sizeof(double) * ((size_t)nb * nb + 4 * (size_t)n * n + 8);
 }
 
 __global__ void __launch_bounds__(AKS_NT)
@@ -947,7 +947,8 @@ k_eig_init(DiscDev d, BatchDev b, int mode) {
 // P, M_c and H_c staged in shared memory: x_b = P^T x~_b written to U (unnormalised), and the chunk's
 // share of x^T M0 x, x^T H x (ORIGINAL blocks, unassembled sums) and of the sign sum.
 // k_eig_scale then adds the shares in a fixed order: U = x / sqrt(x^T M0 x) with a fixed sign,
-// eps = x^T H x / x^T M0 x.
+// eps = x^T H x / x^T M0 x.  The kinetic and Coulomb blocks ride along (same staging, two more FMAs per
+// entry), which gives the per-orbital energies of energies.jl:47-87 without another pass over U.
 __global__ void __launch_bounds__(AKS_NT)
 k_eig_final(DiscDev d, BatchDev b, int mode) {
   const int p = blockIdx.z, ch = blockIdx.y, chunk = blockIdx.x;
@@ -959,18 +960,28 @@ k_eig_final(DiscDev d, BatchDev b, int mode) {
   double* Ps = sm;              // [nb][nb]  P   (Ps[i*nb+j] = P[i][j])
   double* Ms = Ps + nb * nb;    // [n][n]
   double* Hs = Ms + n * n;      // [n][n]
+  double* Ks = Hs + n * n;      // [n][n]  kinetic block (A + l(l+1) M_-2) / 2
+  double* Cs = Ks + n * n;      // [n][n]  M_-1 (Coulomb)
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
   int klo, nhp;
   if (!eig_window(b, p, chan, mode, klo, nhp)) return;
+  const double ll = (double)(l * (l + 1));
   const size_t xs = (size_t)(nb * C + C);
-  double xmx[2] = {0.0, 0.0}, xhx[2] = {0.0, 0.0}, ssum[2] = {0.0, 0.0};
+  double xmx[2] = {0.0, 0.0}, xhx[2] = {0.0, 0.0}, ssum[2] = {0.0, 0.0}, xkx[2] = {0.0, 0.0}, xcx[2] = {0.0, 0.0};
   for (int c = chunk * EIGC_CHUNK; c < min(C, (chunk + 1) * EIGC_CHUNK); ++c) {
     __syncthreads();
     const double* Pc = b.Pm + (chan * C + c) * (size_t)nb * nb;
     const double* Mc = d.M0_loc + (size_t)c * n * n;
     const double* Hc = b.Hfull + (chan * C + c) * (size_t)n * n;
+    const double* Ac = d.A_loc + (size_t)c * n * n;
+    const double* M2c = d.Mm2_loc + (size_t)c * n * n;
+    const double* M1c = d.Mm1_loc + (size_t)c * n * n;
     for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) Ps[idx] = Pc[idx];
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) { Ms[idx] = Mc[idx]; Hs[idx] = Hc[idx]; }
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+      Ms[idx] = Mc[idx]; Hs[idx] = Hc[idx];
+      Ks[idx] = (Ac[idx] + ((l > 0) ? ll * M2c[idx] : 0.0)) / 2.0;
+      Cs[idx] = M1c[idx];
+    }
     __syncthreads();
     const int g0 = d.l2g[c * n + 2];
     const int gR = (c < C - 1) ? d.l2g[c * n] : -1;
@@ -991,13 +1002,18 @@ k_eig_final(DiscDev d, BatchDev b, int mode) {
         if (lane == 0) xl = (c < C - 1) ? X[(size_t)nb * C + c] : 0.0;
         if (lane == 1) xl = (c > 0) ? X[(size_t)nb * C + c - 1] : 0.0;
         if (lane >= n) xl = 0.0;
-        double mx = 0.0, hx = 0.0;
+        double mx = 0.0, hx = 0.0, kx = 0.0, cx = 0.0;
         for (int a = 0; a < n; ++a) {
           const double xa = __shfl_sync(0xffffffffu, xl, a);
-          if (lane < n) { mx = fma(Ms[a * n + lane], xa, mx); hx = fma(Hs[a * n + lane], xa, hx); }
+          if (lane < n) {
+            mx = fma(Ms[a * n + lane], xa, mx); hx = fma(Hs[a * n + lane], xa, hx);
+            kx = fma(Ks[a * n + lane], xa, kx); cx = fma(Cs[a * n + lane], xa, cx);
+          }
         }
         xmx[t] = fma(mx, xl, xmx[t]);
         xhx[t] = fma(hx, xl, xhx[t]);
+        xkx[t] = fma(kx, xl, xkx[t]);
+        xcx[t] = fma(cx, xl, xcx[t]);
         if (lane >= 2 && lane < n) { u[g0 + lane - 2] = xl; ssum[t] += xl; }
         if (lane == 0 && gR >= 0) { u[gR] = xl; ssum[t] += xl; }
       }
@@ -1008,9 +1024,10 @@ k_eig_final(DiscDev d, BatchDev b, int mode) {
     const int k = klo + warp + t * AKS_NW;
     if (k < nhp) {
       const double m = warp_sum(xmx[t]), h = warp_sum(xhx[t]), sg = warp_sum(ssum[t]);
+      const double kk = warp_sum(xkx[t]), cc = warp_sum(xcx[t]);
       if (lane == 0) {
-        double* part = b.eig_part + ((chan * b.nhmax + k) * gridDim.x + chunk) * 4;
-        part[0] = m; part[1] = h; part[2] = sg;
+        double* part = b.eig_part + ((chan * b.nhmax + k) * gridDim.x + chunk) * 6;
+        part[0] = m; part[1] = h; part[2] = sg; part[3] = kk; part[4] = cc;
       }
     }
   }
@@ -1029,9 +1046,11 @@ k_eig_scale(DiscDev d, BatchDev b, int nchunk, int mode) {
   __syncthreads();   // every thread has read kdone before it is advanced
   if (threadIdx.x == 0) b.kdone[chan] = nhp;
   for (int k = klo + warp; k < nhp; k += AKS_NW) {
-    const double* part = b.eig_part + ((chan * b.nhmax + k) * nchunk) * 4;
-    double m = 0.0, h = 0.0, sg = 0.0;
-    for (int q = 0; q < nchunk; ++q) { m += part[4 * q]; h += part[4 * q + 1]; sg += part[4 * q + 2]; }
+    const double* part = b.eig_part + ((chan * b.nhmax + k) * nchunk) * 6;
+    double m = 0.0, h = 0.0, sg = 0.0, kk = 0.0, cc = 0.0;
+    for (int q = 0; q < nchunk; ++q) {
+      m += part[6 * q]; h += part[6 * q + 1]; sg += part[6 * q + 2]; kk += part[6 * q + 3]; cc += part[6 * q + 4];
+    }
     double* u = b.U + (chan * b.nhmax + k) * Nh;
     const double sc = ((sg < 0.0) ? -1.0 : 1.0) / sqrt(m);
     for (int i = lane; i < Nh; i += 32) u[i] *= sc;
@@ -1040,6 +1059,10 @@ k_eig_scale(DiscDev d, BatchDev b, int nchunk, int mode) {
       const int info = b.eig_info[chan * b.nhmax + k];
       if (isfinite(rq) && !(info & 0x80)) b.eps_new[chan * b.nhmax + k] = rq;
       if (mode == 2) b.eps[chan * b.nhmax + k] = b.eps_new[chan * b.nhmax + k];   // no aufbau follows
+      // u^T Kin_l u and u^T Coulomb u of the normalised orbital (compute_kinetic_energy /
+      // compute_coulomb_energy, src/discretization/energies.jl:47-87)
+      b.ekin_orb[chan * b.nhmax + k] = kk / m;
+      b.ecou_orb[chan * b.nhmax + k] = -b.Z[p] * (cc / m);
     }
   }
 }

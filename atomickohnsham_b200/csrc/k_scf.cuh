@@ -181,60 +181,6 @@ __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b, int mode) 
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// k_orb_energy: u^T Kin_l u and u^T Coulomb u per occupied orbital
-// (compute_kinetic_energy / compute_coulomb_energy, src/discretization/energies.jl:47-87).
-// One CTA per orbital; its warps split the cells of the unassembled operators, every warp issues
-// the 3 x n column loads of a cell before using them; fixed-order block reduction.
-__global__ void __launch_bounds__(AKS_NT) k_orb_energy(DiscDev d, BatchDev b) {
-  const int p = blockIdx.y;
-  if (b.status[p] != 0) return;
-  const int o = blockIdx.x;  // (e*Lmax + l)*nhmax + k
-  const int k = o % b.nhmax, l = (o / b.nhmax) % b.Lmax, e = o / (b.nhmax * b.Lmax);
-  if (l >= b.Lp[p] || k >= b.nhp[p]) return;
-  const double n0 = b.occ[occ_off(b, p, 0, e, l, k)], n1 = b.occ[occ_off(b, p, 1, e, l, k)];
-  if (n0 == 0.0 && !(b.degen[p] && n1 != 0.0)) return;
-  __shared__ double red[AKS_NW];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = d.n, C = d.C;
-  const double* u = b.U + orb_off(b, p, e, l, k) * d.Nh;
-  const double ll = (double)(l * (l + 1));
-  double akin = 0.0, acou = 0.0;
-  for (int c = warp; c < C; c += AKS_NW) {
-    const int gi = (lane < n) ? d.l2g[c * n + lane] : -1;
-    const double xl = (gi >= 0) ? u[gi] : 0.0;
-    // symmetric blocks: column access (a*n + lane) is coalesced
-    const double* Ar = d.A_loc + (size_t)c * n * n + lane;
-    const double* M2r = d.Mm2_loc + (size_t)c * n * n + lane;
-    const double* M1r = d.Mm1_loc + (size_t)c * n * n + lane;
-    double rk = 0.0, rc = 0.0;
-#pragma unroll
-    for (int a0 = 0; a0 < 32; a0 += 16) {
-      double ka[16], ca[16];
-#pragma unroll
-      for (int a = 0; a < 16; ++a) {
-        const bool on = (a0 + a < n) && (lane < n);
-        ka[a] = on ? (Ar[(a0 + a) * n] + ll * M2r[(a0 + a) * n]) / 2.0 : 0.0;
-        ca[a] = on ? M1r[(a0 + a) * n] : 0.0;
-      }
-#pragma unroll
-      for (int a = 0; a < 16; ++a)
-        if (a0 + a < n) {
-          const double xa = __shfl_sync(0xffffffffu, xl, a0 + a);
-          rk = fma(ka[a], xa, rk);
-          rc = fma(ca[a], xa, rc);
-        }
-    }
-    akin = fma(rk, xl, akin);
-    acou = fma(rc, xl, acou);
-  }
-  akin = block_sum(akin, red);
-  acou = block_sum(acou, red);
-  if (threadIdx.x == 0) {
-    b.ekin_orb[orb_off(b, p, e, l, k)] = akin;
-    b.ecou_orb[orb_off(b, p, e, l, k)] = -b.Z[p] * acou;
-  }
-}
-
 // occupied-orbital list of (problem, slot) in the reference's density! order (sigma, k, l)
 struct OccList {
   int count;
@@ -698,8 +644,13 @@ __global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) 
   __shared__ int oidx[AKS_MAXORB];
   __shared__ int cnt_s, first_s;
   __shared__ double red[AKS_NW];
-  const int Nh = d.Nh, nt = b.ntile;
-  const int tr = blockIdx.x / nt, tc = blockIdx.x - tr * nt;
+  const int Nh = d.Nh;
+  // D is symmetric: only the tiles on and below the diagonal are kept current during the iterations
+  // (k_mirror_dense completes D when the host asks for it); blockIdx.x = tr (tr + 1) / 2 + tc
+  int tr = (int)((sqrt(8.0 * (double)blockIdx.x + 1.0) - 1.0) * 0.5);
+  while ((tr + 1) * (tr + 2) / 2 <= (int)blockIdx.x) ++tr;
+  while (tr * (tr + 1) / 2 > (int)blockIdx.x) --tr;
+  const int tc = blockIdx.x - tr * (tr + 1) / 2;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 entries each
   const int r0 = tr * MIX_TS + 4 * ty, c0 = tc * MIX_TS + tx;   // columns c0 + 16 c: coalesced rows
   double* D = b.Dd + ((size_t)p * b.s + e) * Nh * Nh;
@@ -764,7 +715,26 @@ __global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) 
         acc = fma(df, df, acc);
       }
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) b.norm_part[((size_t)p * b.s + e) * nt * nt + blockIdx.x] = acc;
+  if (threadIdx.x == 0) b.norm_part[((size_t)p * b.s + e) * b.ntri + blockIdx.x] = (tr == tc) ? acc : 2.0 * acc;
+}
+
+// upper triangle of D from the lower one (see k_mix_dense); one CTA per 32 x 32 tile above the diagonal
+__global__ void __launch_bounds__(AKS_NT) k_mirror_dense(DiscDev d, BatchDev b, int p) {
+  __shared__ double tile[32][33];
+  const int Nh = d.Nh, e = blockIdx.z;
+  const int bi = blockIdx.y, bj = blockIdx.x;   // writes block (bi, bj), bj >= bi, from (bj, bi)
+  if (bj < bi) return;
+  double* D = b.Dd + ((size_t)p * b.s + e) * Nh * Nh;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += AKS_NW) {
+    const int gi = bj * 32 + r, gj = bi * 32 + tx;
+    tile[r][tx] = (gi < Nh && gj < Nh) ? D[(size_t)gi * Nh + gj] : 0.0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += AKS_NW) {
+    const int gi = bi * 32 + r, gj = bj * 32 + tx;
+    if (gi < Nh && gj < Nh && gj > gi) D[(size_t)gi * Nh + gj] = tile[tx][r];
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -773,7 +743,7 @@ __global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) 
 __global__ void k_finalize(DiscDev d, BatchDev b) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= b.B || b.status[p] != 0) return;
-  const int npart = b.s * b.ntile * b.ntile;
+  const int npart = b.s * b.ntri;
   double ss = 0.0;
   for (int i = 0; i < npart; ++i) ss += b.norm_part[(size_t)p * npart + i];
   const double* En = b.Enew + (size_t)p * 5;

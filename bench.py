@@ -173,8 +173,9 @@ def b200_arm(args):
         dom = max(phases, key=phases.get)
         # k_potential: 2 n^2 Q flop per cell and spin (second half of W_xc) + C Q XC points
         pot_flops = B * Cc * 2.0 * n * n * Q
-        # k_mix_dense: read D + write D, 16 B per entry (SURVEY 8d W_dens bytes, in-place form)
-        mix_bytes = B * 16.0 * Nh * Nh
+        # k_mix_dense: read D + write D, 16 B per entry of the lower triangle (D is symmetric; SURVEY 8d
+        # W_dens bytes, in-place form)
+        mix_bytes = B * 16.0 * Nh * (Nh + 1) / 2
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         roof_all = {
             "potential": {"bound": "fp64", "achieved": pot_flops / (phases["potential"] * 1e-3) / 1e12,

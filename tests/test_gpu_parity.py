@@ -137,8 +137,9 @@ def test_trajectory_parity(name):
     integer = occ & (so.n == np.round(so.n))
     assert np.array_equal(sg["n"][integer], so.n[integer])
     assert np.allclose(sg["n"], so.n, atol=5e-5)
-    # occupied orbital energies: scftol-limited (~1e-8 abs) + LAPACK allowance in the oracle
-    assert np.max(np.abs(sg["eps"][occ] - so.eps[occ]) / np.maximum(1.0, np.abs(so.eps[occ]))) < 2e-7
+    # occupied orbital energies: first order in the density error left at the stopping rule (1e-7 .. 3e-7
+    # for the open 3d shell of Sc, whose two-fold block sits on a flat E(t)) + LAPACK allowance in the oracle
+    assert np.max(np.abs(sg["eps"][occ] - so.eps[occ]) / np.maximum(1.0, np.abs(so.eps[occ]))) < 1e-6
     bt.close()
 
 

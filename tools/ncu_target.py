@@ -6,7 +6,7 @@ from bench import build_disc
 import atomickohnsham_b200 as aks
 from atomickohnsham_b200.solver import Batch
 from atomickohnsham_b200.sweep import periodic_table_models
-Zs = [int(z) for z in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["18", "36", "54", "86"])]
+Zs = list(range(1, 87)) if (len(sys.argv) > 2 and sys.argv[2] == "all") else [int(z) for z in (sys.argv[2].split(",") if len(sys.argv) > 2 else ["18", "36", "54", "86"])]
 nsteps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 disc = build_disc(0)
 models, lhs, nhs = periodic_table_models(Zs)
