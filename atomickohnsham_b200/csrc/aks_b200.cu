@@ -430,7 +430,8 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   if (bt->smem_pot > 220 * 1024 || bt->smem_eig > 220 * 1024 || bt->smem_dens > 220 * 1024) {
     ctx->err = "discretization too large for the shared-memory tiling of this build"; aks_batch_destroy(bt); return AKS_EINVAL;
   }
-  CK(cudaFuncSetAttribute(k_potential, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
+  CK(cudaFuncSetAttribute(k_potential<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
+  CK(cudaFuncSetAttribute(k_potential<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
   CK(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
   CK(cudaFuncSetAttribute(k_reduce<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
   CK(cudaFuncSetAttribute(k_reduce<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
@@ -528,12 +529,21 @@ extern "C" int aks_batch_set_eig_window(aks_batch* bt, int32_t margin) {
     }                                                                                         \
   } while (0)
 
-static int launch_potential(aks_batch* bt, double* vxc_out, double* har_out) {
+// problems [p0, p0 + np); a CTA covers one cell and potential_np() problems
+static int launch_potential_range(aks_batch* bt, double* vxc_out, double* har_out, int p0, int np, int force) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
-  k_potential<<<dim3(dv.C, bt->B), AKS_NT, bt->smem_pot, ctx->stream>>>(dv, bt->dev, vxc_out, har_out, 0, 0);
+  const int NP = potential_np(dv.n, bt->dev.s);
+  const dim3 grid(dv.C, (np + NP - 1) / NP);
+  if (potential_nts(dv.n) == 1)
+    k_potential<1, 4><<<grid, AKS_NT, bt->smem_pot, ctx->stream>>>(dv, bt->dev, vxc_out, har_out, p0, np, force);
+  else
+    k_potential<2, 2><<<grid, AKS_NT, bt->smem_pot, ctx->stream>>>(dv, bt->dev, vxc_out, har_out, p0, np, force);
   LAUNCH_CHECK();
   return AKS_OK;
+}
+static int launch_potential(aks_batch* bt, double* vxc_out, double* har_out) {
+  return launch_potential_range(bt, vxc_out, har_out, 0, bt->B, 0);
 }
 // one pass of the eigensolver over the levels its mode selects (k_eig: 0 window, 1 refill, 2 completion)
 static int launch_eig_pass(aks_batch* bt, int mode) {
@@ -820,8 +830,7 @@ static int potential_hook(aks_batch* bt, int prob, double* vxc, double* har) {
   CK(cudaMalloc((void**)&dvxc, sizeof(double) * b.s * cn2));
   CK(cudaMalloc((void**)&dhar, sizeof(double) * cn2));
   // run the kernel for this problem only
-  k_potential<<<dim3(dv.C, 1), AKS_NT, bt->smem_pot, ctx->stream>>>(dv, b, dvxc, dhar, prob, 1);
-  LAUNCH_CHECK();
+  { int rc = launch_potential_range(bt, dvxc, dhar, prob, 1, 1); if (rc != AKS_OK) return rc; }
   std::vector<double> hv(b.s * cn2), hh(cn2);
   CK(cudaMemcpyAsync(hv.data(), dvxc, sizeof(double) * b.s * cn2, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(hh.data(), dhar, sizeof(double) * cn2, cudaMemcpyDeviceToHost, ctx->stream));

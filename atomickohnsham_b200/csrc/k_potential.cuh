@@ -13,50 +13,85 @@
 // the device state (it mixes linearly with D), so only the second GEMM-like half remains:
 //   K[i][j] = inv1 * sum_q g_i(q) (w_q v(rho_q)) g_j(q)          2 n^2 Q flop per cell and spin.
 // One warp owns a q-slice; each lane owns 3x3 register tiles of the symmetric K (upper tile
-// triangle only), generator values are staged per 256-node chunk in shared memory with a row
-// stride = 1 (mod 16) doubles so that the 7 distinct rows a warp touches hit distinct banks.
+// triangle only); generator values are staged per 64-node chunk in shared memory (TMA, 4 stages).
 #pragma once
 #include <cuda/barrier>
 
 #include "aks_device.cuh"
 #include "aks_types.cuh"
 
-// node chunk staged per TMA transfer and its padded row stride in shared memory: 130 doubles keeps every
-// row 16-byte aligned (bulk copies need it) and maps the 7 rows a warp touches (3*ti*130 mod 16 doubles)
-// onto distinct bank groups
-#define POT_QC 128
-#define POT_QCS 130
+// Node chunk staged per TMA transfer and its padded row stride in shared memory: 66 doubles keeps every
+// row 16-byte aligned (bulk copies need it) and maps the 7 rows a warp touches (3*ti*66 mod 16 doubles)
+// onto distinct bank groups.  POT_ST chunks are in flight / in use at any time.
+#define POT_QC 64
+#define POT_QCS 66
+#define POT_ST 4
+
+// A CTA owns one cell and NU "units" = (problem, spin) pairs: the generator chunks, the mass-tensor
+// block F_c and the fixed blocks of the cell are fetched once for all of them, and the 9 products
+// g_i g_j of a lane's tile are formed once per node and reused by every unit (9 DMUL + NU x 9 DFMA).
+// Orders p <= 20 need one 3x3 tile per lane (NTS = 1, NU = 4); larger orders two (NTS = 2, NU = 2).
+__host__ __device__ inline int potential_nts(int n) { const int T = (n + 2) / 3; return (T * (T + 1) / 2 <= 32) ? 1 : 2; }
+__host__ __device__ inline int potential_nu(int n) { return potential_nts(n) == 1 ? 4 : 2; }
+__host__ __device__ inline int potential_np(int n, int s) { const int np = potential_nu(n) / s; return np < 1 ? 1 : np; }
 
 __host__ __device__ inline size_t potential_smem_bytes(int n, int Q, int s) {
   const int T = (n + 2) / 3, n3 = 3 * T;
   const int Qpad = ((Q + POT_QC - 1) / POT_QC) * POT_QC;
-  return sizeof(double) * ((size_t)s * Qpad + 2 * (size_t)n3 * POT_QCS + (size_t)AKS_NW * n3 * n3 +
-                           (size_t)(s + 1) * n * n + n + 8);
+  const int nu = potential_nu(n) < s ? s : potential_nu(n);
+  size_t stage = (size_t)POT_ST * n3 * POT_QCS, kp = (size_t)AKS_NW * n3 * n3;
+  if (kp > stage) stage = kp;
+  return sizeof(double) * ((size_t)nu * Qpad + stage + 2 * (size_t)nu * n * n + (size_t)nu * n + 8);
 }
 
-__global__ void __launch_bounds__(AKS_NT)
+template <int NTS, int NU>
+__global__ void __launch_bounds__(AKS_NT, 2)
 k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __restrict__ har_loc_out,
-            int p0, int force) {
-  const int c = blockIdx.x, p = blockIdx.y + p0;
-  if (!force && b.status[p] != 0) return;
+            int p0, int np, int force) {
+  const int c = blockIdx.x;
+  const int n = d.n, Q = d.Q, s = b.s, C = d.C;
+  constexpr int NUs = NU;                    // units of this CTA
+  const int NP = (NUs / s) < 1 ? 1 : NUs / s;  // problems of this CTA (NU >= s is guaranteed by the host)
+  const int pbase = p0 + blockIdx.y * NP;
+  // unit u -> problem pbase + u / s, spin u % s
+  bool uval[NU];
+  bool any = false;
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    const int pu = pbase + u / s;
+    uval[u] = (u / s < NP) && (pu < p0 + np) && (force || b.status[pu] == 0);
+    any = any || uval[u];
+  }
+  if (!any) return;
   extern __shared__ __align__(16) double sm_pot[];
   double* sm = sm_pot;
-  const int n = d.n, Q = d.Q, s = b.s, C = d.C;
   const int T = (n + 2) / 3, n3 = 3 * T, ntile = T * (T + 1) / 2;
   const int Qpad = ((Q + POT_QC - 1) / POT_QC) * POT_QC;
-  double* fs = sm;                           // [s][Qpad]
-  double* Gs = fs + (size_t)s * Qpad;        // [2][n3][POT_QCS]  double-buffered node chunks (16 B aligned)
-  double* Kp = Gs + 2 * (size_t)n3 * POT_QCS;  // [NW][n3*n3]
-  double* Ks = Kp + (size_t)AKS_NW * n3 * n3;  // [s][n*n]   XC block per spin
-  double* Hs = Ks + (size_t)s * n * n;       // [n*n]      Hartree block
-  double* wl = Hs + n * n;                   // [n]
+  size_t stage = (size_t)POT_ST * n3 * POT_QCS;
+  if ((size_t)AKS_NW * n3 * n3 > stage) stage = (size_t)AKS_NW * n3 * n3;
+  double* fs = sm;                           // [NU][Qpad]   w_q v_u(rho_q)
+  double* Gs = fs + (size_t)NU * Qpad;       // [POT_ST][n3][POT_QCS] node chunks (16 B aligned)
+  double* Kp = Gs;                           // [NW][n3*n3]  cross-warp reduction, after the chunks are done
+  double* Ks = Gs + stage;                   // [NU][n*n]    XC block per unit
+  double* Hs = Ks + (size_t)NU * n * n;      // [NP][n*n]    Hartree block per problem
+  double* wl = Hs + (size_t)NU * n * n;      // [NP][n]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ex = b.ex[p], ec = b.ec[p];
-  const bool has_xc = (ex != 0) || (ec != 0);
   const double inv1 = d.inv1[c];
 
-  // ---- 1. pointwise XC potential at the Gauss nodes: f_sigma[q] = w_q v_sigma(rho(q))
-  if (has_xc) {
+  // ---- 1. pointwise XC potential at the Gauss nodes: f_u[q] = w_q v_u(rho(q))
+  bool any_xc = false;
+  for (int pp = 0; pp < NP; ++pp) {
+    const int p = pbase + pp;
+    const bool val = uval[pp * s];
+    const int ex = val ? b.ex[p] : 0, ec = val ? b.ec[p] : 0;
+    const bool has_xc = (ex != 0) || (ec != 0);
+    any_xc = any_xc || has_xc;
+    double* f0s = fs + (size_t)(pp * s) * Qpad;
+    double* f1s = f0s + Qpad;
+    if (!has_xc) {
+      for (int q = tid; q < s * Qpad; q += AKS_NT) f0s[q] = 0.0;
+      continue;
+    }
     const double* r0 = b.rho_q + ((size_t)(p * s + 0) * C + c) * Q;
     const double* r1 = (s == 2) ? b.rho_q + ((size_t)(p * s + 1) * C + c) * Q : nullptr;
     double* fo0 = b.fxc + ((size_t)(p * s + 0) * C + c) * Q;
@@ -77,14 +112,18 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
           fo1[q] = f1;
         }
       }
-      fs[q] = f0;
-      if (s == 2) fs[Qpad + q] = f1;
+      f0s[q] = f0;
+      if (s == 2) f1s[q] = f1;
     }
   }
+  // units beyond the problems of this CTA (NU > NP * s cannot happen; kept for safety)
+  for (int u = NP * s; u < NU; ++u)
+    for (int q = tid; q < Qpad; q += AKS_NT) fs[(size_t)u * Qpad + q] = 0.0;
 
-  // ---- 2. K_sigma = sum_q f_sigma[q] g g^T, 3x3 register tiles
-  int ti[2], tj[2];
-  for (int ts = 0; ts < 2; ++ts) {
+  // ---- 2. K_u = sum_q f_u[q] g g^T, 3x3 register tiles
+  int ti[NTS], tj[NTS];
+#pragma unroll
+  for (int ts = 0; ts < NTS; ++ts) {
     int tile = lane + 32 * ts;
     ti[ts] = -1;
     tj[ts] = -1;
@@ -95,50 +134,49 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
       tj[ts] = a + rem;
     }
   }
-  double acc[2][2][9];
+  double acc[NTS][NU][9];
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < NTS; ++a)
 #pragma unroll
-    for (int e = 0; e < 2; ++e)
+    for (int u = 0; u < NU; ++u)
 #pragma unroll
-      for (int k = 0; k < 9; ++k) acc[a][e][k] = 0.0;
+      for (int k = 0; k < 9; ++k) acc[a][u][k] = 0.0;
 
-  if (has_xc) {
-    // Generator values at the nodes are streamed through shared memory in 128-node chunks by the TMA
-    // engine (cp.async.bulk, one 1 KB row per transfer, completion on an mbarrier), double buffered:
-    // chunk c+2 is in flight while chunk c is consumed.
+  if (any_xc) {
+    // Generator values at the nodes are streamed through shared memory in 64-node chunks by the TMA
+    // engine (cp.async.bulk, one 512 B row per transfer, completion on an mbarrier), POT_ST stages deep:
+    // chunk ch + POT_ST is requested as soon as every warp is done with chunk ch.
     using barrier_t = cuda::barrier<cuda::thread_scope_block>;
     namespace cde = cuda::device::experimental;
 #pragma nv_diag_suppress static_var_with_dynamic_init
-    __shared__ barrier_t bar[2];
+    __shared__ barrier_t bar[POT_ST];
     const int nch = Qpad / POT_QC;
     const bool tma_ok = ((Q % 2) == 0) && ((d.Qs % 2) == 0);   // 16-byte granularity of every row piece
     if (tid == 0) {
-      init(&bar[0], AKS_NT);
-      init(&bar[1], AKS_NT);
+#pragma unroll
+      for (int st = 0; st < POT_ST; ++st) init(&bar[st], AKS_NT);
       cde::fence_proxy_async_shared_cta();
     }
-    // rows >= n and the tail of the last chunk are never written by the copies: zero both buffers once
-    for (int idx = tid; idx < 2 * n3 * POT_QCS; idx += AKS_NT) Gs[idx] = 0.0;
+    // rows >= n and the tail of the last chunk are never written by the copies: zero the buffers once
+    for (int idx = tid; idx < POT_ST * n3 * POT_QCS; idx += AKS_NT) Gs[idx] = 0.0;
     __syncthreads();
-    barrier_t::arrival_token tok[2];
+    barrier_t::arrival_token tok[POT_ST];
     auto issue = [&](int ch) {   // thread 0 only
-      double* dst = Gs + (size_t)(ch & 1) * n3 * POT_QCS;
+      const int st = ch % POT_ST;
+      double* dst = Gs + (size_t)st * n3 * POT_QCS;
       const int q0 = ch * POT_QC, len = min(POT_QC, Q - q0);
       for (int g = 0; g < n; ++g)
-        cde::cp_async_bulk_global_to_shared(dst + g * POT_QCS, d.Pg + (size_t)g * d.Qs + q0, (uint32_t)(len * 8), bar[ch & 1]);
-      tok[ch & 1] = cuda::device::barrier_arrive_tx(bar[ch & 1], 1, (size_t)n * len * 8);
+        cde::cp_async_bulk_global_to_shared(dst + g * POT_QCS, d.Pg + (size_t)g * d.Qs + q0, (uint32_t)(len * 8), bar[st]);
+      tok[st] = cuda::device::barrier_arrive_tx(bar[st], 1, (size_t)n * len * 8);
     };
-    if (tma_ok && tid == 0) {
-      issue(0);
-      if (nch > 1) issue(1);
-    }
+    if (tma_ok && tid == 0)
+      for (int ch = 0; ch < POT_ST && ch < nch; ++ch) issue(ch);
     for (int ch = 0; ch < nch; ++ch) {
-      const int q0 = ch * POT_QC;
-      double* Gb = Gs + (size_t)(ch & 1) * n3 * POT_QCS;
+      const int q0 = ch * POT_QC, st = ch % POT_ST;
+      double* Gb = Gs + (size_t)st * n3 * POT_QCS;
       if (tma_ok) {
-        if (tid == 0) bar[ch & 1].wait(std::move(tok[ch & 1]));
-        else bar[ch & 1].arrive_and_wait();
+        if (tid == 0) bar[st].wait(std::move(tok[st]));
+        else bar[st].arrive_and_wait();
       } else {
         __syncthreads();
         for (int idx = tid; idx < n * POT_QC; idx += AKS_NT) {
@@ -147,76 +185,59 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
         }
         __syncthreads();
       }
-      // hot loop: per node 6 generator values + f, 3 DMUL + 9 DFMA per spin for this lane's 3x3 tile.
-      // Slot 0 covers the first 32 tiles (all of them for p <= 20); slot 1 only exists for p > 21.
+      // hot loop: per node 6 generator values, 9 products, then one weight + 9 DFMA per unit
       const int jq0 = warp * (POT_QC / AKS_NW);
 #pragma unroll
-      for (int ts = 0; ts < 2; ++ts) {
+      for (int ts = 0; ts < NTS; ++ts) {
         if (ti[ts] < 0) continue;
-        if (ts == 1 && ntile <= 32) break;
         const double* gi = Gb + (3 * ti[ts]) * POT_QCS + jq0;
         const double* gj = Gb + (3 * tj[ts]) * POT_QCS + jq0;
         const double* f0 = fs + q0 + jq0;
-        double* A0 = acc[ts][0];
-        double* A1 = acc[ts][1];
-        if (s == 1) {
-#pragma unroll 4
-          for (int jq = 0; jq < POT_QC / AKS_NW; ++jq) {
-            const double a0 = gi[jq], a1 = gi[POT_QCS + jq], a2 = gi[2 * POT_QCS + jq];
-            const double fq = f0[jq];
-            const double t0 = fq * gj[jq], t1 = fq * gj[POT_QCS + jq], t2 = fq * gj[2 * POT_QCS + jq];
-            A0[0] = fma(a0, t0, A0[0]); A0[1] = fma(a0, t1, A0[1]); A0[2] = fma(a0, t2, A0[2]);
-            A0[3] = fma(a1, t0, A0[3]); A0[4] = fma(a1, t1, A0[4]); A0[5] = fma(a1, t2, A0[5]);
-            A0[6] = fma(a2, t0, A0[6]); A0[7] = fma(a2, t1, A0[7]); A0[8] = fma(a2, t2, A0[8]);
-          }
-        } else {
 #pragma unroll 2
-          for (int jq = 0; jq < POT_QC / AKS_NW; ++jq) {
-            const double a0 = gi[jq], a1 = gi[POT_QCS + jq], a2 = gi[2 * POT_QCS + jq];
-            const double b0 = gj[jq], b1 = gj[POT_QCS + jq], b2 = gj[2 * POT_QCS + jq];
-            const double fu = f0[jq], fd = f0[Qpad + jq];
-            double t0 = fu * b0, t1 = fu * b1, t2 = fu * b2;
-            A0[0] = fma(a0, t0, A0[0]); A0[1] = fma(a0, t1, A0[1]); A0[2] = fma(a0, t2, A0[2]);
-            A0[3] = fma(a1, t0, A0[3]); A0[4] = fma(a1, t1, A0[4]); A0[5] = fma(a1, t2, A0[5]);
-            A0[6] = fma(a2, t0, A0[6]); A0[7] = fma(a2, t1, A0[7]); A0[8] = fma(a2, t2, A0[8]);
-            t0 = fd * b0; t1 = fd * b1; t2 = fd * b2;
-            A1[0] = fma(a0, t0, A1[0]); A1[1] = fma(a0, t1, A1[1]); A1[2] = fma(a0, t2, A1[2]);
-            A1[3] = fma(a1, t0, A1[3]); A1[4] = fma(a1, t1, A1[4]); A1[5] = fma(a1, t2, A1[5]);
-            A1[6] = fma(a2, t0, A1[6]); A1[7] = fma(a2, t1, A1[7]); A1[8] = fma(a2, t2, A1[8]);
+        for (int jq = 0; jq < POT_QC / AKS_NW; ++jq) {
+          const double a0 = gi[jq], a1 = gi[POT_QCS + jq], a2 = gi[2 * POT_QCS + jq];
+          const double b0 = gj[jq], b1 = gj[POT_QCS + jq], b2 = gj[2 * POT_QCS + jq];
+          const double p00 = a0 * b0, p01 = a0 * b1, p02 = a0 * b2;
+          const double p10 = a1 * b0, p11 = a1 * b1, p12 = a1 * b2;
+          const double p20 = a2 * b0, p21 = a2 * b1, p22 = a2 * b2;
+#pragma unroll
+          for (int u = 0; u < NU; ++u) {
+            const double fq = f0[(size_t)u * Qpad + jq];
+            double* A = acc[ts][u];
+            A[0] = fma(p00, fq, A[0]); A[1] = fma(p01, fq, A[1]); A[2] = fma(p02, fq, A[2]);
+            A[3] = fma(p10, fq, A[3]); A[4] = fma(p11, fq, A[4]); A[5] = fma(p12, fq, A[5]);
+            A[6] = fma(p20, fq, A[6]); A[7] = fma(p21, fq, A[7]); A[8] = fma(p22, fq, A[8]);
           }
         }
       }
       if (tma_ok) {
-        __syncthreads();   // everyone is done with this buffer: refill it with chunk ch+2
-        if (tid == 0 && ch + 2 < nch) {
-          // (a shorter last chunk leaves older, finite values in the tail columns; f is zero there)
-          issue(ch + 2);
-        }
+        __syncthreads();   // everyone is done with this buffer: refill it with chunk ch + POT_ST
+        // (a shorter last chunk leaves older, finite values in the tail columns; f is zero there)
+        if (tid == 0 && ch + POT_ST < nch) issue(ch + POT_ST);
       }
     }
   }
   // cross-warp reduction, fixed order; symmetrise diagonal tiles; scale by inv1
 #pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    if (e >= s) break;
+  for (int u = 0; u < NU; ++u) {
     __syncthreads();
-    if (has_xc) {
+    if (any_xc) {
 #pragma unroll
-      for (int ts = 0; ts < 2; ++ts) {
+      for (int ts = 0; ts < NTS; ++ts) {
         if (ti[ts] < 0) continue;
         double* K = Kp + (size_t)warp * n3 * n3;
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
           for (int bb = 0; bb < 3; ++bb)
-            K[(3 * ti[ts] + a) * n3 + 3 * tj[ts] + bb] = acc[ts][e][3 * a + bb];
+            K[(3 * ti[ts] + a) * n3 + 3 * tj[ts] + bb] = acc[ts][u][3 * a + bb];
       }
     }
     __syncthreads();
     for (int idx = tid; idx < n * n; idx += AKS_NT) {
       const int i = idx / n, j = idx - i * n;
       double v = 0.0;
-      if (has_xc) {
+      if (any_xc) {
         const int ii = (i / 3 <= j / 3) ? i : j, jj = (i / 3 <= j / 3) ? j : i;
         double s1 = 0.0, s2 = 0.0;
         for (int wv = 0; wv < AKS_NW; ++wv) {
@@ -226,60 +247,84 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
         v = (i / 3 == j / 3) ? 0.5 * (s1 + s2) : s1;
         v *= inv1;
       }
-      Ks[e * n * n + idx] = v;
+      Ks[(size_t)u * n * n + idx] = v;
     }
   }
 
-  // ---- 3. Hartree block: coeff * (sum_m W_m F[ij][m] + N/Rmax M0)
-  const double coeff = b.hartree[p];
-  if (tid < n) {
-    const int gi = d.l2g[c * n + tid];
-    wl[tid] = (gi >= 0 && coeff != 0.0) ? b.Wv[(size_t)p * d.Nh + gi] : 0.0;
+  // ---- 3. Hartree block per problem: coeff * (sum_m W_m F[ij][m] + N/Rmax M0); F_c is read once
+  for (int idx = tid; idx < NP * n; idx += AKS_NT) {
+    const int pp = idx / n, m = idx - pp * n;
+    const int p = pbase + pp;
+    const int gi = d.l2g[c * n + m];
+    const bool val = uval[pp * s];
+    wl[idx] = (val && gi >= 0 && b.hartree[p] != 0.0) ? b.Wv[(size_t)p * d.Nh + gi] : 0.0;
   }
   __syncthreads();
   {
-    const double shift = b.N[p] / d.Rmax;
     const double* Fc = d.F_loc + (size_t)c * n * n * n;
     const double* M0c = d.M0_loc + (size_t)c * n * n;
+    bool any_h = false;
+    for (int pp = 0; pp < NP; ++pp) any_h = any_h || (uval[pp * s] && b.hartree[pbase + pp] != 0.0);
     for (int idx = tid; idx < n * n; idx += AKS_NT) {
-      double v = 0.0;
-      if (coeff != 0.0) {
-        double fw = 0.0;
-        for (int m = 0; m < n; ++m) fw = fma(wl[m], Fc[(size_t)m * n * n + idx], fw);
-        v = (fw + shift * M0c[idx]) * coeff;
-      }
-      Hs[idx] = v;
+      double fw[NU];
+#pragma unroll
+      for (int pp = 0; pp < NU; ++pp) fw[pp] = 0.0;
+      if (any_h)
+        for (int m = 0; m < n; ++m) {
+          const double fv = Fc[(size_t)m * n * n + idx];
+#pragma unroll
+          for (int pp = 0; pp < NU; ++pp)
+            if (pp < NP) fw[pp] = fma(wl[pp * n + m], fv, fw[pp]);
+        }
+      const double m0 = M0c[idx];
+#pragma unroll
+      for (int pp = 0; pp < NU; ++pp)
+        if (pp < NP) {
+          const int p = pbase + pp;
+          double v = 0.0;
+          if (uval[pp * s]) {
+            const double coeff = b.hartree[p];
+            if (coeff != 0.0) v = (fw[pp] + (b.N[p] / d.Rmax) * m0) * coeff;
+          }
+          Hs[(size_t)pp * n * n + idx] = v;
+        }
     }
   }
   __syncthreads();
 
-  // optional local outputs for the step-level hooks
-  if (vxc_loc_out)
+  // optional local outputs for the step-level hooks (problem p0 only: launched with np = 1)
+  if (vxc_loc_out && blockIdx.y == 0)
     for (int e = 0; e < s; ++e)
       for (int idx = tid; idx < n * n; idx += AKS_NT)
-        vxc_loc_out[((size_t)e * C + c) * n * n + idx] = Ks[e * n * n + idx];
-  if (har_loc_out)
+        vxc_loc_out[((size_t)e * C + c) * n * n + idx] = Ks[(size_t)e * n * n + idx];
+  if (har_loc_out && blockIdx.y == 0)
     for (int idx = tid; idx < n * n; idx += AKS_NT) har_loc_out[(size_t)c * n * n + idx] = Hs[idx];
 
-  // ---- 4. H_l = (Kin_l + Coulomb) + Vxc + Hartree, packed per (sigma, l, cell)
-  const double Zp = b.Z[p];
-  const int Lp = b.Lp[p];
+  // ---- 4. H_l = (Kin_l + Coulomb) + Vxc + Hartree, packed per (problem, sigma, l, cell)
   const double* Ac = d.A_loc + (size_t)c * n * n;
   const double* M1c = d.Mm1_loc + (size_t)c * n * n;
   const double* M2c = d.Mm2_loc + (size_t)c * n * n;
-  for (int e = 0; e < s; ++e) {
-    for (int l = 0; l < Lp; ++l) {
-      double* out = b.Hpk + ((((size_t)p * s + e) * b.Lmax + l) * C + c) * d.npk;
-      double* outf = b.Hfull + ((((size_t)p * s + e) * b.Lmax + l) * C + c) * (size_t)n * n;
-      const double ll = (double)(l * (l + 1));
-      for (int idx = tid; idx < n * n; idx += AKS_NT) {
-        const int lo_idx = d.lo_tab[idx];   // index of the lower-triangle twin: exactly symmetric output
-        const int pk = d.pk_tab[idx];       // packed position, or -1 above the diagonal
-        const double kin = (Ac[lo_idx] + ll * M2c[lo_idx]) * 0.5;
-        const double cou = -Zp * M1c[lo_idx];
-        const double h = ((kin + cou) + Ks[e * n * n + lo_idx]) + Hs[lo_idx];
-        outf[idx] = h;
-        if (pk >= 0) out[pk] = h;
+  for (int pp = 0; pp < NP; ++pp) {
+    if (!uval[pp * s]) continue;
+    const int p = pbase + pp;
+    const double Zp = b.Z[p];
+    const int Lp = b.Lp[p];
+    for (int e = 0; e < s; ++e) {
+      const double* Ku = Ks + (size_t)(pp * s + e) * n * n;
+      const double* Hp = Hs + (size_t)pp * n * n;
+      for (int l = 0; l < Lp; ++l) {
+        double* out = b.Hpk + ((((size_t)p * s + e) * b.Lmax + l) * C + c) * d.npk;
+        double* outf = b.Hfull + ((((size_t)p * s + e) * b.Lmax + l) * C + c) * (size_t)n * n;
+        const double ll = (double)(l * (l + 1));
+        for (int idx = tid; idx < n * n; idx += AKS_NT) {
+          const int lo_idx = d.lo_tab[idx];   // index of the lower-triangle twin: exactly symmetric output
+          const int pk = d.pk_tab[idx];       // packed position, or -1 above the diagonal
+          const double kin = (Ac[lo_idx] + ((l > 0) ? ll * M2c[lo_idx] : 0.0)) * 0.5;
+          const double cou = -Zp * M1c[lo_idx];
+          const double h = ((kin + cou) + Ku[lo_idx]) + Hp[lo_idx];
+          outf[idx] = h;
+          if (pk >= 0) out[pk] = h;
+        }
       }
     }
   }
