@@ -114,6 +114,8 @@ extern "C" int aks_ctx_create(int device, aks_ctx** out) {
   xc.f2p0 = 4.0 / (9.0 * (std::pow(2.0, 1.0 / 3.0) - 1.0));
   xc.two43m2 = std::pow(2.0, 4.0 / 3.0) - 2.0;
   xc.third = 1.0 / 3.0;
+  xc.crs = std::cbrt(3.0 / (4.0 * M_PI));
+  xc.icrs = 1.0 / xc.crs;
   xc.four3 = 4.0 / 3.0;
   CK(cudaMemcpyToSymbol(c_xc, &xc, sizeof xc));
   return AKS_OK;

@@ -4,8 +4,9 @@
 //   src/physics/exchange correlation/SlaterXa.jl:11-30   (Slater exchange)
 //   src/physics/exchange correlation/PerdewWang.jl:15-101 (PW92 correlation)
 //   src/physics/exchange correlation/BuiltinFunctional.jl:74-142 (clamp at 0, zero at rho = 0)
-// x^(1/3), x^(3/2), x^(4/3) are evaluated as cbrt(x), x*sqrt(x), x*cbrt(x) (the reference calls pow);
-// the results differ by <= 1-2 ulp, far inside the 1e-10 parity tolerance.
+// x^(1/3), x^(3/2), x^(4/3) are evaluated from ONE rcbrt(rho) per point (rho^(1/3) = rho * rcbrt^2,
+// rs = (3/4pi)^(1/3) * rcbrt), x*sqrt(x), x*cbrt(x) (the reference calls pow), and the two quotients of
+// G' share one division; the results differ by a few ulp, far inside the 1e-10 parity tolerance.
 // Brent follows Optim.jl's `Brent()` as called from
 //   src/algorithms/optimization/line_search.jl:59-67.
 #pragma once
@@ -26,6 +27,8 @@ struct XcConsts {
   double f2p0;    // 4/(9(2^(1/3)-1))
   double two43m2; // 2^(4/3)-2
   double third;   // 1/3 as a double
+  double crs;     // (3/(4 pi))^(1/3): rs = crs * rho^(-1/3)
+  double icrs;    // 1/crs
   double four3;   // 4/3 as a double
 };
 __constant__ XcConsts c_xc;
@@ -59,21 +62,29 @@ __device__ __forceinline__ PwPar pw_p0() { return {0.031091, 0.21370, 7.5957, 3.
 __device__ __forceinline__ PwPar pw_p1() { return {0.015545, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517}; }
 __device__ __forceinline__ PwPar pw_pa() { return {0.016887, 0.11125, 10.357, 3.6231, 0.88026, 0.49671}; }
 
-// G(rs) and dG/drs (PerdewWang.jl:15-27)
-__device__ __forceinline__ void pw_G(double rs, const PwPar& P, double& G, double& dG) {
-  const double sq = sqrt(rs);
+// rho^(1/3) and rs = (3/(4 pi rho))^(1/3) from one reciprocal cube root
+__device__ __forceinline__ void rho_roots(double rho, double& cr, double& rs) {
+  const double ic = rcbrt(rho);
+  cr = (rho * ic) * ic;
+  rs = c_xc.crs * ic;
+}
+// G(rs) and dG/drs (PerdewWang.jl:15-27); sq = sqrt(rs), isq = 1/sqrt(rs)
+__device__ __forceinline__ void pw_G(double rs, double sq, double isq, const PwPar& P, double& G, double& dG) {
   const double rs32 = rs * sq;
   const double Q0 = -2.0 * P.A * (1.0 + P.a1 * rs);
   const double dQ0 = -2.0 * P.A * P.a1;
   const double Q1 = 2.0 * P.A * (P.b1 * sq + P.b2 * rs + P.b3 * rs32 + P.b4 * (rs * rs));
-  const double dQ1 = 2.0 * P.A * (P.b1 / (2.0 * sq) + P.b2 + 1.5 * P.b3 * sq + 2.0 * P.b4 * rs);
-  const double lg = log(1.0 + 1.0 / Q1);
+  const double dQ1 = 2.0 * P.A * (0.5 * P.b1 * isq + P.b2 + 1.5 * P.b3 * sq + 2.0 * P.b4 * rs);
+  const double iq = 1.0 / (Q1 * (Q1 + 1.0));        // 1/Q1 = (Q1 + 1) * iq
+  const double lg = log(1.0 + (Q1 + 1.0) * iq);
   G = Q0 * lg;
-  dG = dQ0 * lg - Q0 * dQ1 / (Q1 * (Q1 + 1.0));
+  dG = dQ0 * lg - Q0 * dQ1 * iq;
 }
-
-__device__ __forceinline__ double rs_of_rho(double rho) {
-  return cbrt(3.0 / (c_xc.fourpi * rho));
+// G(rs) alone
+__device__ __forceinline__ double pw_G0(double rs, double sq, const PwPar& P) {
+  const double Q0 = -2.0 * P.A * (1.0 + P.a1 * rs);
+  const double Q1 = 2.0 * P.A * (P.b1 * sq + P.b2 * rs + P.b3 * (rs * sq) + P.b4 * (rs * rs));
+  return Q0 * log(1.0 + 1.0 / Q1);
 }
 
 // ---------------------------------------------------------------- unpolarised
@@ -81,25 +92,25 @@ __device__ __forceinline__ double rs_of_rho(double rho) {
 __device__ __forceinline__ double xc_vrho_unpol(double rho, int ex, int ec) {
   double v = 0.0;
   if (rho <= 0.0) return 0.0;
+  double cr, rs;
+  rho_roots(rho, cr, rs);
   if (ec == 12) {
-    const double rs = rs_of_rho(rho);
+    const double sq = sqrt(rs);
     double G, dG;
-    pw_G(rs, pw_p0(), G, dG);
+    pw_G(rs, sq, sq * (cr * c_xc.icrs), pw_p0(), G, dG);   // 1/sqrt(rs) = sqrt(rs) / rs, 1/rs = rho^(1/3) / crs
     v += G - rs / 3.0 * dG;
   }
-  if (ex == 1) v += -c_xc.cx * cbrt(rho);
+  if (ex == 1) v += -c_xc.cx * cr;
   return v;
 }
 // exc per particle = ex + ec
 __device__ __forceinline__ double xc_zk_unpol(double rho, int ex, int ec) {
   double e = 0.0;
   if (rho <= 0.0) return 0.0;
-  if (ec == 12) {
-    double G, dG;
-    pw_G(rs_of_rho(rho), pw_p0(), G, dG);
-    e += G;
-  }
-  if (ex == 1) e += -c_xc.cx34 * cbrt(rho);
+  double cr, rs;
+  rho_roots(rho, cr, rs);
+  if (ec == 12) e += pw_G0(rs, sqrt(rs), pw_p0());
+  if (ex == 1) e += -c_xc.cx34 * cr;
   return e;
 }
 
@@ -118,11 +129,13 @@ __device__ __forceinline__ void xc_vrho_pol(double ru, double rd, int ex, int ec
   const double rho = ru + rd;
   if (ec == 12 && rho > 0.0) {
     const double z = (ru - rd) / rho;
-    const double rs = rs_of_rho(rho);
+    double cr, rs;
+    rho_roots(rho, cr, rs);
+    const double sq = sqrt(rs), isq = sq * (cr * c_xc.icrs);
     double e0, d0, e1, d1, ea, da;
-    pw_G(rs, pw_p0(), e0, d0);
-    pw_G(rs, pw_p1(), e1, d1);
-    pw_G(rs, pw_pa(), ea, da);
+    pw_G(rs, sq, isq, pw_p0(), e0, d0);
+    pw_G(rs, sq, isq, pw_p1(), e1, d1);
+    pw_G(rs, sq, isq, pw_pa(), ea, da);
     const double ac = -ea, dac = -da;
     const double f = pw_fz(z), df = pw_dfz(z);
     const double z3 = z * z * z, z4 = z3 * z;
@@ -146,11 +159,10 @@ __device__ __forceinline__ double xc_zk_pol(double ru, double rd, int ex, int ec
   double e = 0.0;
   if (ec == 12) {
     const double z = (ru - rd) / rho;
-    const double rs = rs_of_rho(rho);
-    double e0, d0, e1, d1, ea, da;
-    pw_G(rs, pw_p0(), e0, d0);
-    pw_G(rs, pw_p1(), e1, d1);
-    pw_G(rs, pw_pa(), ea, da);
+    double cr, rs;
+    rho_roots(rho, cr, rs);
+    const double sq = sqrt(rs);
+    const double e0 = pw_G0(rs, sq, pw_p0()), e1 = pw_G0(rs, sq, pw_p1()), ea = pw_G0(rs, sq, pw_pa());
     const double f = pw_fz(z);
     const double z4 = z * z * z * z;
     e += e0 + (-ea) * (f / c_xc.f2p0) * (1.0 - z4) + (e1 - e0) * f * z4;
