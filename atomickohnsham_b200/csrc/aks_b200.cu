@@ -554,7 +554,7 @@ static int launch_eig_pass(aks_batch* bt, int mode) {
   const BatchDev& b = bt->dev;
   k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
-  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_eig, ctx->stream>>>(dv, b, mode);
+  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->B), EIG_NT, bt->smem_eig, ctx->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
   const int nchunk = (dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK;
   k_eig_final<<<dim3(nchunk, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b, mode);

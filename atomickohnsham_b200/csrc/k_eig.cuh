@@ -34,7 +34,7 @@
 #include "aks_device.cuh"
 #include "aks_types.cuh"
 
-// per-cell reduced data, field-major in shared memory ([field][cell]); in global [cell][field]
+// per-cell reduced data of a channel, field-major ([field][cell]: consecutive cells are consecutive addresses)
 //   td[nb] te[nb] ht0[nb] ht1[nb] mt0[nb] mt1[nb] Hhh[3] pad[1]      (te[nb-1] unused)
 __host__ __device__ inline int red_stride(int nb) { return 6 * nb + 4; }
 
@@ -139,7 +139,7 @@ k_reduce(DiscDev d, BatchDev b) {
   double pcol[NBM];
 #pragma unroll
   for (int m = 0; m < NBM; ++m) pcol[m] = act ? Ls[m * NBM + ir] : 0.0;
-  double* red = b.red + (chan * C + c) * red_stride(nb);
+  double* red = b.red + chan * C * red_stride(nb) + c;   // field-major: entry f of cell c at red[f * C]
   // 5. Householder tridiagonalisation C <- H_k C H_k, P <- H_k P
 #pragma unroll
   for (int k = 0; k + 2 < NBM; ++k) {
@@ -148,15 +148,15 @@ k_reduce(DiscDev d, BatchDev b) {
       const double sig2 = warp_sum((i > k + 1) ? x * x : 0.0);
       const double xk1 = __shfl_sync(0xffffffffu, x, k + 1);
       const double dk = __shfl_sync(0xffffffffu, row[k], k);
-      if (lane == 0) red[k] = dk;
+      if (lane == 0) red[(k) * C] = dk;
       if (sig2 == 0.0) {  // already tridiagonal in this column (warp-uniform)
-        if (lane == 0) red[nb + k] = xk1;
+        if (lane == 0) red[(nb + k) * C] = xk1;
       } else {
         const double alpha = -copysign(sqrt(xk1 * xk1 + sig2), xk1);
         const double vk1 = xk1 - alpha;
         const double v = (i == k + 1) ? vk1 : ((i > k + 1) ? x : 0.0);
         const double tau = 2.0 / (sig2 + vk1 * vk1);
-        if (lane == 0) red[nb + k] = alpha;
+        if (lane == 0) red[(nb + k) * C] = alpha;
         vs[lane] = v;
         __syncwarp();
         const int j0 = (k + 1) / 2;   // v[j] = 0 for j <= k: start at the even index below k+1
@@ -212,15 +212,15 @@ k_reduce(DiscDev d, BatchDev b) {
     __syncwarp();
     if (lane == 0) {
       if (nb >= 2) {
-        red[nb - 2] = Ps[(nb - 2) * LDP + nb - 2];
-        red[nb + nb - 2] = Ps[(nb - 1) * LDP + nb - 2];
+        red[(nb - 2) * C] = Ps[(nb - 2) * LDP + nb - 2];
+        red[(nb + nb - 2) * C] = Ps[(nb - 1) * LDP + nb - 2];
       }
-      red[nb - 1] = Ps[(nb - 1) * LDP + nb - 1];
-      red[nb + nb - 1] = 0.0;
-      red[6 * nb + 0] = Hc[0];
-      red[6 * nb + 1] = Hc[1];
-      red[6 * nb + 2] = Hc[2];
-      red[6 * nb + 3] = 0.0;
+      red[(nb - 1) * C] = Ps[(nb - 1) * LDP + nb - 1];
+      red[(nb + nb - 1) * C] = 0.0;
+      red[(6 * nb + 0) * C] = Hc[0];
+      red[(6 * nb + 1) * C] = Hc[1];
+      red[(6 * nb + 2) * C] = Hc[2];
+      red[(6 * nb + 3) * C] = 0.0;
     }
     __syncwarp();
   }
@@ -241,7 +241,7 @@ k_reduce(DiscDev d, BatchDev b) {
       a2 = fma(pj, __shfl_sync(0xffffffffu, m0, j), a2);
       a3 = fma(pj, __shfl_sync(0xffffffffu, m1, j), a3);
     }
-    if (act) { red[2 * nb + i] = a0; red[3 * nb + i] = a1; red[4 * nb + i] = a2; red[5 * nb + i] = a3; }
+    if (act) { red[(2 * nb + i) * C] = a0; red[(3 * nb + i) * C] = a1; red[(4 * nb + i) * C] = a2; red[(5 * nb + i) * C] = a3; }
   }
   // 7. P (row-major) and P^T
   double* Pm = b.Pm + (chan * C + c) * (size_t)nb * nb;
@@ -259,7 +259,7 @@ k_reduce(DiscDev d, BatchDev b) {
 struct RedVec { double* h; double* t; };
 
 struct EigShared {
-  double* red;      // [red_stride][C]  reduced cell data (field-major)
+  const double* __restrict__ red;   // [red_stride][C]  reduced cell data of the channel (global memory, L1-cached)
   double* mhh;      // [3][C]           M hat-hat blocks
   double* fac;      // [4 nb][C]        dinv[nb] | l[nb] | W0[nb] | W1[nb]
   RedVec x, r, y;   // iterate, r = M~ x, solve output
@@ -276,7 +276,7 @@ struct EigShared {
 };
 
 __host__ __device__ inline size_t eig_smem_bytes(int C, int nb, int Nh) {
-  size_t nd = (size_t)red_stride(nb) * C + 3 * C + (size_t)4 * nb * C + 3 * ((size_t)nb * C + C) +
+  size_t nd = 3 * C + (size_t)4 * nb * C + 3 * ((size_t)nb * C + C) +
               2 * C + 6 * 3 * C + 3 * C + AKS_NW + 8;
   return nd * sizeof(double) + (size_t)(6 * (C + 2) + 2 * C + 16) * sizeof(int);
 }
@@ -582,7 +582,6 @@ __device__ __forceinline__ double warp_colmatvec(const double* __restrict__ base
 __device__ inline void eig_carve(const DiscDev& d, double* sm, EigShared& S) {
   const int C = d.C, n = d.n, nb = d.nb;
   double* ptr = sm;
-  S.red = ptr; ptr += (size_t)red_stride(nb) * C;
   S.mhh = ptr; ptr += 3 * C;
   S.fac = ptr; ptr += (size_t)4 * nb * C;
   S.x.t = ptr; ptr += (size_t)nb * C; S.x.h = ptr; ptr += C;
@@ -627,7 +626,10 @@ enum { EST_BRACKET_LO = 0, EST_BRACKET_HI, EST_BISECT, EST_RQI, EST_CERT_LO, EST
 // every unsolved level lies above everything it examined, and otherwise raises redo[p], for which
 // mode 1 solves the remaining levels (cold) before the aufbau is repeated.  Mode 2 is the same fill
 // pass on request of the host (aks_get_state / end of a run: the reference returns all nh pairs).
-__global__ void __launch_bounds__(AKS_NT, 2)
+#ifndef EIG_NT
+#define EIG_NT 128   // threads per eigenpair CTA: the sweeps are thread-per-cell, occupancy (4 CTAs/SM) matters more
+#endif
+__global__ void __launch_bounds__(EIG_NT, (EIG_NT == 128) ? 4 : 2)
 k_eig(DiscDev d, BatchDev b, int mode) {
   const int k = blockIdx.x, ch = blockIdx.y, p = blockIdx.z;
   if (mode != 2 && b.status[p] != 0) return;
@@ -661,14 +663,7 @@ k_eig(DiscDev d, BatchDev b, int mode) {
   // eps / U of a level outside the last windows are older than one step: still a start, never trusted
   // (every result is certified by inertia counts)
   const bool have_prev = b.warm[p] != 0;
-  {  // reduced data of this channel, transposed to field-major
-    const int rs = red_stride(nb);
-    const double* rg = b.red + chan * C * rs;
-    for (int idx = threadIdx.x; idx < C * rs; idx += blockDim.x) {
-      const int c = idx / rs, f = idx - c * rs;
-      S.red[f * C + c] = rg[idx];
-    }
-  }
+  S.red = b.red + chan * C * red_stride(nb);
   __syncthreads();
 
   // bracket == witnesses: lo = largest shift known with count <= k (clo), hi = smallest with
@@ -888,7 +883,9 @@ k_eig(DiscDev d, BatchDev b, int mode) {
 //   x~_b = P (M_bb x_b)   (exact inverse of x_b = P^T x~_b because P M_bb P^T = I),  hats unchanged.
 // One CTA per (cell chunk, channel): the cell's M_bb and P are staged once in shared memory and
 // reused by all nh vectors (one warp per vector).
-#define EIGC_CHUNK 8
+#ifndef EIGC_CHUNK
+#define EIGC_CHUNK 4
+#endif
 __host__ __device__ inline size_t eig_chan_smem_bytes(int n, int nb) {
   return sizeof(double) * ((size_t)nb * nb + 4 * (size_t)n * n + 8);
 }

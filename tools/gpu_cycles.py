@@ -12,7 +12,7 @@ Zs = list(range(1, 87))
 disc = build_disc(0)
 models, lhs, nhs = periodic_table_models(Zs)
 os.environ["AKS_PHASE_TIMERS"] = "1"
-bt = Batch(models, disc, aks.ODA(scftol=0.0, tinit=0.6), lh=lhs, nh=nhs)
+bt = Batch(models, disc, aks.ODA(scftol=0.0, tinit=0.6), lh=lhs, nh=nhs, eig_margin=-1)
 for it in range(14):
     bt.step()
     if it in (0, 3, 8, 13):
