@@ -12,6 +12,7 @@ that every atom does every step (fixed work).  metric = atom-SCF-iterations per 
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -34,17 +35,21 @@ _RESULT_LINE = []   # the single JSON record, printed by main() on the real stdo
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  nvidia-smi needs
+    ~0.1 s to start, longer than a short timed region, so it is started before the warm-up and its rows are
+    filtered by their own timestamps to the window [mark_begin, mark_end]."""
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -55,25 +60,32 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark_begin(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        parsed = []
         for r in self.rows:
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for nm, v in zip(names, r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+                parsed.append((ts, float(r[1]), float(r[2]), [v.lower().startswith("active") for v in r[3:7]]))
             except Exception:
                 pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        pad = datetime.timedelta(milliseconds=15)   # sampling period: keep the samples that bracket the region
+        inside = [x for x in parsed if self.t0 and self.t1 and self.t0 - pad <= x[0] <= self.t1 + pad]
+        used = inside or parsed
+        sm = sorted(x[1] for x in used)
+        reasons = sorted({nm for x in used for nm, on in zip(names, x[3]) if on})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((x[2] for x in used), default=None),
+                "reasons": reasons, "samples": len(used), "samples_in_timed_region": len(inside)}
 
 
 def build_disc(device):
@@ -118,18 +130,20 @@ def b200_arm(args):
 
     # ---------------- device-resident throughput (`value`)
     bt = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         bt.step_async()
     launches0 = ctx.launches
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
         bt.step_async()
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     launches = ctx.launches - launches0
