@@ -15,7 +15,8 @@ def __getattr__(name):
     """Device-facing API (needs the built CUDA library; no CPU fallback)."""
     _dev = {"KSEModel": "model", "NoFunctional": "model", "BuiltinFunctional": "model", "Functional": "model",
             "RHF": "model", "Slater": "model", "LDA": "model", "ODA": "algorithms",
-            "OptimizedAufbau": "algorithms", "KSEDiscretization": "discretization",
+            "OptimizedAufbau": "algorithms", "SmearedAufbau": "algorithms", "FrozenAufbau": "algorithms",
+            "parse_shell": "algorithms", "KSEDiscretization": "discretization",
             "groundstate": "solver", "KSESolver": "solver", "KSESolution": "solver", "Batch": "solver",
             "CallbackSet": "solver", "LogFileCallback": "solver", "LogBook": "solver"}
     if name in _dev:

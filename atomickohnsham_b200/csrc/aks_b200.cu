@@ -409,7 +409,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk) ZB(double, Hfull, B * s * L * C * n * n)
   ZB(double, eps, B * s * L * nh) ZB(double, eps_new, B * s * L * nh) ZB(double, U, B * s * L * nh * Nh)
   ZB(int, eig_info, B * s * L * nh) ZB(long long, eig_dbg, B * s * L * nh * 8) ZB(double, red, B * s * L * C * (6 * (n - 2) + 4))
-  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * ((C + EIGC_CHUNK - 1) / EIGC_CHUNK) * 6) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, redo_cnt, B) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
+  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * ((C + EIGC_CHUNK - 1) / EIGC_CHUNK) * 6) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, redo_cnt, B) ZB(double, nfix, B * s * L * nh) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
   ZB(double, ecou_orb, B * s * L * nh) ZB(double, occ, B * 2 * s * L * nh) ZB(int, degen, B) ZB(int, occ_cnt, B * 2) ZB(int, occ_elk, B * 2 * AKS_MAXORB) ZB(double, occ_n, B * 2 * AKS_MAXORB)
   ZB(int, degen_idx, B * 2) ZB(double, degen_n, B * 4) ZB(double, rho_q_new, B * 2 * s * C * Q)
   ZB(double, rho_y_new, B * 2 * s * G) ZB(double, corr_part, B * 2 * C) ZB(double, Bloc_new, B * 2 * C * n)
@@ -422,6 +422,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   b.abstol_ls = b.reltol_ls = 1e4 * 2.220446049250313e-16;
   b.max_degen = 2; b.degen_tol = 1e-3; b.handle_spin = 1;
   b.eig_margin = 1;
+  b.aufbau_kind = 0; b.temp = 0.0;
   // launch configuration
   bt->smem_pot = potential_smem_bytes(dv.n, dv.Q, b.s);
   bt->smem_eig = eig_smem_bytes(dv.C, dv.nb, dv.Nh);
@@ -508,6 +509,32 @@ extern "C" int aks_batch_reset(aks_batch* bt) {
   bt->eig_dirty = false;
   CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
+}
+
+extern "C" int aks_batch_set_aufbau(aks_batch* bt, int32_t kind, double temp, const double* nfix) {
+  if (!bt) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  BatchDev& b = bt->dev;
+  if (kind < 0 || kind > 2 || (kind == 1 && !(temp > 0.0)) || (kind == 2 && !nfix)) {
+    ctx->err = "aks_batch_set_aufbau: kind in {0,1,2}, temp > 0 for 1 (SmearedAufbau), nfix for 2 (FrozenAufbau)";
+    return AKS_EINVAL;
+  }
+  int rc = ensure_complete(bt);
+  if (rc != AKS_OK) return rc;
+  if (kind == 2) {
+    // caller: per problem (L, nh[, 2]) column-major  ->  device [s][Lmax][nhmax]
+    const size_t s = b.s, L = b.Lmax, nh = b.nhmax, per = s * L * nh;
+    std::vector<double> h((size_t)bt->B * per, 0.0);
+    for (size_t p = 0; p < (size_t)bt->B; ++p)
+      for (size_t e = 0; e < s; ++e)
+        for (size_t l = 0; l < L; ++l)
+          for (size_t k = 0; k < nh; ++k) h[p * per + (e * L + l) * nh + k] = nfix[p * per + l + L * (k + nh * e)];
+    CK(cudaMemcpyAsync(b.nfix, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  b.aufbau_kind = kind;
+  b.temp = temp;
+  return window_full(bt, 0, bt->B);
 }
 
 extern "C" int aks_batch_set_eig_window(aks_batch* bt, int32_t margin) {

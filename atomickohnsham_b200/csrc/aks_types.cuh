@@ -50,6 +50,9 @@ struct BatchDev {
   // ODA / aufbau options
   double scftol, tinit, abstol_ls, reltol_ls, degen_tol;
   int frozen_t, maxiter_ls, max_degen, handle_spin;
+  int aufbau_kind;   // 0 OptimizedAufbau, 1 SmearedAufbau (temp), 2 FrozenAufbau (nfix)
+  double temp;       // smearing width in Hartree (aufbau/smeared.jl)
+  double* nfix;      // [B][s][Lmax][nhmax] prescribed occupations (aufbau/frozen.jl)
   // persistent state (mixed density, in every representation the path needs)
   double* Dd;     // [B][s][Nh][Nh]  dense density matrix (stopping norm, output)
   double* rho_q;  // [B][s][C][Q]    rho at the Gauss nodes of every cell

@@ -2,6 +2,8 @@
 // representation the path needs, radial Poisson solve, energies + ODA line search, mixing
 // and the stopping rule.  Reference functions replaced are cited per kernel.
 #pragma once
+#include <float.h>
+
 #include "aks_device.cuh"
 #include "aks_types.cuh"
 
@@ -60,7 +62,64 @@ __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b, int mode) 
   }
   __syncwarp();
   int degen = 0;
-  if (lane == 0) {
+  if (b.aufbau_kind != 0) {
+    // ---- SmearedAufbau (aufbau/smeared.jl:68-101): n_i = g_i / (1 + exp((eps_i - mu)/T)), mu by 100
+    // bisection steps on [min eps - 50 T, max eps + 50 T];  FrozenAufbau (aufbau/frozen.jl:84-88): n = nfix
+    if (b.aufbau_kind == 1) {
+      const double T = b.temp, Np = b.N[p];
+      double emin = DBL_MAX, emax = -DBL_MAX;
+      for (int f = lane; f < norb; f += 32) { emin = fmin(emin, ev[f]); emax = fmax(emax, ev[f]); }
+      emin = -warp_max(-emin); emax = warp_max(emax);
+      double lo = emin - 50.0 * T, hi = emax + 50.0 * T;
+      for (int itb = 0; itb < 100; ++itb) {
+        const double mid = (lo + hi) / 2.0;
+        double part = 0.0;
+        for (int f = lane; f < norb; f += 32) {
+          const int l = (f % (Lp * nhp)) % Lp;
+          const double g = (s == 1) ? (double)(4 * l + 2) : (double)(2 * l + 1);
+          part += g / (1.0 + exp((ev[f] - mid) / T));
+        }
+        const double occ = warp_sum(part);
+        if (occ < Np) lo = mid; else hi = mid;
+      }
+      const double mu = (lo + hi) / 2.0;
+      for (int f = lane; f < norb; f += 32) {
+        const int l = (f % (Lp * nhp)) % Lp;
+        const double g = (s == 1) ? (double)(4 * l + 2) : (double)(2 * l + 1);
+        occ_s[0][f] = g / (1.0 + exp((ev[f] - mu) / T));
+      }
+    } else {
+      for (int f = lane; f < norb; f += 32) {
+        const int e = f / (Lp * nhp), r = f - e * Lp * nhp, k = r / Lp, l = r - k * Lp;
+        occ_s[0][f] = b.nfix[orb_off(b, p, e, l, k)];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      b.redo[p] = 0;
+      b.degen[p] = 0;
+      int cnt = 0;
+      int* elk = b.occ_elk + ((size_t)p * 2) * AKS_MAXORB;
+      double* nn = b.occ_n + ((size_t)p * 2) * AKS_MAXORB;
+      for (int e = 0; e < s; ++e)
+        for (int k = 0; k < nhp; ++k)
+          for (int l = 0; l < Lp; ++l) {
+            const double v = occ_s[0][l + Lp * k + Lp * nhp * e];
+            if (v != 0.0) { elk[cnt] = (e << 16) | (l << 8) | k; nn[cnt] = v; ++cnt; }
+          }
+      b.occ_cnt[2 * p] = cnt;
+      b.occ_cnt[2 * p + 1] = 0;
+      // eigenpair window: smeared occupations need every level; frozen ones the prescribed levels
+      for (int e = 0; e < s; ++e)
+        for (int l = 0; l < Lp; ++l) {
+          int top = 0;
+          for (int k = 0; k < nhp; ++k)
+            if (occ_s[0][l + Lp * k + Lp * nhp * e] != 0.0) top = k + 1;
+          b.kact[((size_t)p * s + e) * b.Lmax + l] =
+              (b.aufbau_kind == 1 || b.eig_margin < 0) ? b.nhmax : max(1, top);
+        }
+    }
+  } else if (lane == 0) {
     for (int i = 1; i < norb; ++i) {  // stable insertion sort (sortperm!)
       const int oi = ord[i];
       const double vi = ev[oi];

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _capi
 from ._capi import AKS_ENOTCONV, AKS_MAXITERS, AKS_OK, AKS_RUNNING, AKS_SUCCESS, IterRecord
-from .algorithms import ODA
+from .algorithms import ODA, FrozenAufbau, OptimizedAufbau, SmearedAufbau
 from .discretization import KSEDiscretization
 from .model import KSEModel
 
@@ -108,9 +108,18 @@ class Batch:
         self.h = h
         self.nprob = nprob
         a = alg.aufbau
+        opt = a if isinstance(a, OptimizedAufbau) else OptimizedAufbau()
         self.ctx.check(_capi.lib.aks_batch_set_oda(h, alg.scftol, alg.tinit, int(alg.frozen_t), alg.maxiter_ls,
-                                                   alg.abstol_ls, alg.reltol_ls, a.max_degen, a.tol,
-                                                   int(a.handle_degen_spin_1iter)))
+                                                   alg.abstol_ls, alg.reltol_ls, opt.max_degen, opt.tol,
+                                                   int(opt.handle_degen_spin_1iter)))
+        if isinstance(a, SmearedAufbau):
+            self.ctx.check(_capi.lib.aks_batch_set_aufbau(h, 1, a.Temp, None))
+        elif isinstance(a, FrozenAufbau):
+            # one FrozenAufbauCache per problem, in the discretization's layout (column-major)
+            one = a.nfix(discretization.lh, discretization.nh, discretization.nspin)
+            self._nfix = np.ascontiguousarray(
+                np.concatenate([one.reshape(-1, order="F")] * nprob), dtype=np.float64)
+            self.ctx.check(_capi.lib.aks_batch_set_aufbau(h, 2, 0.0, _capi.dptr(self._nfix)))
         if eig_margin is not None:
             self.set_eig_window(eig_margin)
         self._rec = (IterRecord * nprob)()

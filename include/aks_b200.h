@@ -108,6 +108,11 @@ int aks_batch_set_oda(aks_batch* batch, double scftol, double tinit, int32_t fro
                       int32_t maxiter_ls, double abstol_ls, double reltol_ls,
                       int32_t max_degen, double degen_tol, int32_t handle_degen_spin_1iter);
 
+/* occupation scheme (src/algorithms/aufbau/): kind 0 = OptimizedAufbau (default, options of
+ * aks_batch_set_oda), 1 = SmearedAufbau(Temp = temp) (aufbau/smeared.jl:68-101), 2 = FrozenAufbau with the
+ * cache's nfix (aufbau/frozen.jl:36-88): nfix[nprob][(L, nh[, 2]) column-major], L = lh+1, nh of the disc  */
+int aks_batch_set_aufbau(aks_batch* batch, int32_t kind, double temp, const double* nfix);
+
 /* Eigenpair window (no reference counterpart; the results are the reference's).  The reference solves
  * all nh eigenpairs of every channel in every iteration (oda/loop.jl:65-77) although only the levels
  * the aufbau can reach matter for the iteration.  With margin >= 0 a step solves, per channel, the

@@ -72,10 +72,20 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, 
         (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
         dh[], nprob, Z, N, har, ex, ec, C_NULL, C_NULL, bh))
     a = alg.aufbau
+    opt = a isa OptimizedAufbau ? a : OptimizedAufbau()
     check(ctx[], ccall((:aks_batch_set_oda, LIB), Cint,
         (Ptr{Cvoid}, Float64, Float64, Int32, Int32, Float64, Float64, Int32, Float64, Int32),
         bh[], alg.scftol, alg.tinit, alg.frozen_t, alg.maxiter_ls, alg.abstol_ls, alg.reltol_ls,
-        a.max_degen, a.tol, a.handle_degen_spin_1iter))
+        opt.max_degen, opt.tol, opt.handle_degen_spin_1iter))
+    if a isa AtomicKohnSham.SmearedAufbau
+        check(ctx[], ccall((:aks_batch_set_aufbau, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}),
+            bh[], 1, Float64(a.Temp), C_NULL))
+    elseif a isa AtomicKohnSham.FrozenAufbau
+        # the FrozenAufbauCache holds nfix in the layout of n: (L, nh[, 2]); one copy per problem
+        nfix = reduce(vcat, [vec(Float64.(AtomicKohnSham.create_cache_aufbau(disc, m, a).nfix)) for m in models])
+        GC.@preserve nfix check(ctx[], ccall((:aks_batch_set_aufbau, LIB), Cint,
+            (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}), bh[], 2, 0.0, nfix))
+    end
     # solve!: one ccall per iteration so that register!/callback! fire as in groundstate.jl:55-57
     solvers = [KSESolver(m, disc, alg; maxiter = maxiter, callback = callback) for m in models]
     recs = Vector{IterRecord}(undef, nprob)

@@ -55,6 +55,11 @@ class ODAOptions:
     max_degen: int = 2
     degen_tol: float = 1e-3
     handle_degen_spin_1iter: bool = True
+    # occupation scheme: "optimized" (aufbau/optimized.jl), "smeared" (aufbau/smeared.jl, needs temp),
+    # "frozen" (aufbau/frozen.jl, needs nfix in the layout of n)
+    aufbau_kind: str = "optimized"
+    temp: float = 0.0
+    nfix: object = None
 
 
 @dataclass
@@ -304,6 +309,26 @@ class Oracle:
         """aufbau!(...::OptimizedAufbauCache, niter).  Returns (n, post) where post is
         None or (D1, Energies) when the two-fold branch ran (optimized.jl:228-306)."""
         opt = self.opt
+        if opt.aufbau_kind == "frozen":      # aufbau!(…, ::FrozenAufbauCache, …), frozen.jl:84-88
+            return np.array(opt.nfix, dtype=np.float64).reshape(eps.shape), None
+        if opt.aufbau_kind == "smeared":     # aufbau!(…, ::SmearedAufbauCache, …), smeared.jl:68-101
+            ef = eps.reshape(-1, order="F")
+            deg = np.array([self.degeneracy(i) for i in range(ef.size)], dtype=np.float64)
+            T = opt.temp
+            lo, hi = ef.min() - 50 * T, ef.max() + 50 * T
+            for _ in range(100):
+                mid = (lo + hi) / 2
+                occ = 0.0
+                for i in range(ef.size):
+                    occ += deg[i] / (1 + np.exp((ef[i] - mid) / T))
+                if occ < self.N:
+                    lo = mid
+                else:
+                    hi = mid
+            mu = (lo + hi) / 2
+            with np.errstate(over="ignore"):
+                nf = deg / (1 + np.exp((ef - mu) / T))
+            return nf.reshape(eps.shape, order="F"), None
         ef = eps.reshape(-1, order="F")
         order = np.argsort(ef, kind="stable")
         nf = np.zeros(ef.size)

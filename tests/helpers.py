@@ -68,7 +68,8 @@ def make_oracle(setup, *, tables="package", eig="generalized", **over):
         tb = ReferenceTables(mesh.points, s["p"], npoints)
     opt = ODAOptions(scftol=s.get("scftol", 1e-10), tinit=s.get("tinit", 0.6),
                      frozen_t=s.get("frozen_t", False), max_degen=s.get("max_degen", 2),
-                     degen_tol=s.get("degen_tol", 1e-3))
+                     degen_tol=s.get("degen_tol", 1e-3), aufbau_kind=s.get("aufbau_kind", "optimized"),
+                     temp=s.get("temp", 0.0), nfix=s.get("nfix"))
     nspin = s.get("nspin", 1)
     return Oracle(tb, Z=s["Z"], N=s["N"], hartree=s.get("hartree", 1), ex=s.get("ex"), ec=s.get("ec"),
                   nspin=nspin, lh=s["lh"], nh=s["nh"], options=opt, eig=eig)

@@ -196,6 +196,38 @@ def test_batch_is_deterministic_and_problem_independent():
     b2.close()
 
 
+@pytest.mark.parametrize("kind", ["smeared", "frozen"])
+def test_smeared_and_frozen_aufbau_parity(kind):
+    """SmearedAufbau / FrozenAufbau (aufbau/smeared.jl, aufbau/frozen.jl) through the C ABI against the
+    oracle: oxygen LDA, trajectories step by step (no degenerate branch, so the runs are deterministic)."""
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.solver import Batch
+    from gpu_diag import make_gpu
+    setup = dict(CASES["o_lda"])
+    if kind == "smeared":
+        setup.update(aufbau_kind="smeared", temp=0.05)
+        auf = aks.SmearedAufbau(Temp=0.05)
+    else:
+        auf = aks.FrozenAufbau({"1s": 2.0, "2s": 2.0, "2p": 3.0, "3s": 1.0})
+        setup.update(aufbau_kind="frozen", nfix=auf.nfix(setup["lh"], setup["nh"], 1))
+    o = make_oracle(setup)
+    model, disc, _ = make_gpu(setup)
+    bt = Batch([model], disc, aks.ODA(scftol=0.0, tinit=0.6, aufbau=auf))
+    st = o.initial_state()
+    for it in range(8):
+        o.scf_step(st)
+        rec = bt.step()[0]
+        eo = st.energies
+        assert abs(rec["Etot"] - eo.Etot) <= 1e-10 * abs(eo.Etot), (it, rec["Etot"], eo.Etot)
+        assert abs(rec["t"] - st.t) <= 1e-6
+    sg = bt.state(0, want_D=False, want_U=False)
+    assert np.allclose(sg["n"], st.n, atol=1e-8)
+    assert abs(sg["n"].sum() - 8.0) < 1e-8
+    occ = st.n > 1e-8
+    assert np.max(np.abs(sg["eps"][occ] - st.eps[occ])) < 5e-8
+    bt.close()
+
+
 def test_eigenpair_window_is_transparent():
     """aks_batch_set_eig_window: solving only the levels the aufbau can reach (certified on the device,
     refilled when the certificate fails) must give the iterations of the all-nh solve, and aks_get_state

@@ -146,3 +146,44 @@ def test_two_rank_gloo_partition_and_host_gather(tmp_path):
     outs = [p.communicate(timeout=120) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK 86" in outs[0][0]
+
+
+def test_frozen_and_smeared_aufbau_host_and_oracle():
+    """Behaviour pinned by the reference's own tests (test/algorithms.jl:43-175): shell parsing, the
+    FrozenAufbauCache layout and its spin-suffix errors, SmearedAufbau's constructor check, electron-count
+    conservation, bounds and monotonicity of the Fermi-Dirac occupations."""
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.algorithms import parse_shell
+    assert parse_shell("1s") == (1, 0) and parse_shell("3dUP") == (3, 2, 1) and parse_shell("2p↓") == (2, 1, 2)
+    with pytest.raises(ValueError):
+        parse_shell("1p")
+    af = aks.FrozenAufbau({"1s": 2.0, "2s": 1.5})
+    n = af.nfix(lh=1, nh=2, nspin=1)
+    assert n.shape == (2, 2) and n[0, 0] == 2.0 and n[0, 1] == 1.5 and n.sum() == 3.5
+    with pytest.raises(ValueError):
+        aks.FrozenAufbau({"1s": 1.0}).nfix(lh=0, nh=1, nspin=2)
+    with pytest.raises(ValueError):
+        aks.FrozenAufbau({"1sUP": 1.0}).nfix(lh=0, nh=1, nspin=1)
+    for bad in (0.0, -0.1):
+        with pytest.raises(ValueError):
+            aks.SmearedAufbau(Temp=bad)
+    # oracle: smeared occupations on the reference's test spectrum (lh = 1, nh = 2, N = 3)
+    from oracle.scf import ODAOptions, Oracle
+
+    class _O(Oracle):
+        def __init__(self, opt):
+            self.opt, self.N, self.nspin, self.L, self.nh = opt, 3.0, 1, 2, 2
+
+        def flat_index(self, idx):
+            return idx % 2, idx // 2, 0
+    eps = np.array([-2.0, -1.0, 0.0, 1.0]).reshape((2, 2), order="F")
+    cold, _ = _O(ODAOptions(aufbau_kind="smeared", temp=0.05)).aufbau(eps, None, 0)
+    hot, _ = _O(ODAOptions(aufbau_kind="smeared", temp=1.0)).aufbau(eps, None, 0)
+    deg = np.array([[2.0, 2.0], [6.0, 6.0]])
+    for n in (cold, hot):
+        assert abs(n.sum() - 3.0) < 1e-8 and np.all(n >= 0) and np.all(n <= deg)
+        frac = (n / deg).reshape(-1, order="F")[np.argsort(eps.reshape(-1, order="F"))]
+        assert np.all(np.diff(frac) <= 0)
+    assert hot[1, 1] > cold[1, 1]
+    fz, _ = _O(ODAOptions(aufbau_kind="frozen", nfix=n)).aufbau(eps + 100.0, None, 5)
+    assert np.array_equal(fz, n)
