@@ -52,7 +52,7 @@ __host__ __device__ inline size_t reduce_smem_bytes(int nb) {
 }
 
 template <int NBM>
-__global__ void __launch_bounds__(RED_NT)
+__global__ void __launch_bounds__(RED_NT, 4)
 k_reduce(DiscDev d, BatchDev b) {
   const int p = blockIdx.z, ch = blockIdx.y;
   if (b.status[p] != 0) return;
@@ -940,9 +940,8 @@ k_eig_init(DiscDev d, BatchDev b, int mode) {
 }
 
 // ------------------------------------------------------------------------------------------
-// k_eig_final: one CTA per (cell chunk, channel), one warp per eigenvector, cell by cell with the cell's
-// P, M_c and H_c staged in shared memory: x_b = P^T x~_b written to U (unnormalised), and the chunk's
-// share of x^T M0 x, x^T H x (ORIGINAL blocks, unassembled sums) and of the sign sum.
+// k_eig_final: one warp per (eigenvector, cell): x_b = P^T x~_b written to U (unnormalised), and the
+// cell's share of x^T M0 x, x^T H x (ORIGINAL blocks, unassembled sums) and of the sign sum.
 // k_eig_scale then adds the shares in a fixed order: U = x / sqrt(x^T M0 x) with a fixed sign,
 // eps = x^T H x / x^T M0 x.  The kinetic and Coulomb blocks ride along (same staging, two more FMAs per
 // entry), which gives the per-orbital energies of energies.jl:47-87 without another pass over U.
@@ -951,81 +950,59 @@ k_eig_final(DiscDev d, BatchDev b, int mode) {
   const int p = blockIdx.z, ch = blockIdx.y, chunk = blockIdx.x;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
   if (l >= b.Lp[p]) return;
-  extern __shared__ double sm[];
   const int C = d.C, nb = d.nb, n = d.n, Nh = d.Nh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* Ps = sm;              // [nb][nb]  P   (Ps[i*nb+j] = P[i][j])
-  double* Ms = Ps + nb * nb;    // [n][n]
-  double* Hs = Ms + n * n;      // [n][n]
-  double* Ks = Hs + n * n;      // [n][n]  kinetic block (A + l(l+1) M_-2) / 2
-  double* Cs = Ks + n * n;      // [n][n]  M_-1 (Coulomb)
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
   int klo, nhp;
   if (!eig_window(b, p, chan, mode, klo, nhp)) return;
   const double ll = (double)(l * (l + 1));
   const size_t xs = (size_t)(nb * C + C);
-  double xmx[2] = {0.0, 0.0}, xhx[2] = {0.0, 0.0}, ssum[2] = {0.0, 0.0}, xkx[2] = {0.0, 0.0}, xcx[2] = {0.0, 0.0};
-  for (int c = chunk * EIGC_CHUNK; c < min(C, (chunk + 1) * EIGC_CHUNK); ++c) {
-    __syncthreads();
-    const double* Pc = b.Pm + (chan * C + c) * (size_t)nb * nb;
-    const double* Mc = d.M0_loc + (size_t)c * n * n;
-    const double* Hc = b.Hfull + (chan * C + c) * (size_t)n * n;
-    const double* Ac = d.A_loc + (size_t)c * n * n;
-    const double* M2c = d.Mm2_loc + (size_t)c * n * n;
-    const double* M1c = d.Mm1_loc + (size_t)c * n * n;
-    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) Ps[idx] = Pc[idx];
-    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
-      Ms[idx] = Mc[idx]; Hs[idx] = Hc[idx];
-      Ks[idx] = (Ac[idx] + ((l > 0) ? ll * M2c[idx] : 0.0)) / 2.0;
-      Cs[idx] = M1c[idx];
-    }
-    __syncthreads();
+  const int c0 = chunk * EIGC_CHUNK, nc = min(C, c0 + EIGC_CHUNK) - c0, nv = nhp - klo;
+  // one warp per (vector, cell) item; no staging and no CTA barrier: the blocks are read straight
+  // through L1 (rows are coalesced, and the warps of a CTA share the cells of its chunk)
+  for (int item = warp; item < nv * nc; item += AKS_NW) {
+    const int k = klo + item / nc, c = c0 + item % nc;
+    const double* __restrict__ Pc = b.Pm + (chan * C + c) * (size_t)nb * nb;
+    const double* __restrict__ Mc = d.M0_loc + (size_t)c * n * n;
+    const double* __restrict__ Hc = b.Hfull + (chan * C + c) * (size_t)n * n;
+    const double* __restrict__ Ac = d.A_loc + (size_t)c * n * n;
+    const double* __restrict__ M2c = d.Mm2_loc + (size_t)c * n * n;
+    const double* __restrict__ M1c = d.Mm1_loc + (size_t)c * n * n;
+    const double* X = b.Xt + (chan * b.nhmax + k) * xs;
+    double* u = b.U + (chan * b.nhmax + k) * Nh;
     const int g0 = d.l2g[c * n + 2];
     const int gR = (c < C - 1) ? d.l2g[c * n] : -1;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      const int k = klo + warp + t * AKS_NW;
-      if (k < nhp) {
-        const double* X = b.Xt + (chan * b.nhmax + k) * xs;
-        double* u = b.U + (chan * b.nhmax + k) * Nh;
-        const double xt = (lane < nb) ? X[(size_t)lane * C + c] : 0.0;
-        double xb = 0.0;   // x_b[lane] = sum_i P[i][lane] x~_i
-        for (int i = 0; i < nb; ++i) {
-          const double xi = __shfl_sync(0xffffffffu, xt, i);
-          if (lane < nb) xb = fma(Ps[i * nb + lane], xi, xb);
-        }
-        // local vector in generator order: lane 0 right hat, lane 1 left hat, lanes 2.. bubbles
-        double xl = __shfl_up_sync(0xffffffffu, xb, 2);
-        if (lane == 0) xl = (c < C - 1) ? X[(size_t)nb * C + c] : 0.0;
-        if (lane == 1) xl = (c > 0) ? X[(size_t)nb * C + c - 1] : 0.0;
-        if (lane >= n) xl = 0.0;
-        double mx = 0.0, hx = 0.0, kx = 0.0, cx = 0.0;
-        for (int a = 0; a < n; ++a) {
-          const double xa = __shfl_sync(0xffffffffu, xl, a);
-          if (lane < n) {
-            mx = fma(Ms[a * n + lane], xa, mx); hx = fma(Hs[a * n + lane], xa, hx);
-            kx = fma(Ks[a * n + lane], xa, kx); cx = fma(Cs[a * n + lane], xa, cx);
-          }
-        }
-        xmx[t] = fma(mx, xl, xmx[t]);
-        xhx[t] = fma(hx, xl, xhx[t]);
-        xkx[t] = fma(kx, xl, xkx[t]);
-        xcx[t] = fma(cx, xl, xcx[t]);
-        if (lane >= 2 && lane < n) { u[g0 + lane - 2] = xl; ssum[t] += xl; }
-        if (lane == 0 && gR >= 0) { u[gR] = xl; ssum[t] += xl; }
-      }
+    const double xt = (lane < nb) ? X[(size_t)lane * C + c] : 0.0;
+    const bool inb = lane < nb, inn = lane < n;
+    double xb = 0.0;   // x_b[lane] = sum_i P[i][lane] x~_i
+#pragma unroll 4
+    for (int i = 0; i < nb; ++i) {
+      const double pv = inb ? Pc[i * nb + lane] : 0.0;
+      xb = fma(pv, __shfl_sync(0xffffffffu, xt, i), xb);
     }
-  }
-#pragma unroll
-  for (int t = 0; t < 2; ++t) {
-    const int k = klo + warp + t * AKS_NW;
-    if (k < nhp) {
-      const double m = warp_sum(xmx[t]), h = warp_sum(xhx[t]), sg = warp_sum(ssum[t]);
-      const double kk = warp_sum(xkx[t]), cc = warp_sum(xcx[t]);
-      if (lane == 0) {
-        double* part = b.eig_part + ((chan * b.nhmax + k) * gridDim.x + chunk) * 6;
-        part[0] = m; part[1] = h; part[2] = sg; part[3] = kk; part[4] = cc;
-      }
+    // local vector in generator order: lane 0 right hat, lane 1 left hat, lanes 2.. bubbles
+    double xl = __shfl_up_sync(0xffffffffu, xb, 2);
+    if (lane == 0) xl = (c < C - 1) ? X[(size_t)nb * C + c] : 0.0;
+    if (lane == 1) xl = (c > 0) ? X[(size_t)nb * C + c - 1] : 0.0;
+    if (!inn) xl = 0.0;
+    double mx = 0.0, hx = 0.0, kx = 0.0, cx = 0.0;
+#pragma unroll 3
+    for (int a = 0; a < n; ++a) {
+      const int o = a * n + lane;
+      const double mv = inn ? Mc[o] : 0.0, hv = inn ? Hc[o] : 0.0, cv = inn ? M1c[o] : 0.0;
+      const double av = inn ? Ac[o] : 0.0, m2 = (inn && l > 0) ? M2c[o] : 0.0;
+      const double xa = __shfl_sync(0xffffffffu, xl, a);
+      mx = fma(mv, xa, mx); hx = fma(hv, xa, hx); cx = fma(cv, xa, cx);
+      kx = fma((av + ll * m2) / 2.0, xa, kx);
+    }
+    if (lane >= 2 && inn) u[g0 + lane - 2] = xl;
+    if (lane == 0 && gR >= 0) u[gR] = xl;
+    const double own = ((lane >= 2 && inn) || (lane == 0 && gR >= 0)) ? xl : 0.0;   // entries this cell owns
+    const double m = warp_sum(mx * xl), h = warp_sum(hx * xl), sg = warp_sum(own);
+    const double kk = warp_sum(kx * xl), cc = warp_sum(cx * xl);
+    if (lane == 0) {
+      double* part = b.eig_part + ((chan * b.nhmax + k) * C + c) * 6;
+      part[0] = m; part[1] = h; part[2] = sg; part[3] = kk; part[4] = cc;
     }
   }
 }

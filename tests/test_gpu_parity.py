@@ -219,7 +219,7 @@ def test_smeared_and_frozen_aufbau_parity(kind):
         rec = bt.step()[0]
         eo = st.energies
         assert abs(rec["Etot"] - eo.Etot) <= 1e-10 * abs(eo.Etot), (it, rec["Etot"], eo.Etot)
-        assert abs(rec["t"] - st.t) <= 1e-6
+        assert abs(rec["t"] - st.t) <= 1e-5      # flat minimum of E(t): t is known to sqrt(eps)
     sg = bt.state(0, want_D=False, want_U=False)
     assert np.allclose(sg["n"], st.n, atol=1e-8)
     assert abs(sg["n"].sum() - 8.0) < 1e-8
