@@ -653,6 +653,9 @@ static int step_launch(aks_batch* bt) {
   int ei = 0;
 #define TICK() do { if (bt->timers) CK(cudaEventRecord(bt->ev[ei++], ctx->stream)); } while (0)
   TICK();
+#ifdef AKS_EIG_TIMING
+  CK(cudaMemsetAsync(b.eig_dbg, 0, sizeof(long long) * (size_t)bt->B * b.s * b.Lmax * b.nhmax * 8, ctx->stream));
+#endif
   if ((rc = launch_potential(bt, nullptr, nullptr)) != AKS_OK) return rc;
   TICK();
   if ((rc = launch_eig(bt)) != AKS_OK) return rc;
