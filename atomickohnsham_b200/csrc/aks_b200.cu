@@ -35,10 +35,27 @@ struct aks_disc {
   int nmax_tpl = 32;     // template NMAX for the density kernels
 };
 
+// A lane = a contiguous range of problems with its own stream.  Problems are independent, so the lanes of a
+// batch run the step sequence concurrently: small-grid and latency-bound kernels of one lane (line search,
+// aufbau, refill pass, kernel tails) overlap with the wide kernels of the other.
+struct Lane {
+  BatchDev dev{};   // view of the batch: every per-problem pointer advanced to the lane's first problem
+  int B = 0, p0 = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+};
+struct FieldInfo { size_t offset, bytes_per_problem; };
+
 struct aks_batch {
   aks_disc* disc = nullptr;
   BatchDev dev{};
   std::vector<void*> allocs;
+  std::vector<FieldInfo> fields;   // per-problem device arrays of BatchDev (for the lane views)
+  std::vector<Lane> lanes;         // >= 2 entries when the step is split over streams
+  Lane whole;                      // all problems on the ctx stream
+  Lane* cur = nullptr;             // what the launch helpers act on
+  cudaEvent_t fork_ev = nullptr;
+  bool forked = false;             // lanes are ahead of the ctx stream only by their own steps
   int B = 0;
   bool fac_in_smem = true;
   double* fac_global = nullptr;
@@ -48,7 +65,7 @@ struct aks_batch {
   aks_iter_record* h_rec = nullptr;  // pinned
   bool timers = false;
   bool eig_dirty = false;   // levels outside the eigenpair window are stale (k_eig)
-  cudaEvent_t ev[9];
+  cudaEvent_t ev[11];   // 8 phase boundaries + [9],[10] around k_mix_dense
   double phase_ms[8] = {0};
 };
 
@@ -364,6 +381,9 @@ extern "C" void aks_disc_destroy(aks_disc* disc) {
 extern "C" int aks_batch_reset(aks_batch* bt);
 static int window_full(aks_batch* bt, int p0, int np);
 static int ensure_complete(aks_batch* bt);
+static void refresh_lanes(aks_batch* bt);
+static void main_side(aks_batch* bt);
+static void enter_main(aks_batch* bt) { refresh_lanes(bt); main_side(bt); }
 
 extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const double* N,
                                 const double* hartree, const int32_t* ex_id, const int32_t* ec_id,
@@ -399,11 +419,13 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
     }
   }
   int rc;
-#define UPB(vec, field) if ((rc = dev_upload(ctx, bt->allocs, vec, &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
+#define UPB(vec, field) if ((rc = dev_upload(ctx, bt->allocs, vec, &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; } \
+  bt->fields.push_back({offsetof(BatchDev, field), sizeof(*b.field)});
   UPB(bt->hZ, Z) UPB(bt->hN, N) UPB(bt->hHar, hartree) UPB(ex, ex) UPB(ec, ec) UPB(bt->hLp, Lp) UPB(bt->hnhp, nhp)
 #undef UPB
   const size_t B = nprob, s = b.s, Nh = dv.Nh, C = dv.C, Q = dv.Q, G = dv.G, L = b.Lmax, nh = b.nhmax, n = dv.n;
-#define ZB(T, field, count) if ((rc = dev_zeros<T>(ctx, bt->allocs, (count), &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
+#define ZB(T, field, count) if ((rc = dev_zeros<T>(ctx, bt->allocs, (count), &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; } \
+  bt->fields.push_back({offsetof(BatchDev, field), sizeof(T) * ((size_t)(count) / B)});
   ZB(double, Dd, B * s * Nh * Nh) ZB(double, rho_q, B * s * C * Q) ZB(double, rho_y, B * s * G)
   ZB(double, Bv, B * Nh) ZB(double, Wv, B * Nh) ZB(double, E, B * 5) ZB(double, t, B) ZB(double, stop, B)
   ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk) ZB(double, Hfull, B * s * L * C * n * n)
@@ -453,12 +475,41 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   const char* tenv = getenv("AKS_PHASE_TIMERS");
   bt->timers = tenv && tenv[0] == '1';
   if (bt->timers) for (auto& e : bt->ev) CK(cudaEventCreate(&e));
+  // stream lanes (AKS_STREAM_LANES, default 4: measured 2.05 / 1.87 / 1.71 / 1.63 ms per 86-atom step with
+  // 1 / 2 / 4 / 8 lanes; more lanes cost host launch time in the synchronous path); small batches use fewer
+  {
+    const char* lenv = getenv("AKS_STREAM_LANES");
+    int nl = lenv ? atoi(lenv) : 4;
+    if (nl < 1) nl = 1;
+    if (nl > 8) nl = 8;
+    if (bt->B < 8 * nl) nl = bt->B >= 16 ? 2 : 1;
+    const int NP = potential_np(dv.n, b.s);
+    CK(cudaEventCreateWithFlags(&bt->fork_ev, cudaEventDisableTiming));
+    if (nl > 1) {
+      int prev = 0;
+      for (int k = 0; k < nl; ++k) {
+        int end = (k == nl - 1) ? bt->B : (int)(((long long)bt->B * (k + 1) / nl) / NP * NP);
+        if (end <= prev) continue;
+        Lane ln;
+        ln.p0 = prev; ln.B = end - prev;
+        CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        bt->lanes.push_back(ln);
+        prev = end;
+      }
+    }
+  }
   *out = bt;
   return aks_batch_reset(bt);
 }
 
 extern "C" void aks_batch_destroy(aks_batch* bt) {
   if (!bt) return;
+  for (Lane& ln : bt->lanes) {
+    if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
+    if (ln.done) cudaEventDestroy(ln.done);
+  }
+  if (bt->fork_ev) cudaEventDestroy(bt->fork_ev);
   cudaStream_t st = bt->disc->ctx->stream;
   for (void* p : bt->allocs) cudaFreeAsync(p, st);
   cudaStreamSynchronize(st);
@@ -471,6 +522,7 @@ extern "C" int aks_batch_set_oda(aks_batch* bt, double scftol, double tinit, int
                                  int32_t maxiter_ls, double abstol_ls, double reltol_ls, int32_t max_degen,
                                  double degen_tol, int32_t handle_degen_spin_1iter) {
   if (!bt) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   if (!(scftol >= 0) || !(tinit >= 0 && tinit <= 1) || maxiter_ls < 1 || max_degen < 1 || !(degen_tol >= 0)) {
     ctx->err = "aks_batch_set_oda: bad option"; return AKS_EINVAL;
@@ -487,6 +539,7 @@ extern "C" int aks_batch_set_oda(aks_batch* bt, double scftol, double tinit, int
 
 extern "C" int aks_batch_reset(aks_batch* bt) {
   if (!bt) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   BatchDev& b = bt->dev;
   const DiscDev& dv = bt->disc->dev;
@@ -513,6 +566,7 @@ extern "C" int aks_batch_reset(aks_batch* bt) {
 
 extern "C" int aks_batch_set_aufbau(aks_batch* bt, int32_t kind, double temp, const double* nfix) {
   if (!bt) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   BatchDev& b = bt->dev;
   if (kind < 0 || kind > 2 || (kind == 1 && !(temp > 0.0)) || (kind == 2 && !nfix)) {
@@ -539,6 +593,7 @@ extern "C" int aks_batch_set_aufbau(aks_batch* bt, int32_t kind, double temp, co
 
 extern "C" int aks_batch_set_eig_window(aks_batch* bt, int32_t margin) {
   if (!bt) return AKS_EINVAL;
+  enter_main(bt);
   int rc = ensure_complete(bt);
   if (rc != AKS_OK) return rc;
   bt->dev.eig_margin = margin;
@@ -562,45 +617,45 @@ extern "C" int aks_batch_set_eig_window(aks_batch* bt, int32_t margin) {
 static int launch_potential_range(aks_batch* bt, double* vxc_out, double* har_out, int p0, int np, int force) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
-  const int NP = potential_np(dv.n, bt->dev.s);
+  const int NP = potential_np(dv.n, bt->cur->dev.s);
   const dim3 grid(dv.C, (np + NP - 1) / NP);
   if (potential_nts(dv.n) == 1)
-    k_potential<1, 4><<<grid, AKS_NT, bt->smem_pot, ctx->stream>>>(dv, bt->dev, vxc_out, har_out, p0, np, force);
+    k_potential<1, 4><<<grid, AKS_NT, bt->smem_pot, bt->cur->stream>>>(dv, bt->cur->dev, vxc_out, har_out, p0, np, force);
   else
-    k_potential<2, 2><<<grid, AKS_NT, bt->smem_pot, ctx->stream>>>(dv, bt->dev, vxc_out, har_out, p0, np, force);
+    k_potential<2, 2><<<grid, AKS_NT, bt->smem_pot, bt->cur->stream>>>(dv, bt->cur->dev, vxc_out, har_out, p0, np, force);
   LAUNCH_CHECK();
   return AKS_OK;
 }
 static int launch_potential(aks_batch* bt, double* vxc_out, double* har_out) {
-  return launch_potential_range(bt, vxc_out, har_out, 0, bt->B, 0);
+  return launch_potential_range(bt, vxc_out, har_out, 0, bt->cur->B, 0);
 }
 // one pass of the eigensolver over the levels its mode selects (k_eig: 0 window, 1 refill, 2 completion)
 static int launch_eig_pass(aks_batch* bt, int mode) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
-  const BatchDev& b = bt->dev;
-  k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->B), AKS_NT, bt->smem_chan, ctx->stream>>>(dv, b, mode);
+  const BatchDev& b = bt->cur->dev;
+  k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->cur->B), AKS_NT, bt->smem_chan, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
-  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->B), EIG_NT, bt->smem_eig, ctx->stream>>>(dv, b, mode);
+  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->cur->B), EIG_NT, bt->smem_eig, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
   const int nchunk = (dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK;
-  k_eig_final<<<dim3(nchunk, b.Lmax * b.s, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b, mode);
+  k_eig_final<<<dim3(nchunk, b.Lmax * b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
-  k_eig_scale<<<dim3(b.Lmax * b.s, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b, dv.C, mode);
+  k_eig_scale<<<dim3(b.Lmax * b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b, dv.C, mode);
   LAUNCH_CHECK();
   return AKS_OK;
 }
 static int launch_eig(aks_batch* bt) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
-  const BatchDev& b = bt->dev;
+  const BatchDev& b = bt->cur->dev;
   {
-    const dim3 grid((dv.C + RED_NW - 1) / RED_NW, b.Lmax * b.s, bt->B);
+    const dim3 grid((dv.C + RED_NW - 1) / RED_NW, b.Lmax * b.s, bt->cur->B);
     switch (reduce_nbm(dv.nb)) {
-      case 8: k_reduce<8><<<grid, RED_NT, bt->smem_red, ctx->stream>>>(dv, b); break;
-      case 12: k_reduce<12><<<grid, RED_NT, bt->smem_red, ctx->stream>>>(dv, b); break;
-      case 20: k_reduce<20><<<grid, RED_NT, bt->smem_red, ctx->stream>>>(dv, b); break;
-      default: k_reduce<28><<<grid, RED_NT, bt->smem_red, ctx->stream>>>(dv, b); break;
+      case 8: k_reduce<8><<<grid, RED_NT, bt->smem_red, bt->cur->stream>>>(dv, b); break;
+      case 12: k_reduce<12><<<grid, RED_NT, bt->smem_red, bt->cur->stream>>>(dv, b); break;
+      case 20: k_reduce<20><<<grid, RED_NT, bt->smem_red, bt->cur->stream>>>(dv, b); break;
+      default: k_reduce<28><<<grid, RED_NT, bt->smem_red, bt->cur->stream>>>(dv, b); break;
     }
   }
   LAUNCH_CHECK();
@@ -610,90 +665,137 @@ static int launch_eig(aks_batch* bt) {
 static int ensure_complete(aks_batch* bt) {
   if (!bt->eig_dirty) return AKS_OK;
   aks_ctx* ctx = bt->disc->ctx;
-  k_set_redo<<<(bt->B + 127) / 128, 128, 0, ctx->stream>>>(bt->dev, 1);
+  k_set_redo<<<(bt->cur->B + 127) / 128, 128, 0, bt->cur->stream>>>(bt->cur->dev, 1);
   LAUNCH_CHECK();
   int rc = launch_eig_pass(bt, 2);
   if (rc != AKS_OK) return rc;
-  k_set_redo<<<(bt->B + 127) / 128, 128, 0, ctx->stream>>>(bt->dev, 0);
+  k_set_redo<<<(bt->cur->B + 127) / 128, 128, 0, bt->cur->stream>>>(bt->cur->dev, 0);
   LAUNCH_CHECK();
   bt->eig_dirty = false;
   return AKS_OK;
 }
 static int window_full(aks_batch* bt, int p0, int np) {
   aks_ctx* ctx = bt->disc->ctx;
-  k_window_full<<<(np * bt->dev.s * bt->dev.Lmax + 127) / 128, 128, 0, ctx->stream>>>(bt->dev, p0, np);
+  k_window_full<<<(np * bt->cur->dev.s * bt->cur->dev.Lmax + 127) / 128, 128, 0, bt->cur->stream>>>(bt->cur->dev, p0, np);
   LAUNCH_CHECK();
   return AKS_OK;
 }
 static int launch_dens_cells(aks_batch* bt) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
-  const dim3 grid(dv.C, bt->B, 2);
+  const dim3 grid(dv.C, bt->cur->B, 2);
   switch (bt->disc->nmax_tpl) {
-    case 12: k_dens_cells<12><<<grid, AKS_NT, bt->smem_dens, ctx->stream>>>(dv, bt->dev); break;
-    case 24: k_dens_cells<24><<<grid, AKS_NT, bt->smem_dens, ctx->stream>>>(dv, bt->dev); break;
-    default: k_dens_cells<32><<<grid, AKS_NT, bt->smem_dens, ctx->stream>>>(dv, bt->dev); break;
+    case 12: k_dens_cells<12><<<grid, AKS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
+    case 24: k_dens_cells<24><<<grid, AKS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
+    default: k_dens_cells<32><<<grid, AKS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
   }
   LAUNCH_CHECK();
-  const dim3 g2((dv.G + AKS_NT - 1) / AKS_NT, bt->B, 2);
+  const dim3 g2((dv.G + AKS_NT - 1) / AKS_NT, bt->cur->B, 2);
   switch (bt->disc->nmax_tpl) {
-    case 12: k_dens_grid<12><<<g2, AKS_NT, 0, ctx->stream>>>(dv, bt->dev); break;
-    case 24: k_dens_grid<24><<<g2, AKS_NT, 0, ctx->stream>>>(dv, bt->dev); break;
-    default: k_dens_grid<32><<<g2, AKS_NT, 0, ctx->stream>>>(dv, bt->dev); break;
+    case 12: k_dens_grid<12><<<g2, AKS_NT, 0, bt->cur->stream>>>(dv, bt->cur->dev); break;
+    case 24: k_dens_grid<24><<<g2, AKS_NT, 0, bt->cur->stream>>>(dv, bt->cur->dev); break;
+    default: k_dens_grid<32><<<g2, AKS_NT, 0, bt->cur->stream>>>(dv, bt->cur->dev); break;
   }
   LAUNCH_CHECK();
   return AKS_OK;
 }
 
-static int step_launch(aks_batch* bt) {
+// the kernel sequence of one SCF step for the problems of bt->cur, on its stream
+static int step_on_lane(aks_batch* bt) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
-  const BatchDev& b = bt->dev;
+  const BatchDev& b = bt->cur->dev;
   int rc;
   int ei = 0;
-#define TICK() do { if (bt->timers) CK(cudaEventRecord(bt->ev[ei++], ctx->stream)); } while (0)
+#define TICK() do { if (bt->timers && bt->cur == &bt->whole) CK(cudaEventRecord(bt->ev[ei++], bt->cur->stream)); } while (0)
   TICK();
 #ifdef AKS_EIG_TIMING
-  CK(cudaMemsetAsync(b.eig_dbg, 0, sizeof(long long) * (size_t)bt->B * b.s * b.Lmax * b.nhmax * 8, ctx->stream));
+  CK(cudaMemsetAsync(b.eig_dbg, 0, sizeof(long long) * (size_t)bt->cur->B * b.s * b.Lmax * b.nhmax * 8, bt->cur->stream));
 #endif
   if ((rc = launch_potential(bt, nullptr, nullptr)) != AKS_OK) return rc;
   TICK();
   if ((rc = launch_eig(bt)) != AKS_OK) return rc;
   TICK();
-  k_aufbau<<<bt->B, 32, 0, ctx->stream>>>(dv, b, 0);
+  k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 0);
   LAUNCH_CHECK();
   if (b.eig_margin >= 0) {   // problems whose window could not be certified: solve the rest, repeat
     if ((rc = launch_eig_pass(bt, 1)) != AKS_OK) return rc;
-    k_aufbau<<<bt->B, 32, 0, ctx->stream>>>(dv, b, 1);
+    k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 1);
     LAUNCH_CHECK();
     bt->eig_dirty = true;
   }
   TICK();
   if ((rc = launch_dens_cells(bt)) != AKS_OK) return rc;
   TICK();
-  k_poisson<<<dim3(bt->B, 2), 128, bt->smem_poisson, ctx->stream>>>(dv, b, 0, 0);
+  k_poisson<<<dim3(bt->cur->B, 2), 128, bt->smem_poisson, bt->cur->stream>>>(dv, b, 0, 0);
   LAUNCH_CHECK();
   TICK();
-  k_linesearch<<<bt->B, LS_NT, 0, ctx->stream>>>(dv, b);
+  k_linesearch<<<bt->cur->B, LS_NT, 0, bt->cur->stream>>>(dv, b);
   LAUNCH_CHECK();
   TICK();
   {
     const size_t total = (size_t)b.s * dv.C * dv.Q + (size_t)b.s * dv.G + 2 * (size_t)dv.Nh;
     const int gx = (int)std::min<size_t>((total + 255) / 256, 1024);
-    k_mix_state<<<dim3(gx, bt->B), 256, 0, ctx->stream>>>(dv, b);
+    k_mix_state<<<dim3(gx, bt->cur->B), 256, 0, bt->cur->stream>>>(dv, b);
     LAUNCH_CHECK();
   }
-  k_mix_dense<<<dim3(b.ntri, b.s, bt->B), AKS_NT, 0, ctx->stream>>>(dv, b);
+  if (bt->timers && bt->cur == &bt->whole) CK(cudaEventRecord(bt->ev[9], bt->cur->stream));
+  k_mix_dense<<<dim3(b.ntri, b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b);
   LAUNCH_CHECK();
-  k_finalize<<<(bt->B + 127) / 128, 128, 0, ctx->stream>>>(dv, b);
+  if (bt->timers && bt->cur == &bt->whole) CK(cudaEventRecord(bt->ev[10], bt->cur->stream));
+  k_finalize<<<(bt->cur->B + 127) / 128, 128, 0, bt->cur->stream>>>(dv, b);
   LAUNCH_CHECK();
   TICK();
 #undef TICK
   return AKS_OK;
 }
 
+// lane views of the batch: options and pointers are taken from bt->dev at every step (they are cheap)
+static void refresh_lanes(aks_batch* bt) {
+  bt->whole.dev = bt->dev;
+  bt->whole.B = bt->B;
+  bt->whole.p0 = 0;
+  bt->whole.stream = bt->disc->ctx->stream;
+  for (Lane& ln : bt->lanes) {
+    ln.dev = bt->dev;
+    ln.dev.B = ln.B;
+    for (const FieldInfo& f : bt->fields) {
+      char** ptr = reinterpret_cast<char**>(reinterpret_cast<char*>(&ln.dev) + f.offset);
+      *ptr += (size_t)ln.p0 * f.bytes_per_problem;
+    }
+  }
+}
+// anything enqueued on the ctx stream from now on is ordered after the lanes' work (every step ends with
+// the ctx stream waiting for the lanes); the next step must make the lanes wait for the ctx stream again
+static void main_side(aks_batch* bt) { bt->forked = false; bt->cur = &bt->whole; }
+
+static int step_launch(aks_batch* bt) {
+  aks_ctx* ctx = bt->disc->ctx;
+  refresh_lanes(bt);
+  if (bt->lanes.size() < 2 || bt->timers) {
+    bt->cur = &bt->whole;
+    bt->forked = false;
+    return step_on_lane(bt);
+  }
+  if (!bt->forked) {
+    CK(cudaEventRecord(bt->fork_ev, ctx->stream));
+    for (Lane& ln : bt->lanes) CK(cudaStreamWaitEvent(ln.stream, bt->fork_ev, 0));
+    bt->forked = true;
+  }
+  int rc = AKS_OK;
+  for (Lane& ln : bt->lanes) {
+    bt->cur = &ln;
+    if ((rc = step_on_lane(bt)) != AKS_OK) break;
+    CK(cudaEventRecord(ln.done, ln.stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ln.done, 0));
+  }
+  bt->cur = &bt->whole;
+  return rc;
+}
+
 static int fetch_records(aks_batch* bt, aks_iter_record* out) {
   aks_ctx* ctx = bt->disc->ctx;
+  main_side(bt);
   CK(cudaMemcpyAsync(bt->h_rec, bt->dev.rec, sizeof(aks_iter_record) * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (bt->timers) {
@@ -702,6 +804,9 @@ static int fetch_records(aks_batch* bt, aks_iter_record* out) {
       cudaEventElapsedTime(&ms, bt->ev[i], bt->ev[i + 1]);
       bt->phase_ms[i] = ms;
     }
+    float msd = 0;
+    cudaEventElapsedTime(&msd, bt->ev[9], bt->ev[10]);
+    bt->phase_ms[7] = msd;   // k_mix_dense alone (part of phase 6)
   }
   if (out) memcpy(out, bt->h_rec, sizeof(aks_iter_record) * bt->B);
   return AKS_OK;
@@ -717,6 +822,7 @@ extern "C" int aks_scf_step(aks_batch* bt, aks_iter_record* out) {
 
 extern "C" int aks_scf_run(aks_batch* bt, int32_t maxiter, aks_iter_record* history, aks_iter_record* final_records) {
   if (!bt || maxiter < 1) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   std::vector<aks_iter_record> last(bt->B);
   // records persist on the device between steps; start from the current ones
@@ -764,6 +870,7 @@ extern "C" int aks_last_phase_ms(aks_batch* bt, double out[8]) {
 // ------------------------------------------------------------------------------------ state I/O
 extern "C" int aks_get_state(aks_batch* bt, int32_t prob, double* D, double* U, double* eps, double* nocc, double* W) {
   if (!bt || prob < 0 || prob >= bt->B) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   const BatchDev& b = bt->dev;
@@ -809,6 +916,7 @@ static int launch_state_from_dense(aks_batch* bt, int prob) {
 
 extern "C" int aks_set_density(aks_batch* bt, int32_t prob, const double* D, const double* eprev, int32_t niter) {
   if (!bt || prob < 0 || prob >= bt->B || !D || niter < 0) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   BatchDev& b = bt->dev;
@@ -880,15 +988,18 @@ static int potential_hook(aks_batch* bt, int prob, double* vxc, double* har) {
 
 extern "C" int aks_assemble_hartree(aks_batch* bt, int32_t prob, double* Har) {
   if (!bt || prob < 0 || prob >= bt->B || !Har) return AKS_EINVAL;
+  enter_main(bt);
   return potential_hook(bt, prob, nullptr, Har);
 }
 extern "C" int aks_assemble_vxc(aks_batch* bt, int32_t prob, double* Vxc) {
   if (!bt || prob < 0 || prob >= bt->B || !Vxc) return AKS_EINVAL;
+  enter_main(bt);
   return potential_hook(bt, prob, Vxc, nullptr);
 }
 
 extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* U, double* residuals) {
   if (!bt || prob < 0 || prob >= bt->B) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   const BatchDev& b = bt->dev;
@@ -923,6 +1034,7 @@ extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* 
 
 extern "C" int aks_exc_energy(aks_batch* bt, int32_t prob, double* Exc) {
   if (!bt || prob < 0 || prob >= bt->B || !Exc) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   double* dout = nullptr;
   CK(cudaMalloc((void**)&dout, sizeof(double)));
@@ -936,6 +1048,7 @@ extern "C" int aks_exc_energy(aks_batch* bt, int32_t prob, double* Exc) {
 
 extern "C" int aks_hartree_energy(aks_batch* bt, int32_t prob, double* Ehar) {
   if (!bt || prob < 0 || prob >= bt->B || !Ehar) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   if (bt->hHar[prob] == 0.0) { *Ehar = 0.0; return AKS_OK; }
@@ -951,6 +1064,7 @@ extern "C" int aks_hartree_energy(aks_batch* bt, int32_t prob, double* Ehar) {
 
 extern "C" int aks_debug_eig_cycles(aks_batch* bt, int64_t* out) {
   if (!bt || !out) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const BatchDev& b = bt->dev;
   const size_t cnt = (size_t)bt->B * b.s * b.Lmax * b.nhmax * 8;
@@ -961,6 +1075,7 @@ extern "C" int aks_debug_eig_cycles(aks_batch* bt, int64_t* out) {
 
 extern "C" int aks_debug_eig_refills(aks_batch* bt, int32_t* counts) {
   if (!bt || !counts) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   CK(cudaMemcpyAsync(counts, bt->dev.redo_cnt, sizeof(int) * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -969,6 +1084,7 @@ extern "C" int aks_debug_eig_refills(aks_batch* bt, int32_t* counts) {
 
 extern "C" int aks_debug_eig_info(aks_batch* bt, int32_t* info) {
   if (!bt || !info) return AKS_EINVAL;
+  enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const BatchDev& b = bt->dev;
   const size_t cnt = (size_t)bt->B * b.s * b.Lmax * b.nhmax;
