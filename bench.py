@@ -199,13 +199,23 @@ def b200_arm(args):
             "mix+stop": {"bound": "hbm", "achieved": mix_bytes / (mixd / nrep * 1e-3) / 1e9, "kernel_ms": mixd / nrep,
                          "peak": hbm_peak, "unit": "GB/s"},
         }
-        for v in roof_all.values():
+        # DRAM bytes per launch of the same kernels from the committed ncu --set full capture (same workload)
+        traffic = {}
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            traffic = {"potential": tj["k_potential<1, 4>"]["dram_bytes_per_launch"] * (B / 86.0),
+                       "mix+stop": tj["k_mix_dense"]["dram_bytes_per_launch"] * (B / 86.0)}
+        except Exception:
+            pass
+        for k, v in roof_all.items():
             v["frac"] = v["achieved"] / v["peak"]
-            v["traffic"] = None
+            v["traffic"] = traffic.get(k)
         roof = dict(roof_all["potential"])
         roof["kernel"] = "k_potential"
         roof["peak_source"] = "aks_measure_fp64_peak (DFMA chains, same run); MEASURED_PEAKS.json has no FP64 figure"
         roof["dominant_phase"] = dom
+        roof["algorithmic_per_launch"] = pot_flops
+        roof["traffic_source"] = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch)"
         roof["other"] = {"k_mix_dense": roof_all["mix+stop"],
                          "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
 
