@@ -685,9 +685,9 @@ static int launch_dens_cells(aks_batch* bt) {
   const DiscDev& dv = bt->disc->dev;
   const dim3 grid(dv.C, bt->cur->B, 2);
   switch (bt->disc->nmax_tpl) {
-    case 12: k_dens_cells<12><<<grid, AKS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
-    case 24: k_dens_cells<24><<<grid, AKS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
-    default: k_dens_cells<32><<<grid, AKS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
+    case 12: k_dens_cells<12><<<grid, DENS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
+    case 24: k_dens_cells<24><<<grid, DENS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
+    default: k_dens_cells<32><<<grid, DENS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
   }
   LAUNCH_CHECK();
   const dim3 g2((dv.G + AKS_NT - 1) / AKS_NT, bt->cur->B, 2);

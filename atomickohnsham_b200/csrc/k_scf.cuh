@@ -264,8 +264,9 @@ __device__ inline void build_occ_list(const BatchDev& b, int p, int slot, OccLis
 // (what optimized_eval_density!, assemble.jl:91-125, yields for D = sum n u u^T), the energy
 // correction <Vxc[D_prev], D_new> (energies.jl:15-24) as sum_q fxc(q) q_new(q), and the cell's
 // share of the Hartree rhs B = F:D (tensor_matrix_dict!, src/utils/free allocation.jl:17-36).
+#define DENS_NT 128
 template <int NMAX>
-__global__ void __launch_bounds__(AKS_NT) k_dens_cells(DiscDev d, BatchDev b) {
+__global__ void __launch_bounds__(DENS_NT, 3) k_dens_cells(DiscDev d, BatchDev b) {
   const int c = blockIdx.x, p = blockIdx.y, slot = blockIdx.z;
   if (b.status[p] != 0) return;
   if (slot == 1 && !b.degen[p]) return;
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(AKS_NT) k_dens_cells(DiscDev d, BatchDev b) {
   double* red = Dl + n * n;                     // [NW]
   build_occ_list(b, p, slot, &L);
   const int cnt = L.count;
-  for (int idx = threadIdx.x; idx < cnt * NMAX; idx += AKS_NT) {
+  for (int idx = threadIdx.x; idx < cnt * NMAX; idx += DENS_NT) {
     const int o = idx / NMAX, i = idx - o * NMAX;
     double v = 0.0;
     if (i < n) {
@@ -291,39 +292,54 @@ __global__ void __launch_bounds__(AKS_NT) k_dens_cells(DiscDev d, BatchDev b) {
   const double inv1 = d.inv1[c], inv2 = d.inv2[c];
   const bool has_xc = (b.ex[p] != 0) || (b.ec[p] != 0);
   double corr = 0.0;
-  for (int q = threadIdx.x; q < Q; q += AKS_NT) {
-    double g[NMAX];
+  // two nodes per thread: every (128-bit, broadcast) shared load of orbital coefficients feeds four FMAs --
+  // with one node the kernel is bound by the shared-memory issue rate, not by the FP64 pipe
+  for (int qa = threadIdx.x; qa < Q; qa += 2 * DENS_NT) {
+    const int qb = qa + DENS_NT;
+    const bool hb = qb < Q;
+    double ga[NMAX], gb[NMAX];
 #pragma unroll
-    for (int i = 0; i < NMAX; ++i) g[i] = (i < n) ? d.Pg[(size_t)i * d.Qs + q] : 0.0;
-    double r0 = 0.0, r1 = 0.0;
+    for (int i = 0; i < NMAX; ++i) {
+      ga[i] = (i < n) ? d.Pg[(size_t)i * d.Qs + qa] : 0.0;
+      gb[i] = (i < n && hb) ? d.Pg[(size_t)i * d.Qs + qb] : 0.0;
+    }
+    double ra0 = 0.0, ra1 = 0.0, rb0 = 0.0, rb1 = 0.0;
     for (int o = 0; o < cnt; ++o) {
       const double2* uo = reinterpret_cast<const double2*>(us + (size_t)o * NMAX);   // broadcast LDS.128
-      double psa = 0.0, psb = 0.0;
+      double pa0 = 0.0, pa1 = 0.0, pb0 = 0.0, pb1 = 0.0;
 #pragma unroll
       for (int i = 0; i < NMAX / 2; ++i) {
         const double2 u2 = uo[i];
-        psa = fma(u2.x, g[2 * i], psa);
-        psb = fma(u2.y, g[2 * i + 1], psb);
+        pa0 = fma(u2.x, ga[2 * i], pa0);
+        pa1 = fma(u2.y, ga[2 * i + 1], pa1);
+        pb0 = fma(u2.x, gb[2 * i], pb0);
+        pb1 = fma(u2.y, gb[2 * i + 1], pb1);
       }
-      const double psi = psa + psb;
-      const double t = L.n[o] * psi * psi;
-      if (L.e[o] == 0) r0 += t; else r1 += t;
+      const double psa = pa0 + pa1, psb = pb0 + pb1;
+      const double ta = L.n[o] * psa * psa, tb = L.n[o] * psb * psb;
+      if (L.e[o] == 0) { ra0 += ta; rb0 += tb; } else { ra1 += ta; rb1 += tb; }
     }
-    const double X = inv1 * d.x[q] + inv2;
-    double* out0 = b.rho_q_new + ((((size_t)p * 2 + slot) * s + 0) * C + c) * Q;
-    out0[q] = (r0 / (X * X)) * c_xc.inv4pi;
-    if (has_xc) corr = fma(b.fxc[((size_t)(p * s + 0) * C + c) * Q + q], r0, corr);
-    if (s == 2) {
-      double* out1 = b.rho_q_new + ((((size_t)p * 2 + slot) * s + 1) * C + c) * Q;
-      out1[q] = (r1 / (X * X)) * c_xc.inv4pi;
-      if (has_xc) corr = fma(b.fxc[((size_t)(p * s + 1) * C + c) * Q + q], r1, corr);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = h ? qb : qa;
+      if (h && !hb) break;
+      const double r0 = h ? rb0 : ra0, r1 = h ? rb1 : ra1;
+      const double X = inv1 * d.x[q] + inv2;
+      double* out0 = b.rho_q_new + ((((size_t)p * 2 + slot) * s + 0) * C + c) * Q;
+      out0[q] = (r0 / (X * X)) * c_xc.inv4pi;
+      if (has_xc) corr = fma(b.fxc[((size_t)(p * s + 0) * C + c) * Q + q], r0, corr);
+      if (s == 2) {
+        double* out1 = b.rho_q_new + ((((size_t)p * 2 + slot) * s + 1) * C + c) * Q;
+        out1[q] = (r1 / (X * X)) * c_xc.inv4pi;
+        if (has_xc) corr = fma(b.fxc[((size_t)(p * s + 1) * C + c) * Q + q], r1, corr);
+      }
     }
   }
   corr = block_sum(corr, red);
   if (threadIdx.x == 0) b.corr_part[((size_t)p * 2 + slot) * C + c] = corr * inv1;
   // local density block (both spins summed) and its contraction with the mass tensor
   if (b.hartree[p] != 0.0) {
-    for (int idx = threadIdx.x; idx < n * n; idx += AKS_NT) {
+    for (int idx = threadIdx.x; idx < n * n; idx += DENS_NT) {
       const int i = idx / n, j = idx - i * n;
       double v = 0.0;
       for (int o = 0; o < cnt; ++o) v = fma(L.n[o] * us[(size_t)o * NMAX + i], us[(size_t)o * NMAX + j], v);
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(AKS_NT) k_dens_cells(DiscDev d, BatchDev b) {
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* Fc = d.F_loc + (size_t)c * n * n * n;
-    for (int m = warp; m < n; m += AKS_NW) {
+    for (int m = warp; m < n; m += DENS_NT / 32) {
       double acc = 0.0;
       for (int idx = lane; idx < n * n; idx += 32) acc = fma(Dl[idx], Fc[(size_t)m * n * n + idx], acc);
       acc = warp_sum(acc);
