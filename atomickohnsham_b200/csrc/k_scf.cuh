@@ -817,7 +817,11 @@ __global__ void __launch_bounds__(AKS_NT) k_mirror_dense(DiscDev d, BatchDev b, 
 // (oda/loop.jl:43-49), iteration counter, per-iteration record for LogBook / callbacks.
 __global__ void k_finalize(DiscDev d, BatchDev b) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= b.B || b.status[p] != 0) return;
+  if (p >= b.B) return;
+  if (b.status[p] != 0) {
+    if (b.status[p] < 0) b.rec[p].status = b.status[p];   // an error raised inside this step (AKS_EDEGEN3)
+    return;
+  }
   const int npart = b.s * b.ntri;
   double ss = 0.0;
   for (int i = 0; i < npart; ++i) ss += b.norm_part[(size_t)p * npart + i];

@@ -21,8 +21,11 @@ from .quadrature import GaussLegendre
 class KSEDiscretization:
     def __init__(self, basis: FEMBasis, model=None, *, lh: int, nh: int = 10, nspin: int | None = None,
                  fem_integration_method: GaussLegendre | None = None, femops: FEMOperators | None = None,
-                 device: int = 0):
+                 device: int = 0, dtype: str = "float64"):
         self.basis = basis
+        if dtype not in ("float64", "double64"):
+            raise ValueError("dtype must be 'float64' or 'double64'")
+        self.dtype = dtype   # 'double64' (T = Double64 of the reference) is not built: aks_disc_create -> AKS_ENOSYS
         self.lh, self.nh = int(lh), int(nh)
         self.nspin = int(nspin if nspin is not None else (model.nspin if model is not None else 1))
         self.Nh = basis.size
@@ -65,7 +68,7 @@ class KSEDiscretization:
             Mm2=f64(ops.Mm2.T.reshape(-1)), Fi=i64(Fi + 1), Fj=i64(Fj + 1), Fm=i64(Fm + 1), Fv=f64(Fv),
             cell_len=cell_len, cidx=i64(cidx.reshape(-1)), cgen=i64(cgen.reshape(-1)))
         d = _capi.DiscDesc()
-        d.dtype, d.p, d.C, d.Nh = 0, b.ordermax, Cn, b.size
+        d.dtype, d.p, d.C, d.Nh = (1 if self.dtype == "double64" else 0), b.ordermax, Cn, b.size
         d.Q, d.G, d.lh, d.nh, d.nspin = q.npoints, q.npoints, self.lh, self.nh, self.nspin
         for name in ("mesh", "invshifts", "x", "w", "Pgenx", "y", "wy", "Pgeny", "M0", "A", "Mm1", "Mm2", "Fv"):
             setattr(d, name, _capi.dptr(keep[name]))

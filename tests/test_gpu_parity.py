@@ -228,6 +228,44 @@ def test_smeared_and_frozen_aufbau_parity(kind):
     bt.close()
 
 
+def test_c_abi_error_paths():
+    """Errors never cross the ABI as exceptions: status codes + aks_last_error."""
+    import ctypes as C
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200 import _capi
+    from atomickohnsham_b200._capi import AKSError
+    from atomickohnsham_b200.solver import Batch
+    from gpu_diag import make_gpu
+    from helpers import package_tables
+    setup = dict(CASES["o_lda"])
+    model, disc, alg = make_gpu(setup)
+    # Double64 tables are declared in the ABI but not built
+    basis, ops, quad = package_tables(setup["mesh"], setup["p"], 1000)
+    dd = aks.KSEDiscretization(basis, model, lh=2, nh=5, fem_integration_method=quad, femops=ops, dtype="double64")
+    with pytest.raises(AKSError) as ei:
+        dd.handle()
+    assert ei.value.code == -6
+    # bad arguments
+    lib = _capi.lib
+    assert lib.aks_scf_step(None, None) == -1
+    bt = Batch([model], disc, alg)
+    assert lib.aks_batch_set_oda(bt.h, 1e-10, 2.0, 0, 100, 1e-12, 1e-12, 2, 1e-3, 1) == -1      # tinit > 1
+    assert b"bad option" in lib.aks_last_error(disc.ctx.h)
+    assert lib.aks_batch_set_aufbau(bt.h, 1, 0.0, None) == -1                                    # Temp = 0
+    assert lib.aks_get_state(bt.h, 7, None, None, None, None, None) == -1                        # no such problem
+    bt.close()
+    with pytest.raises(AKSError):
+        Batch([aks.KSEModel(Z=8, N=-1.0)], disc, alg)
+    # > 2-fold degeneracy = the reference's error() (optimized.jl:139): bare-Coulomb sodium has 3s = 3p = 3d
+    na = aks.KSEModel(Z=11, N=11, ex=aks.NoFunctional(1), ec=aks.NoFunctional(1))
+    bt = Batch([na, model], disc, aks.ODA(scftol=1e-10, tinit=0.6, aufbau=aks.OptimizedAufbau(max_degen=3)))
+    recs = bt.step()
+    assert recs[0]["status"] == -4 and recs[1]["status"] == 0        # the neighbour keeps running
+    rc = lib.aks_scf_run(bt.h, 5, None, None)
+    assert rc == -4
+    bt.close()
+
+
 def test_eigenpair_window_is_transparent():
     """aks_batch_set_eig_window: solving only the levels the aufbau can reach (certified on the device,
     refilled when the certificate fails) must give the iterations of the all-nh solve, and aks_get_state
