@@ -49,3 +49,47 @@ def partition(costs, world: int):
         parts[r].append(i)
         loads[r] += costs[i]
     return [sorted(p) for p in parts]
+
+
+def maximum_ionization(Zs, discretization, *, nspin=1, ex="lda_x", ec="lda_c_pw", width=1.2, precision=2,
+                       scftol=1e-6, maxiter=50, tinit=0.4, degen_tol=1e-2, lh=None, nh=None):
+    """Largest electron number N in [Z, Z + width] each nucleus Z can bind, by bisection on N.
+
+    Batched front end of the driver `compute_maximum_ionization` (`examples/periodic table/process.jl:12-86`):
+    the same stability test per trial (the highest occupied level must be negative and the SCF must have
+    reached `scftol`, `process.jl:77-82`), the same bracket, tolerance `10^-precision`, `ODA(0.4)`,
+    `scftol = 1e-6`, `maxiter = 50`, `degen_tol = 1e-2` and `(lh, nh)` rule -- but every bisection round is
+    ONE device batch over all Z on a shared discretization instead of a thread per atom (the reference script
+    also re-meshes per atom from a first neutral run; that stays with the caller, who owns the discretization).
+    Returns {Z: N_max} rounded to `precision` digits.
+    """
+    from .algorithms import ODA, OptimizedAufbau
+    from .solver import Batch
+
+    Zs = [int(z) for z in Zs]
+    mk = lambda name: NoFunctional(nspin) if name is None else BuiltinFunctional(name, nspin)
+    lo = {z: float(z) for z in Zs}
+    hi = {z: z + float(width) for z in Zs}
+    tol = 10.0 ** (-precision)
+    alg = ODA(scftol=scftol, tinit=tinit, aufbau=OptimizedAufbau(tol=degen_tol))
+    mid = dict(lo)
+    while max(hi[z] - lo[z] for z in Zs) > tol:
+        mid = {z: (hi[z] + lo[z]) / 2 for z in Zs}
+        models = [KSEModel(Z=z, N=mid[z], ex=mk(ex), ec=mk(ec)) for z in Zs]
+        lhs = [min(math.ceil(mid[z] / 20), 3) if lh is None else lh for z in Zs]
+        nhs = [basis_size(z)[1] if nh is None else nh for z in Zs]
+        lhs = [min(v, discretization.lh) for v in lhs]
+        nhs = [min(v, discretization.nh) for v in nhs]
+        bt = Batch(models, discretization, alg, lh=lhs, nh=nhs)
+        final, _ = bt.run(maxiter)
+        for i, z in enumerate(Zs):
+            st = bt.state(i, want_D=False, want_U=False)
+            occ = st["n"] != 0
+            homo = float(st["eps"][occ].max())
+            stable = homo <= 0.0 and final[i]["status"] == 1 and final[i]["stop"] <= scftol
+            if stable:
+                lo[z] = mid[z]
+            else:
+                hi[z] = mid[z]
+        bt.close()
+    return {z: round(mid[z], precision) for z in Zs}

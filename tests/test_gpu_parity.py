@@ -228,6 +228,31 @@ def test_smeared_and_frozen_aufbau_parity(kind):
     bt.close()
 
 
+def test_maximum_ionization_driver():
+    """Batched N-bisection front end (examples/periodic table/process.jl:12-86): the returned N is stable
+    (bound HOMO, converged) just below and unstable just above, within the bisection tolerance."""
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.solver import Batch
+    from atomickohnsham_b200.sweep import maximum_ionization
+    from helpers import package_tables
+    basis, ops, quad = package_tables(["exp", 0, 300, 30, 1.3], 10, 1000)
+    disc = aks.KSEDiscretization(basis, None, lh=1, nh=6, nspin=1, fem_integration_method=quad, femops=ops)
+    zs = [1, 2, 3, 9]
+    nmax = maximum_ionization(zs, disc)
+    alg = aks.ODA(scftol=1e-6, tinit=0.4, aufbau=aks.OptimizedAufbau(tol=1e-2))
+    for z in zs:
+        assert z <= nmax[z] <= z + 1.2
+    # LDA binds only a fraction of the extra electron of H-, more of F-
+    assert nmax[1] < 2.0 and nmax[9] > nmax[1] - 1 + 9 - 0.5
+    below = [aks.LDA(Z=z, N=max(float(z), nmax[z] - 0.03)) for z in zs]
+    bt = Batch(below, disc, alg, lh=[1] * 4, nh=[min(max(z, 2), 6) for z in zs])
+    final, _ = bt.run(50)
+    for i, z in enumerate(zs):
+        st = bt.state(i, want_D=False, want_U=False)
+        assert final[i]["status"] == 1 and st["eps"][st["n"] != 0].max() <= 0.0, z
+    bt.close()
+
+
 def test_c_abi_error_paths():
     """Errors never cross the ABI as exceptions: status codes + aks_last_error."""
     import ctypes as C
