@@ -15,7 +15,6 @@
 // One warp owns a q-slice; each lane owns 3x3 register tiles of the symmetric K (upper tile
 // triangle only); generator values are staged per 64-node chunk in shared memory (TMA, 4 stages).
 #pragma once
-#include <cuda/barrier>
 
 #include "aks_device.cuh"
 #include "aks_types.cuh"
@@ -42,6 +41,37 @@ __host__ __device__ inline size_t potential_smem_bytes(int n, int Q, int s) {
   size_t stage = (size_t)POT_ST * n3 * POT_QCS, kp = (size_t)AKS_NW * n3 * n3;
   if (kp > stage) stage = kp;
   return sizeof(double) * ((size_t)nu * Qpad + stage + 2 * (size_t)nu * n * n + (size_t)nu * n + 8);
+}
+
+// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+): a "full" barrier per stage completes on the
+// bytes of the TMA transfers, an "empty" barrier per stage counts the warps that are done with the stage
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 template <int NTS, int NU>
@@ -144,39 +174,36 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
 
   if (any_xc) {
     // Generator values at the nodes are streamed through shared memory in 64-node chunks by the TMA
-    // engine (cp.async.bulk, one 512 B row per transfer, completion on an mbarrier), POT_ST stages deep:
-    // chunk ch + POT_ST is requested as soon as every warp is done with chunk ch.
-    using barrier_t = cuda::barrier<cuda::thread_scope_block>;
-    namespace cde = cuda::device::experimental;
-#pragma nv_diag_suppress static_var_with_dynamic_init
-    __shared__ barrier_t bar[POT_ST];
+    // engine (cp.async.bulk, one 512 B row per transfer), POT_ST stages deep, full/empty mbarrier pair per
+    // stage: chunk ch + POT_ST is requested as soon as every warp has released chunk ch.
+    __shared__ __align__(8) uint64_t full_bar[POT_ST], empty_bar[POT_ST];
     const int nch = Qpad / POT_QC;
     const bool tma_ok = ((Q % 2) == 0) && ((d.Qs % 2) == 0);   // 16-byte granularity of every row piece
     if (tid == 0) {
 #pragma unroll
-      for (int st = 0; st < POT_ST; ++st) init(&bar[st], AKS_NT);
-      cde::fence_proxy_async_shared_cta();
+      for (int st = 0; st < POT_ST; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], AKS_NW); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     // rows >= n and the tail of the last chunk are never written by the copies: zero the buffers once
     for (int idx = tid; idx < POT_ST * n3 * POT_QCS; idx += AKS_NT) Gs[idx] = 0.0;
     __syncthreads();
-    barrier_t::arrival_token tok[POT_ST];
+    if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // zeros before the first bulk writes
     auto issue = [&](int ch) {   // thread 0 only
       const int st = ch % POT_ST;
       double* dst = Gs + (size_t)st * n3 * POT_QCS;
       const int q0 = ch * POT_QC, len = min(POT_QC, Q - q0);
-      for (int g = 0; g < n; ++g)
-        cde::cp_async_bulk_global_to_shared(dst + g * POT_QCS, d.Pg + (size_t)g * d.Qs + q0, (uint32_t)(len * 8), bar[st]);
-      tok[st] = cuda::device::barrier_arrive_tx(bar[st], 1, (size_t)n * len * 8);
+      mbar_expect_tx(&full_bar[st], (uint32_t)(n * len * 8));
+      for (int g = 0; g < n; ++g) bulk_g2s(dst + g * POT_QCS, d.Pg + (size_t)g * d.Qs + q0, (uint32_t)(len * 8), &full_bar[st]);
     };
     if (tma_ok && tid == 0)
       for (int ch = 0; ch < POT_ST && ch < nch; ++ch) issue(ch);
     for (int ch = 0; ch < nch; ++ch) {
       const int q0 = ch * POT_QC, st = ch % POT_ST;
+      const uint32_t parity = (uint32_t)((ch / POT_ST) & 1);
       double* Gb = Gs + (size_t)st * n3 * POT_QCS;
       if (tma_ok) {
-        if (tid == 0) bar[st].wait(std::move(tok[st]));
-        else bar[st].arrive_and_wait();
+        mbar_wait(&full_bar[st], parity);   // the chunk has landed; no CTA-wide barrier: warps drift up to POT_ST chunks
       } else {
         __syncthreads();
         for (int idx = tid; idx < n * POT_QC; idx += AKS_NT) {
@@ -211,9 +238,15 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
         }
       }
       if (tma_ok) {
-        __syncthreads();   // everyone is done with this buffer: refill it with chunk ch + POT_ST
+        // this warp is done with the stage; thread 0 refills it with chunk ch + POT_ST once all warps are
         // (a shorter last chunk leaves older, finite values in the tail columns; f is zero there)
-        if (tid == 0 && ch + POT_ST < nch) issue(ch + POT_ST);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+        if (tid == 0 && ch + POT_ST < nch) {
+          mbar_wait(&empty_bar[st], parity);
+          issue(ch + POT_ST);
+        }
+        __syncwarp();
       }
     }
   }
