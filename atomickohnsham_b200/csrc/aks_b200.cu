@@ -65,8 +65,8 @@ struct aks_batch {
   aks_iter_record* h_rec = nullptr;  // pinned
   bool timers = false;
   bool eig_dirty = false;   // levels outside the eigenpair window are stale (k_eig)
-  cudaEvent_t ev[11];   // 8 phase boundaries + [9],[10] around k_mix_dense
-  double phase_ms[8] = {0};
+  cudaEvent_t ev[14];   // 8 phase boundaries + [9],[10] around k_mix_dense + [11],[12],[13] around k_xc, k_potential
+  double phase_ms[10] = {0};
 };
 
 #define CK(call)                                                                              \
@@ -618,12 +618,18 @@ static int launch_potential_range(aks_batch* bt, double* vxc_out, double* har_ou
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   const int NP = potential_np(dv.n, bt->cur->dev.s);
+  const bool tm = bt->timers && bt->cur == &bt->whole;
+  if (tm) CK(cudaEventRecord(bt->ev[11], bt->cur->stream));
+  k_xc<<<dim3((dv.Q + 255) / 256, dv.C, np), 256, 0, bt->cur->stream>>>(dv, bt->cur->dev, p0, np, force);
+  LAUNCH_CHECK();
+  if (tm) CK(cudaEventRecord(bt->ev[12], bt->cur->stream));
   const dim3 grid(dv.C, (np + NP - 1) / NP);
   if (potential_nts(dv.n) == 1)
     k_potential<1, 4><<<grid, AKS_NT, bt->smem_pot, bt->cur->stream>>>(dv, bt->cur->dev, vxc_out, har_out, p0, np, force);
   else
     k_potential<2, 2><<<grid, AKS_NT, bt->smem_pot, bt->cur->stream>>>(dv, bt->cur->dev, vxc_out, har_out, p0, np, force);
   LAUNCH_CHECK();
+  if (tm) CK(cudaEventRecord(bt->ev[13], bt->cur->stream));
   return AKS_OK;
 }
 static int launch_potential(aks_batch* bt, double* vxc_out, double* har_out) {
@@ -807,6 +813,10 @@ static int fetch_records(aks_batch* bt, aks_iter_record* out) {
     float msd = 0;
     cudaEventElapsedTime(&msd, bt->ev[9], bt->ev[10]);
     bt->phase_ms[7] = msd;   // k_mix_dense alone (part of phase 6)
+    cudaEventElapsedTime(&msd, bt->ev[12], bt->ev[13]);
+    bt->phase_ms[8] = msd;   // k_potential alone (part of phase 0)
+    cudaEventElapsedTime(&msd, bt->ev[11], bt->ev[12]);
+    bt->phase_ms[9] = msd;   // k_xc alone
   }
   if (out) memcpy(out, bt->h_rec, sizeof(aks_iter_record) * bt->B);
   return AKS_OK;
@@ -861,9 +871,9 @@ extern "C" int aks_scf_run(aks_batch* bt, int32_t maxiter, aks_iter_record* hist
   return notconv ? AKS_ENOTCONV : AKS_OK;
 }
 
-extern "C" int aks_last_phase_ms(aks_batch* bt, double out[8]) {
+extern "C" int aks_last_phase_ms(aks_batch* bt, double out[10]) {
   if (!bt || !out) return AKS_EINVAL;
-  for (int i = 0; i < 8; ++i) out[i] = bt->phase_ms[i];
+  for (int i = 0; i < 10; ++i) out[i] = bt->phase_ms[i];
   return bt->timers ? AKS_OK : AKS_EINVAL;
 }
 

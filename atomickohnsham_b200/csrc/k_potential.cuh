@@ -74,6 +74,31 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// k_xc: pointwise XC potential at the Gauss nodes of every cell, f_sigma[q] = w_q v_sigma(rho(q))
+// (evaluate_vrho!, src/physics/models.jl:97-105; clamp at 0, BuiltinFunctional.jl:112).  One thread per node:
+// long dependent FP64 chains (rcbrt, sqrt, log, one division), so it runs at full occupancy on its own
+// instead of inside the register-heavy contraction kernel.  k_dens_cells reads f again for <Vxc[D_prev], D_new>.
+__global__ void __launch_bounds__(256) k_xc(DiscDev d, BatchDev b, int p0, int np, int force) {
+  const int p = p0 + blockIdx.z;
+  if (p >= p0 + np || (!force && b.status[p] != 0)) return;
+  const int ex = b.ex[p], ec = b.ec[p];
+  if (ex == 0 && ec == 0) return;
+  const int c = blockIdx.y, q = blockIdx.x * 256 + threadIdx.x;
+  const int Q = d.Q, C = d.C, s = b.s;
+  if (q >= Q) return;
+  const double wq = d.w[q];
+  const size_t o0 = ((size_t)(p * s + 0) * C + c) * Q + q;
+  if (s == 1) {
+    b.fxc[o0] = xc_vrho_unpol(fmax(b.rho_q[o0], 0.0), ex, ec) * wq;
+  } else {
+    const size_t o1 = ((size_t)(p * s + 1) * C + c) * Q + q;
+    double vu, vd;
+    xc_vrho_pol(fmax(b.rho_q[o0], 0.0), fmax(b.rho_q[o1], 0.0), ex, ec, vu, vd);
+    b.fxc[o0] = vu * wq;
+    b.fxc[o1] = vd * wq;
+  }
+}
+
 template <int NTS, int NU>
 __global__ void __launch_bounds__(AKS_NT, 2)
 k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __restrict__ har_loc_out,
@@ -108,42 +133,17 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double inv1 = d.inv1[c];
 
-  // ---- 1. pointwise XC potential at the Gauss nodes: f_u[q] = w_q v_u(rho(q))
+  // ---- 1. f_u[q] = w_q v_u(rho(q)) of this CTA's units, evaluated by k_xc (pointwise, full occupancy)
   bool any_xc = false;
   for (int pp = 0; pp < NP; ++pp) {
     const int p = pbase + pp;
     const bool val = uval[pp * s];
-    const int ex = val ? b.ex[p] : 0, ec = val ? b.ec[p] : 0;
-    const bool has_xc = (ex != 0) || (ec != 0);
+    const bool has_xc = val && ((b.ex[p] != 0) || (b.ec[p] != 0));
     any_xc = any_xc || has_xc;
-    double* f0s = fs + (size_t)(pp * s) * Qpad;
-    double* f1s = f0s + Qpad;
-    if (!has_xc) {
-      for (int q = tid; q < s * Qpad; q += AKS_NT) f0s[q] = 0.0;
-      continue;
-    }
-    const double* r0 = b.rho_q + ((size_t)(p * s + 0) * C + c) * Q;
-    const double* r1 = (s == 2) ? b.rho_q + ((size_t)(p * s + 1) * C + c) * Q : nullptr;
-    double* fo0 = b.fxc + ((size_t)(p * s + 0) * C + c) * Q;
-    double* fo1 = (s == 2) ? b.fxc + ((size_t)(p * s + 1) * C + c) * Q : nullptr;
-    for (int q = tid; q < Qpad; q += AKS_NT) {
-      double f0 = 0.0, f1 = 0.0;
-      if (q < Q) {
-        const double wq = d.w[q];
-        if (s == 1) {
-          f0 = xc_vrho_unpol(fmax(r0[q], 0.0), ex, ec) * wq;
-          fo0[q] = f0;
-        } else {
-          double vu, vd;
-          xc_vrho_pol(fmax(r0[q], 0.0), fmax(r1[q], 0.0), ex, ec, vu, vd);
-          f0 = vu * wq;
-          f1 = vd * wq;
-          fo0[q] = f0;
-          fo1[q] = f1;
-        }
-      }
-      f0s[q] = f0;
-      if (s == 2) f1s[q] = f1;
+    for (int e = 0; e < s; ++e) {
+      double* fd = fs + (size_t)(pp * s + e) * Qpad;
+      const double* fg = b.fxc + ((size_t)(p * s + e) * C + c) * Q;
+      for (int q = tid; q < Qpad; q += AKS_NT) fd[q] = (has_xc && q < Q) ? fg[q] : 0.0;
     }
   }
   // units beyond the problems of this CTA (NU > NP * s cannot happen; kept for safety)

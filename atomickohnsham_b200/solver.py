@@ -233,7 +233,7 @@ class Batch:
         return info >> 8, info & 0x7f, (info & 0x80) != 0
 
     def phase_ms(self):
-        out = (C.c_double * 8)()
+        out = (C.c_double * 10)()
         rc = _capi.lib.aks_last_phase_ms(self.h, out)
         return list(out) if rc == AKS_OK else None
 

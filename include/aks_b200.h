@@ -185,9 +185,9 @@ int64_t aks_launch_count(const aks_ctx* ctx);
  * the FP64 roofline denominator, which MEASURED_PEAKS.json does not carry                 */
 int aks_measure_fp64_peak(aks_ctx* ctx, double* tflops);
 /* per-phase device time of the LAST aks_scf_step in ms: {potential, eigensolve, aufbau,
- * density, poisson, linesearch, mix, k_mix_dense alone}; valid only if AKS_PHASE_TIMERS=1 in the
- * environment (the batch then runs on one stream instead of its concurrent lanes)          */
-int aks_last_phase_ms(aks_batch* batch, double out[8]);
+ * density, poisson, linesearch, mix, k_mix_dense alone, k_potential alone, k_xc alone}; valid only if
+ * AKS_PHASE_TIMERS=1 in the environment (the batch then runs on one stream instead of its lanes) */
+int aks_last_phase_ms(aks_batch* batch, double out[10]);
 
 #ifdef __cplusplus
 }
