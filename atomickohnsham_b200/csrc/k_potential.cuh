@@ -303,6 +303,7 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
 #pragma unroll
       for (int pp = 0; pp < NU; ++pp) fw[pp] = 0.0;
       if (any_h)
+#pragma unroll 7
         for (int m = 0; m < n; ++m) {
           const double fv = Fc[(size_t)m * n * n + idx];
 #pragma unroll
@@ -333,10 +334,28 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
   if (har_loc_out && blockIdx.y == 0)
     for (int idx = tid; idx < n * n; idx += AKS_NT) har_loc_out[(size_t)c * n * n + idx] = Hs[idx];
 
-  // ---- 4. H_l = (Kin_l + Coulomb) + Vxc + Hartree, packed per (problem, sigma, l, cell)
-  const double* Ac = d.A_loc + (size_t)c * n * n;
-  const double* M1c = d.Mm1_loc + (size_t)c * n * n;
-  const double* M2c = d.Mm2_loc + (size_t)c * n * n;
+  // ---- 4. H_l = (Kin_l + Coulomb) + Vxc + Hartree, packed per (problem, sigma, l, cell).  The fixed blocks
+  // of the cell and the symmetric-twin / packing tables are staged once (the chunk buffers are free now):
+  // the (problem, sigma, l) loop then reads shared memory only.
+  double* As = Gs;                 // [n*n]  A / 2
+  double* M2s = As + n * n;        // [n*n]  M_-2 / 2
+  double* M1s = M2s + n * n;       // [n*n]  M_-1
+  int* los = reinterpret_cast<int*>(M1s + n * n);   // [n*n]
+  int* pks = los + n * n;                           // [n*n]
+  {
+    const double* Ac = d.A_loc + (size_t)c * n * n;
+    const double* M1c = d.Mm1_loc + (size_t)c * n * n;
+    const double* M2c = d.Mm2_loc + (size_t)c * n * n;
+    const bool has_m2 = d.Mm2_loc != nullptr;
+    for (int idx = tid; idx < n * n; idx += AKS_NT) {
+      As[idx] = Ac[idx] * 0.5;
+      M2s[idx] = has_m2 ? M2c[idx] * 0.5 : 0.0;
+      M1s[idx] = M1c[idx];
+      los[idx] = d.lo_tab[idx];   // index of the lower-triangle twin: exactly symmetric output
+      pks[idx] = d.pk_tab[idx];   // packed position, or -1 above the diagonal
+    }
+  }
+  __syncthreads();
   for (int pp = 0; pp < NP; ++pp) {
     if (!uval[pp * s]) continue;
     const int p = pbase + pp;
@@ -350,10 +369,9 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
         double* outf = b.Hfull + ((((size_t)p * s + e) * b.Lmax + l) * C + c) * (size_t)n * n;
         const double ll = (double)(l * (l + 1));
         for (int idx = tid; idx < n * n; idx += AKS_NT) {
-          const int lo_idx = d.lo_tab[idx];   // index of the lower-triangle twin: exactly symmetric output
-          const int pk = d.pk_tab[idx];       // packed position, or -1 above the diagonal
-          const double kin = (Ac[lo_idx] + ((l > 0) ? ll * M2c[lo_idx] : 0.0)) * 0.5;
-          const double cou = -Zp * M1c[lo_idx];
+          const int lo_idx = los[idx], pk = pks[idx];
+          const double kin = As[lo_idx] + ll * M2s[lo_idx];
+          const double cou = -Zp * M1s[lo_idx];
           const double h = ((kin + cou) + Ku[lo_idx]) + Hp[lo_idx];
           outf[idx] = h;
           if (pk >= 0) out[pk] = h;
