@@ -431,7 +431,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk) ZB(double, Hfull, B * s * L * C * n * n)
   ZB(double, eps, B * s * L * nh) ZB(double, eps_new, B * s * L * nh) ZB(double, U, B * s * L * nh * Nh)
   ZB(int, eig_info, B * s * L * nh) ZB(long long, eig_dbg, B * s * L * nh * 8) ZB(double, red, B * s * L * C * (6 * (n - 2) + 4))
-  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * C * 6) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, redo_cnt, B) ZB(double, nfix, B * s * L * nh) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
+  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * C * 6) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, redo_cnt, B) ZB(double, e_cert, B) ZB(int, degen3, B) ZB(double, nfix, B * s * L * nh) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
   ZB(double, ecou_orb, B * s * L * nh) ZB(double, occ, B * 2 * s * L * nh) ZB(int, degen, B) ZB(int, occ_cnt, B * 2) ZB(int, occ_elk, B * 2 * AKS_MAXORB) ZB(double, occ_n, B * 2 * AKS_MAXORB)
   ZB(int, degen_idx, B * 2) ZB(double, degen_n, B * 4) ZB(double, rho_q_new, B * 2 * s * C * Q)
   ZB(double, rho_y_new, B * 2 * s * G) ZB(double, corr_part, B * 2 * C) ZB(double, Bloc_new, B * 2 * C * n)
@@ -443,7 +443,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   b.scftol = 1e-10; b.tinit = 0.6; b.frozen_t = 0; b.maxiter_ls = 100;
   b.abstol_ls = b.reltol_ls = 1e4 * 2.220446049250313e-16;
   b.max_degen = 2; b.degen_tol = 1e-3; b.handle_spin = 1;
-  b.eig_margin = 1;
+  b.eig_margin = 0;
   b.aufbau_kind = 0; b.temp = 0.0;
   // launch configuration
   bt->smem_pot = potential_smem_bytes(dv.n, dv.Q, b.s);
@@ -458,6 +458,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   CK(cudaFuncSetAttribute(k_potential<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
   CK(cudaFuncSetAttribute(k_potential<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
   CK(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
+  CK(cudaFuncSetAttribute(k_eig_cert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
   CK(cudaFuncSetAttribute(k_reduce<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
   CK(cudaFuncSetAttribute(k_reduce<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
   CK(cudaFuncSetAttribute(k_reduce<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
@@ -725,6 +726,8 @@ static int step_on_lane(aks_batch* bt) {
   k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 0);
   LAUNCH_CHECK();
   if (b.eig_margin >= 0) {   // problems whose window could not be certified: solve the rest, repeat
+    k_eig_cert<<<dim3(b.Lmax * b.s, bt->cur->B), EIG_NT, bt->smem_eig, bt->cur->stream>>>(dv, b);
+    LAUNCH_CHECK();
     if ((rc = launch_eig_pass(bt, 1)) != AKS_OK) return rc;
     k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 1);
     LAUNCH_CHECK();

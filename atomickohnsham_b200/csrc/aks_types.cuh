@@ -83,6 +83,8 @@ struct BatchDev {
   int* kdone;        // [B][s][Lmax]  eigenpairs per channel that are current (solved for the last H)
   int* redo;         // [B]  aufbau could not be certified on the window: solve the rest, repeat
   int* redo_cnt;     // [B]  how often that happened (diagnostic)
+  double* e_cert;    // [B]  shift of the window certificate: last level the aufbau examined + degen_tol
+  int* degen3;       // [B]  > 2-fold degeneracy met by the (not yet certified) aufbau
   int* khist;        // [B][s][Lmax][AKS_KHIST]  occupied levels per channel of the last steps
   int eig_margin;    // window = occupied levels + margin per channel; < 0: always all nh
   double* ekin_orb;  // [B][s][Lmax][nhmax]

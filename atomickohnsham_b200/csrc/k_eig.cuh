@@ -622,8 +622,8 @@ enum { EST_BRACKET_LO = 0, EST_BRACKET_HI, EST_BISECT, EST_RQI, EST_CERT_LO, EST
 
 // Eigenpair window.  Only levels that can influence the aufbau have to be current in every SCF step:
 // mode 0 solves the first kact[channel] levels of each channel (occupied levels of the previous step
-// + margin; the others get the sentinel AKS_EPS_MISSING and sort last); k_aufbau then CERTIFIES that
-// every unsolved level lies above everything it examined, and otherwise raises redo[p], for which
+// + margin; the others get the sentinel AKS_EPS_MISSING and sort last); k_eig_cert then CERTIFIES by an
+// inertia count that every unsolved level lies above everything the aufbau examined, else raises redo[p], for which
 // mode 1 solves the remaining levels (cold) before the aufbau is repeated.  Mode 2 is the same fill
 // pass on request of the host (aks_get_state / end of a run: the reference returns all nh pairs).
 #ifndef EIG_NT
@@ -875,6 +875,37 @@ k_eig(DiscDev d, BatchDev b, int mode) {
     long long* dbg = b.eig_dbg + (chan * b.nhmax + k) * 8;
     dbg[0] = t_set; dbg[1] = t_fac; dbg[2] = t_sol; dbg[3] = t_app; dbg[4] = t_fin; dbg[5] = clock64() - t_all;
 #endif
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_eig_cert: certificate of the eigenpair window.  For every channel of which only the first kdone levels
+// were solved: #{eigenvalues < e_cert} (ONE inertia count, the cost of a single RQI factorisation) must equal
+// the number of solved levels below e_cert; otherwise an unsolved level could have been occupied and the
+// problem is marked for the refill pass.  One CTA per (channel, problem).
+__global__ void __launch_bounds__(EIG_NT, (EIG_NT == 128) ? 4 : 2)
+k_eig_cert(DiscDev d, BatchDev b) {
+  const int ch = blockIdx.x, p = blockIdx.y;
+  if (b.status[p] != 0 || b.redo[p] != 0) return;
+  const int e = ch / b.Lmax, l = ch - e * b.Lmax;
+  if (l >= b.Lp[p]) return;
+  const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
+  const int nhp = b.nhp[p], kd = min(nhp, b.kdone[chan]);
+  if (kd >= nhp) return;
+  extern __shared__ double sm[];
+  const int C = d.C, nb = d.nb;
+  EigShared S;
+  eig_carve(d, sm, S);
+  S.red = b.red + chan * C * red_stride(nb);
+  __syncthreads();
+  const double sigma = b.e_cert[p];
+  eig_factor(S, C, nb, 1, sigma, 0);
+  if (threadIdx.x == 0) {
+    int below = 0;
+    for (int k = 0; k < kd; ++k) below += (b.eps_new[chan * b.nhmax + k] < sigma);
+    if (S.cntg[0] > below) {
+      if (atomicExch(&b.redo[p], 1) == 0) b.redo_cnt[p] += 1;
+    }
   }
 }
 

@@ -41,7 +41,11 @@ __device__ inline void write_occ_list(const BatchDev& b, int p, int slot) {
 __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b, int mode) {
   const int p = blockIdx.x;
   if (p >= b.B || b.status[p] != 0) return;
-  if (mode == 1 && b.redo[p] == 0) return;
+  if (mode == 1 && b.redo[p] == 0) {
+    // the window pass was certified (k_eig_cert): commit what it had to defer
+    if (threadIdx.x == 0 && b.degen3[p]) { b.status[p] = AKS_EDEGEN3; b.degen3[p] = 0; }
+    return;
+  }
   const int Lp = b.Lp[p], nhp = b.nhp[p], s = b.s;
   const int norb = Lp * nhp * s;
   // stage everything the serial logic touches in shared memory (one warp per problem): the
@@ -181,21 +185,19 @@ __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b, int mode) 
         break;
       }
     }
-    // certificate of the window: the highest solved level of every truncated channel must lie above
-    // e_last + degen_tol (levels are ordered within a channel, so the unsolved ones lie higher still)
+    // Certificate of the window (mode 0): no unsolved level may lie below e_cert = (last level the fill
+    // examined) + degen_tol.  k_eig_cert checks that with one inertia count per truncated channel; here only
+    // the trivial failure (the fill ran out of solved levels) is decided.
     bool redo = false;
-    if (mode == 0) {
-      if (!(e_last < 0.5 * 1e300)) redo = true;
-      for (int e = 0; e < s && !redo; ++e)
-        for (int l = 0; l < Lp; ++l) {
-          const int kd = b.kdone[((size_t)p * s + e) * b.Lmax + l];
-          if (kd < nhp && !(ev[l + Lp * (kd - 1) + Lp * nhp * e] > e_last + b.degen_tol)) { redo = true; break; }
-        }
+    if (mode == 0 && b.eig_margin >= 0) {
+      redo = !(e_last < 0.5 * AKS_EPS_MISSING);
+      b.e_cert[p] = e_last + b.degen_tol;
     }
     b.redo[p] = redo ? 1 : 0;
     if (redo) b.redo_cnt[p] += 1;
     if (!redo) {
-      if (degen3) b.status[p] = AKS_EDEGEN3;
+      if (mode == 0 && b.eig_margin >= 0) b.degen3[p] = degen3 ? 1 : 0;   // committed once certified
+      else if (degen3) b.status[p] = AKS_EDEGEN3;
       // window of the next step: occupied levels (either slot) + margin
       for (int e = 0; e < s; ++e)
         for (int l = 0; l < Lp; ++l) {

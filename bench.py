@@ -380,7 +380,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--sweeps", type=int, default=1, help="periodic-table sweeps per GPU (default 1)")
-    ap.add_argument("--eig-margin", type=int, default=1, help="eigenpair window margin (-1: all nh every step)")
+    ap.add_argument("--eig-margin", type=int, default=0, help="eigenpair window margin (-1: all nh every step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON record): anything libraries print there (e.g. NCCL's version

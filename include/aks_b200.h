@@ -116,10 +116,10 @@ int aks_batch_set_aufbau(aks_batch* batch, int32_t kind, double temp, const doub
 /* Eigenpair window (no reference counterpart; the results are the reference's).  The reference solves
  * all nh eigenpairs of every channel in every iteration (oda/loop.jl:65-77) although only the levels
  * the aufbau can reach matter for the iteration.  With margin >= 0 a step solves, per channel, the
- * levels occupied in the previous step + margin, certifies on the device that no unsolved level could
- * have been occupied (else solves the rest and repeats the aufbau within the same step), and the
- * remaining eigenpairs of the last Hamiltonian are solved when aks_get_state asks for eps / U.
- * margin < 0: every step solves all nh eigenpairs.  Default 1.                                  */
+ * levels occupied in the previous steps + margin, certifies on the device (one inertia count per
+ * channel) that no unsolved level could have been occupied (else solves the rest and repeats the aufbau
+ * within the same step), and the remaining eigenpairs of the last Hamiltonian are solved when
+ * aks_get_state asks for eps / U.  margin < 0: every step solves all nh eigenpairs.  Default 0.  */
 int aks_batch_set_eig_window(aks_batch* batch, int32_t margin);
 
 /* back to niter = 0, D = 0 (KSESolver constructor, src/solver/solver.jl:61-88) */
