@@ -912,6 +912,33 @@ extern "C" int aks_get_state(aks_batch* bt, int32_t prob, double* D, double* U, 
   return AKS_OK;
 }
 
+// eps, n, W of EVERY problem in three copies (a sweep reads these for all atoms; per-problem calls cost a
+// synchronisation each).  Layout per problem as in aks_get_state: eps, n (L, nh[, 2]) column-major, W (Nh).
+extern "C" int aks_get_state_all(aks_batch* bt, double* eps, double* nocc, double* W) {
+  if (!bt) return AKS_EINVAL;
+  enter_main(bt);
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const BatchDev& b = bt->dev;
+  const size_t s = b.s, Nh = dv.Nh, L = b.Lmax, nh = b.nhmax, B = bt->B, per = s * L * nh;
+  if (eps) { int rc = ensure_complete(bt); if (rc != AKS_OK) return rc; }
+  std::vector<double> he(eps ? B * per : 0), hn(nocc ? B * 2 * per : 0);
+  if (eps) CK(cudaMemcpyAsync(he.data(), b.eps, sizeof(double) * B * per, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nocc) CK(cudaMemcpyAsync(hn.data(), b.occ, sizeof(double) * B * 2 * per, cudaMemcpyDeviceToHost, ctx->stream));
+  if (W) CK(cudaMemcpyAsync(W, b.Wv, sizeof(double) * B * Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t p = 0; p < B; ++p) {
+    for (size_t e = 0; e < s; ++e)
+      for (size_t l = 0; l < L; ++l)
+        for (size_t k = 0; k < nh; ++k) {
+          if (eps) eps[p * per + l + L * (k + nh * e)] = he[p * per + (e * L + l) * nh + k];
+          if (nocc) nocc[p * per + l + L * (k + nh * e)] = hn[p * 2 * per + (e * L + l) * nh + k];   // slot 0
+        }
+    if (W) for (size_t i = 0; i < Nh; ++i) W[p * Nh + i] *= bt->hHar[p];
+  }
+  return AKS_OK;
+}
+
 static int launch_state_from_dense(aks_batch* bt, int prob) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;

@@ -183,6 +183,20 @@ class Batch:
             out["U"] = np.transpose(U, (3, 2, 1, 0))
         return out
 
+    def states(self):
+        """eps, n, W of every problem in one call (aks_get_state_all): list of dicts as `state(i)` returns
+        without D and U."""
+        d = self.disc
+        s, Nh, L, nh = d.nspin, d.Nh, d.lh + 1, d.nh
+        per = s * L * nh
+        eps = np.zeros(self.nprob * per)
+        n = np.zeros(self.nprob * per)
+        W = np.zeros(self.nprob * Nh)
+        self.ctx.check(_capi.lib.aks_get_state_all(self.h, _capi.dptr(eps), _capi.dptr(n), _capi.dptr(W)))
+        return [dict(eps=eps[i * per:(i + 1) * per].reshape((L, nh, s), order="F"),
+                     n=n[i * per:(i + 1) * per].reshape((L, nh, s), order="F"),
+                     W=W[i * Nh:(i + 1) * Nh]) for i in range(self.nprob)]
+
     def set_density(self, prob, D, energies_prev=None, niter=1):
         """Restart / step-level parity: D is (Nh, Nh, nspin) (or (Nh, Nh))."""
         D = np.asarray(D, dtype=np.float64)

@@ -82,8 +82,9 @@ def maximum_ionization(Zs, discretization, *, nspin=1, ex="lda_x", ec="lda_c_pw"
         nhs = [min(v, discretization.nh) for v in nhs]
         bt = Batch(models, discretization, alg, lh=lhs, nh=nhs)
         final, _ = bt.run(maxiter)
+        states = bt.states()
         for i, z in enumerate(Zs):
-            st = bt.state(i, want_D=False, want_U=False)
+            st = states[i]
             occ = st["n"] != 0
             homo = float(st["eps"][occ].max())
             stable = homo <= 0.0 and final[i]["status"] == 1 and final[i]["stop"] <= scftol

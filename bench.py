@@ -231,14 +231,14 @@ def b200_arm(args):
         bt3 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)   # H2D: model parameters
         for _ in range(args.steps):
             bt3.step()                                             # D2H: one record per atom, every step
-        outs = [bt3.state(i, want_D=False, want_U=False) for i in range(B)]  # D2H: eps, n, W per atom
+        outs = bt3.states()                                        # D2H: eps, n, W of every atom
         torch.cuda.synchronize(local)
         e2e_times.append(time.perf_counter() - t0)
         bt3.close()
     t_e2e = sorted(e2e_times)[1]
     assert len(outs) == B
     h2d = B * (3 * 8 + 4 * 4)
-    d2h_total = args.steps * B * 72 + B * (2 * 4 * 10 * 8 + Nh_bytes())
+    d2h_total = args.steps * B * 72 + B * (3 * 4 * 10 * 8 + Nh_bytes())   # records + eps, both occupation slots, W
     e2e_units = torch.tensor([float(B * args.steps), t_e2e], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         import torch.distributed as dist
@@ -281,7 +281,7 @@ def b200_arm(args):
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h_total / args.steps,
-                    "what": "Batch() + K x aks_scf_step with host records + aks_get_state(eps,n,W) of every atom; median of 3",
+                    "what": "Batch() + K x aks_scf_step with host records + aks_get_state_all (eps, n, W of every atom); median of 3",
                     "seconds_each": e2e_times},
             "roofline": roof, "phases_ms": phases,
             "phases_note": "per-phase times are measured with the batch on ONE stream (AKS_PHASE_TIMERS); the timed steps "

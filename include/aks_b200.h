@@ -149,6 +149,8 @@ int aks_scf_run(aks_batch* batch, int32_t maxiter, aks_iter_record* history,
  *   (postcomputations!, oda/loop.jl:51-54; multiplied by the model's hartree coefficient) */
 int aks_get_state(aks_batch* batch, int32_t prob, double* D, double* U, double* eps, double* n,
                   double* W);
+/* eps, n, W of every problem at once: eps, n [nprob][(L, nh[, 2])], W [nprob][Nh]; any pointer may be NULL */
+int aks_get_state_all(aks_batch* batch, double* eps, double* n, double* W);
 /* overwrite one problem's density state from a dense D (Nh,Nh[,2]) -- restart / step-level
  * parity tests ("identical input D").  Energies of the previous step are set from
  * `energies_prev` = {Etot,Ekin,Ecou,Ehar,Eexc} and niter from `niter`.                    */

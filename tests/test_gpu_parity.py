@@ -189,6 +189,11 @@ def test_batch_is_deterministic_and_problem_independent():
     b2 = Batch([models[0]], disc, alg)
     f2, _ = b2.run(100)
     assert f1[0] == f1[3] == f2[0]
+    # aks_get_state_all == aks_get_state of every problem
+    allst = b1.states()
+    for i in range(4):
+        one = b1.state(i, want_D=False, want_U=False)
+        assert all(np.array_equal(allst[i][k], one[k]) for k in ("eps", "n", "W"))
     b1.reset()
     f3, _ = b1.run(100)
     assert f3 == f1
