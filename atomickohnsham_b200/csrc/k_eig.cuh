@@ -697,6 +697,13 @@ k_eig(DiscDev d, BatchDev b, int mode) {
       if (!(gap < 1e300) || !(gap > 0.0)) gap = fmax(fabs(ep), 1.0);
       const double dlt = fmax(0.5 * gap, 1e-12 * fmax(fabs(ep), 1e-3));
       blo = ep - dlt; bhi = ep + dlt;
+    } else if (b.niter[p] == 0) {
+      // first iteration from D = 0: the Hamiltonian is bare Coulomb, level k of channel l sits at the
+      // hydrogenic -Z^2 / (2 n^2), n = k + l + 1 (box states aside); only a bracket to start from
+      const double Z = b.Z[p], nq = (double)(k + l + 1);
+      const double eh = -0.5 * Z * Z / (nq * nq), eh1 = -0.5 * Z * Z / ((nq + 1.0) * (nq + 1.0));
+      const double dlt = 0.25 * (eh1 - eh);
+      blo = eh - dlt; bhi = eh + dlt;
     } else {
       const double Z = b.Z[p];
       blo = -(Z * Z + 10.0); bhi = 1.0;
