@@ -25,6 +25,11 @@ struct aks_ctx {
   cudaStream_t stream = nullptr;
   std::string err;
   int64_t launches = 0;
+  // pinned record buffers and lane streams / events of destroyed batches, reused by the next batch:
+  // cudaFreeHost and stream destruction synchronise the whole device (tens of ms), batches come and go
+  std::vector<std::pair<void*, size_t>> pinned_free;
+  std::vector<cudaStream_t> stream_free;
+  std::vector<cudaEvent_t> event_free;
 };
 
 struct aks_disc {
@@ -63,6 +68,7 @@ struct aks_batch {
   std::vector<double> hZ, hN, hHar;
   std::vector<int> hLp, hnhp;
   aks_iter_record* h_rec = nullptr;  // pinned
+  size_t h_rec_bytes = 0;
   bool timers = false;
   bool eig_dirty = false;   // levels outside the eigenpair window are stale (k_eig)
   cudaEvent_t ev[14];   // 8 phase boundaries + [9],[10] around k_mix_dense + [11],[12],[13] around k_xc, k_potential
@@ -139,6 +145,9 @@ extern "C" int aks_ctx_create(int device, aks_ctx** out) {
 }
 extern "C" void aks_ctx_destroy(aks_ctx* ctx) {
   if (!ctx) return;
+  for (auto& pf : ctx->pinned_free) cudaFreeHost(pf.first);
+  for (cudaStream_t st : ctx->stream_free) cudaStreamDestroy(st);
+  for (cudaEvent_t ev : ctx->event_free) cudaEventDestroy(ev);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -472,7 +481,17 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   CK(cudaFuncSetAttribute(k_cells_from_dense<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
   CK(cudaFuncSetAttribute(k_cells_from_dense<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
   CK(cudaFuncSetAttribute(k_cells_from_dense<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
-  CK(cudaMallocHost((void**)&bt->h_rec, sizeof(aks_iter_record) * B));
+  {
+    const size_t need = sizeof(aks_iter_record) * B;
+    for (size_t i = 0; i < ctx->pinned_free.size(); ++i)
+      if (ctx->pinned_free[i].second >= need) {
+        bt->h_rec = (aks_iter_record*)ctx->pinned_free[i].first;
+        bt->h_rec_bytes = ctx->pinned_free[i].second;
+        ctx->pinned_free.erase(ctx->pinned_free.begin() + i);
+        break;
+      }
+    if (!bt->h_rec) { CK(cudaMallocHost((void**)&bt->h_rec, need)); bt->h_rec_bytes = need; }
+  }
   const char* tenv = getenv("AKS_PHASE_TIMERS");
   bt->timers = tenv && tenv[0] == '1';
   if (bt->timers) for (auto& e : bt->ev) CK(cudaEventCreate(&e));
@@ -485,7 +504,8 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
     if (nl > 8) nl = 8;
     if (bt->B < 8 * nl) nl = bt->B >= 16 ? 2 : 1;
     const int NP = potential_np(dv.n, b.s);
-    CK(cudaEventCreateWithFlags(&bt->fork_ev, cudaEventDisableTiming));
+    if (!ctx->event_free.empty()) { bt->fork_ev = ctx->event_free.back(); ctx->event_free.pop_back(); }
+    else CK(cudaEventCreateWithFlags(&bt->fork_ev, cudaEventDisableTiming));
     if (nl > 1) {
       int prev = 0;
       for (int k = 0; k < nl; ++k) {
@@ -493,8 +513,10 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
         if (end <= prev) continue;
         Lane ln;
         ln.p0 = prev; ln.B = end - prev;
-        CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
+        if (!ctx->stream_free.empty()) { ln.stream = ctx->stream_free.back(); ctx->stream_free.pop_back(); }
+        else CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+        if (!ctx->event_free.empty()) { ln.done = ctx->event_free.back(); ctx->event_free.pop_back(); }
+        else CK(cudaEventCreateWithFlags(&ln.done, cudaEventDisableTiming));
         bt->lanes.push_back(ln);
         prev = end;
       }
@@ -506,15 +528,18 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
 
 extern "C" void aks_batch_destroy(aks_batch* bt) {
   if (!bt) return;
-  for (Lane& ln : bt->lanes) {
-    if (ln.stream) { cudaStreamSynchronize(ln.stream); cudaStreamDestroy(ln.stream); }
-    if (ln.done) cudaEventDestroy(ln.done);
+  {
+    aks_ctx* cx = bt->disc->ctx;
+    for (Lane& ln : bt->lanes) {
+      if (ln.stream) { cudaStreamSynchronize(ln.stream); cx->stream_free.push_back(ln.stream); }
+      if (ln.done) cx->event_free.push_back(ln.done);
+    }
+    if (bt->fork_ev) cx->event_free.push_back(bt->fork_ev);
   }
-  if (bt->fork_ev) cudaEventDestroy(bt->fork_ev);
   cudaStream_t st = bt->disc->ctx->stream;
   for (void* p : bt->allocs) cudaFreeAsync(p, st);
   cudaStreamSynchronize(st);
-  if (bt->h_rec) cudaFreeHost(bt->h_rec);
+  if (bt->h_rec) bt->disc->ctx->pinned_free.push_back({bt->h_rec, bt->h_rec_bytes});
   if (bt->timers) for (auto& e : bt->ev) cudaEventDestroy(e);
   delete bt;
 }
@@ -708,57 +733,79 @@ static int launch_dens_cells(aks_batch* bt) {
 }
 
 // the kernel sequence of one SCF step for the problems of bt->cur, on its stream
-static int step_on_lane(aks_batch* bt) {
+// Segments of the step: the multi-lane driver enqueues segment by segment across the lanes, so that every
+// lane has work queued within a few launches (a lane enqueued as a whole would start 60 launches late).
+#define STEP_SEGMENTS 6
+static int step_segment(aks_batch* bt, int seg) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   const BatchDev& b = bt->cur->dev;
   int rc;
-  int ei = 0;
-#define TICK() do { if (bt->timers && bt->cur == &bt->whole) CK(cudaEventRecord(bt->ev[ei++], bt->cur->stream)); } while (0)
-  TICK();
+  const bool tm = bt->timers && bt->cur == &bt->whole;
+#define TICK(i) do { if (tm) CK(cudaEventRecord(bt->ev[i], bt->cur->stream)); } while (0)
+  switch (seg) {
+    case 0:
+      TICK(0);
 #ifdef AKS_EIG_TIMING
-  CK(cudaMemsetAsync(b.eig_dbg, 0, sizeof(long long) * (size_t)bt->cur->B * b.s * b.Lmax * b.nhmax * 8, bt->cur->stream));
+      CK(cudaMemsetAsync(b.eig_dbg, 0, sizeof(long long) * (size_t)bt->cur->B * b.s * b.Lmax * b.nhmax * 8, bt->cur->stream));
 #endif
-  if ((rc = launch_potential(bt, nullptr, nullptr)) != AKS_OK) return rc;
-  TICK();
-  if ((rc = launch_eig(bt)) != AKS_OK) return rc;
-  TICK();
-  k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 0);
-  LAUNCH_CHECK();
-  if (b.eig_margin >= 0) {   // problems whose window could not be certified: solve the rest, repeat
-    k_eig_cert<<<dim3(b.Lmax * b.s, bt->cur->B), EIG_NT, bt->smem_eig, bt->cur->stream>>>(dv, b);
-    LAUNCH_CHECK();
-    if ((rc = launch_eig_pass(bt, 1)) != AKS_OK) return rc;
-    k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 1);
-    LAUNCH_CHECK();
-    bt->eig_dirty = true;
+      if ((rc = launch_potential(bt, nullptr, nullptr)) != AKS_OK) return rc;
+      TICK(1);
+      break;
+    case 1:
+      if ((rc = launch_eig(bt)) != AKS_OK) return rc;
+      TICK(2);
+      break;
+    case 2:
+      k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 0);
+      LAUNCH_CHECK();
+      if (b.eig_margin >= 0) {   // problems whose window could not be certified: solve the rest, repeat
+        k_eig_cert<<<dim3(b.Lmax * b.s, bt->cur->B), EIG_NT, bt->smem_eig, bt->cur->stream>>>(dv, b);
+        LAUNCH_CHECK();
+        if ((rc = launch_eig_pass(bt, 1)) != AKS_OK) return rc;
+        k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 1);
+        LAUNCH_CHECK();
+        bt->eig_dirty = true;
+      }
+      TICK(3);
+      break;
+    case 3:
+      if ((rc = launch_dens_cells(bt)) != AKS_OK) return rc;
+      TICK(4);
+      break;
+    case 4:
+      k_poisson<<<dim3(bt->cur->B, 2), 128, bt->smem_poisson, bt->cur->stream>>>(dv, b, 0, 0);
+      LAUNCH_CHECK();
+      TICK(5);
+      k_linesearch<<<bt->cur->B, LS_NT, 0, bt->cur->stream>>>(dv, b);
+      LAUNCH_CHECK();
+      TICK(6);
+      break;
+    default: {
+      const size_t total = (size_t)b.s * dv.C * dv.Q + (size_t)b.s * dv.G + 2 * (size_t)dv.Nh;
+      const int gx = (int)std::min<size_t>((total + 255) / 256, 1024);
+      k_mix_state<<<dim3(gx, bt->cur->B), 256, 0, bt->cur->stream>>>(dv, b);
+      LAUNCH_CHECK();
+      TICK(9);
+      k_mix_dense<<<dim3(b.ntri, b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b);
+      LAUNCH_CHECK();
+      TICK(10);
+      k_finalize<<<(bt->cur->B + 127) / 128, 128, 0, bt->cur->stream>>>(dv, b);
+      LAUNCH_CHECK();
+      TICK(7);
+    }
   }
-  TICK();
-  if ((rc = launch_dens_cells(bt)) != AKS_OK) return rc;
-  TICK();
-  k_poisson<<<dim3(bt->cur->B, 2), 128, bt->smem_poisson, bt->cur->stream>>>(dv, b, 0, 0);
-  LAUNCH_CHECK();
-  TICK();
-  k_linesearch<<<bt->cur->B, LS_NT, 0, bt->cur->stream>>>(dv, b);
-  LAUNCH_CHECK();
-  TICK();
-  {
-    const size_t total = (size_t)b.s * dv.C * dv.Q + (size_t)b.s * dv.G + 2 * (size_t)dv.Nh;
-    const int gx = (int)std::min<size_t>((total + 255) / 256, 1024);
-    k_mix_state<<<dim3(gx, bt->cur->B), 256, 0, bt->cur->stream>>>(dv, b);
-    LAUNCH_CHECK();
-  }
-  if (bt->timers && bt->cur == &bt->whole) CK(cudaEventRecord(bt->ev[9], bt->cur->stream));
-  k_mix_dense<<<dim3(b.ntri, b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b);
-  LAUNCH_CHECK();
-  if (bt->timers && bt->cur == &bt->whole) CK(cudaEventRecord(bt->ev[10], bt->cur->stream));
-  k_finalize<<<(bt->cur->B + 127) / 128, 128, 0, bt->cur->stream>>>(dv, b);
-  LAUNCH_CHECK();
-  TICK();
 #undef TICK
   return AKS_OK;
 }
-
+// the kernel sequence of one SCF step for the problems of bt->cur, on its stream
+static int step_on_lane(aks_batch* bt) {
+  for (int seg = 0; seg < STEP_SEGMENTS; ++seg) {
+    const int rc = step_segment(bt, seg);
+    if (rc != AKS_OK) return rc;
+  }
+  return AKS_OK;
+}
 // lane views of the batch: options and pointers are taken from bt->dev at every step (they are cheap)
 static void refresh_lanes(aks_batch* bt) {
   bt->whole.dev = bt->dev;
@@ -792,12 +839,16 @@ static int step_launch(aks_batch* bt) {
     bt->forked = true;
   }
   int rc = AKS_OK;
-  for (Lane& ln : bt->lanes) {
-    bt->cur = &ln;
-    if ((rc = step_on_lane(bt)) != AKS_OK) break;
-    CK(cudaEventRecord(ln.done, ln.stream));
-    CK(cudaStreamWaitEvent(ctx->stream, ln.done, 0));
-  }
+  for (int seg = 0; seg < STEP_SEGMENTS && rc == AKS_OK; ++seg)
+    for (Lane& ln : bt->lanes) {
+      bt->cur = &ln;
+      if ((rc = step_segment(bt, seg)) != AKS_OK) break;
+    }
+  if (rc == AKS_OK)
+    for (Lane& ln : bt->lanes) {
+      CK(cudaEventRecord(ln.done, ln.stream));
+      CK(cudaStreamWaitEvent(ctx->stream, ln.done, 0));
+    }
   bt->cur = &bt->whole;
   return rc;
 }
