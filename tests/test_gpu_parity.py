@@ -258,6 +258,39 @@ def test_maximum_ionization_driver():
     bt.close()
 
 
+@pytest.mark.parametrize("case", ["frozen_t", "cation", "no_hartree"])
+def test_deterministic_trajectories(case):
+    """SURVEY 8(c) protocol (ii): without the Brent line search (frozen t), or where it is well conditioned,
+    the run is deterministic -- same iteration count, Etot of every iteration within 1e-10."""
+    from atomickohnsham_b200.solver import Batch
+    from gpu_diag import make_gpu
+    setup = dict(CASES["o_lda"])
+    if case == "frozen_t":
+        setup.update(frozen_t=True, tinit=0.5, scftol=1e-9)
+    elif case == "cation":
+        setup.update(Z=11, N=10, scftol=1e-9)             # Na+: closed shell
+    else:
+        setup.update(Z=4, N=4, hartree=0, ex=None, ec=None, scftol=1e-9)   # non-interacting: converges in 2 steps
+    o = make_oracle(setup)
+    so, ho = o.groundstate()
+    model, disc, alg = make_gpu(setup)
+    bt = Batch([model], disc, alg)
+    final, hist = bt.run(100, history=True)
+    f = final[0]
+    assert f["status"] == 1 and so.stop < setup["scftol"]
+    assert abs(f["niter"] - so.niter) <= (0 if case != "cation" else 2), (f["niter"], so.niter)
+    for it in range(min(f["niter"], so.niter, 12)):
+        assert abs(hist[0][it]["Etot"] - ho[it]["Etot"]) <= 1e-10 * abs(ho[it]["Etot"]), (it, hist[0][it]["Etot"], ho[it]["Etot"])
+        if case == "frozen_t":
+            assert hist[0][it]["t"] == ho[it]["t"] == 0.5
+    assert abs(f["Etot"] - so.energies.Etot) <= 1e-10 * abs(so.energies.Etot)
+    sg = bt.state(0, want_D=False, want_U=False)
+    occ = so.n != 0
+    assert np.array_equal(sg["n"][occ], so.n[occ])
+    assert np.max(np.abs(sg["eps"][occ] - so.eps[occ])) < 5e-8
+    bt.close()
+
+
 def test_c_abi_error_paths():
     """Errors never cross the ABI as exceptions: status codes + aks_last_error."""
     import ctypes as C

@@ -29,7 +29,7 @@ def make_gpu(setup):
     mk = lambda name: aks.NoFunctional(ns) if name is None else aks.BuiltinFunctional(name, ns)
     model = aks.KSEModel(Z=setup["Z"], N=setup["N"], hartree=setup.get("hartree", 1), ex=mk(setup.get("ex")), ec=mk(setup.get("ec")))
     disc = aks.KSEDiscretization(basis, model, lh=setup["lh"], nh=setup["nh"], fem_integration_method=quad, femops=ops)
-    alg = aks.ODA(scftol=setup.get("scftol", 1e-10), tinit=0.6,
+    alg = aks.ODA(scftol=setup.get("scftol", 1e-10), tinit=setup.get("tinit", 0.6), frozen_t=setup.get("frozen_t", False),
                   aufbau=aks.OptimizedAufbau(max_degen=setup.get("max_degen", 2), tol=setup.get("degen_tol", 1e-3)))
     return model, disc, alg
 
