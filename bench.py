@@ -159,6 +159,12 @@ def b200_arm(args):
         units = tot
     total_units, max_ms = float(units[0]), float(units[1])
     value = total_units / (max_ms * 1e-3)
+    per_rank_ms = [ms]
+    if world > 1:   # load imbalance between the ranks' sweeps
+        import torch.distributed as dist
+        allms = [torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}"))
+        per_rank_ms = [float(x) for x in allms]
 
     # ---------------- per-phase device time + roofline of the dominant kernel (rank 0)
     roof, phases = None, None
@@ -278,7 +284,7 @@ def b200_arm(args):
                        "eig_window_refills_in_run": refills, "scftol": "0 during timed steps (fixed work per step)",
                        "l2": "state per GPU (dense D: %.0f MB) exceeds the 126 MB L2; no explicit flush" % (B * 8 * 799 * 799 / 1e6),
                        "tables": "resident before the timed regions (setup is outside the reference's loop too)"},
-            "clocks": clocks, "gpu_launches": launches,
+            "clocks": clocks, "gpu_launches": launches, "per_rank_ms_per_step": [x / args.steps for x in per_rank_ms],
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h_total / args.steps,
                     "what": "Batch() + K x aks_scf_step with host records + aks_get_state_all (eps, n, W of every atom); median of 3",
@@ -310,7 +316,8 @@ def _oracle_for(Z):
 
 
 def cpu_baseline_single(budget_s=15.0):
-    """Oracle (CPU restatement of the reference; Julia is unavailable) on ONE core: Argon, C2."""
+    """Oracle (CPU restatement of the reference; Julia is unavailable) on ONE core: Argon, C2.  Also the
+    per-iteration assembly (a3-a9) and eigensolve (a10) times, the split SURVEY 8(d) asks to report."""
     o = _oracle_for(18)
     st = o.initial_state()
     o.scf_step(st)  # warm-up (includes first-use costs)
@@ -320,8 +327,14 @@ def cpu_baseline_single(budget_s=15.0):
         o.scf_step(st)
         k += 1
     dt = time.perf_counter() - t0
+    ta = time.perf_counter()
+    Har, Vxc, _ = o.hamiltonian_parts(st.D)
+    tb = time.perf_counter()
+    o.find_orbital(Har, Vxc)
+    tc = time.perf_counter()
     return {"value": k / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{k} SCF iterations of Argon (Z=18, C2 discretization) with the numpy/LAPACK oracle, 1 thread"}
+            "sample": f"{k} SCF iterations of Argon (Z=18, C2 discretization) with the numpy/LAPACK oracle, 1 thread",
+            "ms_per_iteration": dt / k * 1e3, "assembly_ms": (tb - ta) * 1e3, "eigensolve_ms": (tc - tb) * 1e3}
 
 
 _W = {}
