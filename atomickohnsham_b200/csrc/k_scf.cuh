@@ -350,11 +350,27 @@ __global__ void __launch_bounds__(DENS_NT, 3) k_dens_cells(DiscDev d, BatchDev b
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* Fc = d.F_loc + (size_t)c * n * n * n;
-    for (int m = warp; m < n; m += DENS_NT / 32) {
-      double acc = 0.0;
-      for (int idx = lane; idx < n * n; idx += 32) acc = fma(Dl[idx], Fc[(size_t)m * n * n + idx], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) b.Bloc_new[(((size_t)p * 2 + slot) * C + c) * n + m] = acc;
+    // a warp owns the rows m = warp, warp + 4, ...: all of them advance together so that up to 8 loads of
+    // the (L2-resident) tensor block are in flight per lane instead of one
+    constexpr int NWD = DENS_NT / 32, MPW = (32 + NWD - 1) / NWD;
+    double acc[MPW];
+#pragma unroll
+    for (int j = 0; j < MPW; ++j) acc[j] = 0.0;
+    for (int idx = lane; idx < n * n; idx += 32) {
+      const double dv = Dl[idx];
+#pragma unroll
+      for (int j = 0; j < MPW; ++j) {
+        const int m = warp + NWD * j;
+        if (m < n) acc[j] = fma(dv, Fc[(size_t)m * n * n + idx], acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < MPW; ++j) {
+      const int m = warp + NWD * j;
+      if (m < n) {   // warp-uniform
+        const double v = warp_sum(acc[j]);
+        if (lane == 0) b.Bloc_new[(((size_t)p * 2 + slot) * C + c) * n + m] = v;
+      }
     }
   }
 }
