@@ -56,7 +56,7 @@ EXPORTS = ["aks_ctx_create", "aks_ctx_destroy", "aks_last_error", "aks_ctx_strea
            "aks_disc_create", "aks_disc_destroy", "aks_batch_create", "aks_batch_destroy",
            "aks_batch_set_oda", "aks_batch_set_aufbau", "aks_batch_set_eig_window", "aks_batch_reset", "aks_scf_step", "aks_scf_run", "aks_get_state", "aks_get_state_all",
            "aks_set_density", "aks_assemble_hartree", "aks_assemble_vxc", "aks_eig_lowest",
-           "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak",
+           "aks_density", "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak",
            "aks_last_phase_ms", "aks_debug_eig_info", "aks_debug_eig_cycles", "aks_debug_eig_refills"]
 
 
@@ -91,6 +91,7 @@ def _load():
     lib.aks_get_state_all.argtypes = [vp, _dp, _dp, _dp]
     lib.aks_set_density.argtypes = [vp, C.c_int32, _dp, _dp, C.c_int32]
     lib.aks_assemble_hartree.argtypes = [vp, C.c_int32, _dp]
+    lib.aks_density.argtypes = [vp, C.c_int32, _dp]
     lib.aks_assemble_vxc.argtypes = [vp, C.c_int32, _dp]
     lib.aks_eig_lowest.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
     lib.aks_exc_energy.argtypes = [vp, C.c_int32, _dp]

@@ -1123,6 +1123,22 @@ extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* 
   return AKS_OK;
 }
 
+extern "C" int aks_density(aks_batch* bt, int32_t prob, double* D) {
+  if (!bt || prob < 0 || prob >= bt->B || !D) return AKS_EINVAL;
+  enter_main(bt);
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const size_t s = bt->dev.s, Nh = dv.Nh;
+  double* dout = nullptr;
+  CK(cudaMallocAsync((void**)&dout, sizeof(double) * s * Nh * Nh, ctx->stream));
+  k_density_dense<<<dim3((unsigned)((Nh + 15) / 16), (unsigned)((Nh + 15) / 16), (unsigned)s), AKS_NT, 0, ctx->stream>>>(dv, bt->dev, prob, dout);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(D, dout, sizeof(double) * s * Nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaFreeAsync(dout, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
 extern "C" int aks_exc_energy(aks_batch* bt, int32_t prob, double* Exc) {
   if (!bt || prob < 0 || prob >= bt->B || !Exc) return AKS_EINVAL;
   enter_main(bt);

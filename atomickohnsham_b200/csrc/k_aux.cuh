@@ -77,6 +77,23 @@ __global__ void __launch_bounds__(AKS_NT) k_grid_from_dense(DiscDev d, BatchDev 
   }
 }
 
+// density!(D, U, n) (src/discretization/density.jl:15-41) of problem p as a dense matrix: the trial density
+// the SCF loop itself never materialises (k_mix_dense folds it into the mixing).  out [s][Nh][Nh].
+__global__ void __launch_bounds__(AKS_NT) k_density_dense(DiscDev d, BatchDev b, int p, double* __restrict__ out) {
+  const int Nh = d.Nh, e = blockIdx.z;
+  const int i = blockIdx.y * 16 + (threadIdx.x >> 4), j = blockIdx.x * 16 + (threadIdx.x & 15);
+  if (i >= Nh || j >= Nh) return;
+  double acc = 0.0;
+  for (int l = 0; l < b.Lp[p]; ++l)
+    for (int k = 0; k < b.nhp[p]; ++k) {
+      const double nk = b.occ[occ_off(b, p, 0, e, l, k)];
+      if (nk == 0.0) continue;
+      const double* u = b.U + orb_off(b, p, e, l, k) * Nh;
+      acc = fma(nk * u[i], u[j], acc);
+    }
+  out[((size_t)e * Nh + i) * Nh + j] = acc;
+}
+
 // Exc of the current (mixed) state of problem p -> out[0]
 __global__ void __launch_bounds__(AKS_NT) k_exc_state(DiscDev d, BatchDev b, int p, double* out) {
   __shared__ double red[AKS_NW + 2];

@@ -207,6 +207,13 @@ class Batch:
         self.ctx.check(_capi.lib.aks_set_density(self.h, prob, _capi.dptr(Dd), _capi.dptr(e), niter))
 
     # ---- step-level hooks ------------------------------------------------------------
+    def density(self, prob=0):
+        """density!(D, U, n): the dense trial density of the last step, (Nh, Nh, nspin)."""
+        d = self.disc
+        D = np.zeros((d.nspin, d.Nh, d.Nh))
+        self.ctx.check(_capi.lib.aks_density(self.h, prob, _capi.dptr(D)))
+        return np.transpose(D, (1, 2, 0))
+
     def assemble_hartree(self, prob=0):
         out = np.zeros((self.disc.Nh, self.disc.Nh))
         self.ctx.check(_capi.lib.aks_assemble_hartree(self.h, prob, _capi.dptr(out)))

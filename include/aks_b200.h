@@ -165,6 +165,9 @@ int aks_assemble_vxc(aks_batch* batch, int32_t prob, double* Vxc);
 /* find_orbital!      (oda/loop.jl:65-77):   lowest nh eigenpairs of every (l,sigma) channel
  * of H[D]; eps (L,nh[,2]), U (Nh,nh,L[,2]); residuals (L,nh[,2]) = ||(H-eps M0)u||_2 or NULL */
 int aks_eig_lowest(aks_batch* batch, int32_t prob, double* eps, double* U, double* residuals);
+/* density!           (density.jl:15-41):    D (Nh,Nh[,2]) = sum n u u^T of the current orbitals and
+ * occupations (the trial density of the last step, before mixing)                         */
+int aks_density(aks_batch* batch, int32_t prob, double* D);
 /* compute_exc_energy (energies.jl:217-233) of the current D                               */
 int aks_exc_energy(aks_batch* batch, int32_t prob, double* Exc);
 /* compute_hartree_energy (energies.jl:96-114) of the current D                            */
