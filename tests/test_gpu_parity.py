@@ -297,6 +297,38 @@ def test_deterministic_trajectories(case):
     bt.close()
 
 
+@pytest.mark.parametrize("p,ncell,npoints,lh,nspin", [(3, 12, 100, 1, 1), (12, 25, 200, 1, 1), (24, 10, 301, 2, 1),
+                                                      (29, 6, 128, 0, 1), (12, 25, 200, 1, 2), (24, 10, 300, 1, 2)])
+def test_other_orders_and_grids(p, ncell, npoints, lh, nspin):
+    """Every template instantiation and fallback: small / large orders (one or two register tiles per lane,
+    k_reduce<8..28>, k_dens_cells<12..32>), node counts that are not a multiple of the TMA chunk, an odd node
+    count (no 16-byte rows: plain staging instead of bulk copies), cell counts that do not fill a chunk."""
+    from atomickohnsham_b200.solver import Batch
+    from gpu_diag import make_gpu
+    setup = {"Z": 4, "N": 4, "mesh": ["exp", 0, 60, ncell + 1, 1.3], "p": p, "npoints": npoints, "lh": lh, "nh": 3,
+             "ex": "lda_x", "ec": "lda_c_pw", "scftol": 1e-10, "nspin": nspin}
+    if nspin == 2:
+        setup.update(Z=2, N=2)   # helium: lithium's bare-Coulomb 2s = 2p (x2 spins) start is decided by rounding
+    o = make_oracle(setup)
+    model, disc, alg = make_gpu(setup)
+    bt = Batch([model, model, model], disc, alg)     # three problems: a partly filled 4-problem CTA
+    st = o.initial_state()
+    for it in range(4):
+        o.scf_step(st)
+        recs = bt.step()
+        assert recs[0] == recs[1] == recs[2]
+        assert abs(recs[0]["Etot"] - st.energies.Etot) <= 1e-10 * abs(st.energies.Etot), (it, recs[0]["Etot"], st.energies.Etot)
+    sg = bt.state(1)
+    M0 = disc.femops.M0
+    for e in range(nspin):
+        for l in range(lh + 1):
+            U = sg["U"][:, :, l, e]
+            assert np.max(np.abs(U.T @ M0 @ U - np.eye(3))) < 1e-10
+    occ = st.n.reshape(sg["n"].shape) != 0
+    assert np.max(np.abs(sg["eps"][occ] - st.eps.reshape(sg["eps"].shape)[occ])) < 1e-7
+    bt.close()
+
+
 def test_c_abi_error_paths():
     """Errors never cross the ABI as exceptions: status codes + aks_last_error."""
     import ctypes as C
