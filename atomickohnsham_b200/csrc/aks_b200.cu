@@ -495,14 +495,14 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   const char* tenv = getenv("AKS_PHASE_TIMERS");
   bt->timers = tenv && tenv[0] == '1';
   if (bt->timers) for (auto& e : bt->ev) CK(cudaEventCreate(&e));
-  // stream lanes (AKS_STREAM_LANES, default 4: measured 2.05 / 1.87 / 1.71 / 1.63 ms per 86-atom step with
-  // 1 / 2 / 4 / 8 lanes; more lanes cost host launch time in the synchronous path); small batches use fewer
+  // stream lanes (AKS_STREAM_LANES, default 8: measured 1.57 / 1.56 / 1.52 / 1.60 / 1.66 ms per 86-atom step
+  // with 4 / 6 / 8 / 12 / 16 lanes); small batches use fewer
   {
     const char* lenv = getenv("AKS_STREAM_LANES");
-    int nl = lenv ? atoi(lenv) : 4;
+    int nl = lenv ? atoi(lenv) : 8;
     if (nl < 1) nl = 1;
-    if (nl > 8) nl = 8;
-    if (bt->B < 8 * nl) nl = bt->B >= 16 ? 2 : 1;
+    if (nl > 16) nl = 16;
+    while (nl > 1 && bt->B < 4 * nl) nl /= 2;   // at least 4 problems (one k_potential CTA column) per lane
     const int NP = potential_np(dv.n, b.s);
     if (!ctx->event_free.empty()) { bt->fork_ev = ctx->event_free.back(); ctx->event_free.pop_back(); }
     else CK(cudaEventCreateWithFlags(&bt->fork_ev, cudaEventDisableTiming));

@@ -291,7 +291,7 @@ def b200_arm(args):
                     "seconds_each": e2e_times},
             "roofline": roof, "phases_ms": phases,
             "phases_note": "per-phase times are measured with the batch on ONE stream (AKS_PHASE_TIMERS); the timed steps "
-                           "run the batch as 4 concurrent stream lanes, so the phases add up to more than ms_per_step", "cpu_baseline": cpu, "sweep_to_convergence": sweep,
+                           "run the batch as 8 concurrent stream lanes, so the phases add up to more than ms_per_step", "cpu_baseline": cpu, "sweep_to_convergence": sweep,
         }
         _RESULT_LINE.append(json.dumps(line))
     if world > 1:
