@@ -18,7 +18,11 @@ def __getattr__(name):
             "OptimizedAufbau": "algorithms", "SmearedAufbau": "algorithms", "FrozenAufbau": "algorithms",
             "parse_shell": "algorithms", "KSEDiscretization": "discretization",
             "groundstate": "solver", "KSESolver": "solver", "KSESolution": "solver", "Batch": "solver",
-            "CallbackSet": "solver", "LogFileCallback": "solver", "LogBook": "solver"}
+            "CallbackSet": "solver", "LogFileCallback": "solver", "LogBook": "solver",
+            "eval_orbital": "postprocess", "eval_density": "postprocess", "eval_hartree": "postprocess",
+            "eval_nuclear": "postprocess", "eval_kinetic_potential": "postprocess", "eval_vxc": "postprocess",
+            "eval_effective_potential": "postprocess", "SanityChecks": "postprocess",
+            "sanity_checks": "postprocess", "maximum_ionization": "sweep"}
     if name in _dev:
         import importlib
         return getattr(importlib.import_module(f".{_dev[name]}", __name__), name)

@@ -318,6 +318,7 @@ class KSESolution:
     D: np.ndarray | None
     W: np.ndarray
     logbook: LogBook | None = None
+    context: tuple | None = None   # (model, discretization), as `sol.context` of the reference
 
     @property
     def eps(self):
@@ -344,7 +345,7 @@ def _solution(batch: Batch, i: int, rec: dict, logbook=None, want_arrays=True):
                                                             else f"ERROR({rec['status']})")
     return KSESolution(solution_name(m.Z, m.N), succ, rec["niter"], rec["stop"],
                        Energies(rec["Etot"], rec["Ekin"], rec["Ecou"], rec["Ehar"], rec["Eexc"]),
-                       st["eps"], st["n"], st.get("U"), st.get("D"), st["W"], logbook)
+                       st["eps"], st["n"], st.get("U"), st.get("D"), st["W"], logbook, (m, batch.disc))
 
 
 def groundstate(model, discretization: KSEDiscretization, alg: ODA, *, maxiter: int = 100, callback=None,

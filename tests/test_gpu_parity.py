@@ -329,6 +329,38 @@ def test_other_orders_and_grids(p, ncell, npoints, lh, nspin):
     bt.close()
 
 
+def test_postprocessing_and_sanity_checks():
+    """The consumers of the path's outputs (postprocess.jl, sanity.jl): hydrogen-like checks with closed forms
+    and the reference's SanityChecks on a converged LDA atom."""
+    import atomickohnsham_b200 as aks
+    from helpers import package_tables
+    basis, ops, quad = package_tables(["exp", 0, 60, 31, 1.3], 10, 400)
+    disc = aks.KSEDiscretization(basis, None, lh=1, nh=3, nspin=1, fem_integration_method=quad, femops=ops)
+    # one electron, no interaction: the exact 1s orbital 2 exp(-r), rho = exp(-2r)/pi
+    h = aks.groundstate(aks.KSEModel(Z=1, N=1, hartree=0), disc, aks.ODA(scftol=1e-10, tinit=0.6))
+    X = np.array([0.1, 0.5, 1.0, 2.0, 4.0])
+    assert abs(h.energies.Etot + 0.5) < 1e-8
+    u = aks.eval_orbital(h, "1s", X)                                  # R_1s(r) = 2 exp(-r), sign free
+    assert np.max(np.abs(np.abs(u) - 2.0 * np.exp(-X))) < 1e-5
+    rho = aks.eval_density(h, X)
+    assert np.max(np.abs(rho - np.exp(-2 * X) / np.pi)) < 1e-6
+    assert np.allclose(aks.eval_nuclear(h, X), -1.0 / X)
+    assert np.allclose(aks.eval_hartree(h, X), 1.0 / 60.0)          # hartree = 0: boundary term only
+    # neon, LDA: sanity checks as the reference reports them
+    ne = aks.groundstate(aks.LDA(Z=10, N=10), disc, aks.ODA(scftol=1e-10, tinit=0.6))
+    sc = aks.sanity_checks(ne)
+    assert ne.success == "SUCCESS"
+    assert abs(sc.energy_balance) < 1e-9 and abs(sc.electron_count_error) < 1e-12
+    assert abs(sc.density_norm_error) < 1e-6 and sc.orthonormality_error < 1e-10
+    assert 0.95 < sc.virial_ratio < 1.05
+    # V_H -> N/r outside the atom; v_xc < 0; effective potential assembled from its parts
+    far = np.array([20.0, 30.0])
+    assert np.max(np.abs(aks.eval_hartree(ne, far) - 10.0 / far)) < 1e-6
+    assert np.all(aks.eval_vxc(ne, X) < 0)
+    veff = aks.eval_effective_potential(ne, 1, X)
+    assert np.allclose(veff, -10.0 / X + 1.0 / X ** 2 + aks.eval_hartree(ne, X) + aks.eval_vxc(ne, X))
+
+
 def test_c_abi_error_paths():
     """Errors never cross the ABI as exceptions: status codes + aks_last_error."""
     import ctypes as C

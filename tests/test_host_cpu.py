@@ -187,3 +187,18 @@ def test_frozen_and_smeared_aufbau_host_and_oracle():
     assert hot[1, 1] > cold[1, 1]
     fz, _ = _O(ODAOptions(aufbau_kind="frozen", nfix=n)).aufbau(eps + 100.0, None, 5)
     assert np.array_equal(fz, n)
+
+
+def test_host_xc_matches_oracle():
+    """The numpy LDA potentials used by post-processing (eval_vxc) against the oracle's restatement."""
+    from atomickohnsham_b200._xc_host import vxc_polarised, vxc_unpolarised
+    from oracle import xc as oxc
+    rng = np.random.default_rng(3)
+    rho = np.concatenate([[0.0, 1e-30], 10.0 ** rng.uniform(-12, 3, 200)])
+    ref = oxc.slater_vrho(rho) + oxc.pw92_vrho(rho)
+    assert np.allclose(vxc_unpolarised(rho, "lda_x", "lda_c_pw"), ref, rtol=1e-12, atol=1e-300)
+    ru, rd = rho, rho[::-1].copy()
+    vu, vd = vxc_polarised(ru, rd, "lda_x", "lda_c_pw")
+    xu, xd = oxc.slater_vrho_pol(ru, rd)
+    cu, cd = oxc.pw92_vrho_pol(ru, rd)
+    assert np.allclose(vu, xu + cu, rtol=1e-11, atol=1e-300) and np.allclose(vd, xd + cd, rtol=1e-11, atol=1e-300)
