@@ -443,6 +443,36 @@ def test_eigenpair_window_is_transparent():
                 assert np.max(np.abs(G - np.eye(nh))) < 1e-10, (margin, zs[i], l)
 
 
+def test_batches_come_and_go_bit_reproducibly():
+    """Repeated create / step / destroy cycles (pooled memory, recycled streams) give bit-identical records,
+    and two batches alive on one context equal the same problems in a single batch (stream lanes included)."""
+    from bench import build_disc
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.solver import Batch
+    from atomickohnsham_b200.sweep import periodic_table_models
+    disc = build_disc(0)
+    models, lhs, nhs = periodic_table_models(range(1, 87))
+    alg = aks.ODA(scftol=1e-10, tinit=0.6)
+    ref = None
+    for _ in range(8):
+        bt = Batch(models, disc, alg, lh=lhs, nh=nhs)
+        for _ in range(6):
+            recs = bt.step()
+        sig = tuple(r["Etot"] for r in recs)
+        ref = ref or sig
+        assert sig == ref
+        bt.close()
+    b1 = Batch(models[:40], disc, alg, lh=lhs[:40], nh=nhs[:40])
+    b2 = Batch(models[40:], disc, alg, lh=lhs[40:], nh=nhs[40:])
+    for _ in range(5):
+        b1.step_async()
+        b2.step_async()
+    r12 = b1.step() + b2.step()
+    assert tuple(r["Etot"] for r in r12) == ref
+    b1.close()
+    b2.close()
+
+
 def test_sweep_full_size_properties():
     """C5 at full size: properties that need no oracle -- electron count, orthonormality,
     energy balance, aufbau monotonicity, virial-like sanity (reference SanityChecks)."""
