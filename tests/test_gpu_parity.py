@@ -182,6 +182,50 @@ def test_reference_goldens_through_the_c_abi():
     bt.close()
 
 
+@pytest.mark.parametrize("name", ["hydrogen_rhf", "hydrogen_slater", "hydrogen_bare", "readme_hydrogen"])
+def test_hydrogen_goldens_through_the_c_abi(name):
+    """test/hydrogen.jl:55-116,138-171 and README.md:57-84 against the CUDA path (not the oracle)."""
+    from helpers import load_golden
+    g = load_golden("scf_goldens.json")[name]
+    bt, *_ = gpu_batch(g["setup"])
+    final, _ = bt.run(g["setup"].get("maxiter", 100))
+    f = final[0]
+    assert f["status"] == 1 and f["stop"] < g["setup"]["scftol"]
+    for k in ("Ekin", "Ecou", "Ehar", "Eexc", "Etot"):
+        if k in g:
+            assert abs(f[k] - g[k]) < g["tol"], k
+    st = bt.state(0, want_D=False, want_U=False)
+    if "eps_1s" in g:
+        assert abs(st["eps"][0, 0, 0] - g["eps_1s"]) < g.get("eps_tol", 1e-9)
+        assert st["n"][0, 0, 0] == 1.0
+    if "eps" in g:
+        for key, val in g["eps"].items():
+            l, k = map(int, key.split(","))
+            assert abs(st["eps"][l, k, 0] - val) < g["tol"]
+    if "niter" in g:
+        assert abs(f["niter"] - g["niter"]) <= 4      # chaotic Brent tail (SURVEY 0.3)
+    bt.close()
+
+
+@pytest.mark.parametrize("name", ["oxygen_lda", "oxygen_x", "oxygen_none"])
+def test_oxygen_reference_results_through_the_c_abi(name):
+    """examples/functional comparison/{lda,lda_x,none}/results.txt: final energies, levels and occupations."""
+    from helpers import load_golden
+    g = load_golden("trajectories.json")[name]
+    bt, *_ = gpu_batch(g["setup"])
+    final, _ = bt.run(100)
+    r = g["results"]
+    assert final[0]["status"] == 1
+    assert abs(final[0]["Etot"] - r["Etot"]) < 1e-9 * abs(r["Etot"])
+    assert abs(final[0]["niter"] - r["niter"]) <= 6
+    st = bt.state(0, want_D=False, want_U=False)
+    gold = {lab: (e, n) for lab, e, n in r["orbitals"]}
+    for lab, (l, k) in {"1s": (0, 0), "2s": (0, 1), "2p": (1, 0)}.items():
+        assert abs(st["eps"][l, k, 0] - gold[lab][0]) < 2e-7 * max(1.0, abs(gold[lab][0])), lab
+        assert st["n"][l, k, 0] == gold[lab][1]
+    bt.close()
+
+
 def test_batch_is_deterministic_and_problem_independent():
     """A problem's trajectory must not depend on its batch neighbours; runs are bit-reproducible."""
     import atomickohnsham_b200 as aks
