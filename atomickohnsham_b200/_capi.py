@@ -56,7 +56,7 @@ EXPORTS = ["aks_ctx_create", "aks_ctx_destroy", "aks_last_error", "aks_ctx_strea
            "aks_disc_create", "aks_disc_destroy", "aks_batch_create", "aks_batch_destroy",
            "aks_batch_set_oda", "aks_batch_set_aufbau", "aks_batch_set_eig_window", "aks_batch_reset", "aks_scf_step", "aks_scf_run", "aks_get_state", "aks_get_state_all",
            "aks_set_density", "aks_assemble_hartree", "aks_assemble_vxc", "aks_eig_lowest",
-           "aks_density", "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak",
+           "aks_density", "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak", "aks_measure_dmma_peak",
            "aks_last_phase_ms", "aks_debug_eig_info", "aks_debug_eig_cycles", "aks_debug_eig_refills"]
 
 
@@ -99,6 +99,7 @@ def _load():
     lib.aks_launch_count.argtypes = [vp]
     lib.aks_launch_count.restype = C.c_int64
     lib.aks_measure_fp64_peak.argtypes = [vp, _dp]
+    lib.aks_measure_dmma_peak.argtypes = [vp, _dp]
     lib.aks_last_phase_ms.argtypes = [vp, _dp]
     lib.aks_debug_eig_info.argtypes = [vp, _i32p]
     lib.aks_debug_eig_cycles.argtypes = [vp, _ip]
@@ -147,6 +148,11 @@ class Context:
     def fp64_peak_tflops(self) -> float:
         v = C.c_double()
         self.check(lib.aks_measure_fp64_peak(self.h, C.byref(v)))
+        return v.value
+
+    def dmma_peak_tflops(self) -> float:
+        v = C.c_double()
+        self.check(lib.aks_measure_dmma_peak(self.h, C.byref(v)))
         return v.value
 
     def close(self):

@@ -1201,6 +1201,36 @@ extern "C" int aks_debug_eig_info(aks_batch* bt, int32_t* info) {
 }
 
 // ------------------------------------------------------------------------------------ FP64 peak
+extern "C" int aks_measure_dmma_peak(aks_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return AKS_EINVAL;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+  double* dout = nullptr;
+  CK(cudaMalloc((void**)&dout, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0, ctx->stream));
+    k_dmma_peak<<<blocks, threads, 0, ctx->stream>>>(dout, iters);
+    LAUNCH_CHECK();
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    // per warp and iteration: 8 MMAs of 8*8*4 FMAs
+    const double flops = 2.0 * 256.0 * 8.0 * (double)iters * blocks * (threads / 32);
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dout);
+  *tflops = best;
+  return AKS_OK;
+}
+
 extern "C" int aks_measure_fp64_peak(aks_ctx* ctx, double* tflops) {
   if (!ctx || !tflops) return AKS_EINVAL;
   cudaDeviceProp prop;

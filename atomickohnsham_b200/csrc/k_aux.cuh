@@ -177,3 +177,21 @@ __global__ void k_fp64_peak(double* out, int iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
+
+// FP64 tensor-core throughput probe: mma.sync m8n8k4 f64, 8 independent accumulator tiles per warp
+__global__ void k_dmma_peak(double* out, int iters) {
+  double a = 1.0 + (threadIdx.x & 31) * 1e-9, b = 0.999999;
+  double c[8][2];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { c[t][0] = 1e-7 * t; c[t][1] = 2e-7 * t; }
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[t][0]), "+d"(c[t][1]) : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) s += c[t][0] + c[t][1];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}

@@ -189,6 +189,8 @@ int64_t aks_launch_count(const aks_ctx* ctx);
 /* sustained FP64 FMA throughput of the device in TFLOP/s (register-resident DFMA chains);
  * the FP64 roofline denominator, which MEASURED_PEAKS.json does not carry                 */
 int aks_measure_fp64_peak(aks_ctx* ctx, double* tflops);
+/* the same for the FP64 tensor-core path (mma.sync m8n8k4 f64)                                */
+int aks_measure_dmma_peak(aks_ctx* ctx, double* tflops);
 /* per-phase device time of the LAST aks_scf_step in ms: {potential, eigensolve, aufbau,
  * density, poisson, linesearch, mix, k_mix_dense alone, k_potential alone, k_xc alone}; valid only if
  * AKS_PHASE_TIMERS=1 in the environment (the batch then runs on one stream instead of its lanes) */
