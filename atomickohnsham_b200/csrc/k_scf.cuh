@@ -288,9 +288,13 @@ __global__ void __launch_bounds__(DENS_NT, 3) k_dens_cells(DiscDev d, BatchDev b
       const int gi = d.l2g[c * n + i];
       if (gi >= 0) v = b.U[orb_off(b, p, L.e[o], L.l[o], L.k[o]) * d.Nh + gi];
     }
-    us[idx] = v;
+    us[idx] = v * sqrt(L.n[o]);   // occupation folded in: rho = sum_o (sqrt(n_o) psi_o)^2, D_loc = us^T us
   }
   __syncthreads();
+  // the list is ordered by spin (density! order: sigma, k, l): orbitals [0, cnt_up) have sigma = 0
+  int cnt_up = cnt;
+  for (int o = 0; o < cnt; ++o)
+    if (L.e[o] == 1) { cnt_up = o; break; }
   const double inv1 = d.inv1[c], inv2 = d.inv2[c];
   const bool has_xc = (b.ex[p] != 0) || (b.ec[p] != 0);
   double corr = 0.0;
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(DENS_NT, 3) k_dens_cells(DiscDev d, BatchDev b
       gb[i] = (i < n && hb) ? d.Pg[(size_t)i * d.Qs + qb] : 0.0;
     }
     double ra0 = 0.0, ra1 = 0.0, rb0 = 0.0, rb1 = 0.0;
-    for (int o = 0; o < cnt; ++o) {
+    auto psi2 = [&](int o, double& ra, double& rb) {
       const double2* uo = reinterpret_cast<const double2*>(us + (size_t)o * NMAX);   // broadcast LDS.128
       double pa0 = 0.0, pa1 = 0.0, pb0 = 0.0, pb1 = 0.0;
 #pragma unroll
@@ -318,9 +322,11 @@ __global__ void __launch_bounds__(DENS_NT, 3) k_dens_cells(DiscDev d, BatchDev b
         pb1 = fma(u2.y, gb[2 * i + 1], pb1);
       }
       const double psa = pa0 + pa1, psb = pb0 + pb1;
-      const double ta = L.n[o] * psa * psa, tb = L.n[o] * psb * psb;
-      if (L.e[o] == 0) { ra0 += ta; rb0 += tb; } else { ra1 += ta; rb1 += tb; }
-    }
+      ra = fma(psa, psa, ra);
+      rb = fma(psb, psb, rb);
+    };
+    for (int o = 0; o < cnt_up; ++o) psi2(o, ra0, rb0);
+    for (int o = cnt_up; o < cnt; ++o) psi2(o, ra1, rb1);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int q = h ? qb : qa;
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(DENS_NT, 3) k_dens_cells(DiscDev d, BatchDev b
     for (int idx = threadIdx.x; idx < n * n; idx += DENS_NT) {
       const int i = idx / n, j = idx - i * n;
       double v = 0.0;
-      for (int o = 0; o < cnt; ++o) v = fma(L.n[o] * us[(size_t)o * NMAX + i], us[(size_t)o * NMAX + j], v);
+      for (int o = 0; o < cnt; ++o) v = fma(us[(size_t)o * NMAX + i], us[(size_t)o * NMAX + j], v);
       Dl[idx] = v;
     }
     __syncthreads();

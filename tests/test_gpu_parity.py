@@ -80,7 +80,7 @@ def test_step_level_parity_identical_D(name):
         assert rel(Dg, np.asarray(detail["Dtrial"]).reshape(Dg.shape)) < 1e-7
     eo = st.energies
     for k, v in (("Etot", eo.Etot), ("Ekin", eo.Ekin), ("Ecou", eo.Ecou), ("Ehar", eo.Ehar), ("Eexc", eo.Eexc)):
-        tol = 1e-10 if k == "Etot" else 2e-9    # components follow t, which sits on a flat minimum
+        tol = 1e-10 if k == "Etot" else 5e-9    # components follow t, which sits on a flat minimum (dt ~ 1e-8)
         assert abs(rec[k] - v) <= tol * max(1.0, abs(v)), (k, rec[k], v)
     sg = bt.state(0)
     assert np.allclose(sg["n"], st.n, atol=1e-6)
