@@ -81,7 +81,9 @@ struct BatchDev {
   int* warm;         // [B]  1 once eps/U hold a previous solution
   int* kact;         // [B][s][Lmax]  eigenpairs per channel solved in the first pass of the next step
   int* kdone;        // [B][s][Lmax]  eigenpairs per channel that are current (solved for the last H)
-  int* redo;         // [B]  aufbau could not be certified on the window: solve the rest, repeat
+  int* redo;         // [B]  aufbau could not be certified on the window: solve the missing levels, repeat
+  int* kreq;         // [B][s][Lmax]  levels per channel the refill pass has to reach (k_eig_cert)
+  int* full_refill;  // [B]  the aufbau ran out of solved levels: refill every channel completely
   int* redo_cnt;     // [B]  how often that happened (diagnostic)
   double* e_cert;    // [B]  shift of the window certificate: last level the aufbau examined + degen_tol
   int* degen3;       // [B]  > 2-fold degeneracy met by the (not yet certified) aufbau

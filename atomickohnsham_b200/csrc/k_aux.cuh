@@ -161,7 +161,7 @@ __global__ void k_window_full(BatchDev b, int p0, int np) {
     b.kdone[(size_t)p0 * per + i] = b.nhmax;
     for (int h = 0; h < AKS_KHIST; ++h) b.khist[((size_t)p0 * per + i) * AKS_KHIST + h] = 0;
   }
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) b.redo[p0 + i] = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < np; i += gridDim.x * blockDim.x) { b.redo[p0 + i] = 0; b.full_refill[p0 + i] = 0; }
 }
 __global__ void k_set_redo(BatchDev b, int v) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < b.B; i += gridDim.x * blockDim.x) b.redo[i] = v;

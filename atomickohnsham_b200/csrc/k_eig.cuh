@@ -613,7 +613,8 @@ __device__ __forceinline__ bool eig_window(const BatchDev& b, int p, size_t chan
   if (mode == 0) { klo = 0; khi = min(nhp, b.kact[chan]); }
   else {
     if (b.redo[p] == 0) return false;
-    klo = b.kdone[chan]; khi = nhp;
+    klo = b.kdone[chan];
+    khi = (mode == 1) ? min(nhp, b.kreq[chan]) : nhp;   // refill: exactly the levels the certificate missed
   }
   return klo < khi;
 }
@@ -642,7 +643,7 @@ k_eig(DiscDev d, BatchDev b, int mode) {
         if (threadIdx.x == 0) b.eps_new[chan0 * b.nhmax + k] = AKS_EPS_MISSING;
         return;
       }
-    } else if (b.redo[p] == 0 || k < b.kdone[chan0]) return;
+    } else if (b.redo[p] == 0 || k < b.kdone[chan0] || (mode == 1 && k >= b.kreq[chan0])) return;
   }
   extern __shared__ double sm[];
   const int C = d.C, nb = d.nb;
@@ -674,12 +675,16 @@ k_eig(DiscDev d, BatchDev b, int mode) {
   bool from_warm = false, need_start = false, certified = false, converged = false, refined = false;
   // distance to the neighbouring levels of the previous step: RQI converges cubically, so an
   // eigenvalue update below 1e-10 of it means the current vector is already converged
+  // Only eigenvalues of the LAST step qualify: levels outside the window keep older values, and an
+  // overestimated gap would end the iteration early (eigenvector error ~ update / gap).  So the estimate is
+  // used in the window pass only, from neighbours that are inside the window themselves.
   double gap_est = 0.0;
-  if (have_prev) {
+  if (have_prev && mode == 0) {
     const double ep = eps_ch[k];
+    const int kwin = min(nhp, b.kact[chan]);
     gap_est = DBL_MAX;
     if (k > 0) gap_est = fmin(gap_est, fabs(ep - eps_ch[k - 1]));
-    if (k + 1 < nhp) gap_est = fmin(gap_est, fabs(eps_ch[k + 1] - ep));
+    if (k + 1 < kwin) gap_est = fmin(gap_est, fabs(eps_ch[k + 1] - ep));
     if (!(gap_est < 1e300)) gap_est = 0.0;
   }
 
@@ -893,12 +898,17 @@ k_eig(DiscDev d, BatchDev b, int mode) {
 __global__ void __launch_bounds__(EIG_NT, (EIG_NT == 128) ? 4 : 2)
 k_eig_cert(DiscDev d, BatchDev b) {
   const int ch = blockIdx.x, p = blockIdx.y;
-  if (b.status[p] != 0 || b.redo[p] != 0) return;
+  if (b.status[p] != 0) return;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
   if (l >= b.Lp[p]) return;
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
+  if (b.full_refill[p]) {   // the fill ran out of solved levels (k_aufbau): everything that is left
+    if (threadIdx.x == 0) b.kreq[chan] = b.nhp[p];
+    return;
+  }
   const int nhp = b.nhp[p], kd = min(nhp, b.kdone[chan]);
-  if (kd >= nhp) return;
+  if (threadIdx.x == 0) b.kreq[chan] = kd;
+  if (kd >= nhp || b.aufbau_kind != 0 || b.redo[p] != 0) return;   // nothing truncated / occupations do not depend on eps
   extern __shared__ double sm[];
   const int C = d.C, nb = d.nb;
   EigShared S;
@@ -911,6 +921,9 @@ k_eig_cert(DiscDev d, BatchDev b) {
     int below = 0;
     for (int k = 0; k < kd; ++k) below += (b.eps_new[chan * b.nhmax + k] < sigma);
     if (S.cntg[0] > below) {
+      // exactly cnt - below unsolved levels lie below e_cert.  Once they are solved the aufbau is final: more
+      // low candidates can only lower the last level it examines, so e_cert still bounds the unsolved rest.
+      b.kreq[chan] = min(nhp, kd + (S.cntg[0] - below));
       if (atomicExch(&b.redo[p], 1) == 0) b.redo_cnt[p] += 1;
     }
   }

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b, int mode) 
     __syncwarp();
     if (lane == 0) {
       b.redo[p] = 0;
+      b.full_refill[p] = 0;
       b.degen[p] = 0;
       int cnt = 0;
       int* elk = b.occ_elk + ((size_t)p * 2) * AKS_MAXORB;
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(32) k_aufbau(DiscDev d, BatchDev b, int mode) 
     bool redo = false;
     if (mode == 0 && b.eig_margin >= 0) {
       redo = !(e_last < 0.5 * AKS_EPS_MISSING);
+      b.full_refill[p] = redo ? 1 : 0;
       b.e_cert[p] = e_last + b.degen_tol;
     }
     b.redo[p] = redo ? 1 : 0;
