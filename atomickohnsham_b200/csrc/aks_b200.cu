@@ -440,7 +440,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk) ZB(double, Hfull, B * s * L * C * n * n)
   ZB(double, eps, B * s * L * nh) ZB(double, eps_new, B * s * L * nh) ZB(double, U, B * s * L * nh * Nh)
   ZB(int, eig_info, B * s * L * nh) ZB(long long, eig_dbg, B * s * L * nh * 8) ZB(double, red, B * s * L * C * (6 * (n - 2) + 4))
-  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * C * 6) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, kreq, B * s * L) ZB(int, full_refill, B) ZB(int, redo_cnt, B) ZB(double, e_cert, B) ZB(int, degen3, B) ZB(double, nfix, B * s * L * nh) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
+  ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * C * 6) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, kreq, B * s * L) ZB(int, full_refill, B) ZB(int, cert_cnt, B * s * L) ZB(int, redo_cnt, B) ZB(double, e_cert, B) ZB(int, degen3, B) ZB(double, nfix, B * s * L * nh) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
   ZB(double, ecou_orb, B * s * L * nh) ZB(double, occ, B * 2 * s * L * nh) ZB(int, degen, B) ZB(int, occ_cnt, B * 2) ZB(int, occ_elk, B * 2 * AKS_MAXORB) ZB(double, occ_n, B * 2 * AKS_MAXORB)
   ZB(int, degen_idx, B * 2) ZB(double, degen_n, B * 4) ZB(double, rho_q_new, B * 2 * s * C * Q)
   ZB(double, rho_y_new, B * 2 * s * G) ZB(double, corr_part, B * 2 * C) ZB(double, Bloc_new, B * 2 * C * n)

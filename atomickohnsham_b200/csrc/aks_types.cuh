@@ -84,6 +84,7 @@ struct BatchDev {
   int* redo;         // [B]  aufbau could not be certified on the window: solve the missing levels, repeat
   int* kreq;         // [B][s][Lmax]  levels per channel the refill pass has to reach (k_eig_cert)
   int* full_refill;  // [B]  the aufbau ran out of solved levels: refill every channel completely
+  int* cert_cnt;     // [B][s][Lmax]  #{eigenvalues < e_cert} of the channel (k_eig_cert)
   int* redo_cnt;     // [B]  how often that happened (diagnostic)
   double* e_cert;    // [B]  shift of the window certificate: last level the aufbau examined + degen_tol
   int* degen3;       // [B]  > 2-fold degeneracy met by the (not yet certified) aufbau

@@ -731,7 +731,20 @@ k_eig(DiscDev d, BatchDev b, int mode) {
   };
 
   double* Xt = b.Xt + (chan * b.nhmax + k) * (size_t)(nb * C + C);
-  if (have_prev && b.stop[p] < 0.3) {
+  // refill pass after a failed certificate: the missing levels lie between the last solved level of the
+  // channel and e_cert, and the certificate's count is a witness for the upper end -- start from that bracket
+  bool bracketed = false;
+  if (mode == 1 && b.full_refill[p] == 0) {
+    const int kd = b.kdone[chan];
+    if (kd >= 1 && k >= kd) {
+      const double el = b.eps_new[chan * b.nhmax + kd - 1];
+      lo = el - fmax(1e-8 * fabs(el), 1e-12); clo = kd - 1;
+      hi = b.e_cert[p]; chi = b.cert_cnt[chan];
+      bracketed = (lo < hi) && (chi >= k + 1);
+      if (!bracketed) { lo = -DBL_MAX; hi = DBL_MAX; clo = chi = -1; }
+    }
+  }
+  if (have_prev && b.stop[p] < 0.3 && !bracketed) {
     // ---- warm start: previous eigenvector, already in reduced coordinates (k_eig_init);
     // its Rayleigh quotient with the new H~ is the first shift
     for (int i = threadIdx.x; i < nb * C; i += blockDim.x) S.x.t[i] = Xt[i];
@@ -920,6 +933,7 @@ k_eig_cert(DiscDev d, BatchDev b) {
   if (threadIdx.x == 0) {
     int below = 0;
     for (int k = 0; k < kd; ++k) below += (b.eps_new[chan * b.nhmax + k] < sigma);
+    b.cert_cnt[chan] = S.cntg[0];
     if (S.cntg[0] > below) {
       // exactly cnt - below unsolved levels lie below e_cert.  Once they are solved the aufbau is final: more
       // low candidates can only lower the last level it examines, so e_cert still bounds the unsolved rest.
