@@ -298,12 +298,20 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
     const int nbC = nb * C;
     const double* Rj = R + c;      // field td, advanced by C per step
     double* Fj = F + c;
+    // software pipelined: the six table values of step j + 1 are requested before the pivot recurrence of
+    // step j (a division and four dependent FMAs) is evaluated
+    double n_td = Rj[0], n_te = 0.0, n_h0 = Rj[2 * nbC], n_h1 = Rj[3 * nbC], n_m0 = Rj[4 * nbC], n_m1 = Rj[5 * nbC];
     for (int j = 0; j < nb; ++j, Rj += C, Fj += C) {
-      const double tdj = Rj[0] - sigma;
+      const double c_td = n_td, c_te = n_te, c_h0 = n_h0, c_h1 = n_h1, c_m0 = n_m0, c_m1 = n_m1;
+      if (j + 1 < nb) {
+        n_td = Rj[C]; n_te = Rj[nbC]; n_h0 = Rj[2 * nbC + C]; n_h1 = Rj[3 * nbC + C];
+        n_m0 = Rj[4 * nbC + C]; n_m1 = Rj[5 * nbC + C];
+      }
+      const double tdj = c_td - sigma;
       scale = fmax(scale, fabs(tdj));
       double lj = 0.0, dj = tdj;
       if (j > 0) {
-        const double te = Rj[nbC - C];
+        const double te = c_te;
         lj = te * dprev_inv;
         dj = tdj - lj * te;
       }
@@ -311,8 +319,8 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
       if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
       neg += (dj < 0.0);
       const double dinv = 1.0 / dj;
-      const double g0 = Rj[2 * nbC] - sigma * Rj[4 * nbC];
-      const double g1 = Rj[3 * nbC] - sigma * Rj[5 * nbC];
+      const double g0 = c_h0 - sigma * c_m0;
+      const double g1 = c_h1 - sigma * c_m1;
       const double y0 = g0 - lj * y0p, y1 = g1 - lj * y1p;
       s00 = fma(y0 * dinv, y0, s00);
       s10 = fma(y1 * dinv, y0, s10);
