@@ -335,6 +335,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
     }
     if (store) {  // W = L^-T D^-1 y
       double w0n = 0.0, w1n = 0.0;
+#pragma unroll 4
       for (int j = nb - 1; j >= 0; --j) {
         double w0 = F[(2 * nb + j) * C + c], w1 = F[(3 * nb + j) * C + c];
         if (j < nb - 1) {
@@ -363,6 +364,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
       int neg = 0;
       for (int cc = 0; cc < C; ++cc) neg += S.negc[cc];
       double dinvp = 0.0, offprev = 0.0, scale = 0.0;
+#pragma unroll 4
       for (int j = 0; j < tw; ++j) {
         const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
         scale = fmax(scale, fabs(diag));
@@ -382,6 +384,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
     } else if (threadIdx.x == 32) {
       int neg = 0;
       double dinvn = 0.0, offnext = 0.0, scale = 0.0;
+#pragma unroll 4
       for (int j = m - 1; j > tw; --j) {
         const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
         scale = fmax(scale, fabs(diag));
@@ -416,6 +419,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
     for (int cc = 0; cc < C; ++cc) neg += ngc[cc];
     double dinvp = 0.0, offprev = 0.0, dinvn = 0.0, offnext = 0.0, scale = 0.0;
     const int nup = m - 1 - tw;  // rows of the bottom sweep
+#pragma unroll 2
     for (int q = 0; q < max(tw, nup); ++q) {
       if (q < tw) {
         const int j = q;
@@ -459,6 +463,7 @@ __device__ __forceinline__ void eig_solve(const EigShared& S, int C, int nb) {
     if (c < C) {
       const double* F = S.fac;
       double t0 = 0.0, t1 = 0.0, zp = 0.0;
+#pragma unroll 4
       for (int j = 0; j < nb; ++j) {
         const double rj = S.r.t[j * C + c];
         t0 = fma(F[(2 * nb + j) * C + c], rj, t0);
@@ -468,6 +473,7 @@ __device__ __forceinline__ void eig_solve(const EigShared& S, int C, int nb) {
         zp = z;
       }
       double zn = 0.0;
+#pragma unroll 4
       for (int j = nb - 1; j >= 0; --j) {
         double z = S.y.t[j * C + c] * F[j * C + c];
         if (j < nb - 1) z -= F[(nb + j + 1) * C + c] * zn;
@@ -540,6 +546,7 @@ __device__ __forceinline__ void eig_apply_red(const EigShared& S, int C, int nb,
     const double xR = (c < C - 1) ? in.h[c] : 0.0, xL = (c > 0) ? in.h[c - 1] : 0.0;
     const int o0 = which ? 2 * nb : 4 * nb, o1 = which ? 3 * nb : 5 * nb;
     double p0 = 0.0, p1 = 0.0, xprev = 0.0, xj = in.t[c];
+#pragma unroll 4
     for (int j = 0; j < nb; ++j) {
       const double xnext = (j + 1 < nb) ? in.t[(j + 1) * C + c] : 0.0;
       const double c0 = R[(o0 + j) * C + c], c1 = R[(o1 + j) * C + c];
