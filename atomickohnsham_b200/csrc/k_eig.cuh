@@ -283,6 +283,18 @@ __host__ __device__ inline size_t eig_smem_bytes(int C, int nb, int Nh) {
 
 #define EIG_NG 6   // shifts evaluated concurrently in the count-only states (groups of C threads)
 
+// Reciprocal of a pivot on the sequential critical path: hardware seed + two Newton steps (1 ulp), about half
+// the dependent FP64 operations of the correctly rounded division.  Pivots are clamped away from zero before.
+__device__ __forceinline__ double pivot_rcp(double dval) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(dval));
+  double err = fma(-dval, x, 1.0);
+  x = fma(x, err, x);
+  err = fma(-dval, x, 1.0);
+  x = fma(x, err, x);
+  return x;
+}
+
 // ---- factor T(sigma) for up to EIG_NG shifts at once: thread t = g*C + c handles cell c of shift g.
 // store != 0 (only with ng == 1): keep the factors of shift 0 for eig_solve.  Inertia counts -> S.cntg[g].
 __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, int ng, double sigma, int store) {
@@ -318,7 +330,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
       const double pivmin = fmax(scale * 4.9e-32, pivmin0);
       if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
       neg += (dj < 0.0);
-      const double dinv = 1.0 / dj;
+      const double dinv = pivot_rcp(dj);
       const double g0 = c_h0 - sigma * c_m0;
       const double g1 = c_h1 - sigma * c_m1;
       const double y0 = g0 - lj * y0p, y1 = g1 - lj * y1p;
@@ -373,7 +385,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
         const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
         if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
         neg += (dj < 0.0);
-        dinvp = 1.0 / dj;
+        dinvp = pivot_rcp(dj);
         S.tri_di[j] = dinvp;
         if (j > 0) S.tri_l[j - 1] = l;
         offprev = sc[3 * (j + 1) + 1];
@@ -393,7 +405,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
         const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
         if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
         neg += (dj < 0.0);
-        dinvn = 1.0 / dj;
+        dinvn = pivot_rcp(dj);
         S.tri_di[j] = dinvn;
         if (j < m - 1) S.tri_l[j] = u;
         offnext = sc[3 * j + 1];
@@ -408,7 +420,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
       double gam = diag - S.xh[0] - S.xh[1];
       const double pivmin = fmax(fabs(diag) * 4.9e-32, DBL_MIN * 1e8);
       if (fabs(gam) < pivmin) gam = (gam < 0.0) ? -pivmin : pivmin;
-      S.tri_di[tw] = 1.0 / gam;
+      S.tri_di[tw] = pivot_rcp(gam);
       S.cntg[0] = S.negc[C] + S.negc[C + 1] + (gam < 0.0);
     }
   } else if (c == 0 && g < ng) {
@@ -430,7 +442,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
         const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
         if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
         neg += (dj < 0.0);
-        dinvp = 1.0 / dj;
+        dinvp = pivot_rcp(dj);
         offprev = sc[3 * (j + 1) + 1];
       }
       if (q < nup) {
@@ -442,7 +454,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
         const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
         if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
         neg += (dj < 0.0);
-        dinvn = 1.0 / dj;
+        dinvn = pivot_rcp(dj);
         offnext = sc[3 * j + 1];
       }
     }
