@@ -57,7 +57,8 @@ EXPORTS = ["aks_ctx_create", "aks_ctx_destroy", "aks_last_error", "aks_ctx_strea
            "aks_batch_set_oda", "aks_batch_set_aufbau", "aks_batch_set_eig_window", "aks_batch_reset", "aks_scf_step", "aks_scf_run", "aks_get_state", "aks_get_state_all",
            "aks_set_density", "aks_assemble_hartree", "aks_assemble_vxc", "aks_eig_lowest",
            "aks_density", "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak", "aks_measure_dmma_peak",
-           "aks_last_phase_ms", "aks_debug_eig_info", "aks_debug_eig_cycles", "aks_debug_eig_refills"]
+           "aks_last_phase_ms", "aks_debug_eig_info", "aks_debug_eig_cycles", "aks_debug_eig_refills",
+           "aks_get_records_dd"]
 
 
 def _load():
@@ -103,6 +104,7 @@ def _load():
     lib.aks_last_phase_ms.argtypes = [vp, _dp]
     lib.aks_debug_eig_info.argtypes = [vp, _i32p]
     lib.aks_debug_eig_cycles.argtypes = [vp, _ip]
+    lib.aks_get_records_dd.argtypes = [vp, _dp]
     return lib
 
 

@@ -19,6 +19,10 @@
 #include "k_eig.cuh"
 #include "k_potential.cuh"
 #include "k_scf.cuh"
+#include "k_dd.cuh"
+
+struct DDDiscHost;
+struct DDBatchHost;
 
 struct aks_ctx {
   int device = 0;
@@ -38,6 +42,7 @@ struct aks_disc {
   std::vector<void*> allocs;
   std::vector<int> l2g;  // host copy [C][n]
   int nmax_tpl = 32;     // template NMAX for the density kernels
+  DDDiscHost* dd = nullptr;   // dtype = 1 (Double64): the double-double tables (aks_dd.cuh)
 };
 
 // A lane = a contiguous range of problems with its own stream.  Problems are independent, so the lanes of a
@@ -73,6 +78,7 @@ struct aks_batch {
   bool eig_dirty = false;   // levels outside the eigenpair window are stale (k_eig)
   cudaEvent_t ev[14];   // 8 phase boundaries + [9],[10] around k_mix_dense + [11],[12],[13] around k_xc, k_potential
   double phase_ms[10] = {0};
+  DDBatchHost* dd = nullptr;   // batch on a Double64 discretization (aks_dd.cuh)
 };
 
 #define CK(call)                                                                              \
@@ -108,6 +114,22 @@ static int dev_zeros(aks_ctx* ctx, std::vector<void*>& allocs, size_t count, T**
   *out = (T*)p;
   return AKS_OK;
 }
+
+// Double64 path (aks_dd.cuh, included at the end of this file)
+static int dd_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** out);
+static void dd_disc_free(aks_disc* disc);
+static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const double* N, const double* hartree,
+                           const int32_t* ex_id, const int32_t* ec_id, const int32_t* lh_p, const int32_t* nh_p,
+                           aks_batch** out);
+static void dd_batch_free(aks_batch* bt);
+static int dd_batch_reset(aks_batch* bt);
+static int dd_set_oda(aks_batch* bt, double scftol, double tinit, int frozen_t, int max_degen, double degen_tol);
+static int dd_step_launch(aks_batch* bt);
+static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* eps, double* nocc, double* W);
+#define DD_UNSUPPORTED(bt, what)                                                               \
+  do {                                                                                         \
+    if ((bt)->dd) { (bt)->disc->ctx->err = what " is not built for Double64 batches"; return AKS_ENOSYS; } \
+  } while (0)
 
 // ------------------------------------------------------------------------------------ context
 extern "C" int aks_ctx_create(int device, aks_ctx** out) {
@@ -180,7 +202,7 @@ static bool chol_inverse(std::vector<double>& A, int m) {
 extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** out) {
   if (!ctx || !D || !out) return AKS_EINVAL;
   *out = nullptr;
-  if (D->dtype == 1) { ctx->err = "dtype=1 (Double64) is not built in this round"; return AKS_ENOSYS; }
+  if (D->dtype == 1) return dd_disc_create(ctx, D, out);
   if (D->dtype != 0) { ctx->err = "bad dtype"; return AKS_EINVAL; }
   const int p = D->p, C = D->C, Nh = D->Nh, Q = D->Q, G = D->G, n = p + 1, nb = p - 1;
   if (p < 2 || p > 29 || C < 2 || Nh != p * C - 1 || Q < 1 || G < 1 || D->lh < 0 || D->nh < 1 ||
@@ -383,6 +405,7 @@ extern "C" void aks_disc_destroy(aks_disc* disc) {
   if (!disc) return;
   for (void* p : disc->allocs) cudaFreeAsync(p, disc->ctx->stream);
   cudaStreamSynchronize(disc->ctx->stream);
+  dd_disc_free(disc);
   delete disc;
 }
 
@@ -400,6 +423,7 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   if (!disc || !out || nprob < 1 || !Z || !N) return AKS_EINVAL;
   aks_ctx* ctx = disc->ctx;
   *out = nullptr;
+  if (disc->dd) return dd_batch_create(disc, nprob, Z, N, hartree, ex_id, ec_id, lh_p, nh_p, out);
   const DiscDev& dv = disc->dev;
   aks_batch* bt = new aks_batch();
   bt->disc = disc;
@@ -541,6 +565,7 @@ extern "C" void aks_batch_destroy(aks_batch* bt) {
   cudaStreamSynchronize(st);
   if (bt->h_rec) bt->disc->ctx->pinned_free.push_back({bt->h_rec, bt->h_rec_bytes});
   if (bt->timers) for (auto& e : bt->ev) cudaEventDestroy(e);
+  dd_batch_free(bt);
   delete bt;
 }
 
@@ -553,6 +578,7 @@ extern "C" int aks_batch_set_oda(aks_batch* bt, double scftol, double tinit, int
   if (!(scftol >= 0) || !(tinit >= 0 && tinit <= 1) || maxiter_ls < 1 || max_degen < 1 || !(degen_tol >= 0)) {
     ctx->err = "aks_batch_set_oda: bad option"; return AKS_EINVAL;
   }
+  if (bt->dd) return dd_set_oda(bt, scftol, tinit, frozen_t, max_degen, degen_tol);
   BatchDev& b = bt->dev;
   b.scftol = scftol; b.tinit = tinit; b.frozen_t = frozen_t; b.maxiter_ls = maxiter_ls;
   b.abstol_ls = abstol_ls; b.reltol_ls = reltol_ls; b.max_degen = max_degen; b.degen_tol = degen_tol;
@@ -565,6 +591,7 @@ extern "C" int aks_batch_set_oda(aks_batch* bt, double scftol, double tinit, int
 
 extern "C" int aks_batch_reset(aks_batch* bt) {
   if (!bt) return AKS_EINVAL;
+  if (bt->dd) return dd_batch_reset(bt);
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   BatchDev& b = bt->dev;
@@ -592,6 +619,8 @@ extern "C" int aks_batch_reset(aks_batch* bt) {
 
 extern "C" int aks_batch_set_aufbau(aks_batch* bt, int32_t kind, double temp, const double* nfix) {
   if (!bt) return AKS_EINVAL;
+  if (bt->dd && kind == 0) return AKS_OK;
+  DD_UNSUPPORTED(bt, "SmearedAufbau / FrozenAufbau");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   BatchDev& b = bt->dev;
@@ -619,6 +648,7 @@ extern "C" int aks_batch_set_aufbau(aks_batch* bt, int32_t kind, double temp, co
 
 extern "C" int aks_batch_set_eig_window(aks_batch* bt, int32_t margin) {
   if (!bt) return AKS_EINVAL;
+  if (bt->dd) return AKS_OK;   // the Double64 path solves all nh eigenpairs in every step
   enter_main(bt);
   int rc = ensure_complete(bt);
   if (rc != AKS_OK) return rc;
@@ -827,6 +857,7 @@ static void main_side(aks_batch* bt) { bt->forked = false; bt->cur = &bt->whole;
 
 static int step_launch(aks_batch* bt) {
   aks_ctx* ctx = bt->disc->ctx;
+  if (bt->dd) { refresh_lanes(bt); main_side(bt); return dd_step_launch(bt); }
   refresh_lanes(bt);
   if (bt->lanes.size() < 2 || bt->timers) {
     bt->cur = &bt->whole;
@@ -934,6 +965,7 @@ extern "C" int aks_last_phase_ms(aks_batch* bt, double out[10]) {
 // ------------------------------------------------------------------------------------ state I/O
 extern "C" int aks_get_state(aks_batch* bt, int32_t prob, double* D, double* U, double* eps, double* nocc, double* W) {
   if (!bt || prob < 0 || prob >= bt->B) return AKS_EINVAL;
+  if (bt->dd) return dd_get_state(bt, prob, D, U, eps, nocc, W);
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
@@ -967,6 +999,15 @@ extern "C" int aks_get_state(aks_batch* bt, int32_t prob, double* D, double* U, 
 // synchronisation each).  Layout per problem as in aks_get_state: eps, n (L, nh[, 2]) column-major, W (Nh).
 extern "C" int aks_get_state_all(aks_batch* bt, double* eps, double* nocc, double* W) {
   if (!bt) return AKS_EINVAL;
+  if (bt->dd) {   // pairs: eps, n [nprob][(L, nh)][2], W [nprob][Nh][2]
+    const size_t per = 2 * (size_t)bt->dev.Lmax * bt->dev.nhmax, Nh2 = 2 * (size_t)bt->disc->dev.Nh;
+    for (int p = 0; p < bt->B; ++p) {
+      const int rc = dd_get_state(bt, p, nullptr, nullptr, eps ? eps + p * per : nullptr, nocc ? nocc + p * per : nullptr,
+                                  W ? W + p * Nh2 : nullptr);
+      if (rc != AKS_OK) return rc;
+    }
+    return AKS_OK;
+  }
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
@@ -1007,6 +1048,7 @@ static int launch_state_from_dense(aks_batch* bt, int prob) {
 
 extern "C" int aks_set_density(aks_batch* bt, int32_t prob, const double* D, const double* eprev, int32_t niter) {
   if (!bt || prob < 0 || prob >= bt->B || !D || niter < 0) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_set_density");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
@@ -1079,17 +1121,20 @@ static int potential_hook(aks_batch* bt, int prob, double* vxc, double* har) {
 
 extern "C" int aks_assemble_hartree(aks_batch* bt, int32_t prob, double* Har) {
   if (!bt || prob < 0 || prob >= bt->B || !Har) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_assemble_hartree");
   enter_main(bt);
   return potential_hook(bt, prob, nullptr, Har);
 }
 extern "C" int aks_assemble_vxc(aks_batch* bt, int32_t prob, double* Vxc) {
   if (!bt || prob < 0 || prob >= bt->B || !Vxc) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_assemble_vxc");
   enter_main(bt);
   return potential_hook(bt, prob, Vxc, nullptr);
 }
 
 extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* U, double* residuals) {
   if (!bt || prob < 0 || prob >= bt->B) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_eig_lowest");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
@@ -1125,6 +1170,7 @@ extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* 
 
 extern "C" int aks_density(aks_batch* bt, int32_t prob, double* D) {
   if (!bt || prob < 0 || prob >= bt->B || !D) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_density");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
@@ -1141,6 +1187,7 @@ extern "C" int aks_density(aks_batch* bt, int32_t prob, double* D) {
 
 extern "C" int aks_exc_energy(aks_batch* bt, int32_t prob, double* Exc) {
   if (!bt || prob < 0 || prob >= bt->B || !Exc) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_exc_energy");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   double* dout = nullptr;
@@ -1155,6 +1202,7 @@ extern "C" int aks_exc_energy(aks_batch* bt, int32_t prob, double* Exc) {
 
 extern "C" int aks_hartree_energy(aks_batch* bt, int32_t prob, double* Ehar) {
   if (!bt || prob < 0 || prob >= bt->B || !Ehar) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_hartree_energy");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
@@ -1171,6 +1219,7 @@ extern "C" int aks_hartree_energy(aks_batch* bt, int32_t prob, double* Ehar) {
 
 extern "C" int aks_debug_eig_cycles(aks_batch* bt, int64_t* out) {
   if (!bt || !out) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_debug_eig_cycles");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const BatchDev& b = bt->dev;
@@ -1182,6 +1231,7 @@ extern "C" int aks_debug_eig_cycles(aks_batch* bt, int64_t* out) {
 
 extern "C" int aks_debug_eig_refills(aks_batch* bt, int32_t* counts) {
   if (!bt || !counts) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_debug_eig_refills");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   CK(cudaMemcpyAsync(counts, bt->dev.redo_cnt, sizeof(int) * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1191,6 +1241,7 @@ extern "C" int aks_debug_eig_refills(aks_batch* bt, int32_t* counts) {
 
 extern "C" int aks_debug_eig_info(aks_batch* bt, int32_t* info) {
   if (!bt || !info) return AKS_EINVAL;
+  DD_UNSUPPORTED(bt, "aks_debug_eig_info");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   const BatchDev& b = bt->dev;
@@ -1259,3 +1310,5 @@ extern "C" int aks_measure_fp64_peak(aks_ctx* ctx, double* tflops) {
   *tflops = best;
   return AKS_OK;
 }
+
+#include "aks_dd.cuh"

@@ -1,0 +1,292 @@
+// Host side of the Double64 (dtype = 1) path: table splitting in double-double, device memory, the launch
+// sequence of k_dd.cuh.  Included at the end of aks_b200.cu (one translation unit); the C-ABI entry points
+// dispatch here when the discretization was created with dtype = 1.  Every floating-point table of
+// aks_disc_desc and every floating-point output buffer is then an array of interleaved (hi, lo) pairs --
+// the memory layout of Julia's Vector{Double64}.
+#pragma once
+
+struct DDDiscHost {
+  DDDiscDev dev{};
+};
+struct DDBatchHost {
+  DDBatchDev dev{};
+  int max_orb_launch = DD_MAXORB;
+};
+
+static inline dd ddh_pair(const double* a, size_t idx) { return dd_make(a[2 * idx], a[2 * idx + 1]); }
+
+static int dd_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** out) {
+  const int p = D->p, C = D->C, Nh = D->Nh, n = p + 1, nb = p - 1;
+  if (p < 2 || p > DD_MAXN - 1 || C < 2 || C > DD_NT || Nh != p * C - 1 || D->lh < 0 || D->nh < 1) {
+    ctx->err = "aks_disc_create(dtype=1): need 2 <= p <= 29, 2 <= C <= 64, Nh == p*C-1";
+    return AKS_EINVAL;
+  }
+  if (D->nspin != 1) { ctx->err = "dtype=1 (Double64): nspin = 2 is not built"; return AKS_ENOSYS; }
+  if ((D->lh + 1) * D->nh > DD_MAXORB) { ctx->err = "(lh+1)*nh exceeds DD_MAXORB"; return AKS_EINVAL; }
+  if (!D->mesh || !D->M0 || !D->A || !D->Mm1 || !D->cell_len || !D->cell_indices || !D->cell_generators) {
+    ctx->err = "aks_disc_create(dtype=1): NULL table";
+    return AKS_EINVAL;
+  }
+  if (D->lh > 0 && !D->Mm2) { ctx->err = "Mm2 required when lh > 0"; return AKS_EINVAL; }
+  aks_disc* disc = new aks_disc();
+  disc->ctx = ctx;
+  disc->dd = new DDDiscHost();
+  DDDiscDev& dv = disc->dd->dev;
+  dv.p = p; dv.n = n; dv.nb = nb; dv.C = C; dv.Nh = Nh; dv.L = D->lh + 1; dv.nh = D->nh;
+  dv.Rmax = ddh_pair(D->mesh, C);
+  {  // the Float64 view carries the sizes only
+    DiscDev& d0 = disc->dev;
+    d0.p = p; d0.n = n; d0.nb = nb; d0.C = C; d0.Nh = Nh; d0.L = dv.L; d0.nh = dv.nh; d0.nspin = 1;
+    d0.Q = 0; d0.G = 0; d0.Rmax = dv.Rmax.hi;
+  }
+  std::vector<int>& l2g = disc->l2g;
+  l2g.assign((size_t)C * n, -1);
+  for (int c = 0; c < C; ++c) {
+    const int len = (int)D->cell_len[c];
+    if (len < 1 || len > n) { ctx->err = "bad cell_len"; aks_disc_destroy(disc); return AKS_EINVAL; }
+    for (int j = 0; j < len; ++j) {
+      const int64_t I = D->cell_indices[(size_t)c * n + j], g = D->cell_generators[(size_t)c * n + j];
+      if (I < 1 || I > Nh || g < 1 || g > n) { ctx->err = "bad cell index/generator"; aks_disc_destroy(disc); return AKS_EINVAL; }
+      l2g[(size_t)c * n + (g - 1)] = (int)(I - 1);
+    }
+  }
+  bool chain = (l2g[1] == -1 && l2g[(size_t)(C - 1) * n] == -1);
+  for (int c = 0; c + 1 < C && chain; ++c)
+    chain = l2g[(size_t)c * n] >= 0 && l2g[(size_t)c * n] == l2g[(size_t)(c + 1) * n + 1];
+  for (int c = 0; c < C && chain; ++c)
+    for (int i = 0; i < nb; ++i)
+      if (l2g[(size_t)c * n + 2 + i] != l2g[(size_t)c * n + 2] + i) chain = false;
+  if (!chain) { ctx->err = "cell maps are not a P1+bubble chain with Dirichlet ends"; aks_disc_destroy(disc); return AKS_EINVAL; }
+
+  // global symmetric matrices (pairs, column-major) -> cell-owned blocks: an entry shared by two cells
+  // belongs to the lower one
+  auto split = [&](const double* Gm, std::vector<dd>& loc) {
+    loc.assign((size_t)C * n * n, dd_make(0.0));
+    if (!Gm) return;
+    std::vector<char> owned((size_t)Nh * Nh, 0);
+    for (int c = 0; c < C; ++c)
+      for (int a = 0; a < n; ++a) {
+        const int I = l2g[(size_t)c * n + a];
+        if (I < 0) continue;
+        for (int bq = 0; bq < n; ++bq) {
+          const int J = l2g[(size_t)c * n + bq];
+          if (J < 0 || owned[(size_t)I * Nh + J]) continue;
+          owned[(size_t)I * Nh + J] = 1;
+          loc[((size_t)c * n + a) * n + bq] =
+              (ddh_pair(Gm, (size_t)I + (size_t)Nh * J) + ddh_pair(Gm, (size_t)J + (size_t)Nh * I)) * 0.5;
+        }
+      }
+  };
+  std::vector<dd> M0l, Al, M1l, M2l;
+  split(D->M0, M0l);
+  split(D->A, Al);
+  split(D->Mm1, M1l);
+  split(D->Mm2, M2l);
+  std::vector<dd> Fl((size_t)C * n * n * n, dd_make(0.0));
+  if (D->nF > 0) {
+    if (!D->Fi || !D->Fj || !D->Fm || !D->Fv) { ctx->err = "NULL F arrays"; aks_disc_destroy(disc); return AKS_EINVAL; }
+    std::vector<int> cell_of((size_t)Nh * 2, -1), loc_of((size_t)Nh * 2, -1);
+    for (int c = 0; c < C; ++c)
+      for (int a = 0; a < n; ++a) {
+        const int I = l2g[(size_t)c * n + a];
+        if (I < 0) continue;
+        const int slot = (cell_of[2 * I] < 0) ? 0 : 1;
+        cell_of[2 * I + slot] = c;
+        loc_of[2 * I + slot] = a;
+      }
+    for (int64_t t = 0; t < D->nF; ++t) {
+      const int I = (int)D->Fi[t] - 1, J = (int)D->Fj[t] - 1, Mi = (int)D->Fm[t] - 1;
+      if (I < 0 || J < 0 || Mi < 0 || I >= Nh || J >= Nh || Mi >= Nh) { ctx->err = "bad F index"; aks_disc_destroy(disc); return AKS_EINVAL; }
+      int owner = -1, la = 0, lb = 0, lm = 0;
+      for (int si = 0; si < 2 && owner < 0; ++si) {
+        const int c = cell_of[2 * I + si];
+        if (c < 0) continue;
+        int fj = -1, fm = -1;
+        for (int sj = 0; sj < 2; ++sj) if (cell_of[2 * J + sj] == c) fj = loc_of[2 * J + sj];
+        for (int sm2 = 0; sm2 < 2; ++sm2) if (cell_of[2 * Mi + sm2] == c) fm = loc_of[2 * Mi + sm2];
+        if (fj >= 0 && fm >= 0) { owner = c; la = loc_of[2 * I + si]; lb = fj; lm = fm; }
+      }
+      if (owner < 0) continue;
+      const dd half = ddh_pair(D->Fv, (size_t)t) * 0.5;   // symmetrised in (i, j)
+      dd& e1 = Fl[(((size_t)owner * n + lm) * n + la) * n + lb];
+      e1 = e1 + half;
+      dd& e2 = Fl[(((size_t)owner * n + lm) * n + lb) * n + la];
+      e2 = e2 + half;
+    }
+  }
+  int rc;
+#define UPD(vec, field)                                                                          \
+  if ((rc = dev_upload(ctx, disc->allocs, vec, &dv.field)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
+  UPD(Al, A_loc) UPD(M0l, M0_loc) UPD(M1l, Mm1_loc) UPD(M2l, Mm2_loc) UPD(Fl, F_loc) UPD(l2g, l2g)
+#undef UPD
+  if ((rc = dev_zeros<dd>(ctx, disc->allocs, (size_t)C * n * n, &dv.Afac)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
+  if ((rc = dev_zeros<dd>(ctx, disc->allocs, (size_t)2 * DD_NT, &dv.Atri)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
+  ddk_setup<<<1, DD_NT, 0, ctx->stream>>>(dv);
+  ctx->launches += 1;
+  {
+    cudaError_t e_ = cudaStreamSynchronize(ctx->stream);
+    if (e_ == cudaSuccess) e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) { ctx->err = std::string("ddk_setup -> ") + cudaGetErrorString(e_); aks_disc_destroy(disc); return AKS_ECUDA; }
+  }
+  *out = disc;
+  return AKS_OK;
+}
+
+static int dd_batch_reset(aks_batch* bt) {
+  aks_ctx* ctx = bt->disc->ctx;
+  DDBatchDev& b = bt->dd->dev;
+  const DDDiscDev& dv = bt->disc->dd->dev;
+  const size_t B = bt->B, Nh = dv.Nh;
+  CK(cudaMemsetAsync(b.D, 0, sizeof(dd) * B * Nh * Nh, ctx->stream));
+  CK(cudaMemsetAsync(b.Bv, 0, sizeof(dd) * B * Nh, ctx->stream));
+  CK(cudaMemsetAsync(b.Wv, 0, sizeof(dd) * B * Nh, ctx->stream));
+  CK(cudaMemsetAsync(b.E, 0, sizeof(dd) * B * 5, ctx->stream));
+  CK(cudaMemsetAsync(b.niter, 0, sizeof(int) * B, ctx->stream));
+  CK(cudaMemsetAsync(b.status, 0, sizeof(int) * B, ctx->stream));
+  CK(cudaMemsetAsync(b.warm, 0, sizeof(int) * B, ctx->stream));
+  CK(cudaMemsetAsync(b.eig_fail, 0, sizeof(int) * B, ctx->stream));
+  CK(cudaMemsetAsync(b.rec, 0, sizeof(dd) * B * 7, ctx->stream));
+  CK(cudaMemsetAsync(b.rec64, 0, sizeof(aks_iter_record) * B, ctx->stream));
+  std::vector<dd> tv(B, dd_make(b.tinit));
+  CK(cudaMemcpyAsync(b.t, tv.data(), sizeof(dd) * B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
+static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const double* N, const double* hartree,
+                           const int32_t* ex_id, const int32_t* ec_id, const int32_t* lh_p, const int32_t* nh_p,
+                           aks_batch** out) {
+  aks_ctx* ctx = disc->ctx;
+  const DDDiscDev& dv = disc->dd->dev;
+  for (int i = 0; i < nprob; ++i)
+    if ((ex_id && ex_id[i] != AKS_XC_NONE) || (ec_id && ec_id[i] != AKS_XC_NONE)) {
+      ctx->err = "dtype=1 (Double64): exchange-correlation functionals are not built (the reference's own Double64 "
+                 "example runs without one)";
+      return AKS_ENOSYS;
+    }
+  aks_batch* bt = new aks_batch();
+  bt->disc = disc;
+  bt->B = nprob;
+  bt->dd = new DDBatchHost();
+  DDBatchDev& b = bt->dd->dev;
+  b.B = nprob; b.L = dv.L; b.nh = dv.nh;
+  bt->hZ.assign(Z, Z + nprob);
+  bt->hN.assign(N, N + nprob);
+  bt->hHar.assign(nprob, 1.0);
+  if (hartree) bt->hHar.assign(hartree, hartree + nprob);
+  bt->hLp.assign(nprob, dv.L);
+  bt->hnhp.assign(nprob, dv.nh);
+  for (int i = 0; i < nprob; ++i) {
+    if (lh_p) bt->hLp[i] = lh_p[i] + 1;
+    if (nh_p) bt->hnhp[i] = nh_p[i];
+    if (bt->hLp[i] < 1 || bt->hLp[i] > dv.L || bt->hnhp[i] < 1 || bt->hnhp[i] > dv.nh || !(N[i] > 0) || !(Z[i] > 0)) {
+      ctx->err = "bad per-problem lh/nh/Z/N"; aks_batch_destroy(bt); return AKS_EINVAL;
+    }
+  }
+  int rc;
+#define UPB(vec, field) if ((rc = dev_upload(ctx, bt->allocs, vec, &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
+  UPB(bt->hZ, Z) UPB(bt->hN, N) UPB(bt->hHar, hartree) UPB(bt->hLp, Lp) UPB(bt->hnhp, nhp)
+#undef UPB
+  const size_t B = nprob, Nh = dv.Nh, C = dv.C, L = dv.L, nh = dv.nh, n = dv.n;
+  b.nparts = (int)std::min<size_t>((Nh * Nh + 255) / 256, 148);
+#define ZB(T, field, count) if ((rc = dev_zeros<T>(ctx, bt->allocs, (count), &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
+  ZB(dd, D, B * Nh * Nh) ZB(dd, Bv, B * Nh) ZB(dd, Wv, B * Nh) ZB(dd, E, B * 5) ZB(dd, t, B) ZB(int, niter, B)
+  ZB(int, status, B) ZB(int, warm, B) ZB(dd, H, B * L * C * n * n) ZB(dd, eps, B * L * nh) ZB(dd, U, B * L * nh * Nh)
+  ZB(dd, vtmp, B * L * nh * Nh) ZB(dd, ekin_orb, B * L * nh) ZB(dd, ecou_orb, B * L * nh) ZB(dd, occ, B * L * nh)
+  ZB(int, eig_fail, B) ZB(dd, scratch, B * L * nh * C * n * n) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
+  ZB(dd, orb_n0, B * DD_MAXORB) ZB(dd, orb_n1, B * DD_MAXORB) ZB(dd, orb_n, B * DD_MAXORB) ZB(int, degen, B)
+  ZB(dd, bloc, B * DD_MAXORB * C * n) ZB(dd, borb, B * DD_MAXORB * Nh) ZB(dd, worb, B * DD_MAXORB * Nh)
+  ZB(dd, Bnew, B * Nh) ZB(dd, Wnew, B * Nh) ZB(dd, Enew, B * 5) ZB(dd, tmix, B) ZB(dd, tnew, B)
+  ZB(dd, norm_part, B * b.nparts) ZB(dd, rec, B * 7) ZB(aks_iter_record, rec64, B)
+#undef ZB
+  b.scftol = 1e-10; b.tinit = 0.6; b.frozen_t = 0; b.max_degen = 2; b.degen_tol = 1e-3;
+  // the generic driver (aks_scf_run, fetch_records) reads the records and status words through the Float64 view
+  bt->dev.B = nprob; bt->dev.s = 1; bt->dev.Lmax = dv.L; bt->dev.nhmax = dv.nh;
+  bt->dev.rec = b.rec64;
+  bt->dev.status = b.status;
+  {
+    const size_t need = sizeof(aks_iter_record) * B;
+    CK(cudaMallocHost((void**)&bt->h_rec, need));
+    bt->h_rec_bytes = need;
+  }
+  // at most this many orbitals carry weight: every level of every channel
+  bt->dd->max_orb_launch = (int)std::min<size_t>(L * nh, 32);
+  *out = bt;
+  return dd_batch_reset(bt);
+}
+
+static int dd_set_oda(aks_batch* bt, double scftol, double tinit, int frozen_t, int max_degen, double degen_tol) {
+  aks_ctx* ctx = bt->disc->ctx;
+  DDBatchDev& b = bt->dd->dev;
+  b.scftol = scftol; b.tinit = tinit; b.frozen_t = frozen_t; b.max_degen = max_degen; b.degen_tol = degen_tol;
+  std::vector<dd> tv(bt->B, dd_make(tinit));
+  CK(cudaMemcpyAsync(b.t, tv.data(), sizeof(dd) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
+static int dd_step_launch(aks_batch* bt) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const DDDiscDev& dv = bt->disc->dd->dev;
+  const DDBatchDev& b = bt->dd->dev;
+  cudaStream_t st = ctx->stream;
+  const int B = bt->B, no = bt->dd->max_orb_launch;
+  CK(cudaMemsetAsync(b.eig_fail, 0, sizeof(int) * B, st));
+  ddk_H<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
+  LAUNCH_CHECK();
+  ddk_eig<<<dim3(dv.nh, dv.L, B), DD_NT, 0, st>>>(dv, b);
+  LAUNCH_CHECK();
+  ddk_aufbau<<<(B + 31) / 32, 32, 0, st>>>(dv, b);
+  LAUNCH_CHECK();
+  ddk_orbB<<<dim3(dv.C, no, B), 32, 0, st>>>(dv, b);
+  LAUNCH_CHECK();
+  ddk_poisson<<<dim3(no, B), DD_NT, 0, st>>>(dv, b);
+  LAUNCH_CHECK();
+  ddk_decide<<<B, 128, 0, st>>>(dv, b);
+  LAUNCH_CHECK();
+  ddk_mix<<<dim3(b.nparts, B), 256, 0, st>>>(dv, b);
+  LAUNCH_CHECK();
+  ddk_finish<<<B, 128, 0, st>>>(dv, b);
+  LAUNCH_CHECK();
+  return AKS_OK;
+}
+
+// outputs in the reference's layouts, every number an interleaved (hi, lo) pair:
+// D (Nh,Nh)  U (Nh,nh,L)  eps, n (L,nh)  W (Nh)
+static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* eps, double* nocc, double* W) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const DDDiscDev& dv = bt->disc->dd->dev;
+  const DDBatchDev& b = bt->dd->dev;
+  const size_t Nh = dv.Nh, L = dv.L, nh = dv.nh;
+  if (D) CK(cudaMemcpyAsync(D, b.D + (size_t)prob * Nh * Nh, sizeof(dd) * Nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  if (U) CK(cudaMemcpyAsync(U, b.U + (size_t)prob * L * nh * Nh, sizeof(dd) * L * nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<dd> he(L * nh), hn(L * nh), hw(Nh);
+  if (eps) CK(cudaMemcpyAsync(he.data(), b.eps + (size_t)prob * L * nh, sizeof(dd) * L * nh, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nocc) CK(cudaMemcpyAsync(hn.data(), b.occ + (size_t)prob * L * nh, sizeof(dd) * L * nh, cudaMemcpyDeviceToHost, ctx->stream));
+  if (W) CK(cudaMemcpyAsync(hw.data(), b.Wv + (size_t)prob * Nh, sizeof(dd) * Nh, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (size_t l = 0; l < L; ++l)
+    for (size_t k = 0; k < nh; ++k) {
+      const size_t o = l + L * k, i = l * nh + k;
+      if (eps) { eps[2 * o] = he[i].hi; eps[2 * o + 1] = he[i].lo; }
+      if (nocc) { nocc[2 * o] = hn[i].hi; nocc[2 * o + 1] = hn[i].lo; }
+    }
+  if (W)
+    for (size_t i = 0; i < Nh; ++i) {
+      const dd v = hw[i] * bt->hHar[prob];
+      W[2 * i] = v.hi; W[2 * i + 1] = v.lo;
+    }
+  return AKS_OK;
+}
+
+extern "C" int aks_get_records_dd(aks_batch* bt, double* out) {
+  if (!bt || !out) return AKS_EINVAL;
+  aks_ctx* ctx = bt->disc->ctx;
+  if (!bt->dd) { ctx->err = "aks_get_records_dd: not a Double64 batch"; return AKS_EINVAL; }
+  CK(cudaMemcpyAsync(out, bt->dd->dev.rec, sizeof(dd) * 7 * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
+static void dd_disc_free(aks_disc* disc) { delete disc->dd; disc->dd = nullptr; }
+static void dd_batch_free(aks_batch* bt) { delete bt->dd; bt->dd = nullptr; }

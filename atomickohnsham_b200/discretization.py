@@ -25,13 +25,20 @@ class KSEDiscretization:
         self.basis = basis
         if dtype not in ("float64", "double64"):
             raise ValueError("dtype must be 'float64' or 'double64'")
-        self.dtype = dtype   # 'double64' (T = Double64 of the reference) is not built: aks_disc_create -> AKS_ENOSYS
+        self.dtype = dtype   # 'double64' = T = Double64 of the reference: double-double tables and kernels
         self.lh, self.nh = int(lh), int(nh)
         self.nspin = int(nspin if nspin is not None else (model.nspin if model is not None else 1))
         self.Nh = basis.size
         self.Rmax = basis.mesh.last
-        self.fem_integration_method = fem_integration_method or GaussLegendre(basis)
-        self.femops = femops or build_femops(basis)
+        if dtype == "double64":
+            # the Double64 path runs without an exchange-correlation functional (as the reference's own
+            # Double64 example does): no Gauss tables are needed
+            from .dd import build_femops_dd
+            self.fem_integration_method = fem_integration_method
+            self.femops = femops or build_femops_dd(basis)
+        else:
+            self.fem_integration_method = fem_integration_method or GaussLegendre(basis)
+            self.femops = femops or build_femops(basis)
         self.device = device
         self._handle = None
         self._ctx = None
@@ -48,6 +55,8 @@ class KSEDiscretization:
         """aks_disc* of this discretization (created on first use)."""
         if self._handle is not None:
             return self._handle
+        if self.dtype == "double64":
+            return self._handle_dd()
         b, ops, q = self.basis, self.femops, self.fem_integration_method
         n, Cn = b.nloc, b.ncells
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -74,6 +83,41 @@ class KSEDiscretization:
             setattr(d, name, _capi.dptr(keep[name]))
         d.ycell = _capi.iptr(keep["ycell"])
         d.nF = len(Fv)
+        d.Fi, d.Fj, d.Fm = _capi.iptr(keep["Fi"]), _capi.iptr(keep["Fj"]), _capi.iptr(keep["Fm"])
+        d.cell_len = _capi.iptr(keep["cell_len"])
+        d.cell_indices = _capi.iptr(keep["cidx"])
+        d.cell_generators = _capi.iptr(keep["cgen"])
+        h = C.c_void_p()
+        self.ctx.check(_capi.lib.aks_disc_create(self.ctx.h, C.byref(d), C.byref(h)))
+        self._handle = h
+        return h
+
+    def _handle_dd(self):
+        """aks_disc* with dtype = 1: every floating-point table is an array of interleaved (hi, lo) pairs."""
+        b, ops = self.basis, self.femops
+        n, Cn = b.nloc, b.ncells
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        cidx = np.zeros((Cn, n), dtype=np.int64)
+        cgen = np.zeros((Cn, n), dtype=np.int64)
+        for c in range(Cn):
+            L = len(b.cells_to_indices[c])
+            cidx[c, :L] = np.asarray(b.cells_to_indices[c]) + 1
+            cgen[c, :L] = np.asarray(b.cells_to_generators[c]) + 1
+        Fi, Fj, Fm, Fv = ops.F_coo_pairs()
+        pairs_of = lambda v: np.ascontiguousarray(np.stack([np.asarray(v, dtype=np.float64),
+                                                            np.zeros(len(v))], axis=-1))
+        # global matrices are symmetric: row- and column-major coincide
+        keep = dict(mesh=pairs_of(b.mesh.points), M0=ops.assemble_pairs(ops.M0_loc), A=ops.assemble_pairs(ops.A_loc),
+                    Mm1=ops.assemble_pairs(ops.Mm1_loc), Mm2=ops.assemble_pairs(ops.Mm2_loc),
+                    Fi=i64(Fi + 1), Fj=i64(Fj + 1), Fm=i64(Fm + 1), Fv=Fv,
+                    cell_len=i64([len(v) for v in b.cells_to_indices]), cidx=i64(cidx.reshape(-1)),
+                    cgen=i64(cgen.reshape(-1)))
+        d = _capi.DiscDesc()
+        d.dtype, d.p, d.C, d.Nh = 1, b.ordermax, Cn, b.size
+        d.Q, d.G, d.lh, d.nh, d.nspin = 0, 0, self.lh, self.nh, self.nspin
+        for name in ("mesh", "M0", "A", "Mm1", "Mm2", "Fv"):
+            setattr(d, name, _capi.dptr(keep[name]))
+        d.nF = len(Fi)
         d.Fi, d.Fj, d.Fm = _capi.iptr(keep["Fi"]), _capi.iptr(keep["Fj"]), _capi.iptr(keep["Fm"])
         d.cell_len = _capi.iptr(keep["cell_len"])
         d.cell_indices = _capi.iptr(keep["cidx"])

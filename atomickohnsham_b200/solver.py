@@ -163,8 +163,34 @@ class Batch:
                     out[i].append(r.asdict())
         return final, out
 
+    def records_dd(self):
+        """Double64 batches: the last record of every problem as (hi, lo) pairs, shape (nprob, 7, 2) with the
+        columns stop, Etot, Ekin, Ecou, Ehar, Eexc, t (aks_get_records_dd)."""
+        out = np.zeros((self.nprob, 7, 2))
+        self.ctx.check(_capi.lib.aks_get_records_dd(self.h, _capi.dptr(out)))
+        return out
+
+    def _state_dd(self, prob, want_D, want_U):
+        """Double64 batches: every array carries a trailing axis (hi, lo)."""
+        d = self.disc
+        Nh, L, nh = d.Nh, d.lh + 1, d.nh
+        D = np.zeros((Nh, Nh, 2)) if want_D else None
+        U = np.zeros((L, nh, Nh, 2)) if want_U else None
+        eps, n, W = np.zeros((L * nh, 2)), np.zeros((L * nh, 2)), np.zeros((Nh, 2))
+        self.ctx.check(_capi.lib.aks_get_state(self.h, prob, _capi.dptr(D), _capi.dptr(U), _capi.dptr(eps),
+                                               _capi.dptr(n), _capi.dptr(W)))
+        col = lambda a: np.stack([a[:, 0].reshape((L, nh, 1), order="F"), a[:, 1].reshape((L, nh, 1), order="F")], -1)
+        out = dict(eps=col(eps), n=col(n), W=W)
+        if want_D:
+            out["D"] = D[:, :, None, :]
+        if want_U:
+            out["U"] = np.transpose(U, (2, 1, 0, 3))[:, :, :, None, :]
+        return out
+
     def state(self, prob=0, *, want_D=True, want_U=True):
         d = self.disc
+        if d.dtype == "double64":
+            return self._state_dd(prob, want_D, want_U)
         s, Nh, L, nh = d.nspin, d.Nh, d.lh + 1, d.nh
         D = np.zeros((s, Nh, Nh)) if want_D else None
         U = np.zeros((s, L, nh, Nh)) if want_U else None

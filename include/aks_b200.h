@@ -32,7 +32,7 @@ extern "C" {
 #define AKS_ENOTCONV (-3) /* aks_scf_run: at least one problem hit maxiter             */
 #define AKS_EDEGEN3 (-4)  /* >2-fold degeneracy (reference error(), optimized.jl:139)   */
 #define AKS_ENAN (-5)     /* non-finite value in a problem's energies                   */
-#define AKS_ENOSYS (-6)   /* feature not built (e.g. dtype = double-double)             */
+#define AKS_ENOSYS (-6)   /* feature not built (e.g. a functional on a Double64 batch)     */
 
 /* per-problem status word in aks_iter_record.status */
 #define AKS_RUNNING 0
@@ -59,7 +59,10 @@ void* aks_ctx_stream(const aks_ctx* ctx);
  * (src/discretization/discretization.jl:270-341, src/fem/integration methods.jl:30-70,
  *  src/fem/generators.jl:79-138).  Sizes: n = p+1 generators, C cells, Nh = p*C-1.       */
 typedef struct aks_disc_desc {
-  int32_t dtype;  /* 0 = Float64; 1 = Double64 (hi,lo) pairs -> AKS_ENOSYS in this build    */
+  int32_t dtype;  /* 0 = Float64; 1 = Double64 (the reference's T = Double64, discretization.jl:289): every
+                     `const double*` table below then holds interleaved (hi, lo) pairs (Julia's
+                     Vector{Double64} layout, twice the length); x, w, Pgenx, y, wy, ycell, Pgeny, invshifts
+                     may be NULL with Q = G = 0 (no exchange-correlation in the Double64 build); nspin = 1 */
   int32_t p;      /* ordermax                                                             */
   int32_t C;      /* number of cells = length(mesh)-1                                     */
   int32_t Nh;     /* basis size                                                           */
@@ -149,6 +152,11 @@ int aks_scf_run(aks_batch* batch, int32_t maxiter, aks_iter_record* history,
  *   (postcomputations!, oda/loop.jl:51-54; multiplied by the model's hartree coefficient) */
 int aks_get_state(aks_batch* batch, int32_t prob, double* D, double* U, double* eps, double* n,
                   double* W);
+/* Batches on a dtype = 1 (Double64) discretization: D, U, eps, n, W of aks_get_state / aks_get_state_all are
+ * (hi, lo) pairs in the same layouts (buffers twice as long); aks_iter_record carries the leading doubles and
+ * aks_get_records_dd the full pairs of the last step: out[nprob][7][2] = stop, Etot, Ekin, Ecou, Ehar, Eexc, t.
+ * aks_set_density and the step-level hooks return AKS_ENOSYS for such batches.                              */
+int aks_get_records_dd(aks_batch* batch, double* out);
 /* eps, n, W of every problem at once: eps, n [nprob][(L, nh[, 2])], W [nprob][Nh]; any pointer may be NULL */
 int aks_get_state_all(aks_batch* batch, double* eps, double* n, double* W);
 /* overwrite one problem's density state from a dense D (Nh,Nh[,2]) -- restart / step-level
