@@ -1,0 +1,93 @@
+"""CPU tests of the Double64 host side: double-double NumPy arithmetic and the dd FEM tables
+(atomickohnsham_b200/dd.py) against mpmath, and the committed Double64 golden of the reference."""
+import mpmath as mp
+import numpy as np
+
+from helpers import load_golden, make_mesh
+
+
+def test_dd_numpy_arithmetic_against_mpmath():
+    from atomickohnsham_b200.dd import DD, from_mp
+    mp.mp.dps = 60
+    rng = np.random.default_rng(20261020)
+    a = [mp.mpf(float(x)) * mp.mpf(10) ** int(e) + mp.mpf(float(y)) * mp.mpf(2) ** -60
+         for x, y, e in zip(rng.standard_normal(50), rng.standard_normal(50), rng.integers(-5, 5, 50))]
+    b = [mp.mpf(float(x)) + mp.mpf(float(y)) * mp.mpf(2) ** -58 for x, y in zip(rng.standard_normal(50), rng.standard_normal(50))]
+    A, B = from_mp(a), from_mp(b)
+    for got, ref in ((A + B, [x + y for x, y in zip(a, b)]), (A * B, [x * y for x, y in zip(a, b)]),
+                     (A - B, [x - y for x, y in zip(a, b)])):
+        for g, r, x, y in zip(got.to_mp(), ref, a, b):
+            assert abs(g - r) <= mp.mpf(2) ** -102 * max(abs(x), abs(y), abs(r)), (g, r)
+    s = A.sum(axis=0).to_mp()[0]
+    assert abs(s - sum(a)) < mp.mpf(2) ** -100 * sum(abs(x) for x in a)
+    assert A.pairs().shape == (50, 2) and isinstance(A[3:5], DD)
+
+
+def test_dd_tables_against_mpmath_quadrature_and_float64_tables():
+    from atomickohnsham_b200.basis import P1IntLegendreBasis
+    from atomickohnsham_b200.dd import build_femops_dd, pair_to_mp
+    from atomickohnsham_b200.femops import build_femops
+    mp.mp.dps = 45
+    mesh = make_mesh(["exp", 0, 50, 7, 1.3])
+    basis = P1IntLegendreBasis(mesh, ordermax=5)
+    ops = build_femops_dd(basis)
+    o64 = build_femops(basis)
+    for nm in ("M0_loc", "A_loc", "Mm1_loc", "Mm2_loc", "F_loc"):
+        a, b = getattr(ops, nm), getattr(o64, nm)
+        assert np.max(np.abs(a.hi - b)) <= 1e-13 * max(1.0, np.max(np.abs(b))), nm
+        assert np.all(np.abs(a.lo) <= 2.0 ** -52 * np.abs(a.hi) + 1e-300), nm
+
+    def gen(g, x):
+        if g == 0:
+            return 1 + x
+        if g == 1:
+            return 1 - x
+        k = g - 1
+        return (mp.legendre(k + 1, x) - mp.legendre(k - 1, x)) / (2 * k + 1)
+
+    def dgen(g, x):
+        return mp.mpf(1) if g == 0 else (mp.mpf(-1) if g == 1 else mp.legendre(g - 1, x))
+
+    pts = [mp.mpf(float(v)) for v in mesh.points]
+    for (c, i, j, m) in [(1, 0, 1, 2), (3, 4, 5, 3), (0, 0, 2, 2), (5, 1, 3, 5), (2, 0, 0, 0)]:
+        a, b = pts[c], pts[c + 1]
+        h2 = (b - a) / 2
+        mid = a + h2
+        ref = dict(
+            F=h2 * mp.quad(lambda x: gen(i, x) * gen(j, x) * gen(m, x) / (h2 * x + mid), [-1, 0, 1]),
+            Mm1=h2 * mp.quad(lambda x: gen(i, x) * gen(j, x) / (h2 * x + mid), [-1, 0, 1]),
+            Mm2=h2 * mp.quad(lambda x: gen(i, x) * gen(j, x) / (h2 * x + mid) ** 2, [-1, 0, 1]),
+            M0=h2 * mp.quad(lambda x: gen(i, x) * gen(j, x), [-1, 0, 1]),
+            A=mp.quad(lambda x: dgen(i, x) * dgen(j, x), [-1, 0, 1]) / h2)
+        got = dict(F=pair_to_mp(ops.F_loc.hi[c, i, j, m], ops.F_loc.lo[c, i, j, m]),
+                   **{k: pair_to_mp(getattr(ops, k + "_loc").hi[c, i, j], getattr(ops, k + "_loc").lo[c, i, j])
+                      for k in ("Mm1", "Mm2", "M0", "A")})
+        for k in ref:
+            assert abs(got[k] - ref[k]) <= mp.mpf("1e-29") * max(abs(ref[k]), 1 / h2, mp.mpf(1)), (c, i, j, m, k)
+    # global views: pairs, symmetric, COO keys of the Float64 builder
+    P = ops.assemble_pairs(ops.Mm1_loc)
+    assert P.shape == (basis.size, basis.size, 2) and np.array_equal(P[..., 0], P[..., 0].T)
+    assert np.max(np.abs(P[..., 0] - o64.Mm1)) < 1e-13
+    I, J, M, V = ops.F_coo_pairs()
+    i64, j64, m64, v64 = o64.F_coo()
+    d1 = {(a, b, c): x for a, b, c, x in zip(i64, j64, m64, v64)}
+    d2 = {(a, b, c): x for a, b, c, x in zip(I, J, M, V[:, 0])}
+    assert set(d1) == set(d2) and max(abs(d1[k] - d2[k]) for k in d1) < 1e-13
+
+
+def test_double64_golden_fixture_is_consistent():
+    """The transcribed reference log: 59 iterations, Etot = Ekin + Ecou + Ehar + Eexc to 1e-30, monotone
+    energies, final report == last iteration."""
+    mp.mp.dps = 50
+    g = load_golden("sodium_double64.json")
+    its = g["iterations"]
+    assert len(its) == 59 == g["final"]["niter"]
+    prev = None
+    for r in its:
+        e = {k: mp.mpf(r[k]) for k in ("Etot", "Ekin", "Ecou", "Ehar", "Eexc")}
+        assert abs(e["Etot"] - (e["Ekin"] + e["Ecou"] + e["Ehar"] + e["Eexc"])) < mp.mpf("1e-30") * abs(e["Etot"])
+        if prev is not None:
+            assert e["Etot"] <= prev + mp.mpf("1e-28")
+        prev = e["Etot"]
+    assert mp.mpf(its[-1]["Etot"]) == mp.mpf(g["final"]["Etot"])
+    assert mp.mpf(its[-1]["stop"]) < mp.mpf(g["setup"]["scftol"])

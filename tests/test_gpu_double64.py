@@ -1,0 +1,201 @@
+"""Double64 (T = Double64 of the reference) through the C ABI.
+
+The oracle for this row is the reference itself: `tests/golden/sodium_double64.json` transcribes the
+committed log of `examples/basic_example_doublefloat/` (sodium, Hartree only, scftol = 1e-20, 59 iterations,
+36 digits per number; made by tools/make_golden_dd.py).  Tolerances (north star: 1e-20 relative in Double64):
+Etot of EVERY iteration within 1e-24 relative (measured 1e-30), the energy components within
+max(1e-24, 1e-28 / stop), the iteration count +-1 (measured: 59 = 59, final stop 1.5777e-30 = the reference's).
+
+Why the components and the orbital energies of the END of the run cannot agree better than ~1e-15 absolute:
+the reference's run does not stop because D has converged to 1e-20 but because its line search returns
+t = 0 exactly (last line of the log: t = 0.0, stop = 1.6e-30 = |dE| alone).  The quadratic coefficient of the
+line search, a = h0 + h1 - 2 h01, is a difference of O(70) numbers of size ||dD||^2; below ||dD|| ~ 1e-13 it
+is rounding noise in ANY 106-bit arithmetic, so t (printed in the log) is noise from iteration ~50 on and the
+final D is the iterate at ||dD|| ~ 2e-15.  Etot is stationary (error ~ ||dD||^2 = 1e-30), Ekin / Ecou / Ehar
+and the orbital energies are first order in that residual.
+"""
+import mpmath as mp
+import numpy as np
+import pytest
+
+from helpers import load_golden, make_mesh
+
+pytestmark = pytest.mark.gpu
+
+NAMES = ["stop", "Etot", "Ekin", "Ecou", "Ehar", "Eexc", "t"]
+
+
+def _mpf(pair):
+    return mp.mpf(float(pair[0])) + mp.mpf(float(pair[1]))
+
+
+def _setup(g, **over):
+    from atomickohnsham_b200 import KSEDiscretization, KSEModel, ODA, OptimizedAufbau, P1IntLegendreBasis
+    from atomickohnsham_b200.solver import Batch
+    s = dict(g["setup"])
+    s.update(over)
+    basis = P1IntLegendreBasis(make_mesh(s["mesh"]), ordermax=s["p"])
+    model = KSEModel(Z=s["Z"], N=s["N"])
+    disc = KSEDiscretization(basis, model, lh=s["lh"], nh=s["nh"], dtype="double64")
+    alg = ODA(tinit=s["tinit"], scftol=s["scftol"],
+              aufbau=OptimizedAufbau(max_degen=s["max_degen"], tol=s["degen_tol"]))
+    return Batch([model], disc, alg), disc, model
+
+
+def _mantissa_match(ours, ref_str, rel):
+    """The reference prints t without its exponent unless it is 1.0 / 0.0 / 0.6: compare mantissas."""
+    ref = mp.mpf(ref_str)
+    if ref == 0:
+        return abs(ours) < rel
+    return any(abs(ours * mp.mpf(10) ** k - ref) <= rel * abs(ref) for k in range(0, 4))
+
+
+def test_sodium_double64_trajectory_matches_reference_log():
+    mp.mp.dps = 50
+    g = load_golden("sodium_double64.json")
+    bt, disc, _ = _setup(g)
+    its = g["iterations"]
+    worst = mp.mpf(0)
+    status = 0
+    k = 0
+    for k in range(100):
+        r = bt.step()[0]
+        rd = bt.records_dd()[0]
+        vals = {nm: _mpf(rd[i]) for i, nm in enumerate(NAMES)}
+        # the leading doubles of the record are the Float64 view of the same numbers
+        assert r["Etot"] == rd[1, 0] and r["stop"] == rd[0, 0]
+        if k < len(its):
+            ref = its[k]
+            # see the module docstring: the components carry the rounding noise of the line-search parameter,
+            # which grows like 1e-30 / stop; Etot (stationary) stays exact
+            tol = max(mp.mpf("1e-24"), mp.mpf("1e-28") / mp.mpf(ref["stop"]))
+            for nm in ("Ekin", "Ecou", "Ehar"):
+                dev = abs(vals[nm] - mp.mpf(ref[nm])) / abs(mp.mpf(ref[nm]))
+                assert dev < tol, (k, nm, mp.nstr(dev, 5))
+            dev = abs(vals["Etot"] - mp.mpf(ref["Etot"])) / abs(mp.mpf(ref["Etot"]))
+            assert dev < mp.mpf("1e-24"), (k, "Etot", mp.nstr(dev, 5))
+            worst = max(worst, dev)
+            if mp.mpf(ref["stop"]) > mp.mpf("1e-4"):
+                assert abs(vals["stop"] - mp.mpf(ref["stop"])) < mp.mpf("1e-18") * abs(mp.mpf(ref["stop"])), k
+                assert _mantissa_match(vals["t"], ref["t"], mp.mpf("1e-15")), (k, mp.nstr(vals["t"], 30), ref["t"])
+        status = r["status"]
+        if status != 0:
+            break
+    assert status == 1, status
+    fin = g["final"]
+    assert abs((k + 1) - fin["niter"]) <= 1, (k + 1, fin["niter"])
+    rd = bt.records_dd()[0]
+    for i, nm, tol in ((1, "Etot", "1e-28"), (2, "Ekin", "1e-15"), (3, "Ecou", "1e-15"), (4, "Ehar", "1e-15")):
+        dev = abs(_mpf(rd[i]) - mp.mpf(fin[nm])) / abs(mp.mpf(fin[nm]))
+        assert dev < mp.mpf(tol), (nm, mp.nstr(dev, 5))
+    assert _mpf(rd[0]) < mp.mpf("1e-20")
+    # orbital energies and occupations of the report (bit-exact integer occupations)
+    st = bt.state(0)
+    lab = {"1s": (0, 0), "2s": (0, 1), "3s": (0, 2), "2p": (1, 0)}
+    for name, ref in fin["orbitals"].items():
+        l, kk = lab[name]
+        e = _mpf(st["eps"][l, kk, 0])
+        assert abs(e - mp.mpf(ref["eps"])) < mp.mpf("2e-14"), (name, mp.nstr(e, 34))   # first order in the final dD
+        assert st["n"][l, kk, 0, 0] == float(ref["n"]) and st["n"][l, kk, 0, 1] == 0.0
+    occ = st["n"][..., 0, 0]
+    assert occ.sum() == 11.0 and np.count_nonzero(occ) == 4
+    # orthonormality in the mass matrix and the eigen-residuals of the last Hamiltonian's occupied pairs,
+    # evaluated on the host in double-double from the returned pairs: U^T M0 U = I to 1e-28
+    from atomickohnsham_b200.dd import DD
+    M0 = disc.femops.assemble_pairs(disc.femops.M0_loc)
+    M = DD(M0[..., 0], M0[..., 1])
+    U = st["U"]
+    for l in range(3):
+        V = DD(U[:, :4, l, 0, 0], U[:, :4, l, 0, 1])               # (Nh, 4)
+        MV = (M[:, :, None] * V[None, :, :]).sum(axis=1)            # (Nh, 4)
+        G = (V[:, :, None] * MV[:, None, :]).sum(axis=0)            # (4, 4)
+        err = np.abs(G.hi - np.eye(4)) + np.abs(G.lo)
+        assert err.max() < 1e-27, (l, err.max())
+    # trace(D M0) = N
+    D = st["D"]
+    Dd = DD(D[:, :, 0, 0], D[:, :, 0, 1])
+    tr = (Dd * M).sum(axis=0).sum(axis=0)
+    assert abs((float(tr.hi) - 11.0) + float(tr.lo)) < 1e-26
+    bt.close()
+
+
+def test_double64_run_and_float64_agree_and_errors():
+    """aks_scf_run on a Double64 batch; the Float64 path on the same discretization agrees to Float64
+    accuracy; unsupported options are refused loudly."""
+    from atomickohnsham_b200 import KSEDiscretization, KSEModel, ODA, OptimizedAufbau, P1IntLegendreBasis, LDA
+    from atomickohnsham_b200 import _capi
+    from atomickohnsham_b200.solver import Batch
+    mp.mp.dps = 50
+    g = load_golden("sodium_double64.json")
+    bt, disc, model = _setup(g)
+    final, hist = bt.run(100, history=True)
+    assert final[0]["status"] == 1 and abs(final[0]["niter"] - g["final"]["niter"]) <= 1
+    assert len(hist[0]) == final[0]["niter"]
+    e_dd = _mpf(bt.records_dd()[0][1])
+    assert abs(e_dd - mp.mpf(g["final"]["Etot"])) < mp.mpf("1e-24") * abs(e_dd)
+    # two problems in one batch (neutral atom and cation) are independent of each other
+    ion = KSEModel(Z=11, N=10)
+    bt2 = Batch([model, ion], disc, bt.alg)
+    f2, _ = bt2.run(100)
+    r2 = bt2.records_dd()
+    assert abs(_mpf(r2[0][1]) - e_dd) < mp.mpf("1e-28") * abs(e_dd)
+    assert f2[1]["status"] == 1 and _mpf(r2[1][1]) > e_dd
+    bt2.close()
+    # Float64 path, same mesh and basis
+    s = g["setup"]
+    basis = P1IntLegendreBasis(make_mesh(s["mesh"]), ordermax=s["p"])
+    d64 = KSEDiscretization(basis, model, lh=s["lh"], nh=s["nh"])
+    alg64 = ODA(tinit=0.6, scftol=1e-11, aufbau=OptimizedAufbau(max_degen=2, tol=1e-2))
+    b64 = Batch([model], d64, alg64)
+    f64, _ = b64.run(100)
+    assert abs(f64[0]["Etot"] - float(e_dd)) < 1e-10 * abs(float(e_dd))
+    b64.close()
+    # a functional on a Double64 discretization is refused (AKS_ENOSYS), as are the Float64-only hooks
+    with pytest.raises(_capi.AKSError) as ei:
+        Batch([LDA(Z=11, N=11)], disc, bt.alg)
+    assert ei.value.code == _capi.AKS_ENOSYS
+    with pytest.raises(_capi.AKSError) as ei:
+        bt.assemble_hartree(0)
+    assert ei.value.code == _capi.AKS_ENOSYS
+    bt.close()
+
+
+def test_double64_other_atoms_against_float64():
+    """Closed-shell and open-shell atoms on a small order-6 discretization: the Double64 result agrees with
+    the Float64 path to Float64 accuracy and satisfies the virial-free identities in double-double
+    (Etot = Ekin + Ecou + Ehar exactly as the reference assembles it)."""
+    from atomickohnsham_b200 import KSEDiscretization, KSEModel, ODA, OptimizedAufbau, P1IntLegendreBasis
+    from atomickohnsham_b200.solver import Batch
+    mp.mp.dps = 50
+    basis = P1IntLegendreBasis(make_mesh(["exp", 0, 100, 16, 1.5]), ordermax=6)
+    models = [KSEModel(Z=z, N=z) for z in (2, 4, 10, 12)]
+    ddisc = KSEDiscretization(basis, models[0], lh=1, nh=5, dtype="double64")
+    fdisc = KSEDiscretization(basis, models[0], lh=1, nh=5)
+    alg = ODA(tinit=0.6, scftol=1e-20, aufbau=OptimizedAufbau(max_degen=2, tol=1e-3))
+    bdd = Batch(models, ddisc, alg)
+    fdd, _ = bdd.run(200)
+    rdd = bdd.records_dd()
+    b64 = Batch(models, fdisc, ODA(tinit=0.6, scftol=1e-11, aufbau=OptimizedAufbau(max_degen=2, tol=1e-3)))
+    f64, _ = b64.run(200)
+    for i in range(len(models)):
+        assert fdd[i]["status"] == 1, (i, fdd[i])
+        e = [_mpf(rdd[i][q]) for q in range(1, 6)]
+        assert abs(e[0] - (e[1] + e[2] + e[3] + e[4])) < mp.mpf("1e-28") * abs(e[0])
+        assert abs(float(e[0]) - f64[i]["Etot"]) < 2e-10 * abs(f64[i]["Etot"]), (i, float(e[0]), f64[i]["Etot"])
+    bdd.close()
+    b64.close()
+    # the C2 / C4 discretization (order 20, 40 cells, Nh = 799): neon and the fluoride anion, Hartree only
+    basis = P1IntLegendreBasis(make_mesh(["exp", 0, 300, 41, 1.5]), ordermax=20)
+    models = [KSEModel(Z=10, N=10), KSEModel(Z=9, N=10)]
+    ddisc = KSEDiscretization(basis, models[0], lh=1, nh=4, dtype="double64")
+    fdisc = KSEDiscretization(basis, models[0], lh=1, nh=4)
+    bdd = Batch(models, ddisc, alg)
+    fdd, _ = bdd.run(200)
+    rdd = bdd.records_dd()
+    b64 = Batch(models, fdisc, ODA(tinit=0.6, scftol=1e-11, aufbau=OptimizedAufbau(max_degen=2, tol=1e-3)))
+    f64, _ = b64.run(200)
+    for i in range(len(models)):
+        assert fdd[i]["status"] == 1, (i, fdd[i])
+        assert abs(float(_mpf(rdd[i][1])) - f64[i]["Etot"]) < 2e-10 * abs(f64[i]["Etot"]), (i, fdd[i], f64[i])
+    bdd.close()
+    b64.close()
