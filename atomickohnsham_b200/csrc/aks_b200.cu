@@ -123,7 +123,8 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
                            aks_batch** out);
 static void dd_batch_free(aks_batch* bt);
 static int dd_batch_reset(aks_batch* bt);
-static int dd_set_oda(aks_batch* bt, double scftol, double tinit, int frozen_t, int max_degen, double degen_tol);
+static int dd_set_oda(aks_batch* bt, double scftol, double tinit, int frozen_t, int max_degen, double degen_tol,
+                      int maxiter_ls, double abstol_ls, double reltol_ls);
 static int dd_step_launch(aks_batch* bt);
 static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* eps, double* nocc, double* W);
 #define DD_UNSUPPORTED(bt, what)                                                               \
@@ -578,7 +579,7 @@ extern "C" int aks_batch_set_oda(aks_batch* bt, double scftol, double tinit, int
   if (!(scftol >= 0) || !(tinit >= 0 && tinit <= 1) || maxiter_ls < 1 || max_degen < 1 || !(degen_tol >= 0)) {
     ctx->err = "aks_batch_set_oda: bad option"; return AKS_EINVAL;
   }
-  if (bt->dd) return dd_set_oda(bt, scftol, tinit, frozen_t, max_degen, degen_tol);
+  if (bt->dd) return dd_set_oda(bt, scftol, tinit, frozen_t, max_degen, degen_tol, maxiter_ls, abstol_ls, reltol_ls);
   BatchDev& b = bt->dev;
   b.scftol = scftol; b.tinit = tinit; b.frozen_t = frozen_t; b.maxiter_ls = maxiter_ls;
   b.abstol_ls = abstol_ls; b.reltol_ls = reltol_ls; b.max_degen = max_degen; b.degen_tol = degen_tol;

@@ -11,6 +11,7 @@ struct DDDiscHost {
 struct DDBatchHost {
   DDBatchDev dev{};
   int max_orb_launch = DD_MAXORB;
+  bool any_xc = false;
 };
 
 static inline dd ddh_pair(const double* a, size_t idx) { return dd_make(a[2 * idx], a[2 * idx + 1]); }
@@ -34,10 +35,15 @@ static int dd_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** out) 
   DDDiscDev& dv = disc->dd->dev;
   dv.p = p; dv.n = n; dv.nb = nb; dv.C = C; dv.Nh = Nh; dv.L = D->lh + 1; dv.nh = D->nh;
   dv.Rmax = ddh_pair(D->mesh, C);
+  dv.Q = D->Q; dv.G = D->G;
+  if (D->Q < 0 || D->G < 0 || (D->Q > 0) != (D->G > 0)) { ctx->err = "aks_disc_create(dtype=1): Q and G must both be 0 or both positive"; dd_disc_free(disc); delete disc; return AKS_EINVAL; }
+  if (D->Q > 0 && (!D->x || !D->w || !D->Pgenx || !D->invshifts || !D->y || !D->wy || !D->ycell || !D->Pgeny)) {
+    ctx->err = "aks_disc_create(dtype=1): Q > 0 needs x, w, Pgenx, invshifts, y, wy, ycell, Pgeny"; dd_disc_free(disc); delete disc; return AKS_EINVAL;
+  }
   {  // the Float64 view carries the sizes only
     DiscDev& d0 = disc->dev;
     d0.p = p; d0.n = n; d0.nb = nb; d0.C = C; d0.Nh = Nh; d0.L = dv.L; d0.nh = dv.nh; d0.nspin = 1;
-    d0.Q = 0; d0.G = 0; d0.Rmax = dv.Rmax.hi;
+    d0.Q = D->Q; d0.G = D->G; d0.Rmax = dv.Rmax.hi;
   }
   std::vector<int>& l2g = disc->l2g;
   l2g.assign((size_t)C * n, -1);
@@ -114,10 +120,29 @@ static int dd_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** out) 
       e2 = e2 + half;
     }
   }
+  // Gauss tables (pairs; Pgenx / Pgeny column-major (p+1, Q) -> [g][q])
+  const int Q = D->Q, G = D->G;
+  std::vector<dd> Pg((size_t)n * Q), Pgy((size_t)n * G), xv(Q), wv(Q), yv(G), wyv(G), inv1(C), inv2(C);
+  std::vector<int> ycell(G);
+  if (Q > 0) {
+    for (int g = 0; g < n; ++g) {
+      for (int q = 0; q < Q; ++q) Pg[(size_t)g * Q + q] = ddh_pair(D->Pgenx, (size_t)g + (size_t)n * q);
+      for (int q = 0; q < G; ++q) Pgy[(size_t)g * G + q] = ddh_pair(D->Pgeny, (size_t)g + (size_t)n * q);
+    }
+    for (int q = 0; q < Q; ++q) { xv[q] = ddh_pair(D->x, q); wv[q] = ddh_pair(D->w, q); }
+    for (int q = 0; q < G; ++q) {
+      yv[q] = ddh_pair(D->y, q); wyv[q] = ddh_pair(D->wy, q);
+      const int64_t cc = D->ycell[q];
+      if (cc < 1 || cc > C) { ctx->err = "ycell out of range"; aks_disc_destroy(disc); return AKS_EINVAL; }
+      ycell[q] = (int)cc - 1;
+    }
+    for (int c = 0; c < C; ++c) { inv1[c] = ddh_pair(D->invshifts, 2 * (size_t)c); inv2[c] = ddh_pair(D->invshifts, 2 * (size_t)c + 1); }
+  }
   int rc;
 #define UPD(vec, field)                                                                          \
   if ((rc = dev_upload(ctx, disc->allocs, vec, &dv.field)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
   UPD(Al, A_loc) UPD(M0l, M0_loc) UPD(M1l, Mm1_loc) UPD(M2l, Mm2_loc) UPD(Fl, F_loc) UPD(l2g, l2g)
+  UPD(Pg, Pg) UPD(Pgy, Pgy) UPD(xv, xq) UPD(wv, wq) UPD(yv, y) UPD(wyv, wy) UPD(ycell, ycell) UPD(inv1, inv1) UPD(inv2, inv2)
 #undef UPD
   if ((rc = dev_zeros<dd>(ctx, disc->allocs, (size_t)C * n * n, &dv.Afac)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
   if ((rc = dev_zeros<dd>(ctx, disc->allocs, (size_t)2 * DD_NT, &dv.Atri)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
@@ -145,6 +170,10 @@ static int dd_batch_reset(aks_batch* bt) {
   CK(cudaMemsetAsync(b.status, 0, sizeof(int) * B, ctx->stream));
   CK(cudaMemsetAsync(b.warm, 0, sizeof(int) * B, ctx->stream));
   CK(cudaMemsetAsync(b.eig_fail, 0, sizeof(int) * B, ctx->stream));
+  if (bt->dd->any_xc) {
+    CK(cudaMemsetAsync(b.rho_q, 0, sizeof(dd) * B * dv.C * dv.Q, ctx->stream));
+    CK(cudaMemsetAsync(b.rho_y, 0, sizeof(dd) * B * dv.G, ctx->stream));
+  }
   CK(cudaMemsetAsync(b.rec, 0, sizeof(dd) * B * 7, ctx->stream));
   CK(cudaMemsetAsync(b.rec64, 0, sizeof(aks_iter_record) * B, ctx->stream));
   std::vector<dd> tv(B, dd_make(b.tinit));
@@ -158,12 +187,19 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
                            aks_batch** out) {
   aks_ctx* ctx = disc->ctx;
   const DDDiscDev& dv = disc->dd->dev;
-  for (int i = 0; i < nprob; ++i)
-    if ((ex_id && ex_id[i] != AKS_XC_NONE) || (ec_id && ec_id[i] != AKS_XC_NONE)) {
-      ctx->err = "dtype=1 (Double64): exchange-correlation functionals are not built (the reference's own Double64 "
-                 "example runs without one)";
-      return AKS_ENOSYS;
+  std::vector<int> ex(nprob, 0), ec(nprob, 0);
+  for (int i = 0; i < nprob; ++i) {
+    if (ex_id) ex[i] = ex_id[i];
+    if (ec_id) ec[i] = ec_id[i];
+    if ((ex[i] != AKS_XC_NONE && ex[i] != AKS_LDA_X) || (ec[i] != AKS_XC_NONE && ec[i] != AKS_LDA_C_PW)) {
+      ctx->err = "unsupported functional id (LDA only: ex in {0,1}, ec in {0,12})"; return AKS_EINVAL;
     }
+    if ((ex[i] || ec[i]) && dv.Q == 0) {
+      ctx->err = "dtype=1 (Double64): this discretization was created without Gauss tables (Q = 0), a functional "
+                 "needs them";
+      return AKS_EINVAL;
+    }
+  }
   aks_batch* bt = new aks_batch();
   bt->disc = disc;
   bt->B = nprob;
@@ -185,9 +221,13 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   }
   int rc;
 #define UPB(vec, field) if ((rc = dev_upload(ctx, bt->allocs, vec, &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
-  UPB(bt->hZ, Z) UPB(bt->hN, N) UPB(bt->hHar, hartree) UPB(bt->hLp, Lp) UPB(bt->hnhp, nhp)
+  UPB(bt->hZ, Z) UPB(bt->hN, N) UPB(bt->hHar, hartree) UPB(bt->hLp, Lp) UPB(bt->hnhp, nhp) UPB(ex, ex) UPB(ec, ec)
 #undef UPB
-  const size_t B = nprob, Nh = dv.Nh, C = dv.C, L = dv.L, nh = dv.nh, n = dv.n;
+  const size_t B = nprob, Nh = dv.Nh, C = dv.C, L = dv.L, nh = dv.nh, n = dv.n, Q = dv.Q, G = dv.G;
+  bool any_xc = false;
+  for (int i = 0; i < nprob; ++i) any_xc = any_xc || ex[i] || ec[i];
+  bt->dd->any_xc = any_xc;
+  const size_t xq = any_xc ? Q : 0, xg = any_xc ? G : 0;   // batches without a functional hold no node arrays
   b.nparts = (int)std::min<size_t>((Nh * Nh + 255) / 256, 148);
 #define ZB(T, field, count) if ((rc = dev_zeros<T>(ctx, bt->allocs, (count), &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; }
   ZB(dd, D, B * Nh * Nh) ZB(dd, Bv, B * Nh) ZB(dd, Wv, B * Nh) ZB(dd, E, B * 5) ZB(dd, t, B) ZB(int, niter, B)
@@ -198,8 +238,11 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   ZB(dd, bloc, B * DD_MAXORB * C * n) ZB(dd, borb, B * DD_MAXORB * Nh) ZB(dd, worb, B * DD_MAXORB * Nh)
   ZB(dd, Bnew, B * Nh) ZB(dd, Wnew, B * Nh) ZB(dd, Enew, B * 5) ZB(dd, tmix, B) ZB(dd, tnew, B)
   ZB(dd, norm_part, B * b.nparts) ZB(dd, rec, B * 7) ZB(aks_iter_record, rec64, B)
+  ZB(dd, rho_q, B * C * xq) ZB(dd, rho_y, B * xg) ZB(dd, fxc, B * C * xq) ZB(dd, rho_q_new, B * 2 * C * xq)
+  ZB(dd, rho_y_new, B * 2 * xg) ZB(dd, corr_part, B * 2 * C) ZB(dd, td, B)
 #undef ZB
   b.scftol = 1e-10; b.tinit = 0.6; b.frozen_t = 0; b.max_degen = 2; b.degen_tol = 1e-3;
+  b.abstol_ls = b.reltol_ls = 4.930380657631324e-28; b.maxiter_ls = 100;   // 1e4 eps(Double64), oda/types.jl:39-40
   // the generic driver (aks_scf_run, fetch_records) reads the records and status words through the Float64 view
   bt->dev.B = nprob; bt->dev.s = 1; bt->dev.Lmax = dv.L; bt->dev.nhmax = dv.nh;
   bt->dev.rec = b.rec64;
@@ -215,10 +258,12 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   return dd_batch_reset(bt);
 }
 
-static int dd_set_oda(aks_batch* bt, double scftol, double tinit, int frozen_t, int max_degen, double degen_tol) {
+static int dd_set_oda(aks_batch* bt, double scftol, double tinit, int frozen_t, int max_degen, double degen_tol,
+                      int maxiter_ls, double abstol_ls, double reltol_ls) {
   aks_ctx* ctx = bt->disc->ctx;
   DDBatchDev& b = bt->dd->dev;
   b.scftol = scftol; b.tinit = tinit; b.frozen_t = frozen_t; b.max_degen = max_degen; b.degen_tol = degen_tol;
+  b.maxiter_ls = maxiter_ls; b.abstol_ls = abstol_ls; b.reltol_ls = reltol_ls;
   std::vector<dd> tv(bt->B, dd_make(tinit));
   CK(cudaMemcpyAsync(b.t, tv.data(), sizeof(dd) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
@@ -232,6 +277,10 @@ static int dd_step_launch(aks_batch* bt) {
   cudaStream_t st = ctx->stream;
   const int B = bt->B, no = bt->dd->max_orb_launch;
   CK(cudaMemsetAsync(b.eig_fail, 0, sizeof(int) * B, st));
+  if (bt->dd->any_xc) {
+    ddk_xc<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
+    LAUNCH_CHECK();
+  }
   ddk_H<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
   LAUNCH_CHECK();
   ddk_eig<<<dim3(dv.nh, dv.L, B), DD_NT, 0, st>>>(dv, b);
@@ -242,6 +291,12 @@ static int dd_step_launch(aks_batch* bt) {
   LAUNCH_CHECK();
   ddk_poisson<<<dim3(no, B), DD_NT, 0, st>>>(dv, b);
   LAUNCH_CHECK();
+  if (bt->dd->any_xc) {
+    ddk_rho_nodes<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
+    LAUNCH_CHECK();
+    ddk_rho_grid<<<dim3((dv.G + 127) / 128, B), 128, 0, st>>>(dv, b);
+    LAUNCH_CHECK();
+  }
   ddk_decide<<<B, 128, 0, st>>>(dv, b);
   LAUNCH_CHECK();
   ddk_mix<<<dim3(b.nparts, B), 256, 0, st>>>(dv, b);
@@ -290,3 +345,22 @@ extern "C" int aks_get_records_dd(aks_batch* bt, double* out) {
 
 static void dd_disc_free(aks_disc* disc) { delete disc->dd; disc->dd = nullptr; }
 static void dd_batch_free(aks_batch* bt) { delete bt->dd; bt->dd = nullptr; }
+
+// test hook: pointwise vxc / exc per particle of the Double64 functionals; rho, vrho, zk: npts (hi, lo) pairs
+extern "C" int aks_dd_xc_eval(aks_ctx* ctx, int32_t npts, const double* rho, int32_t ex_id, int32_t ec_id,
+                              double* vrho, double* zk) {
+  if (!ctx || npts < 1 || !rho || !vrho || !zk) return AKS_EINVAL;
+  dd *dr = nullptr, *dv_ = nullptr, *dz = nullptr;
+  const size_t bytes = sizeof(dd) * (size_t)npts;
+  CK(cudaMallocAsync((void**)&dr, bytes, ctx->stream));
+  CK(cudaMallocAsync((void**)&dv_, bytes, ctx->stream));
+  CK(cudaMallocAsync((void**)&dz, bytes, ctx->stream));
+  CK(cudaMemcpyAsync(dr, rho, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  ddk_xc_eval<<<(npts + 127) / 128, 128, 0, ctx->stream>>>(dr, npts, ex_id, ec_id, dv_, dz);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(vrho, dv_, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(zk, dz, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFreeAsync(dr, ctx->stream); cudaFreeAsync(dv_, ctx->stream); cudaFreeAsync(dz, ctx->stream);
+  return AKS_OK;
+}

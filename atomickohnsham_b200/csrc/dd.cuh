@@ -89,6 +89,60 @@ DD_HD dd dd_min(dd a, dd b) { return (a < b) ? a : b; }
 DD_HD dd dd_max(dd a, dd b) { return (a < b) ? b : a; }
 DD_HD bool dd_isfinite(dd a) { return isfinite(a.hi) && isfinite(a.lo); }
 
+// ---- elementary functions (the reference's Double64 functionals call log, ^ and sqrt of DoubleFloats)
+#define DD_LN2_HI 6.931471805599452862e-01
+#define DD_LN2_LO 2.319046813846299558e-17
+DD_HD dd dd_ldexp(dd a, int e) { return dd_make(ldexp(a.hi, e), ldexp(a.lo, e)); }
+// exp: x = k ln2 + r, r / 256 by Taylor on expm1, eight doublings p <- 2p + p^2, 2^k
+DD_HD dd dd_exp(dd x) {
+  if (x.hi <= -709.0) return dd_make(0.0);
+  if (x.hi >= 709.0) return dd_make(INFINITY);
+  const double kf = floor(x.hi / DD_LN2_HI + 0.5);
+  const dd ln2 = dd_make(DD_LN2_HI, DD_LN2_LO);
+  dd r = dd_ldexp(x - ln2 * kf, -8);
+  // expm1(r) = r + r^2/2! + ... (|r| < 1.4e-3: 11 terms reach 1e-36)
+  dd term = r, p = r;
+  for (int n = 2; n <= 11; ++n) {
+    term = (term * r) / (double)n;
+    p = p + term;
+  }
+  for (int i = 0; i < 8; ++i) p = p * 2.0 + p * p;
+  return dd_ldexp(p + 1.0, (int)kf);
+}
+// log by one Newton step on exp from the double logarithm: y <- y + x exp(-y) - 1
+DD_HD dd dd_log(dd x) {
+  if (x.hi <= 0.0) return dd_make(x.hi == 0.0 ? -INFINITY : NAN);
+  dd y = dd_make(log(x.hi));
+  y = y + (x * dd_exp(-y) - 1.0);
+  return y;
+}
+// log(1 + e) without forming 1 + e when e is small: 2 atanh(e / (2 + e))
+DD_HD dd dd_log1p(dd e) {
+  if (fabs(e.hi) > 0.25) return dd_log(e + 1.0);
+  const dd z = e / (e + 2.0), z2 = z * z;
+  dd term = z, acc = z;
+  for (int k = 3; k <= 61; k += 2) {
+    term = term * z2;
+    const dd add = term / (double)k;
+    acc = acc + add;
+    if (fabs(add.hi) < 1e-36 * fabs(acc.hi)) break;
+  }
+  return acc * 2.0;
+}
+DD_HD dd dd_pow(dd x, dd e) {   // x > 0
+  if (x.hi <= 0.0) return dd_make(0.0);
+  return dd_exp(e * dd_log(x));
+}
+DD_HD dd dd_cbrt(dd x) {        // x > 0: two Newton steps from the double cube root
+  if (x.hi <= 0.0) return dd_make(0.0);
+  dd y = dd_make(cbrt(x.hi));
+  for (int i = 0; i < 2; ++i) {
+    const dd y2 = y * y;
+    y = y - (y2 * y - x) / (y2 * 3.0);
+  }
+  return y;
+}
+
 // ---- a scalar trait so that the cell-local linear algebra (static condensation, LDL^T, Sturm counts) is
 // written once and instantiated for double (bracketing) and dd (the results)
 template <class R> struct Sc;

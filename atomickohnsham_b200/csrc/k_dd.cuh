@@ -18,8 +18,14 @@
 //   ddk_mix      D = t D_new + (1-t) D_prev (loop.jl:100) with density! (density.jl:15-41) folded in, ||dD||_F
 //   ddk_finish   stopping rule (loop.jl:43-49), record, state mixing
 //
-// Exchange-correlation in dd is not built: the reference's own Double64 example runs without a functional
-// (its Gauss tables are Float64-only, run.jl:9-20); batches on a dd discretization must have ex = ec = none.
+//   ddk_xc       evaluate_vrho! in dd (models.jl:97-105; SlaterXa.jl:11-12, PerdewWang.jl:15-43) at the Gauss nodes
+//   ddk_rho*     optimized_eval_density! / eval_density! (assemble.jl:91-125, density.jl:97-126) from the orbitals,
+//                for both extreme fillings, and <Vxc[D_prev], D_new> (energies.jl:15-24)
+// With a functional, ddk_H adds B^T diag(w v) B (assemble.jl:277-319, local matrix.jl:129-155) and ddk_decide runs
+// Optim's Brent in dd on a t^2 + b t + c + Exc[t rho_A + (1-t) rho_B] (rho is linear in D).  The number-type
+// mixture of the reference's Double64 run is kept: (3/pi)^(1/3), 4 pi, 1/(4 pi) and the
+// PW92 parameters are Float64 values, rho^(1/3) of Slater exchange is rho^Double64(Float64(1/3)), the rational
+// powers of PW92 are exact.  Spin-unpolarised functionals only (nspin = 1).
 #pragma once
 #include "dd.cuh"
 
@@ -36,6 +42,17 @@ struct DDDiscDev {
   const dd* Mm2_loc;
   const dd* F_loc;    // [C][n (m)][n*n (ij)]
   const int* l2g;     // [C][n]
+  // Gauss tables (NULL / 0 when the discretization was created without them: no functional possible)
+  int Q, G;
+  const dd* Pg;       // [n][Q]  generator g at Gauss node q
+  const dd* xq;       // [Q]
+  const dd* wq;       // [Q]
+  const dd* inv1;     // [C]  h/2
+  const dd* inv2;     // [C]  midpoint
+  const dd* y;        // [G]
+  const dd* wy;       // [G]
+  const int* ycell;   // [G]  0-based
+  const dd* Pgy;      // [n][G]
   dd* Afac;           // [C][n][n]  condensed factors of the stiffness blocks (ddk_setup)
   dd* Atri;           // [2][64]    inverse pivots / multipliers of the hat system
 };
@@ -43,9 +60,16 @@ struct DDDiscDev {
 struct DDBatchDev {
   int B, L, nh;
   const double *Z, *N, *hartree;
-  const int *Lp, *nhp;
-  double scftol, tinit, degen_tol;
-  int frozen_t, max_degen;
+  const int *Lp, *nhp, *ex, *ec;
+  double scftol, tinit, degen_tol, abstol_ls, reltol_ls;
+  int frozen_t, max_degen, maxiter_ls;
+  dd* rho_q;      // [B][C][Q]     mixed density at the Gauss nodes
+  dd* rho_y;      // [B][G]        mixed density on the energy grid
+  dd* fxc;        // [B][C][Q]     w_q vxc(rho(q))
+  dd* rho_q_new;  // [B][2][C][Q]  the two extreme fillings of the trial density
+  dd* rho_y_new;  // [B][2][G]
+  dd* corr_part;  // [B][2][C]     <Vxc[D_prev], D_new> per cell
+  dd* td;         // [B]           weight of filling 0 in the trial density
   dd* D;        // [B][Nh][Nh]
   dd* Bv;       // [B][Nh]   F:D of the mixed density
   dd* Wv;       // [B][Nh]   A^-1 Bv
@@ -315,15 +339,174 @@ __global__ void __launch_bounds__(DD_NT) ddk_setup(DDDiscDev dv) {
   }
 }
 
+// ------------------------------------------------------------------ LDA exchange-correlation in dd
+// Number-type mixture of the reference's Double64 run: Float64 constants, the Slater
+// exponent is Float64(1/3) promoted to Double64, PW92's rational powers are exact.
+#define DD_CX 0.9847450218426965        // Float64 (3/pi)^(1/3)          (SlaterXa.jl:12)
+#define DD_CX34 (-0.7385587663820223)   // Float64 -3/4 * (3/pi)^(1/3)   (SlaterXa.jl:11)
+#define DD_THIRD_F64 0.3333333333333333 // Float64 1/3, the exponent of rho^(1/3)
+#define DD_FOURPI 12.566370614359172    // Float64 4 pi
+#define DD_INV4PI 0.07957747154594767   // Float64 1/(4 pi)              (assemble.jl:123)
+
+// G(rs) and dG/drs of PW92 with the zeta = 0 parameters (PerdewWang.jl:15-30)
+__device__ void dd_pw_G(dd rs, dd& G, dd& dG, bool want_d) {
+  const double A = 0.031091, a1 = 0.21370, b1 = 7.5957, b2 = 3.5876, b3 = 1.6382, b4 = 0.49294;
+  const dd sq = dd_sqrt(rs);
+  const dd Q0 = (rs * a1 + 1.0) * (-2.0 * A);
+  const dd Q1 = (sq * b1 + rs * b2 + (rs * sq) * b3 + (rs * rs) * b4) * (2.0 * A);
+  const dd lg = dd_log1p(dd_inv(Q1));
+  G = Q0 * lg;
+  if (want_d) {
+    const double dQ0 = -2.0 * A * a1;
+    const dd dQ1 = (dd_make(b1) / (sq * 2.0) + b2 + sq * (1.5 * b3) + rs * (2.0 * b4)) * (2.0 * A);
+    dG = lg * dQ0 - (Q0 * dQ1) / (Q1 * (Q1 + 1.0));
+  }
+}
+__device__ dd dd_rs_of_rho(dd rho) { return dd_cbrt(dd_make(3.0) / (rho * DD_FOURPI)); }   // PerdewWang.jl:34
+// vxc = vx + vc at rho >= 0 (clamped by the caller, BuiltinFunctional.jl:112); zero at rho = 0
+__device__ dd dd_xc_vrho(dd rho, int ex, int ec) {
+  dd v = dd_make(0.0);
+  if (rho.hi <= 0.0) return v;
+  if (ec == 12) {
+    const dd rs = dd_rs_of_rho(rho);
+    dd G, dG;
+    dd_pw_G(rs, G, dG, true);
+    v = v + (G - (rs / 3.0) * dG);
+  }
+  if (ex == 1) v = v - dd_pow(rho, dd_make(DD_THIRD_F64)) * DD_CX;
+  return v;
+}
+// exc per particle
+__device__ dd dd_xc_zk(dd rho, int ex, int ec) {
+  dd e = dd_make(0.0);
+  if (rho.hi <= 0.0) return e;
+  if (ec == 12) {
+    dd G, dG;
+    dd_pw_G(dd_rs_of_rho(rho), G, dG, false);
+    e = e + G;
+  }
+  if (ex == 1) e = e + dd_pow(rho, dd_make(DD_THIRD_F64)) * DD_CX34;
+  return e;
+}
+// test hook: pointwise vrho / zk of an array of densities
+__global__ void ddk_xc_eval(const dd* rho, int npts, int ex, int ec, dd* vrho, dd* zk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  const dd r = dd_max(rho[i], dd_make(0.0));
+  vrho[i] = dd_xc_vrho(r, ex, ec);
+  zk[i] = dd_xc_zk(r, ex, ec);
+}
+
+// f = w_q vxc(rho(q)) at every Gauss node of every cell
+__global__ void __launch_bounds__(128) ddk_xc(DDDiscDev dv, DDBatchDev bt) {
+  const int c = blockIdx.x, b = blockIdx.y;
+  if (bt.status[b] != 0) return;
+  const int ex = bt.ex[b], ec = bt.ec[b];
+  if (ex == 0 && ec == 0) return;
+  const size_t off = ((size_t)b * dv.C + c) * dv.Q;
+  for (int q = threadIdx.x; q < dv.Q; q += blockDim.x)
+    bt.fxc[off + q] = dv.wq[q] * dd_xc_vrho(dd_max(bt.rho_q[off + q], dd_make(0.0)), ex, ec);
+}
+
+// rho of the two extreme fillings at the Gauss nodes of cell c, from the orbitals, and <Vxc[D_prev], D_new>
+__global__ void __launch_bounds__(128) ddk_rho_nodes(DDDiscDev dv, DDBatchDev bt) {
+  const int c = blockIdx.x, b = blockIdx.y, n = dv.n, Q = dv.Q;
+  if (bt.status[b] != 0) return;
+  if (bt.ex[b] == 0 && bt.ec[b] == 0) return;
+  __shared__ dd ul[32 * DD_MAXN];
+  __shared__ dd red0[128], red1[128];
+  const int no = min(bt.norb[b], 32);
+  for (int idx = threadIdx.x; idx < no * n; idx += blockDim.x) {
+    const int o = idx / n, g = idx - o * n;
+    const int lk = bt.orb_lk[(size_t)b * DD_MAXORB + o], gi = dv.l2g[c * n + g];
+    const dd* u = bt.U + (((size_t)b * bt.L + (lk >> 8)) * bt.nh + (lk & 0xff)) * dv.Nh;
+    ul[idx] = (gi >= 0) ? u[gi] : dd_make(0.0);
+  }
+  __syncthreads();
+  const dd* n0 = bt.orb_n0 + (size_t)b * DD_MAXORB;
+  const dd* n1 = bt.orb_n1 + (size_t)b * DD_MAXORB;
+  const dd* f = bt.fxc + ((size_t)b * dv.C + c) * Q;
+  dd* out0 = bt.rho_q_new + (((size_t)b * 2 + 0) * dv.C + c) * Q;
+  dd* out1 = bt.rho_q_new + (((size_t)b * 2 + 1) * dv.C + c) * Q;
+  dd c0 = dd_make(0.0), c1 = dd_make(0.0);
+  for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    dd a0 = dd_make(0.0), a1 = dd_make(0.0);
+    for (int o = 0; o < no; ++o) {
+      dd psi = dd_make(0.0);
+      for (int g = 0; g < n; ++g) psi = psi + ul[o * n + g] * dv.Pg[(size_t)g * Q + q];
+      const dd p2 = psi * psi;
+      a0 = a0 + p2 * n0[o];
+      a1 = a1 + p2 * n1[o];
+    }
+    const dd r = dv.inv1[c] * dv.xq[q] + dv.inv2[c];
+    const dd r2 = r * r;
+    out0[q] = (a0 / r2) * DD_INV4PI;     // divide, then multiply (assemble.jl:121-123)
+    out1[q] = (a1 / r2) * DD_INV4PI;
+    c0 = c0 + f[q] * a0;
+    c1 = c1 + f[q] * a1;
+  }
+  red0[threadIdx.x] = c0;
+  red1[threadIdx.x] = c1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dd s0 = dd_make(0.0), s1 = dd_make(0.0);
+    for (int i = 0; i < 128; ++i) { s0 = s0 + red0[i]; s1 = s1 + red1[i]; }
+    bt.corr_part[((size_t)b * 2 + 0) * dv.C + c] = s0 * dv.inv1[c];
+    bt.corr_part[((size_t)b * 2 + 1) * dv.C + c] = s1 * dv.inv1[c];
+  }
+}
+// the same on the global energy grid (eval_density!, density.jl:97-126)
+__global__ void __launch_bounds__(128) ddk_rho_grid(DDDiscDev dv, DDBatchDev bt) {
+  const int b = blockIdx.y, n = dv.n, G = dv.G;
+  if (bt.status[b] != 0) return;
+  if (bt.ex[b] == 0 && bt.ec[b] == 0) return;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= G) return;
+  const int c = dv.ycell[q], no = min(bt.norb[b], 32);
+  dd a0 = dd_make(0.0), a1 = dd_make(0.0);
+  for (int o = 0; o < no; ++o) {
+    const int lk = bt.orb_lk[(size_t)b * DD_MAXORB + o];
+    const dd* u = bt.U + (((size_t)b * bt.L + (lk >> 8)) * bt.nh + (lk & 0xff)) * dv.Nh;
+    dd psi = dd_make(0.0);
+    for (int g = 0; g < n; ++g) {
+      const int gi = dv.l2g[c * n + g];
+      if (gi >= 0) psi = psi + u[gi] * dv.Pgy[(size_t)g * G + q];
+    }
+    const dd p2 = psi * psi;
+    a0 = a0 + p2 * bt.orb_n0[(size_t)b * DD_MAXORB + o];
+    a1 = a1 + p2 * bt.orb_n1[(size_t)b * DD_MAXORB + o];
+  }
+  const dd den = (dv.y[q] * dv.y[q]) * DD_FOURPI;
+  bt.rho_y_new[((size_t)b * 2 + 0) * G + q] = a0 / den;
+  bt.rho_y_new[((size_t)b * 2 + 1) * G + q] = a1 / den;
+}
+
 // ------------------------------------------------------------------ Hamiltonian blocks
 __global__ void __launch_bounds__(128) ddk_H(DDDiscDev dv, DDBatchDev bt) {
   const int c = blockIdx.x, b = blockIdx.y, n = dv.n, nn = n * n;
   if (bt.status[b] != 0) return;
   __shared__ dd Wl[DD_MAXN];
+  __shared__ dd Vs[DD_MAXN * DD_MAXN];
   const double har = bt.hartree[b];
+  const bool has_xc = bt.ex[b] != 0 || bt.ec[b] != 0;
   if (threadIdx.x < n) {
     const int g = dv.l2g[c * n + threadIdx.x];
     Wl[threadIdx.x] = (g >= 0 && har != 0.0) ? bt.Wv[(size_t)b * dv.Nh + g] : dd_make(0.0);
+  }
+  // exchange-correlation block of the cell: K_ij = h/2 sum_q (w v)_q g_i(x_q) g_j(x_q), lower triangle
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+    const int i = e / n, j = e - i * n;
+    if (j > i) continue;
+    dd acc = dd_make(0.0);
+    if (has_xc && dv.l2g[c * n + i] >= 0 && dv.l2g[c * n + j] >= 0) {
+      const dd* f = bt.fxc + ((size_t)b * dv.C + c) * dv.Q;
+      const dd* gi = dv.Pg + (size_t)i * dv.Q;
+      const dd* gj = dv.Pg + (size_t)j * dv.Q;
+      for (int q = 0; q < dv.Q; ++q) acc = acc + (gi[q] * gj[q]) * f[q];
+      acc = acc * dv.inv1[c];
+    }
+    Vs[i * n + j] = acc;
+    Vs[j * n + i] = acc;
   }
   __syncthreads();
   const dd shift = dd_make(bt.N[b]) / dv.Rmax;
@@ -334,6 +517,7 @@ __global__ void __launch_bounds__(128) ddk_H(DDDiscDev dv, DDBatchDev bt) {
       for (int m = 0; m < n; ++m) fw = fw + dv.F_loc[((size_t)c * n + m) * nn + e] * Wl[m];
       fw = (fw + shift * dv.M0_loc[(size_t)c * nn + e]) * har;
     }
+    fw = fw + Vs[e];
     const dd a = dv.A_loc[(size_t)c * nn + e], m1 = dv.Mm1_loc[(size_t)c * nn + e], m2 = dv.Mm2_loc[(size_t)c * nn + e];
     const dd cou = m1 * (-bt.Z[b]);
     for (int l = 0; l < Lp; ++l) {
@@ -566,36 +750,162 @@ __global__ void __launch_bounds__(DD_NT) ddk_poisson(DDDiscDev dv, DDBatchDev bt
 }
 
 // ------------------------------------------------------------------ occupations, energies, ODA parameter
-// line_search_energy without an exchange-correlation term (line_search.jl:45-80): the energy along the
-// segment is the quadratic a t^2 + b t + c
-__device__ __forceinline__ void dd_line_search(dd k0, dd k1, dd c0, dd c1, dd h0, dd h1, dd h01, dd& t, dd& emin) {
-  const dd A0 = k0 + c0, A1 = k1 + c1;
-  const dd a = h0 + h1 - h01 * 2.0;
-  const dd bq = (A0 - A1) + (h01 - h1) * 2.0;
-  const dd cq = A1 + h1;
-  if (a > dd_make(0.0)) {
-    t = -bq / (a * 2.0);
-    t = dd_min(dd_max(t, dd_make(0.0)), dd_make(1.0));
-  } else {
-    t = (cq <= cq + bq + a) ? dd_make(0.0) : dd_make(1.0);
+// Optim.jl's Brent() as called from line_search.jl:59-67, in dd; one thread drives the
+// state machine, the CTA evaluates the objective between steps
+struct DDBrent {
+  dd lo, hi, x, fx, ox, ofx, oox, oofx, step, old_step, abs_tol, rel_tol, next;
+  int it, maxit;
+};
+__device__ inline dd dd_golden() { return (dd_make(3.0) - dd_sqrt(dd_make(5.0))) * 0.5; }
+__device__ inline void ddb_init(DDBrent& s, dd lo, dd hi, dd abs_tol, dd rel_tol, int maxit) {
+  s.lo = lo; s.hi = hi; s.abs_tol = abs_tol; s.rel_tol = rel_tol; s.maxit = maxit; s.it = 0;
+  s.step = dd_make(0.0); s.old_step = dd_make(0.0);
+  s.next = lo + dd_golden() * (hi - lo);
+}
+__device__ inline void ddb_first(DDBrent& s, dd f) {
+  s.x = s.ox = s.oox = s.next;
+  s.fx = s.ofx = s.oofx = f;
+}
+__device__ inline bool ddb_propose(DDBrent& s) {
+  if (s.it >= s.maxit) return false;
+  const dd zero = dd_make(0.0);
+  dd p = zero, q = zero;
+  const dd x_tol = s.rel_tol * dd_abs(s.x) + s.abs_tol;
+  const dd mid = (s.hi + s.lo) * 0.5;
+  if (dd_abs(s.x - mid) <= x_tol * 2.0 - (s.hi - s.lo) * 0.5) return false;
+  s.it += 1;
+  if (dd_abs(s.old_step) > x_tol) {
+    const dd r = (s.x - s.ox) * (s.fx - s.oofx);
+    q = (s.x - s.oox) * (s.fx - s.ofx);
+    p = (s.x - s.oox) * q - (s.x - s.ox) * r;
+    q = (q - r) * 2.0;
+    if (q > zero) p = -p; else q = -q;
   }
-  emin = cq + bq * t + a * t * t;
+  if (dd_abs(p) < dd_abs(q * s.old_step * 0.5) && p < q * (s.hi - s.x) && p < q * (s.x - s.lo)) {
+    s.old_step = s.step;
+    s.step = p / q;
+    const dd xt = s.x + s.step;
+    if ((xt - s.lo) < x_tol * 2.0 || (s.hi - xt) < x_tol * 2.0) s.step = (s.x < mid) ? x_tol : -x_tol;
+  } else {
+    s.old_step = (s.x < mid) ? s.hi - s.x : s.lo - s.x;
+    s.step = dd_golden() * s.old_step;
+  }
+  if (dd_abs(s.step) >= x_tol) s.next = s.x + s.step;
+  else s.next = s.x + ((s.step > zero) ? x_tol : -x_tol);
+  return true;
+}
+__device__ inline void ddb_update(DDBrent& s, dd nf) {
+  const dd nx = s.next;
+  if (nf < s.fx) {
+    if (nx < s.x) s.hi = s.x; else s.lo = s.x;
+    s.oox = s.ox; s.oofx = s.ofx;
+    s.ox = s.x; s.ofx = s.fx;
+    s.x = nx; s.fx = nf;
+  } else {
+    if (nx < s.x) s.lo = nx; else s.hi = nx;
+    if (nf <= s.ofx || s.ox == s.x) {
+      s.oox = s.ox; s.oofx = s.ofx;
+      s.ox = nx; s.ofx = nf;
+    } else if (nf <= s.oofx || s.oox == s.x || s.oox == s.ox) {
+      s.oox = nx; s.oofx = nf;
+    }
+  }
 }
 
+struct DDDecideShared {
+  dd g[32 * 32];    // Gram matrix b_a . w_b of the involved orbitals
+  dd hp[32];        // b_a . W_prev
+  dd nfin[32];
+  dd red[128];
+  DDBrent br;
+  dd t, f;
+  int go;
+};
+
+// Exc on the global grid for rho = a new0 + bq new1 + cq prev (compute_exc_energy, energies.jl:217-233)
+__device__ dd dd_exc_grid(const DDDiscDev& dv, const DDBatchDev& bt, int b, dd a, dd bq, dd cq, bool use1,
+                          DDDecideShared& S) {
+  const int G = dv.G, ex = bt.ex[b], ec = bt.ec[b];
+  const dd* n0 = bt.rho_y_new + ((size_t)b * 2 + 0) * G;
+  const dd* n1 = bt.rho_y_new + ((size_t)b * 2 + 1) * G;
+  const dd* pr = bt.rho_y + (size_t)b * G;
+  dd acc = dd_make(0.0);
+  for (int q = threadIdx.x; q < G; q += blockDim.x) {
+    dd r = a * n0[q] + cq * pr[q];
+    if (use1) r = r + bq * n1[q];
+    const dd val = r * dd_xc_zk(dd_max(r, dd_make(0.0)), ex, ec);
+    acc = acc + dv.wy[q] * (val * (dv.y[q] * dv.y[q]));
+  }
+  __syncthreads();
+  S.red[threadIdx.x] = acc;
+  __syncthreads();
+  dd sum = dd_make(0.0);
+  for (int i = 0; i < (int)blockDim.x; ++i) sum = sum + S.red[i];
+  return sum * DD_FOURPI;
+}
+
+// minimise a t^2 + b t + c + F(t) on [0, 1] (line_search_energy, line_search.jl:45-80).  F(t) = Exc[t rho_A +
+// (1-t) rho_B] with (A, B) = (filling 0, filling 1) [mode 0] or (trial, previous) [mode 1]; without a
+// functional the quadratic is minimised in closed form.  Called by every thread of the CTA.
+__device__ void dd_line_search(const DDDiscDev& dv, const DDBatchDev& bt, int b, dd qa, dd qb, dd qc, bool has_xc,
+                               int mode, dd td, bool degen, double abstol, double reltol, int maxit,
+                               DDDecideShared& S, dd& t_out, dd& f_out) {
+  const dd zero = dd_make(0.0), one = dd_make(1.0);
+  if (!has_xc) {
+    dd t;
+    if (qa > zero) t = dd_min(dd_max(-qb / (qa * 2.0), zero), one);
+    else t = (qc <= qc + qb + qa) ? zero : one;
+    t_out = t;
+    f_out = qc + qb * t + qa * t * t;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    ddb_init(S.br, zero, one, dd_make(abstol), dd_make(reltol), maxit);
+    S.t = S.br.next;
+    S.go = 1;
+  }
+  __syncthreads();
+  bool first = true;
+  while (true) {
+    const dd t = S.t;
+    dd F;
+    if (mode == 0) F = dd_exc_grid(dv, bt, b, t, one - t, zero, true, S);
+    else F = dd_exc_grid(dv, bt, b, t * td, t * (one - td), one - t, degen, S);
+    if (threadIdx.x == 0) {
+      const dd fv = qa * (t * t) + qb * t + qc + F;
+      if (first) ddb_first(S.br, fv); else ddb_update(S.br, fv);
+      S.go = ddb_propose(S.br) ? 1 : 0;
+      S.t = S.br.next;
+      if (!S.go) { S.t = S.br.x; S.f = S.br.fx; }
+    }
+    first = false;
+    __syncthreads();
+    const int go = S.go;
+    __syncthreads();
+    if (!go) break;
+  }
+  t_out = S.t;
+  f_out = S.f;
+  __syncthreads();
+}
+
+// The scalar logic is executed redundantly by every thread (identical results), so that the CTA-wide
+// evaluations of Exc sit in uniform control flow; thread 0 writes.
 __global__ void __launch_bounds__(128) ddk_decide(DDDiscDev dv, DDBatchDev bt) {
   const int b = blockIdx.x, Nh = dv.Nh, tid = threadIdx.x;
   if (bt.status[b] != 0) return;
-  __shared__ dd g[32 * 32];      // Gram matrix b_a . w_b of the involved orbitals
-  __shared__ dd hp[32];          // b_a . W_prev
-  __shared__ dd nfin[DD_MAXORB];
+  __shared__ DDDecideShared S;
   const int no = bt.norb[b];
   const dd* borb = bt.borb + (size_t)b * DD_MAXORB * Nh;
   const dd* worb = bt.worb + (size_t)b * DD_MAXORB * Nh;
   const dd* Wp = bt.Wv + (size_t)b * Nh;
   const bool har_on = bt.hartree[b] != 0.0;
-  if (no > 32) { if (tid == 0) bt.status[b] = AKS_EINVAL; return; }
+  const bool has_xc = bt.ex[b] != 0 || bt.ec[b] != 0;
+  const bool degen = bt.degen[b] != 0;
+  const dd zero = dd_make(0.0), one = dd_make(1.0);
+  if (no > 32) { if (tid == 0) { bt.status[b] = AKS_EINVAL; bt.rec64[b].status = AKS_EINVAL; } return; }
   for (int pq = tid; pq < no * no + no; pq += blockDim.x) {
-    dd acc = dd_make(0.0);
+    dd acc = zero;
     if (har_on) {
       if (pq < no * no) {
         const dd* x = borb + (size_t)(pq / no) * Nh;
@@ -606,91 +916,112 @@ __global__ void __launch_bounds__(128) ddk_decide(DDDiscDev dv, DDBatchDev bt) {
         for (int i = 0; i < Nh; ++i) acc = acc + x[i] * Wp[i];
       }
     }
-    if (pq < no * no) g[pq] = acc; else hp[pq - no * no] = acc;
+    if (pq < no * no) S.g[pq] = acc; else S.hp[pq - no * no] = acc;
   }
   __syncthreads();
-  if (tid == 0) {
-    const dd* n0 = bt.orb_n0 + (size_t)b * DD_MAXORB;
-    const dd* n1 = bt.orb_n1 + (size_t)b * DD_MAXORB;
-    const int* lk = bt.orb_lk + (size_t)b * DD_MAXORB;
-    const dd Nb = dd_make(bt.N[b]);
-    const dd self = har_on ? (Nb * Nb) / dv.Rmax : dd_make(0.0);   // N^2 / Rmax
-    dd kin[2], cou[2], har[2], seps[2];
-    for (int s = 0; s < 2; ++s) {
-      const dd* ns = s ? n1 : n0;
-      kin[s] = cou[s] = seps[s] = dd_make(0.0);
-      dd q = dd_make(0.0);
-      for (int a = 0; a < no; ++a) {
-        const size_t pair = ((size_t)b * bt.L + (lk[a] >> 8)) * bt.nh + (lk[a] & 0xff);
-        kin[s] = kin[s] + ns[a] * bt.ekin_orb[pair];
-        cou[s] = cou[s] + ns[a] * bt.ecou_orb[pair];
-        seps[s] = seps[s] + ns[a] * bt.eps[pair];
-        dd r = dd_make(0.0);
-        for (int c2 = 0; c2 < no; ++c2) r = r + g[a * no + c2] * ns[c2];
-        q = q + r * ns[a];
-      }
-      har[s] = har_on ? (q + self) * 0.5 : dd_make(0.0);
+  const dd* n0 = bt.orb_n0 + (size_t)b * DD_MAXORB;
+  const dd* n1 = bt.orb_n1 + (size_t)b * DD_MAXORB;
+  const int* lk = bt.orb_lk + (size_t)b * DD_MAXORB;
+  const dd Nb = dd_make(bt.N[b]);
+  const dd self = har_on ? (Nb * Nb) / dv.Rmax : zero;   // N^2 / Rmax
+  dd kin[2], cou[2], har[2], seps[2], corr[2];
+  for (int s = 0; s < 2; ++s) {
+    const dd* ns = s ? n1 : n0;
+    kin[s] = cou[s] = seps[s] = corr[s] = zero;
+    dd q = zero;
+    for (int a = 0; a < no; ++a) {
+      const size_t pair = ((size_t)b * bt.L + (lk[a] >> 8)) * bt.nh + (lk[a] & 0xff);
+      kin[s] = kin[s] + ns[a] * bt.ekin_orb[pair];
+      cou[s] = cou[s] + ns[a] * bt.ecou_orb[pair];
+      seps[s] = seps[s] + ns[a] * bt.eps[pair];
+      dd r = zero;
+      for (int c2 = 0; c2 < no; ++c2) r = r + S.g[a * no + c2] * ns[c2];
+      q = q + r * ns[a];
     }
-    dd e[5];   // Etot, Ekin, Ecou, Ehar, Eexc of the trial density
-    if (bt.degen[b]) {
-      // resolve_twofold_degeneracy!: line search between the two extreme fillings
-      dd q01 = dd_make(0.0);
-      for (int a = 0; a < no; ++a) {
-        dd r = dd_make(0.0);
-        for (int c2 = 0; c2 < no; ++c2) r = r + g[a * no + c2] * n0[c2];   // B[D2] . W[D1]
-        q01 = q01 + r * n1[a];
-      }
-      const dd har01 = har_on ? (q01 + self) * 0.5 : dd_make(0.0);
-      dd td, emin;
-      dd_line_search(kin[0], kin[1], cou[0], cou[1], har[0], har[1], har01, td, emin);
-      const dd um = dd_make(1.0) - td;
-      for (int a = 0; a < no; ++a) nfin[a] = td * n0[a] + um * n1[a];
-      e[0] = emin;
-      e[1] = td * kin[0] + um * kin[1];
-      e[2] = td * cou[0] + um * cou[1];
-      e[3] = td * td * har[0] + um * um * har[1] + td * um * har01 * 2.0;
-      e[4] = e[0] - e[1] - e[2] - e[3];
-    } else {
-      for (int a = 0; a < no; ++a) nfin[a] = n0[a];
-      e[0] = seps[0] - har[0];   // compute_total_energy without a functional: sum n eps - Ehar
-      e[1] = kin[0]; e[2] = cou[0]; e[3] = har[0]; e[4] = dd_make(0.0);
+    har[s] = har_on ? (q + self) * 0.5 : zero;
+    if (has_xc)
+      for (int c = 0; c < dv.C; ++c) corr[s] = corr[s] + bt.corr_part[((size_t)b * 2 + s) * dv.C + c];
+  }
+  dd e[5];   // Etot, Ekin, Ecou, Ehar, Eexc of the trial density
+  dd td = one;
+  if (degen) {
+    // resolve_twofold_degeneracy!: line search between the two extreme fillings
+    dd q01 = zero;
+    for (int a = 0; a < no; ++a) {
+      dd r = zero;
+      for (int c2 = 0; c2 < no; ++c2) r = r + S.g[a * no + c2] * n0[c2];   // B[D2] . W[D1]
+      q01 = q01 + r * n1[a];
     }
-    // ODA step (oda/loop.jl:79-116)
-    dd t = bt.t[b], tmix = dd_make(1.0);
-    dd en[5];
-    for (int q = 0; q < 5; ++q) en[q] = e[q];
-    if (bt.niter[b] > 0) {
-      const dd* ep = bt.E + (size_t)b * 5;
-      dd q01 = dd_make(0.0);
-      for (int a = 0; a < no; ++a) q01 = q01 + hp[a] * nfin[a];
-      const dd har01 = har_on ? (q01 + self) * 0.5 : dd_make(0.0);
-      dd etot = dd_make(0.0);
-      if (!bt.frozen_t) dd_line_search(e[1], ep[1], e[2], ep[2], e[3], ep[3], har01, t, etot);
-      const dd um = dd_make(1.0) - t;
+    const dd har01 = har_on ? (q01 + self) * 0.5 : zero;
+    const dd A0 = kin[0] + cou[0], A1 = kin[1] + cou[1];
+    const dd qa = har[0] + har[1] - har01 * 2.0, qb = (A0 - A1) + (har01 - har[1]) * 2.0, qc = A1 + har[1];
+    dd emin;
+    // the degenerate search runs with the default tolerances of line_search_energy, 1e4 eps(Double64)
+    dd_line_search(dv, bt, b, qa, qb, qc, has_xc, 0, one, true, 4.930380657631324e-28, 4.930380657631324e-28, 100, S,
+                   td, emin);
+    const dd um = one - td;
+    if (tid < no) S.nfin[tid] = td * n0[tid] + um * n1[tid];
+    e[0] = emin;
+    e[1] = td * kin[0] + um * kin[1];
+    e[2] = td * cou[0] + um * cou[1];
+    e[3] = td * td * har[0] + um * um * har[1] + td * um * har01 * 2.0;
+    e[4] = e[0] - e[1] - e[2] - e[3];
+  } else {
+    if (tid < no) S.nfin[tid] = n0[tid];
+    e[1] = kin[0]; e[2] = cou[0]; e[3] = har[0];
+    e[4] = has_xc ? dd_exc_grid(dv, bt, b, one, zero, zero, false, S) : zero;
+    // compute_total_energy (energies.jl:7-39): sum n eps - Ehar [+ Exc - <Vxc[D_prev], D>]
+    e[0] = has_xc ? (seps[0] - har[0] + e[4] - corr[0]) : (seps[0] - har[0]);
+  }
+  __syncthreads();
+  // ODA step (oda/loop.jl:79-116)
+  dd t = bt.t[b], tmix = one;
+  dd en[5];
+  for (int q = 0; q < 5; ++q) en[q] = e[q];
+  if (bt.niter[b] > 0) {
+    const dd* ep = bt.E + (size_t)b * 5;
+    dd q01 = zero;
+    for (int a = 0; a < no; ++a) q01 = q01 + S.hp[a] * S.nfin[a];
+    const dd har01 = har_on ? (q01 + self) * 0.5 : zero;
+    dd etot = zero;
+    if (bt.frozen_t) {
+      const dd um = one - t;
       en[1] = t * e[1] + um * ep[1];
       en[2] = t * e[2] + um * ep[2];
       en[3] = t * t * e[3] + um * um * ep[3] + t * um * har01 * 2.0;
-      if (bt.frozen_t) { en[4] = dd_make(0.0); en[0] = en[1] + en[2] + en[3]; }
-      else { en[0] = etot; en[4] = etot - en[1] - en[2] - en[3]; }
-      tmix = t;
+      en[4] = has_xc ? dd_exc_grid(dv, bt, b, t * td, t * (one - td), um, degen, S) : zero;
+      en[0] = en[1] + en[2] + en[3] + en[4];
+    } else {
+      const dd A0 = e[1] + e[2], A1 = ep[1] + ep[2];
+      const dd qa = e[3] + ep[3] - har01 * 2.0, qb = (A0 - A1) + (har01 - ep[3]) * 2.0, qc = A1 + ep[3];
+      dd_line_search(dv, bt, b, qa, qb, qc, has_xc, 1, td, degen, bt.abstol_ls, bt.reltol_ls, bt.maxiter_ls, S, t, etot);
+      const dd um = one - t;
+      en[1] = t * e[1] + um * ep[1];
+      en[2] = t * e[2] + um * ep[2];
+      en[3] = t * t * e[3] + um * um * ep[3] + t * um * har01 * 2.0;
+      en[0] = etot;
+      en[4] = etot - en[1] - en[2] - en[3];
     }
+    tmix = t;
+  }
+  if (tid == 0) {
     for (int q = 0; q < 5; ++q) bt.Enew[(size_t)b * 5 + q] = en[q];
     bt.tnew[b] = t;
     bt.tmix[b] = tmix;
+    bt.td[b] = td;
     // occupations of the trial density, (l, k) layout
-    for (int q = 0; q < bt.L * bt.nh; ++q) bt.occ[(size_t)b * bt.L * bt.nh + q] = dd_make(0.0);
+    for (int q = 0; q < bt.L * bt.nh; ++q) bt.occ[(size_t)b * bt.L * bt.nh + q] = zero;
     for (int a = 0; a < no; ++a) {
-      bt.orb_n[(size_t)b * DD_MAXORB + a] = nfin[a];
-      bt.occ[((size_t)b * bt.L + (lk[a] >> 8)) * bt.nh + (lk[a] & 0xff)] = nfin[a];
+      bt.orb_n[(size_t)b * DD_MAXORB + a] = S.nfin[a];
+      bt.occ[((size_t)b * bt.L + (lk[a] >> 8)) * bt.nh + (lk[a] & 0xff)] = S.nfin[a];
     }
   }
-  __syncthreads();
   // B, W of the trial density are linear in the occupations
   for (int i = tid; i < Nh; i += blockDim.x) {
-    dd bs = dd_make(0.0), ws = dd_make(0.0);
+    dd bs = zero, ws = zero;
     for (int a = 0; a < no; ++a) {
-      bs = bs + borb[(size_t)a * Nh + i] * nfin[a];
-      ws = ws + worb[(size_t)a * Nh + i] * nfin[a];
+      bs = bs + borb[(size_t)a * Nh + i] * S.nfin[a];
+      ws = ws + worb[(size_t)a * Nh + i] * S.nfin[a];
     }
     bt.Bnew[(size_t)b * Nh + i] = bs;
     bt.Wnew[(size_t)b * Nh + i] = ws;
@@ -739,6 +1070,25 @@ __global__ void __launch_bounds__(128) ddk_finish(DDDiscDev dv, DDBatchDev bt) {
     const size_t e = (size_t)b * Nh + i;
     bt.Bv[e] = t * bt.Bnew[e] + um * bt.Bv[e];
     bt.Wv[e] = t * bt.Wnew[e] + um * bt.Wv[e];
+  }
+  if (bt.ex[b] != 0 || bt.ec[b] != 0) {
+    // the linear images of D the next step reads: rho at the Gauss nodes and on the energy grid
+    const dd td = bt.td[b], ud = dd_make(1.0) - td;
+    const bool degen = bt.degen[b] != 0;
+    const size_t nq = (size_t)dv.C * dv.Q, ny = dv.G;
+    for (size_t i = tid; i < nq + ny; i += blockDim.x) {
+      dd *dst;
+      const dd *a0, *a1;
+      if (i < nq) {
+        dst = bt.rho_q + (size_t)b * nq + i;
+        a0 = bt.rho_q_new + ((size_t)b * 2 + 0) * nq + i; a1 = bt.rho_q_new + ((size_t)b * 2 + 1) * nq + i;
+      } else {
+        dst = bt.rho_y + (size_t)b * ny + (i - nq);
+        a0 = bt.rho_y_new + ((size_t)b * 2 + 0) * ny + (i - nq); a1 = bt.rho_y_new + ((size_t)b * 2 + 1) * ny + (i - nq);
+      }
+      const dd trial = degen ? (td * (*a0) + ud * (*a1)) : *a0;
+      *dst = t * trial + um * (*dst);
+    }
   }
   __syncthreads();
   if (tid == 0) {

@@ -92,6 +92,18 @@ class DD:
 
     __rmul__ = __mul__
 
+    def __truediv__(self, o):
+        """Long division with three quotient terms."""
+        if not isinstance(o, DD):
+            o = DD(np.asarray(o, dtype=np.float64))
+        q1 = self.hi / o.hi
+        r = self - o * DD(q1)
+        q2 = r.hi / o.hi
+        r = r - o * DD(q2)
+        q3 = r.hi / o.hi
+        s, e = two_sum(q1, q2)
+        return DD(s, e) + DD(q3)
+
     def sum(self, axis=-1):
         """Sequential double-double sum along one axis."""
         hi = np.moveaxis(self.hi, axis, 0)
@@ -274,3 +286,73 @@ def build_femops_dd(basis: FEMBasis, *, nquad: int | None = None, dps: int = 50)
                 GGw = GG * wr[None, None, :]
                 F[c] = ((G[:, None, None, :] * GGw[None, :, :, :]).sum(axis=-1) * h2d) * m3
     return FEMOperatorsDD(basis, M0, A, Mm1, Mm2, F)
+
+
+# ---------------------------------------------------------------------------- Gauss tables in double-double
+def legendre_dd(nmax: int, x: DD):
+    """P_0..P_nmax at the points x (Bonnet recurrence in double-double, vectorised over the points)."""
+    P = [DD(np.ones(x.shape)), x.copy()]
+    for m in range(2, nmax + 1):
+        P.append((x * P[m - 1] * float(2 * m - 1) - P[m - 2] * float(m - 1)) / float(m))
+    return P[:nmax + 1]
+
+
+def generator_values_dd(p: int, x: DD) -> DD:
+    """Generator values (p+1, len(x)) at reference points x (src/fem/generators.jl:34-57)."""
+    P = legendre_dd(max(p, 1), x)
+    one = DD(np.ones(x.shape))
+    rows = [one + x, one - x]
+    for k in range(1, p):
+        rows.append((P[k + 1] - P[k - 1]) / float(2 * k + 1))
+    return DD(np.stack([r.hi for r in rows]), np.stack([r.lo for r in rows]))
+
+
+def gauss_legendre_dd(n: int):
+    """n-point Gauss-Legendre rule in double-double: Newton on P_n from the extended-precision nodes of
+    `quadrature.gauss_legendre` (the reference calls `QuadGK.gauss(Double64, n)`,
+    src/fem/integration methods.jl:50)."""
+    from .quadrature import gauss_legendre
+    x0, _ = gauss_legendre(n)
+    hi = np.asarray(x0, dtype=np.float64)
+    lo = np.asarray(x0 - hi.astype(np.longdouble), dtype=np.float64)
+    x = DD(hi, lo)
+    one = DD(np.ones(n))
+    for _ in range(3):
+        P = legendre_dd(n, x)
+        dp = (x * P[n] - P[n - 1]) * float(n) / (x * x - one)
+        x = x - P[n] / dp
+    # exact antisymmetry of the nodes
+    x = (x - DD(x.hi[::-1].copy(), x.lo[::-1].copy())) * 0.5
+    P = legendre_dd(n, x)
+    dp = (x * P[n] - P[n - 1]) * float(n) / (x * x - one)
+    w = DD(2.0 * np.ones(n)) / ((one - x * x) * dp * dp)
+    w = (w + DD(w.hi[::-1].copy(), w.lo[::-1].copy())) * 0.5
+    return x, w
+
+
+class GaussLegendreDD:
+    """`GaussLegendre(basis, npoints)` with T = Double64 (src/fem/integration methods.jl:30-70): nodes and
+    weights on [-1, 1], the global energy grid y, wy, the generator values at the nodes (`Pgenx`) and -- what
+    the reference recomputes in every `eval_density!` -- the cell and the generator values of every grid point."""
+
+    def __init__(self, basis: FEMBasis, npoints: int = 1000):
+        self.npoints = int(npoints)
+        p, C = basis.ordermax, basis.ncells
+        self.x, self.w = gauss_legendre_dd(self.npoints)
+        self.Pgenx = generator_values_dd(p, self.x)                     # (p+1, Q)
+        pts = np.asarray(basis.mesh.points, dtype=np.float64)
+        half = DD(np.array(pts[-1])) * 0.5                               # Rmax / 2 (the mesh starts at 0)
+        a = DD(np.array(pts[0]))
+        half = (DD(np.array(pts[-1])) - a) * 0.5
+        self.y = self.x * half + (a + half)
+        self.wy = self.w * half
+        self.ycell = np.clip(np.searchsorted(pts, self.y.hi, side="right") - 1, 0, C - 1).astype(np.int64)
+        # affine maps in double-double (src/fem/basis.jl:185-190)
+        left, right = DD(pts[:-1].copy()), DD(pts[1:].copy())
+        h = right - left
+        self.invshifts = DD(np.stack([(h * 0.5).hi, (left + h * 0.5).hi], axis=1),
+                            np.stack([(h * 0.5).lo, (left + h * 0.5).lo], axis=1))   # (C, 2)
+        c1 = DD(2.0 * np.ones(C)) / h
+        c0 = -(left * c1) - DD(np.ones(C))
+        xi = self.y * c1[self.ycell] + c0[self.ycell]
+        self.Pgeny = generator_values_dd(p, xi)                          # (p+1, G)

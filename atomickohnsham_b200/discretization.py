@@ -31,9 +31,11 @@ class KSEDiscretization:
         self.Nh = basis.size
         self.Rmax = basis.mesh.last
         if dtype == "double64":
-            # the Double64 path runs without an exchange-correlation functional (as the reference's own
-            # Double64 example does): no Gauss tables are needed
-            from .dd import build_femops_dd
+            # Gauss tables in double-double are only needed (and only built by default) when the model has
+            # an exchange-correlation functional; the reference's own Double64 example runs without one
+            from .dd import GaussLegendreDD, build_femops_dd
+            if fem_integration_method is None and model is not None and model.has_exchcorr:
+                fem_integration_method = GaussLegendreDD(basis)
             self.fem_integration_method = fem_integration_method
             self.femops = femops or build_femops_dd(basis)
         else:
@@ -115,8 +117,18 @@ class KSEDiscretization:
         d = _capi.DiscDesc()
         d.dtype, d.p, d.C, d.Nh = 1, b.ordermax, Cn, b.size
         d.Q, d.G, d.lh, d.nh, d.nspin = 0, 0, self.lh, self.nh, self.nspin
-        for name in ("mesh", "M0", "A", "Mm1", "Mm2", "Fv"):
+        q = self.fem_integration_method
+        names = ["mesh", "M0", "A", "Mm1", "Mm2", "Fv"]
+        if q is not None:
+            colmajor = lambda t: np.ascontiguousarray(np.transpose(t.pairs(), (1, 0, 2)))   # (p+1, Q) column-major
+            keep.update(x=q.x.pairs(), w=q.w.pairs(), y=q.y.pairs(), wy=q.wy.pairs(), Pgenx=colmajor(q.Pgenx),
+                        Pgeny=colmajor(q.Pgeny), invshifts=q.invshifts.pairs(), ycell=i64(q.ycell + 1))
+            d.Q = d.G = q.npoints
+            d.ycell = _capi.iptr(keep["ycell"])
+            names += ["x", "w", "y", "wy", "Pgenx", "Pgeny", "invshifts"]
+        for name in names:
             setattr(d, name, _capi.dptr(keep[name]))
+        self._keep = keep
         d.nF = len(Fi)
         d.Fi, d.Fj, d.Fm = _capi.iptr(keep["Fi"]), _capi.iptr(keep["Fj"]), _capi.iptr(keep["Fm"])
         d.cell_len = _capi.iptr(keep["cell_len"])

@@ -109,8 +109,14 @@ class Batch:
         self.nprob = nprob
         a = alg.aufbau
         opt = a if isinstance(a, OptimizedAufbau) else OptimizedAufbau()
+        abstol_ls, reltol_ls = alg.abstol_ls, alg.reltol_ls
+        if discretization.dtype == "double64":
+            # ODA's defaults are 1e4 eps(typeof(tinit)) (oda/types.jl:39-40): eps(Double64) for a Double64 run
+            f64_default, dd_default = 1e4 * np.finfo(np.float64).eps, 4.930380657631324e-28
+            abstol_ls = dd_default if abstol_ls == f64_default else abstol_ls
+            reltol_ls = dd_default if reltol_ls == f64_default else reltol_ls
         self.ctx.check(_capi.lib.aks_batch_set_oda(h, alg.scftol, alg.tinit, int(alg.frozen_t), alg.maxiter_ls,
-                                                   alg.abstol_ls, alg.reltol_ls, opt.max_degen, opt.tol,
+                                                   abstol_ls, reltol_ls, opt.max_degen, opt.tol,
                                                    int(opt.handle_degen_spin_1iter)))
         if isinstance(a, SmearedAufbau):
             self.ctx.check(_capi.lib.aks_batch_set_aufbau(h, 1, a.Temp, None))

@@ -62,7 +62,7 @@ typedef struct aks_disc_desc {
   int32_t dtype;  /* 0 = Float64; 1 = Double64 (the reference's T = Double64, discretization.jl:289): every
                      `const double*` table below then holds interleaved (hi, lo) pairs (Julia's
                      Vector{Double64} layout, twice the length); x, w, Pgenx, y, wy, ycell, Pgeny, invshifts
-                     may be NULL with Q = G = 0 (no exchange-correlation in the Double64 build); nspin = 1 */
+                     may be NULL with Q = G = 0 (batches without a functional only); nspin = 1             */
   int32_t p;      /* ordermax                                                             */
   int32_t C;      /* number of cells = length(mesh)-1                                     */
   int32_t Nh;     /* basis size                                                           */
@@ -157,6 +157,10 @@ int aks_get_state(aks_batch* batch, int32_t prob, double* D, double* U, double* 
  * aks_get_records_dd the full pairs of the last step: out[nprob][7][2] = stop, Etot, Ekin, Ecou, Ehar, Eexc, t.
  * aks_set_density and the step-level hooks return AKS_ENOSYS for such batches.                              */
 int aks_get_records_dd(aks_batch* batch, double* out);
+/* test hook of the Double64 functionals (evaluate_vrho! / evaluate_zk! with T = Double64, models.jl:97-116):
+ * rho, vrho, zk are npts (hi, lo) pairs; densities are clamped at 0 as BuiltinFunctional.jl:112 does       */
+int aks_dd_xc_eval(aks_ctx* ctx, int32_t npts, const double* rho, int32_t ex_id, int32_t ec_id, double* vrho,
+                   double* zk);
 /* eps, n, W of every problem at once: eps, n [nprob][(L, nh[, 2])], W [nprob][Nh]; any pointer may be NULL */
 int aks_get_state_all(aks_batch* batch, double* eps, double* n, double* W);
 /* overwrite one problem's density state from a dense D (Nh,Nh[,2]) -- restart / step-level

@@ -91,3 +91,28 @@ def test_double64_golden_fixture_is_consistent():
         prev = e["Etot"]
     assert mp.mpf(its[-1]["Etot"]) == mp.mpf(g["final"]["Etot"])
     assert mp.mpf(its[-1]["stop"]) < mp.mpf(g["setup"]["scftol"])
+
+
+def test_xc_dd_oracle_matches_float64_oracle():
+    """The mpmath restatement of the Double64 functionals (oracle/xc_dd.py) against the Float64 oracle
+    (oracle/xc.py, pinned to the reference's goldens) on Float64 densities."""
+    from oracle import xc as xc64
+    from oracle import xc_dd
+    mp.mp.dps = 40
+    rho = np.concatenate([10.0 ** np.linspace(-28, 3, 40), [0.0, -1e-9]])
+    vx, zx = xc64.slater_vrho(rho), xc64.slater_zk(rho)
+    X = xc64.XC("lda_x", "lda_c_pw", 1)
+    v_all, z_all = X.vrho(rho), X.zk(rho)
+    for i, r in enumerate(rho):
+        assert abs(float(xc_dd.vrho(r, True, False)) - vx[i]) <= 4e-15 * abs(vx[i])
+        assert abs(float(xc_dd.zk(r, True, False)) - zx[i]) <= 4e-15 * abs(zx[i])
+        # log(1 + 1/Q1) of PW92 is evaluated by the Float64 oracle (and by the reference) as written: its relative
+        # error grows like eps * Q1 ~ eps * rs^2 towards low densities
+        if r > 0:
+            rs = (3.0 / (4.0 * np.pi * r)) ** (1.0 / 3.0)
+            tol = 1e-13 + 1e-16 * (1.0 + rs * rs)
+            if tol < 1e-3:
+                assert abs(float(xc_dd.vrho(r, True, True)) - v_all[i]) <= tol * abs(v_all[i])
+                assert abs(float(xc_dd.zk(r, True, True)) - z_all[i]) <= tol * abs(z_all[i])
+        else:
+            assert xc_dd.vrho(r, True, True) == 0 and xc_dd.zk(r, True, True) == 0 and v_all[i] == 0

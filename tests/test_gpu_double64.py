@@ -150,10 +150,10 @@ def test_double64_run_and_float64_agree_and_errors():
     f64, _ = b64.run(100)
     assert abs(f64[0]["Etot"] - float(e_dd)) < 1e-10 * abs(float(e_dd))
     b64.close()
-    # a functional on a Double64 discretization is refused (AKS_ENOSYS), as are the Float64-only hooks
+    # a functional on a Double64 discretization built without Gauss tables is refused, as are the Float64-only hooks
     with pytest.raises(_capi.AKSError) as ei:
         Batch([LDA(Z=11, N=11)], disc, bt.alg)
-    assert ei.value.code == _capi.AKS_ENOSYS
+    assert ei.value.code == _capi.AKS_EINVAL
     with pytest.raises(_capi.AKSError) as ei:
         bt.assemble_hartree(0)
     assert ei.value.code == _capi.AKS_ENOSYS
@@ -197,5 +197,68 @@ def test_double64_other_atoms_against_float64():
     for i in range(len(models)):
         assert fdd[i]["status"] == 1, (i, fdd[i])
         assert abs(float(_mpf(rdd[i][1])) - f64[i]["Etot"]) < 2e-10 * abs(f64[i]["Etot"]), (i, fdd[i], f64[i])
+    bdd.close()
+    b64.close()
+
+
+def test_double64_functionals_pointwise_against_mpmath():
+    """evaluate_vrho! / evaluate_zk! in double-double (aks_dd_xc_eval) against the mpmath restatement of the
+    reference's Double64 formulas (oracle/xc_dd.py): 1e-27 relative, zero at rho <= 0."""
+    import ctypes as C
+    from atomickohnsham_b200 import _capi
+    from atomickohnsham_b200.dd import from_mp
+    from oracle import xc_dd
+    mp.mp.dps = 50
+    ctx = _capi.default_context(0)
+    rng = np.random.default_rng(20261020)
+    vals = [mp.mpf(10) ** mp.mpf(float(e)) * (1 + mp.mpf(float(u)) * mp.mpf(2) ** -54)
+            for e, u in zip(np.linspace(-30, 4, 120), rng.standard_normal(120))]
+    vals += [mp.mpf(0), mp.mpf("-1e-12"), mp.mpf(1), mp.mpf("0.5")]
+    rho = from_mp(vals).pairs()
+    for ex, ec in ((1, 0), (0, 12), (1, 12)):
+        v = np.zeros_like(rho)
+        z = np.zeros_like(rho)
+        ctx.check(_capi.lib.aks_dd_xc_eval(ctx.h, len(vals), _capi.dptr(rho), ex, ec, _capi.dptr(v), _capi.dptr(z)))
+        for i, r in enumerate(vals):
+            rr = _mpf(rho[i])
+            for got, ref in ((_mpf(v[i]), xc_dd.vrho(rr, ex == 1, ec == 12)), (_mpf(z[i]), xc_dd.zk(rr, ex == 1, ec == 12))):
+                if rr <= 0:
+                    assert got == 0
+                else:
+                    assert abs(got - ref) <= mp.mpf("1e-27") * abs(ref), (ex, ec, mp.nstr(rr, 5), mp.nstr(got, 30), mp.nstr(ref, 30))
+
+
+def test_double64_lda_against_float64_path():
+    """LDA (lda_x + lda_c_pw) and exchange-only atoms / an anion in Double64 against the Float64 path (pinned to
+    the oracle and the reference's goldens by the other GPU tests) on the same mesh and Gauss rule: Etot within
+    1e-11 relative, the same occupations, Etot = Ekin + Ecou + Ehar + Eexc in double-double."""
+    from atomickohnsham_b200 import (KSEDiscretization, KSEModel, LDA, ODA, OptimizedAufbau, P1IntLegendreBasis,
+                                     Slater)
+    from atomickohnsham_b200.dd import GaussLegendreDD
+    from atomickohnsham_b200.quadrature import GaussLegendre
+    from atomickohnsham_b200.solver import Batch
+    mp.mp.dps = 50
+    basis = P1IntLegendreBasis(make_mesh(["exp", 0, 60, 21, 1.5]), ordermax=8)
+    models = [LDA(Z=2, N=2), LDA(Z=10, N=10), Slater(Z=4, N=4), LDA(Z=9, N=10), LDA(Z=6, N=6)]
+    ddisc = KSEDiscretization(basis, models[0], lh=1, nh=4, dtype="double64",
+                              fem_integration_method=GaussLegendreDD(basis, 300))
+    fdisc = KSEDiscretization(basis, models[0], lh=1, nh=4, fem_integration_method=GaussLegendre(basis, 300))
+    aufbau = OptimizedAufbau(max_degen=2, tol=1e-3)
+    bdd = Batch(models, ddisc, ODA(tinit=0.6, scftol=1e-18, aufbau=aufbau))
+    fdd, _ = bdd.run(150)
+    rdd = bdd.records_dd()
+    b64 = Batch(models, fdisc, ODA(tinit=0.6, scftol=1e-11, aufbau=aufbau))
+    f64, _ = b64.run(150)
+    for i in range(len(models)):
+        assert fdd[i]["status"] == 1, (i, fdd[i])
+        e = [_mpf(rdd[i][q]) for q in range(1, 6)]
+        assert abs(e[0] - (e[1] + e[2] + e[3] + e[4])) < mp.mpf("1e-28") * abs(e[0])
+        assert abs(float(e[0]) - f64[i]["Etot"]) < 1e-11 * abs(f64[i]["Etot"]), (i, float(e[0]), f64[i]["Etot"])
+        for q, nm in ((1, "Ekin"), (2, "Ecou"), (3, "Ehar"), (4, "Eexc")):
+            assert abs(float(e[q]) - f64[i][nm]) < 1e-7 * abs(f64[i][nm]), (i, nm)
+        sd, sf = bdd.state(i, want_D=False, want_U=False), b64.state(i, want_D=False, want_U=False)
+        assert np.allclose(sd["n"][..., 0, 0], sf["n"][..., 0], atol=1e-6)
+        occ = sf["n"][..., 0] > 0
+        assert np.allclose(sd["eps"][..., 0, 0][occ], sf["eps"][..., 0][occ], rtol=0, atol=1e-8)
     bdd.close()
     b64.close()
