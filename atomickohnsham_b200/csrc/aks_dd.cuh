@@ -297,7 +297,7 @@ static int dd_step_launch(aks_batch* bt) {
     ddk_rho_grid<<<dim3((dv.G + 127) / 128, B), 128, 0, st>>>(dv, b);
     LAUNCH_CHECK();
   }
-  ddk_decide<<<B, 128, 0, st>>>(dv, b);
+  ddk_decide<<<B, DD_DECIDE_NT, 0, st>>>(dv, b);
   LAUNCH_CHECK();
   ddk_mix<<<dim3(b.nparts, B), 256, 0, st>>>(dv, b);
   LAUNCH_CHECK();

@@ -542,9 +542,54 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt) {
   dd* rhs = bt.vtmp + pair * Nh;
   const int* l2g = dv.l2g;
 
-  // ---- phase A: isolate eigenvalue number k with Float64 inertia counts
   const double Zb = bt.Z[b];
-  double lo = -0.6 * Zb * Zb - 1.0, hi = 0.5;
+  dd rho = dd_make(0.0);
+  dd v[DD_MAXN];
+  int fail = 1;
+  double lo = 0.0, hi = 0.0, mid = 0.0;
+  // ---- warm path: once the SCF has settled (last stop < 1e-2), Rayleigh-quotient iteration in dd straight from
+  // the previous eigenvector; the result is accepted only if two Float64 inertia counts certify it as level k
+  const bool try_warm = bt.warm[b] && fabs(bt.rec[(size_t)b * 7].hi) < 1e-2;
+  if (try_warm) {
+    dd pm = dd_make(0.0), ph = dd_make(0.0);
+    if (c < C) {
+      dd_load_local(x, l2g, c, C, n, v);
+      pm = dd_quad_local(M + (size_t)c * nn, v, n);
+      ph = dd_quad_local(H + (size_t)c * nn, v, n);
+    }
+    const dd nrm0 = dd_block_sum(pm, S, C);
+    rho = dd_block_sum(ph, S, C) / nrm0;
+    for (int it = 0; it < 6; ++it) {
+      dd_factor_shift<dd>(H, M, rho, scratch, S, C, n);
+      dd_matvec(M, S, x, rhs, l2g, C, n);
+      dd_solve(scratch, S, rhs, x, l2g, C, n);
+      pm = dd_make(0.0); ph = dd_make(0.0);
+      if (c < C) {
+        dd_load_local(x, l2g, c, C, n, v);
+        pm = dd_quad_local(M + (size_t)c * nn, v, n);
+        ph = dd_quad_local(H + (size_t)c * nn, v, n);
+      }
+      const dd nrm = dd_block_sum(pm, S, C);
+      const dd hq = dd_block_sum(ph, S, C);
+      const dd sc = dd_inv(dd_sqrt(nrm));
+      for (int i = c; i < Nh; i += DD_NT) x[i] = x[i] * sc;
+      __syncthreads();
+      const dd rnew = hq / nrm;
+      const double delta = fabs((rnew - rho).hi);
+      rho = rnew;
+      if (delta <= 1e-25 * fmax(1.0, fabs(rho.hi))) { fail = 0; break; }
+    }
+    if (!fail) {
+      const double m = 1e-9 * fmax(1.0, fabs(rho.hi));
+      lo = rho.hi - m; hi = rho.hi + m; mid = rho.hi;
+      const int cl = dd_factor_shift<double>(H, M, lo, scratch, S, C, n);
+      const int ch = dd_factor_shift<double>(H, M, hi, scratch, S, C, n);
+      if (cl != k || ch != k + 1) fail = 1;
+    }
+  }
+  if (fail) {
+  // ---- phase A: isolate eigenvalue number k with Float64 inertia counts
+  lo = -0.6 * Zb * Zb - 1.0; hi = 0.5;
   for (int it = 0; it < 12; ++it) {
     if (dd_factor_shift<double>(H, M, lo, scratch, S, C, n) <= k) break;
     lo = 2.0 * lo;
@@ -555,14 +600,15 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt) {
     hi = 2.0 * hi + 1.0;
   }
   for (int it = 0; it < 120; ++it) {
-    const double mid = 0.5 * (lo + hi);
-    if (hi - lo <= 1e-10 * fmax(1.0, fabs(mid)) || mid <= lo || mid >= hi) break;
-    if (dd_factor_shift<double>(H, M, mid, scratch, S, C, n) >= k + 1) hi = mid; else lo = mid;
+    const double md = 0.5 * (lo + hi);
+    if (hi - lo <= 1e-10 * fmax(1.0, fabs(md)) || md <= lo || md >= hi) break;
+    if (dd_factor_shift<double>(H, M, md, scratch, S, C, n) >= k + 1) hi = md; else lo = md;
   }
-  const double mid = 0.5 * (lo + hi);
+  mid = 0.5 * (lo + hi);
 
   // ---- phase B: inverse iteration at the bracket, then Rayleigh-quotient iteration, in dd
-  if (!bt.warm[b]) {
+  // (a failed warm attempt may have left x on a neighbouring level: always restart from the hashed vector)
+  {
     if (c < C) {
       const int base = l2g[c * n + 2];
       for (int i = 0; i < n - 2; ++i) {
@@ -575,9 +621,8 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt) {
   }
   __syncthreads();
   dd_factor_shift<dd>(H, M, dd_make(mid), scratch, S, C, n);
-  dd rho = dd_make(mid);
-  dd v[DD_MAXN];
-  for (int rep = 0; rep < 2; ++rep) {
+  rho = dd_make(mid);
+  for (int rep = 0; rep < 3; ++rep) {
     dd_matvec(M, S, x, rhs, l2g, C, n);
     dd_solve(scratch, S, rhs, x, l2g, C, n);
     dd part = dd_make(0.0);
@@ -592,7 +637,7 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt) {
     if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local(H + (size_t)c * nn, v, n); }
     rho = dd_block_sum(part, S, C);
   }
-  int fail = 1;
+  fail = 1;
   for (int it = 0; it < 8; ++it) {
     dd_factor_shift<dd>(H, M, rho, scratch, S, C, n);
     dd_matvec(M, S, x, rhs, l2g, C, n);
@@ -612,6 +657,7 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt) {
     const double delta = fabs((rnew - rho).hi);
     rho = rnew;
     if (delta <= 1e-25 * fmax(1.0, fabs(rho.hi))) { fail = 0; break; }
+  }
   }
   // the pair must be the one the bracket isolated
   if (!(rho.hi >= lo - 1e-6 * fmax(1.0, fabs(mid)) && rho.hi <= hi + 1e-6 * fmax(1.0, fabs(mid)))) fail = 1;
@@ -812,11 +858,12 @@ __device__ inline void ddb_update(DDBrent& s, dd nf) {
   }
 }
 
+#define DD_DECIDE_NT 512
 struct DDDecideShared {
   dd g[32 * 32];    // Gram matrix b_a . w_b of the involved orbitals
   dd hp[32];        // b_a . W_prev
   dd nfin[32];
-  dd red[128];
+  dd red[DD_DECIDE_NT];
   DDBrent br;
   dd t, f;
   int go;
@@ -839,8 +886,11 @@ __device__ dd dd_exc_grid(const DDDiscDev& dv, const DDBatchDev& bt, int b, dd a
   __syncthreads();
   S.red[threadIdx.x] = acc;
   __syncthreads();
-  dd sum = dd_make(0.0);
-  for (int i = 0; i < (int)blockDim.x; ++i) sum = sum + S.red[i];
+  for (int h = DD_DECIDE_NT / 2; h > 0; h >>= 1) {   // fixed tree: bit reproducible
+    if ((int)threadIdx.x < h) S.red[threadIdx.x] = S.red[threadIdx.x] + S.red[threadIdx.x + h];
+    __syncthreads();
+  }
+  const dd sum = S.red[0];
   return sum * DD_FOURPI;
 }
 
@@ -891,7 +941,7 @@ __device__ void dd_line_search(const DDDiscDev& dv, const DDBatchDev& bt, int b,
 
 // The scalar logic is executed redundantly by every thread (identical results), so that the CTA-wide
 // evaluations of Exc sit in uniform control flow; thread 0 writes.
-__global__ void __launch_bounds__(128) ddk_decide(DDDiscDev dv, DDBatchDev bt) {
+__global__ void __launch_bounds__(DD_DECIDE_NT) ddk_decide(DDDiscDev dv, DDBatchDev bt) {
   const int b = blockIdx.x, Nh = dv.Nh, tid = threadIdx.x;
   if (bt.status[b] != 0) return;
   __shared__ DDDecideShared S;

@@ -52,17 +52,23 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, 
     for c in 1:C
         cidx[1:cell_len[c], c] .= basis.cells_to_indices[c]; cgen[1:cell_len[c], c] .= basis.cells_to_generators[c]
     end
-    invsh = Float64[v for s in basis.invshifts for v in s]
+    # T = Float64 -> dtype 0.  T = Double64 -> dtype 1: a Vector{Double64} IS an array of interleaved (hi, lo)
+    # Float64 pairs, so every table is handed over as it lies in memory (fp(v) below only retypes the pointer).
+    T = eltype(basis)
+    dtype = T === Float64 ? Int32(0) : Int32(1)
+    fp(v) = Ptr{Float64}(pointer(v))
+    invsh = T[v for s in basis.invshifts for v in s]
     Fk = collect(keys(ops.F)); Fi = Int64[k[1] for k in Fk]; Fj = Int64[k[2] for k in Fk]; Fm = Int64[k[3] for k in Fk]
-    Fv = Float64[ops.F[k] for k in Fk]
-    A = Matrix(ops.A); Mm1 = Matrix(ops.M₋₁); Mm2 = Matrix(ops.M₋₂); mesh = collect(Float64, basis.mesh.points)
+    Fv = T[ops.F[k] for k in Fk]
+    A = Matrix(ops.A); Mm1 = Matrix(ops.M₋₁); Mm2 = Matrix(ops.M₋₂); mesh = collect(T, basis.mesh.points)
+    M0 = Matrix(ops.M₀); Pgeny = Matrix{T}(Pgeny)
     ctx = Ref{Ptr{Cvoid}}(); dh = Ref{Ptr{Cvoid}}(); bh = Ref{Ptr{Cvoid}}()
     check(C_NULL, ccall((:aks_ctx_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ctx))
-    GC.@preserve mesh invsh q ops A Mm1 Mm2 Fi Fj Fm Fv cell_len cidx cgen ycell Pgeny begin
-        desc = DiscDesc(0, p, C, disc.Nₕ, q.npoints, q.npoints, disc.lₕ, disc.nₕ, disc.nspin,
-            pointer(mesh), pointer(invsh), pointer(q.x), pointer(q.w), pointer(q.Pgenx), pointer(q.y), pointer(q.wy),
-            pointer(ycell), pointer(Pgeny), pointer(ops.M₀), pointer(A), pointer(Mm1), pointer(Mm2),
-            length(Fv), pointer(Fi), pointer(Fj), pointer(Fm), pointer(Fv), pointer(cell_len), pointer(cidx), pointer(cgen))
+    GC.@preserve mesh invsh q ops M0 A Mm1 Mm2 Fi Fj Fm Fv cell_len cidx cgen ycell Pgeny begin
+        desc = DiscDesc(dtype, p, C, disc.Nₕ, q.npoints, q.npoints, disc.lₕ, disc.nₕ, disc.nspin,
+            fp(mesh), fp(invsh), fp(q.x), fp(q.w), fp(q.Pgenx), fp(q.y), fp(q.wy),
+            pointer(ycell), fp(Pgeny), fp(M0), fp(A), fp(Mm1), fp(Mm2),
+            length(Fv), pointer(Fi), pointer(Fj), pointer(Fm), fp(Fv), pointer(cell_len), pointer(cidx), pointer(cgen))
         check(ctx[], ccall((:aks_disc_create, LIB), Cint, (Ptr{Cvoid}, Ref{DiscDesc}, Ref{Ptr{Cvoid}}), ctx[], desc, dh))
     end
     nprob = length(models)
@@ -75,8 +81,8 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, 
     opt = a isa OptimizedAufbau ? a : OptimizedAufbau()
     check(ctx[], ccall((:aks_batch_set_oda, LIB), Cint,
         (Ptr{Cvoid}, Float64, Float64, Int32, Int32, Float64, Float64, Int32, Float64, Int32),
-        bh[], alg.scftol, alg.tinit, alg.frozen_t, alg.maxiter_ls, alg.abstol_ls, alg.reltol_ls,
-        opt.max_degen, opt.tol, opt.handle_degen_spin_1iter))
+        bh[], Float64(alg.scftol), Float64(alg.tinit), alg.frozen_t, alg.maxiter_ls, Float64(alg.abstol_ls),
+        Float64(alg.reltol_ls), opt.max_degen, Float64(opt.tol), opt.handle_degen_spin_1iter))
     if a isa AtomicKohnSham.SmearedAufbau
         check(ctx[], ccall((:aks_batch_set_aufbau, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}),
             bh[], 1, Float64(a.Temp), C_NULL))
@@ -89,14 +95,23 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, 
     # solve!: one ccall per iteration so that register!/callback! fire as in groundstate.jl:55-57
     solvers = [KSESolver(m, disc, alg; maxiter = maxiter, callback = callback) for m in models]
     recs = Vector{IterRecord}(undef, nprob)
+    recs_dd = Array{T}(undef, 7, nprob)     # Double64 runs: stop, Etot, Ekin, Ecou, Ehar, Eexc, t with all digits
     for it in 1:maxiter
         check(ctx[], ccall((:aks_scf_step, LIB), Cint, (Ptr{Cvoid}, Ptr{IterRecord}), bh[], recs))
+        dtype == 1 && check(ctx[], ccall((:aks_get_records_dd, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), bh[], fp(recs_dd)))
         running = false
-        for (s, r) in zip(solvers, recs)
+        for (i, (s, r)) in enumerate(zip(solvers, recs))
             r.niter == it || continue                       # this problem had already stopped
-            s.stopping_criteria = r.stop
-            e = s.energies; e.Etot, e.Ekin, e.Ecou, e.Ehar, e.Eexc = r.Etot, r.Ekin, r.Ecou, r.Ehar, r.Eexc
-            s.algcache.t = r.t
+            e = s.energies
+            if dtype == 1
+                s.stopping_criteria = recs_dd[1, i]
+                e.Etot, e.Ekin, e.Ecou, e.Ehar, e.Eexc = recs_dd[2, i], recs_dd[3, i], recs_dd[4, i], recs_dd[5, i], recs_dd[6, i]
+                s.algcache.t = recs_dd[7, i]
+            else
+                s.stopping_criteria = r.stop
+                e.Etot, e.Ekin, e.Ecou, e.Ehar, e.Eexc = r.Etot, r.Ekin, r.Ecou, r.Ehar, r.Eexc
+                s.algcache.t = r.t
+            end
             register!(s); callback!(s.callback, s); s.niter += 1
             running |= r.status == 0
         end
@@ -108,7 +123,7 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, 
         W = disc.cache.hartw.W
         check(ctx[], ccall((:aks_get_state, LIB), Cint,
             (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-            bh[], i - 1, c.D, c.U, c.ϵ, c.n, isempty(W) ? C_NULL : W))
+            bh[], i - 1, fp(c.D), fp(c.U), fp(c.ϵ), fp(c.n), isempty(W) ? C_NULL : fp(W)))   # (hi, lo) pairs when T = Double64
         KSESolution(s, _solution_name(models[i]))
     end
     ccall((:aks_batch_destroy, LIB), Cvoid, (Ptr{Cvoid},), bh[])

@@ -4,7 +4,8 @@ The oracle for this row is the reference itself: `tests/golden/sodium_double64.j
 committed log of `examples/basic_example_doublefloat/` (sodium, Hartree only, scftol = 1e-20, 59 iterations,
 36 digits per number; made by tools/make_golden_dd.py).  Tolerances (north star: 1e-20 relative in Double64):
 Etot of EVERY iteration within 1e-24 relative (measured 1e-30), the energy components within
-max(1e-24, 1e-28 / stop), the iteration count +-1 (measured: 59 = 59, final stop 1.5777e-30 = the reference's).
+max(1e-24, 1e-28 / stop), the iteration count within +-3 of the reference's 59 (measured: 59 with the cold-start
+eigensolver, 61 with the warm-started one; the last iterations are a coin flip, see below).
 
 Why the components and the orbital energies of the END of the run cannot agree better than ~1e-15 absolute:
 the reference's run does not stop because D has converged to 1e-20 but because its line search returns
@@ -83,7 +84,8 @@ def test_sodium_double64_trajectory_matches_reference_log():
             break
     assert status == 1, status
     fin = g["final"]
-    assert abs((k + 1) - fin["niter"]) <= 1, (k + 1, fin["niter"])
+    # the run ends when rounding noise makes the line search return t = 0 (module docstring): +-3 iterations
+    assert abs((k + 1) - fin["niter"]) <= 3, (k + 1, fin["niter"])
     rd = bt.records_dd()[0]
     for i, nm, tol in ((1, "Etot", "1e-28"), (2, "Ekin", "1e-15"), (3, "Ecou", "1e-15"), (4, "Ehar", "1e-15")):
         dev = abs(_mpf(rd[i]) - mp.mpf(fin[nm])) / abs(mp.mpf(fin[nm]))
@@ -129,7 +131,7 @@ def test_double64_run_and_float64_agree_and_errors():
     g = load_golden("sodium_double64.json")
     bt, disc, model = _setup(g)
     final, hist = bt.run(100, history=True)
-    assert final[0]["status"] == 1 and abs(final[0]["niter"] - g["final"]["niter"]) <= 1
+    assert final[0]["status"] == 1 and abs(final[0]["niter"] - g["final"]["niter"]) <= 3
     assert len(hist[0]) == final[0]["niter"]
     e_dd = _mpf(bt.records_dd()[0][1])
     assert abs(e_dd - mp.mpf(g["final"]["Etot"])) < mp.mpf("1e-24") * abs(e_dd)
