@@ -9,6 +9,7 @@ from .mesh import (Mesh, expmesh, geometricmesh, linmesh, polynomialmesh, explin
 from .basis import P1IntLegendreBasis, FEMBasis  # noqa: F401
 from .quadrature import GaussLegendre  # noqa: F401
 from .femops import FEMOperators, build_femops  # noqa: F401
+from .dd import FEMOperatorsDD, GaussLegendreDD, build_femops_dd  # noqa: F401  (Double64 host tables)
 
 
 def __getattr__(name):

@@ -33,7 +33,10 @@ class KSEDiscretization:
         if dtype == "double64":
             # Gauss tables in double-double are only needed (and only built by default) when the model has
             # an exchange-correlation functional; the reference's own Double64 example runs without one
-            from .dd import GaussLegendreDD, build_femops_dd
+            from .dd import FEMOperatorsDD, GaussLegendreDD, build_femops_dd
+            if (femops is not None and not isinstance(femops, FEMOperatorsDD)) or \
+                    (fem_integration_method is not None and not isinstance(fem_integration_method, GaussLegendreDD)):
+                raise TypeError("dtype='double64' needs FEMOperatorsDD / GaussLegendreDD tables (atomickohnsham_b200.dd)")
             if fem_integration_method is None and model is not None and model.has_exchcorr:
                 fem_integration_method = GaussLegendreDD(basis)
             self.fem_integration_method = fem_integration_method

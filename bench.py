@@ -279,6 +279,12 @@ def b200_arm(args):
                  "iterations_max": max(r["niter"] for r in final)}
         btc.close()
 
+    # ---------------- Double64 path, informational: 20 anions on the same
+    # order-20 discretization with double-double tables and kernels
+    dd64 = None
+    if rank == 0 and world == 1 and not args.no_dd:
+        dd64 = double64_leg(local)
+
     # ---------------- CPU baseline (rank 0, N = 1 only): the oracle on one host core
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -305,11 +311,45 @@ def b200_arm(args):
             "roofline": roof, "phases_ms": phases,
             "phases_note": "per-phase times are measured with the batch on ONE stream (AKS_PHASE_TIMERS); the timed steps "
                            "run the batch as 8 concurrent stream lanes, so the phases add up to more than ms_per_step", "cpu_baseline": cpu, "sweep_to_convergence": sweep,
+            "double64": dd64,
         }
         _RESULT_LINE.append(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def double64_leg(device, steps=8, warmup=4):
+    """C4 of SURVEY.md section 8: anions Z = 1..20, N = Z + 1, order 20, 40 cells, Q = G = 1000, builtin
+    lda_x + lda_c_pw, T = Double64 (dtype = 1: double-double tables and kernels).  Per-step time of iterations
+    warmup .. warmup+steps of a cold start, host-synchronised through the iteration records."""
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.solver import Batch
+    Zs = list(range(1, 21))
+    basis = aks.P1IntLegendreBasis(aks.expmesh(0, 300, 41, s=1.5), ordermax=20)
+    models = [aks.LDA(Z=z, N=z + 1) for z in Zs]
+    lh = [min(-(-z // 20), 3) + 1 for z in Zs]
+    nh = [min(max(z, 2), 10) for z in Zs]
+    t0 = time.perf_counter()
+    disc = aks.KSEDiscretization(basis, models[0], lh=max(lh), nh=max(nh), dtype="double64", device=device)
+    disc.handle()
+    t_tab = time.perf_counter() - t0
+    bt = Batch(models, disc, aks.ODA(tinit=0.6, scftol=0.0, aufbau=aks.OptimizedAufbau(max_degen=2, tol=1e-3)), lh=lh, nh=nh)
+    for _ in range(warmup):
+        bt.step()
+    l0 = disc.ctx.launches
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rec = bt.step()
+    dt = time.perf_counter() - t0
+    out = {"workload": "C4: anions Z=1..20, N=Z+1, ordermax=20, 40 cells, Q=G=1000, lda_x+lda_c_pw, Double64",
+           "dtype": "double-double (2 x f64)", "atoms": len(Zs), "steps": steps, "warmup": warmup,
+           "ms_per_step": dt / steps * 1e3, "atom_iterations_per_s": len(Zs) * steps / dt,
+           "gpu_launches": disc.ctx.launches - l0, "host_tables_s": t_tab,
+           "all_finite": all(r["Etot"] == r["Etot"] and abs(r["Etot"]) < 1e300 for r in rec)}
+    bt.close()
+    disc.close()
+    return out
 
 
 def Nh_bytes():
@@ -408,6 +448,7 @@ def main():
     ap.add_argument("--sweeps", type=int, default=1, help="periodic-table sweeps per GPU (default 1)")
     ap.add_argument("--eig-margin", type=int, default=0, help="eigenpair window margin (-1: all nh every step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-dd", action="store_true", help="skip the informational Double64 (C4) leg")
     args = ap.parse_args()
     # stdout carries exactly ONE line (the JSON record): anything libraries print there (e.g. NCCL's version
     # banner under torchrun) is sent to stderr instead.

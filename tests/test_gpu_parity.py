@@ -416,12 +416,15 @@ def test_c_abi_error_paths():
     from helpers import package_tables
     setup = dict(CASES["o_lda"])
     model, disc, alg = make_gpu(setup)
-    # Double64 tables are declared in the ABI but not built
-    basis, ops, quad = package_tables(setup["mesh"], setup["p"], 1000)
-    dd = aks.KSEDiscretization(basis, model, lh=2, nh=5, fem_integration_method=quad, femops=ops, dtype="double64")
+    # Double64 (dtype = 1) is built for nspin = 1 (tests/test_gpu_double64.py); spin-polarised Double64 is refused
+    small = aks.P1IntLegendreBasis(aks.expmesh(0, 50, 7, s=1.3), ordermax=4)
+    dd = aks.KSEDiscretization(small, None, lh=0, nh=2, nspin=2, dtype="double64")
     with pytest.raises(AKSError) as ei:
         dd.handle()
     assert ei.value.code == -6
+    with pytest.raises(TypeError):      # Float64 tables cannot be passed off as Double64 ones
+        basis, ops, quad = package_tables(setup["mesh"], setup["p"], 1000)
+        aks.KSEDiscretization(basis, model, lh=2, nh=5, fem_integration_method=quad, femops=ops, dtype="double64")
     # bad arguments
     lib = _capi.lib
     assert lib.aks_scf_step(None, None) == -1
