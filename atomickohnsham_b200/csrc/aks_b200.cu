@@ -126,6 +126,7 @@ static int dd_batch_reset(aks_batch* bt);
 static int dd_set_oda(aks_batch* bt, double scftol, double tinit, int frozen_t, int max_degen, double degen_tol,
                       int maxiter_ls, double abstol_ls, double reltol_ls);
 static int dd_step_launch(aks_batch* bt);
+static int dd_eig_cold(aks_batch* bt, int32_t* counts);
 static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* eps, double* nocc, double* W);
 #define DD_UNSUPPORTED(bt, what)                                                               \
   do {                                                                                         \
@@ -1232,7 +1233,7 @@ extern "C" int aks_debug_eig_cycles(aks_batch* bt, int64_t* out) {
 
 extern "C" int aks_debug_eig_refills(aks_batch* bt, int32_t* counts) {
   if (!bt || !counts) return AKS_EINVAL;
-  DD_UNSUPPORTED(bt, "aks_debug_eig_refills");
+  if (bt->dd) return dd_eig_cold(bt, counts);   // Double64: eigenpairs of the last step that took the cold path
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   CK(cudaMemcpyAsync(counts, bt->dev.redo_cnt, sizeof(int) * bt->B, cudaMemcpyDeviceToHost, ctx->stream));

@@ -233,7 +233,7 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   ZB(dd, D, B * Nh * Nh) ZB(dd, Bv, B * Nh) ZB(dd, Wv, B * Nh) ZB(dd, E, B * 5) ZB(dd, t, B) ZB(int, niter, B)
   ZB(int, status, B) ZB(int, warm, B) ZB(dd, H, B * L * C * n * n) ZB(dd, eps, B * L * nh) ZB(dd, U, B * L * nh * Nh)
   ZB(dd, vtmp, B * L * nh * Nh) ZB(dd, ekin_orb, B * L * nh) ZB(dd, ecou_orb, B * L * nh) ZB(dd, occ, B * L * nh)
-  ZB(int, eig_fail, B) ZB(dd, scratch, B * L * nh * C * n * n) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
+  ZB(int, eig_fail, B) ZB(int, eig_cold, B) ZB(int, eig_code, B * L * nh) ZB(dd, scratch, B * L * nh * C * n * n) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
   ZB(dd, orb_n0, B * DD_MAXORB) ZB(dd, orb_n1, B * DD_MAXORB) ZB(dd, orb_n, B * DD_MAXORB) ZB(int, degen, B)
   ZB(dd, bloc, B * DD_MAXORB * C * n) ZB(dd, borb, B * DD_MAXORB * Nh) ZB(dd, worb, B * DD_MAXORB * Nh)
   ZB(dd, Bnew, B * Nh) ZB(dd, Wnew, B * Nh) ZB(dd, Enew, B * 5) ZB(dd, tmix, B) ZB(dd, tnew, B)
@@ -277,6 +277,7 @@ static int dd_step_launch(aks_batch* bt) {
   cudaStream_t st = ctx->stream;
   const int B = bt->B, no = bt->dd->max_orb_launch;
   CK(cudaMemsetAsync(b.eig_fail, 0, sizeof(int) * B, st));
+  CK(cudaMemsetAsync(b.eig_cold, 0, sizeof(int) * B, st));
   if (bt->dd->any_xc) {
     ddk_xc<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
     LAUNCH_CHECK();
@@ -362,5 +363,19 @@ extern "C" int aks_dd_xc_eval(aks_ctx* ctx, int32_t npts, const double* rho, int
   CK(cudaMemcpyAsync(zk, dz, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   cudaFreeAsync(dr, ctx->stream); cudaFreeAsync(dv_, ctx->stream); cudaFreeAsync(dz, ctx->stream);
+  return AKS_OK;
+}
+
+static int dd_eig_cold(aks_batch* bt, int32_t* counts) {
+  aks_ctx* ctx = bt->disc->ctx;
+  if (getenv("AKS_DD_EIG_CODES")) {   // debug: per-pair reason codes of problem 0 instead ([L][nh] words)
+    const DDBatchDev& b = bt->dd->dev;
+    std::vector<int> h((size_t)b.L * b.nh);
+    CK(cudaMemcpyAsync(h.data(), b.eig_code, sizeof(int) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < h.size(); ++i) if (h[i]) fprintf(stderr, "[dd eig] l=%zu k=%zu code=%d cl=%d ch=%d\n", i / b.nh, i % b.nh, h[i] & 0xff, (h[i] >> 8) & 0xff, (h[i] >> 16) & 0xff);
+  }
+  CK(cudaMemcpyAsync(counts, bt->dd->dev.eig_cold, sizeof(int) * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
 }

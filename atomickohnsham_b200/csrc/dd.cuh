@@ -89,6 +89,11 @@ DD_HD dd dd_min(dd a, dd b) { return (a < b) ? a : b; }
 DD_HD dd dd_max(dd a, dd b) { return (a < b) ? b : a; }
 DD_HD bool dd_isfinite(dd a) { return isfinite(a.hi) && isfinite(a.lo); }
 
+// 1/k for a small integer k to double-double accuracy: hi = fl(1/k), lo = (1 - k hi)/k with the residual exact (FMA)
+DD_HD dd dd_inv_int(double k) {
+  const double hi = 1.0 / k;
+  return dd_make(hi, fma(-hi, k, 1.0) / k);
+}
 // ---- elementary functions (the reference's Double64 functionals call log, ^ and sqrt of DoubleFloats)
 #define DD_LN2_HI 6.931471805599452862e-01
 #define DD_LN2_LO 2.319046813846299558e-17
@@ -103,7 +108,7 @@ DD_HD dd dd_exp(dd x) {
   // expm1(r) = r + r^2/2! + ... (|r| < 1.4e-3: 11 terms reach 1e-36)
   dd term = r, p = r;
   for (int n = 2; n <= 11; ++n) {
-    term = (term * r) / (double)n;
+    term = (term * r) * dd_inv_int((double)n);
     p = p + term;
   }
   for (int i = 0; i < 8; ++i) p = p * 2.0 + p * p;
@@ -123,7 +128,7 @@ DD_HD dd dd_log1p(dd e) {
   dd term = z, acc = z;
   for (int k = 3; k <= 61; k += 2) {
     term = term * z2;
-    const dd add = term / (double)k;
+    const dd add = term * dd_inv_int((double)k);
     acc = acc + add;
     if (fabs(add.hi) < 1e-36 * fabs(acc.hi)) break;
   }

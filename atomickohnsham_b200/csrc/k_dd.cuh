@@ -86,6 +86,8 @@ struct DDBatchDev {
   dd* ecou_orb; // [B][L][nh]
   dd* occ;      // [B][L][nh]   occupations of the trial density
   int* eig_fail;// [B]
+  int* eig_code;// [B][L][nh]  why the warm path was left: 1 RQI not converged, 2 index not certified (debug)
+  int* eig_cold;// [B]   eigenpairs of the last step that went through the cold (bisection) path
   dd* scratch;  // [B][L][nh][C][n*n]
   int* norb;    // [B]
   int* orb_lk;  // [B][DD_MAXORB]   l << 8 | k
@@ -550,6 +552,7 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt) {
   // ---- warm path: once the SCF has settled (last stop < 1e-2), Rayleigh-quotient iteration in dd straight from
   // the previous eigenvector; the result is accepted only if two Float64 inertia counts certify it as level k
   const bool try_warm = bt.warm[b] && fabs(bt.rec[(size_t)b * 7].hi) < 1e-2;
+  if (c == 0) bt.eig_code[pair] = 0;
   if (try_warm) {
     dd pm = dd_make(0.0), ph = dd_make(0.0);
     if (c < C) {
@@ -584,10 +587,11 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt) {
       lo = rho.hi - m; hi = rho.hi + m; mid = rho.hi;
       const int cl = dd_factor_shift<double>(H, M, lo, scratch, S, C, n);
       const int ch = dd_factor_shift<double>(H, M, hi, scratch, S, C, n);
-      if (cl != k || ch != k + 1) fail = 1;
-    }
+      if (cl != k || ch != k + 1) { fail = 1; if (c == 0) bt.eig_code[pair] = 2 | (cl << 8) | (ch << 16); }
+    } else if (c == 0) bt.eig_code[pair] = 1;
   }
   if (fail) {
+  if (c == 0) atomicAdd(&bt.eig_cold[b], 1);
   // ---- phase A: isolate eigenvalue number k with Float64 inertia counts
   lo = -0.6 * Zb * Zb - 1.0; hi = 0.5;
   for (int it = 0; it < 12; ++it) {

@@ -37,7 +37,8 @@ for it in range(maxiter):
     steps.append(time.time() - t1)
     nrun = sum(1 for r in rec if r["status"] == 0)
     if it < 5 or it % 10 == 0 or nrun == 0:
-        print(f"it {it:3d} {steps[-1] * 1e3:8.2f} ms running {nrun}", flush=True)
+        cold = bdd.eig_refills()
+        print(f"it {it:3d} {steps[-1] * 1e3:8.2f} ms running {nrun}  cold-path eigenpairs {int(cold.sum())} (per anion: {cold.tolist()})", flush=True)
     if nrun == 0:
         break
 f64, _ = b64.run(maxiter)
