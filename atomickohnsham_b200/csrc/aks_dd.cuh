@@ -12,6 +12,7 @@ struct DDBatchHost {
   DDBatchDev dev{};
   int max_orb_launch = DD_MAXORB;
   bool any_xc = false;
+  size_t eig_smem = 0;   // dynamic shared memory of ddk_eig (0: the packed cell blocks go to global scratch)
 };
 
 static inline dd ddh_pair(const double* a, size_t idx) { return dd_make(a[2 * idx], a[2 * idx + 1]); }
@@ -144,7 +145,7 @@ static int dd_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** out) 
   UPD(Al, A_loc) UPD(M0l, M0_loc) UPD(M1l, Mm1_loc) UPD(M2l, Mm2_loc) UPD(Fl, F_loc) UPD(l2g, l2g)
   UPD(Pg, Pg) UPD(Pgy, Pgy) UPD(xv, xq) UPD(wv, wq) UPD(yv, y) UPD(wyv, wy) UPD(ycell, ycell) UPD(inv1, inv1) UPD(inv2, inv2)
 #undef UPD
-  if ((rc = dev_zeros<dd>(ctx, disc->allocs, (size_t)C * n * n, &dv.Afac)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
+  if ((rc = dev_zeros<dd>(ctx, disc->allocs, (size_t)C * dd_npk(nb), &dv.Afac)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
   if ((rc = dev_zeros<dd>(ctx, disc->allocs, (size_t)2 * DD_NT, &dv.Atri)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
   ddk_setup<<<1, DD_NT, 0, ctx->stream>>>(dv);
   ctx->launches += 1;
@@ -224,6 +225,12 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   UPB(bt->hZ, Z) UPB(bt->hN, N) UPB(bt->hHar, hartree) UPB(bt->hLp, Lp) UPB(bt->hnhp, nhp) UPB(ex, ex) UPB(ec, ec)
 #undef UPB
   const size_t B = nprob, Nh = dv.Nh, C = dv.C, L = dv.L, nh = dv.nh, n = dv.n, Q = dv.Q, G = dv.G;
+  {
+    const size_t need = sizeof(dd) * C * dd_npk((int)n - 2);
+    bt->dd->eig_smem = (need <= 200 * 1024) ? need : 0;
+    if (bt->dd->eig_smem > 40 * 1024)
+      CK(cudaFuncSetAttribute(ddk_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->dd->eig_smem));
+  }
   bool any_xc = false;
   for (int i = 0; i < nprob; ++i) any_xc = any_xc || ex[i] || ec[i];
   bt->dd->any_xc = any_xc;
@@ -233,7 +240,7 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   ZB(dd, D, B * Nh * Nh) ZB(dd, Bv, B * Nh) ZB(dd, Wv, B * Nh) ZB(dd, E, B * 5) ZB(dd, t, B) ZB(int, niter, B)
   ZB(int, status, B) ZB(int, warm, B) ZB(dd, H, B * L * C * n * n) ZB(dd, eps, B * L * nh) ZB(dd, U, B * L * nh * Nh)
   ZB(dd, vtmp, B * L * nh * Nh) ZB(dd, ekin_orb, B * L * nh) ZB(dd, ecou_orb, B * L * nh) ZB(dd, occ, B * L * nh)
-  ZB(int, eig_fail, B) ZB(int, eig_cold, B) ZB(int, eig_code, B * L * nh) ZB(dd, scratch, B * L * nh * C * n * n) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
+  ZB(int, eig_fail, B) ZB(int, eig_cold, B) ZB(int, eig_code, B * L * nh) ZB(dd, scratch, (bt->dd->eig_smem ? 1 : B * L * nh * C * dd_npk((int)n - 2))) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
   ZB(dd, orb_n0, B * DD_MAXORB) ZB(dd, orb_n1, B * DD_MAXORB) ZB(dd, orb_n, B * DD_MAXORB) ZB(int, degen, B)
   ZB(dd, bloc, B * DD_MAXORB * C * n) ZB(dd, borb, B * DD_MAXORB * Nh) ZB(dd, worb, B * DD_MAXORB * Nh)
   ZB(dd, Bnew, B * Nh) ZB(dd, Wnew, B * Nh) ZB(dd, Enew, B * 5) ZB(dd, tmix, B) ZB(dd, tnew, B)
@@ -284,7 +291,7 @@ static int dd_step_launch(aks_batch* bt) {
   }
   ddk_H<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
   LAUNCH_CHECK();
-  ddk_eig<<<dim3(dv.nh, dv.L, B), DD_NT, 0, st>>>(dv, b);
+  ddk_eig<<<dim3(dv.nh, dv.L, B), DD_NT, bt->dd->eig_smem, st>>>(dv, b, bt->dd->eig_smem ? 1 : 0);
   LAUNCH_CHECK();
   ddk_aufbau<<<(B + 31) / 32, 32, 0, st>>>(dv, b);
   LAUNCH_CHECK();

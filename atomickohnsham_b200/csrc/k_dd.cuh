@@ -53,7 +53,7 @@ struct DDDiscDev {
   const dd* wy;       // [G]
   const int* ycell;   // [G]  0-based
   const dd* Pgy;      // [n][G]
-  dd* Afac;           // [C][n][n]  condensed factors of the stiffness blocks (ddk_setup)
+  dd* Afac;           // [npk][C]   packed, cell-interleaved condensed factors of the stiffness blocks (ddk_setup)
   dd* Atri;           // [2][64]    inverse pivots / multipliers of the hat system
 };
 
@@ -88,7 +88,7 @@ struct DDBatchDev {
   int* eig_fail;// [B]
   int* eig_code;// [B][L][nh]  why the warm path was left: 1 RQI not converged, 2 index not certified (debug)
   int* eig_cold;// [B]   eigenpairs of the last step that went through the cold (bisection) path
-  dd* scratch;  // [B][L][nh][C][n*n]
+  dd* scratch;  // [B][L][nh][npk][C]  packed cell blocks of the eigensolver when they do not fit shared memory
   int* norb;    // [B]
   int* orb_lk;  // [B][DD_MAXORB]   l << 8 | k
   dd* orb_n0;   // [B][DD_MAXORB]   first extreme filling (the filling itself when not degenerate)
@@ -110,66 +110,81 @@ struct DDBatchDev {
 };
 
 // ------------------------------------------------------------------ cell-local linear algebra
-// K: n x n row-major symmetric block in generator order (0: right hat, 1: left hat, 2..: bubbles).  On exit
-// the lower triangle of the bubble block holds L (unit lower) with the INVERSE pivots on the diagonal, rows
-// 0 / 1 hold X_g = K_bb^{-1} K_bg, and (s00, s10, s11) is the Schur complement on the two hats; neg counts
-// the negative pivots (Sylvester: eigenvalues below the shift that belong to this cell's elimination).
+// Packed, cell-interleaved storage of one shifted cell block (generator order 0: right hat, 1: left hat, 2..:
+// bubbles): element e of cell c lives at K[e * ks] with K = base + c and ks = C, so that the threads of a warp
+// (one cell each) touch consecutive addresses -- conflict free in shared memory, coalesced in global memory.
+//   e = i(i+1)/2 + j            bubble block, lower triangle (i >= j); after the factorisation: L, with the
+//                               INVERSE pivots on the diagonal
+//   e = T + g nb + i            column g of the hat-bubble coupling K_bg        (T = nb(nb+1)/2)
+//   e = T + 2nb + g nb + i      X_g = K_bb^{-1} K_bg (written by the factorisation)
+//   e = T + 4nb + {0,1,2}       K_00, K_10, K_11
+__host__ __device__ inline int dd_npk(int nb) { return nb * (nb + 1) / 2 + 4 * nb + 3; }
+
 template <class R>
-__device__ __forceinline__ void dd_bb_solve(const R* __restrict__ K, int n, R* x) {
-  const int nb = n - 2;
+__device__ __forceinline__ void dd_bb_solve(const R* __restrict__ K, int ks, int nb, R* x) {
   for (int i = 0; i < nb; ++i) {
     R a = x[i];
-    const R* Ki = K + (2 + i) * n + 2;
-    for (int k = 0; k < i; ++k) a = a - Ki[k] * x[k];
+    const R* Ki = K + (size_t)(i * (i + 1) / 2) * ks;
+    for (int k = 0; k < i; ++k) a = a - Ki[(size_t)k * ks] * x[k];
     x[i] = a;
   }
-  for (int i = 0; i < nb; ++i) x[i] = x[i] * K[(2 + i) * n + 2 + i];
+  for (int i = 0; i < nb; ++i) x[i] = x[i] * K[(size_t)(i * (i + 1) / 2 + i) * ks];
   for (int i = nb - 1; i >= 0; --i) {
     R a = x[i];
-    for (int k = i + 1; k < nb; ++k) a = a - K[(2 + k) * n + 2 + i] * x[k];
+    for (int k = i + 1; k < nb; ++k) a = a - K[(size_t)(k * (k + 1) / 2 + i) * ks] * x[k];
     x[i] = a;
   }
 }
 
+// (s00, s10, s11): Schur complement on the two hats; neg: negative pivots (Sylvester: eigenvalues below the
+// shift that belong to this cell's elimination)
 template <class R>
-__device__ void dd_cell_factor(R* __restrict__ K, int n, R& s00, R& s10, R& s11, int& neg) {
-  const int nb = n - 2;
+__device__ void dd_cell_factor(R* __restrict__ K, int ks, int nb, R& s00, R& s10, R& s11, int& neg) {
   R w[DD_MAXN], dl[DD_MAXN];
+  const int T = nb * (nb + 1) / 2;
   neg = 0;
   for (int j = 0; j < nb; ++j) {
-    R* Kj = K + (2 + j) * n + 2;
-    R d = Kj[j];
+    R* Kj = K + (size_t)(j * (j + 1) / 2) * ks;
+    R d = Kj[(size_t)j * ks];
     for (int k = 0; k < j; ++k) {
-      w[k] = Kj[k] * dl[k];
-      d = d - Kj[k] * w[k];
+      const R ljk = Kj[(size_t)k * ks];
+      w[k] = ljk * dl[k];
+      d = d - ljk * w[k];
     }
     if (Sc<R>::hi(d) < 0.0) ++neg;
     if (Sc<R>::hi(d) == 0.0) d = Sc<R>::fromd(1e-100);
     dl[j] = d;
     const R di = Sc<R>::inv(d);
-    Kj[j] = di;
+    Kj[(size_t)j * ks] = di;
     for (int i = j + 1; i < nb; ++i) {
-      R* Ki = K + (2 + i) * n + 2;
-      R a = Ki[j];
-      for (int k = 0; k < j; ++k) a = a - Ki[k] * w[k];
-      Ki[j] = a * di;
+      R* Ki = K + (size_t)(i * (i + 1) / 2) * ks;
+      R a = Ki[(size_t)j * ks];
+      for (int k = 0; k < j; ++k) a = a - Ki[(size_t)k * ks] * w[k];
+      Ki[(size_t)j * ks] = a * di;
     }
   }
   R* x = w;
-  for (int i = 0; i < nb; ++i) x[i] = K[(2 + i) * n + 0];
-  dd_bb_solve<R>(K, n, x);
-  s00 = K[0];
-  s10 = K[n];
+  const R* c0 = K + (size_t)T * ks;
+  const R* c1 = K + (size_t)(T + nb) * ks;
+  R* x0 = K + (size_t)(T + 2 * nb) * ks;
+  R* x1 = K + (size_t)(T + 3 * nb) * ks;
+  const R* hh = K + (size_t)(T + 4 * nb) * ks;
+  for (int i = 0; i < nb; ++i) x[i] = c0[(size_t)i * ks];
+  dd_bb_solve<R>(K, ks, nb, x);
+  s00 = hh[0];
+  s10 = hh[ks];
   for (int i = 0; i < nb; ++i) {
-    s00 = s00 - K[(2 + i) * n + 0] * x[i];
-    s10 = s10 - K[(2 + i) * n + 1] * x[i];
+    s00 = s00 - c0[(size_t)i * ks] * x[i];
+    s10 = s10 - c1[(size_t)i * ks] * x[i];
+    x0[(size_t)i * ks] = x[i];
   }
-  for (int i = 0; i < nb; ++i) K[2 + i] = x[i];
-  for (int i = 0; i < nb; ++i) x[i] = K[(2 + i) * n + 1];
-  dd_bb_solve<R>(K, n, x);
-  s11 = K[n + 1];
-  for (int i = 0; i < nb; ++i) s11 = s11 - K[(2 + i) * n + 1] * x[i];
-  for (int i = 0; i < nb; ++i) K[n + 2 + i] = x[i];
+  for (int i = 0; i < nb; ++i) x[i] = c1[(size_t)i * ks];
+  dd_bb_solve<R>(K, ks, nb, x);
+  s11 = hh[2 * (size_t)ks];
+  for (int i = 0; i < nb; ++i) {
+    s11 = s11 - c1[(size_t)i * ks] * x[i];
+    x1[(size_t)i * ks] = x[i];
+  }
 }
 
 // shared work arrays of the per-cell kernels (R = double reuses the same storage)
@@ -183,7 +198,6 @@ struct DDShared {
 template <class R>
 __device__ int dd_tri_factor(const R* s00, const R* s10, const R* s11, R* trid, R* tril, int C) {
   int neg = 0;
-  R dprev = Sc<R>::fromd(1.0);
   for (int j = 0; j < C - 1; ++j) {
     R d = s00[j] + s11[j + 1];
     R l = Sc<R>::fromd(0.0);
@@ -196,10 +210,23 @@ __device__ int dd_tri_factor(const R* s00, const R* s10, const R* s11, R* trid, 
     if (Sc<R>::hi(d) == 0.0) d = Sc<R>::fromd(1e-100);
     tril[j] = l;
     trid[j] = Sc<R>::inv(d);
-    dprev = d;
   }
-  (void)dprev;
   return neg;
+}
+
+// packed (Op_c - sigma M_c) of cell c from the full blocks (M == nullptr: Op_c alone)
+template <class R>
+__device__ __forceinline__ void dd_fill_packed(const dd* __restrict__ Hc, const dd* __restrict__ Mc, R sigma, R* K, int ks,
+                                               int n) {
+  const int nb = n - 2, T = nb * (nb + 1) / 2;
+  auto val = [&](int e) { return Mc ? Sc<R>::from(Hc[e]) - sigma * Sc<R>::from(Mc[e]) : Sc<R>::from(Hc[e]); };
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j <= i; ++j) K[(size_t)(i * (i + 1) / 2 + j) * ks] = val((2 + i) * n + 2 + j);
+  for (int g = 0; g < 2; ++g)
+    for (int i = 0; i < nb; ++i) K[(size_t)(T + g * nb + i) * ks] = val((2 + i) * n + g);
+  K[(size_t)(T + 4 * nb) * ks] = val(0);
+  K[(size_t)(T + 4 * nb + 1) * ks] = val(n);
+  K[(size_t)(T + 4 * nb + 2) * ks] = val(n + 1);
 }
 
 // (Hc - sigma Mc) of every cell into the CTA's scratch, factor; all threads return the inertia count
@@ -210,13 +237,11 @@ __device__ int dd_factor_shift(const dd* __restrict__ H, const dd* __restrict__ 
   R* s00 = (R*)S.s00; R* s10 = (R*)S.s10; R* s11 = (R*)S.s11;
   __syncthreads();
   if (c < C) {
-    R* K = (R*)scratch + (size_t)c * n * n;
-    const dd* Hc = H + (size_t)c * n * n;
-    const dd* Mc = M + (size_t)c * n * n;
-    for (int e = 0; e < n * n; ++e) K[e] = Sc<R>::from(Hc[e]) - sigma * Sc<R>::from(Mc[e]);
+    R* K = (R*)scratch + c;
+    dd_fill_packed<R>(H + (size_t)c * n * n, M + (size_t)c * n * n, sigma, K, C, n);
     R a, b, d;
     int neg;
-    dd_cell_factor<R>(K, n, a, b, d, neg);
+    dd_cell_factor<R>(K, C, n - 2, a, b, d, neg);
     s00[c] = a; s10[c] = b; s11[c] = d;
     S.neg[c] = neg;
   }
@@ -230,22 +255,23 @@ __device__ int dd_factor_shift(const dd* __restrict__ H, const dd* __restrict__ 
   return S.total;
 }
 
-// x = K^{-1} b for the factored operator in `fac` ([C][n][n] dd) and the hat factors in S.trid / S.tril;
-// b, x: global vectors in the reference numbering (may alias)
+// x = K^{-1} b for the factored operator in `fac` (packed, interleaved, dd) and the hat factors in S.trid /
+// S.tril; b, x: global vectors in the reference numbering (may alias)
 __device__ void dd_solve(const dd* __restrict__ fac, DDShared& S, const dd* b, dd* x, const int* __restrict__ l2g,
                          int C, int n) {
-  const int c = threadIdx.x, nb = n - 2;
+  const int c = threadIdx.x, nb = n - 2, T = nb * (nb + 1) / 2;
+  const size_t ks = C;
   dd y[DD_MAXN];
-  const dd* K = fac + (size_t)c * n * n;
+  const dd* K = fac + c;
   int base = 0;
   if (c < C) {
     base = l2g[c * n + 2];
     for (int i = 0; i < nb; ++i) y[i] = b[base + i];
-    dd_bb_solve<dd>(K, n, y);
+    dd_bb_solve<dd>(K, C, nb, y);
     dd r0 = dd_make(0.0), r1 = dd_make(0.0);
     for (int i = 0; i < nb; ++i) {
-      r0 = r0 + K[(2 + i) * n + 0] * y[i];
-      r1 = r1 + K[(2 + i) * n + 1] * y[i];
+      r0 = r0 + K[(T + i) * ks] * y[i];
+      r1 = r1 + K[(T + nb + i) * ks] * y[i];
     }
     S.hr[c] = r0;
     S.hl[c] = r1;
@@ -268,7 +294,7 @@ __device__ void dd_solve(const dd* __restrict__ fac, DDShared& S, const dd* b, d
   if (c < C) {
     const dd xr = (c < C - 1) ? S.xh[c] : dd_make(0.0);
     const dd xl = (c > 0) ? S.xh[c - 1] : dd_make(0.0);
-    for (int i = 0; i < nb; ++i) x[base + i] = y[i] - K[2 + i] * xr - K[n + 2 + i] * xl;
+    for (int i = 0; i < nb; ++i) x[base + i] = y[i] - K[(T + 2 * nb + i) * ks] * xr - K[(T + 3 * nb + i) * ks] * xl;
     if (c < C - 1) x[l2g[c * n + 0]] = xr;
   }
   __syncthreads();
@@ -327,11 +353,11 @@ __global__ void __launch_bounds__(DD_NT) ddk_setup(DDDiscDev dv) {
   __shared__ DDShared S;
   const int c = threadIdx.x, n = dv.n, C = dv.C;
   if (c < C) {
-    dd* K = dv.Afac + (size_t)c * n * n;
-    for (int e = 0; e < n * n; ++e) K[e] = dv.A_loc[(size_t)c * n * n + e];
+    dd* K = dv.Afac + c;
+    dd_fill_packed<dd>(dv.A_loc + (size_t)c * n * n, nullptr, dd_make(0.0), K, C, n);
     dd a, b, d;
     int neg;
-    dd_cell_factor<dd>(K, n, a, b, d, neg);
+    dd_cell_factor<dd>(K, C, n - 2, a, b, d, neg);
     S.s00[c] = a; S.s10[c] = b; S.s11[c] = d;
   }
   __syncthreads();
@@ -530,7 +556,9 @@ __global__ void __launch_bounds__(128) ddk_H(DDDiscDev dv, DDBatchDev bt) {
 }
 
 // ------------------------------------------------------------------ eigenpairs
-__global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt) {
+// use_smem: the CTA's packed cell blocks live in dynamic shared memory (C * dd_npk(nb) dd) instead of global scratch
+extern __shared__ dd dd_dyn_smem[];
+__global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, int use_smem) {
   __shared__ DDShared S;
   const int k = blockIdx.x, l = blockIdx.y, b = blockIdx.z;
   if (bt.status[b] != 0) return;
@@ -539,7 +567,7 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt) {
   const size_t chan = (size_t)b * bt.L + l, pair = chan * bt.nh + k;
   const dd* H = bt.H + chan * C * nn;
   const dd* M = dv.M0_loc;
-  dd* scratch = bt.scratch + pair * C * nn;
+  dd* scratch = use_smem ? dd_dyn_smem : bt.scratch + pair * C * dd_npk(n - 2);
   dd* x = bt.U + pair * Nh;
   dd* rhs = bt.vtmp + pair * Nh;
   const int* l2g = dv.l2g;
