@@ -120,20 +120,34 @@ struct DDBatchDev {
 //   e = T + 4nb + {0,1,2}       K_00, K_10, K_11
 __host__ __device__ inline int dd_npk(int nb) { return nb * (nb + 1) / 2 + 4 * nb + 3; }
 
+// init - sum_k term(k) with four independent accumulators: the threads run one cell each at two warps per SM, so
+// instruction-level parallelism is what hides the latency of the dependent double-double chains
+template <class R, class F>
+__device__ __forceinline__ R dd_dot_sub(R init, int cnt, F term) {
+  R a0 = init, a1 = Sc<R>::fromd(0.0), a2 = Sc<R>::fromd(0.0), a3 = Sc<R>::fromd(0.0);
+  int k = 0;
+  for (; k + 3 < cnt; k += 4) {
+    a0 = a0 - term(k);
+    a1 = a1 - term(k + 1);
+    a2 = a2 - term(k + 2);
+    a3 = a3 - term(k + 3);
+  }
+  for (; k < cnt; ++k) a0 = a0 - term(k);
+  return (a0 + a1) + (a2 + a3);
+}
+
 template <class R>
 __device__ __forceinline__ void dd_bb_solve(const R* __restrict__ K, int ks, int nb, R* x) {
   for (int i = 0; i < nb; ++i) {
-    R a = x[i];
     const R* Ki = K + (size_t)(i * (i + 1) / 2) * ks;
-    for (int k = 0; k < i; ++k) a = a - Ki[(size_t)k * ks] * x[k];
-    x[i] = a;
+    x[i] = dd_dot_sub<R>(x[i], i, [&](int k) { return Ki[(size_t)k * ks] * x[k]; });
   }
   for (int i = 0; i < nb; ++i) x[i] = x[i] * K[(size_t)(i * (i + 1) / 2 + i) * ks];
-  for (int i = nb - 1; i >= 0; --i) {
-    R a = x[i];
-    for (int k = i + 1; k < nb; ++k) a = a - K[(size_t)(k * (k + 1) / 2 + i) * ks] * x[k];
-    x[i] = a;
-  }
+  for (int i = nb - 1; i >= 0; --i)
+    x[i] = dd_dot_sub<R>(x[i], nb - 1 - i, [&](int q) {
+      const int k = i + 1 + q;
+      return K[(size_t)(k * (k + 1) / 2 + i) * ks] * x[k];
+    });
 }
 
 // (s00, s10, s11): Schur complement on the two hats; neg: negative pivots (Sylvester: eigenvalues below the
@@ -145,12 +159,8 @@ __device__ void dd_cell_factor(R* __restrict__ K, int ks, int nb, R& s00, R& s10
   neg = 0;
   for (int j = 0; j < nb; ++j) {
     R* Kj = K + (size_t)(j * (j + 1) / 2) * ks;
-    R d = Kj[(size_t)j * ks];
-    for (int k = 0; k < j; ++k) {
-      const R ljk = Kj[(size_t)k * ks];
-      w[k] = ljk * dl[k];
-      d = d - ljk * w[k];
-    }
+    for (int k = 0; k < j; ++k) w[k] = Kj[(size_t)k * ks] * dl[k];
+    R d = dd_dot_sub<R>(Kj[(size_t)j * ks], j, [&](int k) { return Kj[(size_t)k * ks] * w[k]; });
     if (Sc<R>::hi(d) < 0.0) ++neg;
     if (Sc<R>::hi(d) == 0.0) d = Sc<R>::fromd(1e-100);
     dl[j] = d;
@@ -158,8 +168,7 @@ __device__ void dd_cell_factor(R* __restrict__ K, int ks, int nb, R& s00, R& s10
     Kj[(size_t)j * ks] = di;
     for (int i = j + 1; i < nb; ++i) {
       R* Ki = K + (size_t)(i * (i + 1) / 2) * ks;
-      R a = Ki[(size_t)j * ks];
-      for (int k = 0; k < j; ++k) a = a - Ki[(size_t)k * ks] * w[k];
+      const R a = dd_dot_sub<R>(Ki[(size_t)j * ks], j, [&](int k) { return Ki[(size_t)k * ks] * w[k]; });
       Ki[(size_t)j * ks] = a * di;
     }
   }
@@ -530,7 +539,7 @@ __global__ void __launch_bounds__(128) ddk_H(DDDiscDev dv, DDBatchDev bt) {
       const dd* f = bt.fxc + ((size_t)b * dv.C + c) * dv.Q;
       const dd* gi = dv.Pg + (size_t)i * dv.Q;
       const dd* gj = dv.Pg + (size_t)j * dv.Q;
-      for (int q = 0; q < dv.Q; ++q) acc = acc + (gi[q] * gj[q]) * f[q];
+      acc = -dd_dot_sub<dd>(dd_make(0.0), dv.Q, [&](int q) { return (gi[q] * gj[q]) * f[q]; });
       acc = acc * dv.inv1[c];
     }
     Vs[i * n + j] = acc;
@@ -577,6 +586,7 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, in
   dd v[DD_MAXN];
   int fail = 1;
   double lo = 0.0, hi = 0.0, mid = 0.0;
+  bool have_bracket = false;
   // ---- warm path: once the SCF has settled (last stop < 1e-2), Rayleigh-quotient iteration in dd straight from
   // the previous eigenvector; the result is accepted only if two Float64 inertia counts certify it as level k
   const bool try_warm = bt.warm[b] && fabs(bt.rec[(size_t)b * 7].hi) < 1e-2;
@@ -615,21 +625,29 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, in
       lo = rho.hi - m; hi = rho.hi + m; mid = rho.hi;
       const int cl = dd_factor_shift<double>(H, M, lo, scratch, S, C, n);
       const int ch = dd_factor_shift<double>(H, M, hi, scratch, S, C, n);
-      if (cl != k || ch != k + 1) { fail = 1; if (c == 0) bt.eig_code[pair] = 2 | (cl << 8) | (ch << 16); }
+      if (cl != k || ch != k + 1) {
+        fail = 1;
+        // a neighbour sits inside the window (e.g. a localised resonance crossing a box state within 1e-9): the
+        // window still brackets level k, bisect from there
+        have_bracket = (cl <= k && ch >= k + 1);
+        if (c == 0) bt.eig_code[pair] = 2 | (cl << 8) | (ch << 16);
+      }
     } else if (c == 0) bt.eig_code[pair] = 1;
   }
   if (fail) {
   if (c == 0) atomicAdd(&bt.eig_cold[b], 1);
   // ---- phase A: isolate eigenvalue number k with Float64 inertia counts
-  lo = -0.6 * Zb * Zb - 1.0; hi = 0.5;
-  for (int it = 0; it < 12; ++it) {
-    if (dd_factor_shift<double>(H, M, lo, scratch, S, C, n) <= k) break;
-    lo = 2.0 * lo;
-  }
-  for (int it = 0; it < 80; ++it) {
-    if (dd_factor_shift<double>(H, M, hi, scratch, S, C, n) >= k + 1) break;
-    lo = hi;
-    hi = 2.0 * hi + 1.0;
+  if (!have_bracket) {
+    lo = -0.6 * Zb * Zb - 1.0; hi = 0.5;
+    for (int it = 0; it < 12; ++it) {
+      if (dd_factor_shift<double>(H, M, lo, scratch, S, C, n) <= k) break;
+      lo = 2.0 * lo;
+    }
+    for (int it = 0; it < 80; ++it) {
+      if (dd_factor_shift<double>(H, M, hi, scratch, S, C, n) >= k + 1) break;
+      lo = hi;
+      hi = 2.0 * hi + 1.0;
+    }
   }
   for (int it = 0; it < 120; ++it) {
     const double md = 0.5 * (lo + hi);

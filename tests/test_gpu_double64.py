@@ -186,21 +186,23 @@ def test_double64_other_atoms_against_float64():
         assert abs(float(e[0]) - f64[i]["Etot"]) < 2e-10 * abs(f64[i]["Etot"]), (i, float(e[0]), f64[i]["Etot"])
     bdd.close()
     b64.close()
-    # the C2 / C4 discretization (order 20, 40 cells, Nh = 799): neon and the fluoride anion, Hartree only
-    basis = P1IntLegendreBasis(make_mesh(["exp", 0, 300, 41, 1.5]), ordermax=20)
-    models = [KSEModel(Z=10, N=10), KSEModel(Z=9, N=10)]
-    ddisc = KSEDiscretization(basis, models[0], lh=1, nh=4, dtype="double64")
-    fdisc = KSEDiscretization(basis, models[0], lh=1, nh=4)
-    bdd = Batch(models, ddisc, alg)
-    fdd, _ = bdd.run(200)
-    rdd = bdd.records_dd()
-    b64 = Batch(models, fdisc, ODA(tinit=0.6, scftol=1e-11, aufbau=OptimizedAufbau(max_degen=2, tol=1e-3)))
-    f64, _ = b64.run(200)
-    for i in range(len(models)):
-        assert fdd[i]["status"] == 1, (i, fdd[i])
-        assert abs(float(_mpf(rdd[i][1])) - f64[i]["Etot"]) < 2e-10 * abs(f64[i]["Etot"]), (i, fdd[i], f64[i])
-    bdd.close()
-    b64.close()
+    # the C2 / C4 discretization (order 20, 40 cells, Nh = 799): neon and the fluoride anion, Hartree only; and
+    # 52 cells (Nh = 1039), where the eigensolver's packed cell blocks no longer fit shared memory (global scratch)
+    for npts in (41, 53):
+        basis = P1IntLegendreBasis(make_mesh(["exp", 0, 300, npts, 1.5]), ordermax=20)
+        models = [KSEModel(Z=10, N=10), KSEModel(Z=9, N=10)]
+        ddisc = KSEDiscretization(basis, models[0], lh=1, nh=4, dtype="double64")
+        fdisc = KSEDiscretization(basis, models[0], lh=1, nh=4)
+        bdd = Batch(models, ddisc, alg)
+        fdd, _ = bdd.run(200)
+        rdd = bdd.records_dd()
+        b64 = Batch(models, fdisc, ODA(tinit=0.6, scftol=1e-11, aufbau=OptimizedAufbau(max_degen=2, tol=1e-3)))
+        f64, _ = b64.run(200)
+        for i in range(len(models)):
+            assert fdd[i]["status"] == 1, (npts, i, fdd[i])
+            assert abs(float(_mpf(rdd[i][1])) - f64[i]["Etot"]) < 2e-10 * abs(f64[i]["Etot"]), (npts, i, fdd[i], f64[i])
+        bdd.close()
+        b64.close()
 
 
 def test_double64_functionals_pointwise_against_mpmath():
@@ -266,3 +268,54 @@ def test_double64_lda_against_float64_path():
         assert np.allclose(sd["eps"][..., 0, 0][occ], sf["eps"][..., 0][occ], rtol=0, atol=1e-7)
     bdd.close()
     b64.close()
+
+
+def test_double64_reset_state_all_and_frozen_t():
+    """aks_batch_reset reproduces a Double64 run bit for bit; aks_get_state_all returns the pairs of every problem;
+    frozen_t = true (oda/loop.jl:86-96) keeps t at tinit and converges to the same Etot as the line search."""
+    import ctypes as C
+    from atomickohnsham_b200 import KSEDiscretization, KSEModel, ODA, OptimizedAufbau, P1IntLegendreBasis
+    from atomickohnsham_b200 import _capi
+    from atomickohnsham_b200.solver import Batch
+    mp.mp.dps = 50
+    basis = P1IntLegendreBasis(make_mesh(["exp", 0, 80, 15, 1.4]), ordermax=6)
+    models = [KSEModel(Z=2, N=2), KSEModel(Z=10, N=10), KSEModel(Z=3, N=2)]
+    disc = KSEDiscretization(basis, models[0], lh=1, nh=4, dtype="double64")
+    aufbau = OptimizedAufbau(max_degen=2, tol=1e-3)
+    bt = Batch(models, disc, ODA(tinit=0.6, scftol=1e-22, aufbau=aufbau), lh=[0, 1, 0], nh=[2, 4, 3])
+    f1, _ = bt.run(200)
+    r1 = bt.records_dd().copy()
+    s1 = [bt.state(i) for i in range(3)]
+    bt.reset()
+    f2, _ = bt.run(200)
+    r2 = bt.records_dd()
+    assert [f["niter"] for f in f1] == [f["niter"] for f in f2] and np.array_equal(r1, r2)
+    for i in range(3):
+        s2 = bt.state(i)
+        for k in ("eps", "n", "W", "D", "U"):
+            assert np.array_equal(s1[i][k], s2[k]), (i, k)
+    # every problem at once
+    L, nh, Nh = 2, 4, basis.size
+    eps = np.zeros((3, L * nh, 2))
+    n = np.zeros((3, L * nh, 2))
+    W = np.zeros((3, Nh, 2))
+    bt.ctx.check(_capi.lib.aks_get_state_all(bt.h, _capi.dptr(eps), _capi.dptr(n), _capi.dptr(W)))
+    for i in range(3):
+        assert np.array_equal(eps[i].reshape((L, nh, 2), order="F")[..., 0], s1[i]["eps"][..., 0, 0]) or \
+            np.array_equal(eps[i][:, 0].reshape((L, nh), order="F"), s1[i]["eps"][..., 0, 0])
+        assert np.array_equal(W[i], s1[i]["W"])
+        assert n[i][:, 0].sum() == models[i].N
+    # per-problem channel / level counts: helium was solved with lh = 0, nh = 2 only
+    assert np.count_nonzero(s1[0]["eps"][1, :, 0, 0]) == 0 and np.count_nonzero(s1[0]["eps"][0, 2:, 0, 0]) == 0
+    bt.close()
+    # frozen t
+    # (the two-electron systems: plain damping with t = 0.6 converges linearly there)
+    bf = Batch([models[0], models[2]], disc, ODA(tinit=0.6, scftol=1e-24, frozen_t=True, aufbau=aufbau), lh=[0, 0], nh=[2, 3])
+    ff, _ = bf.run(600)
+    rf = bf.records_dd()
+    for j, i in enumerate((0, 2)):
+        assert ff[j]["status"] == 1 and ff[j]["t"] == 0.6, ff[j]
+        e_ls, e_fr = _mpf(r1[i][1]), _mpf(rf[j][1])
+        # the line-search run ends when rounding noise makes t = 0 (module docstring): its Etot carries ~||dD||^2
+        assert abs(e_ls - e_fr) < mp.mpf("1e-20") * abs(e_ls), (i, mp.nstr(e_ls, 34), mp.nstr(e_fr, 34))
+    bf.close()
