@@ -229,7 +229,7 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
     const size_t need = sizeof(dd) * C * dd_npk((int)n - 2);
     bt->dd->eig_smem = (need <= 200 * 1024) ? need : 0;
     if (bt->dd->eig_smem > 40 * 1024)
-      CK(cudaFuncSetAttribute(ddk_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->dd->eig_smem));
+      CK(cudaFuncSetAttribute(ddk_eig<DD_EIG_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->dd->eig_smem));
   }
   bool any_xc = false;
   for (int i = 0; i < nprob; ++i) any_xc = any_xc || ex[i] || ec[i];
@@ -291,7 +291,7 @@ static int dd_step_launch(aks_batch* bt) {
   }
   ddk_H<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
   LAUNCH_CHECK();
-  ddk_eig<<<dim3(dv.nh, dv.L, B), DD_NT, bt->dd->eig_smem, st>>>(dv, b, bt->dd->eig_smem ? 1 : 0);
+  ddk_eig<DD_EIG_LN><<<dim3(dv.nh, dv.L, B), DD_EIG_LN * DD_NT, bt->dd->eig_smem, st>>>(dv, b, bt->dd->eig_smem ? 1 : 0);
   LAUNCH_CHECK();
   ddk_aufbau<<<(B + 31) / 32, 32, 0, st>>>(dv, b);
   LAUNCH_CHECK();

@@ -151,9 +151,15 @@ __device__ __forceinline__ void dd_bb_solve(const R* __restrict__ K, int ks, int
 }
 
 // (s00, s10, s11): Schur complement on the two hats; neg: negative pivots (Sylvester: eigenvalues below the
-// shift that belong to this cell's elimination)
-template <class R>
-__device__ void dd_cell_factor(R* __restrict__ K, int ks, int nb, R& s00, R& s10, R& s11, int& neg) {
+// shift that belong to this cell's elimination).  LN lanes of one warp work on a cell (sub = lane within the
+// group): every lane forms the pivot of column j (redundantly, identically), the rows below it are dealt out to
+// the lanes; with LN > 1 lane 0 returns s00, s10 and lane 1 returns s11 (each solves one hat column).
+__device__ __forceinline__ dd dd_shfl_xor(unsigned m, dd v, int lane) {
+  return dd_make(__shfl_xor_sync(m, v.hi, lane), __shfl_xor_sync(m, v.lo, lane));
+}
+template <class R, int LN>
+__device__ void dd_cell_factor(R* __restrict__ K, int ks, int nb, int sub, unsigned gm, R& s00, R& s10, R& s11,
+                               int& neg) {
   R w[DD_MAXN], dl[DD_MAXN];
   const int T = nb * (nb + 1) / 2;
   neg = 0;
@@ -165,12 +171,14 @@ __device__ void dd_cell_factor(R* __restrict__ K, int ks, int nb, R& s00, R& s10
     if (Sc<R>::hi(d) == 0.0) d = Sc<R>::fromd(1e-100);
     dl[j] = d;
     const R di = Sc<R>::inv(d);
-    Kj[(size_t)j * ks] = di;
-    for (int i = j + 1; i < nb; ++i) {
+    for (int i = j + 1 + sub; i < nb; i += LN) {
       R* Ki = K + (size_t)(i * (i + 1) / 2) * ks;
       const R a = dd_dot_sub<R>(Ki[(size_t)j * ks], j, [&](int k) { return Ki[(size_t)k * ks] * w[k]; });
       Ki[(size_t)j * ks] = a * di;
     }
+    if (LN > 1) __syncwarp(gm);           // every lane has read the pivot entry and row j
+    if (sub == 0) Kj[(size_t)j * ks] = di;
+    if (LN > 1) __syncwarp(gm);
   }
   R* x = w;
   const R* c0 = K + (size_t)T * ks;
@@ -178,22 +186,28 @@ __device__ void dd_cell_factor(R* __restrict__ K, int ks, int nb, R& s00, R& s10
   R* x0 = K + (size_t)(T + 2 * nb) * ks;
   R* x1 = K + (size_t)(T + 3 * nb) * ks;
   const R* hh = K + (size_t)(T + 4 * nb) * ks;
-  for (int i = 0; i < nb; ++i) x[i] = c0[(size_t)i * ks];
-  dd_bb_solve<R>(K, ks, nb, x);
-  s00 = hh[0];
-  s10 = hh[ks];
-  for (int i = 0; i < nb; ++i) {
-    s00 = s00 - c0[(size_t)i * ks] * x[i];
-    s10 = s10 - c1[(size_t)i * ks] * x[i];
-    x0[(size_t)i * ks] = x[i];
+  s00 = s10 = s11 = Sc<R>::fromd(0.0);
+  if (LN == 1 || sub == 0) {
+    for (int i = 0; i < nb; ++i) x[i] = c0[(size_t)i * ks];
+    dd_bb_solve<R>(K, ks, nb, x);
+    s00 = hh[0];
+    s10 = hh[ks];
+    for (int i = 0; i < nb; ++i) {
+      s00 = s00 - c0[(size_t)i * ks] * x[i];
+      s10 = s10 - c1[(size_t)i * ks] * x[i];
+      x0[(size_t)i * ks] = x[i];
+    }
   }
-  for (int i = 0; i < nb; ++i) x[i] = c1[(size_t)i * ks];
-  dd_bb_solve<R>(K, ks, nb, x);
-  s11 = hh[2 * (size_t)ks];
-  for (int i = 0; i < nb; ++i) {
-    s11 = s11 - c1[(size_t)i * ks] * x[i];
-    x1[(size_t)i * ks] = x[i];
+  if (LN == 1 || sub == 1) {
+    for (int i = 0; i < nb; ++i) x[i] = c1[(size_t)i * ks];
+    dd_bb_solve<R>(K, ks, nb, x);
+    s11 = hh[2 * (size_t)ks];
+    for (int i = 0; i < nb; ++i) {
+      s11 = s11 - c1[(size_t)i * ks] * x[i];
+      x1[(size_t)i * ks] = x[i];
+    }
   }
+  if (LN > 1) __syncwarp(gm);
 }
 
 // shared work arrays of the per-cell kernels (R = double reuses the same storage)
@@ -223,39 +237,47 @@ __device__ int dd_tri_factor(const R* s00, const R* s10, const R* s11, R* trid, 
   return neg;
 }
 
-// packed (Op_c - sigma M_c) of cell c from the full blocks (M == nullptr: Op_c alone)
-template <class R>
+// packed (Op_c - sigma M_c) of cell c from the full blocks (M == nullptr: Op_c alone); the entries are dealt out
+// to the LN lanes of the cell
+template <class R, int LN>
 __device__ __forceinline__ void dd_fill_packed(const dd* __restrict__ Hc, const dd* __restrict__ Mc, R sigma, R* K, int ks,
-                                               int n) {
+                                               int n, int sub) {
   const int nb = n - 2, T = nb * (nb + 1) / 2;
   auto val = [&](int e) { return Mc ? Sc<R>::from(Hc[e]) - sigma * Sc<R>::from(Mc[e]) : Sc<R>::from(Hc[e]); };
+  int cnt = 0;
   for (int i = 0; i < nb; ++i)
-    for (int j = 0; j <= i; ++j) K[(size_t)(i * (i + 1) / 2 + j) * ks] = val((2 + i) * n + 2 + j);
+    for (int j = 0; j <= i; ++j)
+      if (LN == 1 || (cnt++ % LN) == sub) K[(size_t)(i * (i + 1) / 2 + j) * ks] = val((2 + i) * n + 2 + j);
   for (int g = 0; g < 2; ++g)
-    for (int i = 0; i < nb; ++i) K[(size_t)(T + g * nb + i) * ks] = val((2 + i) * n + g);
-  K[(size_t)(T + 4 * nb) * ks] = val(0);
-  K[(size_t)(T + 4 * nb + 1) * ks] = val(n);
-  K[(size_t)(T + 4 * nb + 2) * ks] = val(n + 1);
+    for (int i = 0; i < nb; ++i)
+      if (LN == 1 || (cnt++ % LN) == sub) K[(size_t)(T + g * nb + i) * ks] = val((2 + i) * n + g);
+  if (sub == 0) {
+    K[(size_t)(T + 4 * nb) * ks] = val(0);
+    K[(size_t)(T + 4 * nb + 1) * ks] = val(n);
+    K[(size_t)(T + 4 * nb + 2) * ks] = val(n + 1);
+  }
 }
 
 // (Hc - sigma Mc) of every cell into the CTA's scratch, factor; all threads return the inertia count
-template <class R>
+template <class R, int LN>
 __device__ int dd_factor_shift(const dd* __restrict__ H, const dd* __restrict__ M, R sigma, void* scratch,
                                DDShared& S, int C, int n) {
-  const int c = threadIdx.x;
+  const int c = threadIdx.x / LN, sub = threadIdx.x % LN;
   R* s00 = (R*)S.s00; R* s10 = (R*)S.s10; R* s11 = (R*)S.s11;
   __syncthreads();
   if (c < C) {
+    const unsigned gm = __activemask();
     R* K = (R*)scratch + c;
-    dd_fill_packed<R>(H + (size_t)c * n * n, M + (size_t)c * n * n, sigma, K, C, n);
+    dd_fill_packed<R, LN>(H + (size_t)c * n * n, M + (size_t)c * n * n, sigma, K, C, n, sub);
+    if (LN > 1) __syncwarp(gm);
     R a, b, d;
     int neg;
-    dd_cell_factor<R>(K, C, n - 2, a, b, d, neg);
-    s00[c] = a; s10[c] = b; s11[c] = d;
-    S.neg[c] = neg;
+    dd_cell_factor<R, LN>(K, C, n - 2, sub, gm, a, b, d, neg);
+    if (sub == 0) { s00[c] = a; s10[c] = b; S.neg[c] = neg; }
+    if (LN == 1 || sub == 1) s11[c] = d;
   }
   __syncthreads();
-  if (c == 0) {
+  if (threadIdx.x == 0) {
     int tot = dd_tri_factor<R>(s00, s10, s11, (R*)S.trid, (R*)S.tril, C);
     for (int j = 0; j < C; ++j) tot += S.neg[j];
     S.total = tot;
@@ -265,15 +287,18 @@ __device__ int dd_factor_shift(const dd* __restrict__ H, const dd* __restrict__ 
 }
 
 // x = K^{-1} b for the factored operator in `fac` (packed, interleaved, dd) and the hat factors in S.trid /
-// S.tril; b, x: global vectors in the reference numbering (may alias)
+// S.tril; b, x: global vectors in the reference numbering (may alias).  Lane 0 of every cell does the (sequential)
+// substitutions.
+template <int LN>
 __device__ void dd_solve(const dd* __restrict__ fac, DDShared& S, const dd* b, dd* x, const int* __restrict__ l2g,
                          int C, int n) {
-  const int c = threadIdx.x, nb = n - 2, T = nb * (nb + 1) / 2;
+  const int c = threadIdx.x / LN, sub = threadIdx.x % LN, nb = n - 2, T = nb * (nb + 1) / 2;
   const size_t ks = C;
   dd y[DD_MAXN];
   const dd* K = fac + c;
   int base = 0;
-  if (c < C) {
+  const bool mine = (c < C && sub == 0);
+  if (mine) {
     base = l2g[c * n + 2];
     for (int i = 0; i < nb; ++i) y[i] = b[base + i];
     dd_bb_solve<dd>(K, C, nb, y);
@@ -286,7 +311,7 @@ __device__ void dd_solve(const dd* __restrict__ fac, DDShared& S, const dd* b, d
     S.hl[c] = r1;
   }
   __syncthreads();
-  if (c == 0) {
+  if (threadIdx.x == 0) {
     const int m = C - 1;
     for (int j = 0; j < m; ++j) {
       dd rh = b[l2g[j * n + 0]] - S.hr[j] - S.hl[j + 1];
@@ -300,7 +325,7 @@ __device__ void dd_solve(const dd* __restrict__ fac, DDShared& S, const dd* b, d
     }
   }
   __syncthreads();
-  if (c < C) {
+  if (mine) {
     const dd xr = (c < C - 1) ? S.xh[c] : dd_make(0.0);
     const dd xl = (c > 0) ? S.xh[c - 1] : dd_make(0.0);
     for (int i = 0; i < nb; ++i) x[base + i] = y[i] - K[(T + 2 * nb + i) * ks] * xr - K[(T + 3 * nb + i) * ks] * xl;
@@ -316,35 +341,42 @@ __device__ __forceinline__ void dd_load_local(const dd* x, const int* __restrict
   const int base = l2g[c * n + 2];
   for (int i = 0; i < n - 2; ++i) v[2 + i] = x[base + i];
 }
+// v^T K v of one cell: the rows are dealt out to the LN lanes of the cell, every lane returns the total
+template <int LN>
 __device__ __forceinline__ dd dd_quad_local(const dd* __restrict__ K, const dd* v, int n) {
+  const int sub = threadIdx.x % LN;
+  const unsigned gm = (LN > 1) ? __activemask() : 0u;
   dd acc = dd_make(0.0);
-  for (int i = 0; i < n; ++i) {
+  for (int i = sub; i < n; i += LN) {
     dd r = dd_make(0.0);
     for (int j = 0; j < n; ++j) r = r + K[i * n + j] * v[j];
     acc = acc + r * v[i];
   }
+  for (int o = 1; o < LN; o <<= 1) acc = acc + dd_shfl_xor(gm, acc, o);
   return acc;
 }
-// sum over the CTA in a fixed order; every thread receives the same value
+// sum of one value per cell over the CTA in a fixed order; every thread receives the same value
+template <int LN>
 __device__ __forceinline__ dd dd_block_sum(dd v, DDShared& S, int nact) {
   __syncthreads();
-  S.red[threadIdx.x] = v;
+  if (threadIdx.x % LN == 0 && (int)(threadIdx.x / LN) < DD_NT) S.red[threadIdx.x / LN] = v;
   __syncthreads();
   dd s = dd_make(0.0);
   for (int i = 0; i < nact; ++i) s = s + S.red[i];
   return s;
 }
 // y = Op x, Op given by cell-owned blocks
+template <int LN>
 __device__ void dd_matvec(const dd* __restrict__ Op, DDShared& S, const dd* x, dd* y, const int* __restrict__ l2g,
                           int C, int n) {
-  const int c = threadIdx.x;
+  const int c = threadIdx.x / LN, sub = threadIdx.x % LN;
   __syncthreads();
   if (c < C) {
     dd v[DD_MAXN];
     dd_load_local(x, l2g, c, C, n, v);
     const dd* K = Op + (size_t)c * n * n;
     const int base = l2g[c * n + 2];
-    for (int i = 0; i < n; ++i) {
+    for (int i = sub; i < n; i += LN) {
       dd r = dd_make(0.0);
       for (int j = 0; j < n; ++j) r = r + K[i * n + j] * v[j];
       if (i == 0) S.hr[c] = r;
@@ -353,7 +385,7 @@ __device__ void dd_matvec(const dd* __restrict__ Op, DDShared& S, const dd* x, d
     }
   }
   __syncthreads();
-  if (c < C - 1) y[l2g[c * n + 0]] = S.hr[c] + S.hl[c + 1];
+  if (sub == 0 && c < C - 1) y[l2g[c * n + 0]] = S.hr[c] + S.hl[c + 1];
   __syncthreads();
 }
 
@@ -363,10 +395,10 @@ __global__ void __launch_bounds__(DD_NT) ddk_setup(DDDiscDev dv) {
   const int c = threadIdx.x, n = dv.n, C = dv.C;
   if (c < C) {
     dd* K = dv.Afac + c;
-    dd_fill_packed<dd>(dv.A_loc + (size_t)c * n * n, nullptr, dd_make(0.0), K, C, n);
+    dd_fill_packed<dd, 1>(dv.A_loc + (size_t)c * n * n, nullptr, dd_make(0.0), K, C, n, 0);
     dd a, b, d;
     int neg;
-    dd_cell_factor<dd>(K, C, n - 2, a, b, d, neg);
+    dd_cell_factor<dd, 1>(K, C, n - 2, 0, 0u, a, b, d, neg);
     S.s00[c] = a; S.s10[c] = b; S.s11[c] = d;
   }
   __syncthreads();
@@ -567,12 +599,14 @@ __global__ void __launch_bounds__(128) ddk_H(DDDiscDev dv, DDBatchDev bt) {
 // ------------------------------------------------------------------ eigenpairs
 // use_smem: the CTA's packed cell blocks live in dynamic shared memory (C * dd_npk(nb) dd) instead of global scratch
 extern __shared__ dd dd_dyn_smem[];
-__global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, int use_smem) {
+#define DD_EIG_LN 4     // lanes per cell in ddk_eig
+template <int LN>
+__global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, int use_smem) {
   __shared__ DDShared S;
   const int k = blockIdx.x, l = blockIdx.y, b = blockIdx.z;
   if (bt.status[b] != 0) return;
   if (l >= bt.Lp[b] || k >= bt.nhp[b]) return;
-  const int n = dv.n, nn = n * n, C = dv.C, Nh = dv.Nh, c = threadIdx.x;
+  const int n = dv.n, nn = n * n, C = dv.C, Nh = dv.Nh, c = threadIdx.x / LN, tid = threadIdx.x;
   const size_t chan = (size_t)b * bt.L + l, pair = chan * bt.nh + k;
   const dd* H = bt.H + chan * C * nn;
   const dd* M = dv.M0_loc;
@@ -590,30 +624,30 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, in
   // ---- warm path: once the SCF has settled (last stop < 1e-2), Rayleigh-quotient iteration in dd straight from
   // the previous eigenvector; the result is accepted only if two Float64 inertia counts certify it as level k
   const bool try_warm = bt.warm[b] && fabs(bt.rec[(size_t)b * 7].hi) < 1e-2;
-  if (c == 0) bt.eig_code[pair] = 0;
+  if (tid == 0) bt.eig_code[pair] = 0;
   if (try_warm) {
     dd pm = dd_make(0.0), ph = dd_make(0.0);
     if (c < C) {
       dd_load_local(x, l2g, c, C, n, v);
-      pm = dd_quad_local(M + (size_t)c * nn, v, n);
-      ph = dd_quad_local(H + (size_t)c * nn, v, n);
+      pm = dd_quad_local<LN>(M + (size_t)c * nn, v, n);
+      ph = dd_quad_local<LN>(H + (size_t)c * nn, v, n);
     }
-    const dd nrm0 = dd_block_sum(pm, S, C);
-    rho = dd_block_sum(ph, S, C) / nrm0;
+    const dd nrm0 = dd_block_sum<LN>(pm, S, C);
+    rho = dd_block_sum<LN>(ph, S, C) / nrm0;
     for (int it = 0; it < 6; ++it) {
-      dd_factor_shift<dd>(H, M, rho, scratch, S, C, n);
-      dd_matvec(M, S, x, rhs, l2g, C, n);
-      dd_solve(scratch, S, rhs, x, l2g, C, n);
+      dd_factor_shift<dd, LN>(H, M, rho, scratch, S, C, n);
+      dd_matvec<LN>(M, S, x, rhs, l2g, C, n);
+      dd_solve<LN>(scratch, S, rhs, x, l2g, C, n);
       pm = dd_make(0.0); ph = dd_make(0.0);
       if (c < C) {
         dd_load_local(x, l2g, c, C, n, v);
-        pm = dd_quad_local(M + (size_t)c * nn, v, n);
-        ph = dd_quad_local(H + (size_t)c * nn, v, n);
+        pm = dd_quad_local<LN>(M + (size_t)c * nn, v, n);
+        ph = dd_quad_local<LN>(H + (size_t)c * nn, v, n);
       }
-      const dd nrm = dd_block_sum(pm, S, C);
-      const dd hq = dd_block_sum(ph, S, C);
+      const dd nrm = dd_block_sum<LN>(pm, S, C);
+      const dd hq = dd_block_sum<LN>(ph, S, C);
       const dd sc = dd_inv(dd_sqrt(nrm));
-      for (int i = c; i < Nh; i += DD_NT) x[i] = x[i] * sc;
+      for (int i = tid; i < Nh; i += LN * DD_NT) x[i] = x[i] * sc;
       __syncthreads();
       const dd rnew = hq / nrm;
       const double delta = fabs((rnew - rho).hi);
@@ -623,28 +657,28 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, in
     if (!fail) {
       const double m = 1e-9 * fmax(1.0, fabs(rho.hi));
       lo = rho.hi - m; hi = rho.hi + m; mid = rho.hi;
-      const int cl = dd_factor_shift<double>(H, M, lo, scratch, S, C, n);
-      const int ch = dd_factor_shift<double>(H, M, hi, scratch, S, C, n);
+      const int cl = dd_factor_shift<double, LN>(H, M, lo, scratch, S, C, n);
+      const int ch = dd_factor_shift<double, LN>(H, M, hi, scratch, S, C, n);
       if (cl != k || ch != k + 1) {
         fail = 1;
         // a neighbour sits inside the window (e.g. a localised resonance crossing a box state within 1e-9): the
         // window still brackets level k, bisect from there
         have_bracket = (cl <= k && ch >= k + 1);
-        if (c == 0) bt.eig_code[pair] = 2 | (cl << 8) | (ch << 16);
+        if (tid == 0) bt.eig_code[pair] = 2 | (cl << 8) | (ch << 16);
       }
-    } else if (c == 0) bt.eig_code[pair] = 1;
+    } else if (tid == 0) bt.eig_code[pair] = 1;
   }
   if (fail) {
-  if (c == 0) atomicAdd(&bt.eig_cold[b], 1);
+  if (tid == 0) atomicAdd(&bt.eig_cold[b], 1);
   // ---- phase A: isolate eigenvalue number k with Float64 inertia counts
   if (!have_bracket) {
     lo = -0.6 * Zb * Zb - 1.0; hi = 0.5;
     for (int it = 0; it < 12; ++it) {
-      if (dd_factor_shift<double>(H, M, lo, scratch, S, C, n) <= k) break;
+      if (dd_factor_shift<double, LN>(H, M, lo, scratch, S, C, n) <= k) break;
       lo = 2.0 * lo;
     }
     for (int it = 0; it < 80; ++it) {
-      if (dd_factor_shift<double>(H, M, hi, scratch, S, C, n) >= k + 1) break;
+      if (dd_factor_shift<double, LN>(H, M, hi, scratch, S, C, n) >= k + 1) break;
       lo = hi;
       hi = 2.0 * hi + 1.0;
     }
@@ -652,7 +686,7 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, in
   for (int it = 0; it < 120; ++it) {
     const double md = 0.5 * (lo + hi);
     if (hi - lo <= 1e-10 * fmax(1.0, fabs(md)) || md <= lo || md >= hi) break;
-    if (dd_factor_shift<double>(H, M, md, scratch, S, C, n) >= k + 1) hi = md; else lo = md;
+    if (dd_factor_shift<double, LN>(H, M, md, scratch, S, C, n) >= k + 1) hi = md; else lo = md;
   }
   mid = 0.5 * (lo + hi);
 
@@ -670,38 +704,38 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, in
     }
   }
   __syncthreads();
-  dd_factor_shift<dd>(H, M, dd_make(mid), scratch, S, C, n);
+  dd_factor_shift<dd, LN>(H, M, dd_make(mid), scratch, S, C, n);
   rho = dd_make(mid);
   for (int rep = 0; rep < 3; ++rep) {
-    dd_matvec(M, S, x, rhs, l2g, C, n);
-    dd_solve(scratch, S, rhs, x, l2g, C, n);
+    dd_matvec<LN>(M, S, x, rhs, l2g, C, n);
+    dd_solve<LN>(scratch, S, rhs, x, l2g, C, n);
     dd part = dd_make(0.0);
-    if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local(M + (size_t)c * nn, v, n); }
-    const dd nrm = dd_block_sum(part, S, C);
+    if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local<LN>(M + (size_t)c * nn, v, n); }
+    const dd nrm = dd_block_sum<LN>(part, S, C);
     const dd sc = dd_inv(dd_sqrt(nrm));
-    for (int i = c; i < Nh; i += DD_NT) x[i] = x[i] * sc;
+    for (int i = tid; i < Nh; i += LN * DD_NT) x[i] = x[i] * sc;
     __syncthreads();
   }
   {
     dd part = dd_make(0.0);
-    if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local(H + (size_t)c * nn, v, n); }
-    rho = dd_block_sum(part, S, C);
+    if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local<LN>(H + (size_t)c * nn, v, n); }
+    rho = dd_block_sum<LN>(part, S, C);
   }
   fail = 1;
   for (int it = 0; it < 8; ++it) {
-    dd_factor_shift<dd>(H, M, rho, scratch, S, C, n);
-    dd_matvec(M, S, x, rhs, l2g, C, n);
-    dd_solve(scratch, S, rhs, x, l2g, C, n);
+    dd_factor_shift<dd, LN>(H, M, rho, scratch, S, C, n);
+    dd_matvec<LN>(M, S, x, rhs, l2g, C, n);
+    dd_solve<LN>(scratch, S, rhs, x, l2g, C, n);
     dd pm = dd_make(0.0), ph = dd_make(0.0);
     if (c < C) {
       dd_load_local(x, l2g, c, C, n, v);
-      pm = dd_quad_local(M + (size_t)c * nn, v, n);
-      ph = dd_quad_local(H + (size_t)c * nn, v, n);
+      pm = dd_quad_local<LN>(M + (size_t)c * nn, v, n);
+      ph = dd_quad_local<LN>(H + (size_t)c * nn, v, n);
     }
-    const dd nrm = dd_block_sum(pm, S, C);
-    const dd hq = dd_block_sum(ph, S, C);
+    const dd nrm = dd_block_sum<LN>(pm, S, C);
+    const dd hq = dd_block_sum<LN>(ph, S, C);
     const dd sc = dd_inv(dd_sqrt(nrm));
-    for (int i = c; i < Nh; i += DD_NT) x[i] = x[i] * sc;
+    for (int i = tid; i < Nh; i += LN * DD_NT) x[i] = x[i] * sc;
     __syncthreads();
     const dd rnew = hq / nrm;
     const double delta = fabs((rnew - rho).hi);
@@ -717,15 +751,15 @@ __global__ void __launch_bounds__(DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, in
   if (c < C) {
     dd_load_local(x, l2g, c, C, n, v);
     // Kin_l = (A + l(l+1) Mm2)/2, Coulomb = -Z Mm1 (assemble.jl:11,25)
-    const dd qa = dd_quad_local(dv.A_loc + (size_t)c * nn, v, n);
-    const dd q2 = (l > 0) ? dd_quad_local(dv.Mm2_loc + (size_t)c * nn, v, n) : dd_make(0.0);
-    const dd q1 = dd_quad_local(dv.Mm1_loc + (size_t)c * nn, v, n);
+    const dd qa = dd_quad_local<LN>(dv.A_loc + (size_t)c * nn, v, n);
+    const dd q2 = (l > 0) ? dd_quad_local<LN>(dv.Mm2_loc + (size_t)c * nn, v, n) : dd_make(0.0);
+    const dd q1 = dd_quad_local<LN>(dv.Mm1_loc + (size_t)c * nn, v, n);
     pk = (qa + q2 * (double)(l * (l + 1))) * 0.5;
     pc = q1 * (-Zb);
   }
-  const dd ekin = dd_block_sum(pk, S, C);
-  const dd ecou = dd_block_sum(pc, S, C);
-  if (c == 0) {
+  const dd ekin = dd_block_sum<LN>(pk, S, C);
+  const dd ecou = dd_block_sum<LN>(pc, S, C);
+  if (tid == 0) {
     bt.eps[pair] = rho;
     bt.ekin_orb[pair] = ekin;
     bt.ecou_orb[pair] = ecou;
@@ -842,7 +876,7 @@ __global__ void __launch_bounds__(DD_NT) ddk_poisson(DDDiscDev dv, DDBatchDev bt
   }
   for (int j = c; j < C; j += DD_NT) { S.trid[j] = dv.Atri[j]; S.tril[j] = dv.Atri[DD_NT + j]; }
   __syncthreads();
-  dd_solve(dv.Afac, S, bo, wo, dv.l2g, C, n);
+  dd_solve<1>(dv.Afac, S, bo, wo, dv.l2g, C, n);
 }
 
 // ------------------------------------------------------------------ occupations, energies, ODA parameter

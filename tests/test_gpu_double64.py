@@ -5,7 +5,7 @@ committed log of `examples/basic_example_doublefloat/` (sodium, Hartree only, sc
 36 digits per number; made by tools/make_golden_dd.py).  Tolerances (north star: 1e-20 relative in Double64):
 Etot of EVERY iteration within 1e-24 relative (measured 1e-30), the energy components within
 max(1e-24, 1e-28 / stop), the iteration count within +-3 of the reference's 59 (measured: 59 with the cold-start
-eigensolver, 61 with the warm-started one; the last iterations are a coin flip, see below).
+eigensolver, 61 / 58 with the warm-started one at 1 / 4 lanes per cell; the last iterations are a coin flip, see below).
 
 Why the components and the orbital energies of the END of the run cannot agree better than ~1e-15 absolute:
 the reference's run does not stop because D has converged to 1e-20 but because its line search returns
