@@ -12,6 +12,7 @@ struct DDBatchHost {
   DDBatchDev dev{};
   int max_orb_launch = DD_MAXORB;
   bool any_xc = false;
+  bool eig_dirty = false;   // levels outside the eigenpair window are stale
   size_t eig_smem = 0;   // dynamic shared memory of ddk_eig (0: the packed cell blocks go to global scratch)
 };
 
@@ -179,6 +180,10 @@ static int dd_batch_reset(aks_batch* bt) {
   CK(cudaMemsetAsync(b.rec64, 0, sizeof(aks_iter_record) * B, ctx->stream));
   std::vector<dd> tv(B, dd_make(b.tinit));
   CK(cudaMemcpyAsync(b.t, tv.data(), sizeof(dd) * B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(b.redo, 0, sizeof(int) * B, ctx->stream));
+  ddk_window_set<<<(int)((B * dv.L + 127) / 128), 128, 0, ctx->stream>>>(b, 1, -1);
+  LAUNCH_CHECK();
+  bt->dd->eig_dirty = false;
   CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
 }
@@ -240,7 +245,7 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   ZB(dd, D, B * Nh * Nh) ZB(dd, Bv, B * Nh) ZB(dd, Wv, B * Nh) ZB(dd, E, B * 5) ZB(dd, t, B) ZB(int, niter, B)
   ZB(int, status, B) ZB(int, warm, B) ZB(dd, H, B * L * C * n * n) ZB(dd, eps, B * L * nh) ZB(dd, U, B * L * nh * Nh)
   ZB(dd, vtmp, B * L * nh * Nh) ZB(dd, ekin_orb, B * L * nh) ZB(dd, ecou_orb, B * L * nh) ZB(dd, occ, B * L * nh)
-  ZB(int, eig_fail, B) ZB(int, eig_cold, B) ZB(int, eig_code, B * L * nh) ZB(dd, scratch, (bt->dd->eig_smem ? 1 : B * L * nh * C * dd_npk((int)n - 2))) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
+  ZB(int, eig_fail, B) ZB(int, kact, B * L) ZB(int, kdone, B * L) ZB(int, redo, B) ZB(int, eig_cold, B) ZB(int, eig_code, B * L * nh) ZB(dd, scratch, (bt->dd->eig_smem ? 1 : B * L * nh * C * dd_npk((int)n - 2))) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
   ZB(dd, orb_n0, B * DD_MAXORB) ZB(dd, orb_n1, B * DD_MAXORB) ZB(dd, orb_n, B * DD_MAXORB) ZB(int, degen, B)
   ZB(dd, bloc, B * DD_MAXORB * C * n) ZB(dd, borb, B * DD_MAXORB * Nh) ZB(dd, worb, B * DD_MAXORB * Nh)
   ZB(dd, Bnew, B * Nh) ZB(dd, Wnew, B * Nh) ZB(dd, Enew, B * 5) ZB(dd, tmix, B) ZB(dd, tnew, B)
@@ -249,7 +254,11 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   ZB(dd, rho_y_new, B * 2 * xg) ZB(dd, corr_part, B * 2 * C) ZB(dd, td, B)
 #undef ZB
   b.scftol = 1e-10; b.tinit = 0.6; b.frozen_t = 0; b.max_degen = 2; b.degen_tol = 1e-3;
-  b.abstol_ls = b.reltol_ls = 4.930380657631324e-28; b.maxiter_ls = 100;   // 1e4 eps(Double64), oda/types.jl:39-40
+  b.abstol_ls = b.reltol_ls = 4.930380657631324e-28; b.maxiter_ls = 100;
+  {
+    const char* wenv = getenv("AKS_DD_EIG_WINDOW");
+    b.eig_window = wenv ? atoi(wenv) : 1;
+  }   // 1e4 eps(Double64), oda/types.jl:39-40
   // the generic driver (aks_scf_run, fetch_records) reads the records and status words through the Float64 view
   bt->dev.B = nprob; bt->dev.s = 1; bt->dev.Lmax = dv.L; bt->dev.nhmax = dv.nh;
   bt->dev.rec = b.rec64;
@@ -291,10 +300,17 @@ static int dd_step_launch(aks_batch* bt) {
   }
   ddk_H<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
   LAUNCH_CHECK();
-  ddk_eig<DD_EIG_LN><<<dim3(dv.nh, dv.L, B), DD_EIG_LN * DD_NT, bt->dd->eig_smem, st>>>(dv, b, bt->dd->eig_smem ? 1 : 0);
+  ddk_eig<DD_EIG_LN><<<dim3(dv.nh, dv.L, B), DD_EIG_LN * DD_NT, bt->dd->eig_smem, st>>>(dv, b, bt->dd->eig_smem ? 1 : 0, 0);
   LAUNCH_CHECK();
-  ddk_aufbau<<<(B + 31) / 32, 32, 0, st>>>(dv, b);
+  ddk_aufbau<<<(B + 31) / 32, 32, 0, st>>>(dv, b, 0);
   LAUNCH_CHECK();
+  if (b.eig_window) {   // problems whose window could not be certified: the remaining levels, then the aufbau again
+    ddk_eig<DD_EIG_LN><<<dim3(dv.nh, dv.L, B), DD_EIG_LN * DD_NT, bt->dd->eig_smem, st>>>(dv, b, bt->dd->eig_smem ? 1 : 0, 1);
+    LAUNCH_CHECK();
+    ddk_aufbau<<<(B + 31) / 32, 32, 0, st>>>(dv, b, 1);
+    LAUNCH_CHECK();
+    bt->dd->eig_dirty = true;
+  }
   ddk_orbB<<<dim3(dv.C, no, B), 32, 0, st>>>(dv, b);
   LAUNCH_CHECK();
   ddk_poisson<<<dim3(no, B), DD_NT, 0, st>>>(dv, b);
@@ -305,7 +321,7 @@ static int dd_step_launch(aks_batch* bt) {
     ddk_rho_grid<<<dim3((dv.G + 127) / 128, B), 128, 0, st>>>(dv, b);
     LAUNCH_CHECK();
   }
-  ddk_decide<<<B, DD_DECIDE_NT, 0, st>>>(dv, b);
+  ddk_decide<<<dim3(DD_DECIDE_CL, B), DD_DECIDE_NT, 0, st>>>(dv, b);
   LAUNCH_CHECK();
   ddk_mix<<<dim3(b.nparts, B), 256, 0, st>>>(dv, b);
   LAUNCH_CHECK();
@@ -321,6 +337,14 @@ static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* e
   const DDDiscDev& dv = bt->disc->dd->dev;
   const DDBatchDev& b = bt->dd->dev;
   const size_t Nh = dv.Nh, L = dv.L, nh = dv.nh;
+  if ((U || eps) && bt->dd->eig_dirty) {
+    // the caller receives all nh eigenpairs of the last Hamiltonian: solve the levels outside the window now
+    ddk_eig<DD_EIG_LN><<<dim3(dv.nh, dv.L, bt->B), DD_EIG_LN * DD_NT, bt->dd->eig_smem, ctx->stream>>>(dv, b, bt->dd->eig_smem ? 1 : 0, 2);
+    LAUNCH_CHECK();
+    ddk_window_set<<<(int)((bt->B * dv.L + 127) / 128), 128, 0, ctx->stream>>>(b, 0, 1);
+    LAUNCH_CHECK();
+    bt->dd->eig_dirty = false;
+  }
   if (D) CK(cudaMemcpyAsync(D, b.D + (size_t)prob * Nh * Nh, sizeof(dd) * Nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
   if (U) CK(cudaMemcpyAsync(U, b.U + (size_t)prob * L * nh * Nh, sizeof(dd) * L * nh * Nh, cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<dd> he(L * nh), hn(L * nh), hw(Nh);

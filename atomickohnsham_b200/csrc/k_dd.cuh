@@ -27,6 +27,8 @@
 // PW92 parameters are Float64 values, rho^(1/3) of Slater exchange is rho^Double64(Float64(1/3)), the rational
 // powers of PW92 are exact.  Spin-unpolarised functionals only (nspin = 1).
 #pragma once
+#include <cooperative_groups.h>
+
 #include "dd.cuh"
 
 #define DD_MAXN 30     // p + 1 <= 30
@@ -86,6 +88,10 @@ struct DDBatchDev {
   dd* ecou_orb; // [B][L][nh]
   dd* occ;      // [B][L][nh]   occupations of the trial density
   int* eig_fail;// [B]
+  int* kact;    // [B][L]  eigenpair window: levels per channel the first pass of the next step solves
+  int* kdone;   // [B][L]  levels per channel that are current for the last Hamiltonian
+  int* redo;    // [B]     the window could not be certified: solve the remaining levels, repeat the aufbau
+  int eig_window;  // 0: every step solves all nh levels of every channel
   int* eig_code;// [B][L][nh]  why the warm path was left: 1 RQI not converged, 2 index not certified (debug)
   int* eig_cold;// [B]   eigenpairs of the last step that went through the cold (bisection) path
   dd* scratch;  // [B][L][nh][npk][C]  packed cell blocks of the eigensolver when they do not fit shared memory
@@ -601,11 +607,27 @@ __global__ void __launch_bounds__(128) ddk_H(DDDiscDev dv, DDBatchDev bt) {
 extern __shared__ dd dd_dyn_smem[];
 #define DD_EIG_LN 4     // lanes per cell in ddk_eig
 template <int LN>
-__global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, int use_smem) {
+// pass 0: levels below the eigenpair window kact of every running problem (the others get a sentinel);
+// pass 1: the remaining levels of the problems whose window was not certified (ddk_aufbau);
+// pass 2: the remaining levels of every problem (aks_get_state returns all nh eigenpairs of the last Hamiltonian)
+#define DD_EPS_MISSING 1e300
+__global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev bt, int use_smem, int pass) {
   __shared__ DDShared S;
   const int k = blockIdx.x, l = blockIdx.y, b = blockIdx.z;
-  if (bt.status[b] != 0) return;
+  if (pass == 2 ? bt.status[b] < 0 : bt.status[b] != 0) return;
   if (l >= bt.Lp[b] || k >= bt.nhp[b]) return;
+  {
+    const int ch = b * bt.L + l;
+    if (pass == 0) {
+      if (k >= bt.kact[ch]) {
+        if (threadIdx.x == 0) bt.eps[(size_t)ch * bt.nh + k] = dd_make(DD_EPS_MISSING);
+        return;
+      }
+    } else {
+      if (pass == 1 && !bt.redo[b]) return;
+      if (k < bt.kdone[ch]) return;
+    }
+  }
   const int n = dv.n, nn = n * n, C = dv.C, Nh = dv.Nh, c = threadIdx.x / LN, tid = threadIdx.x;
   const size_t chan = (size_t)b * bt.L + l, pair = chan * bt.nh + k;
   const dd* H = bt.H + chan * C * nn;
@@ -634,7 +656,9 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
     }
     const dd nrm0 = dd_block_sum<LN>(pm, S, C);
     rho = dd_block_sum<LN>(ph, S, C) / nrm0;
-    for (int it = 0; it < 6; ++it) {
+    // (a level that was outside the eigenpair window so far has no previous vector: straight to the cold path)
+    const int warm_its = (nrm0.hi > 0.0 && isfinite(rho.hi)) ? 6 : 0;
+    for (int it = 0; it < warm_its; ++it) {
       dd_factor_shift<dd, LN>(H, M, rho, scratch, S, C, n);
       dd_matvec<LN>(M, S, x, rhs, l2g, C, n);
       dd_solve<LN>(scratch, S, rhs, x, l2g, C, n);
@@ -768,9 +792,10 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
 }
 
 // ------------------------------------------------------------------ aufbau (one thread per problem)
-__global__ void ddk_aufbau(DDDiscDev dv, DDBatchDev bt) {
+__global__ void ddk_aufbau(DDDiscDev dv, DDBatchDev bt, int pass) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= bt.B || bt.status[b] != 0) return;
+  if (pass == 1 && !bt.redo[b]) return;
   const int Lp = bt.Lp[b], nhp = bt.nhp[b], ne = Lp * nhp;
   int order[DD_MAXORB];
   dd ef[DD_MAXORB], nf0[DD_MAXORB], nf1[DD_MAXORB];
@@ -789,6 +814,10 @@ __global__ void ddk_aufbau(DDDiscDev dv, DDBatchDev bt) {
   dd left = dd_make(bt.N[b]);
   int i = 0, degen = 0, err = 0;
   const dd tol = dd_make(bt.degen_tol);
+  dd e_last = dd_make(-1e300);       // head of the last block the fill examined
+  int top_ex[8];                     // highest level per channel the fill examined (L <= 8 channels tracked)
+  for (int l = 0; l < 8; ++l) top_ex[l] = -1;
+  bool touched_missing = false;
   while (left > dd_make(0.0) && i < ne) {
     int blk[8];
     int len = 1;
@@ -796,8 +825,14 @@ __global__ void ddk_aufbau(DDDiscDev dv, DDBatchDev bt) {
     int j = i + 1;
     while (j < ne && dd_abs(ef[order[j]] - ef[blk[0]]) < tol && len < bt.max_degen && len < 8) { blk[len++] = order[j]; ++j; }
     i += len;
+    e_last = ef[blk[0]];
     dd tot = dd_make(0.0);
-    for (int q = 0; q < len; ++q) tot = tot + (double)(4 * (blk[q] % Lp) + 2);
+    for (int q = 0; q < len; ++q) {
+      tot = tot + (double)(4 * (blk[q] % Lp) + 2);
+      if (ef[blk[q]].hi > 0.5 * DD_EPS_MISSING) touched_missing = true;
+      const int lq = blk[q] % Lp, kq = blk[q] / Lp;
+      if (lq < 8 && kq > top_ex[lq]) top_ex[lq] = kq;
+    }
     if (left >= tot) {
       for (int q = 0; q < len; ++q) { nf0[blk[q]] = dd_make((double)(4 * (blk[q] % Lp) + 2)); nf1[blk[q]] = nf0[blk[q]]; }
       left = left - tot;
@@ -819,6 +854,40 @@ __global__ void ddk_aufbau(DDDiscDev dv, DDBatchDev bt) {
       break;
     }
   }
+  // ---- certificate of the eigenpair window: the levels of a channel are ordered, so if the highest solved level
+  // of every truncated channel lies above (last block head + tol), no unsolved level could have been occupied or
+  // have joined a degenerate block -- the fill is the one of the all-nh solve.  Otherwise: solve the rest (pass 1).
+  if (pass == 0 && bt.eig_window) {
+    bool unsafe = touched_missing;
+    for (int l = 0; l < Lp; ++l) {
+      const int ka = bt.kact[b * bt.L + l];
+      bt.kdone[b * bt.L + l] = ka;
+      if (ka < nhp) {
+        const dd top = bt.eps[((size_t)b * bt.L + l) * bt.nh + ka - 1];
+        if (!(top > e_last + tol)) unsafe = true;
+      }
+    }
+    if (unsafe) {
+      bt.redo[b] = 1;
+      for (int l = 0; l < Lp; ++l) bt.kact[b * bt.L + l] = nhp;
+      return;
+    }
+    bt.redo[b] = 0;
+  } else {
+    for (int l = 0; l < Lp; ++l) bt.kdone[b * bt.L + l] = nhp;
+    bt.redo[b] = 0;
+  }
+  if (bt.eig_window)
+    // window of the next step: every level of the channel up to (last block head + tol), one level above it (the
+    // certificate needs it) and one spare; shrinks by at most one level per step
+    for (int l = 0; l < Lp; ++l) {
+      const int solved = bt.kdone[b * bt.L + l];
+      int cnt = 0;
+      for (int k = 0; k < solved; ++k)
+        if (!(bt.eps[((size_t)b * bt.L + l) * bt.nh + k] > e_last + tol)) cnt = k + 1;
+      if (l < 8 && top_ex[l] + 1 > cnt) cnt = top_ex[l] + 1;
+      bt.kact[b * bt.L + l] = min(nhp, max(cnt + 2, solved - 1));
+    }
   // orbitals that carry weight in either filling, density! order (k outer, l inner, density.jl:15-41)
   int cnt = 0;
   for (int idx = 0; idx < ne; ++idx) {
@@ -837,6 +906,14 @@ __global__ void ddk_aufbau(DDDiscDev dv, DDBatchDev bt) {
     bt.status[b] = st;
     bt.rec64[b].status = st;
   }
+}
+// every level is current / the next step solves every level (reset, after the completion pass of aks_get_state)
+__global__ void ddk_window_set(DDBatchDev bt, int set_kact, int set_kdone) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= bt.B * bt.L) return;
+  const int nhp = bt.nhp[i / bt.L];
+  if (set_kact) bt.kact[i] = nhp;
+  if (set_kdone) bt.kdone[i] = set_kdone > 0 ? nhp : 0;
 }
 
 // ------------------------------------------------------------------ b_o = F:(u_o u_o^T) per cell
@@ -942,8 +1019,11 @@ __device__ inline void ddb_update(DDBrent& s, dd nf) {
   }
 }
 
-#define DD_DECIDE_NT 512
+#define DD_DECIDE_NT 256   // threads per CTA of ddk_decide
+#define DD_DECIDE_CL 4     // CTAs (one thread-block cluster) per problem: the grid evaluations of Exc are split
+                           // over the cluster and summed through distributed shared memory
 struct DDDecideShared {
+  dd part;          // this CTA's share of the last grid sum (read by the whole cluster)
   dd g[32 * 32];    // Gram matrix b_a . w_b of the involved orbitals
   dd hp[32];        // b_a . W_prev
   dd nfin[32];
@@ -953,18 +1033,23 @@ struct DDDecideShared {
   int go;
 };
 
-// Exc on the global grid for rho = a new0 + bq new1 + cq prev (compute_exc_energy, energies.jl:217-233)
+// Exc on the global grid for rho = a new0 + bq new1 + cq prev (compute_exc_energy, energies.jl:217-233).  The
+// points are dealt out to the CTAs of the cluster; every CTA adds the partial sums of all ranks in the same fixed
+// order, so the whole cluster holds the same value (the Brent state machines of the CTAs stay in lockstep).
 __device__ dd dd_exc_grid(const DDDiscDev& dv, const DDBatchDev& bt, int b, dd a, dd bq, dd cq, bool use1,
                           DDDecideShared& S) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  const int R = (int)cl.num_blocks(), r = (int)cl.block_rank();
   const int G = dv.G, ex = bt.ex[b], ec = bt.ec[b];
   const dd* n0 = bt.rho_y_new + ((size_t)b * 2 + 0) * G;
   const dd* n1 = bt.rho_y_new + ((size_t)b * 2 + 1) * G;
   const dd* pr = bt.rho_y + (size_t)b * G;
   dd acc = dd_make(0.0);
-  for (int q = threadIdx.x; q < G; q += blockDim.x) {
-    dd r = a * n0[q] + cq * pr[q];
-    if (use1) r = r + bq * n1[q];
-    const dd val = r * dd_xc_zk(dd_max(r, dd_make(0.0)), ex, ec);
+  for (int q = r * (int)blockDim.x + (int)threadIdx.x; q < G; q += R * (int)blockDim.x) {
+    dd rr = a * n0[q] + cq * pr[q];
+    if (use1) rr = rr + bq * n1[q];
+    const dd val = rr * dd_xc_zk(dd_max(rr, dd_make(0.0)), ex, ec);
     acc = acc + dv.wy[q] * (val * (dv.y[q] * dv.y[q]));
   }
   __syncthreads();
@@ -974,7 +1059,11 @@ __device__ dd dd_exc_grid(const DDDiscDev& dv, const DDBatchDev& bt, int b, dd a
     if ((int)threadIdx.x < h) S.red[threadIdx.x] = S.red[threadIdx.x] + S.red[threadIdx.x + h];
     __syncthreads();
   }
-  const dd sum = S.red[0];
+  if (threadIdx.x == 0) S.part = S.red[0];
+  cl.sync();
+  dd sum = dd_make(0.0);
+  for (int rr = 0; rr < R; ++rr) sum = sum + *cl.map_shared_rank(&S.part, rr);
+  cl.sync();   // nobody overwrites its share before every rank has read it
   return sum * DD_FOURPI;
 }
 
@@ -1025,8 +1114,9 @@ __device__ void dd_line_search(const DDDiscDev& dv, const DDBatchDev& bt, int b,
 
 // The scalar logic is executed redundantly by every thread (identical results), so that the CTA-wide
 // evaluations of Exc sit in uniform control flow; thread 0 writes.
-__global__ void __launch_bounds__(DD_DECIDE_NT) ddk_decide(DDDiscDev dv, DDBatchDev bt) {
-  const int b = blockIdx.x, Nh = dv.Nh, tid = threadIdx.x;
+__global__ void __cluster_dims__(DD_DECIDE_CL, 1, 1) __launch_bounds__(DD_DECIDE_NT) ddk_decide(DDDiscDev dv, DDBatchDev bt) {
+  const int b = blockIdx.y, Nh = dv.Nh, tid = threadIdx.x;
+  const bool writer = (blockIdx.x == 0);   // every CTA of the cluster computes the same numbers, rank 0 stores them
   if (bt.status[b] != 0) return;
   __shared__ DDDecideShared S;
   const int no = bt.norb[b];
@@ -1138,7 +1228,7 @@ __global__ void __launch_bounds__(DD_DECIDE_NT) ddk_decide(DDDiscDev dv, DDBatch
     }
     tmix = t;
   }
-  if (tid == 0) {
+  if (tid == 0 && writer) {
     for (int q = 0; q < 5; ++q) bt.Enew[(size_t)b * 5 + q] = en[q];
     bt.tnew[b] = t;
     bt.tmix[b] = tmix;
@@ -1151,7 +1241,7 @@ __global__ void __launch_bounds__(DD_DECIDE_NT) ddk_decide(DDDiscDev dv, DDBatch
     }
   }
   // B, W of the trial density are linear in the occupations
-  for (int i = tid; i < Nh; i += blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + tid; i < Nh; i += gridDim.x * blockDim.x) {
     dd bs = zero, ws = zero;
     for (int a = 0; a < no; ++a) {
       bs = bs + borb[(size_t)a * Nh + i] * S.nfin[a];
