@@ -127,6 +127,7 @@ static int dd_set_oda(aks_batch* bt, double scftol, double tinit, int frozen_t, 
                       int maxiter_ls, double abstol_ls, double reltol_ls);
 static int dd_step_launch(aks_batch* bt);
 static int dd_eig_cold(aks_batch* bt, int32_t* counts);
+static int dd_set_window(aks_batch* bt, int32_t margin);
 static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* eps, double* nocc, double* W);
 #define DD_UNSUPPORTED(bt, what)                                                               \
   do {                                                                                         \
@@ -650,7 +651,7 @@ extern "C" int aks_batch_set_aufbau(aks_batch* bt, int32_t kind, double temp, co
 
 extern "C" int aks_batch_set_eig_window(aks_batch* bt, int32_t margin) {
   if (!bt) return AKS_EINVAL;
-  if (bt->dd) return AKS_OK;   // the Double64 path solves all nh eigenpairs in every step
+  if (bt->dd) return dd_set_window(bt, margin);
   enter_main(bt);
   int rc = ensure_complete(bt);
   if (rc != AKS_OK) return rc;

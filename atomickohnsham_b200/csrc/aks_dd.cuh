@@ -410,3 +410,15 @@ static int dd_eig_cold(aks_batch* bt, int32_t* counts) {
   CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
 }
+
+// aks_batch_set_eig_window on a Double64 batch: margin >= 0 switches the (certified) eigenpair window on,
+// margin < 0 makes every step solve all nh levels; the window size itself is chosen by ddk_aufbau
+static int dd_set_window(aks_batch* bt, int32_t margin) {
+  aks_ctx* ctx = bt->disc->ctx;
+  DDBatchDev& b = bt->dd->dev;
+  b.eig_window = margin >= 0 ? 1 : 0;
+  ddk_window_set<<<(int)(((size_t)bt->B * b.L + 127) / 128), 128, 0, ctx->stream>>>(b, 1, 0);
+  LAUNCH_CHECK();
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}

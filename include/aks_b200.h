@@ -122,7 +122,8 @@ int aks_batch_set_aufbau(aks_batch* batch, int32_t kind, double temp, const doub
  * levels occupied in the previous steps + margin, certifies on the device (one inertia count per
  * channel) that no unsolved level could have been occupied (else solves the rest and repeats the aufbau
  * within the same step), and the remaining eigenpairs of the last Hamiltonian are solved when
- * aks_get_state asks for eps / U.  margin < 0: every step solves all nh eigenpairs.  Default 0.  */
+ * aks_get_state asks for eps / U.  margin < 0: every step solves all nh eigenpairs.  Default 0.
+ * Double64 batches: margin >= 0 switches their (certified) window on, margin < 0 off; its size is chosen on the device. */
 int aks_batch_set_eig_window(aks_batch* batch, int32_t margin);
 
 /* back to niter = 0, D = 0 (KSESolver constructor, src/solver/solver.jl:61-88) */

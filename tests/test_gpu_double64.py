@@ -135,6 +135,20 @@ def test_double64_run_and_float64_agree_and_errors():
     assert len(hist[0]) == final[0]["niter"]
     e_dd = _mpf(bt.records_dd()[0][1])
     assert abs(e_dd - mp.mpf(g["final"]["Etot"])) < mp.mpf("1e-24") * abs(e_dd)
+    # the eigenpair window of the Double64 path is transparent: with every level solved in every step
+    # (margin < 0) the run is the same bit for bit, and aks_get_state returns all nh eigenpairs either way
+    rec_win, st_win = bt.records_dd().copy(), bt.state(0)
+    bt.reset()
+    bt.set_eig_window(-1)
+    final_all, _ = bt.run(100)
+    assert final_all[0]["niter"] == final[0]["niter"] and np.array_equal(bt.records_dd(), rec_win)
+    st_all = bt.state(0)
+    occ = st_all["n"][..., 0, 0] > 0
+    assert np.array_equal(st_all["eps"][occ], st_win["eps"][occ]) and np.array_equal(st_all["n"], st_win["n"])
+    unocc = ~occ
+    dev = np.abs(st_all["eps"][unocc][:, 0] - st_win["eps"][unocc][:, 0])
+    assert dev.max() < 1e-25 + 1e-28 * np.abs(st_all["eps"][unocc][:, 0]).max() or dev.max() < 1e-20
+    bt.set_eig_window(0)
     # two problems in one batch (neutral atom and cation) are independent of each other
     ion = KSEModel(Z=11, N=10)
     bt2 = Batch([model, ion], disc, bt.alg)
