@@ -160,6 +160,14 @@ __device__ __forceinline__ void dd_bb_solve(const R* __restrict__ K, int ks, int
 // shift that belong to this cell's elimination).  LN lanes of one warp work on a cell (sub = lane within the
 // group): every lane forms the pivot of column j (redundantly, identically), the rows below it are dealt out to
 // the lanes; with LN > 1 lane 0 returns s00, s10 and lane 1 returns s11 (each solves one hat column).
+// lanes of this warp that belong to a cell (< C) when LN lanes work on each cell: the participation mask of the
+// warp-level synchronisations and shuffles (computed, not __activemask(): convergence is not guaranteed)
+template <int LN>
+__device__ __forceinline__ unsigned dd_group_mask(int C) {
+  int nact = C * LN - (int)(threadIdx.x / 32) * 32;
+  nact = nact < 0 ? 0 : (nact > 32 ? 32 : nact);
+  return nact == 32 ? 0xffffffffu : ((1u << nact) - 1u);
+}
 __device__ __forceinline__ dd dd_shfl_xor(unsigned m, dd v, int lane) {
   return dd_make(__shfl_xor_sync(m, v.hi, lane), __shfl_xor_sync(m, v.lo, lane));
 }
@@ -272,7 +280,7 @@ __device__ int dd_factor_shift(const dd* __restrict__ H, const dd* __restrict__ 
   R* s00 = (R*)S.s00; R* s10 = (R*)S.s10; R* s11 = (R*)S.s11;
   __syncthreads();
   if (c < C) {
-    const unsigned gm = __activemask();
+    const unsigned gm = dd_group_mask<LN>(C);
     R* K = (R*)scratch + c;
     dd_fill_packed<R, LN>(H + (size_t)c * n * n, M + (size_t)c * n * n, sigma, K, C, n, sub);
     if (LN > 1) __syncwarp(gm);
@@ -349,9 +357,9 @@ __device__ __forceinline__ void dd_load_local(const dd* x, const int* __restrict
 }
 // v^T K v of one cell: the rows are dealt out to the LN lanes of the cell, every lane returns the total
 template <int LN>
-__device__ __forceinline__ dd dd_quad_local(const dd* __restrict__ K, const dd* v, int n) {
+__device__ __forceinline__ dd dd_quad_local(const dd* __restrict__ K, const dd* v, int n, int C) {
   const int sub = threadIdx.x % LN;
-  const unsigned gm = (LN > 1) ? __activemask() : 0u;
+  const unsigned gm = dd_group_mask<LN>(C);
   dd acc = dd_make(0.0);
   for (int i = sub; i < n; i += LN) {
     dd r = dd_make(0.0);
@@ -651,8 +659,8 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
     dd pm = dd_make(0.0), ph = dd_make(0.0);
     if (c < C) {
       dd_load_local(x, l2g, c, C, n, v);
-      pm = dd_quad_local<LN>(M + (size_t)c * nn, v, n);
-      ph = dd_quad_local<LN>(H + (size_t)c * nn, v, n);
+      pm = dd_quad_local<LN>(M + (size_t)c * nn, v, n, C);
+      ph = dd_quad_local<LN>(H + (size_t)c * nn, v, n, C);
     }
     const dd nrm0 = dd_block_sum<LN>(pm, S, C);
     rho = dd_block_sum<LN>(ph, S, C) / nrm0;
@@ -665,8 +673,8 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
       pm = dd_make(0.0); ph = dd_make(0.0);
       if (c < C) {
         dd_load_local(x, l2g, c, C, n, v);
-        pm = dd_quad_local<LN>(M + (size_t)c * nn, v, n);
-        ph = dd_quad_local<LN>(H + (size_t)c * nn, v, n);
+        pm = dd_quad_local<LN>(M + (size_t)c * nn, v, n, C);
+        ph = dd_quad_local<LN>(H + (size_t)c * nn, v, n, C);
       }
       const dd nrm = dd_block_sum<LN>(pm, S, C);
       const dd hq = dd_block_sum<LN>(ph, S, C);
@@ -734,7 +742,7 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
     dd_matvec<LN>(M, S, x, rhs, l2g, C, n);
     dd_solve<LN>(scratch, S, rhs, x, l2g, C, n);
     dd part = dd_make(0.0);
-    if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local<LN>(M + (size_t)c * nn, v, n); }
+    if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local<LN>(M + (size_t)c * nn, v, n, C); }
     const dd nrm = dd_block_sum<LN>(part, S, C);
     const dd sc = dd_inv(dd_sqrt(nrm));
     for (int i = tid; i < Nh; i += LN * DD_NT) x[i] = x[i] * sc;
@@ -742,7 +750,7 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
   }
   {
     dd part = dd_make(0.0);
-    if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local<LN>(H + (size_t)c * nn, v, n); }
+    if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local<LN>(H + (size_t)c * nn, v, n, C); }
     rho = dd_block_sum<LN>(part, S, C);
   }
   fail = 1;
@@ -753,8 +761,8 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
     dd pm = dd_make(0.0), ph = dd_make(0.0);
     if (c < C) {
       dd_load_local(x, l2g, c, C, n, v);
-      pm = dd_quad_local<LN>(M + (size_t)c * nn, v, n);
-      ph = dd_quad_local<LN>(H + (size_t)c * nn, v, n);
+      pm = dd_quad_local<LN>(M + (size_t)c * nn, v, n, C);
+      ph = dd_quad_local<LN>(H + (size_t)c * nn, v, n, C);
     }
     const dd nrm = dd_block_sum<LN>(pm, S, C);
     const dd hq = dd_block_sum<LN>(ph, S, C);
@@ -775,9 +783,9 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
   if (c < C) {
     dd_load_local(x, l2g, c, C, n, v);
     // Kin_l = (A + l(l+1) Mm2)/2, Coulomb = -Z Mm1 (assemble.jl:11,25)
-    const dd qa = dd_quad_local<LN>(dv.A_loc + (size_t)c * nn, v, n);
-    const dd q2 = (l > 0) ? dd_quad_local<LN>(dv.Mm2_loc + (size_t)c * nn, v, n) : dd_make(0.0);
-    const dd q1 = dd_quad_local<LN>(dv.Mm1_loc + (size_t)c * nn, v, n);
+    const dd qa = dd_quad_local<LN>(dv.A_loc + (size_t)c * nn, v, n, C);
+    const dd q2 = (l > 0) ? dd_quad_local<LN>(dv.Mm2_loc + (size_t)c * nn, v, n, C) : dd_make(0.0);
+    const dd q1 = dd_quad_local<LN>(dv.Mm1_loc + (size_t)c * nn, v, n, C);
     pk = (qa + q2 * (double)(l * (l + 1))) * 0.5;
     pc = q1 * (-Zb);
   }
