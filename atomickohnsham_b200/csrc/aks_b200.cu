@@ -128,6 +128,7 @@ static int dd_set_oda(aks_batch* bt, double scftol, double tinit, int frozen_t, 
 static int dd_step_launch(aks_batch* bt);
 static int dd_eig_cold(aks_batch* bt, int32_t* counts);
 static int dd_set_window(aks_batch* bt, int32_t margin);
+static int dd_set_aufbau(aks_batch* bt, int32_t kind, double temp, const double* nfix);
 static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* eps, double* nocc, double* W);
 #define DD_UNSUPPORTED(bt, what)                                                               \
   do {                                                                                         \
@@ -622,8 +623,13 @@ extern "C" int aks_batch_reset(aks_batch* bt) {
 
 extern "C" int aks_batch_set_aufbau(aks_batch* bt, int32_t kind, double temp, const double* nfix) {
   if (!bt) return AKS_EINVAL;
-  if (bt->dd && kind == 0) return AKS_OK;
-  DD_UNSUPPORTED(bt, "SmearedAufbau / FrozenAufbau");
+  if (bt->dd) {
+    if (kind < 0 || kind > 2 || (kind == 1 && !(temp > 0.0)) || (kind == 2 && !nfix)) {
+      bt->disc->ctx->err = "aks_batch_set_aufbau: kind in {0,1,2}, temp > 0 for 1 (SmearedAufbau), nfix for 2 (FrozenAufbau)";
+      return AKS_EINVAL;
+    }
+    return dd_set_aufbau(bt, kind, temp, nfix);
+  }
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   BatchDev& b = bt->dev;

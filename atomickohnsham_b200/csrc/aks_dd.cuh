@@ -245,7 +245,7 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   ZB(dd, D, B * Nh * Nh) ZB(dd, Bv, B * Nh) ZB(dd, Wv, B * Nh) ZB(dd, E, B * 5) ZB(dd, t, B) ZB(int, niter, B)
   ZB(int, status, B) ZB(int, warm, B) ZB(dd, H, B * L * C * n * n) ZB(dd, eps, B * L * nh) ZB(dd, U, B * L * nh * Nh)
   ZB(dd, vtmp, B * L * nh * Nh) ZB(dd, ekin_orb, B * L * nh) ZB(dd, ecou_orb, B * L * nh) ZB(dd, occ, B * L * nh)
-  ZB(int, eig_fail, B) ZB(int, kact, B * L) ZB(int, kdone, B * L) ZB(int, redo, B) ZB(int, eig_cold, B) ZB(int, eig_code, B * L * nh) ZB(dd, scratch, (bt->dd->eig_smem ? 1 : B * L * nh * C * dd_npk((int)n - 2))) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
+  ZB(int, eig_fail, B) ZB(double, nfix, B * L * nh) ZB(int, kact, B * L) ZB(int, kdone, B * L) ZB(int, redo, B) ZB(int, eig_cold, B) ZB(int, eig_code, B * L * nh) ZB(dd, scratch, (bt->dd->eig_smem ? 1 : B * L * nh * C * dd_npk((int)n - 2))) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
   ZB(dd, orb_n0, B * DD_MAXORB) ZB(dd, orb_n1, B * DD_MAXORB) ZB(dd, orb_n, B * DD_MAXORB) ZB(int, degen, B)
   ZB(dd, bloc, B * DD_MAXORB * C * n) ZB(dd, borb, B * DD_MAXORB * Nh) ZB(dd, worb, B * DD_MAXORB * Nh)
   ZB(dd, Bnew, B * Nh) ZB(dd, Wnew, B * Nh) ZB(dd, Enew, B * 5) ZB(dd, tmix, B) ZB(dd, tnew, B)
@@ -253,6 +253,7 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   ZB(dd, rho_q, B * C * xq) ZB(dd, rho_y, B * xg) ZB(dd, fxc, B * C * xq) ZB(dd, rho_q_new, B * 2 * C * xq)
   ZB(dd, rho_y_new, B * 2 * xg) ZB(dd, corr_part, B * 2 * C) ZB(dd, td, B)
 #undef ZB
+  b.aufbau_kind = 0; b.temp = 0.0;
   b.scftol = 1e-10; b.tinit = 0.6; b.frozen_t = 0; b.max_degen = 2; b.degen_tol = 1e-3;
   b.abstol_ls = b.reltol_ls = 4.930380657631324e-28; b.maxiter_ls = 100;
   {
@@ -269,7 +270,7 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
     bt->h_rec_bytes = need;
   }
   // at most this many orbitals carry weight: every level of every channel
-  bt->dd->max_orb_launch = (int)std::min<size_t>(L * nh, 32);
+  bt->dd->max_orb_launch = (int)std::min<size_t>(L * nh, DD_MAXINV);
   *out = bt;
   return dd_batch_reset(bt);
 }
@@ -416,7 +417,30 @@ static int dd_eig_cold(aks_batch* bt, int32_t* counts) {
 static int dd_set_window(aks_batch* bt, int32_t margin) {
   aks_ctx* ctx = bt->disc->ctx;
   DDBatchDev& b = bt->dd->dev;
-  b.eig_window = margin >= 0 ? 1 : 0;
+  b.eig_window = (margin >= 0 && b.aufbau_kind == 0) ? 1 : 0;
+  ddk_window_set<<<(int)(((size_t)bt->B * b.L + 127) / 128), 128, 0, ctx->stream>>>(b, 1, 0);
+  LAUNCH_CHECK();
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
+// aks_batch_set_aufbau on a Double64 batch (kinds as in the Float64 path; nfix per problem (L, nh) column-major,
+// Float64 values: occupations are small integers or user-given fractions)
+static int dd_set_aufbau(aks_batch* bt, int32_t kind, double temp, const double* nfix) {
+  aks_ctx* ctx = bt->disc->ctx;
+  DDBatchDev& b = bt->dd->dev;
+  if (kind == 2) {
+    const size_t L = b.L, nh = b.nh, per = L * nh;
+    std::vector<double> h((size_t)bt->B * per, 0.0);
+    for (size_t p = 0; p < (size_t)bt->B; ++p)
+      for (size_t l = 0; l < L; ++l)
+        for (size_t k = 0; k < nh; ++k) h[p * per + l * nh + k] = nfix[p * per + l + L * k];
+    CK(cudaMemcpyAsync(b.nfix, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  b.aufbau_kind = kind;
+  b.temp = temp;
+  if (kind != 0) b.eig_window = 0;
   ddk_window_set<<<(int)(((size_t)bt->B * b.L + 127) / 128), 128, 0, ctx->stream>>>(b, 1, 0);
   LAUNCH_CHECK();
   CK(cudaStreamSynchronize(ctx->stream));

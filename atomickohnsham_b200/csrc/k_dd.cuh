@@ -34,6 +34,7 @@
 #define DD_MAXN 30     // p + 1 <= 30
 #define DD_NT 64       // threads of the per-cell kernels: one thread per cell, C <= 64
 #define DD_MAXORB 96
+#define DD_MAXINV 40    // orbitals that may carry weight in a step (every level of 4 channels x 10 with smearing)
 
 struct DDDiscDev {
   int p, n, nb, C, Nh, L, nh;
@@ -92,6 +93,9 @@ struct DDBatchDev {
   int* kdone;   // [B][L]  levels per channel that are current for the last Hamiltonian
   int* redo;    // [B]     the window could not be certified: solve the remaining levels, repeat the aufbau
   int eig_window;  // 0: every step solves all nh levels of every channel
+  int aufbau_kind; // 0 OptimizedAufbau, 1 SmearedAufbau (temp), 2 FrozenAufbau (nfix)
+  double temp;     // smearing width in Hartree (aufbau/smeared.jl)
+  double* nfix;    // [B][L][nh] prescribed occupations (aufbau/frozen.jl)
   int* eig_code;// [B][L][nh]  why the warm path was left: 1 RQI not converged, 2 index not certified (debug)
   int* eig_cold;// [B]   eigenpairs of the last step that went through the cold (bisection) path
   dd* scratch;  // [B][L][nh][npk][C]  packed cell blocks of the eigensolver when they do not fit shared memory
@@ -496,9 +500,9 @@ __global__ void __launch_bounds__(128) ddk_rho_nodes(DDDiscDev dv, DDBatchDev bt
   const int c = blockIdx.x, b = blockIdx.y, n = dv.n, Q = dv.Q;
   if (bt.status[b] != 0) return;
   if (bt.ex[b] == 0 && bt.ec[b] == 0) return;
-  __shared__ dd ul[32 * DD_MAXN];
+  __shared__ dd ul[DD_MAXINV * DD_MAXN];
   __shared__ dd red0[128], red1[128];
-  const int no = min(bt.norb[b], 32);
+  const int no = min(bt.norb[b], DD_MAXINV);
   for (int idx = threadIdx.x; idx < no * n; idx += blockDim.x) {
     const int o = idx / n, g = idx - o * n;
     const int lk = bt.orb_lk[(size_t)b * DD_MAXORB + o], gi = dv.l2g[c * n + g];
@@ -545,7 +549,7 @@ __global__ void __launch_bounds__(128) ddk_rho_grid(DDDiscDev dv, DDBatchDev bt)
   if (bt.ex[b] == 0 && bt.ec[b] == 0) return;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= G) return;
-  const int c = dv.ycell[q], no = min(bt.norb[b], 32);
+  const int c = dv.ycell[q], no = min(bt.norb[b], DD_MAXINV);
   dd a0 = dd_make(0.0), a1 = dd_make(0.0);
   for (int o = 0; o < no; ++o) {
     const int lk = bt.orb_lk[(size_t)b * DD_MAXORB + o];
@@ -819,6 +823,49 @@ __global__ void ddk_aufbau(DDDiscDev dv, DDBatchDev bt, int pass) {
     while (j > 0 && ef[i] < ef[order[j - 1]]) { order[j] = order[j - 1]; --j; }
     order[j] = i;
   }
+  if (bt.aufbau_kind != 0) {
+    // SmearedAufbau (aufbau/smeared.jl:68-101): n_i = g_i / (1 + exp((eps_i - mu)/T)), mu by 100 bisection steps on
+    // [min eps - 50 T, max eps + 50 T];  FrozenAufbau (aufbau/frozen.jl:84-88): n = nfix.  Both run without the
+    // eigenpair window (every level is solved in every step).
+    if (bt.aufbau_kind == 1) {
+      const dd T = dd_make(bt.temp), Np = dd_make(bt.N[b]);
+      dd lo = ef[order[0]] - T * 50.0, hi = ef[order[ne - 1]] + T * 50.0;
+      for (int itb = 0; itb < 100; ++itb) {
+        const dd mid = (lo + hi) * 0.5;
+        dd occ = dd_make(0.0);
+        for (int idx = 0; idx < ne; ++idx) {
+          const dd xa = (ef[idx] - mid) / T;
+          if (xa.hi < 700.0) occ = occ + dd_make((double)(4 * (idx % Lp) + 2)) / (dd_exp(xa) + 1.0);
+        }
+        if (occ < Np) lo = mid; else hi = mid;
+      }
+      const dd mu = (lo + hi) * 0.5;
+      for (int idx = 0; idx < ne; ++idx) {
+        const dd xa = (ef[idx] - mu) / T;
+        nf0[idx] = (xa.hi < 700.0) ? dd_make((double)(4 * (idx % Lp) + 2)) / (dd_exp(xa) + 1.0) : dd_make(0.0);
+        nf1[idx] = nf0[idx];
+      }
+    } else {
+      for (int idx = 0; idx < ne; ++idx) {
+        nf0[idx] = dd_make(bt.nfix[((size_t)b * bt.L + idx % Lp) * bt.nh + idx / Lp]);
+        nf1[idx] = nf0[idx];
+      }
+    }
+    int cnt = 0;
+    for (int idx = 0; idx < ne; ++idx)
+      if (nf0[idx].hi != 0.0 && cnt < DD_MAXORB) {
+        bt.orb_lk[(size_t)b * DD_MAXORB + cnt] = ((idx % Lp) << 8) | (idx / Lp);
+        bt.orb_n0[(size_t)b * DD_MAXORB + cnt] = nf0[idx];
+        bt.orb_n1[(size_t)b * DD_MAXORB + cnt] = nf0[idx];
+        ++cnt;
+      }
+    bt.norb[b] = cnt;
+    bt.degen[b] = 0;
+    bt.redo[b] = 0;
+    for (int l = 0; l < Lp; ++l) bt.kdone[b * bt.L + l] = nhp;
+    if (bt.eig_fail[b]) { bt.status[b] = AKS_ENAN; bt.rec64[b].status = AKS_ENAN; }
+    return;
+  }
   dd left = dd_make(bt.N[b]);
   int i = 0, degen = 0, err = 0;
   const dd tol = dd_make(bt.degen_tol);
@@ -1032,9 +1079,9 @@ __device__ inline void ddb_update(DDBrent& s, dd nf) {
                            // over the cluster and summed through distributed shared memory
 struct DDDecideShared {
   dd part;          // this CTA's share of the last grid sum (read by the whole cluster)
-  dd g[32 * 32];    // Gram matrix b_a . w_b of the involved orbitals
-  dd hp[32];        // b_a . W_prev
-  dd nfin[32];
+  dd g[DD_MAXINV * DD_MAXINV];   // Gram matrix b_a . w_b of the involved orbitals
+  dd hp[DD_MAXINV];               // b_a . W_prev
+  dd nfin[DD_MAXINV];
   dd red[DD_DECIDE_NT];
   DDBrent br;
   dd t, f;
@@ -1135,7 +1182,7 @@ __global__ void __cluster_dims__(DD_DECIDE_CL, 1, 1) __launch_bounds__(DD_DECIDE
   const bool has_xc = bt.ex[b] != 0 || bt.ec[b] != 0;
   const bool degen = bt.degen[b] != 0;
   const dd zero = dd_make(0.0), one = dd_make(1.0);
-  if (no > 32) { if (tid == 0) { bt.status[b] = AKS_EINVAL; bt.rec64[b].status = AKS_EINVAL; } return; }
+  if (no > DD_MAXINV) { if (tid == 0) { bt.status[b] = AKS_EINVAL; bt.rec64[b].status = AKS_EINVAL; } return; }
   for (int pq = tid; pq < no * no + no; pq += blockDim.x) {
     dd acc = zero;
     if (har_on) {

@@ -333,3 +333,33 @@ def test_double64_reset_state_all_and_frozen_t():
         # the line-search run ends when rounding noise makes t = 0 (module docstring): its Etot carries ~||dD||^2
         assert abs(e_ls - e_fr) < mp.mpf("1e-20") * abs(e_ls), (i, mp.nstr(e_ls, 34), mp.nstr(e_fr, 34))
     bf.close()
+
+
+@pytest.mark.parametrize("kind", ["smeared", "frozen"])
+def test_double64_smeared_and_frozen_aufbau_against_float64(kind):
+    """SmearedAufbau / FrozenAufbau (aufbau/smeared.jl:68-101, aufbau/frozen.jl:84-88) on a Double64 batch against the
+    Float64 path (pinned to the oracle by test_smeared_and_frozen_aufbau_parity)."""
+    from atomickohnsham_b200 import (FrozenAufbau, KSEDiscretization, KSEModel, ODA, P1IntLegendreBasis, SmearedAufbau)
+    from atomickohnsham_b200.solver import Batch
+    mp.mp.dps = 50
+    basis = P1IntLegendreBasis(make_mesh(["exp", 0, 60, 15, 1.5]), ordermax=6)
+    models = [KSEModel(Z=8, N=8), KSEModel(Z=11, N=11)]
+    auf = SmearedAufbau(Temp=0.05) if kind == "smeared" else FrozenAufbau({"1s": 2.0, "2s": 2.0, "2p": 3.0, "3s": 1.0})
+    if kind == "frozen":
+        models = [KSEModel(Z=8, N=8)]
+    ddisc = KSEDiscretization(basis, models[0], lh=1, nh=4, dtype="double64")
+    fdisc = KSEDiscretization(basis, models[0], lh=1, nh=4)
+    bdd = Batch(models, ddisc, ODA(tinit=0.6, scftol=1e-18, aufbau=auf))
+    b64 = Batch(models, fdisc, ODA(tinit=0.6, scftol=1e-11, aufbau=auf))
+    fdd, _ = bdd.run(200)
+    f64, _ = b64.run(200)
+    rdd = bdd.records_dd()
+    for i in range(len(models)):
+        assert fdd[i]["status"] == 1 and f64[i]["status"] == 1, (fdd[i], f64[i])
+        assert abs(float(_mpf(rdd[i][1])) - f64[i]["Etot"]) < 1e-10 * abs(f64[i]["Etot"]), (i, fdd[i], f64[i])
+        nd = bdd.state(i, want_D=False, want_U=False)["n"]
+        nf = b64.state(i, want_D=False, want_U=False)["n"]
+        assert np.allclose(nd[..., 0, 0] + nd[..., 0, 1], nf[..., 0], rtol=0, atol=1e-8)
+        assert abs((nd[..., 0, 0].sum() + nd[..., 0, 1].sum()) - models[i].N) < 1e-12
+    bdd.close()
+    b64.close()
