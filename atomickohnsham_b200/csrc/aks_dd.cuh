@@ -299,7 +299,7 @@ static int dd_step_launch(aks_batch* bt) {
     ddk_xc<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
     LAUNCH_CHECK();
   }
-  ddk_H<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
+  ddk_H<<<dim3(dv.C, B), 256, 0, st>>>(dv, b);
   LAUNCH_CHECK();
   ddk_eig<DD_EIG_LN><<<dim3(dv.nh, dv.L, B), DD_EIG_LN * DD_NT, bt->dd->eig_smem, st>>>(dv, b, bt->dd->eig_smem ? 1 : 0, 0);
   LAUNCH_CHECK();
