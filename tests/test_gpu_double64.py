@@ -113,6 +113,30 @@ def test_sodium_double64_trajectory_matches_reference_log():
         G = (V[:, :, None] * MV[:, None, :]).sum(axis=0)            # (4, 4)
         err = np.abs(G.hi - np.eye(4)) + np.abs(G.lo)
         assert err.max() < 1e-27, (l, err.max())
+    # eigen-residuals in double-double on the host: H_l = Kin_l - Z M-1 + F.W + N/Rmax M0 assembled from the dd
+    # tables and the returned W (the last step had t = 0, so W belongs to the Hamiltonian of the returned pairs)
+    ops, bs = disc.femops, disc.basis
+    Wd = DD(st["W"][:, 0], st["W"][:, 1])
+    shift = DD(np.array(11.0)) / DD(np.array(float(bs.mesh.points[-1])))
+    for l in range(3):
+        Hh, Hl = np.zeros((bs.size, bs.size)), np.zeros((bs.size, bs.size))
+        Hm = DD(Hh, Hl)
+        for c in range(bs.ncells):
+            Ib, Ig = np.asarray(bs.cells_to_indices[c]), np.asarray(bs.cells_to_generators[c])
+            sub2, sub3 = np.ix_(Ig, Ig), np.ix_(Ig, Ig, Ig)
+            pick = lambda t, sub: DD(t.hi[c][sub], t.lo[c][sub])
+            FW = (pick(ops.F_loc, sub3) * Wd[Ib][None, None, :]).sum(axis=2)
+            blk = (pick(ops.A_loc, sub2) + pick(ops.Mm2_loc, sub2) * float(l * (l + 1))) * 0.5 \
+                + pick(ops.Mm1_loc, sub2) * (-11.0) + FW + pick(ops.M0_loc, sub2) * shift
+            g = np.ix_(Ib, Ib)
+            Hm[g] = Hm[g] + blk
+        V = DD(U[:, :4, l, 0, 0], U[:, :4, l, 0, 1])
+        E = DD(st["eps"][l, :4, 0, 0], st["eps"][l, :4, 0, 1])
+        HV = (Hm[:, :, None] * V[None, :, :]).sum(axis=1)
+        MV = (M[:, :, None] * V[None, :, :]).sum(axis=1)
+        R = HV - MV * E[None, :]
+        res = np.abs(R.hi).max()
+        assert res < 1e-26 * max(1.0, np.abs(E.hi).max()), (l, res)
     # trace(D M0) = N
     D = st["D"]
     Dd = DD(D[:, :, 0, 0], D[:, :, 0, 1])
