@@ -245,7 +245,7 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   ZB(dd, D, B * Nh * Nh) ZB(dd, Bv, B * Nh) ZB(dd, Wv, B * Nh) ZB(dd, E, B * 5) ZB(dd, t, B) ZB(int, niter, B)
   ZB(int, status, B) ZB(int, warm, B) ZB(dd, H, B * L * C * n * n) ZB(dd, eps, B * L * nh) ZB(dd, U, B * L * nh * Nh)
   ZB(dd, vtmp, B * L * nh * Nh) ZB(dd, ekin_orb, B * L * nh) ZB(dd, ecou_orb, B * L * nh) ZB(dd, occ, B * L * nh)
-  ZB(int, eig_fail, B) ZB(double, nfix, B * L * nh) ZB(int, kact, B * L) ZB(int, kdone, B * L) ZB(int, redo, B) ZB(int, eig_cold, B) ZB(int, eig_code, B * L * nh) ZB(dd, scratch, (bt->dd->eig_smem ? 1 : B * L * nh * C * dd_npk((int)n - 2))) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
+  ZB(int, eig_fail, B) ZB(double, nfix, B * L * nh) ZB(int, kact, B * L) ZB(int, kdone, B * L) ZB(int, redo, B) ZB(int, eig_cold, B) ZB(long long, eig_cyc, B * L * nh * 6) ZB(int, eig_code, B * L * nh) ZB(dd, scratch, (bt->dd->eig_smem ? 1 : B * L * nh * C * dd_npk((int)n - 2))) ZB(int, norb, B) ZB(int, orb_lk, B * DD_MAXORB)
   ZB(dd, orb_n0, B * DD_MAXORB) ZB(dd, orb_n1, B * DD_MAXORB) ZB(dd, orb_n, B * DD_MAXORB) ZB(int, degen, B)
   ZB(dd, bloc, B * DD_MAXORB * C * n) ZB(dd, borb, B * DD_MAXORB * Nh) ZB(dd, worb, B * DD_MAXORB * Nh)
   ZB(dd, Bnew, B * Nh) ZB(dd, Wnew, B * Nh) ZB(dd, Enew, B * 5) ZB(dd, tmix, B) ZB(dd, tnew, B)
@@ -295,6 +295,7 @@ static int dd_step_launch(aks_batch* bt) {
   const int B = bt->B, no = bt->dd->max_orb_launch;
   CK(cudaMemsetAsync(b.eig_fail, 0, sizeof(int) * B, st));
   CK(cudaMemsetAsync(b.eig_cold, 0, sizeof(int) * B, st));
+  CK(cudaMemsetAsync(b.eig_cyc, 0, sizeof(long long) * (size_t)B * b.L * b.nh * 6, st));
   if (bt->dd->any_xc) {
     ddk_xc<<<dim3(dv.C, B), 128, 0, st>>>(dv, b);
     LAUNCH_CHECK();
@@ -400,6 +401,21 @@ extern "C" int aks_dd_xc_eval(aks_ctx* ctx, int32_t npts, const double* rho, int
 
 static int dd_eig_cold(aks_batch* bt, int32_t* counts) {
   aks_ctx* ctx = bt->disc->ctx;
+  if (getenv("AKS_DD_EIG_CYCLES")) {   // debug: average cycle split of the CTAs of the last step (thread 0's clock)
+    const DDBatchDev& b = bt->dd->dev;
+    std::vector<long long> h((size_t)bt->B * b.L * b.nh * 6);
+    CK(cudaMemcpyAsync(h.data(), b.eig_cyc, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    double sum[6] = {0, 0, 0, 0, 0, 0}, mx = 0; int cnt = 0;
+    for (size_t i = 0; i < h.size() / 6; ++i) {
+      if (h[i * 6 + 4] <= 0) continue;
+      for (int q = 0; q < 6; ++q) sum[q] += (double)h[i * 6 + q];
+      mx = std::max(mx, (double)h[i * 6 + 4]);
+      ++cnt;
+    }
+    if (cnt) fprintf(stderr, "[dd eig cycles] CTAs %d  avg: dd-factor %.0f  dd-solve %.0f  matvec %.0f  total %.0f  (dd factorisations %.2f)  max total %.0f\n",
+                     cnt, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[4] / cnt, sum[5] / cnt, mx);
+  }
   if (getenv("AKS_DD_EIG_CODES")) {   // debug: per-pair reason codes of problem 0 instead ([L][nh] words)
     const DDBatchDev& b = bt->dd->dev;
     std::vector<int> h((size_t)b.L * b.nh);

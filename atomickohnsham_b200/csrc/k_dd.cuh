@@ -97,6 +97,8 @@ struct DDBatchDev {
   double temp;     // smearing width in Hartree (aufbau/smeared.jl)
   double* nfix;    // [B][L][nh] prescribed occupations (aufbau/frozen.jl)
   int* eig_code;// [B][L][nh]  why the warm path was left: 1 RQI not converged, 2 index not certified (debug)
+  long long* eig_cyc; // [B][L][nh][6] cycles of the last step: dd factorisations, dd solves, mat-vecs, -, total,
+                      // number of dd factorisations (thread 0 of the CTA; debug aid, AKS_DD_EIG_CYCLES)
   int* eig_cold;// [B]   eigenpairs of the last step that went through the cold (bisection) path
   dd* scratch;  // [B][L][nh][npk][C]  packed cell blocks of the eigensolver when they do not fit shared memory
   int* norb;    // [B]
@@ -649,6 +651,9 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
   dd* rhs = bt.vtmp + pair * Nh;
   const int* l2g = dv.l2g;
 
+  long long cyc[6] = {0, 0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
+#define DD_TIME(slot, ...) do { const long long t0_ = clock64(); __VA_ARGS__; cyc[slot] += clock64() - t0_; } while (0)
   const double Zb = bt.Z[b];
   dd rho = dd_make(0.0);
   dd v[DD_MAXN];
@@ -671,9 +676,9 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
     // (a level that was outside the eigenpair window so far has no previous vector: straight to the cold path)
     const int warm_its = (nrm0.hi > 0.0 && isfinite(rho.hi)) ? 6 : 0;
     for (int it = 0; it < warm_its; ++it) {
-      dd_factor_shift<dd, LN>(H, M, rho, scratch, S, C, n);
-      dd_matvec<LN>(M, S, x, rhs, l2g, C, n);
-      dd_solve<LN>(scratch, S, rhs, x, l2g, C, n);
+      DD_TIME(0, dd_factor_shift<dd, LN>(H, M, rho, scratch, S, C, n)); cyc[5] += 1;
+      DD_TIME(2, dd_matvec<LN>(M, S, x, rhs, l2g, C, n));
+      DD_TIME(1, dd_solve<LN>(scratch, S, rhs, x, l2g, C, n));
       pm = dd_make(0.0); ph = dd_make(0.0);
       if (c < C) {
         dd_load_local(x, l2g, c, C, n, v);
@@ -740,11 +745,11 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
     }
   }
   __syncthreads();
-  dd_factor_shift<dd, LN>(H, M, dd_make(mid), scratch, S, C, n);
+  DD_TIME(0, dd_factor_shift<dd, LN>(H, M, dd_make(mid), scratch, S, C, n)); cyc[5] += 1;
   rho = dd_make(mid);
   for (int rep = 0; rep < 3; ++rep) {
-    dd_matvec<LN>(M, S, x, rhs, l2g, C, n);
-    dd_solve<LN>(scratch, S, rhs, x, l2g, C, n);
+    DD_TIME(2, dd_matvec<LN>(M, S, x, rhs, l2g, C, n));
+    DD_TIME(1, dd_solve<LN>(scratch, S, rhs, x, l2g, C, n));
     dd part = dd_make(0.0);
     if (c < C) { dd_load_local(x, l2g, c, C, n, v); part = dd_quad_local<LN>(M + (size_t)c * nn, v, n, C); }
     const dd nrm = dd_block_sum<LN>(part, S, C);
@@ -759,9 +764,9 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
   }
   fail = 1;
   for (int it = 0; it < 8; ++it) {
-    dd_factor_shift<dd, LN>(H, M, rho, scratch, S, C, n);
-    dd_matvec<LN>(M, S, x, rhs, l2g, C, n);
-    dd_solve<LN>(scratch, S, rhs, x, l2g, C, n);
+    DD_TIME(0, dd_factor_shift<dd, LN>(H, M, rho, scratch, S, C, n)); cyc[5] += 1;
+    DD_TIME(2, dd_matvec<LN>(M, S, x, rhs, l2g, C, n));
+    DD_TIME(1, dd_solve<LN>(scratch, S, rhs, x, l2g, C, n));
     dd pm = dd_make(0.0), ph = dd_make(0.0);
     if (c < C) {
       dd_load_local(x, l2g, c, C, n, v);
@@ -800,6 +805,8 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
     bt.ekin_orb[pair] = ekin;
     bt.ecou_orb[pair] = ecou;
     if (fail) atomicAdd(&bt.eig_fail[b], 1);
+    cyc[4] = clock64() - t_begin;
+    for (int q = 0; q < 6; ++q) bt.eig_cyc[pair * 6 + q] = cyc[q];
   }
 }
 
