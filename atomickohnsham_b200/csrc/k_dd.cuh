@@ -660,9 +660,9 @@ __global__ void __launch_bounds__(LN * DD_NT) ddk_eig(DDDiscDev dv, DDBatchDev b
   int fail = 1;
   double lo = 0.0, hi = 0.0, mid = 0.0;
   bool have_bracket = false;
-  // ---- warm path: once the SCF has settled (last stop < 1e-2), Rayleigh-quotient iteration in dd straight from
+  // ---- warm path: once the SCF has settled (last stop < 0.3), Rayleigh-quotient iteration in dd straight from
   // the previous eigenvector; the result is accepted only if two Float64 inertia counts certify it as level k
-  const bool try_warm = bt.warm[b] && fabs(bt.rec[(size_t)b * 7].hi) < 1e-2;
+  const bool try_warm = bt.warm[b] && fabs(bt.rec[(size_t)b * 7].hi) < 0.3;
   if (tid == 0) bt.eig_code[pair] = 0;
   if (try_warm) {
     dd pm = dd_make(0.0), ph = dd_make(0.0);
