@@ -14,11 +14,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaks_b200.so")
 
-AKS_OK, AKS_EINVAL, AKS_ECUDA, AKS_ENOTCONV, AKS_EDEGEN3, AKS_ENAN, AKS_ENOSYS = 0, -1, -2, -3, -4, -5, -6
+AKS_OK, AKS_EINVAL, AKS_ECUDA, AKS_ENOTCONV, AKS_EDEGEN3, AKS_ENAN, AKS_ENOSYS, AKS_EEIG = 0, -1, -2, -3, -4, -5, -6, -7
 AKS_RUNNING, AKS_SUCCESS, AKS_MAXITERS = 0, 1, 2
 AKS_XC_NONE, AKS_LDA_X, AKS_LDA_C_PW = 0, 1, 12
 STATUS_NAMES = {AKS_EINVAL: "AKS_EINVAL", AKS_ECUDA: "AKS_ECUDA", AKS_ENOTCONV: "AKS_ENOTCONV",
-                AKS_EDEGEN3: "AKS_EDEGEN3", AKS_ENAN: "AKS_ENAN", AKS_ENOSYS: "AKS_ENOSYS"}
+                AKS_EDEGEN3: "AKS_EDEGEN3", AKS_ENAN: "AKS_ENAN", AKS_ENOSYS: "AKS_ENOSYS", AKS_EEIG: "AKS_EEIG"}
 
 
 class AKSError(RuntimeError):
@@ -52,12 +52,12 @@ class DiscDesc(C.Structure):
                 ("cell_len", _ip), ("cell_indices", _ip), ("cell_generators", _ip)]
 
 
-EXPORTS = ["aks_ctx_create", "aks_ctx_destroy", "aks_last_error", "aks_ctx_stream",
+EXPORTS = ["aks_ctx_create", "aks_ctx_destroy", "aks_last_error", "aks_ctx_stream", "aks_ctx_configure",
            "aks_disc_create", "aks_disc_destroy", "aks_batch_create", "aks_batch_destroy",
-           "aks_batch_set_oda", "aks_batch_set_aufbau", "aks_batch_set_eig_window", "aks_batch_reset", "aks_scf_step", "aks_scf_run", "aks_get_state", "aks_get_state_all",
+           "aks_batch_set_oda", "aks_batch_set_oda_problem", "aks_batch_set_aufbau", "aks_batch_set_eig_window", "aks_batch_reset", "aks_scf_step", "aks_scf_run", "aks_get_state", "aks_get_state_all",
            "aks_set_density", "aks_assemble_hartree", "aks_assemble_vxc", "aks_eig_lowest",
            "aks_density", "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak", "aks_measure_dmma_peak",
-           "aks_last_phase_ms", "aks_debug_eig_info", "aks_debug_eig_cycles", "aks_debug_eig_refills",
+           "aks_last_phase_ms", "aks_last_kernel_ms", "aks_debug_eig_info", "aks_debug_eig_cycles", "aks_debug_eig_refills",
            "aks_get_records_dd", "aks_dd_xc_eval"]
 
 
@@ -74,6 +74,7 @@ def _load():
     lib.aks_last_error.restype = C.c_char_p
     lib.aks_ctx_stream.argtypes = [vp]
     lib.aks_ctx_stream.restype = vp
+    lib.aks_ctx_configure.argtypes = [vp, C.c_int32, C.c_int32]
     lib.aks_disc_create.argtypes = [vp, C.POINTER(DiscDesc), C.POINTER(vp)]
     lib.aks_disc_destroy.argtypes = [vp]
     lib.aks_disc_destroy.restype = None
@@ -83,6 +84,7 @@ def _load():
     lib.aks_batch_set_oda.argtypes = [vp, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double,
                                       C.c_double, C.c_int32, C.c_double, C.c_int32]
     lib.aks_batch_set_eig_window.argtypes = [vp, C.c_int32]
+    lib.aks_batch_set_oda_problem.argtypes = [vp, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32]
     lib.aks_batch_set_aufbau.argtypes = [vp, C.c_int32, C.c_double, _dp]
     lib.aks_debug_eig_refills.argtypes = [vp, _i32p]
     lib.aks_batch_reset.argtypes = [vp]
@@ -102,6 +104,7 @@ def _load():
     lib.aks_measure_fp64_peak.argtypes = [vp, _dp]
     lib.aks_measure_dmma_peak.argtypes = [vp, _dp]
     lib.aks_last_phase_ms.argtypes = [vp, _dp]
+    lib.aks_last_kernel_ms.argtypes = [vp, C.c_int32, _dp, C.c_char_p, C.c_int32, _i32p]
     lib.aks_debug_eig_info.argtypes = [vp, _i32p]
     lib.aks_debug_eig_cycles.argtypes = [vp, _ip]
     lib.aks_get_records_dd.argtypes = [vp, _dp]
@@ -139,6 +142,11 @@ class Context:
         if rc not in ok:
             raise AKSError(rc, lib.aks_last_error(self.h).decode())
         return rc
+
+    def configure(self, *, use_graphs=None, check_every=None):
+        """Execution options (aks_ctx_configure): CUDA-graph replay of the step, status polling period of run()."""
+        self.check(lib.aks_ctx_configure(self.h, -1 if use_graphs is None else int(bool(use_graphs)),
+                                         0 if check_every is None else int(check_every)))
 
     @property
     def launches(self) -> int:

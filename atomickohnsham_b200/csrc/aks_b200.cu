@@ -34,7 +34,23 @@ struct aks_ctx {
   std::vector<std::pair<void*, size_t>> pinned_free;
   std::vector<cudaStream_t> stream_free;
   std::vector<cudaEvent_t> event_free;
+  int check_every = 4;    // aks_scf_run reads the status words every this many steps (AKS_CHECK_EVERY)
+  bool use_graphs = true; // the step sequence of a lane is captured once and replayed as a CUDA graph (AKS_NO_GRAPH=1: off)
 };
+
+// Every entry point runs with the ctx's device current and restores the caller's device on return: several
+// contexts (one per GPU, each driven by its own host thread) and other CUDA users (torch) share the process.
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DevGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DevGuard() { if (switched) cudaSetDevice(prev); }
+  DevGuard(const DevGuard&) = delete;
+  DevGuard& operator=(const DevGuard&) = delete;
+};
+#define GUARD(ctxp) DevGuard dev_guard_((ctxp)->device)
 
 struct aks_disc {
   aks_ctx* ctx = nullptr;
@@ -53,6 +69,8 @@ struct Lane {
   int B = 0, p0 = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  cudaGraphExec_t gexec = nullptr;   // the lane's step sequence, captured once per set of options
+  int gkernels = 0;                  // kernels per replay
 };
 struct FieldInfo { size_t offset, bytes_per_problem; };
 
@@ -70,14 +88,21 @@ struct aks_batch {
   bool fac_in_smem = true;
   double* fac_global = nullptr;
   size_t smem_pot = 0, smem_eig = 0, smem_red = 0, smem_chan = 0, smem_dens = 0, smem_poisson = 0;
-  std::vector<double> hZ, hN, hHar;
-  std::vector<int> hLp, hnhp;
+  std::vector<double> hZ, hN, hHar, hScftol, hTinit;
+  std::vector<int> hLp, hnhp, hFrozen, hMaxiter;
+  bool graphs_valid = false;         // lanes' graphs match bt->dev (options, pointers)
+  size_t hist_cap_alloc = 0;         // records per problem the device history can hold
   aks_iter_record* h_rec = nullptr;  // pinned
   size_t h_rec_bytes = 0;
   bool timers = false;
   bool eig_dirty = false;   // levels outside the eigenpair window are stale (k_eig)
-  cudaEvent_t ev[14];   // 8 phase boundaries + [9],[10] around k_mix_dense + [11],[12],[13] around k_xc, k_potential
+  cudaEvent_t ev[14] = {};   // 8 phase boundaries + [9],[10] around k_mix_dense + [11],[12],[13] around k_xc, k_potential
   double phase_ms[10] = {0};
+  // per-kernel device times of the last step (AKS_PHASE_TIMERS): an event after every launch
+  std::vector<cudaEvent_t> kev;
+  std::vector<const char*> knames;
+  std::vector<double> kms;
+  size_t kcount = 0;
   DDBatchHost* dd = nullptr;   // batch on a Double64 discretization (aks_dd.cuh)
 };
 
@@ -136,6 +161,25 @@ static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* e
   } while (0)
 
 // ------------------------------------------------------------------------------------ context
+// Dynamic shared memory limits are per function and device, i.e. process-global state: they are raised ONCE per
+// ctx to the device's opt-in maximum, never to the sizes of one batch (a later, smaller batch would otherwise
+// lower the limit under a live larger one).  Launches still request only what they need.
+static int set_kernel_attributes(aks_ctx* ctx) {
+  int optin = 0;
+  CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+#define SMEM_MAX(fn) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))
+  SMEM_MAX((k_potential<1, 4>)); SMEM_MAX((k_potential<2, 2>));
+  SMEM_MAX(k_eig); SMEM_MAX(k_eig_cert);
+  SMEM_MAX(k_reduce<8>); SMEM_MAX(k_reduce<12>); SMEM_MAX(k_reduce<20>); SMEM_MAX(k_reduce<28>);
+  SMEM_MAX(k_eig_init); SMEM_MAX(k_eig_final); SMEM_MAX(k_poisson);
+  SMEM_MAX(k_dens_cells<12>); SMEM_MAX(k_dens_cells<24>); SMEM_MAX(k_dens_cells<32>);
+  SMEM_MAX(k_cells_from_dense<12>); SMEM_MAX(k_cells_from_dense<24>); SMEM_MAX(k_cells_from_dense<32>);
+  SMEM_MAX(k_eig_residual);
+  SMEM_MAX(ddk_eig<DD_EIG_LN>);
+#undef SMEM_MAX
+  return AKS_OK;
+}
+
 extern "C" int aks_ctx_create(int device, aks_ctx** out) {
   if (!out) return AKS_EINVAL;
   aks_ctx* ctx = new aks_ctx();
@@ -144,8 +188,11 @@ extern "C" int aks_ctx_create(int device, aks_ctx** out) {
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) { ctx->err = "no such CUDA device"; return AKS_ECUDA; }
-  CK(cudaSetDevice(device));
+  GUARD(ctx);
   CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  { int rc = set_kernel_attributes(ctx); if (rc != AKS_OK) return rc; }
+  if (const char* e = getenv("AKS_CHECK_EVERY")) ctx->check_every = std::max(1, atoi(e));
+  if (const char* e = getenv("AKS_NO_GRAPH")) ctx->use_graphs = !(e[0] == '1');
   {
     // batches come and go (one per sweep / restart): their device arrays are taken from the device's
     // stream-ordered pool, which keeps freed memory instead of returning it to the OS
@@ -171,6 +218,7 @@ extern "C" int aks_ctx_create(int device, aks_ctx** out) {
 }
 extern "C" void aks_ctx_destroy(aks_ctx* ctx) {
   if (!ctx) return;
+  GUARD(ctx);
   for (auto& pf : ctx->pinned_free) cudaFreeHost(pf.first);
   for (cudaStream_t st : ctx->stream_free) cudaStreamDestroy(st);
   for (cudaEvent_t ev : ctx->event_free) cudaEventDestroy(ev);
@@ -180,6 +228,12 @@ extern "C" void aks_ctx_destroy(aks_ctx* ctx) {
 extern "C" const char* aks_last_error(const aks_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
 extern "C" void* aks_ctx_stream(const aks_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int64_t aks_launch_count(const aks_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int aks_ctx_configure(aks_ctx* ctx, int32_t use_graphs, int32_t check_every) {
+  if (!ctx) return AKS_EINVAL;
+  if (use_graphs >= 0) ctx->use_graphs = use_graphs != 0;   // batches capture lazily: takes effect at their next step
+  if (check_every >= 1) ctx->check_every = check_every;
+  return AKS_OK;
+}
 
 // ------------------------------------------------------------------------------------ disc
 // small dense helpers (setup only)
@@ -206,6 +260,7 @@ static bool chol_inverse(std::vector<double>& A, int m) {
 extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** out) {
   if (!ctx || !D || !out) return AKS_EINVAL;
   *out = nullptr;
+  GUARD(ctx);
   if (D->dtype == 1) return dd_disc_create(ctx, D, out);
   if (D->dtype != 0) { ctx->err = "bad dtype"; return AKS_EINVAL; }
   const int p = D->p, C = D->C, Nh = D->Nh, Q = D->Q, G = D->G, n = p + 1, nb = p - 1;
@@ -407,6 +462,7 @@ extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** 
 
 extern "C" void aks_disc_destroy(aks_disc* disc) {
   if (!disc) return;
+  GUARD(disc->ctx);
   for (void* p : disc->allocs) cudaFreeAsync(p, disc->ctx->stream);
   cudaStreamSynchronize(disc->ctx->stream);
   dd_disc_free(disc);
@@ -421,17 +477,31 @@ static void refresh_lanes(aks_batch* bt);
 static void main_side(aks_batch* bt);
 static void enter_main(aks_batch* bt) { refresh_lanes(bt); main_side(bt); }
 
+static int batch_create_impl(aks_batch* bt, aks_disc* disc, int32_t nprob, const double* Z, const double* N,
+                             const double* hartree, const int32_t* ex_id, const int32_t* ec_id,
+                             const int32_t* lh_p, const int32_t* nh_p);
+
 extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const double* N,
                                 const double* hartree, const int32_t* ex_id, const int32_t* ec_id,
                                 const int32_t* lh_p, const int32_t* nh_p, aks_batch** out) {
   if (!disc || !out || nprob < 1 || !Z || !N) return AKS_EINVAL;
-  aks_ctx* ctx = disc->ctx;
   *out = nullptr;
+  GUARD(disc->ctx);
   if (disc->dd) return dd_batch_create(disc, nprob, Z, N, hartree, ex_id, ec_id, lh_p, nh_p, out);
-  const DiscDev& dv = disc->dev;
   aks_batch* bt = new aks_batch();
   bt->disc = disc;
   bt->B = nprob;
+  const int rc = batch_create_impl(bt, disc, nprob, Z, N, hartree, ex_id, ec_id, lh_p, nh_p);
+  if (rc != AKS_OK) { aks_batch_destroy(bt); return rc; }   // every error path releases what was allocated
+  *out = bt;
+  return AKS_OK;
+}
+
+static int batch_create_impl(aks_batch* bt, aks_disc* disc, int32_t nprob, const double* Z, const double* N,
+                             const double* hartree, const int32_t* ex_id, const int32_t* ec_id,
+                             const int32_t* lh_p, const int32_t* nh_p) {
+  aks_ctx* ctx = disc->ctx;
+  const DiscDev& dv = disc->dev;
   BatchDev& b = bt->dev;
   b.B = nprob; b.s = dv.nspin; b.Lmax = dv.L; b.nhmax = dv.nh;
   b.ntile = (dv.Nh + MIX_TS - 1) / MIX_TS;
@@ -449,19 +519,19 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
     if (lh_p) bt->hLp[i] = lh_p[i] + 1;
     if (nh_p) bt->hnhp[i] = nh_p[i];
     if ((ex[i] != AKS_XC_NONE && ex[i] != AKS_LDA_X) || (ec[i] != AKS_XC_NONE && ec[i] != AKS_LDA_C_PW)) {
-      ctx->err = "unsupported functional id (LDA only: ex in {0,1}, ec in {0,12})"; delete bt; return AKS_EINVAL;
+      ctx->err = "unsupported functional id (LDA only: ex in {0,1}, ec in {0,12})"; return AKS_EINVAL;
     }
     if (bt->hLp[i] < 1 || bt->hLp[i] > dv.L || bt->hnhp[i] < 1 || bt->hnhp[i] > dv.nh || !(N[i] > 0) || !(Z[i] > 0)) {
-      ctx->err = "bad per-problem lh/nh/Z/N"; delete bt; return AKS_EINVAL;
+      ctx->err = "bad per-problem lh/nh/Z/N"; return AKS_EINVAL;
     }
   }
   int rc;
-#define UPB(vec, field) if ((rc = dev_upload(ctx, bt->allocs, vec, &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; } \
+#define UPB(vec, field) if ((rc = dev_upload(ctx, bt->allocs, vec, &b.field)) != AKS_OK) return rc; \
   bt->fields.push_back({offsetof(BatchDev, field), sizeof(*b.field)});
   UPB(bt->hZ, Z) UPB(bt->hN, N) UPB(bt->hHar, hartree) UPB(ex, ex) UPB(ec, ec) UPB(bt->hLp, Lp) UPB(bt->hnhp, nhp)
 #undef UPB
   const size_t B = nprob, s = b.s, Nh = dv.Nh, C = dv.C, Q = dv.Q, G = dv.G, L = b.Lmax, nh = b.nhmax, n = dv.n;
-#define ZB(T, field, count) if ((rc = dev_zeros<T>(ctx, bt->allocs, (count), &b.field)) != AKS_OK) { aks_batch_destroy(bt); return rc; } \
+#define ZB(T, field, count) if ((rc = dev_zeros<T>(ctx, bt->allocs, (count), &b.field)) != AKS_OK) return rc; \
   bt->fields.push_back({offsetof(BatchDev, field), sizeof(T) * ((size_t)(count) / B)});
   ZB(double, Dd, B * s * Nh * Nh) ZB(double, rho_q, B * s * C * Q) ZB(double, rho_y, B * s * G)
   ZB(double, Bv, B * Nh) ZB(double, Wv, B * Nh) ZB(double, E, B * 5) ZB(double, t, B) ZB(double, stop, B)
@@ -474,8 +544,12 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   ZB(double, rho_y_new, B * 2 * s * G) ZB(double, corr_part, B * 2 * C) ZB(double, Bloc_new, B * 2 * C * n)
   ZB(double, B_new, B * 2 * Nh) ZB(double, W_new, B * 2 * Nh) ZB(double, scal, B * 2 * 4) ZB(double, td, B)
   ZB(double, tmix, B) ZB(double, norm_part, B * s * b.ntri) ZB(aks_iter_record, rec, B)
-  ZB(double, Enew, B * 5)
+  ZB(double, Enew, B * 5) ZB(double, scftol_p, B) ZB(int, frozen_p, B) ZB(int, maxiter_p, B) ZB(int, eig_fail, B)
+  ZB(int, niter0, B)
 #undef ZB
+  // device history of aks_scf_run: allocated by the first run that asks for it; a lane sees it from its first problem
+  b.hist = nullptr; b.hist_cap = 0; b.hist_stride = nprob;
+  bt->fields.push_back({offsetof(BatchDev, hist), sizeof(aks_iter_record)});
   // ODA defaults (oda/types.jl:38-44, optimized.jl:23-26)
   b.scftol = 1e-10; b.tinit = 0.6; b.frozen_t = 0; b.maxiter_ls = 100;
   b.abstol_ls = b.reltol_ls = 1e4 * 2.220446049250313e-16;
@@ -490,25 +564,9 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
   bt->smem_dens = sizeof(double) * ((size_t)AKS_MAXORB * disc->nmax_tpl + (size_t)std::max<int>(dv.n * dv.n * b.s, dv.n * dv.n) + AKS_NW + 8);
   bt->smem_poisson = sizeof(double) * ((size_t)2 * dv.Nh + 3 * dv.C + 16);
   if (bt->smem_pot > 220 * 1024 || bt->smem_eig > 220 * 1024 || bt->smem_dens > 220 * 1024) {
-    ctx->err = "discretization too large for the shared-memory tiling of this build"; aks_batch_destroy(bt); return AKS_EINVAL;
+    ctx->err = "discretization too large for the shared-memory tiling of this build"; return AKS_EINVAL;
   }
-  CK(cudaFuncSetAttribute(k_potential<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
-  CK(cudaFuncSetAttribute(k_potential<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_pot));
-  CK(cudaFuncSetAttribute(k_eig, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
-  CK(cudaFuncSetAttribute(k_eig_cert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_eig));
-  CK(cudaFuncSetAttribute(k_reduce<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
-  CK(cudaFuncSetAttribute(k_reduce<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
-  CK(cudaFuncSetAttribute(k_reduce<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
-  CK(cudaFuncSetAttribute(k_reduce<28>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_red));
-  CK(cudaFuncSetAttribute(k_eig_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_chan));
-  CK(cudaFuncSetAttribute(k_eig_final, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_chan));
-  CK(cudaFuncSetAttribute(k_poisson, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_poisson));
-  CK(cudaFuncSetAttribute(k_dens_cells<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
-  CK(cudaFuncSetAttribute(k_dens_cells<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
-  CK(cudaFuncSetAttribute(k_dens_cells<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
-  CK(cudaFuncSetAttribute(k_cells_from_dense<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
-  CK(cudaFuncSetAttribute(k_cells_from_dense<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
-  CK(cudaFuncSetAttribute(k_cells_from_dense<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt->smem_dens));
+  // (the kernels' dynamic shared-memory limits were raised once per ctx: set_kernel_attributes)
   {
     const size_t need = sizeof(aks_iter_record) * B;
     for (size_t i = 0; i < ctx->pinned_free.size(); ++i)
@@ -550,25 +608,34 @@ extern "C" int aks_batch_create(aks_disc* disc, int32_t nprob, const double* Z, 
       }
     }
   }
-  *out = bt;
+  // ODA defaults for every problem
+  bt->hScftol.assign(nprob, b.scftol);
+  bt->hTinit.assign(nprob, b.tinit);
+  bt->hFrozen.assign(nprob, 0);
+  bt->hMaxiter.assign(nprob, 0);
+  CK(cudaMemcpyAsync(b.scftol_p, bt->hScftol.data(), sizeof(double) * nprob, cudaMemcpyHostToDevice, ctx->stream));
   return aks_batch_reset(bt);
 }
 
 extern "C" void aks_batch_destroy(aks_batch* bt) {
   if (!bt) return;
+  GUARD(bt->disc->ctx);
   {
     aks_ctx* cx = bt->disc->ctx;
     for (Lane& ln : bt->lanes) {
       if (ln.stream) { cudaStreamSynchronize(ln.stream); cx->stream_free.push_back(ln.stream); }
       if (ln.done) cx->event_free.push_back(ln.done);
+      if (ln.gexec) cudaGraphExecDestroy(ln.gexec);
     }
+    if (bt->whole.gexec) { cudaStreamSynchronize(cx->stream); cudaGraphExecDestroy(bt->whole.gexec); }
     if (bt->fork_ev) cx->event_free.push_back(bt->fork_ev);
   }
   cudaStream_t st = bt->disc->ctx->stream;
   for (void* p : bt->allocs) cudaFreeAsync(p, st);
   cudaStreamSynchronize(st);
   if (bt->h_rec) bt->disc->ctx->pinned_free.push_back({bt->h_rec, bt->h_rec_bytes});
-  if (bt->timers) for (auto& e : bt->ev) cudaEventDestroy(e);
+  for (auto& e : bt->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : bt->kev) if (e) cudaEventDestroy(e);
   dd_batch_free(bt);
   delete bt;
 }
@@ -577,6 +644,7 @@ extern "C" int aks_batch_set_oda(aks_batch* bt, double scftol, double tinit, int
                                  int32_t maxiter_ls, double abstol_ls, double reltol_ls, int32_t max_degen,
                                  double degen_tol, int32_t handle_degen_spin_1iter) {
   if (!bt) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
   if (!(scftol >= 0) || !(tinit >= 0 && tinit <= 1) || maxiter_ls < 1 || max_degen < 1 || !(degen_tol >= 0)) {
@@ -587,14 +655,43 @@ extern "C" int aks_batch_set_oda(aks_batch* bt, double scftol, double tinit, int
   b.scftol = scftol; b.tinit = tinit; b.frozen_t = frozen_t; b.maxiter_ls = maxiter_ls;
   b.abstol_ls = abstol_ls; b.reltol_ls = reltol_ls; b.max_degen = max_degen; b.degen_tol = degen_tol;
   b.handle_spin = handle_degen_spin_1iter;
-  std::vector<double> tv(bt->B, tinit);
-  CK(cudaMemcpyAsync(b.t, tv.data(), sizeof(double) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
+  bt->graphs_valid = false;   // the options are kernel arguments, baked into the captured step
+  // every problem back to the batch-wide algorithm (aks_batch_set_oda_problem overrides one)
+  bt->hScftol.assign(bt->B, scftol);
+  bt->hTinit.assign(bt->B, tinit);
+  bt->hFrozen.assign(bt->B, frozen_t ? 1 : 0);
+  bt->hMaxiter.assign(bt->B, 0);
+  CK(cudaMemcpyAsync(b.t, bt->hTinit.data(), sizeof(double) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.scftol_p, bt->hScftol.data(), sizeof(double) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.frozen_p, bt->hFrozen.data(), sizeof(int) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.maxiter_p, bt->hMaxiter.data(), sizeof(int) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
+extern "C" int aks_batch_set_oda_problem(aks_batch* bt, int32_t prob, double scftol, double tinit, int32_t frozen_t,
+                                         int32_t maxiter) {
+  if (!bt || prob < 0 || prob >= bt->B) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
+  DD_UNSUPPORTED(bt, "aks_batch_set_oda_problem");
+  enter_main(bt);
+  aks_ctx* ctx = bt->disc->ctx;
+  if (!(scftol >= 0) || !(tinit >= 0 && tinit <= 1) || maxiter < 0) {
+    ctx->err = "aks_batch_set_oda_problem: need scftol >= 0, 0 <= tinit <= 1, maxiter >= 0"; return AKS_EINVAL;
+  }
+  BatchDev& b = bt->dev;
+  bt->hScftol[prob] = scftol; bt->hTinit[prob] = tinit; bt->hFrozen[prob] = frozen_t ? 1 : 0; bt->hMaxiter[prob] = maxiter;
+  CK(cudaMemcpyAsync(b.t + prob, &bt->hTinit[prob], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.scftol_p + prob, &bt->hScftol[prob], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.frozen_p + prob, &bt->hFrozen[prob], sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(b.maxiter_p + prob, &bt->hMaxiter[prob], sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
 }
 
 extern "C" int aks_batch_reset(aks_batch* bt) {
   if (!bt) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   if (bt->dd) return dd_batch_reset(bt);
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -612,8 +709,9 @@ extern "C" int aks_batch_reset(aks_batch* bt) {
   CK(cudaMemsetAsync(b.status, 0, sizeof(int) * B, ctx->stream));
   CK(cudaMemsetAsync(b.warm, 0, sizeof(int) * B, ctx->stream));
   CK(cudaMemsetAsync(b.degen, 0, sizeof(int) * B, ctx->stream));
-  std::vector<double> tv(B, b.tinit);
-  CK(cudaMemcpyAsync(b.t, tv.data(), sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(b.eig_fail, 0, sizeof(int) * B, ctx->stream));
+  CK(cudaMemsetAsync(b.rec, 0, sizeof(aks_iter_record) * B, ctx->stream));
+  CK(cudaMemcpyAsync(b.t, bt->hTinit.data(), sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream));
   int rc = window_full(bt, 0, bt->B);
   if (rc != AKS_OK) return rc;
   bt->eig_dirty = false;
@@ -623,6 +721,8 @@ extern "C" int aks_batch_reset(aks_batch* bt) {
 
 extern "C" int aks_batch_set_aufbau(aks_batch* bt, int32_t kind, double temp, const double* nfix) {
   if (!bt) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
+  bt->graphs_valid = false;
   if (bt->dd) {
     if (kind < 0 || kind > 2 || (kind == 1 && !(temp > 0.0)) || (kind == 2 && !nfix)) {
       bt->disc->ctx->err = "aks_batch_set_aufbau: kind in {0,1,2}, temp > 0 for 1 (SmearedAufbau), nfix for 2 (FrozenAufbau)";
@@ -657,6 +757,8 @@ extern "C" int aks_batch_set_aufbau(aks_batch* bt, int32_t kind, double temp, co
 
 extern "C" int aks_batch_set_eig_window(aks_batch* bt, int32_t margin) {
   if (!bt) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
+  bt->graphs_valid = false;
   if (bt->dd) return dd_set_window(bt, margin);
   enter_main(bt);
   int rc = ensure_complete(bt);
@@ -678,6 +780,21 @@ extern "C" int aks_batch_set_eig_window(aks_batch* bt, int32_t margin) {
     }                                                                                         \
   } while (0)
 
+// AKS_PHASE_TIMERS: an event after every kernel of the step (name = the kernel just launched; nullptr = start)
+static void ktick(aks_batch* bt, const char* name) {
+  if (!(bt->timers && bt->cur == &bt->whole)) return;
+  if (name == nullptr) bt->kcount = 0;
+  if (bt->kcount == bt->kev.size()) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    bt->kev.push_back(e);
+    bt->knames.push_back(nullptr);
+  }
+  cudaEventRecord(bt->kev[bt->kcount], bt->cur->stream);
+  bt->knames[bt->kcount] = name;
+  bt->kcount += 1;
+}
+
 // problems [p0, p0 + np); a CTA covers one cell and potential_np() problems
 static int launch_potential_range(aks_batch* bt, double* vxc_out, double* har_out, int p0, int np, int force) {
   aks_ctx* ctx = bt->disc->ctx;
@@ -687,6 +804,7 @@ static int launch_potential_range(aks_batch* bt, double* vxc_out, double* har_ou
   if (tm) CK(cudaEventRecord(bt->ev[11], bt->cur->stream));
   k_xc<<<dim3((dv.Q + 255) / 256, dv.C, np), 256, 0, bt->cur->stream>>>(dv, bt->cur->dev, p0, np, force);
   LAUNCH_CHECK();
+  ktick(bt, "k_xc");
   if (tm) CK(cudaEventRecord(bt->ev[12], bt->cur->stream));
   const dim3 grid(dv.C, (np + NP - 1) / NP);
   if (potential_nts(dv.n) == 1)
@@ -694,6 +812,7 @@ static int launch_potential_range(aks_batch* bt, double* vxc_out, double* har_ou
   else
     k_potential<2, 2><<<grid, AKS_NT, bt->smem_pot, bt->cur->stream>>>(dv, bt->cur->dev, vxc_out, har_out, p0, np, force);
   LAUNCH_CHECK();
+  ktick(bt, "k_potential");
   if (tm) CK(cudaEventRecord(bt->ev[13], bt->cur->stream));
   return AKS_OK;
 }
@@ -705,15 +824,22 @@ static int launch_eig_pass(aks_batch* bt, int mode) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   const BatchDev& b = bt->cur->dev;
+  static const char* const nm[3][4] = {{"k_eig_init", "k_eig", "k_eig_final", "k_eig_scale"},
+                                       {"k_eig_init (refill)", "k_eig (refill)", "k_eig_final (refill)", "k_eig_scale (refill)"},
+                                       {"k_eig_init (completion)", "k_eig (completion)", "k_eig_final (completion)", "k_eig_scale (completion)"}};
   k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->cur->B), AKS_NT, bt->smem_chan, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
+  ktick(bt, nm[mode][0]);
   k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->cur->B), EIG_NT, bt->smem_eig, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
+  ktick(bt, nm[mode][1]);
   const int nchunk = (dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK;
   k_eig_final<<<dim3(nchunk, b.Lmax * b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
+  ktick(bt, nm[mode][2]);
   k_eig_scale<<<dim3(b.Lmax * b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b, dv.C, mode);
   LAUNCH_CHECK();
+  ktick(bt, nm[mode][3]);
   return AKS_OK;
 }
 static int launch_eig(aks_batch* bt) {
@@ -730,6 +856,7 @@ static int launch_eig(aks_batch* bt) {
     }
   }
   LAUNCH_CHECK();
+  ktick(bt, "k_reduce");
   return launch_eig_pass(bt, 0);
 }
 // every level current again (the reference returns all nh eigenpairs of the last Hamiltonian)
@@ -761,6 +888,7 @@ static int launch_dens_cells(aks_batch* bt) {
     default: k_dens_cells<32><<<grid, DENS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
   }
   LAUNCH_CHECK();
+  ktick(bt, "k_dens_cells");
   const dim3 g2((dv.G + AKS_NT - 1) / AKS_NT, bt->cur->B, 2);
   switch (bt->disc->nmax_tpl) {
     case 12: k_dens_grid<12><<<g2, AKS_NT, 0, bt->cur->stream>>>(dv, bt->cur->dev); break;
@@ -768,6 +896,7 @@ static int launch_dens_cells(aks_batch* bt) {
     default: k_dens_grid<32><<<g2, AKS_NT, 0, bt->cur->stream>>>(dv, bt->cur->dev); break;
   }
   LAUNCH_CHECK();
+  ktick(bt, "k_dens_grid");
   return AKS_OK;
 }
 
@@ -785,6 +914,7 @@ static int step_segment(aks_batch* bt, int seg) {
   switch (seg) {
     case 0:
       TICK(0);
+      ktick(bt, nullptr);
 #ifdef AKS_EIG_TIMING
       CK(cudaMemsetAsync(b.eig_dbg, 0, sizeof(long long) * (size_t)bt->cur->B * b.s * b.Lmax * b.nhmax * 8, bt->cur->stream));
 #endif
@@ -798,12 +928,15 @@ static int step_segment(aks_batch* bt, int seg) {
     case 2:
       k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 0);
       LAUNCH_CHECK();
+      ktick(bt, "k_aufbau");
       if (b.eig_margin >= 0) {   // problems whose window could not be certified: solve the rest, repeat
         k_eig_cert<<<dim3(b.Lmax * b.s, bt->cur->B), EIG_NT, bt->smem_eig, bt->cur->stream>>>(dv, b);
         LAUNCH_CHECK();
+        ktick(bt, "k_eig_cert");
         if ((rc = launch_eig_pass(bt, 1)) != AKS_OK) return rc;
         k_aufbau<<<bt->cur->B, 32, 0, bt->cur->stream>>>(dv, b, 1);
         LAUNCH_CHECK();
+        ktick(bt, "k_aufbau (refill)");
         bt->eig_dirty = true;
       }
       TICK(3);
@@ -815,9 +948,11 @@ static int step_segment(aks_batch* bt, int seg) {
     case 4:
       k_poisson<<<dim3(bt->cur->B, 2), 128, bt->smem_poisson, bt->cur->stream>>>(dv, b, 0, 0);
       LAUNCH_CHECK();
+      ktick(bt, "k_poisson");
       TICK(5);
       k_linesearch<<<bt->cur->B, LS_NT, 0, bt->cur->stream>>>(dv, b);
       LAUNCH_CHECK();
+      ktick(bt, "k_linesearch");
       TICK(6);
       break;
     default: {
@@ -825,12 +960,15 @@ static int step_segment(aks_batch* bt, int seg) {
       const int gx = (int)std::min<size_t>((total + 255) / 256, 1024);
       k_mix_state<<<dim3(gx, bt->cur->B), 256, 0, bt->cur->stream>>>(dv, b);
       LAUNCH_CHECK();
+      ktick(bt, "k_mix_state");
       TICK(9);
       k_mix_dense<<<dim3(b.ntri, b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b);
       LAUNCH_CHECK();
+      ktick(bt, "k_mix_dense");
       TICK(10);
       k_finalize<<<(bt->cur->B + 127) / 128, 128, 0, bt->cur->stream>>>(dv, b);
       LAUNCH_CHECK();
+      ktick(bt, "k_finalize");
       TICK(7);
     }
   }
@@ -856,7 +994,7 @@ static void refresh_lanes(aks_batch* bt) {
     ln.dev.B = ln.B;
     for (const FieldInfo& f : bt->fields) {
       char** ptr = reinterpret_cast<char**>(reinterpret_cast<char*>(&ln.dev) + f.offset);
-      *ptr += (size_t)ln.p0 * f.bytes_per_problem;
+      if (*ptr) *ptr += (size_t)ln.p0 * f.bytes_per_problem;
     }
   }
 }
@@ -864,14 +1002,54 @@ static void refresh_lanes(aks_batch* bt) {
 // the ctx stream waiting for the lanes); the next step must make the lanes wait for the ctx stream again
 static void main_side(aks_batch* bt) { bt->forked = false; bt->cur = &bt->whole; }
 
+// The step sequence of a lane (21 kernels, all with fixed grids: finished problems exit at block entry) is
+// captured ONCE per set of options into a CUDA graph and replayed: one graph launch per lane and step instead of
+// 21 kernel launches, and the kernels of a replay follow each other without the per-launch gap of the stream.
+static void drop_graphs(aks_batch* bt) {
+  for (Lane& ln : bt->lanes) if (ln.gexec) { cudaGraphExecDestroy(ln.gexec); ln.gexec = nullptr; }
+  if (bt->whole.gexec) { cudaGraphExecDestroy(bt->whole.gexec); bt->whole.gexec = nullptr; }
+}
+static int capture_lane(aks_batch* bt, Lane* ln) {
+  aks_ctx* ctx = bt->disc->ctx;
+  const int64_t l0 = ctx->launches;
+  bt->cur = ln;
+  CK(cudaStreamBeginCapture(ln->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = step_on_lane(bt);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(ln->stream, &graph);
+  ln->gkernels = (int)(ctx->launches - l0);
+  ctx->launches = l0;   // a capture launches nothing
+  if (rc != AKS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture -> ") + cudaGetErrorString(e); return AKS_ECUDA; }
+  CK(cudaGraphInstantiate(&ln->gexec, graph, 0));
+  CK(cudaGraphDestroy(graph));
+  return AKS_OK;
+}
+static int run_lane(aks_batch* bt, Lane* ln) {
+  aks_ctx* ctx = bt->disc->ctx;
+  if (!ctx->use_graphs) { bt->cur = ln; return step_on_lane(bt); }
+  if (!ln->gexec) { const int rc = capture_lane(bt, ln); if (rc != AKS_OK) return rc; }
+  CK(cudaGraphLaunch(ln->gexec, ln->stream));
+  ctx->launches += ln->gkernels;
+  if (bt->dev.eig_margin >= 0) bt->eig_dirty = true;   // what step_segment notes when it runs the window pass
+  return AKS_OK;
+}
+
 static int step_launch(aks_batch* bt) {
   aks_ctx* ctx = bt->disc->ctx;
   if (bt->dd) { refresh_lanes(bt); main_side(bt); return dd_step_launch(bt); }
   refresh_lanes(bt);
-  if (bt->lanes.size() < 2 || bt->timers) {
+  if (!bt->graphs_valid) { drop_graphs(bt); bt->graphs_valid = true; }
+  if (bt->timers) {   // per-phase events: plain launches on the ctx stream
     bt->cur = &bt->whole;
     bt->forked = false;
     return step_on_lane(bt);
+  }
+  if (bt->lanes.size() < 2) {
+    bt->forked = false;
+    const int rc = run_lane(bt, &bt->whole);
+    bt->cur = &bt->whole;
+    return rc;
   }
   if (!bt->forked) {
     CK(cudaEventRecord(bt->fork_ev, ctx->stream));
@@ -879,11 +1057,16 @@ static int step_launch(aks_batch* bt) {
     bt->forked = true;
   }
   int rc = AKS_OK;
-  for (int seg = 0; seg < STEP_SEGMENTS && rc == AKS_OK; ++seg)
-    for (Lane& ln : bt->lanes) {
-      bt->cur = &ln;
-      if ((rc = step_segment(bt, seg)) != AKS_OK) break;
-    }
+  if (ctx->use_graphs) {
+    for (Lane& ln : bt->lanes)
+      if ((rc = run_lane(bt, &ln)) != AKS_OK) break;
+  } else {
+    for (int seg = 0; seg < STEP_SEGMENTS && rc == AKS_OK; ++seg)
+      for (Lane& ln : bt->lanes) {
+        bt->cur = &ln;
+        if ((rc = step_segment(bt, seg)) != AKS_OK) break;
+      }
+  }
   if (rc == AKS_OK)
     for (Lane& ln : bt->lanes) {
       CK(cudaEventRecord(ln.done, ln.stream));
@@ -911,6 +1094,12 @@ static int fetch_records(aks_batch* bt, aks_iter_record* out) {
     bt->phase_ms[8] = msd;   // k_potential alone (part of phase 0)
     cudaEventElapsedTime(&msd, bt->ev[11], bt->ev[12]);
     bt->phase_ms[9] = msd;   // k_xc alone
+    bt->kms.assign(bt->kcount, 0.0);
+    for (size_t i = 1; i < bt->kcount; ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, bt->kev[i - 1], bt->kev[i]);
+      bt->kms[i] = ms;
+    }
   }
   if (out) memcpy(out, bt->h_rec, sizeof(aks_iter_record) * bt->B);
   return AKS_OK;
@@ -918,55 +1107,122 @@ static int fetch_records(aks_batch* bt, aks_iter_record* out) {
 
 extern "C" int aks_scf_step(aks_batch* bt, aks_iter_record* out) {
   if (!bt) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   int rc = step_launch(bt);
   if (rc != AKS_OK) return rc;
   if (!out && !bt->timers) return AKS_OK;  // enqueue only: the caller synchronises the ctx stream
   return fetch_records(bt, out);
 }
 
+// solve! (groundstate.jl:53-62).  The loop condition lives on the device: k_finalize sets the status word of a
+// problem (SUCCESS / MAXITERS of its own cap / error) and every kernel skips finished problems, so the host only
+// has to look at the status words every `check_every` steps; the per-step records the reference's LogBook wants
+// are written into a device-side history by k_finalize and copied once at the end.
 extern "C" int aks_scf_run(aks_batch* bt, int32_t maxiter, aks_iter_record* history, aks_iter_record* final_records) {
   if (!bt || maxiter < 1) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
-  std::vector<aks_iter_record> last(bt->B);
+  const size_t B = bt->B;
+  int rc;
+  const bool dev_hist = history && !bt->dd;
+  if (dev_hist) {
+    BatchDev& b = bt->dev;
+    if (bt->hist_cap_alloc < (size_t)maxiter) {
+      void* ptr = nullptr;
+      CK(cudaMallocAsync(&ptr, sizeof(aks_iter_record) * B * (size_t)maxiter, ctx->stream));
+      bt->allocs.push_back(ptr);   // an older, smaller buffer stays in the list until the batch is destroyed
+      b.hist = (aks_iter_record*)ptr;
+      bt->hist_cap_alloc = (size_t)maxiter;
+      bt->graphs_valid = false;
+    }
+    if (b.hist_cap != maxiter) { b.hist_cap = maxiter; bt->graphs_valid = false; }
+    CK(cudaMemsetAsync(b.hist, 0, sizeof(aks_iter_record) * B * (size_t)maxiter, ctx->stream));
+    CK(cudaMemcpyAsync(b.niter0, b.niter, sizeof(int) * B, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else if (!bt->dd && bt->dev.hist_cap != 0) {
+    bt->dev.hist_cap = 0;   // no history wanted: k_finalize's slot test fails for every step
+    bt->graphs_valid = false;
+  }
+  std::vector<aks_iter_record> last(B);
   // records persist on the device between steps; start from the current ones
-  int rc = fetch_records(bt, last.data());
-  if (rc != AKS_OK) return rc;
-  bool any_error = false;
-  for (int it = 0; it < maxiter; ++it) {
-    if ((rc = step_launch(bt)) != AKS_OK) return rc;
+  if ((rc = fetch_records(bt, last.data())) != AKS_OK) return rc;
+  const std::vector<aks_iter_record> first = last;
+  // a Double64 batch keeps the per-step host loop (its history is host-side)
+  const int every = (bt->dd && history) ? 1 : std::max(1, ctx->check_every);
+  for (int it = 0; it < maxiter;) {
+    const int chunk = std::min(every, maxiter - it);
+    for (int q = 0; q < chunk; ++q) {
+      if ((rc = step_launch(bt)) != AKS_OK) return rc;
+      if (bt->dd && history) {
+        if ((rc = fetch_records(bt, nullptr)) != AKS_OK) return rc;
+        for (size_t i = 0; i < B; ++i) {
+          const aks_iter_record& r = bt->h_rec[i];
+          if (r.niter != last[i].niter || r.status != last[i].status) last[i] = r;
+          history[(size_t)(it + q) * B + i] = last[i];
+        }
+      }
+    }
+    it += chunk;
     if ((rc = fetch_records(bt, nullptr)) != AKS_OK) return rc;
     bool running = false;
-    for (int i = 0; i < bt->B; ++i) {
-      // a problem that was not running this step keeps its old record
-      const aks_iter_record& r = bt->h_rec[i];
-      if (r.niter != last[i].niter || r.status != last[i].status) last[i] = r;
-      if (history) history[(size_t)it * bt->B + i] = last[i];
+    for (size_t i = 0; i < B; ++i) {
+      last[i] = bt->h_rec[i];
       if (last[i].status == AKS_RUNNING) running = true;
-      if (last[i].status < 0) any_error = true;
     }
-    if (!running) break;
+    if (!running) {
+      if (bt->dd && history)   // a problem that was not running keeps its old record
+        for (int k = it; k < maxiter; ++k) for (size_t i = 0; i < B; ++i) history[(size_t)k * B + i] = last[i];
+      break;
+    }
+  }
+  if (dev_hist) {
+    CK(cudaMemcpyAsync(history, bt->dev.hist, sizeof(aks_iter_record) * B * (size_t)maxiter, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    // slots a problem did not step in (finished earlier) repeat its last record, as the per-step host loop did
+    for (size_t i = 0; i < B; ++i) {
+      aks_iter_record cur = first[i];
+      for (int k = 0; k < maxiter; ++k) {
+        aks_iter_record& h = history[(size_t)k * B + i];
+        if (h.niter > 0) cur = h; else h = cur;
+      }
+    }
   }
   // problems still running have exhausted maxiter
-  std::vector<int> st(bt->B);
-  CK(cudaMemcpyAsync(st.data(), bt->dev.status, sizeof(int) * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  bool notconv = false;
-  for (int i = 0; i < bt->B; ++i)
-    if (st[i] == AKS_RUNNING) { st[i] = AKS_MAXITERS; last[i].status = AKS_MAXITERS; notconv = true; }
+  bool notconv = false, any_error = false;
+  std::vector<int> st(B);
+  for (size_t i = 0; i < B; ++i) {
+    st[i] = last[i].status;
+    if (st[i] == AKS_RUNNING) { st[i] = AKS_MAXITERS; last[i].status = AKS_MAXITERS; }
+    if (st[i] == AKS_MAXITERS) notconv = true;
+    if (st[i] < 0) any_error = true;
+  }
   if (notconv) {
-    CK(cudaMemcpyAsync(bt->dev.status, st.data(), sizeof(int) * bt->B, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(bt->dev.status, st.data(), sizeof(int) * B, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
-  if (final_records) memcpy(final_records, last.data(), sizeof(aks_iter_record) * bt->B);
-  if (any_error) {
-    for (int i = 0; i < bt->B; ++i) if (last[i].status < 0) return last[i].status;
-  }
+  if (final_records) memcpy(final_records, last.data(), sizeof(aks_iter_record) * B);
+  if (any_error)
+    for (size_t i = 0; i < B; ++i) if (last[i].status < 0) return last[i].status;
   return notconv ? AKS_ENOTCONV : AKS_OK;
+}
+
+extern "C" int aks_last_kernel_ms(aks_batch* bt, int32_t cap, double* ms, char* names, int32_t name_stride, int32_t* count) {
+  if (!bt || !count) return AKS_EINVAL;
+  if (!bt->timers) return AKS_EINVAL;
+  const int n = bt->kms.empty() ? 0 : (int)bt->kms.size() - 1;   // entry 0 is the start marker
+  *count = n;
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (ms) ms[i] = bt->kms[i + 1];
+    if (names && name_stride > 0) {
+      snprintf(names + (size_t)i * name_stride, (size_t)name_stride, "%s", bt->knames[i + 1] ? bt->knames[i + 1] : "?");
+    }
+  }
+  return AKS_OK;
 }
 
 extern "C" int aks_last_phase_ms(aks_batch* bt, double out[10]) {
   if (!bt || !out) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   for (int i = 0; i < 10; ++i) out[i] = bt->phase_ms[i];
   return bt->timers ? AKS_OK : AKS_EINVAL;
 }
@@ -974,6 +1230,7 @@ extern "C" int aks_last_phase_ms(aks_batch* bt, double out[10]) {
 // ------------------------------------------------------------------------------------ state I/O
 extern "C" int aks_get_state(aks_batch* bt, int32_t prob, double* D, double* U, double* eps, double* nocc, double* W) {
   if (!bt || prob < 0 || prob >= bt->B) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   if (bt->dd) return dd_get_state(bt, prob, D, U, eps, nocc, W);
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -1008,6 +1265,7 @@ extern "C" int aks_get_state(aks_batch* bt, int32_t prob, double* D, double* U, 
 // synchronisation each).  Layout per problem as in aks_get_state: eps, n (L, nh[, 2]) column-major, W (Nh).
 extern "C" int aks_get_state_all(aks_batch* bt, double* eps, double* nocc, double* W) {
   if (!bt) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   if (bt->dd) {   // pairs: eps, n [nprob][(L, nh)][2], W [nprob][Nh][2]
     const size_t per = 2 * (size_t)bt->dev.Lmax * bt->dev.nhmax, Nh2 = 2 * (size_t)bt->disc->dev.Nh;
     for (int p = 0; p < bt->B; ++p) {
@@ -1057,6 +1315,7 @@ static int launch_state_from_dense(aks_batch* bt, int prob) {
 
 extern "C" int aks_set_density(aks_batch* bt, int32_t prob, const double* D, const double* eprev, int32_t niter) {
   if (!bt || prob < 0 || prob >= bt->B || !D || niter < 0) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   DD_UNSUPPORTED(bt, "aks_set_density");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -1130,12 +1389,14 @@ static int potential_hook(aks_batch* bt, int prob, double* vxc, double* har) {
 
 extern "C" int aks_assemble_hartree(aks_batch* bt, int32_t prob, double* Har) {
   if (!bt || prob < 0 || prob >= bt->B || !Har) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   DD_UNSUPPORTED(bt, "aks_assemble_hartree");
   enter_main(bt);
   return potential_hook(bt, prob, nullptr, Har);
 }
 extern "C" int aks_assemble_vxc(aks_batch* bt, int32_t prob, double* Vxc) {
   if (!bt || prob < 0 || prob >= bt->B || !Vxc) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   DD_UNSUPPORTED(bt, "aks_assemble_vxc");
   enter_main(bt);
   return potential_hook(bt, prob, Vxc, nullptr);
@@ -1143,6 +1404,7 @@ extern "C" int aks_assemble_vxc(aks_batch* bt, int32_t prob, double* Vxc) {
 
 extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* U, double* residuals) {
   if (!bt || prob < 0 || prob >= bt->B) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   DD_UNSUPPORTED(bt, "aks_eig_lowest");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -1179,6 +1441,7 @@ extern "C" int aks_eig_lowest(aks_batch* bt, int32_t prob, double* eps, double* 
 
 extern "C" int aks_density(aks_batch* bt, int32_t prob, double* D) {
   if (!bt || prob < 0 || prob >= bt->B || !D) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   DD_UNSUPPORTED(bt, "aks_density");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -1196,6 +1459,7 @@ extern "C" int aks_density(aks_batch* bt, int32_t prob, double* D) {
 
 extern "C" int aks_exc_energy(aks_batch* bt, int32_t prob, double* Exc) {
   if (!bt || prob < 0 || prob >= bt->B || !Exc) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   DD_UNSUPPORTED(bt, "aks_exc_energy");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -1211,6 +1475,7 @@ extern "C" int aks_exc_energy(aks_batch* bt, int32_t prob, double* Exc) {
 
 extern "C" int aks_hartree_energy(aks_batch* bt, int32_t prob, double* Ehar) {
   if (!bt || prob < 0 || prob >= bt->B || !Ehar) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   DD_UNSUPPORTED(bt, "aks_hartree_energy");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -1228,6 +1493,7 @@ extern "C" int aks_hartree_energy(aks_batch* bt, int32_t prob, double* Ehar) {
 
 extern "C" int aks_debug_eig_cycles(aks_batch* bt, int64_t* out) {
   if (!bt || !out) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   DD_UNSUPPORTED(bt, "aks_debug_eig_cycles");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -1240,6 +1506,7 @@ extern "C" int aks_debug_eig_cycles(aks_batch* bt, int64_t* out) {
 
 extern "C" int aks_debug_eig_refills(aks_batch* bt, int32_t* counts) {
   if (!bt || !counts) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   if (bt->dd) return dd_eig_cold(bt, counts);   // Double64: eigenpairs of the last step that took the cold path
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -1250,6 +1517,7 @@ extern "C" int aks_debug_eig_refills(aks_batch* bt, int32_t* counts) {
 
 extern "C" int aks_debug_eig_info(aks_batch* bt, int32_t* info) {
   if (!bt || !info) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   DD_UNSUPPORTED(bt, "aks_debug_eig_info");
   enter_main(bt);
   aks_ctx* ctx = bt->disc->ctx;
@@ -1263,6 +1531,7 @@ extern "C" int aks_debug_eig_info(aks_batch* bt, int32_t* info) {
 // ------------------------------------------------------------------------------------ FP64 peak
 extern "C" int aks_measure_dmma_peak(aks_ctx* ctx, double* tflops) {
   if (!ctx || !tflops) return AKS_EINVAL;
+  GUARD(ctx);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, ctx->device));
   const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
@@ -1293,6 +1562,7 @@ extern "C" int aks_measure_dmma_peak(aks_ctx* ctx, double* tflops) {
 
 extern "C" int aks_measure_fp64_peak(aks_ctx* ctx, double* tflops) {
   if (!ctx || !tflops) return AKS_EINVAL;
+  GUARD(ctx);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, ctx->device));
   const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;

@@ -370,6 +370,7 @@ static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* e
 
 extern "C" int aks_get_records_dd(aks_batch* bt, double* out) {
   if (!bt || !out) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
   aks_ctx* ctx = bt->disc->ctx;
   if (!bt->dd) { ctx->err = "aks_get_records_dd: not a Double64 batch"; return AKS_EINVAL; }
   CK(cudaMemcpyAsync(out, bt->dd->dev.rec, sizeof(dd) * 7 * bt->B, cudaMemcpyDeviceToHost, ctx->stream));
@@ -384,6 +385,7 @@ static void dd_batch_free(aks_batch* bt) { delete bt->dd; bt->dd = nullptr; }
 extern "C" int aks_dd_xc_eval(aks_ctx* ctx, int32_t npts, const double* rho, int32_t ex_id, int32_t ec_id,
                               double* vrho, double* zk) {
   if (!ctx || npts < 1 || !rho || !vrho || !zk) return AKS_EINVAL;
+  GUARD(ctx);
   dd *dr = nullptr, *dv_ = nullptr, *dz = nullptr;
   const size_t bytes = sizeof(dd) * (size_t)npts;
   CK(cudaMallocAsync((void**)&dr, bytes, ctx->stream));

@@ -50,6 +50,17 @@ struct BatchDev {
   // ODA / aufbau options
   double scftol, tinit, abstol_ls, reltol_ls, degen_tol;
   int frozen_t, maxiter_ls, max_degen, handle_spin;
+  // per-problem ODA options (aks_batch_set_oda fills them for every problem, aks_batch_set_oda_problem for one:
+  // the reference chooses algorithm and maxiter per atom, examples/atomic density comparison/run.jl:74-76)
+  double* scftol_p;  // [B]
+  int* frozen_p;     // [B]
+  int* maxiter_p;    // [B]  cap on the problem's niter enforced on the device (status MAXITERS); 0 = none
+  int* eig_fail;     // [B]  an eigenpair of the current step could not be certified (k_eig) -> status AKS_EEIG
+  // device-side history of aks_scf_run: record of the step that took problem p from niter0[p] + k to
+  // niter0[p] + k + 1 at hist[k * hist_stride + p]
+  aks_iter_record* hist;
+  int* niter0;       // [B]
+  int hist_cap, hist_stride;
   int aufbau_kind;   // 0 OptimizedAufbau, 1 SmearedAufbau (temp), 2 FrozenAufbau (nfix)
   double temp;       // smearing width in Hartree (aufbau/smeared.jl)
   double* nfix;      // [B][s][Lmax][nhmax] prescribed occupations (aufbau/frozen.jl)

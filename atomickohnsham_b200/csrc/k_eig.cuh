@@ -1124,6 +1124,7 @@ k_eig_scale(DiscDev d, BatchDev b, int nchunk, int mode) {
       const double rq = h / m;
       const int info = b.eig_info[chan * b.nhmax + k];
       if (isfinite(rq) && !(info & 0x80)) b.eps_new[chan * b.nhmax + k] = rq;
+      else if (mode != 2) b.eig_fail[p] = 1;   // the aufbau would run on an uncertified level: k_finalize raises AKS_EEIG
       if (mode == 2) b.eps[chan * b.nhmax + k] = b.eps_new[chan * b.nhmax + k];   // no aufbau follows
       // u^T Kin_l u and u^T Coulomb u of the normalised orbital (compute_kinetic_energy /
       // compute_coulomb_energy, src/discretization/energies.jl:47-87)

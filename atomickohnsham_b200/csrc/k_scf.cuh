@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
       h01 = (bpw + n2r) / 2.0;
     }
     double ekin_m, ecou_m, ehar_m, eexc_m, etot_m;
-    if (b.frozen_t) {
+    if (b.frozen_p[p]) {
       ekin_m = t * Ekin + (1.0 - t) * Ep[1];
       ecou_m = t * Ecou + (1.0 - t) * Ep[2];
       ehar_m = (t * t) * Ehar + ((1.0 - t) * (1.0 - t)) * Ep[3] + 2.0 * t * (1.0 - t) * h01;
@@ -858,13 +858,21 @@ __global__ void k_finalize(DiscDev d, BatchDev b) {
   b.stop[p] = stop;
   b.niter[p] += 1;
   b.warm[p] = 1;
+  const int efail = b.eig_fail[p];
+  b.eig_fail[p] = 0;
   int st = 0;
   if (!(isfinite(En[0]) && isfinite(stop))) st = AKS_ENAN;
-  else if (stop < b.scftol) st = AKS_SUCCESS;
+  else if (efail) st = AKS_EEIG;   // a level of the window was not converged + certified (k_eig): never report SUCCESS on it
+  else if (stop < b.scftol_p[p]) st = AKS_SUCCESS;
+  else if (b.maxiter_p[p] > 0 && b.niter[p] >= b.maxiter_p[p]) st = AKS_MAXITERS;   // groundstate(...; maxiter)
   b.status[p] = st;
   aks_iter_record r;
   r.niter = b.niter[p]; r.status = st; r.stop = stop;
   r.Etot = En[0]; r.Ekin = En[1]; r.Ecou = En[2]; r.Ehar = En[3]; r.Eexc = En[4];
   r.t = b.t[p];
   b.rec[p] = r;
+  if (b.hist) {   // history of aks_scf_run, one slot per step of the run
+    const int slot = r.niter - b.niter0[p] - 1;
+    if (slot >= 0 && slot < b.hist_cap) b.hist[(size_t)slot * b.hist_stride + p] = r;
+  }
 }

@@ -49,6 +49,15 @@ class KSEDiscretization:
         self._ctx = None
         self._keep = None
 
+    def on_device(self, device: int) -> "KSEDiscretization":
+        """The same discretization (host tables shared, nothing recomputed) bound to another GPU: every device
+        of a partitioned sweep holds its own copy of the tables (a few MB), there is no peer access."""
+        if device == self.device:
+            return self
+        return KSEDiscretization(self.basis, None, lh=self.lh, nh=self.nh, nspin=self.nspin,
+                                 fem_integration_method=self.fem_integration_method, femops=self.femops,
+                                 device=device, dtype=self.dtype)
+
     # ---- device side -------------------------------------------------------------------
     @property
     def ctx(self) -> _capi.Context:

@@ -82,11 +82,27 @@ def solution_name(Z, N):
 class Batch:
     """A batch of models sharing one discretization, resident on the device (aks_batch)."""
 
-    def __init__(self, models, discretization: KSEDiscretization, alg: ODA, *, lh=None, nh=None, eig_margin=None):
+    def __init__(self, models, discretization: KSEDiscretization, alg, *, lh=None, nh=None, eig_margin=None,
+                 maxiter=None):
+        """`alg` is one ODA for the whole batch or a sequence with one ODA per problem (the reference chooses the
+        algorithm per atom, examples/atomic density comparison/run.jl:74); the occupation scheme and the line
+        search tolerances are those of the first.  `maxiter` (int or one per problem) caps each problem's
+        iteration count ON THE DEVICE (status MAXITERS), as `groundstate(...; maxiter)` does per call."""
         self.models = list(models)
         self.disc = discretization
-        self.alg = alg
         nprob = len(self.models)
+        self.algs = None
+        if not isinstance(alg, ODA):
+            self.algs = list(alg)
+            if len(self.algs) != nprob:
+                raise ValueError("one ODA per problem expected")
+            if discretization.dtype == "double64":
+                raise NotImplementedError("per-problem ODA options are not built for Double64 batches")
+            alg = self.algs[0]
+        self.alg = alg
+        if maxiter is not None and not np.isscalar(maxiter) and len(maxiter) != nprob:
+            raise ValueError("one maxiter per problem expected")
+        self.maxiter = maxiter
         for m in self.models:
             if m.nspin != discretization.nspin:
                 raise ValueError("all models of a batch must have the discretization's spin count")
@@ -128,7 +144,18 @@ class Batch:
             self.ctx.check(_capi.lib.aks_batch_set_aufbau(h, 2, 0.0, _capi.dptr(self._nfix)))
         if eig_margin is not None:
             self.set_eig_window(eig_margin)
+        if self.algs is not None or maxiter is not None:
+            for i in range(nprob):
+                a_i = self.algs[i] if self.algs is not None else alg
+                m_i = 0 if maxiter is None else int(maxiter if np.isscalar(maxiter) else maxiter[i])
+                self.set_oda_problem(i, a_i.scftol, a_i.tinit, a_i.frozen_t, m_i)
         self._rec = (IterRecord * nprob)()
+
+    def set_oda_problem(self, prob, scftol, tinit, frozen_t=False, maxiter=0):
+        """Algorithm of ONE problem (aks_batch_set_oda_problem): ODA(scftol, tinit, frozen_t) and the cap on its
+        iteration count, enforced on the device (0: none)."""
+        self.ctx.check(_capi.lib.aks_batch_set_oda_problem(self.h, int(prob), float(scftol), float(tinit),
+                                                           int(bool(frozen_t)), int(maxiter)))
 
     def set_eig_window(self, margin):
         """Eigenpair window (aks_batch_set_eig_window): levels solved per channel and step = occupied +
@@ -217,14 +244,19 @@ class Batch:
 
     def states(self):
         """eps, n, W of every problem in one call (aks_get_state_all): list of dicts as `state(i)` returns
-        without D and U."""
+        without D and U.  Double64 batches: every array carries a trailing (hi, lo) axis, as `state(i)` does."""
         d = self.disc
         s, Nh, L, nh = d.nspin, d.Nh, d.lh + 1, d.nh
         per = s * L * nh
-        eps = np.zeros(self.nprob * per)
-        n = np.zeros(self.nprob * per)
-        W = np.zeros(self.nprob * Nh)
+        w = 2 if d.dtype == "double64" else 1   # Double64 numbers cross the ABI as (hi, lo) pairs
+        eps = np.zeros(self.nprob * per * w)
+        n = np.zeros(self.nprob * per * w)
+        W = np.zeros(self.nprob * Nh * w)
         self.ctx.check(_capi.lib.aks_get_state_all(self.h, _capi.dptr(eps), _capi.dptr(n), _capi.dptr(W)))
+        if w == 2:
+            col = lambda a: np.stack([a[:, 0].reshape((L, nh, 1), order="F"), a[:, 1].reshape((L, nh, 1), order="F")], -1)
+            eps, n, W = eps.reshape(self.nprob, per, 2), n.reshape(self.nprob, per, 2), W.reshape(self.nprob, Nh, 2)
+            return [dict(eps=col(eps[i]), n=col(n[i]), W=W[i]) for i in range(self.nprob)]
         return [dict(eps=eps[i * per:(i + 1) * per].reshape((L, nh, s), order="F"),
                      n=n[i * per:(i + 1) * per].reshape((L, nh, s), order="F"),
                      W=W[i * Nh:(i + 1) * Nh]) for i in range(self.nprob)]
@@ -289,6 +321,18 @@ class Batch:
         out = (C.c_double * 10)()
         rc = _capi.lib.aks_last_phase_ms(self.h, out)
         return list(out) if rc == AKS_OK else None
+
+    def kernel_ms(self):
+        """[(kernel name, device ms)] of the last step, launch order (AKS_PHASE_TIMERS=1 batches only)."""
+        cap, stride = 64, 48
+        ms = (C.c_double * cap)()
+        names = C.create_string_buffer(cap * stride)
+        cnt = C.c_int32()
+        rc = _capi.lib.aks_last_kernel_ms(self.h, cap, ms, names, stride, C.byref(cnt))
+        if rc != AKS_OK:
+            return None
+        raw = names.raw
+        return [(raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(), ms[i]) for i in range(min(cnt.value, cap))]
 
     def close(self):
         if self.h:
@@ -360,13 +404,16 @@ class KSESolution:
     def occupied(self):
         """[(label, eps, n)] sorted by energy (solution/types.jl `occupied`)."""
         out = []
-        L, nh, s = self.n.shape
+        nn, ee = self.n, self.ϵ
+        if nn.ndim == 4:   # Double64 solution: trailing (hi, lo) axis; labels and sorting need the leading part only
+            nn, ee = nn[..., 0] + nn[..., 1], ee[..., 0] + ee[..., 1]
+        L, nh, s = nn.shape
         for sg in range(s):
             for l in range(L):
                 for k in range(nh):
-                    if self.n[l, k, sg] != 0:
+                    if nn[l, k, sg] != 0:
                         lab = f"{k + l + 1}{'spdfgh'[l]}" + ("" if s == 1 else "↑↓"[sg])
-                        out.append((lab, float(self.ϵ[l, k, sg]), float(self.n[l, k, sg])))
+                        out.append((lab, float(ee[l, k, sg]), float(nn[l, k, sg])))
         return sorted(out, key=lambda v: v[1])
 
 
@@ -380,13 +427,33 @@ def _solution(batch: Batch, i: int, rec: dict, logbook=None, want_arrays=True):
                        st["eps"], st["n"], st.get("U"), st.get("D"), st["W"], logbook, (m, batch.disc))
 
 
-def groundstate(model, discretization: KSEDiscretization, alg: ODA, *, maxiter: int = 100, callback=None,
-                lh=None, nh=None, want_arrays=True):
+def _run_batch(models, discretization, alg, maxiter, lh, nh, want_arrays, history=True):
+    """One device batch to convergence -> list of KSESolution (the body of the batched `groundstate`)."""
+    per_problem = not np.isscalar(maxiter)
+    batch = Batch(models, discretization, alg, lh=lh, nh=nh, maxiter=maxiter if per_problem else None)
+    final, hist = batch.run(int(max(maxiter)) if per_problem else int(maxiter), history=history)
+    sols = []
+    for i, rec in enumerate(final):
+        lb = LogBook([h["stop"] for h in hist[i]], [h["Etot"] for h in hist[i]]) if hist else None
+        sols.append(_solution(batch, i, rec, lb, want_arrays))
+    batch.close()
+    return sols
+
+
+def groundstate(model, discretization: KSEDiscretization, alg, *, maxiter=100, callback=None,
+                lh=None, nh=None, want_arrays=True, devices=None):
     """Ground state of one model (-> KSESolution) or of a list of models (-> list), on the B200.
 
     With a callback the loop runs one `aks_scf_step` per iteration so that `register!` and
     the callback fire exactly as in the reference; without one the whole loop is a single
     `aks_scf_run`.
+
+    For a list of models, `alg` and `maxiter` may be sequences with one entry per model (the reference picks
+    both per atom, examples/atomic density comparison/run.jl:74-76), and `devices = [0, 1, ...]` partitions the
+    list over several GPUs of the node: the problems are independent (the only parallel axis of the reference,
+    `Threads.@threads for z`, examples/periodic table/process.jl:92), so each device runs its share as one batch
+    from its own host thread, with its own copy of the tables and no device-to-device traffic; the solutions
+    come back in the order of `model`.
     """
     if isinstance(model, KSEModel):
         if callback is not None:
@@ -399,11 +466,41 @@ def groundstate(model, discretization: KSEDiscretization, alg: ODA, *, maxiter: 
         models, single = [model], True
     else:
         models, single = list(model), False
-    batch = Batch(models, discretization, alg, lh=lh, nh=nh)
-    final, hist = batch.run(maxiter, history=True)
-    sols = []
-    for i, rec in enumerate(final):
-        lb = LogBook([h["stop"] for h in hist[i]], [h["Etot"] for h in hist[i]])
-        sols.append(_solution(batch, i, rec, lb, want_arrays))
-    batch.close()
+    if devices is not None and len(devices) > 1 and len(models) > 1:
+        return _groundstate_multi(models, discretization, alg, maxiter, lh, nh, want_arrays, list(devices))
+    if devices is not None and len(devices) == 1:
+        discretization = discretization.on_device(int(devices[0]))
+    sols = _run_batch(models, discretization, alg, maxiter, lh, nh, want_arrays)
     return sols[0] if single else sols
+
+
+def _groundstate_multi(models, discretization, alg, maxiter, lh, nh, want_arrays, devices):
+    """Partitioned sweep: static LPT split (sweep.partition) by a per-problem cost, one host thread per GPU."""
+    import threading
+    from .sweep import partition
+    n = len(models)
+    L = [discretization.lh] * n if lh is None else list(lh)
+    K = [discretization.nh] * n if nh is None else list(nh)
+    costs = [(L[i] + 1) * K[i] + 4.0 for i in range(n)]
+    parts = [p for p in partition(costs, len(devices)) if p]
+    pick = lambda v, idx: v if (v is None or np.isscalar(v) or isinstance(v, ODA)) else [v[i] for i in idx]
+    out, errs = [None] * n, []
+
+    def work(dev, idx):
+        try:
+            disc = discretization.on_device(int(dev))
+            sols = _run_batch([models[i] for i in idx], disc, pick(alg, idx), pick(maxiter, idx), pick(lh, idx),
+                              pick(nh, idx), want_arrays)
+            for i, sol in zip(idx, sols):
+                out[i] = sol
+        except Exception as e:   # surfaced in the caller's thread
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(dev, idx)) for dev, idx in zip(devices, parts)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out

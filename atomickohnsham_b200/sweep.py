@@ -51,6 +51,43 @@ def partition(costs, world: int):
     return [sorted(p) for p in parts]
 
 
+def solve_sweep(models, discretization, *, lh=None, nh=None, alg=None, maxiter=100, remedy_alg=None,
+                remedy_maxiter=800, devices=None, want_arrays=False):
+    """A sweep of independent problems solved with the reference's own two-stage protocol
+    (`examples/atomic density comparison/run.jl:40-47,74-76`, there hard-wired to iron; here decided by the outcome):
+
+      pass 1  every problem with the reference's default algorithm `alg` (run.jl:39: ODA(tinit = 0.4,
+              scftol = 1e-10) with OptimizedAufbau(tol = 1e-2), run.jl:70), `maxiter` steps (run.jl:41: 100);
+      pass 2  every problem that ended pass 1 with MAXITERS (open d / f shells: the adaptive line search keeps
+              oscillating between two fillings of a near-degenerate block) is solved again FROM SCRATCH with the
+              algorithm the reference gives iron, `remedy_alg` = ODA(tinit = 0.15, frozen_t = true, scftol = 1e-12),
+              for up to `remedy_maxiter` steps.  As the reference notes for iron, such a run may still plateau and
+              report MAXITERS -- a defined end state: status, stop and energies are returned as they are.
+              `remedy_maxiter = 0` skips this pass.
+
+    Both passes are single device batches (`groundstate` of a list; partitioned over `devices` when given).
+    Returns a list of (KSESolution, pass_number) in the order of `models`.
+    """
+    from .algorithms import ODA, OptimizedAufbau
+    from .solver import groundstate
+    alg = alg or ODA(scftol=1e-10, tinit=0.4, aufbau=OptimizedAufbau(tol=1e-2))
+    remedy_alg = remedy_alg or ODA(scftol=1e-12, tinit=0.15, frozen_t=True, aufbau=alg.aufbau)
+    models = list(models)
+    first = groundstate(models, discretization, alg, maxiter=maxiter, lh=lh, nh=nh, want_arrays=want_arrays,
+                        devices=devices)
+    out = [(sol, 1) for sol in first]
+    todo = [i for i, sol in enumerate(first) if sol.success == "MAXITERS"] if remedy_maxiter else []
+    if todo:
+        sub = lambda v: None if v is None else [v[i] for i in todo]
+        second = groundstate([models[i] for i in todo], discretization, remedy_alg, maxiter=remedy_maxiter,
+                             lh=sub(lh), nh=sub(nh), want_arrays=want_arrays, devices=devices)
+        if not isinstance(second, list):
+            second = [second]
+        for i, sol in zip(todo, second):
+            out[i] = (sol, 2)
+    return out
+
+
 def maximum_ionization(Zs, discretization, *, nspin=1, ex="lda_x", ec="lda_c_pw", width=1.2, precision=2,
                        scftol=1e-6, maxiter=50, tinit=0.4, degen_tol=1e-2, lh=None, nh=None):
     """Largest electron number N in [Z, Z + width] each nucleus Z can bind, by bisection on N.
@@ -85,8 +122,11 @@ def maximum_ionization(Zs, discretization, *, nspin=1, ex="lda_x", ec="lda_c_pw"
         states = bt.states()
         for i, z in enumerate(Zs):
             st = states[i]
-            occ = st["n"] != 0
-            homo = float(st["eps"][occ].max())
+            nn, ee = st["n"], st["eps"]
+            if discretization.dtype == "double64":   # (hi, lo) pairs: the test below only needs the leading parts
+                nn, ee = nn[..., 0], ee[..., 0]
+            occ = nn != 0
+            homo = float(ee[occ].max())
             stable = homo <= 0.0 and final[i]["status"] == 1 and final[i]["stop"] <= scftol
             if stable:
                 lo[z] = mid[z]

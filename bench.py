@@ -7,6 +7,12 @@ Z-dependent (lh, nh) rule.  A "step" is one `scf_step!` (assembly + eigensolve +
 line search + mixing) of every atom of the batch; `scftol` is set to 0 for the timed steps so
 that every atom does every step (fixed work).  metric = atom-SCF-iterations per second.
 
+Beside `value` (K fixed steps, one 86-atom sweep per GPU: weak scaling) the line carries, as first-class keys,
+`atoms_per_s_to_convergence` / `converged` / `sweeps_to_convergence`: ONE problem list (the 86 atoms of C5 with the
+reference's two-pass protocol; ~1000 atoms x ions x functionals) partitioned over the N GPUs and solved to
+convergence (strong scaling), `sustained` (>= 300 more steps), `variants` (eigenpair window off; no CUDA graph) and
+`roofline.kernels` (every kernel of the step against the FP64 and HBM peaks).
+
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 """
 from __future__ import annotations
@@ -97,11 +103,118 @@ def build_disc(device):
     return disc
 
 
+WORKLOAD = ("C5 periodic-table sweep Z=1..86, neutral atoms, LDA (lda_x + lda_c_pw), on the C2 Argon discretization: "
+            "expmesh(0,300,41;s=1.5), ordermax=20, Nh=799, 1000 Gauss points/element, lh=min(ceil(Z/20),3), nh=clamp(Z,2,10); "
+            "a step = one scf_step! of every atom")
+# identical in both arms (the reference arm times the same 86 atoms on the host cores)
+CONFIG = {"workload": WORKLOAD, "atoms_per_step": 86, "scftol": "0 during timed steps (fixed work per step)"}
+
+
+def kernel_table(kms, stats, fp64_peak, hbm_peak):
+    """Per-kernel roofline rows.  kms: {kernel: ms} (device time, one stream, plain launches); stats: per-batch sums
+    of the ALGORITHMIC work (DESIGN.md section 5 states every formula): flops and HBM bytes per launch."""
+    rows = []
+    tot = sum(kms.values())
+    for name, ms in sorted(kms.items(), key=lambda kv: -kv[1]):
+        base = name.split(" (")[0]
+        fl, by = stats.get(base, (0.0, 0.0))
+        if "(refill)" in name or "(completion)" in name:
+            fl = by = 0.0     # data dependent (problems whose window certificate failed): time only
+        tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        gb = by / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        f64, fhb = tf / fp64_peak, gb / hbm_peak
+        bound = "fp64" if f64 >= fhb else "hbm"
+        if max(f64, fhb) < 0.05:
+            bound = "latency"
+        rows.append({"kernel": name, "ms": ms, "share_of_step": ms / tot if tot else 0.0, "algorithmic_flops": fl,
+                     "algorithmic_bytes": by, "tflops": tf, "gbs": gb, "frac_fp64_peak": f64, "frac_hbm_peak": fhb,
+                     "bound": bound})
+    return rows
+
+
+def workload_stats(lhs, nhs, states, eig_info):
+    """Algorithmic flops / HBM bytes per launch of every kernel for this batch (C2 discretization)."""
+    import numpy as np
+    n, nb, C, Q, G, Nh = 21, 19, 40, 1000, 1000, 799
+    npk = n * (n + 1) // 2
+    st = {k: [0.0, 0.0] for k in ("k_xc", "k_potential", "k_reduce", "k_eig_init", "k_eig", "k_eig_final", "k_eig_scale",
+                                  "k_aufbau", "k_eig_cert", "k_dens_cells", "k_dens_grid", "k_poisson", "k_linesearch",
+                                  "k_mix_state", "k_mix_dense", "k_finalize")}
+    counts, rqi, _ = eig_info
+    for i, (lh, nh) in enumerate(zip(lhs, nhs)):
+        L = lh + 1
+        occ = states[i]["n"][:L, :nh, 0] != 0
+        nocc = int(occ.sum())
+        nwin = nocc                                   # eigenpair window = occupied levels (margin 0)
+        st["k_xc"][0] += C * Q * 80.0;                st["k_xc"][1] += C * Q * 16.0
+        st["k_potential"][0] += C * (2.0 * n * n * Q + 2.0 * n ** 3)
+        st["k_potential"][1] += C * (8.0 * Q + L * (npk + n * n) * 8.0)
+        st["k_reduce"][0] += L * C * (10.0 / 3.0) * nb ** 3
+        st["k_reduce"][1] += L * C * (npk + 6 * nb + 4 + 2 * nb * nb) * 8.0
+        st["k_eig_init"][0] += nwin * C * 4.0 * nb * nb
+        st["k_eig_init"][1] += L * C * nb * nb * 8.0 + nwin * Nh * 16.0
+        cw = counts[i, 0, :L, :nh][occ].sum()
+        rw = rqi[i, 0, :L, :nh][occ].sum()
+        st["k_eig"][0] += (60.0 * rw + 75.0 * cw) * nb * C
+        st["k_eig"][1] += nwin * (C * (6 * nb + 4) * 8.0 + (nb * C + C) * 16.0)
+        st["k_eig_final"][0] += nwin * C * (2.0 * nb * nb + 10.0 * n * n)
+        st["k_eig_final"][1] += L * C * (nb * nb + n * n) * 8.0 + nwin * (Nh + nb * C + C) * 8.0
+        st["k_eig_scale"][1] += nwin * Nh * 16.0
+        st["k_eig_cert"][0] += L * 25.0 * nb * C
+        st["k_dens_cells"][0] += C * (Q * (2.0 * n + 3.0) * nocc + 2.0 * n * n * nocc + 2.0 * n ** 3)
+        st["k_dens_cells"][1] += C * Q * 16.0
+        st["k_dens_grid"][0] += G * (2.0 * n + 3.0) * nocc
+        st["k_dens_grid"][1] += G * 8.0 + nocc * Nh * 8.0
+        st["k_poisson"][0] += 2.0 * C * nb * nb + 8.0 * C * nb
+        st["k_poisson"][1] += 4.0 * Nh * 8.0
+        st["k_linesearch"][0] += 40.0 * G * 60.0      # ~40 evaluations of Exc on the grid (Brent), ~60 flop per point
+        st["k_linesearch"][1] += 3.0 * G * 8.0
+        st["k_mix_state"][1] += 24.0 * (C * Q + G + 2 * Nh)
+        st["k_mix_dense"][0] += 2.0 * nocc * Nh * (Nh + 1) / 2
+        st["k_mix_dense"][1] += 16.0 * Nh * (Nh + 1) / 2
+    return {k: tuple(v) for k, v in st.items()}
+
+
+def sweep_lists():
+    """(i) the C5 list: 86 neutral LDA atoms; (ii) ~1000 independent problems: atoms x ions (charge 0..3) x functionals
+    (LDA, exchange-only, no functional)."""
+    from atomickohnsham_b200.sweep import periodic_table_models
+    c5 = periodic_table_models(range(1, 87))
+    big = ([], [], [])
+    for ex, ec in (("lda_x", "lda_c_pw"), ("lda_x", None), (None, None)):
+        for charge in (0, 1, 2, 3):
+            m, l, k = periodic_table_models(range(1, 87), ex=ex, ec=ec, charge=charge)
+            big[0].extend(m); big[1].extend(l); big[2].extend(k)
+    return c5, big
+
+
+def partitioned_sweep(models, lhs, nhs, disc, rank, world, local, two_pass, barrier):
+    """ONE problem list split over the ranks (static LPT partition by cost, sweep.partition), each rank solving its
+    share to convergence as device batches (sweep.solve_sweep), no data-path collective; timed on every rank from a
+    common barrier to the end of its own share (records and eps, n on the host).  Returns this rank's
+    (seconds, [(index, success, niter, pass)])."""
+    import torch
+    from atomickohnsham_b200.sweep import partition, solve_sweep
+    costs = [(lhs[i] + 1) * nhs[i] + 4.0 for i in range(len(models))]
+    mine = partition(costs, world)[rank]
+    barrier()
+    t0 = time.perf_counter()
+    out = []
+    if mine:
+        sols = solve_sweep([models[i] for i in mine], disc, lh=[lhs[i] for i in mine], nh=[nhs[i] for i in mine],
+                           remedy_maxiter=800 if two_pass else 0, want_arrays=False)
+        out = [(i, s_.success, s_.niter, p_) for i, (s_, p_) in zip(mine, sols)]
+    torch.cuda.synchronize(local)
+    return time.perf_counter() - t0, out
+
+
 def b200_arm(args):
+    import numpy as np
     import torch
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -121,14 +234,33 @@ def b200_arm(args):
     B = len(models)
     alg_fixed = aks.ODA(scftol=0.0, tinit=0.6, aufbau=aks.OptimizedAufbau(tol=1e-3))
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    dev = f"cuda:{local}"
 
     def barrier():
         if world > 1:
-            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize(local)
 
-    # ---------------- device-resident throughput (`value`)
+    def allreduce(vals, op):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+        return [float(v) for v in t]
+
+    def timed_steps(bt, nwarm, nsteps):
+        """nwarm untimed + exactly nsteps timed steps, CUDA events on the ctx stream (every step ends on it)."""
+        for _ in range(nwarm):
+            bt.step_async()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(nsteps):
+            bt.step_async()
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
+    # ---------------- device-resident throughput (`value`): weak scaling, one 86-atom sweep per GPU
     bt = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)
     sampler = ClockSampler(local)
     sampler.start()
@@ -137,57 +269,62 @@ def b200_arm(args):
     launches0 = ctx.launches
     barrier()
     sampler.mark_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        bt.step_async()
-    e1.record(stream)
-    barrier()
+    ms = timed_steps(bt, 0, args.steps)
+    launches = ctx.launches - launches0
+    # sustained region: the driver's K is short (20 steps = 30 ms); clocks are sampled over >= 300 more steps
+    long_steps = max(300, args.steps)
+    ms_long = timed_steps(bt, 0, long_steps)
     sampler.mark_end()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launches - launches0
     refills = int(bt.eig_refills().sum())
     recs = bt.step()  # sanity: energies finite
     assert all(r["status"] >= 0 for r in recs), "a problem failed"
-    units = torch.tensor([float(B * args.steps), ms], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        import torch.distributed as dist
-        tot = units.clone()
-        dist.all_reduce(tot[0:1], op=dist.ReduceOp.SUM)
-        dist.all_reduce(tot[1:2], op=dist.ReduceOp.MAX)
-        units = tot
-    total_units, max_ms = float(units[0]), float(units[1])
-    value = total_units / (max_ms * 1e-3)
+    tot_units, = allreduce([float(B * args.steps)], "SUM")
+    max_ms, max_ms_long = allreduce([ms, ms_long], "MAX")
+    value = tot_units / (max_ms * 1e-3)
     per_rank_ms = [ms]
     if world > 1:   # load imbalance between the ranks' sweeps
-        import torch.distributed as dist
-        allms = [torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
-        dist.all_gather(allms, torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}"))
+        allms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([ms], dtype=torch.float64, device=dev))
         per_rank_ms = [float(x) for x in allms]
+    bt.close()
 
-    # ---------------- per-phase device time + roofline of the dominant kernel (rank 0)
+    # the same steps with the eigenpair window off (every step solves all nh pairs of every channel, as the
+    # reference does) and with plain stream launches instead of the graph replay: reported beside `value`
+    variants = {}
+    if rank == 0:
+        btm = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=-1)
+        msm = timed_steps_local(btm, args.warmup, args.steps, stream, local)
+        btm.close()
+        variants["eig_window_off_margin_-1"] = {"ms_per_step": msm / args.steps, "value": B * args.steps / (msm * 1e-3)}
+        ctx.configure(use_graphs=False)
+        btn = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)
+        msn = timed_steps_local(btn, args.warmup, args.steps, stream, local)
+        btn.close()
+        ctx.configure(use_graphs=True)
+        variants["plain_stream_launches_no_graph"] = {"ms_per_step": msn / args.steps, "value": B * args.steps / (msn * 1e-3)}
+
+    # ---------------- per-phase and per-kernel device time + roofline of every kernel (rank 0)
     roof, phases = None, None
     if rank == 0:
         os.environ["AKS_PHASE_TIMERS"] = "1"
         bt2 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)
         del os.environ["AKS_PHASE_TIMERS"]
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(args.warmup, 8)):      # past the shell reordering of the cold start (refills)
             bt2.step()
         acc = [0.0] * 7
-        mixd = potk = xck = 0.0
-        nrep = 5
+        kacc = {}
+        nrep = 8
         for _ in range(nrep):
             bt2.step()
             ph = bt2.phase_ms()
             acc = [a + b for a, b in zip(acc, ph[:7])]
-            mixd += ph[7]
-            potk += ph[8]
-            xck += ph[9]
-        names = ["potential", "eigensolve", "aufbau+orbital_energies", "density", "poisson", "linesearch", "mix+stop"]
+            for name, kms_ in bt2.kernel_ms():
+                kacc[name] = kacc.get(name, 0.0) + kms_
+        names = ["potential", "eigensolve", "aufbau+certificate+refill", "density", "poisson", "linesearch", "mix+stop"]
         phases = {n: a / nrep for n, a in zip(names, acc)}
-        phases["potential: k_xc"] = xck / nrep
-        phases["potential: k_potential"] = potk / nrep
+        kms = {k: v / nrep for k, v in kacc.items()}
+        stats = workload_stats(lhs, nhs, bt2.states(), bt2.eig_info())
         bt2.close()
         peaks = {}
         try:
@@ -195,52 +332,30 @@ def b200_arm(args):
         except Exception:
             pass
         fp64_peak = ctx.fp64_peak_tflops()
-        n, Q, Cc, Nh = C2["p"] + 1, C2["npoints"], 40, 799
-        dom = max(names, key=lambda nm: phases[nm])
-        # k_potential: 2 n^2 Q flop per cell and spin (second half of W_xc) + C Q XC points
-        pot_flops = B * Cc * 2.0 * n * n * Q
-        # k_mix_dense: read D + write D, 16 B per entry of the lower triangle (D is symmetric; SURVEY 8d
-        # W_dens bytes, in-place form)
-        mix_bytes = B * 16.0 * Nh * (Nh + 1) / 2
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        roof_all = {
-            "potential": {"bound": "fp64", "achieved": pot_flops / (potk / nrep * 1e-3) / 1e12, "kernel_ms": potk / nrep,
-                          "peak": fp64_peak, "unit": "TFLOP/s"},
-            "mix+stop": {"bound": "hbm", "achieved": mix_bytes / (mixd / nrep * 1e-3) / 1e9, "kernel_ms": mixd / nrep,
-                         "peak": hbm_peak, "unit": "GB/s"},
-        }
-        # DRAM bytes per launch of the same kernels from the committed ncu --set full capture (same workload)
+        rows = kernel_table(kms, stats, fp64_peak, hbm_peak)
         traffic = {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            traffic = {"potential": tj["k_potential<1, 4>"]["dram_bytes_per_launch"] * (B / 86.0),
-                       "mix+stop": tj["k_mix_dense"]["dram_bytes_per_launch"] * (B / 86.0)}
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
         except Exception:
             pass
-        for k, v in roof_all.items():
-            v["frac"] = v["achieved"] / v["peak"]
-            v["traffic"] = traffic.get(k)
-        roof = dict(roof_all["potential"])
-        roof["kernel"] = "k_potential"
-        roof["peak_source"] = "aks_measure_fp64_peak (DFMA chains, same run); MEASURED_PEAKS.json has no FP64 figure"
-        roof["dominant_phase"] = dom
-        roof["algorithmic_per_launch"] = pot_flops
-        roof["traffic_source"] = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch)"
-        # the largest PHASE is the eigensolve; SURVEY 8(d) counts it as the banded two-stage reduction
-        # W_eig = L s 12 Nh^2 b flop per atom (b = 39; the reference's dense route is L s (16/3) Nh^3).  The
-        # per-cell reduction + certified RQI used here does ~1000x fewer flops and is latency bound, so the
-        # "equivalent" rate below can exceed the FP64 peak: it measures the algorithmic saving, not the pipe.
-        nchan = sum(l + 1 for l in lhs)
-        w_eig_banded = nchan * 12.0 * Nh * Nh * 39
-        w_eig_dense = nchan * (16.0 / 3.0) * Nh ** 3
-        eig_s = phases["eigensolve"] * 1e-3
-        roof["other"] = {"k_mix_dense": roof_all["mix+stop"],
-                         "eigensolve_phase": {"ms": phases["eigensolve"], "channels": nchan,
-                                              "survey_banded_flops": w_eig_banded,
-                                              "equivalent_tflops_vs_banded_count": w_eig_banded / eig_s / 1e12,
-                                              "equivalent_tflops_vs_reference_dense_count": w_eig_dense / eig_s / 1e12,
-                                              "bound": "latency (sequential pivots); see DESIGN.md 3.2"},
-                         "hbm_peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}
+        for r in rows:
+            t = traffic.get(r["kernel"])
+            r["traffic"] = t["dram_bytes_per_launch"] * (B / 86.0) if t else None
+        top = rows[0]
+        use_f = top["bound"] == "fp64" or (top["bound"] == "latency" and top["frac_fp64_peak"] >= top["frac_hbm_peak"])
+        roof = {"kernel": top["kernel"], "bound": "tensor" if False else ("hbm" if not use_f else "fp64"),
+                "achieved": top["tflops"] if use_f else top["gbs"], "peak": fp64_peak if use_f else hbm_peak,
+                "unit": "TFLOP/s" if use_f else "GB/s", "frac": top["frac_fp64_peak"] if use_f else top["frac_hbm_peak"],
+                "traffic": top["traffic"], "kernel_ms": top["ms"], "share_of_step": top["share_of_step"],
+                "algorithmic_per_launch": top["algorithmic_flops"] if use_f else top["algorithmic_bytes"],
+                "note": "dominant kernel of the step (largest device time, one stream); `kernels` lists EVERY kernel of the "
+                        "step with its algorithmic flops and HBM bytes per launch (DESIGN.md section 5) against both peaks",
+                "peak_source": {"fp64": "aks_measure_fp64_peak (register-resident DFMA chains, same run); MEASURED_PEAKS.json "
+                                        "has no FP64 figure", "hbm": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650"},
+                "fp64_peak_tflops": fp64_peak, "hbm_peak_gbs": hbm_peak,
+                "traffic_source": "profiles/r02_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                "kernels": rows}
 
     # ---------------- end to end through the public API with host buffers (`e2e`)
     e2e_times = []
@@ -248,36 +363,45 @@ def b200_arm(args):
         barrier()
         t0 = time.perf_counter()
         bt3 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)   # H2D: model parameters
-        for _ in range(args.steps):
-            bt3.step()                                             # D2H: one record per atom, every step
+        final, hist = bt3.run(args.steps, history=True)            # D2H: every record of every step (history) + status polls
         outs = bt3.states()                                        # D2H: eps, n, W of every atom
         torch.cuda.synchronize(local)
         e2e_times.append(time.perf_counter() - t0)
+        assert all(len(h) == args.steps for h in hist)
         bt3.close()
     t_e2e = sorted(e2e_times)[1]
     assert len(outs) == B
-    h2d = B * (3 * 8 + 4 * 4)
-    d2h_total = args.steps * B * 72 + B * (3 * 4 * 10 * 8 + Nh_bytes())   # records + eps, both occupation slots, W
-    e2e_units = torch.tensor([float(B * args.steps), t_e2e], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(e2e_units[0:1], op=dist.ReduceOp.SUM)
-        dist.all_reduce(e2e_units[1:2], op=dist.ReduceOp.MAX)
-    e2e_val = float(e2e_units[0]) / float(e2e_units[1])
+    h2d = B * (3 * 8 + 4 * 4 + 8 + 8)
+    polls = -(-args.steps // 4) + 1
+    d2h_total = args.steps * B * 72 + polls * B * 72 + B * (3 * 4 * 10 * 8 + Nh_bytes())   # history + status polls + eps, n (2 slots), W
+    e2e_units, = allreduce([float(B * args.steps)], "SUM")
+    e2e_t, = allreduce([t_e2e], "MAX")
+    e2e_val = e2e_units / e2e_t
 
-    # ---------------- full sweep to convergence (atoms/s), informational
-    sweep = None
-    if rank == 0:
-        alg = aks.ODA(scftol=1e-10, tinit=0.6, aufbau=aks.OptimizedAufbau(tol=1e-3))
-        btc = Batch(models, disc, alg, lh=lhs, nh=nhs, eig_margin=args.eig_margin)
-        t0 = time.perf_counter()
-        final, _ = btc.run(100)
-        dt = time.perf_counter() - t0
-        sweep = {"atoms": B, "seconds": dt, "atoms_per_s": B / dt,
-                 "converged": sum(1 for r in final if r["status"] == 1),
-                 "iterations_total": sum(r["niter"] for r in final),
-                 "iterations_max": max(r["niter"] for r in final)}
-        btc.close()
+    # ---------------- ONE problem list partitioned over the N GPUs, to convergence (strong scaling)
+    (c5m, c5l, c5k), (bigm, bigl, bigk) = sweep_lists()
+    sweeps = {}
+    for key, (mm, ll, kk), two_pass in (("c5_86_atoms", (c5m, c5l, c5k), True), ("atoms_x_ions_x_functionals", (bigm, bigl, bigk), False)):
+        partitioned_sweep(mm[:8], ll[:8], kk[:8], disc, rank, world, local, False, barrier)   # warm-up (graph capture, pools)
+        secs, mine = partitioned_sweep(mm, ll, kk, disc, rank, world, local, two_pass, barrier)
+        tmax, = allreduce([secs], "MAX")
+        per_rank = [secs]
+        counts = [float(len(mine)), float(sum(1 for m_ in mine if m_[1] == "SUCCESS")), float(sum(m_[2] for m_ in mine)),
+                  float(sum(1 for m_ in mine if m_[3] == 2))]
+        if world > 1:
+            alls = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(alls, torch.tensor([secs], dtype=torch.float64, device=dev))
+            per_rank = [float(x) for x in alls]
+        counts = allreduce(counts, "SUM")
+        sweeps[key] = {"problems": int(counts[0]), "n_gpus": world, "seconds": tmax, "atoms_per_s": counts[0] / tmax,
+                       "converged": int(counts[1]), "ended_in_a_defined_state": int(counts[0]), "iterations_total": int(counts[2]),
+                       "second_pass_problems": int(counts[3]), "per_rank_seconds": per_rank,
+                       "load_imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / len(per_rank)),
+                       "protocol": ("the reference's (examples/atomic density comparison/run.jl:39-47,70-76): pass 1 ODA(tinit 0.4, "
+                                    "scftol 1e-10), OptimizedAufbau(tol 1e-2), maxiter 100; pass 2 for what ends at MAXITERS: "
+                                    "ODA(tinit 0.15, frozen_t, scftol 1e-12), maxiter 800") if two_pass
+                       else "ODA(tinit 0.4, scftol 1e-10), OptimizedAufbau(tol 1e-2), maxiter 100 (one pass)",
+                       "scaling": "strong (one list, LPT partition over the ranks, no data-path collective, host gather)"}
 
     # ---------------- Double64 path, informational: 20 anions on the same
     # order-20 discretization with double-double tables and kernels
@@ -290,33 +414,53 @@ def b200_arm(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_single(budget_s=15.0)
 
-    bt.close()
     if rank == 0:
+        c5 = sweeps["c5_86_atoms"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C5 periodic-table sweep Z=1..86 (one sweep per GPU; rank r: functional/charge "
-                                   "variant r) on the C2 Argon discretization: expmesh(0,300,41;s=1.5), ordermax=20, "
-                                   "Nh=799, 1000 Gauss points/element, LDA, lh=min(ceil(Z/20),3), nh=clamp(Z,2,10)",
-                       "atoms_per_gpu": B, "eig_window_margin": args.eig_margin,
-                       "eig_window_refills_in_run": refills, "scftol": "0 during timed steps (fixed work per step)",
-                       "l2": "state per GPU (dense D: %.0f MB) exceeds the 126 MB L2; no explicit flush" % (B * 8 * 799 * 799 / 1e6),
-                       "tables": "resident before the timed regions (setup is outside the reference's loop too)"},
+            "config": dict(CONFIG),
+            "run_info": {"atoms_per_gpu": B, "weak_scaling": "one 86-atom sweep per GPU; rank r runs functional/charge variant r",
+                         "eig_window_margin": args.eig_margin, "eig_window_refills_in_run": refills,
+                         "l2": "state per GPU (dense D: %.0f MB) exceeds the 126 MB L2; no explicit flush" % (B * 8 * 799 * 799 / 1e6),
+                         "tables": "resident before the timed regions (setup is outside the reference's loop too)",
+                         "launch": "each lane's step (21 kernels) replayed as one CUDA graph; gpu_launches counts the kernels"},
             "clocks": clocks, "gpu_launches": launches, "per_rank_ms_per_step": [x / args.steps for x in per_rank_ms],
+            "sustained": {"steps": long_steps, "ms_per_step": max_ms_long / long_steps,
+                          "value": tot_units / args.steps * long_steps / (max_ms_long * 1e-3),
+                          "note": "the same steps continued for >= 300 more (0.4 s): what the clock samples cover"},
+            "variants": variants,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h_total / args.steps,
-                    "what": "Batch() + K x aks_scf_step with host records + aks_get_state_all (eps, n, W of every atom); median of 3",
+                    "what": "Batch() + aks_scf_run(K steps, per-step history of every atom) + aks_get_state_all (eps, n, W of "
+                            "every atom), host buffers; the host polls the status words every 4 steps; median of 3",
                     "seconds_each": e2e_times},
+            "atoms_per_s_to_convergence": c5["atoms_per_s"], "converged": c5["converged"],
+            "sweeps_to_convergence": sweeps,
             "roofline": roof, "phases_ms": phases,
-            "phases_note": "per-phase times are measured with the batch on ONE stream (AKS_PHASE_TIMERS); the timed steps "
-                           "run the batch as 8 concurrent stream lanes, so the phases add up to more than ms_per_step", "cpu_baseline": cpu, "sweep_to_convergence": sweep,
-            "double64": dd64,
+            "phases_note": "per-phase and per-kernel times are measured with the batch on ONE stream and plain launches "
+                           "(AKS_PHASE_TIMERS); the timed steps run the batch as 8 concurrent stream lanes, so they add up "
+                           "to more than ms_per_step",
+            "cpu_baseline": cpu, "double64": dd64,
         }
         _RESULT_LINE.append(json.dumps(line))
     if world > 1:
-        import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def timed_steps_local(bt, nwarm, nsteps, stream, local):
+    import torch
+    for _ in range(nwarm):
+        bt.step_async()
+    torch.cuda.synchronize(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(nsteps):
+        bt.step_async()
+    e1.record(stream)
+    torch.cuda.synchronize(local)
+    return e0.elapsed_time(e1)
 
 
 def double64_leg(device, steps=8, warmup=4):
@@ -328,7 +472,7 @@ def double64_leg(device, steps=8, warmup=4):
     Zs = list(range(1, 21))
     basis = aks.P1IntLegendreBasis(aks.expmesh(0, 300, 41, s=1.5), ordermax=20)
     models = [aks.LDA(Z=z, N=z + 1) for z in Zs]
-    lh = [min(-(-z // 20), 3) + 1 for z in Zs]
+    lh = [min(-(-z // 20), 3) for z in Zs]   # lh (L = lh + 1 channels), SURVEY 8 C4
     nh = [min(max(z, 2), 10) for z in Zs]
     t0 = time.perf_counter()
     disc = aks.KSEDiscretization(basis, models[0], lh=max(lh), nh=max(nh), dtype="double64", device=device)
@@ -393,31 +537,42 @@ def cpu_baseline_single(budget_s=15.0):
 _W = {}
 
 
-def _worker_init(Z):
-    _W["o"] = _oracle_for(Z)
-    _W["st"] = _W["o"].initial_state()
-    _W["o"].scf_step(_W["st"])
-    return Z
+def _worker_init(Zs):
+    """One host process = several atoms of the sweep (tables are built once per process and shared)."""
+    _W["atoms"] = []
+    for Z in Zs:
+        o = _oracle_for(Z)
+        st = o.initial_state()
+        o.scf_step(st)
+        _W["atoms"].append((o, st))
+    return len(Zs)
 
 
 def _worker_step(_):
-    _W["o"].scf_step(_W["st"])
-    return 1
+    for o, st in _W["atoms"]:
+        o.scf_step(st)
+    return len(_W["atoms"])
 
 
 def reference_arm(args):
-    """The reference's CPU implementation of the path = the oracle (Julia cannot run here), one
-    atom per host core, every step = one SCF iteration of each core's atom."""
+    """The reference's CPU implementation of the path = the oracle (Julia cannot run here) on ALL host cores, on
+    the SAME workload as the B200 arm: the 86 atoms Z = 1..86 of the sweep, spread over one process per core
+    (LPT by cost); a step = one SCF iteration of every atom."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     import multiprocessing as mp
+    from atomickohnsham_b200.sweep import partition, problem_cost
     ncore = os.cpu_count() or 1
-    Zs = [18, 36, 54, 86, 10, 26, 47, 79][:ncore] if ncore <= 8 else [(7 * i) % 86 + 1 for i in range(ncore)]
+    nwork = min(ncore, 86)
+    Zall = list(range(1, 87))
+    parts = [[Zall[i] for i in p] for p in partition([problem_cost(z) for z in Zall], nwork)]
+    # single-core figure first (nothing else running): Argon alone
+    single = cpu_baseline_single(budget_s=6.0)
     ctx = mp.get_context("spawn")
-    pools = [ctx.Pool(1) for _ in Zs]
-    for p, Z in zip(pools, Zs):
-        p.apply_async(_worker_init, (Z,)).get()
+    pools = [ctx.Pool(1) for _ in parts]
+    for r in [p.apply_async(_worker_init, (zs,)) for p, zs in zip(pools, parts)]:
+        r.get()
     for _ in range(args.warmup):
         for r in [p.apply_async(_worker_step, (0,)) for p in pools]:
             r.get()
@@ -428,13 +583,16 @@ def reference_arm(args):
     dt = time.perf_counter() - t0
     for p in pools:
         p.terminate()
-    val = len(Zs) * args.steps / dt
+    val = 86 * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "same C2 discretization and LDA model; one atom per host core, Z in %s" % Zs},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": len(Zs), "kind": "port",
-                             "sample": f"{args.steps} steps x {len(Zs)} atoms, numpy/LAPACK oracle (Julia reference cannot run: no julia in the image)"},
+            "config": dict(CONFIG),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": nwork, "kind": "port",
+                             "sample": f"{args.steps} steps x 86 atoms (Z = 1..86, the B200 arm's batch) on {nwork} processes, "
+                                       "numpy/LAPACK oracle (the Julia reference cannot run: no julia in the image)",
+                             "single_core": {"value": single["value"], "unit": UNIT, "ms_per_iteration": single["ms_per_iteration"],
+                                             "sample": single["sample"]}},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _RESULT_LINE.append(json.dumps(line))
 

@@ -33,6 +33,7 @@ extern "C" {
 #define AKS_EDEGEN3 (-4)  /* >2-fold degeneracy (reference error(), optimized.jl:139)   */
 #define AKS_ENAN (-5)     /* non-finite value in a problem's energies                   */
 #define AKS_ENOSYS (-6)   /* feature not built (e.g. a functional on a Double64 batch)     */
+#define AKS_EEIG (-7)     /* an eigenpair the aufbau needs could not be converged and certified */
 
 /* per-problem status word in aks_iter_record.status */
 #define AKS_RUNNING 0
@@ -54,6 +55,12 @@ void aks_ctx_destroy(aks_ctx* ctx);
 const char* aks_last_error(const aks_ctx* ctx);
 /* the CUDA stream (cudaStream_t) all work of this ctx is launched on */
 void* aks_ctx_stream(const aks_ctx* ctx);
+/* execution options (no reference counterpart; results do not depend on them):
+ *   use_graphs   1: the kernel sequence of a step is captured once per batch and replayed as a CUDA graph
+ *                (default; environment AKS_NO_GRAPH=1 starts with 0), 0: plain stream launches, < 0: unchanged
+ *   check_every  aks_scf_run reads the problems' status words every this many steps (default 4, environment
+ *                AKS_CHECK_EVERY); < 1: unchanged                                                         */
+int aks_ctx_configure(aks_ctx* ctx, int32_t use_graphs, int32_t check_every);
 
 /* ---- discretization: replaces KSEDiscretization + init_cache! tables --------------------
  * (src/discretization/discretization.jl:270-341, src/fem/integration methods.jl:30-70,
@@ -111,6 +118,16 @@ int aks_batch_set_oda(aks_batch* batch, double scftol, double tinit, int32_t fro
                       int32_t maxiter_ls, double abstol_ls, double reltol_ls,
                       int32_t max_degen, double degen_tol, int32_t handle_degen_spin_1iter);
 
+/* The reference chooses the algorithm and the iteration cap per problem
+ * (examples/atomic density comparison/run.jl:40-47,74-76: iron gets ODA(tinit = 0.15, frozen_t = true,
+ * scftol = 1e-12) and maxiter = 800, every other atom the defaults).  Overrides scftol, tinit, frozen_t of ONE
+ * problem of the batch (aks_batch_set_oda resets every problem to its arguments) and sets the cap `maxiter` on
+ * that problem's iteration count, enforced on the device: the problem stops with status AKS_MAXITERS when its
+ * niter reaches it (0 = no per-problem cap: only the maxiter of aks_scf_run applies).  Takes effect from the
+ * problem's next step; tinit also replaces its current t.  Not built for Double64 batches (AKS_ENOSYS).       */
+int aks_batch_set_oda_problem(aks_batch* batch, int32_t prob, double scftol, double tinit, int32_t frozen_t,
+                              int32_t maxiter);
+
 /* occupation scheme (src/algorithms/aufbau/): kind 0 = OptimizedAufbau (default, options of
  * aks_batch_set_oda), 1 = SmearedAufbau(Temp = temp) (aufbau/smeared.jl:68-101), 2 = FrozenAufbau with the
  * cache's nfix (aufbau/frozen.jl:36-88): nfix[nprob][(L, nh[, 2]) column-major], L = lh+1, nh of the disc  */
@@ -144,7 +161,10 @@ int aks_scf_step(aks_batch* batch, aks_iter_record* out);
 
 /* solve!: iterate until every problem converged or reached maxiter.  history may be NULL
  * or [maxiter*nprob] (record of problem i after iteration k at history[k*nprob+i]);
- * final[nprob] receives the last record of each problem.                                  */
+ * final[nprob] receives the last record of each problem.  Convergence is decided on the device
+ * (per-problem status word); the host reads the status words every few steps (AKS_CHECK_EVERY, default 4)
+ * instead of after every step, steps enqueued for a finished problem do nothing, and the history is written
+ * on the device and copied once at the end.                                                */
 int aks_scf_run(aks_batch* batch, int32_t maxiter, aks_iter_record* history,
                 aks_iter_record* final_records);
 
@@ -208,6 +228,9 @@ int aks_measure_dmma_peak(aks_ctx* ctx, double* tflops);
  * density, poisson, linesearch, mix, k_mix_dense alone, k_potential alone, k_xc alone}; valid only if
  * AKS_PHASE_TIMERS=1 in the environment (the batch then runs on one stream instead of its lanes) */
 int aks_last_phase_ms(aks_batch* batch, double out[10]);
+/* device time of EVERY kernel of the last aks_scf_step, in launch order (same AKS_PHASE_TIMERS mode):
+ * ms[i] and the NUL-terminated name of kernel i at names + i * name_stride; *count = kernels in the step     */
+int aks_last_kernel_ms(aks_batch* batch, int32_t cap, double* ms, char* names, int32_t name_stride, int32_t* count);
 
 #ifdef __cplusplus
 }
