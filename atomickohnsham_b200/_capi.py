@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaks_b200.so")
+# AKS_B200_LIB: an instrumented build of the same library (tools/: -DAKS_EIG_TIMING cycle counters)
+LIB_PATH = os.environ.get("AKS_B200_LIB") or os.path.join(_HERE, "libaks_b200.so")
 
 AKS_OK, AKS_EINVAL, AKS_ECUDA, AKS_ENOTCONV, AKS_EDEGEN3, AKS_ENAN, AKS_ENOSYS, AKS_EEIG = 0, -1, -2, -3, -4, -5, -6, -7
 AKS_RUNNING, AKS_SUCCESS, AKS_MAXITERS = 0, 1, 2

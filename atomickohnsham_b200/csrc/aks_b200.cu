@@ -87,7 +87,7 @@ struct aks_batch {
   int B = 0;
   bool fac_in_smem = true;
   double* fac_global = nullptr;
-  size_t smem_pot = 0, smem_eig = 0, smem_red = 0, smem_chan = 0, smem_dens = 0, smem_poisson = 0;
+  size_t smem_pot = 0, smem_eig = 0, smem_eig_main = 0, smem_red = 0, smem_chan = 0, smem_dens = 0, smem_poisson = 0;
   std::vector<double> hZ, hN, hHar, hScftol, hTinit;
   std::vector<int> hLp, hnhp, hFrozen, hMaxiter;
   bool graphs_valid = false;         // lanes' graphs match bt->dev (options, pointers)
@@ -167,7 +167,13 @@ static int dd_get_state(aks_batch* bt, int prob, double* D, double* U, double* e
 static int set_kernel_attributes(aks_ctx* ctx) {
   int optin = 0;
   CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-#define SMEM_MAX(fn) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin))
+  // dynamic + static shared memory of a kernel must stay within the opt-in maximum
+#define SMEM_MAX(fn)                                                                                          \
+  do {                                                                                                        \
+    cudaFuncAttributes fa_;                                                                                   \
+    CK(cudaFuncGetAttributes(&fa_, fn));                                                                      \
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa_.sharedSizeBytes)); \
+  } while (0)
   SMEM_MAX((k_potential<1, 4>)); SMEM_MAX((k_potential<2, 2>));
   SMEM_MAX(k_eig); SMEM_MAX(k_eig_cert);
   SMEM_MAX(k_reduce<8>); SMEM_MAX(k_reduce<12>); SMEM_MAX(k_reduce<20>); SMEM_MAX(k_reduce<28>);
@@ -559,11 +565,12 @@ static int batch_create_impl(aks_batch* bt, aks_disc* disc, int32_t nprob, const
   // launch configuration
   bt->smem_pot = potential_smem_bytes(dv.n, dv.Q, b.s);
   bt->smem_eig = eig_smem_bytes(dv.C, dv.nb, dv.Nh);
+  bt->smem_eig_main = bt->smem_eig + eig_red_smem_bytes(dv.C, dv.nb);
   bt->smem_red = reduce_smem_bytes(dv.nb);
   bt->smem_chan = eig_chan_smem_bytes(dv.n, dv.nb);
   bt->smem_dens = sizeof(double) * ((size_t)AKS_MAXORB * disc->nmax_tpl + (size_t)std::max<int>(dv.n * dv.n * b.s, dv.n * dv.n) + AKS_NW + 8);
   bt->smem_poisson = sizeof(double) * ((size_t)2 * dv.Nh + 3 * dv.C + 16);
-  if (bt->smem_pot > 220 * 1024 || bt->smem_eig > 220 * 1024 || bt->smem_dens > 220 * 1024) {
+  if (bt->smem_pot > 220 * 1024 || bt->smem_eig_main > 220 * 1024 || bt->smem_dens > 220 * 1024) {
     ctx->err = "discretization too large for the shared-memory tiling of this build"; return AKS_EINVAL;
   }
   // (the kernels' dynamic shared-memory limits were raised once per ctx: set_kernel_attributes)
@@ -830,7 +837,7 @@ static int launch_eig_pass(aks_batch* bt, int mode) {
   k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->cur->B), AKS_NT, bt->smem_chan, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
   ktick(bt, nm[mode][0]);
-  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->cur->B), EIG_NT, bt->smem_eig, bt->cur->stream>>>(dv, b, mode);
+  k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->cur->B), EIG_NT, bt->smem_eig_main, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
   ktick(bt, nm[mode][1]);
   const int nchunk = (dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK;
@@ -950,7 +957,14 @@ static int step_segment(aks_batch* bt, int seg) {
       LAUNCH_CHECK();
       ktick(bt, "k_poisson");
       TICK(5);
-      k_linesearch<<<bt->cur->B, LS_NT, 0, bt->cur->stream>>>(dv, b);
+      if (dv.G > LS_NT * LS_MAXP) { ctx->err = "more than 2048 grid points: not supported by k_linesearch"; return AKS_EINVAL; }
+      if (b.s == 1) {
+        if (dv.G <= 2 * LS_NT) k_linesearch<2, 1><<<bt->cur->B, LS_NT, 0, bt->cur->stream>>>(dv, b);
+        else k_linesearch<4, 1><<<bt->cur->B, LS_NT, 0, bt->cur->stream>>>(dv, b);
+      } else {
+        if (dv.G <= 2 * LS_NT) k_linesearch<2, 2><<<bt->cur->B, LS_NT, 0, bt->cur->stream>>>(dv, b);
+        else k_linesearch<4, 2><<<bt->cur->B, LS_NT, 0, bt->cur->stream>>>(dv, b);
+      }
       LAUNCH_CHECK();
       ktick(bt, "k_linesearch");
       TICK(6);

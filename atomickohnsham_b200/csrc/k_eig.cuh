@@ -280,6 +280,17 @@ __host__ __device__ inline size_t eig_smem_bytes(int C, int nb, int Nh) {
               2 * C + 6 * 3 * C + 3 * C + AKS_NW + 8;
   return nd * sizeof(double) + (size_t)(6 * (C + 2) + 2 * C + 16) * sizeof(int);
 }
+// EIG_RED_SMEM = 1: k_eig stages the channel's reduced cell data (red_stride x C doubles, 37.8 KB at order 20) in
+// shared memory with one bulk copy.  Measured (profiles/r02_k_eig_experiments.md): a factorisation drops from 20.4 k
+// to 14.2 k cycles, but only two CTAs fit per SM instead of four and the kernel as a whole is slower (0.261 vs
+// 0.235 ms): the sweeps are bound by the latency of dependent FP64 operations, which only more resident
+// eigenpairs per SM (or shorter dependency chains) hide.  Off by default.
+#ifndef EIG_RED_SMEM
+#define EIG_RED_SMEM 0
+#endif
+__host__ __device__ inline size_t eig_red_smem_bytes(int C, int nb) {
+  return EIG_RED_SMEM ? sizeof(double) * (size_t)(6 * nb + 4) * C : 0;
+}
 
 #define EIG_NG 6   // shifts evaluated concurrently in the count-only states (groups of C threads)
 
@@ -297,8 +308,20 @@ __device__ __forceinline__ double pivot_rcp(double dval) {
 
 // ---- factor T(sigma) for up to EIG_NG shifts at once: thread t = g*C + c handles cell c of shift g.
 // store != 0 (only with ng == 1): keep the factors of shift 0 for eig_solve.  Inertia counts -> S.cntg[g].
-__device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, int ng, double sigma, int store) {
+#ifdef AKS_EIG_TIMING
+#define EIG_FT_DECL , long long* ft
+#define EIG_FT_ARG , ft_
+#define EIG_FT_MARK(i) do { if (ft) { const long long now_ = clock64(); ft[i] += now_ - ft[3]; ft[3] = now_; } } while (0)
+#else
+#define EIG_FT_DECL
+#define EIG_FT_ARG
+#define EIG_FT_MARK(i)
+#endif
+__device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, int ng, double sigma, int store EIG_FT_DECL) {
   const int g = threadIdx.x / C, c = threadIdx.x - g * C;
+#ifdef AKS_EIG_TIMING
+  if (ft) ft[3] = clock64();
+#endif
   if (g < ng) {
     const double* R = S.red;
     double* F = S.fac;
@@ -365,6 +388,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
     S.negc[g * (C + 2) + c] = neg;
   }
   __syncthreads();
+  EIG_FT_MARK(0);   // cell sweeps (+ barrier)
   // hat node j sits between cell j (its right hat, g=0) and cell j+1 (its left hat, g=1).
   // Twisted factorisation of the (C-1) tridiagonal: a sweep down from the top and a sweep up from the
   // bottom meet at the twist index tw; inertia = negatives of both sweeps + sign of the twist pivot.
@@ -465,6 +489,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
     S.cntg[g] = neg + (gam < 0.0);
   }
   __syncthreads();
+  EIG_FT_MARK(1);   // hat system (+ barriers)
 }
 
 // ---- y = T~(sigma)^{-1} r in reduced coordinates with the stored factors
@@ -549,32 +574,77 @@ __device__ __forceinline__ void eig_solve(const EigShared& S, int C, int nb) {
   __syncthreads();
 }
 
+#include "k_eig_pf.cuh"
+
+// EIG_PF = 1: product-form factorisation / no-W solve of k_eig_pf.cuh (the ratio form above stays the fallback for
+// degenerate shifts).  It shortens the dependent FP64 chain of a pivot step from 92 to 22 cycles, yet it is SLOWER
+// in the kernel (tools/micro/eig_factor_bench.cu on a B200: cell sweeps 26.9 k vs 12.0 k cycles per factorisation,
+// solve 19.1 k vs 10.9 k): with one or two active warps per scheduler the sweeps are bound by the number of
+// instructions issued (~5 cycles each, little ILP), not by the FP64 latency of the recurrence, and the product form
+// issues ~50 % more of them.  Off by default; kept as the measured experiment (profiles/r02_k_eig_experiments.md).
+#ifndef EIG_PF
+#define EIG_PF 0
+#endif
+__device__ __forceinline__ bool eig_factor_any(const EigShared& S, int C, int nb, int ng, double sigma, int store EIG_FT_DECL) {
+#if EIG_PF
+  if (eig_factor_pf(S, C, nb, ng, sigma, store
+#ifdef AKS_EIG_TIMING
+                    , ft
+#endif
+                    )) return true;
+#endif
+  eig_factor(S, C, nb, ng, sigma, store
+#ifdef AKS_EIG_TIMING
+             , ft
+#endif
+             );
+  return false;
+}
+__device__ __forceinline__ void eig_solve_any(const EigShared& S, int C, int nb, bool pf_layout) {
+  if (pf_layout) eig_solve_pf(S, C, nb);
+  else eig_solve(S, C, nb);
+}
+
 // ---- out = M~ in  (which = 0)  or  out = H~ in  (which = 1), reduced coordinates, O(nb) per cell
 __device__ __forceinline__ void eig_apply_red(const EigShared& S, int C, int nb, int which, const RedVec& in,
                                               const RedVec& out) {
   const int c = threadIdx.x;
   if (c < C) {
-    const double* R = S.red;
+    const double* R = S.red + c;
     const double xR = (c < C - 1) ? in.h[c] : 0.0, xL = (c > 0) ? in.h[c - 1] : 0.0;
-    const int o0 = which ? 2 * nb : 4 * nb, o1 = which ? 3 * nb : 5 * nb;
-    double p0 = 0.0, p1 = 0.0, xprev = 0.0, xj = in.t[c];
-#pragma unroll 4
-    for (int j = 0; j < nb; ++j) {
-      const double xnext = (j + 1 < nb) ? in.t[(j + 1) * C + c] : 0.0;
-      const double c0 = R[(o0 + j) * C + c], c1 = R[(o1 + j) * C + c];
-      double v;
-      if (which) {
-        v = R[j * C + c] * xj;
-        if (j > 0) v = fma(R[(nb + j - 1) * C + c], xprev, v);
-        if (j + 1 < nb) v = fma(R[(nb + j) * C + c], xnext, v);
-      } else v = xj;
-      out.t[j * C + c] = v + c0 * xR + c1 * xL;
-      p0 = fma(c0, xj, p0);
-      p1 = fma(c1, xj, p1);
-      xprev = xj; xj = xnext;
+    const int o0 = (which ? 2 * nb : 4 * nb) * C, o1 = (which ? 3 * nb : 5 * nb) * C, nbC = nb * C;
+    double p0 = 0.0, p1 = 0.0, xprev = 0.0, xj = in.t[c], teprev = 0.0;
+    // four steps at a time: every table value of the group is requested before the first is used (the table
+    // lives in global memory / L2, a dependent load-FMA loop would expose every one of the latencies)
+    for (int j0 = 0; j0 < nb; j0 += 4) {
+      double c0[4], c1[4], td[4], te[4], xn[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < nb) {
+          const int o = (j0 + u) * C;
+          c0[u] = R[o0 + o]; c1[u] = R[o1 + o];
+          if (which) { td[u] = R[o]; te[u] = R[nbC + o]; }
+          xn[u] = (j0 + u + 1 < nb) ? in.t[o + C + c] : 0.0;
+        }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < nb) {
+          const int j = j0 + u;
+          double v;
+          if (which) {
+            v = td[u] * xj;
+            if (j > 0) v = fma(teprev, xprev, v);
+            if (j + 1 < nb) v = fma(te[u], xn[u], v);
+            teprev = te[u];
+          } else v = xj;
+          out.t[j * C + c] = v + c0[u] * xR + c1[u] * xL;
+          p0 = fma(c0[u], xj, p0);
+          p1 = fma(c1[u], xj, p1);
+          xprev = xj; xj = xn[u];
+        }
     }
     double h00, h10, h11;
-    if (which) { h00 = R[(6 * nb) * C + c]; h10 = R[(6 * nb + 1) * C + c]; h11 = R[(6 * nb + 2) * C + c]; }
+    if (which) { h00 = R[6 * nbC]; h10 = R[6 * nbC + C]; h11 = R[6 * nbC + 2 * C]; }
     else { h00 = S.mhh[c]; h10 = S.mhh[C + c]; h11 = S.mhh[2 * C + c]; }
     S.hatpart[2 * c] = p0 + h00 * xR + h10 * xL;
     S.hatpart[2 * c + 1] = p1 + h10 * xR + h11 * xL;
@@ -657,7 +727,7 @@ enum { EST_BRACKET_LO = 0, EST_BRACKET_HI, EST_BISECT, EST_RQI, EST_CERT_LO, EST
 #ifndef EIG_NT
 #define EIG_NT 128   // threads per eigenpair CTA: the sweeps are thread-per-cell, occupancy (4 CTAs/SM) matters more
 #endif
-__global__ void __launch_bounds__(EIG_NT, (EIG_NT == 128) ? 4 : 2)
+__global__ void __launch_bounds__(EIG_NT, EIG_RED_SMEM ? 2 : ((EIG_NT == 128) ? 4 : 2))
 k_eig(DiscDev d, BatchDev b, int mode) {
   const int k = blockIdx.x, ch = blockIdx.y, p = blockIdx.z;
   if (mode != 2 && b.status[p] != 0) return;
@@ -672,10 +742,31 @@ k_eig(DiscDev d, BatchDev b, int mode) {
       }
     } else if (b.redo[p] == 0 || k < b.kdone[chan0] || (mode == 1 && k >= b.kreq[chan0])) return;
   }
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   const int C = d.C, nb = d.nb;
+#if EIG_RED_SMEM
+  // one bulk copy (TMA engine) of the channel's reduced data, overlapped with the set-up below
+  __shared__ __align__(8) uint64_t red_bar;
+  double* red_s = sm;
+  {
+    const size_t chan_ = ((size_t)p * b.s + e) * b.Lmax + l;
+    const uint32_t bytes = (uint32_t)(sizeof(double) * (size_t)red_stride(nb) * C);
+    if (threadIdx.x == 0) {
+      mbar_init(&red_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&red_bar, bytes);
+      bulk_g2s(red_s, b.red + chan_ * C * red_stride(nb), bytes, &red_bar);
+    }
+  }
+  double* sm_rest = sm + (size_t)red_stride(nb) * C;
+#else
+  double* sm_rest = sm;
+#endif
 #ifdef AKS_EIG_TIMING
   long long t_set = 0, t_fac = 0, t_sol = 0, t_app = 0, t_fin = 0, t_all = clock64(), t0_ = clock64();
+  long long ftv_[4] = {0, 0, 0, 0};
+  long long* ft_ = ftv_;
 #define TSTART() t0_ = clock64()
 #define TADD(v) v += clock64() - t0_
 #else
@@ -683,7 +774,7 @@ k_eig(DiscDev d, BatchDev b, int mode) {
 #define TADD(v)
 #endif
   EigShared S;
-  eig_carve(d, sm, S);
+  eig_carve(d, sm_rest, S);
 
   const size_t chan = ((size_t)p * b.s + e) * b.Lmax + l;
   const double* eps_ch = b.eps + chan * b.nhmax;
@@ -691,14 +782,21 @@ k_eig(DiscDev d, BatchDev b, int mode) {
   // eps / U of a level outside the last windows are older than one step: still a start, never trusted
   // (every result is certified by inertia counts)
   const bool have_prev = b.warm[p] != 0;
+#if EIG_RED_SMEM
+  S.red = red_s;
+  __syncthreads();            // red_bar initialised by thread 0 before anyone waits on it
+  mbar_wait(&red_bar, 0);     // the bulk copy has landed (visible to every thread that observed the phase)
+#else
   S.red = b.red + chan * C * red_stride(nb);
   __syncthreads();
+#endif
 
   // bracket == witnesses: lo = largest shift known with count <= k (clo), hi = smallest with
   // count >= k+1 (chi); -1 = not known yet
   double lo = -DBL_MAX, hi = DBL_MAX, step = 1.0, sigma = 0.0, rho = 0.0, prev_upd = DBL_MAX;
   int clo = -1, chi = -1;
   int state, nfac = 0, its = 0, its_cap = 12, ncount = 0;
+  int bis_left = 0, rebisect = 0;   // cold path: extra bisection rounds between inverse iterations (close pairs)
   bool from_warm = false, need_start = false, certified = false, converged = false, refined = false;
   // distance to the neighbouring levels of the previous step: RQI converges cubically, so an
   // eigenvalue update below 1e-10 of it means the current vector is already converged
@@ -718,6 +816,7 @@ k_eig(DiscDev d, BatchDev b, int mode) {
   auto cold_init = [&]() {
     from_warm = false;
     its = 0; its_cap = 12; prev_upd = DBL_MAX; converged = false;
+    bis_left = 0; rebisect = 0;
     need_start = true;
     if (clo >= 0 && chi >= 0 && lo < hi) { state = EST_BISECT; sigma = 0.5 * (lo + hi); return; }
     double blo, bhi;
@@ -823,7 +922,7 @@ k_eig(DiscDev d, BatchDev b, int mode) {
     else if (state == EST_CERT_LO) ng = min(2, ngmax);
     sg_mine = shift_of(min(gme, ng - 1));
     TSTART();
-    eig_factor(S, C, nb, ng, sg_mine, store);
+    const bool pf_layout = eig_factor_any(S, C, nb, ng, sg_mine, store EIG_FT_ARG);
     TADD(t_fac);
     nfac += 1;
     if (!store) ncount += 1;   // count-only rounds (each evaluates up to EIG_NG shifts)
@@ -861,12 +960,13 @@ k_eig(DiscDev d, BatchDev b, int mode) {
       }
       lo = nlo; hi = nhi; clo = nclo; chi = nchi;
       const double mid = 0.5 * (lo + hi);
-      if (narrow() || !(mid > lo && mid < hi)) state = EST_RQI;
+      if (bis_left > 0) { if (--bis_left == 0 || !(mid > lo && mid < hi)) { bis_left = 0; state = EST_RQI; } }
+      else if (narrow() || !(mid > lo && mid < hi)) state = EST_RQI;
       sigma = mid;
     } else if (state == EST_RQI) {
       witness(sigma, cnt);
       TSTART();
-      eig_solve(S, C, nb);                                        // y = (H~ - sigma M~)^{-1} M~ x
+      eig_solve_any(S, C, nb, pf_layout);                         // y = (H~ - sigma M~)^{-1} M~ x
       TADD(t_sol);
       TSTART();
       const double yr = eig_dot_red(S, C, nb, S.y, S.r);          // y^T M~ x
@@ -893,7 +993,14 @@ k_eig(DiscDev d, BatchDev b, int mode) {
       if (its >= its_cap) { fail(); continue; }
       if (rho > lo && rho < hi) sigma = rho;
       else if (from_warm) { fail(); continue; }
-      else sigma = 0.5 * (lo + hi);
+      else if (clo == k && chi == k + 1 && rebisect < 8) {
+        // Level k is isolated in (lo, hi) but the Rayleigh quotient left the bracket: a neighbour as close as the
+        // bracket is wide (a box state crossing a resonance, 1e-10 apart) still weighs in the iterate.  Two more
+        // bisection rounds narrow the bracket 16x (EIG_NG = 3 shifts a round), then the inverse iteration goes on
+        // FROM THE CURRENT VECTOR with the shift at the new midpoint: its contraction improves 16x per cycle.
+        state = EST_BISECT; bis_left = 2; rebisect += 1; its_cap += 3;
+        sigma = 0.5 * (lo + hi);
+      } else sigma = 0.5 * (lo + hi);
     } else if (state == EST_CERT_LO) {
       // sigma = rho - dl (shift 0); with two groups the upper certificate rho + dl rides along (shift 1)
       bool ok = true;
@@ -926,6 +1033,7 @@ k_eig(DiscDev d, BatchDev b, int mode) {
     TADD(t_fin);
     long long* dbg = b.eig_dbg + (chan * b.nhmax + k) * 8;
     dbg[0] = t_set; dbg[1] = t_fac; dbg[2] = t_sol; dbg[3] = t_app; dbg[4] = t_fin; dbg[5] = clock64() - t_all;
+    dbg[6] = ftv_[0]; dbg[7] = ftv_[1];   // split of the factorisations: cell sweeps, hat system
 #endif
   }
 }
@@ -956,7 +1064,10 @@ k_eig_cert(DiscDev d, BatchDev b) {
   S.red = b.red + chan * C * red_stride(nb);
   __syncthreads();
   const double sigma = b.e_cert[p];
-  eig_factor(S, C, nb, 1, sigma, 0);
+#ifdef AKS_EIG_TIMING
+  long long* ft_ = nullptr;
+#endif
+  eig_factor_any(S, C, nb, 1, sigma, 0 EIG_FT_ARG);
   if (threadIdx.x == 0) {
     int below = 0;
     for (int k = 0; k < kd; ++k) below += (b.eps_new[chan * b.nhmax + k] < sigma);

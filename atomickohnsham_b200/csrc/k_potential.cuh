@@ -43,36 +43,7 @@ __host__ __device__ inline size_t potential_smem_bytes(int n, int Q, int s) {
   return sizeof(double) * ((size_t)nu * Qpad + stage + 2 * (size_t)nu * n * n + (size_t)nu * n + 8);
 }
 
-// ---- mbarrier / bulk-copy primitives (PTX ISA 8.x, sm_90+): a "full" barrier per stage completes on the
-// bytes of the TMA transfers, an "empty" barrier per stage counts the warps that are done with the stage
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
+// (mbarrier / bulk-copy primitives: aks_device.cuh)
 
 // k_xc: pointwise XC potential at the Gauss nodes of every cell, f_sigma[q] = w_q v_sigma(rho(q))
 // (evaluate_vrho!, src/physics/models.jl:97-105; clamp at 0, BuiltinFunctional.jl:112).  One thread per node:

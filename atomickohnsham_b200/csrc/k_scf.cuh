@@ -530,11 +530,66 @@ __device__ double exc_grid(const DiscDev& d, const BatchDev& b, int p, double a,
   return c_xc.fourpi * block_sum(acc, red);
 }
 
+// ------------------------------------------------------------------------------------------
+// k_linesearch: energies of the trial density (compute_total_energy & co, energies.jl:7-141),
+// two-fold degeneracy resolution (optimized.jl:228-306) and the ODA line search
+// (line_search_density!, oda/loop.jl:79-116).  One CTA per problem.
+//
+// The whole Brent loop (Optim.jl's Brent(), ~30-60 SEQUENTIAL evaluations of Exc on the grid) runs inside the
+// kernel, so the time of one evaluation is what matters.  Every thread keeps the grid densities of its points
+// (trial slot 0 / slot 1 / previous, both spins) and the quadrature weights in REGISTERS for the whole kernel: an
+// evaluation is then pure arithmetic (rho(t) is linear in t) + one warp shuffle reduction + ONE pass through shared
+// memory with two barriers -- no global loads, no per-evaluation block_sum of 32 partials.
+#define LS_NT 512
+#define LS_MAXP 4   // grid points per thread held in registers: G <= LS_NT * LS_MAXP = 2048
+// MAXP points per thread (2 for G <= 1024, else 4), NS spins: compile-time so that the arrays live in registers
+template <int MAXP, int NS>
+struct LsGrid {
+  double n0u[MAXP], n1u[MAXP], pru[MAXP], wy[MAXP], y2[MAXP];
+  double n0d[NS == 2 ? MAXP : 1], n1d[NS == 2 ? MAXP : 1], prd[NS == 2 ? MAXP : 1];
+};
+struct LsShared { double t; double f; int go; };
+
+// Exc[a*new0 + bq*new1 + cq*prev] from the register-resident grid (same per-point arithmetic as exc_grid)
+template <int MAXP, int NS>
+__device__ __forceinline__ double ls_exc(const LsGrid<MAXP, NS>& g, int G, int ex, int ec, double a, double bq, double cq,
+                                         bool use1, double* red /*[LS_NT/32]*/) {
+  constexpr int s = NS;
+  double acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < MAXP; ++j) {
+    const int q = threadIdx.x + j * LS_NT;
+    if (q < G) {
+      double ru = a * g.n0u[j] + cq * g.pru[j];
+      if (use1) ru += bq * g.n1u[j];
+      double val;
+      if (s == 1) {
+        val = ru * xc_zk_unpol(fmax(ru, 0.0), ex, ec);
+      } else {
+        constexpr int jd = (NS == 2) ? 1 : 0;   // (index kept in range for the one-element arrays of NS = 1)
+        double rd = a * g.n0d[j * jd] + cq * g.prd[j * jd];
+        if (use1) rd += bq * g.n1d[j * jd];
+        val = (ru + rd) * xc_zk_pol(fmax(ru, 0.0), fmax(rd, 0.0), ex, ec);
+      }
+      acc = fma(g.wy[j], val * g.y2[j], acc);
+    }
+  }
+  acc = warp_sum(acc);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = acc;
+  __syncthreads();
+  double sum = 0.0;
+#pragma unroll
+  for (int i = 0; i < LS_NT / 32; ++i) sum += red[i];   // fixed order: every thread forms the same value
+  return c_xc.fourpi * sum;
+}
+
 // minimise a t^2 + b t + c + F(t) on [0,1] (line_search_energy, line_search.jl:45-80);
 // F(t) = Exc[t*rhoA + (1-t)*rhoB] where (A,B) = (new0,new1) [degenerate aufbau] or
 // (trial, prev) [ODA].  All threads of the CTA call this; returns (tmin, fmin) to all.
-struct LsShared { double t; double f; int go; };
-__device__ void line_search(const DiscDev& d, const BatchDev& b, int p, double qa, double qb, double qc,
+// Thread 0 drives Brent's state machine; per evaluation: ls_exc (one barrier) + publish (one barrier).
+template <int MAXP, int NS>
+__device__ void line_search(const LsGrid<MAXP, NS>& g, int G, int ex, int ec, double qa, double qb, double qc,
                             bool has_xc, int mode /*0: new0 vs new1, 1: trial(td) vs prev*/, double td,
                             bool degen, double abstol, double reltol, int maxit, LsShared* ls,
                             double* red, double& t_out, double& f_out) {
@@ -547,70 +602,100 @@ __device__ void line_search(const DiscDev& d, const BatchDev& b, int p, double q
     return;
   }
   BrentState st;
-  if (threadIdx.x == 0) { brent_init(st, 0.0, 1.0, abstol, reltol, maxit); ls->t = st.next; ls->go = 1; }
-  __syncthreads();
+  brent_init(st, 0.0, 1.0, abstol, reltol, maxit);   // every thread: the first abscissa needs no broadcast
+  double t = st.next;
   bool first = true;
   while (true) {
-    const double t = ls->t;
     double F;
-    if (mode == 0) F = exc_grid(d, b, p, t, 1.0 - t, 0.0, true, red);
-    else F = exc_grid(d, b, p, t * td, t * (1.0 - td), 1.0 - t, degen, red);
+    if (mode == 0) F = ls_exc(g, G, ex, ec, t, 1.0 - t, 0.0, true, red);
+    else F = ls_exc(g, G, ex, ec, t * td, t * (1.0 - td), 1.0 - t, degen, red);
     if (threadIdx.x == 0) {
       const double fv = qa * (t * t) + qb * t + qc + F;
       if (first) brent_first(st, fv); else brent_update(st, fv);
-      ls->go = brent_propose(st) ? 1 : 0;
-      ls->t = st.next;
-      if (!ls->go) { ls->t = st.x; ls->f = st.fx; }
+      const int go = brent_propose(st) ? 1 : 0;
+      ls->go = go;
+      ls->t = go ? st.next : st.x;
+      ls->f = st.fx;
     }
     first = false;
-    __syncthreads();
-    const int go = ls->go;
-    __syncthreads();
-    if (!go) break;
+    __syncthreads();   // publishes ls; also orders this evaluation's reads of `red` before the next writes
+    t = ls->t;
+    if (!ls->go) break;
   }
-  t_out = ls->t;
+  t_out = t;
   f_out = ls->f;
-  __syncthreads();
+  __syncthreads();     // ls is rewritten by the next search
 }
 
-// ------------------------------------------------------------------------------------------
-// k_linesearch: energies of the trial density (compute_total_energy & co, energies.jl:7-141),
-// two-fold degeneracy resolution (optimized.jl:228-306) and the ODA line search
-// (line_search_density!, oda/loop.jl:79-116).  One CTA per problem.
-#define LS_NT 1024
+template <int MAXP, int NS>
 __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
   const int p = blockIdx.x;
   if (b.status[p] != 0) return;
   __shared__ double red[LS_NT / 32 + 2];
   __shared__ LsShared ls;
   __shared__ double sh[16];
-  const int s = b.s, C = d.C, Nh = d.Nh;
-  const bool has_xc = (b.ex[p] != 0) || (b.ec[p] != 0);
+  __shared__ double s_occ[2][AKS_MAXORB], s_eps[AKS_MAXORB], s_ek[AKS_MAXORB], s_ec[AKS_MAXORB];
+  constexpr int s = NS;
+  const int C = d.C, Nh = d.Nh, G = d.G;
+  const int ex = b.ex[p], ec = b.ec[p];
+  const bool has_xc = (ex != 0) || (ec != 0);
   const bool har_on = b.hartree[p] != 0.0;
   const bool degen = b.degen[p] != 0;
   const double Np = b.N[p], Rmax = d.Rmax;
   const double n2r = Np * Np / Rmax;
   const double eps64 = 2.220446049250313e-16;
-  // orbital sums for both slots (thread 0, fixed order sigma, l, k as in energies.jl:52-61)
-  if (threadIdx.x == 0) {
-    for (int slot = 0; slot < 2; ++slot) {
-      double sne = 0.0, ek = 0.0, ecs = 0.0;
-      if (slot == 0 || degen)
-        for (int e = 0; e < s; ++e)
-          for (int l = 0; l < b.Lp[p]; ++l)
-            for (int k = 0; k < b.nhp[p]; ++k) {
-              const double nn = b.occ[occ_off(b, p, slot, e, l, k)];
-              if (nn != 0.0) {
-                sne += nn * b.eps[orb_off(b, p, e, l, k)];
-                ek += nn * b.ekin_orb[orb_off(b, p, e, l, k)];
-                ecs += nn * b.ecou_orb[orb_off(b, p, e, l, k)];
-              }
-            }
-      double corr = 0.0;
-      if (has_xc && (slot == 0 || degen))
-        for (int c = 0; c < C; ++c) corr += b.corr_part[((size_t)p * 2 + slot) * C + c];
-      sh[4 * slot + 0] = sne; sh[4 * slot + 1] = ek; sh[4 * slot + 2] = ecs; sh[4 * slot + 3] = corr;
+  const int Lp = b.Lp[p], nhp = b.nhp[p];
+  // ---- grid densities of this thread's points -> registers (read once)
+  LsGrid<MAXP, NS> g;
+  const bool in_regs = (G <= LS_NT * MAXP) && (b.s == NS);
+  if (has_xc) {
+    const double* n0 = b.rho_y_new + (((size_t)p * 2 + 0) * s) * G;
+    const double* n1 = b.rho_y_new + (((size_t)p * 2 + 1) * s) * G;
+    const double* pr = b.rho_y + ((size_t)p * s) * G;
+#pragma unroll
+    for (int j = 0; j < MAXP; ++j) {
+      const int q = threadIdx.x + j * LS_NT;
+      const bool in = q < G;
+      g.n0u[j] = in ? n0[q] : 0.0;
+      g.pru[j] = in ? pr[q] : 0.0;
+      g.n1u[j] = (in && degen) ? n1[q] : 0.0;
+      if (NS == 2) {
+        g.n0d[j * (NS - 1)] = in ? n0[G + q] : 0.0;
+        g.prd[j * (NS - 1)] = in ? pr[G + q] : 0.0;
+        g.n1d[j * (NS - 1)] = (in && degen) ? n1[G + q] : 0.0;
+      }
+      g.wy[j] = in ? d.wy[q] : 0.0;
+      const double yq = in ? d.y[q] : 0.0;
+      g.y2[j] = yq * yq;
     }
+  }
+  if (!in_regs) {   // never with the supported shapes (npoints <= 2048); keep the failure loud
+    if (threadIdx.x == 0) b.status[p] = AKS_EINVAL;
+    return;
+  }
+  // ---- orbital sums for both slots: loads by all threads, sums by thread 0 in the reference's order
+  // (sigma, l, k as in energies.jl:52-61)
+  for (int f = threadIdx.x; f < s * Lp * nhp; f += LS_NT) {
+    const int e = f / (Lp * nhp), r = f - e * Lp * nhp, l = r / nhp, k = r - l * nhp;
+    s_occ[0][f] = b.occ[occ_off(b, p, 0, e, l, k)];
+    s_occ[1][f] = degen ? b.occ[occ_off(b, p, 1, e, l, k)] : 0.0;
+    s_eps[f] = b.eps[orb_off(b, p, e, l, k)];
+    s_ek[f] = b.ekin_orb[orb_off(b, p, e, l, k)];
+    s_ec[f] = b.ecou_orb[orb_off(b, p, e, l, k)];
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int slot = threadIdx.x;
+    double sne = 0.0, ek = 0.0, ecs = 0.0;
+    if (slot == 0 || degen)
+      for (int f = 0; f < s * Lp * nhp; ++f) {
+        const double nn = s_occ[slot][f];
+        if (nn != 0.0) { sne += nn * s_eps[f]; ek += nn * s_ek[f]; ecs += nn * s_ec[f]; }
+      }
+    double corr = 0.0;
+    if (has_xc && (slot == 0 || degen))
+      for (int c = 0; c < C; ++c) corr += b.corr_part[((size_t)p * 2 + slot) * C + c];
+    sh[4 * slot + 0] = sne; sh[4 * slot + 1] = ek; sh[4 * slot + 2] = ecs; sh[4 * slot + 3] = corr;
   }
   __syncthreads();
   const double* sc0 = b.scal + ((size_t)p * 2 + 0) * 4;
@@ -628,11 +713,12 @@ __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
       double acc = 0.0;
       for (int i = threadIdx.x; i < Nh; i += blockDim.x) acc = fma(B1[i], W0[i], acc);
       h01 = (block_sum(acc, red) + n2r) / 2.0;
+      __syncthreads();
     }
     const double A0 = k0 + c0, A1 = k1 + c1;
     const double qa = h0 + h1 - 2.0 * h01, qb = (A0 - A1) + 2.0 * (h01 - h1), qc = A1 + h1;
     double emin;
-    line_search(d, b, p, qa, qb, qc, has_xc, 0, 1.0, true, 1e4 * eps64, 1e4 * eps64, 100, &ls, red, td, emin);
+    line_search(g, G, ex, ec, qa, qb, qc, has_xc, 0, 1.0, true, 1e4 * eps64, 1e4 * eps64, 100, &ls, red, td, emin);
     Etot = emin;
     Ekin = td * k0 + (1.0 - td) * k1;
     Ecou = td * c0 + (1.0 - td) * c1;
@@ -650,7 +736,8 @@ __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
     Ekin = sh[1];
     Ecou = sh[2];
     Ehar = har_on ? (sc0[0] + n2r) / 2.0 : 0.0;
-    Eexc = has_xc ? exc_grid(d, b, p, 1.0, 0.0, 0.0, false, red) : 0.0;
+    Eexc = 0.0;
+    if (has_xc) { Eexc = ls_exc(g, G, ex, ec, 1.0, 0.0, 0.0, false, red); __syncthreads(); }
     Etot = has_xc ? (sh[0] - Ehar + Eexc - sh[3]) : (sh[0] - Ehar);
   }
   // ---- ODA relaxation (niter > 0)
@@ -668,12 +755,13 @@ __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
       ekin_m = t * Ekin + (1.0 - t) * Ep[1];
       ecou_m = t * Ecou + (1.0 - t) * Ep[2];
       ehar_m = (t * t) * Ehar + ((1.0 - t) * (1.0 - t)) * Ep[3] + 2.0 * t * (1.0 - t) * h01;
-      eexc_m = has_xc ? exc_grid(d, b, p, t * td, t * (1.0 - td), 1.0 - t, degen, red) : 0.0;
+      eexc_m = 0.0;
+      if (has_xc) { eexc_m = ls_exc(g, G, ex, ec, t * td, t * (1.0 - td), 1.0 - t, degen, red); __syncthreads(); }
       etot_m = ekin_m + ecou_m + ehar_m + eexc_m;
     } else {
       const double A0 = Ekin + Ecou, A1 = Ep[1] + Ep[2];
       const double qa = Ehar + Ep[3] - 2.0 * h01, qb = (A0 - A1) + 2.0 * (h01 - Ep[3]), qc = A1 + Ep[3];
-      line_search(d, b, p, qa, qb, qc, has_xc, 1, td, degen, b.abstol_ls, b.reltol_ls, b.maxiter_ls, &ls,
+      line_search(g, G, ex, ec, qa, qb, qc, has_xc, 1, td, degen, b.abstol_ls, b.reltol_ls, b.maxiter_ls, &ls,
                   red, t, etot_m);
       ekin_m = t * Ekin + (1.0 - t) * Ep[1];
       ecou_m = t * Ecou + (1.0 - t) * Ep[2];

@@ -62,8 +62,15 @@ def solve_sweep(models, discretization, *, lh=None, nh=None, alg=None, maxiter=1
               oscillating between two fillings of a near-degenerate block) is solved again FROM SCRATCH with the
               algorithm the reference gives iron, `remedy_alg` = ODA(tinit = 0.15, frozen_t = true, scftol = 1e-12),
               for up to `remedy_maxiter` steps.  As the reference notes for iron, such a run may still plateau and
-              report MAXITERS -- a defined end state: status, stop and energies are returned as they are.
-              `remedy_maxiter = 0` skips this pass.
+              report MAXITERS (run.jl:43-47); for some open f shells the frozen step even cycles between fillings.
+              The sweep therefore keeps, per problem, the BETTER of its two end states: pass 2 if it converged or
+              stopped at a smaller stopping criterion than pass 1, else pass 1.  `remedy_maxiter = 0` skips pass 2.
+
+    A two-fold degenerate block makes the reference's algorithm minimise an energy that is flat to rounding in the
+    mixing parameters (Brent on function values: t is only determined to ~sqrt(eps)), so its stopping criterion
+    bounces in 1e-10 ... 1e-6 and whether `scftol = 1e-10` is met within `maxiter` is decided by rounding noise -- in
+    the reference too (run.jl:33-37: "stopping criterion bounces between 1e-9 and 1e-7 for hundreds of iterations").
+    Such an end state (MAXITERS with a stopping criterion below ~1e-6) has Etot converged to ~1e-14 relative.
 
     Both passes are single device batches (`groundstate` of a list; partitioned over `devices` when given).
     Returns a list of (KSESolution, pass_number) in the order of `models`.
@@ -84,7 +91,8 @@ def solve_sweep(models, discretization, *, lh=None, nh=None, alg=None, maxiter=1
         if not isinstance(second, list):
             second = [second]
         for i, sol in zip(todo, second):
-            out[i] = (sol, 2)
+            if sol.success == "SUCCESS" or sol.stopping_criteria < first[i].stopping_criteria:
+                out[i] = (sol, 2)
     return out
 
 

@@ -17,9 +17,10 @@ import math
 
 
 def brent_minimize(f, lo: float, hi: float, *, abs_tol: float, rel_tol: float,
-                   iterations: int = 100):
-    """Returns (minimizer, minimum, n_f_calls)."""
-    golden = 0.5 * (3.0 - math.sqrt(5.0))
+                   iterations: int = 100, sqrt=math.sqrt):
+    """Returns (minimizer, minimum, n_f_calls).  Works on any number type with the usual operators (the Double64
+    oracle passes mpmath numbers and `sqrt = mpmath.sqrt`: Optim forms the golden ratio in the type of the bounds)."""
+    golden = (3 - sqrt(lo * 0 + 5)) / 2
     x = lo + golden * (hi - lo)
     fx = f(x)
     calls = 1

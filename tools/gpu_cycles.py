@@ -27,4 +27,4 @@ for it in range(14):
         g = lambda j: cyc[..., j][act]
         print(f"it {it}: eig phase {bt.phase_ms()[1]:.2f} ms; counts {cnt[act].mean():.1f} its {its[act].mean():.2f}; per item cycles: setup {g(0).mean():.0f} factor {g(1).mean():.0f} "
               f"(per call {g(1).sum()/nf.sum():.0f}) solve {g(2).mean():.0f} (per call {g(2).sum()/max(its[act].sum(),1):.0f}) apply+dots {g(3).mean():.0f} (per rqi {g(3).sum()/max(its[act].sum(),1):.0f}) "
-              f"final {g(4).mean():.0f} total {g(5).mean():.0f} max {g(5).max()};  sum/296 = {g(5).sum()/296/1.9e6:.2f} ms", flush=True)
+              f"[factor split: cells {g(6).sum()/nf.sum():.0f} hats {g(7).sum()/nf.sum():.0f} per call] final {g(4).mean():.0f} total {g(5).mean():.0f} max {g(5).max()};  sum/296 = {g(5).sum()/296/1.9e6:.2f} ms", flush=True)
