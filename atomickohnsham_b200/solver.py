@@ -180,11 +180,17 @@ class Batch:
         """Enqueue one scf_step! on the ctx stream without reading anything back."""
         self.ctx.check(_capi.lib.aks_scf_step(self.h, None))
 
-    def run(self, maxiter=100, history=False):
-        """solve!: returns (final records, history or None)."""
+    def run(self, maxiter=100, history=False, raise_on_problem_error=True):
+        """solve!: returns (final records, history or None).  A problem that ends in an error (negative status:
+        AKS_EDEGEN3 = the reference's `error()` of optimized.jl:139, AKS_EEIG, AKS_ENAN) raises, unless
+        `raise_on_problem_error=False` (sweeps: the other problems of the batch are unaffected, the status is in the
+        record)."""
         hist = (IterRecord * (maxiter * self.nprob))() if history else None
         rc = _capi.lib.aks_scf_run(self.h, maxiter, hist, self._rec)
-        self.ctx.check(rc, ok=(AKS_OK, AKS_ENOTCONV))
+        ok = (AKS_OK, AKS_ENOTCONV)
+        if not raise_on_problem_error and rc in (_capi.AKS_EDEGEN3, _capi.AKS_EEIG, _capi.AKS_ENAN):
+            ok = ok + (rc,)
+        self.ctx.check(rc, ok=ok)
         final = [r.asdict() for r in self._rec]
         if not history:
             return final, None
@@ -310,12 +316,21 @@ class Batch:
         return v.value
 
     def eig_info(self):
-        """(counts, rqi_its, not_converged) arrays of shape (nprob, nspin, L, nh) for the last step."""
+        """(counts, rqi_its, not_converged) arrays of shape (nprob, nspin, L, nh) for the last step (word layout:
+        counts << 8 | 0x80 not converged / certified | 0x40 member of a cluster of near-degenerate levels | RQI its)."""
         d = self.disc
         info = np.zeros(self.nprob * d.nspin * (d.lh + 1) * d.nh, dtype=np.int32)
         self.ctx.check(_capi.lib.aks_debug_eig_info(self.h, _capi.i32ptr(info)))
         info = info.reshape(self.nprob, d.nspin, d.lh + 1, d.nh)
-        return info >> 8, info & 0x7f, (info & 0x80) != 0
+        return info >> 8, info & 0x3f, (info & 0x80) != 0
+
+    def eig_clusters(self):
+        """Boolean (nprob, nspin, L, nh): levels the last step certified as members of a cluster of near-degenerate
+        levels of one channel (info bit 0x40, k_eig)."""
+        d = self.disc
+        info = np.zeros(self.nprob * d.nspin * (d.lh + 1) * d.nh, dtype=np.int32)
+        self.ctx.check(_capi.lib.aks_debug_eig_info(self.h, _capi.i32ptr(info)))
+        return (info.reshape(self.nprob, d.nspin, d.lh + 1, d.nh) & 0x40) != 0
 
     def phase_ms(self):
         out = (C.c_double * 10)()
@@ -431,7 +446,8 @@ def _run_batch(models, discretization, alg, maxiter, lh, nh, want_arrays, histor
     """One device batch to convergence -> list of KSESolution (the body of the batched `groundstate`)."""
     per_problem = not np.isscalar(maxiter)
     batch = Batch(models, discretization, alg, lh=lh, nh=nh, maxiter=maxiter if per_problem else None)
-    final, hist = batch.run(int(max(maxiter)) if per_problem else int(maxiter), history=history)
+    final, hist = batch.run(int(max(maxiter)) if per_problem else int(maxiter), history=history,
+                            raise_on_problem_error=len(models) == 1)
     sols = []
     for i, rec in enumerate(final):
         lb = LogBook([h["stop"] for h in hist[i]], [h["Etot"] for h in hist[i]]) if hist else None

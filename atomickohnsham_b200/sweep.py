@@ -126,7 +126,7 @@ def maximum_ionization(Zs, discretization, *, nspin=1, ex="lda_x", ec="lda_c_pw"
         lhs = [min(v, discretization.lh) for v in lhs]
         nhs = [min(v, discretization.nh) for v in nhs]
         bt = Batch(models, discretization, alg, lh=lhs, nh=nhs)
-        final, _ = bt.run(maxiter)
+        final, _ = bt.run(maxiter, raise_on_problem_error=False)   # a failed trial counts as not bound
         states = bt.states()
         for i, z in enumerate(Zs):
             st = states[i]

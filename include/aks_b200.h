@@ -207,7 +207,8 @@ int aks_exc_energy(aks_batch* batch, int32_t prob, double* Exc);
 int aks_hartree_energy(aks_batch* batch, int32_t prob, double* Ehar);
 
 /* eigensolver diagnostics of the last step: info[nprob*nspin*L*nh], device order [prob][sigma][l][k];
- * each word = (inertia counts << 8) | (0x80 if RQI did not converge) | RQI iterations       */
+ * each word = (inertia counts << 8) | (0x80: not converged + certified -> the problem ends with AKS_EEIG) |
+ * (0x40: certified as a member of a cluster of levels closer than the certificate resolves) | RQI iterations  */
 int aks_debug_eig_info(aks_batch* batch, int32_t* info);
 /* counts[nprob]: steps in which the eigenpair window of a problem had to be refilled (see
  * aks_batch_set_eig_window) since the batch was created                                     */

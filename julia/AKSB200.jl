@@ -38,7 +38,12 @@ xc_id(f) = f isa AtomicKohnSham.NoFunctional ? Int32(0) :
 Drop-in for `groundstate` on one model or a vector of models sharing `disc`.  The tables are the ones
 `init_cache!` / `GaussLegendre` build on the host; every SCF iteration is one `aks_scf_step`.
 """
-function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, callback = nothing, device = 0)
+function groundstate_b200(models::Vector{<:KSEModel}, disc, algs; maxiter = 100, callback = nothing, device = 0)
+    # `algs` / `maxiter`: one ODA / Int for every model, or a vector with one entry per model (the reference picks
+    # both per atom: examples/atomic density comparison/run.jl:74-76) -> aks_batch_set_oda_problem
+    alg = algs isa AbstractVector ? first(algs) : algs
+    maxit_of(i) = maxiter isa AbstractVector ? maxiter[i] : maxiter
+    maxit_all = maxiter isa AbstractVector ? maximum(maxiter) : maxiter
     basis, q = disc.basis, disc.fem_integration_method
     init_cache!(disc, first(models))                      # A, M0, M-1, M-2, F (host, once)
     ops = disc.femops
@@ -92,11 +97,33 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, 
         GC.@preserve nfix check(ctx[], ccall((:aks_batch_set_aufbau, LIB), Cint,
             (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}), bh[], 2, 0.0, nfix))
     end
-    # solve!: one ccall per iteration so that register!/callback! fire as in groundstate.jl:55-57
-    solvers = [KSESolver(m, disc, alg; maxiter = maxiter, callback = callback) for m in models]
+    if algs isa AbstractVector || maxiter isa AbstractVector
+        for i in 1:nprob
+            ai = algs isa AbstractVector ? algs[i] : algs
+            check(ctx[], ccall((:aks_batch_set_oda_problem, LIB), Cint, (Ptr{Cvoid}, Int32, Float64, Float64, Int32, Int32),
+                bh[], i - 1, Float64(ai.scftol), Float64(ai.tinit), ai.frozen_t, maxiter isa AbstractVector ? maxit_of(i) : 0))
+        end
+    end
+    solvers = [KSESolver(m, disc, algs isa AbstractVector ? algs[i] : algs; maxiter = maxit_of(i), callback = callback)
+               for (i, m) in enumerate(models)]
     recs = Vector{IterRecord}(undef, nprob)
     recs_dd = Array{T}(undef, 7, nprob)     # Double64 runs: stop, Etot, Ekin, Ecou, Ehar, Eexc, t with all digits
-    for it in 1:maxiter
+    if callback === nothing && dtype == 0
+        # solve! in ONE ccall: convergence is decided on the device, the per-iteration records LogBook wants are
+        # written there and copied once (aks_scf_run); register! is replayed from the history
+        hist = Matrix{IterRecord}(undef, nprob, maxit_all)
+        rc = ccall((:aks_scf_run, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{IterRecord}, Ptr{IterRecord}), bh[], maxit_all, hist, recs)
+        rc in (0, -3) || check(ctx[], rc)                     # -3 = AKS_ENOTCONV: some problem ended with MAXITERS
+        for (i, s) in enumerate(solvers), it in 1:recs[i].niter
+            r = hist[i, it]; e = s.energies
+            s.stopping_criteria = r.stop
+            e.Etot, e.Ekin, e.Ecou, e.Ehar, e.Eexc = r.Etot, r.Ekin, r.Ecou, r.Ehar, r.Eexc
+            s.algcache.t = r.t
+            register!(s); s.niter += 1
+        end
+    else
+    # solve!: one ccall per iteration so that register!/callback! fire as in groundstate.jl:55-57
+    for it in 1:maxit_all
         check(ctx[], ccall((:aks_scf_step, LIB), Cint, (Ptr{Cvoid}, Ptr{IterRecord}), bh[], recs))
         dtype == 1 && check(ctx[], ccall((:aks_get_records_dd, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), bh[], fp(recs_dd)))
         running = false
@@ -116,6 +143,7 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, alg; maxiter = 100, 
             running |= r.status == 0
         end
         running || break
+    end
     end
     # copy D, U, ϵ, n, W back into the ODACache so that KSESolution(solver, name) works untouched
     sols = map(enumerate(solvers)) do (i, s)

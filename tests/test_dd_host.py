@@ -116,3 +116,29 @@ def test_xc_dd_oracle_matches_float64_oracle():
                 assert abs(float(xc_dd.zk(r, True, True)) - z_all[i]) <= tol * abs(z_all[i])
         else:
             assert xc_dd.vrho(r, True, True) == 0 and xc_dd.zk(r, True, True) == 0 and v_all[i] == 0
+
+
+def test_mpmath_step_oracle_matches_float64_oracle():
+    """oracle/scf_mp.py (checker of the Double64 path with a functional) pinned to oracle/scf.py, which is pinned to the
+    reference's goldens: two SCF steps of helium (LDA) on the same small discretization; rounded to Float64 the
+    50-digit restatement must reproduce the Float64 one (Etot 1e-12, orbital energies 1e-10, t 1e-8: the Float64 line
+    search only determines t to sqrt(eps))."""
+    import mpmath as mp
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.dd import GaussLegendreDD, build_femops_dd
+    from helpers import make_oracle
+    from oracle.scf_mp import OracleMP
+    basis = aks.P1IntLegendreBasis(aks.expmesh(0, 30, 9, s=1.5), ordermax=6)
+    o = OracleMP(basis, build_femops_dd(basis), GaussLegendreDD(basis, 64), Z=2, N=2, lh=1, nh=3)
+    of = make_oracle({"Z": 2, "N": 2, "mesh": ["exp", 0, 30, 9, 1.5], "p": 6, "npoints": 64, "lh": 1, "nh": 3,
+                      "ex": "lda_x", "ec": "lda_c_pw", "scftol": 1e-12})
+    st, sf = o.initial_state(), of.initial_state()
+    for it in range(2):
+        o.scf_step(st)
+        of.scf_step(sf)
+        assert abs(float(st["E"]["Etot"]) - sf.energies.Etot) < 1e-12 * abs(sf.energies.Etot), it
+        assert abs(float(st["t"]) - sf.t) < 1e-8
+        for l in range(2):
+            for k in range(3):
+                assert abs(float(st["eps"][l][k]) - sf.eps[l, k, 0]) < 1e-10 * max(1.0, abs(sf.eps[l, k, 0])), (it, l, k)
+                assert float(st["n"][l][k]) == sf.n[l, k, 0]

@@ -387,3 +387,118 @@ def test_double64_smeared_and_frozen_aufbau_against_float64(kind):
         assert abs((nd[..., 0, 0].sum() + nd[..., 0, 1].sum()) - models[i].N) < 1e-12
     bdd.close()
     b64.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Double64 WITH a functional (config C4 runs lda_x + lda_c_pw): step oracle in mpmath, oracle/scf_mp.py
+def _mp_case(Z, *, frozen_t, tinit="0.6"):
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.dd import GaussLegendreDD, build_femops_dd
+    from atomickohnsham_b200.solver import Batch
+    from oracle.scf_mp import OracleMP
+    mp.mp.dps = 50
+    basis = aks.P1IntLegendreBasis(aks.expmesh(0, 30, 9, s=1.5), ordermax=6)     # 8 cells, Nh = 47
+    ops, quad = build_femops_dd(basis), GaussLegendreDD(basis, 64)
+    model = aks.LDA(Z=Z, N=Z)
+    disc = aks.KSEDiscretization(basis, model, lh=1, nh=3, dtype="double64", fem_integration_method=quad, femops=ops)
+    bt = Batch([model], disc, aks.ODA(tinit=float(tinit), scftol=1e-25, frozen_t=frozen_t,
+                                      aufbau=aks.OptimizedAufbau(max_degen=2, tol=1e-3)))
+    # tinit crosses the C ABI as a Float64 (ODA(tinit = 0.6) is the Float64 number 0.6 in the reference too)
+    o = OracleMP(basis, ops, quad, Z=Z, N=Z, lh=1, nh=3, tinit=mp.mpf(float(tinit)), frozen_t=frozen_t, scftol="1e-25")
+    return bt, o
+
+
+def _gpu_step(bt):
+    bt.step()
+    rd = bt.records_dd()[0]
+    st = bt.state(0, want_D=False, want_U=False)
+    rec = {k: _mpf(rd[i]) for i, k in enumerate(NAMES)}
+    eps = [[_mpf(st["eps"][l, k, 0]) for k in range(3)] for l in range(2)]
+    n = [[_mpf(st["n"][l, k, 0]) for k in range(3)] for l in range(2)]
+    return rec, eps, n
+
+
+def _rel(a, b):
+    return abs(a - b) / max(abs(b), mp.mpf("1e-300"))
+
+
+@pytest.mark.parametrize("Z", [2, 10])
+def test_double64_with_functional_frozen_t_against_mpmath_step_oracle(Z):
+    """Closes the parity gap of row a20: the Double64 path WITH lda_x + lda_c_pw against the mpmath restatement of the
+    reference's step (oracle/scf_mp.py) on identical double-double tables.  With frozen_t the trajectory is a
+    deterministic function of the tables (no Brent on a flat minimum), so EVERY quantity of every step is pinned:
+    all energies, t, stop, all orbital energies and the occupations, to 1e-24 relative (north star: 1e-20).
+    Exercises ddk_xc, ddk_H (Vxc and Hartree blocks), ddk_eig, ddk_aufbau, ddk_rho_*, ddk_decide (Exc on the grid,
+    energy bookkeeping), ddk_mix, ddk_finish."""
+    bt, o = _mp_case(Z, frozen_t=True, tinit="0.5")
+    st = o.initial_state()
+    worst = mp.mpf(0)
+    for it in range(4):
+        o.scf_step(st)
+        rec, eps, n = _gpu_step(bt)
+        for k in ("Etot", "Ekin", "Ecou", "Ehar", "Eexc"):
+            worst = max(worst, _rel(rec[k], st["E"][k]))
+            assert _rel(rec[k], st["E"][k]) < mp.mpf("1e-24"), (it, k, mp.nstr(rec[k], 34), mp.nstr(st["E"][k], 34))
+        assert _rel(rec["stop"], st["stop"]) < mp.mpf("1e-22"), (it, mp.nstr(rec["stop"], 30), mp.nstr(st["stop"], 30))
+        assert rec["t"] == (mp.mpf("0.5") if it > 0 else rec["t"])
+        for l in range(2):
+            for k in range(3):
+                assert n[l][k] == st["n"][l][k], (it, l, k)                           # occupations: exact
+                # orbital energies: every level, occupied or not (relative to the spectrum's scale for |eps| << 1)
+                tol = mp.mpf("1e-24") * max(abs(st["eps"][l][k]), mp.mpf(1))
+                assert abs(eps[l][k] - st["eps"][l][k]) < tol, (it, l, k, mp.nstr(eps[l][k], 34), mp.nstr(st["eps"][l][k], 34))
+    print(f"[dd + LDA, frozen_t] Z={Z}: 4 steps, worst relative energy difference {mp.nstr(worst, 3)}")
+    bt.close()
+
+
+def test_double64_with_functional_oda_brent_against_mpmath_step_oracle():
+    """The same with the adaptive line search (Brent in double-double, tolerances 1e4 eps(Double64)).  Step 0 (Harris-like
+    energy of the first trial density) and the orbital energies of step 1 (eigenvalues of H[D_0] with Vxc[D_0]) do not
+    depend on any line search: 1e-24.  From step 1 on the mixing parameter is the minimiser of an energy that is flat to
+    rounding (t is determined to ~sqrt(eps) = 1e-16 by function values, in the reference's Double64 arithmetic too): Etot
+    stays pinned (stationary in t), t and everything first order in t to 1e-12.  Step 2 of neon ends on the boundary
+    t -> 1, where E(t) is NOT stationary and Brent runs into `maxiter_ls = 100` before its 1e-27 tolerance (golden
+    section steps shrink the bracket by 0.62: 0.62^100 = 1e-21), so the last t -- and with it Etot -- is a path-dependent
+    1 - O(1e-21) in ANY implementation of the reference's algorithm: Etot to the north star's 1e-20 there."""
+    bt, o = _mp_case(10, frozen_t=False)
+    st = o.initial_state()
+    for it in range(3):
+        o.scf_step(st)
+        rec, eps, n = _gpu_step(bt)
+        assert _rel(rec["Etot"], st["E"]["Etot"]) < (mp.mpf("1e-24") if it <= 1 else mp.mpf("1e-20")), \
+            (it, mp.nstr(rec["Etot"], 34), mp.nstr(st["E"]["Etot"], 34))
+        tol = mp.mpf("1e-24") if it == 0 else mp.mpf("1e-12")
+        for k in ("Ekin", "Ecou", "Ehar", "Eexc"):
+            assert _rel(rec[k], st["E"][k]) < tol, (it, k, mp.nstr(rec[k], 34), mp.nstr(st["E"][k], 34))
+        assert abs(rec["t"] - st["t"]) < (mp.mpf("1e-30") if it == 0 else mp.mpf("1e-12")), (it, mp.nstr(rec["t"], 30), mp.nstr(st["t"], 30))
+        etol = mp.mpf("1e-24") if it <= 1 else mp.mpf("1e-11")
+        for l in range(2):
+            for k in range(3):
+                assert n[l][k] == st["n"][l][k]
+                assert abs(eps[l][k] - st["eps"][l][k]) < etol * max(abs(st["eps"][l][k]), mp.mpf(1)), (it, l, k)
+    bt.close()
+
+
+def test_double64_states_all_and_occupied_labels():
+    """Batch.states() of a Double64 batch (aks_get_state_all writes (hi, lo) pairs: twice the Float64 size),
+    KSESolution.occupied and sweep.maximum_ionization on a Double64 discretization."""
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.solver import Batch, groundstate
+    from atomickohnsham_b200.sweep import maximum_ionization
+    basis = aks.P1IntLegendreBasis(aks.expmesh(0, 30, 9, s=1.5), ordermax=6)
+    models = [aks.KSEModel(Z=2, N=2), aks.KSEModel(Z=4, N=4)]
+    disc = aks.KSEDiscretization(basis, models[0], lh=1, nh=3, dtype="double64")
+    bt = Batch(models, disc, aks.ODA(tinit=0.6, scftol=1e-20))
+    for _ in range(3):
+        bt.step()
+    sts = bt.states()
+    for i in range(2):
+        one = bt.state(i, want_D=False, want_U=False)
+        assert sts[i]["eps"].shape == (2, 3, 1, 2) and sts[i]["W"].shape == (disc.Nh, 2)
+        assert np.array_equal(sts[i]["eps"], one["eps"]) and np.array_equal(sts[i]["n"], one["n"])
+        assert np.array_equal(sts[i]["W"], one["W"])
+    bt.close()
+    sol = groundstate(models[0], disc, aks.ODA(tinit=0.6, scftol=1e-20), maxiter=60)
+    assert [o[0] for o in sol.occupied] == ["1s"] and abs(sol.occupied[0][2] - 2.0) < 1e-30
+    nmax = maximum_ionization([2], disc, ex=None, ec=None, width=0.4, precision=1, maxiter=30)
+    assert 2.0 <= nmax[2] <= 2.4
