@@ -51,6 +51,7 @@ struct DevGuard {
   DevGuard& operator=(const DevGuard&) = delete;
 };
 #define GUARD(ctxp) DevGuard dev_guard_((ctxp)->device)
+#define AKS_GRAPH_MAX_BATCH 32
 
 struct aks_disc {
   aks_ctx* ctx = nullptr;
@@ -83,6 +84,7 @@ struct aks_batch {
   Lane whole;                      // all problems on the ctx stream
   Lane* cur = nullptr;             // what the launch helpers act on
   cudaEvent_t fork_ev = nullptr;
+  cudaEvent_t poll_ev[2] = {nullptr, nullptr};   // aks_scf_run: status read-back of a chunk of steps
   bool forked = false;             // lanes are ahead of the ctx stream only by their own steps
   int B = 0;
   bool fac_in_smem = true;
@@ -575,7 +577,7 @@ static int batch_create_impl(aks_batch* bt, aks_disc* disc, int32_t nprob, const
   }
   // (the kernels' dynamic shared-memory limits were raised once per ctx: set_kernel_attributes)
   {
-    const size_t need = sizeof(aks_iter_record) * B;
+    const size_t need = 2 * sizeof(aks_iter_record) * B;   // two slots: aks_scf_run polls one chunk while the next runs
     for (size_t i = 0; i < ctx->pinned_free.size(); ++i)
       if (ctx->pinned_free[i].second >= need) {
         bt->h_rec = (aks_iter_record*)ctx->pinned_free[i].first;
@@ -636,6 +638,7 @@ extern "C" void aks_batch_destroy(aks_batch* bt) {
     }
     if (bt->whole.gexec) { cudaStreamSynchronize(cx->stream); cudaGraphExecDestroy(bt->whole.gexec); }
     if (bt->fork_ev) cx->event_free.push_back(bt->fork_ev);
+    for (auto& e : bt->poll_ev) if (e) cx->event_free.push_back(e);
   }
   cudaStream_t st = bt->disc->ctx->stream;
   for (void* p : bt->allocs) cudaFreeAsync(p, st);
@@ -1039,9 +1042,13 @@ static int capture_lane(aks_batch* bt, Lane* ln) {
   CK(cudaGraphDestroy(graph));
   return AKS_OK;
 }
+// Graph replay pays where launch latency matters: measured (profiles/r02_e2e_breakdown.txt) 0.439 vs 0.468 ms per
+// step for one atom, 0.582 vs 0.600 for 11, nothing for 86 (the step is GPU bound) -- while capturing and
+// instantiating eight lane graphs costs 1.4 ms per batch.  Large batches therefore launch plainly.
+static bool graphs_on(const aks_batch* bt) { return bt->disc->ctx->use_graphs && bt->B <= AKS_GRAPH_MAX_BATCH; }
 static int run_lane(aks_batch* bt, Lane* ln) {
   aks_ctx* ctx = bt->disc->ctx;
-  if (!ctx->use_graphs) { bt->cur = ln; return step_on_lane(bt); }
+  if (!graphs_on(bt)) { bt->cur = ln; return step_on_lane(bt); }
   if (!ln->gexec) { const int rc = capture_lane(bt, ln); if (rc != AKS_OK) return rc; }
   CK(cudaGraphLaunch(ln->gexec, ln->stream));
   ctx->launches += ln->gkernels;
@@ -1071,7 +1078,7 @@ static int step_launch(aks_batch* bt) {
     bt->forked = true;
   }
   int rc = AKS_OK;
-  if (ctx->use_graphs) {
+  if (graphs_on(bt)) {
     for (Lane& ln : bt->lanes)
       if ((rc = run_lane(bt, &ln)) != AKS_OK) break;
   } else {
@@ -1161,33 +1168,58 @@ extern "C" int aks_scf_run(aks_batch* bt, int32_t maxiter, aks_iter_record* hist
   // records persist on the device between steps; start from the current ones
   if ((rc = fetch_records(bt, last.data())) != AKS_OK) return rc;
   const std::vector<aks_iter_record> first = last;
-  // a Double64 batch keeps the per-step host loop (its history is host-side)
-  const int every = (bt->dd && history) ? 1 : std::max(1, ctx->check_every);
-  for (int it = 0; it < maxiter;) {
-    const int chunk = std::min(every, maxiter - it);
-    for (int q = 0; q < chunk; ++q) {
+  if (bt->dd && history) {
+    // a Double64 batch keeps its history on the host: one poll per step
+    for (int it = 0; it < maxiter; ++it) {
       if ((rc = step_launch(bt)) != AKS_OK) return rc;
-      if (bt->dd && history) {
-        if ((rc = fetch_records(bt, nullptr)) != AKS_OK) return rc;
-        for (size_t i = 0; i < B; ++i) {
-          const aks_iter_record& r = bt->h_rec[i];
-          if (r.niter != last[i].niter || r.status != last[i].status) last[i] = r;
-          history[(size_t)(it + q) * B + i] = last[i];
-        }
+      if ((rc = fetch_records(bt, nullptr)) != AKS_OK) return rc;
+      bool running = false;
+      for (size_t i = 0; i < B; ++i) {
+        const aks_iter_record& r = bt->h_rec[i];
+        if (r.niter != last[i].niter || r.status != last[i].status) last[i] = r;
+        history[(size_t)it * B + i] = last[i];
+        running = running || last[i].status == AKS_RUNNING;
+      }
+      if (!running) {   // a problem that was not running keeps its old record
+        for (int k = it + 1; k < maxiter; ++k) for (size_t i = 0; i < B; ++i) history[(size_t)k * B + i] = last[i];
+        break;
       }
     }
-    it += chunk;
-    if ((rc = fetch_records(bt, nullptr)) != AKS_OK) return rc;
-    bool running = false;
-    for (size_t i = 0; i < B; ++i) {
-      last[i] = bt->h_rec[i];
-      if (last[i].status == AKS_RUNNING) running = true;
+  } else {
+    // chunks of `check_every` steps; the status words of chunk i are read back while chunk i + 1 already runs, so
+    // the device never waits for the host.  A chunk enqueued after every problem has finished only launches kernels
+    // that return at block entry.
+    const int every = std::max(1, ctx->check_every);
+    for (auto& e : bt->poll_ev)
+      if (!e) {
+        if (!ctx->event_free.empty()) { e = ctx->event_free.back(); ctx->event_free.pop_back(); }
+        else CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      }
+    int enq = 0;
+    auto enqueue_chunk = [&](int slot) -> int {
+      const int nstep = std::min(every, maxiter - enq);
+      for (int q = 0; q < nstep; ++q) { const int r_ = step_launch(bt); if (r_ != AKS_OK) return r_; }
+      enq += nstep;
+      main_side(bt);
+      CK(cudaMemcpyAsync(bt->h_rec + (size_t)slot * B, bt->dev.rec, sizeof(aks_iter_record) * B, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaEventRecord(bt->poll_ev[slot], ctx->stream));
+      return AKS_OK;
+    };
+    int slot = 0;
+    if ((rc = enqueue_chunk(slot)) != AKS_OK) return rc;
+    while (true) {
+      const bool more = enq < maxiter;
+      if (more && (rc = enqueue_chunk(slot ^ 1)) != AKS_OK) return rc;
+      CK(cudaEventSynchronize(bt->poll_ev[slot]));
+      bool running = false;
+      for (size_t i = 0; i < B; ++i) {
+        last[i] = bt->h_rec[(size_t)slot * B + i];
+        running = running || last[i].status == AKS_RUNNING;
+      }
+      if (!running || !more) break;
+      slot ^= 1;
     }
-    if (!running) {
-      if (bt->dd && history)   // a problem that was not running keeps its old record
-        for (int k = it; k < maxiter; ++k) for (size_t i = 0; i < B; ++i) history[(size_t)k * B + i] = last[i];
-      break;
-    }
+    CK(cudaStreamSynchronize(ctx->stream));   // a chunk may still be in flight (no-ops)
   }
   if (dev_hist) {
     CK(cudaMemcpyAsync(history, bt->dev.hist, sizeof(aks_iter_record) * B * (size_t)maxiter, cudaMemcpyDeviceToHost, ctx->stream));

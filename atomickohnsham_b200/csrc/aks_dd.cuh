@@ -265,7 +265,7 @@ static int dd_batch_create(aks_disc* disc, int32_t nprob, const double* Z, const
   bt->dev.rec = b.rec64;
   bt->dev.status = b.status;
   {
-    const size_t need = sizeof(aks_iter_record) * B;
+    const size_t need = 2 * sizeof(aks_iter_record) * B;
     CK(cudaMallocHost((void**)&bt->h_rec, need));
     bt->h_rec_bytes = need;
   }

@@ -285,6 +285,9 @@ __host__ __device__ inline size_t eig_smem_bytes(int C, int nb, int Nh) {
 // to 14.2 k cycles, but only two CTAs fit per SM instead of four and the kernel as a whole is slower (0.261 vs
 // 0.235 ms): the sweeps are bound by the latency of dependent FP64 operations, which only more resident
 // eigenpairs per SM (or shorter dependency chains) hide.  Off by default.
+#ifndef EIG_PIGGYBACK
+#define EIG_PIGGYBACK 0
+#endif
 #ifndef EIG_RED_SMEM
 #define EIG_RED_SMEM 0
 #endif
@@ -306,8 +309,54 @@ __device__ __forceinline__ double pivot_rcp(double dval) {
   return x;
 }
 
+// Inertia count of the hat system alone (count-only shifts): one thread runs both sweeps of the twisted
+// factorisation interleaved (two independent dependency chains).  Not inlined: it is called from three places of
+// eig_factor and would otherwise push k_eig over its register budget.
+__device__ __noinline__ int eig_hat_count(const double* sc, const int* ngc, int C) {
+  const int m = C - 1, tw = m / 2;
+
+    // count only: one thread per shift runs both sweeps interleaved (two independent dependency chains)
+    int neg = 0;
+    for (int cc = 0; cc < C; ++cc) neg += ngc[cc];
+    double dinvp = 0.0, offprev = 0.0, dinvn = 0.0, offnext = 0.0, scale = 0.0;
+    const int nup = m - 1 - tw;  // rows of the bottom sweep
+#pragma unroll 2
+    for (int q = 0; q < max(tw, nup); ++q) {
+      if (q < tw) {
+        const int j = q;
+        const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
+        scale = fmax(scale, fabs(diag));
+        double dj = diag;
+        if (j > 0) dj = diag - (offprev * dinvp) * offprev;
+        const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
+        if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
+        neg += (dj < 0.0);
+        dinvp = pivot_rcp(dj);
+        offprev = sc[3 * (j + 1) + 1];
+      }
+      if (q < nup) {
+        const int j = m - 1 - q;
+        const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
+        scale = fmax(scale, fabs(diag));
+        double dj = diag;
+        if (j < m - 1) dj = diag - (offnext * dinvn) * offnext;
+        const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
+        if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
+        neg += (dj < 0.0);
+        dinvn = pivot_rcp(dj);
+        offnext = sc[3 * j + 1];
+      }
+    }
+    const double diag = sc[3 * tw] + sc[3 * (tw + 1) + 2];
+    double gam = diag;
+    if (tw > 0) gam -= offprev * dinvp * offprev;
+    if (tw < m - 1) gam -= offnext * dinvn * offnext;
+    return neg + (gam < 0.0);
+    }
+
 // ---- factor T(sigma) for up to EIG_NG shifts at once: thread t = g*C + c handles cell c of shift g.
-// store != 0 (only with ng == 1): keep the factors of shift 0 for eig_solve.  Inertia counts -> S.cntg[g].
+// store != 0: keep the factors of shift 0 for eig_solve; further shifts (g >= 1) ride along count-only (the
+// certificate's shifts next to a Rayleigh-quotient iteration, on threads that would idle).  Inertia counts -> S.cntg[g].
 #ifdef AKS_EIG_TIMING
 #define EIG_FT_DECL , long long* ft
 #define EIG_FT_ARG , ft_
@@ -360,7 +409,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
       s00 = fma(y0 * dinv, y0, s00);
       s10 = fma(y1 * dinv, y0, s10);
       s11 = fma(y1 * dinv, y1, s11);
-      if (store) {
+      if (store && g == 0) {
         Fj[0] = dinv;
         Fj[nbC] = lj;
         Fj[2 * nbC] = y0 * dinv;
@@ -368,7 +417,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
       }
       dprev_inv = dinv; y0p = y0; y1p = y1;
     }
-    if (store) {  // W = L^-T D^-1 y
+    if (store && g == 0) {  // W = L^-T D^-1 y
       double w0n = 0.0, w1n = 0.0;
 #pragma unroll 4
       for (int j = nb - 1; j >= 0; --j) {
@@ -393,9 +442,13 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
   // Twisted factorisation of the (C-1) tridiagonal: a sweep down from the top and a sweep up from the
   // bottom meet at the twist index tw; inertia = negatives of both sweeps + sign of the twist pivot.
   const int m = C - 1, tw = m / 2;
+  auto hat_count = [&](int gg) { S.cntg[gg] = eig_hat_count(S.sc + (size_t)gg * 3 * C, S.negc + gg * (C + 2), C); };
   if (store) {
     // shift 0, factors kept: thread 0 runs the top sweep, thread 32 the bottom sweep
     const double* sc = S.sc;
+    // shifts riding along count-only: one thread each, in warps of their own (64: shift 1, 96: shift 2)
+    if (ng >= 2 && threadIdx.x == 64) hat_count(1);
+    if (ng >= 3 && threadIdx.x == 96) hat_count(2);
     if (threadIdx.x == 0) {
       int neg = 0;
       for (int cc = 0; cc < C; ++cc) neg += S.negc[cc];
@@ -448,45 +501,7 @@ __device__ __forceinline__ void eig_factor(const EigShared& S, int C, int nb, in
       S.cntg[0] = S.negc[C] + S.negc[C + 1] + (gam < 0.0);
     }
   } else if (c == 0 && g < ng) {
-    // count only: one thread per shift runs both sweeps interleaved (two independent dependency chains)
-    const double* sc = S.sc + (size_t)g * 3 * C;
-    const int* ngc = S.negc + g * (C + 2);
-    int neg = 0;
-    for (int cc = 0; cc < C; ++cc) neg += ngc[cc];
-    double dinvp = 0.0, offprev = 0.0, dinvn = 0.0, offnext = 0.0, scale = 0.0;
-    const int nup = m - 1 - tw;  // rows of the bottom sweep
-#pragma unroll 2
-    for (int q = 0; q < max(tw, nup); ++q) {
-      if (q < tw) {
-        const int j = q;
-        const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
-        scale = fmax(scale, fabs(diag));
-        double dj = diag;
-        if (j > 0) dj = diag - (offprev * dinvp) * offprev;
-        const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
-        if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
-        neg += (dj < 0.0);
-        dinvp = pivot_rcp(dj);
-        offprev = sc[3 * (j + 1) + 1];
-      }
-      if (q < nup) {
-        const int j = m - 1 - q;
-        const double diag = sc[3 * j] + sc[3 * (j + 1) + 2];
-        scale = fmax(scale, fabs(diag));
-        double dj = diag;
-        if (j < m - 1) dj = diag - (offnext * dinvn) * offnext;
-        const double pivmin = fmax(scale * 4.9e-32, DBL_MIN * 1e8);
-        if (fabs(dj) < pivmin) dj = (dj < 0.0) ? -pivmin : pivmin;
-        neg += (dj < 0.0);
-        dinvn = pivot_rcp(dj);
-        offnext = sc[3 * j + 1];
-      }
-    }
-    const double diag = sc[3 * tw] + sc[3 * (tw + 1) + 2];
-    double gam = diag;
-    if (tw > 0) gam -= offprev * dinvp * offprev;
-    if (tw < m - 1) gam -= offnext * dinvn * offnext;
-    S.cntg[g] = neg + (gam < 0.0);
+    hat_count(g);
   }
   __syncthreads();
   EIG_FT_MARK(1);   // hat system (+ barriers)
@@ -610,41 +625,27 @@ __device__ __forceinline__ void eig_apply_red(const EigShared& S, int C, int nb,
                                               const RedVec& out) {
   const int c = threadIdx.x;
   if (c < C) {
-    const double* R = S.red + c;
+    const double* R = S.red;
     const double xR = (c < C - 1) ? in.h[c] : 0.0, xL = (c > 0) ? in.h[c - 1] : 0.0;
-    const int o0 = (which ? 2 * nb : 4 * nb) * C, o1 = (which ? 3 * nb : 5 * nb) * C, nbC = nb * C;
-    double p0 = 0.0, p1 = 0.0, xprev = 0.0, xj = in.t[c], teprev = 0.0;
-    // four steps at a time: every table value of the group is requested before the first is used (the table
-    // lives in global memory / L2, a dependent load-FMA loop would expose every one of the latencies)
-    for (int j0 = 0; j0 < nb; j0 += 4) {
-      double c0[4], c1[4], td[4], te[4], xn[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (j0 + u < nb) {
-          const int o = (j0 + u) * C;
-          c0[u] = R[o0 + o]; c1[u] = R[o1 + o];
-          if (which) { td[u] = R[o]; te[u] = R[nbC + o]; }
-          xn[u] = (j0 + u + 1 < nb) ? in.t[o + C + c] : 0.0;
-        }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (j0 + u < nb) {
-          const int j = j0 + u;
-          double v;
-          if (which) {
-            v = td[u] * xj;
-            if (j > 0) v = fma(teprev, xprev, v);
-            if (j + 1 < nb) v = fma(te[u], xn[u], v);
-            teprev = te[u];
-          } else v = xj;
-          out.t[j * C + c] = v + c0[u] * xR + c1[u] * xL;
-          p0 = fma(c0[u], xj, p0);
-          p1 = fma(c1[u], xj, p1);
-          xprev = xj; xj = xn[u];
-        }
+    const int o0 = which ? 2 * nb : 4 * nb, o1 = which ? 3 * nb : 5 * nb;
+    double p0 = 0.0, p1 = 0.0, xprev = 0.0, xj = in.t[c];
+#pragma unroll 4
+    for (int j = 0; j < nb; ++j) {
+      const double xnext = (j + 1 < nb) ? in.t[(j + 1) * C + c] : 0.0;
+      const double c0 = R[(o0 + j) * C + c], c1 = R[(o1 + j) * C + c];
+      double v;
+      if (which) {
+        v = R[j * C + c] * xj;
+        if (j > 0) v = fma(R[(nb + j - 1) * C + c], xprev, v);
+        if (j + 1 < nb) v = fma(R[(nb + j) * C + c], xnext, v);
+      } else v = xj;
+      out.t[j * C + c] = v + c0 * xR + c1 * xL;
+      p0 = fma(c0, xj, p0);
+      p1 = fma(c1, xj, p1);
+      xprev = xj; xj = xnext;
     }
     double h00, h10, h11;
-    if (which) { h00 = R[6 * nbC]; h10 = R[6 * nbC + C]; h11 = R[6 * nbC + 2 * C]; }
+    if (which) { h00 = R[(6 * nb) * C + c]; h10 = R[(6 * nb + 1) * C + c]; h11 = R[(6 * nb + 2) * C + c]; }
     else { h00 = S.mhh[c]; h10 = S.mhh[C + c]; h11 = S.mhh[2 * C + c]; }
     S.hatpart[2 * c] = p0 + h00 * xR + h10 * xL;
     S.hatpart[2 * c + 1] = p1 + h10 * xR + h11 * xL;
@@ -914,7 +915,15 @@ k_eig(DiscDev d, BatchDev b, int mode) {
     int ng = 1;
     const int gme = threadIdx.x / C;
     double sg_mine = sigma;
+    // EIG_PIGGYBACK = 1: in Rayleigh-quotient rounds the certificate's two shifts (current estimate -/+ dl) ride along
+    // count-only on the threads that would idle (3 x C <= 128), so that a converged pair is usually certified by these
+    // witnesses without a separate certificate round.  Measured on the 86-atom sweep: count-only rounds per pair drop
+    // from 1.7 to 1.4, but every RQI round pays for two more hat sweeps (11.8 k vs 9.0 k cycles): k_eig 0.281 vs
+    // 0.237 ms.  Off.
+    const double pref = (its == 0) ? sigma : rho;
+    const double dlp = fmax(1e-8 * fabs(pref), 1e-13);
     auto shift_of = [&](int g) -> double {
+      if (state == EST_RQI) return (g == 0) ? sigma : ((g == 1) ? pref - dlp : pref + dlp);
       if (state == EST_BRACKET_LO) return sigma - step * (double)((1 << g) - 1);
       if (state == EST_BRACKET_HI) return sigma + step * (double)((1 << g) - 1);
       if (state == EST_BISECT) return lo + (hi - lo) * (double)(g + 1) / (double)(ng + 1);
@@ -923,6 +932,9 @@ k_eig(DiscDev d, BatchDev b, int mode) {
     };
     if (state == EST_BRACKET_LO || state == EST_BRACKET_HI || state == EST_BISECT) ng = ngmax;
     else if (state == EST_CERT_LO) ng = min(2, ngmax);
+#if EIG_PIGGYBACK
+    else if (state == EST_RQI && ngmax >= 3 && isfinite(pref)) ng = 3;
+#endif
     sg_mine = shift_of(min(gme, ng - 1));
     TSTART();
     const bool pf_layout = eig_factor_any(S, C, nb, ng, sg_mine, store EIG_FT_ARG);
@@ -968,6 +980,7 @@ k_eig(DiscDev d, BatchDev b, int mode) {
       sigma = mid;
     } else if (state == EST_RQI) {
       witness(sigma, cnt);
+      if (ng >= 3) { witness(shift_of(1), S.cntg[1]); witness(shift_of(2), S.cntg[2]); }
       TSTART();
       eig_solve_any(S, C, nb, pf_layout);                         // y = (H~ - sigma M~)^{-1} M~ x
       TADD(t_sol);

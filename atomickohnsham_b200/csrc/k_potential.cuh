@@ -183,28 +183,47 @@ k_potential(DiscDev d, BatchDev b, double* __restrict__ vxc_loc_out, double* __r
         }
         __syncthreads();
       }
-      // hot loop: per node 6 generator values, 9 products, then one weight + 9 DFMA per unit
+      // hot loop: two nodes per iteration -- every shared-memory access is a 128-bit load (the rows of a chunk and the
+      // weights are 16-byte aligned, a warp's slice starts at an even node): 6 + NU LDS.128 feed 18 DMUL + NU x 18 DFMA
       const int jq0 = warp * (POT_QC / AKS_NW);
 #pragma unroll
       for (int ts = 0; ts < NTS; ++ts) {
         if (ti[ts] < 0) continue;
-        const double* gi = Gb + (3 * ti[ts]) * POT_QCS + jq0;
-        const double* gj = Gb + (3 * tj[ts]) * POT_QCS + jq0;
-        const double* f0 = fs + q0 + jq0;
-#pragma unroll 2
-        for (int jq = 0; jq < POT_QC / AKS_NW; ++jq) {
-          const double a0 = gi[jq], a1 = gi[POT_QCS + jq], a2 = gi[2 * POT_QCS + jq];
-          const double b0 = gj[jq], b1 = gj[POT_QCS + jq], b2 = gj[2 * POT_QCS + jq];
-          const double p00 = a0 * b0, p01 = a0 * b1, p02 = a0 * b2;
-          const double p10 = a1 * b0, p11 = a1 * b1, p12 = a1 * b2;
-          const double p20 = a2 * b0, p21 = a2 * b1, p22 = a2 * b2;
+        const double2* gi = reinterpret_cast<const double2*>(Gb + (3 * ti[ts]) * POT_QCS + jq0);
+        const double2* gj = reinterpret_cast<const double2*>(Gb + (3 * tj[ts]) * POT_QCS + jq0);
+        const double2* f0 = reinterpret_cast<const double2*>(fs + q0 + jq0);
+#pragma unroll 1
+        for (int jq = 0; jq < POT_QC / AKS_NW / 2; ++jq) {
+          const double2 a0 = gi[jq], a1 = gi[POT_QCS / 2 + jq], a2 = gi[POT_QCS + jq];
+          const double2 b0 = gj[jq], b1 = gj[POT_QCS / 2 + jq], b2 = gj[POT_QCS + jq];
+          double2 fq[NU];
 #pragma unroll
-          for (int u = 0; u < NU; ++u) {
-            const double fq = f0[(size_t)u * Qpad + jq];
-            double* A = acc[ts][u];
-            A[0] = fma(p00, fq, A[0]); A[1] = fma(p01, fq, A[1]); A[2] = fma(p02, fq, A[2]);
-            A[3] = fma(p10, fq, A[3]); A[4] = fma(p11, fq, A[4]); A[5] = fma(p12, fq, A[5]);
-            A[6] = fma(p20, fq, A[6]); A[7] = fma(p21, fq, A[7]); A[8] = fma(p22, fq, A[8]);
+          for (int u = 0; u < NU; ++u) fq[u] = f0[(size_t)u * (Qpad / 2) + jq];
+          {
+            const double p00 = a0.x * b0.x, p01 = a0.x * b1.x, p02 = a0.x * b2.x;
+            const double p10 = a1.x * b0.x, p11 = a1.x * b1.x, p12 = a1.x * b2.x;
+            const double p20 = a2.x * b0.x, p21 = a2.x * b1.x, p22 = a2.x * b2.x;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+              const double fv = fq[u].x;
+              double* A = acc[ts][u];
+              A[0] = fma(p00, fv, A[0]); A[1] = fma(p01, fv, A[1]); A[2] = fma(p02, fv, A[2]);
+              A[3] = fma(p10, fv, A[3]); A[4] = fma(p11, fv, A[4]); A[5] = fma(p12, fv, A[5]);
+              A[6] = fma(p20, fv, A[6]); A[7] = fma(p21, fv, A[7]); A[8] = fma(p22, fv, A[8]);
+            }
+          }
+          {
+            const double p00 = a0.y * b0.y, p01 = a0.y * b1.y, p02 = a0.y * b2.y;
+            const double p10 = a1.y * b0.y, p11 = a1.y * b1.y, p12 = a1.y * b2.y;
+            const double p20 = a2.y * b0.y, p21 = a2.y * b1.y, p22 = a2.y * b2.y;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+              const double fv = fq[u].y;
+              double* A = acc[ts][u];
+              A[0] = fma(p00, fv, A[0]); A[1] = fma(p01, fv, A[1]); A[2] = fma(p02, fv, A[2]);
+              A[3] = fma(p10, fv, A[3]); A[4] = fma(p11, fv, A[4]); A[5] = fma(p12, fv, A[5]);
+              A[6] = fma(p20, fv, A[6]); A[7] = fma(p21, fv, A[7]); A[8] = fma(p22, fv, A[8]);
+            }
           }
         }
       }

@@ -823,15 +823,13 @@ __global__ void k_mix_state(DiscDev d, BatchDev b) {
 // owns 4 rows x 4 strided columns (8 shared loads per 16 FMAs of the rank-n_occ update), whose old values are all
 // requested before the update is accumulated.
 #define MIX_TS 64
-#define MIX_OCH 16   // orbitals per staging chunk
+#define MIX_OCH 40   // orbitals staged at once: in practice every occupied orbital of one spin (<= 26 for Z <= 86)
 __global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) {
   const int p = blockIdx.z, e = blockIdx.y;
   if (b.status[p] != 0) return;
+  // 2 x 40 x 64 doubles = 40 KB of static shared memory
   __shared__ double Ui[MIX_OCH][MIX_TS];
   __shared__ double Uj[MIX_OCH][MIX_TS];
-  __shared__ double nk[AKS_MAXORB];
-  __shared__ int oidx[AKS_MAXORB];
-  __shared__ int cnt_s, first_s;
   __shared__ double red[AKS_NW];
   const int Nh = d.Nh;
   // D is symmetric: only the tiles on and below the diagonal are kept current during the iterations
@@ -843,46 +841,43 @@ __global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 entries each
   const int r0 = tr * MIX_TS + 4 * ty, c0 = tc * MIX_TS + tx;   // columns c0 + 16 c: coalesced rows
   double* D = b.Dd + ((size_t)p * b.s + e) * Nh * Nh;
+  // 1. request the old values of the tile (HBM) ...
   double old[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       old[a][c] = (r0 + a < Nh && c0 + 16 * c < Nh) ? D[(size_t)(r0 + a) * Nh + c0 + 16 * c] : 0.0;
-  {
-    // the list is ordered by spin: entries of spin e are contiguous
-    const int tot = b.occ_cnt[2 * p];
-    const int* elk = b.occ_elk + ((size_t)p * 2) * AKS_MAXORB;
-    const double* nn = b.occ_n + ((size_t)p * 2) * AKS_MAXORB;
-    if (threadIdx.x == 0) { cnt_s = 0; first_s = AKS_MAXORB; }
-    __syncthreads();
-    const int o = threadIdx.x;
-    int v = 0;
-    const bool mine = (o < tot) && (((v = elk[o]) >> 16) == e);
-    if (mine) { atomicMin(&first_s, o); atomicAdd(&cnt_s, 1); }
-    __syncthreads();
-    if (mine) { nk[o - first_s] = nn[o]; oidx[o - first_s] = (((v >> 8) & 0xff) * b.nhmax) + (v & 0xff); }
-    __syncthreads();
-  }
-  const int cnt = cnt_s;
-  const double t = b.tmix[p];
+  // 2. ... and, while they are in flight, stage the two 64-entry slices of EVERY occupied orbital of this spin (L2):
+  // the compact list of k_aufbau / k_linesearch is ordered by spin, so the entries of spin e are contiguous.  One
+  // barrier for the whole tile (the chunked staging of round 1 had two per 16 orbitals plus three in a prologue
+  // that rebuilt the list with shared-memory atomics; ncu showed the barrier as the top stall reason).
+  const int tot = b.occ_cnt[2 * p];
+  const int* elk = b.occ_elk + ((size_t)p * 2) * AKS_MAXORB;
+  const double* nn = b.occ_n + ((size_t)p * 2) * AKS_MAXORB;
+  const int sp = ((int)threadIdx.x < tot) ? (elk[threadIdx.x] >> 16) : 99;   // AKS_MAXORB <= blockDim.x
+  const int first = __syncthreads_count(sp < e);
+  const int cnt = __syncthreads_count(sp == e);
   const double* Ubase = b.U + (((size_t)p * b.s + e) * b.Lmax * b.nhmax) * Nh;
+  const double t = b.tmix[p];
   double dn[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int c = 0; c < 4; ++c) dn[a][c] = 0.0;
-  for (int o0 = 0; o0 < cnt; o0 += MIX_OCH) {
+  for (int o0 = 0; o0 < cnt; o0 += MIX_OCH) {   // one pass unless more than MIX_OCH orbitals of this spin are occupied
     const int oc = min(MIX_OCH, cnt - o0);
-    __syncthreads();
+    if (o0 > 0) __syncthreads();
     for (int idx = threadIdx.x; idx < oc * MIX_TS; idx += AKS_NT) {
       const int o = idx / MIX_TS, r = idx - o * MIX_TS;
-      const double* u = Ubase + (size_t)oidx[o0 + o] * Nh;
+      const int v = elk[first + o0 + o];
+      const double* u = Ubase + (size_t)((((v >> 8) & 0xff) * b.nhmax) + (v & 0xff)) * Nh;
       const int gi = tr * MIX_TS + r, gj = tc * MIX_TS + r;
-      Ui[o][r] = (gi < Nh) ? nk[o0 + o] * u[gi] : 0.0;   // occupation folded into the row factor
+      Ui[o][r] = (gi < Nh) ? nn[first + o0 + o] * u[gi] : 0.0;   // occupation folded into the row factor
       Uj[o][r] = (gj < Nh) ? u[gj] : 0.0;
     }
     __syncthreads();
+#pragma unroll 2
     for (int o = 0; o < oc; ++o) {
       const double a0 = Ui[o][4 * ty], a1 = Ui[o][4 * ty + 1], a2 = Ui[o][4 * ty + 2], a3 = Ui[o][4 * ty + 3];
       const double b0 = Uj[o][tx], b1 = Uj[o][tx + 16], b2 = Uj[o][tx + 32], b3 = Uj[o][tx + 48];

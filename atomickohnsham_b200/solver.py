@@ -20,6 +20,10 @@ from .algorithms import ODA, FrozenAufbau, OptimizedAufbau, SmearedAufbau
 from .discretization import KSEDiscretization
 from .model import KSEModel
 
+RECORD_DTYPE = np.dtype([("niter", np.int32), ("status", np.int32), ("stop", np.float64), ("Etot", np.float64),
+                         ("Ekin", np.float64), ("Ecou", np.float64), ("Ehar", np.float64), ("Eexc", np.float64),
+                         ("t", np.float64)])   # aks_iter_record
+
 ATOMIC_NAMES = ("Hydrogen Helium Lithium Beryllium Boron Carbon Nitrogen Oxygen Fluorine Neon Sodium "
                 "Magnesium Aluminium Silicon Phosphorus Sulfur Chlorine Argon Potassium Calcium Scandium "
                 "Titanium Vanadium Chromium Manganese Iron Cobalt Nickel Copper Zinc Gallium Germanium "
@@ -181,8 +185,10 @@ class Batch:
         self.ctx.check(_capi.lib.aks_scf_step(self.h, None))
 
     def run(self, maxiter=100, history=False, raise_on_problem_error=True):
-        """solve!: returns (final records, history or None).  A problem that ends in an error (negative status:
-        AKS_EDEGEN3 = the reference's `error()` of optimized.jl:139, AKS_EEIG, AKS_ENAN) raises, unless
+        """solve!: returns (final records, history or None).  history=True: per problem the list of its per-iteration
+        records (dicts); history="array": the raw structured array (maxiter, nprob) the library filled, where slot k of
+        a problem holds its record after iteration k + 1 (its last record repeated once it has stopped).
+        A problem that ends in an error (negative status: AKS_EDEGEN3 = the reference's `error()` of optimized.jl:139, AKS_EEIG, AKS_ENAN) raises, unless
         `raise_on_problem_error=False` (sweeps: the other problems of the batch are unaffected, the status is in the
         record)."""
         hist = (IterRecord * (maxiter * self.nprob))() if history else None
@@ -194,12 +200,16 @@ class Batch:
         final = [r.asdict() for r in self._rec]
         if not history:
             return final, None
-        out = [[] for _ in range(self.nprob)]
-        for k in range(maxiter):
-            for i in range(self.nprob):
-                r = hist[k * self.nprob + i]
-                if r.niter == k + 1 and (not out[i] or out[i][-1]["niter"] != r.niter):
-                    out[i].append(r.asdict())
+        # the history buffer as a structured array (maxiter, nprob): no per-record Python work
+        arr = np.frombuffer(hist, dtype=RECORD_DTYPE).reshape(maxiter, self.nprob)
+        if history == "array":
+            return final, arr
+        out = []
+        for i in range(self.nprob):
+            col = arr[:, i]
+            # iteration k of this problem sits in slot k (slots after its last iteration repeat the last record)
+            keep = col["niter"] == np.arange(1, maxiter + 1)
+            out.append([dict(zip(RECORD_DTYPE.names, row.tolist())) for row in col[keep]])
         return final, out
 
     def records_dd(self):

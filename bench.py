@@ -290,19 +290,24 @@ def b200_arm(args):
     bt.close()
 
     # the same steps with the eigenpair window off (every step solves all nh pairs of every channel, as the
-    # reference does) and with plain stream launches instead of the graph replay: reported beside `value`
+    # reference does), reported beside `value`; and a single atom alone
     variants = {}
     if rank == 0:
         btm = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=-1)
         msm = timed_steps_local(btm, args.warmup, args.steps, stream, local)
         btm.close()
         variants["eig_window_off_margin_-1"] = {"ms_per_step": msm / args.steps, "value": B * args.steps / (msm * 1e-3)}
-        ctx.configure(use_graphs=False)
-        btn = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)
-        msn = timed_steps_local(btn, args.warmup, args.steps, stream, local)
-        btn.close()
+        # one atom alone (SURVEY 8d metric 1, "SCF iterations/s per atom"): Argon, C2; the step is a chain of 21
+        # dependent launches, replayed as a CUDA graph (batches <= 32 problems) or launched plainly
+        single = {}
+        for key, graphs in (("cuda_graph", True), ("plain_launches", False)):
+            ctx.configure(use_graphs=graphs)
+            bta = Batch([aks.LDA(Z=18, N=18)], disc, alg_fixed, lh=[1], nh=[10], eig_margin=args.eig_margin)
+            msa = timed_steps_local(bta, 10, 200, stream, local)
+            bta.close()
+            single[key] = {"ms_per_iteration": msa / 200, "iterations_per_s": 200 / (msa * 1e-3)}
         ctx.configure(use_graphs=True)
-        variants["plain_stream_launches_no_graph"] = {"ms_per_step": msn / args.steps, "value": B * args.steps / (msn * 1e-3)}
+        variants["single_atom_argon_C2"] = single
 
     # ---------------- per-phase and per-kernel device time + roofline of every kernel (rank 0)
     roof, phases = None, None
@@ -363,17 +368,17 @@ def b200_arm(args):
         barrier()
         t0 = time.perf_counter()
         bt3 = Batch(models, disc, alg_fixed, lh=lhs, nh=nhs, eig_margin=args.eig_margin)   # H2D: model parameters
-        final, hist = bt3.run(args.steps, history=True)            # D2H: every record of every step (history) + status polls
+        final, hist = bt3.run(args.steps, history="array")         # D2H: every record of every step (history) + status polls
         outs = bt3.states()                                        # D2H: eps, n, W of every atom
         torch.cuda.synchronize(local)
         e2e_times.append(time.perf_counter() - t0)
-        assert all(len(h) == args.steps for h in hist)
+        assert hist.shape == (args.steps, B) and (hist["niter"][-1] == args.steps).all() and np.isfinite(hist["Etot"]).all()
         bt3.close()
     t_e2e = sorted(e2e_times)[1]
     assert len(outs) == B
     h2d = B * (3 * 8 + 4 * 4 + 8 + 8)
     polls = -(-args.steps // 4) + 1
-    d2h_total = args.steps * B * 72 + polls * B * 72 + B * (3 * 4 * 10 * 8 + Nh_bytes())   # history + status polls + eps, n (2 slots), W
+    d2h_total = args.steps * B * 64 + polls * B * 64 + B * (3 * 4 * 10 * 8 + Nh_bytes())   # history + status polls + eps, n (2 slots), W
     e2e_units, = allreduce([float(B * args.steps)], "SUM")
     e2e_t, = allreduce([t_e2e], "MAX")
     e2e_val = e2e_units / e2e_t
@@ -425,7 +430,8 @@ def b200_arm(args):
                          "eig_window_margin": args.eig_margin, "eig_window_refills_in_run": refills,
                          "l2": "state per GPU (dense D: %.0f MB) exceeds the 126 MB L2; no explicit flush" % (B * 8 * 799 * 799 / 1e6),
                          "tables": "resident before the timed regions (setup is outside the reference's loop too)",
-                         "launch": "each lane's step (21 kernels) replayed as one CUDA graph; gpu_launches counts the kernels"},
+                         "launch": "8 stream lanes, plain launches (CUDA-graph replay is used for batches <= 32 problems, where "
+                                   "launch latency matters); gpu_launches counts the kernels"},
             "clocks": clocks, "gpu_launches": launches, "per_rank_ms_per_step": [x / args.steps for x in per_rank_ms],
             "sustained": {"steps": long_steps, "ms_per_step": max_ms_long / long_steps,
                           "value": tot_units / args.steps * long_steps / (max_ms_long * 1e-3),
@@ -434,7 +440,8 @@ def b200_arm(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h_total / args.steps,
                     "what": "Batch() + aks_scf_run(K steps, per-step history of every atom) + aks_get_state_all (eps, n, W of "
-                            "every atom), host buffers; the host polls the status words every 4 steps; median of 3",
+                            "every atom), host buffers; the status words of a chunk of 4 steps are read back while the next "
+                            "chunk runs; median of 3",
                     "seconds_each": e2e_times},
             "atoms_per_s_to_convergence": c5["atoms_per_s"], "converged": c5["converged"],
             "sweeps_to_convergence": sweeps,
