@@ -59,7 +59,7 @@ EXPORTS = ["aks_ctx_create", "aks_ctx_destroy", "aks_last_error", "aks_ctx_strea
            "aks_set_density", "aks_assemble_hartree", "aks_assemble_vxc", "aks_eig_lowest",
            "aks_density", "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak", "aks_measure_dmma_peak",
            "aks_last_phase_ms", "aks_last_kernel_ms", "aks_debug_eig_info", "aks_debug_eig_cycles", "aks_debug_eig_refills",
-           "aks_get_records_dd", "aks_dd_xc_eval"]
+           "aks_get_records_dd", "aks_dd_xc_eval", "aks_dd_gauss_legendre", "aks_dd_build_operators"]
 
 
 def _load():
@@ -110,6 +110,8 @@ def _load():
     lib.aks_debug_eig_cycles.argtypes = [vp, _ip]
     lib.aks_get_records_dd.argtypes = [vp, _dp]
     lib.aks_dd_xc_eval.argtypes = [vp, C.c_int32, _dp, C.c_int32, C.c_int32, _dp, _dp]
+    lib.aks_dd_gauss_legendre.argtypes = [vp, C.c_int32, _dp, _dp]
+    lib.aks_dd_build_operators.argtypes = [vp, C.c_int32, C.c_int32, _dp, _i32p, C.c_int32, _dp, _dp, _dp, _dp, _dp]
     return lib
 
 

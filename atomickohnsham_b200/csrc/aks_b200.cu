@@ -20,6 +20,7 @@
 #include "k_potential.cuh"
 #include "k_scf.cuh"
 #include "k_dd.cuh"
+#include "k_dd_tables.cuh"
 
 struct DDDiscHost;
 struct DDBatchHost;

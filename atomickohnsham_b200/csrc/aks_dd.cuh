@@ -464,3 +464,59 @@ static int dd_set_aufbau(aks_batch* bt, int32_t kind, double temp, const double*
   CK(cudaStreamSynchronize(ctx->stream));
   return AKS_OK;
 }
+
+
+// ------------------------------------------------------------------------------------ Double64 tables on the device
+// SURVEY 8(f) rank 1.  Results in caller-owned host buffers of (hi, lo) pairs -- exactly what aks_disc_create
+// (dtype = 1) consumes, so a caller that has no Double64 tables of its own builds them here.
+extern "C" int aks_dd_gauss_legendre(aks_ctx* ctx, int32_t n, double* x, double* w) {
+  if (!ctx || n < 1 || !x || !w) return AKS_EINVAL;
+  GUARD(ctx);
+  dd *dx = nullptr, *dw = nullptr;
+  CK(cudaMallocAsync((void**)&dx, sizeof(dd) * n, ctx->stream));
+  CK(cudaMallocAsync((void**)&dw, sizeof(dd) * n, ctx->stream));
+  ddk_tab_gauss<<<(n + 63) / 64, 64, 0, ctx->stream>>>(n, dx, dw);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(x, dx, sizeof(dd) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(w, dw, sizeof(dd) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFreeAsync(dx, ctx->stream); cudaFreeAsync(dw, ctx->stream);
+  return AKS_OK;
+}
+
+extern "C" int aks_dd_build_operators(aks_ctx* ctx, int32_t p, int32_t C, const double* mesh, const int32_t* present,
+                                      int32_t nq, double* M0_loc, double* A_loc, double* Mm1_loc, double* Mm2_loc,
+                                      double* F_loc) {
+  if (!ctx || !mesh || !present || !M0_loc || !A_loc || !Mm1_loc || !Mm2_loc || !F_loc) return AKS_EINVAL;
+  if (p < 1 || p >= DDT_PMAX || C < 1 || nq < 1) { ctx->err = "aks_dd_build_operators: need 1 <= p <= 29, C >= 1, nq >= 1"; return AKS_EINVAL; }
+  GUARD(ctx);
+  const size_t n = (size_t)p + 1, n2 = (size_t)C * n * n, n3 = n2 * n;
+  double* dmesh = nullptr; int* dpres = nullptr;
+  dd *dx, *dw, *dG, *ddG, *dscr, *dM0, *dA, *dM1, *dM2, *dF;
+  std::vector<void*> tmp;
+  auto alloc = [&](void** ptr, size_t bytes) -> cudaError_t { cudaError_t e = cudaMallocAsync(ptr, bytes, ctx->stream); if (e == cudaSuccess) tmp.push_back(*ptr); return e; };
+  CK(alloc((void**)&dmesh, sizeof(double) * (C + 1)));
+  CK(alloc((void**)&dpres, sizeof(int) * C * n));
+  CK(alloc((void**)&dx, sizeof(dd) * nq)); CK(alloc((void**)&dw, sizeof(dd) * nq));
+  CK(alloc((void**)&dG, sizeof(dd) * n * nq)); CK(alloc((void**)&ddG, sizeof(dd) * n * nq));
+  CK(alloc((void**)&dscr, sizeof(dd) * (size_t)C * 3 * nq));
+  CK(alloc((void**)&dM0, sizeof(dd) * n2)); CK(alloc((void**)&dA, sizeof(dd) * n2));
+  CK(alloc((void**)&dM1, sizeof(dd) * n2)); CK(alloc((void**)&dM2, sizeof(dd) * n2));
+  CK(alloc((void**)&dF, sizeof(dd) * n3));
+  CK(cudaMemcpyAsync(dmesh, mesh, sizeof(double) * (C + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(dpres, present, sizeof(int) * C * n, cudaMemcpyHostToDevice, ctx->stream));
+  ddk_tab_gauss<<<(nq + 63) / 64, 64, 0, ctx->stream>>>(nq, dx, dw);
+  LAUNCH_CHECK();
+  ddk_tab_genvals<<<(nq + 63) / 64, 64, 0, ctx->stream>>>(p, nq, dx, dG, ddG);
+  LAUNCH_CHECK();
+  ddk_tab_cells<<<C, 256, 0, ctx->stream>>>(p, C, nq, dmesh, dpres, dx, dw, dG, ddG, dscr, dM0, dA, dM1, dM2, dF);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(M0_loc, dM0, sizeof(dd) * n2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(A_loc, dA, sizeof(dd) * n2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(Mm1_loc, dM1, sizeof(dd) * n2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(Mm2_loc, dM2, sizeof(dd) * n2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(F_loc, dF, sizeof(dd) * n3, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (void* q : tmp) cudaFreeAsync(q, ctx->stream);
+  return AKS_OK;
+}

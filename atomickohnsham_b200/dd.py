@@ -232,15 +232,28 @@ class FEMOperatorsDD:
         return cat(I, np.int64), cat(J, np.int64), cat(M, np.int64), vals
 
 
-def build_femops_dd(basis: FEMBasis, *, nquad: int | None = None, dps: int = 50) -> FEMOperatorsDD:
+def build_femops_dd(basis: FEMBasis, *, nquad: int | None = None, dps: int = 50, ctx=None) -> FEMOperatorsDD:
     """All density-independent blocks in double-double (`init_cache!`,
     `src/discretization/discretization.jl:320-341`): the polynomial parts are integrated exactly by the
     Gauss rule, the 1/r and 1/r^2 weights converge geometrically (3p + 80 nodes reach 1e-34 on
-    exponential meshes)."""
+    exponential meshes).  With `ctx` (a `_capi.Context`) the blocks are built on the device
+    (`aks_dd_build_operators`, csrc/k_dd_tables.cuh: the same quadratures in double-double kernels, milliseconds
+    instead of 4.5 s at order 20); without, by the mpmath / NumPy mirror below (what the CPU tests check it against)."""
     p = basis.ordermax
     n = p + 1
     C = basis.ncells
     nq = nquad or (3 * p + 80)
+    if ctx is not None:
+        from . import _capi
+        present = np.zeros((C, n), dtype=np.int32)
+        for c in range(C):
+            present[c, np.asarray(basis.cells_to_generators[c])] = 1
+        pts = np.ascontiguousarray(basis.mesh.points, dtype=np.float64)
+        out = [np.zeros((C, n, n, 2)) for _ in range(4)] + [np.zeros((C, n, n, n, 2))]
+        ctx.check(_capi.lib.aks_dd_build_operators(ctx.h, p, C, _capi.dptr(pts), _capi.i32ptr(present), nq,
+                                                   *[_capi.dptr(o) for o in out]))
+        M0, A, Mm1, Mm2, F = (DD(np.ascontiguousarray(o[..., 0]), np.ascontiguousarray(o[..., 1])) for o in out)
+        return FEMOperatorsDD(basis, M0, A, Mm1, Mm2, F)
     with mp.workdps(dps):
         xs, ws = gauss_legendre_mp(nq)
         Gm, dGm = generator_values_mp(p, xs)
@@ -307,10 +320,15 @@ def generator_values_dd(p: int, x: DD) -> DD:
     return DD(np.stack([r.hi for r in rows]), np.stack([r.lo for r in rows]))
 
 
-def gauss_legendre_dd(n: int):
+def gauss_legendre_dd(n: int, ctx=None):
     """n-point Gauss-Legendre rule in double-double: Newton on P_n from the extended-precision nodes of
     `quadrature.gauss_legendre` (the reference calls `QuadGK.gauss(Double64, n)`,
-    src/fem/integration methods.jl:50)."""
+    src/fem/integration methods.jl:50).  With `ctx` the rule is computed on the device (`aks_dd_gauss_legendre`)."""
+    if ctx is not None:
+        from . import _capi
+        x, w = np.zeros((n, 2)), np.zeros((n, 2))
+        ctx.check(_capi.lib.aks_dd_gauss_legendre(ctx.h, int(n), _capi.dptr(x), _capi.dptr(w)))
+        return DD(x[:, 0].copy(), x[:, 1].copy()), DD(w[:, 0].copy(), w[:, 1].copy())
     from .quadrature import gauss_legendre
     x0, _ = gauss_legendre(n)
     hi = np.asarray(x0, dtype=np.float64)
@@ -335,10 +353,10 @@ class GaussLegendreDD:
     weights on [-1, 1], the global energy grid y, wy, the generator values at the nodes (`Pgenx`) and -- what
     the reference recomputes in every `eval_density!` -- the cell and the generator values of every grid point."""
 
-    def __init__(self, basis: FEMBasis, npoints: int = 1000):
+    def __init__(self, basis: FEMBasis, npoints: int = 1000, ctx=None):
         self.npoints = int(npoints)
         p, C = basis.ordermax, basis.ncells
-        self.x, self.w = gauss_legendre_dd(self.npoints)
+        self.x, self.w = gauss_legendre_dd(self.npoints, ctx=ctx)   # ctx: on the device
         self.Pgenx = generator_values_dd(p, self.x)                     # (p+1, Q)
         pts = np.asarray(basis.mesh.points, dtype=np.float64)
         half = DD(np.array(pts[-1])) * 0.5                               # Rmax / 2 (the mesh starts at 0)

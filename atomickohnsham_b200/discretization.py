@@ -21,7 +21,7 @@ from .quadrature import GaussLegendre
 class KSEDiscretization:
     def __init__(self, basis: FEMBasis, model=None, *, lh: int, nh: int = 10, nspin: int | None = None,
                  fem_integration_method: GaussLegendre | None = None, femops: FEMOperators | None = None,
-                 device: int = 0, dtype: str = "float64"):
+                 device: int = 0, dtype: str = "float64", table_builder: str = "device"):
         self.basis = basis
         if dtype not in ("float64", "double64"):
             raise ValueError("dtype must be 'float64' or 'double64'")
@@ -37,10 +37,16 @@ class KSEDiscretization:
             if (femops is not None and not isinstance(femops, FEMOperatorsDD)) or \
                     (fem_integration_method is not None and not isinstance(fem_integration_method, GaussLegendreDD)):
                 raise TypeError("dtype='double64' needs FEMOperatorsDD / GaussLegendreDD tables (atomickohnsham_b200.dd)")
+            # tables the caller does not bring are built by the library on the device (aks_dd_build_operators,
+            # aks_dd_gauss_legendre) or, table_builder="host", by the mpmath / NumPy mirror (dd.py)
+            if table_builder not in ("device", "host"):
+                raise ValueError("table_builder must be 'device' or 'host'")
+            tctx = _capi.default_context(device) if table_builder == "device" and (
+                femops is None or (fem_integration_method is None and model is not None and model.has_exchcorr)) else None
             if fem_integration_method is None and model is not None and model.has_exchcorr:
-                fem_integration_method = GaussLegendreDD(basis)
+                fem_integration_method = GaussLegendreDD(basis, ctx=tctx)
             self.fem_integration_method = fem_integration_method
-            self.femops = femops or build_femops_dd(basis)
+            self.femops = femops or build_femops_dd(basis, ctx=tctx)
         else:
             self.fem_integration_method = fem_integration_method or GaussLegendre(basis)
             self.femops = femops or build_femops(basis)

@@ -182,6 +182,18 @@ int aks_get_records_dd(aks_batch* batch, double* out);
  * rho, vrho, zk are npts (hi, lo) pairs; densities are clamped at 0 as BuiltinFunctional.jl:112 does       */
 int aks_dd_xc_eval(aks_ctx* ctx, int32_t npts, const double* rho, int32_t ex_id, int32_t ec_id, double* vrho,
                    double* zk);
+/* Double64 tables built by the library, on the device (no reference counterpart as an interface: replaces what
+ * GaussLegendre{Double64}(basis, n) -- QuadGK.gauss(T, n), src/fem/integration methods.jl:50 -- and init_cache!
+ * (src/discretization/discretization.jl:320-341 with the local matrices of src/fem/local matrix.jl:5-123 and the mass
+ * tensor of src/fem/matrices.jl:297-343) compute on the host for T = Double64).  Outputs are (hi, lo) pairs in
+ * caller-owned buffers, in the layouts aks_disc_create (dtype = 1) and the host mirror use:
+ *   aks_dd_gauss_legendre : x, w [n][2], nodes ascending on [-1, 1]
+ *   aks_dd_build_operators: cell-local blocks in generator order (0: 1+x, 1: 1-x, k+1: integrated Legendre k),
+ *       M0, A, Mm1, Mm2 [C][p+1][p+1][2] and the mass tensor F [C][p+1][p+1][p+1][2]; present [C][p+1] marks the
+ *       generators a cell has (Dirichlet ends); nq = Gauss nodes per cell of the build (3p + 80 reach 1e-34)       */
+int aks_dd_gauss_legendre(aks_ctx* ctx, int32_t n, double* x, double* w);
+int aks_dd_build_operators(aks_ctx* ctx, int32_t p, int32_t C, const double* mesh, const int32_t* present, int32_t nq,
+                           double* M0_loc, double* A_loc, double* Mm1_loc, double* Mm2_loc, double* F_loc);
 /* eps, n, W of every problem at once: eps, n [nprob][(L, nh[, 2])], W [nprob][Nh]; any pointer may be NULL */
 int aks_get_state_all(aks_batch* batch, double* eps, double* n, double* W);
 /* overwrite one problem's density state from a dense D (Nh,Nh[,2]) -- restart / step-level

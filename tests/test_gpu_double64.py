@@ -502,3 +502,47 @@ def test_double64_states_all_and_occupied_labels():
     assert [o[0] for o in sol.occupied] == ["1s"] and abs(sol.occupied[0][2] - 2.0) < 1e-30
     nmax = maximum_ionization([2], disc, ex=None, ec=None, width=0.4, precision=1, maxiter=30)
     assert 2.0 <= nmax[2] <= 2.4
+
+
+def test_double64_tables_built_on_the_device_match_the_host_mirror():
+    """the Double64 tables (`GaussLegendre{Double64}`, `init_cache!`) built by the library on the
+    device (`aks_dd_gauss_legendre`, `aks_dd_build_operators`) against the mpmath / NumPy double-double mirror of dd.py
+    (itself checked against mpmath quadrature in tests/test_dd_host.py): 1e-30 relative per table at order 20; and a
+    Double64 run on device-built tables reproduces the reference's committed sodium log like the host-built ones."""
+    import time
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200 import _capi
+    from atomickohnsham_b200.dd import GaussLegendreDD, build_femops_dd, gauss_legendre_dd
+    ctx = _capi.default_context(0)
+
+    def rel(a, b):
+        d = (a.hi - b.hi) + (a.lo - b.lo)
+        return float(np.max(np.abs(d)) / np.max(np.abs(b.hi)))
+
+    for n in (7, 140, 1000):
+        xd, wd = gauss_legendre_dd(n, ctx=ctx)
+        xh, wh = gauss_legendre_dd(n)
+        assert rel(xd, xh) < 1e-30 and rel(wd, wh) < 5e-30, (n, rel(xd, xh), rel(wd, wh))
+    basis = aks.P1IntLegendreBasis(aks.expmesh(0, 300, 41, s=1.5), ordermax=20)
+    t0 = time.perf_counter()
+    dev = build_femops_dd(basis, ctx=ctx)
+    qd = GaussLegendreDD(basis, 1000, ctx=ctx)
+    t_dev = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    host = build_femops_dd(basis)
+    qh = GaussLegendreDD(basis, 1000)
+    t_host = time.perf_counter() - t0
+    for name in ("M0_loc", "A_loc", "Mm1_loc", "Mm2_loc", "F_loc"):
+        assert rel(getattr(dev, name), getattr(host, name)) < 1e-30, (name, rel(getattr(dev, name), getattr(host, name)))
+    for name in ("x", "w", "y", "wy", "Pgenx", "Pgeny"):
+        assert rel(getattr(qd, name), getattr(qh, name)) < 1e-28, (name, rel(getattr(qd, name), getattr(qh, name)))
+    print(f"[dd tables, order 20, 40 cells, Q = 1000] device {t_dev:.3f} s, host mirror {t_host:.2f} s")
+    assert t_dev < 0.5
+    # the reference's Double64 sodium run on device-built tables (default of KSEDiscretization(dtype="double64"))
+    g = load_golden("sodium_double64.json")
+    bt, disc, _ = _setup(g)
+    for it in range(3):
+        bt.step()
+        rd = bt.records_dd()[0]
+        assert abs(_mpf(rd[1]) - mp.mpf(g["iterations"][it]["Etot"])) < mp.mpf("1e-24") * abs(mp.mpf(g["iterations"][it]["Etot"]))
+    bt.close()
