@@ -36,6 +36,7 @@ struct aks_ctx {
   std::vector<cudaStream_t> stream_free;
   std::vector<cudaEvent_t> event_free;
   int check_every = 4;    // aks_scf_run reads the status words every this many steps (AKS_CHECK_EVERY)
+  bool pot_tc = true;     // potential blocks by k_potential_tc (FP64 tensor cores; orders p <= 23) -- AKS_POTENTIAL_TC=0: k_potential
   bool use_graphs = true; // the step sequence of a lane is captured once and replayed as a CUDA graph (AKS_NO_GRAPH=1: off)
 };
 
@@ -90,6 +91,7 @@ struct aks_batch {
   int B = 0;
   bool fac_in_smem = true;
   double* fac_global = nullptr;
+  bool pot_tc = false;
   size_t smem_pot = 0, smem_eig = 0, smem_eig_main = 0, smem_red = 0, smem_chan = 0, smem_dens = 0, smem_poisson = 0;
   std::vector<double> hZ, hN, hHar, hScftol, hTinit;
   std::vector<int> hLp, hnhp, hFrozen, hMaxiter;
@@ -177,7 +179,7 @@ static int set_kernel_attributes(aks_ctx* ctx) {
     CK(cudaFuncGetAttributes(&fa_, fn));                                                                      \
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa_.sharedSizeBytes)); \
   } while (0)
-  SMEM_MAX((k_potential<1, 4>)); SMEM_MAX((k_potential<2, 2>));
+  SMEM_MAX((k_potential<1, 4>)); SMEM_MAX((k_potential<2, 2>)); SMEM_MAX(k_potential_tc); SMEM_MAX(k_hassemble);
   SMEM_MAX(k_eig); SMEM_MAX(k_eig_cert);
   SMEM_MAX(k_reduce<8>); SMEM_MAX(k_reduce<12>); SMEM_MAX(k_reduce<20>); SMEM_MAX(k_reduce<28>);
   SMEM_MAX(k_eig_init); SMEM_MAX(k_eig_final); SMEM_MAX(k_poisson);
@@ -202,6 +204,7 @@ extern "C" int aks_ctx_create(int device, aks_ctx** out) {
   { int rc = set_kernel_attributes(ctx); if (rc != AKS_OK) return rc; }
   if (const char* e = getenv("AKS_CHECK_EVERY")) ctx->check_every = std::max(1, atoi(e));
   if (const char* e = getenv("AKS_NO_GRAPH")) ctx->use_graphs = !(e[0] == '1');
+  if (const char* e = getenv("AKS_POTENTIAL_TC")) ctx->pot_tc = (e[0] != '0');
   {
     // batches come and go (one per sweep / restart): their device arrays are taken from the device's
     // stream-ordered pool, which keeps freed memory instead of returning it to the OS
@@ -544,7 +547,7 @@ static int batch_create_impl(aks_batch* bt, aks_disc* disc, int32_t nprob, const
   bt->fields.push_back({offsetof(BatchDev, field), sizeof(T) * ((size_t)(count) / B)});
   ZB(double, Dd, B * s * Nh * Nh) ZB(double, rho_q, B * s * C * Q) ZB(double, rho_y, B * s * G)
   ZB(double, Bv, B * Nh) ZB(double, Wv, B * Nh) ZB(double, E, B * 5) ZB(double, t, B) ZB(double, stop, B)
-  ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Hpk, B * s * L * C * dv.npk) ZB(double, Hfull, B * s * L * C * n * n)
+  ZB(int, niter, B) ZB(int, status, B) ZB(double, fxc, B * s * C * Q) ZB(double, Kxc, B * s * C * n * n) ZB(double, Hpk, B * s * L * C * dv.npk) ZB(double, Hfull, B * s * L * C * n * n)
   ZB(double, eps, B * s * L * nh) ZB(double, eps_new, B * s * L * nh) ZB(double, U, B * s * L * nh * Nh)
   ZB(int, eig_info, B * s * L * nh) ZB(long long, eig_dbg, B * s * L * nh * 8) ZB(double, red, B * s * L * C * (6 * (n - 2) + 4))
   ZB(double, Pm, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Pt, B * s * L * C * (n - 2) * (n - 2)) ZB(double, Xt, B * s * L * nh * ((n - 2) * C + C)) ZB(double, eig_part, B * s * L * nh * C * 6) ZB(int, warm, B) ZB(int, kact, B * s * L) ZB(int, kdone, B * s * L) ZB(int, redo, B) ZB(int, kreq, B * s * L) ZB(int, full_refill, B) ZB(int, cert_cnt, B * s * L) ZB(int, redo_cnt, B) ZB(double, e_cert, B) ZB(int, degen3, B) ZB(double, nfix, B * s * L * nh) ZB(int, khist, B * s * L * AKS_KHIST) ZB(double, ekin_orb, B * s * L * nh)
@@ -566,7 +569,8 @@ static int batch_create_impl(aks_batch* bt, aks_disc* disc, int32_t nprob, const
   b.eig_margin = 0;
   b.aufbau_kind = 0; b.temp = 0.0;
   // launch configuration
-  bt->smem_pot = potential_smem_bytes(dv.n, dv.Q, b.s);
+  bt->pot_tc = ctx->pot_tc && potential_tc_ok(dv.n, dv.Q, dv.Qs, b.s);
+  bt->smem_pot = bt->pot_tc ? potential_tc_smem_bytes() : potential_smem_bytes(dv.n, dv.Q, b.s);
   bt->smem_eig = eig_smem_bytes(dv.C, dv.nb, dv.Nh);
   bt->smem_eig_main = bt->smem_eig + eig_red_smem_bytes(dv.C, dv.nb);
   bt->smem_red = reduce_smem_bytes(dv.nb);
@@ -818,6 +822,18 @@ static int launch_potential_range(aks_batch* bt, double* vxc_out, double* har_ou
   ktick(bt, "k_xc");
   if (tm) CK(cudaEventRecord(bt->ev[12], bt->cur->stream));
   const dim3 grid(dv.C, (np + NP - 1) / NP);
+  if (bt->pot_tc) {
+    const int npc = POT_TC_NU / bt->cur->dev.s;
+    const dim3 gtc(dv.C, (np + npc - 1) / npc);
+    k_potential_tc<<<gtc, POT_TC_NT, bt->smem_pot, bt->cur->stream>>>(dv, bt->cur->dev, p0, np, force);
+    LAUNCH_CHECK();
+    ktick(bt, "k_potential_tc");
+    k_hassemble<<<gtc, AKS_NT, hassemble_smem_bytes(dv.n), bt->cur->stream>>>(dv, bt->cur->dev, vxc_out, har_out, p0, np, force);
+    LAUNCH_CHECK();
+    ktick(bt, "k_hassemble");
+    if (tm) CK(cudaEventRecord(bt->ev[13], bt->cur->stream));
+    return AKS_OK;
+  }
   if (potential_nts(dv.n) == 1)
     k_potential<1, 4><<<grid, AKS_NT, bt->smem_pot, bt->cur->stream>>>(dv, bt->cur->dev, vxc_out, har_out, p0, np, force);
   else

@@ -268,3 +268,10 @@ __device__ inline void brent_update(BrentState& s, double nf) {
     }
   }
 }
+
+// FP64 tensor-core tile update C(8x8) += A(8x4) B(4x8), mma.sync m8n8k4: lane holds A[lane/4][lane%4], B[lane%4][lane/4]
+// and C[lane/4][2 (lane%4) + {0,1}]
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}

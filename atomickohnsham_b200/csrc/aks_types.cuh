@@ -77,6 +77,7 @@ struct BatchDev {
   int* status;    // [B]
   // per-iteration work
   double* fxc;       // [B][s][C][Q]   w_q * vxc_sigma(rho(q))
+  double* Kxc;       // [B][s][C][n*n] XC block of every cell (k_potential_tc -> k_hassemble)
   double* Hpk;       // [B][s][Lmax][C][npk]  packed lower blocks (k_reduce)
   double* Hfull;     // [B][s][Lmax][C][n*n]  the same blocks, full symmetric (mat-vecs in k_eig)
   double* eps;       // [B][s][Lmax][nhmax]

@@ -97,7 +97,7 @@ def solve_sweep(models, discretization, *, lh=None, nh=None, alg=None, maxiter=1
 
 
 def maximum_ionization(Zs, discretization, *, nspin=1, ex="lda_x", ec="lda_c_pw", width=1.2, precision=2,
-                       scftol=1e-6, maxiter=50, tinit=0.4, degen_tol=1e-2, lh=None, nh=None):
+                       scftol=1e-6, maxiter=50, tinit=0.4, degen_tol=1e-2, lh=None, nh=None, trace=None):
     """Largest electron number N in [Z, Z + width] each nucleus Z can bind, by bisection on N.
 
     Batched front end of the driver `compute_maximum_ionization` (`examples/periodic table/process.jl:12-86`):
@@ -106,7 +106,8 @@ def maximum_ionization(Zs, discretization, *, nspin=1, ex="lda_x", ec="lda_c_pw"
     `scftol = 1e-6`, `maxiter = 50`, `degen_tol = 1e-2` and `(lh, nh)` rule -- but every bisection round is
     ONE device batch over all Z on a shared discretization instead of a thread per atom (the reference script
     also re-meshes per atom from a first neutral run; that stays with the caller, who owns the discretization).
-    Returns {Z: N_max} rounded to `precision` digits.
+    Returns {Z: N_max} rounded to `precision` digits (the last trial N, process.jl:85).  `trace`, a dict, receives per Z the
+    list of trials (N, HOMO energy, bound?) in bisection order.
     """
     from .algorithms import ODA, OptimizedAufbau
     from .solver import Batch
@@ -136,6 +137,8 @@ def maximum_ionization(Zs, discretization, *, nspin=1, ex="lda_x", ec="lda_c_pw"
             occ = nn != 0
             homo = float(ee[occ].max())
             stable = homo <= 0.0 and final[i]["status"] == 1 and final[i]["stop"] <= scftol
+            if trace is not None:
+                trace.setdefault(z, []).append((mid[z], homo, bool(stable)))
             if stable:
                 lo[z] = mid[z]
             else:

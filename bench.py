@@ -137,7 +137,7 @@ def workload_stats(lhs, nhs, states, eig_info):
     import numpy as np
     n, nb, C, Q, G, Nh = 21, 19, 40, 1000, 1000, 799
     npk = n * (n + 1) // 2
-    st = {k: [0.0, 0.0] for k in ("k_xc", "k_potential", "k_reduce", "k_eig_init", "k_eig", "k_eig_final", "k_eig_scale",
+    st = {k: [0.0, 0.0] for k in ("k_xc", "k_potential", "k_potential_tc", "k_hassemble", "k_reduce", "k_eig_init", "k_eig", "k_eig_final", "k_eig_scale",
                                   "k_aufbau", "k_eig_cert", "k_dens_cells", "k_dens_grid", "k_poisson", "k_linesearch",
                                   "k_mix_state", "k_mix_dense", "k_finalize")}
     counts, rqi, _ = eig_info
@@ -149,6 +149,11 @@ def workload_stats(lhs, nhs, states, eig_info):
         st["k_xc"][0] += C * Q * 80.0;                st["k_xc"][1] += C * Q * 16.0
         st["k_potential"][0] += C * (2.0 * n * n * Q + 2.0 * n ** 3)
         st["k_potential"][1] += C * (8.0 * Q + L * (npk + n * n) * 8.0)
+        # default path: the contraction (FP64 tensor cores) and the streaming Hartree block + H_l assembly are two kernels
+        st["k_potential_tc"][0] += C * 2.0 * n * n * Q
+        st["k_potential_tc"][1] += C * (8.0 * Q + 8.0 * n * n)
+        st["k_hassemble"][0] += C * 2.0 * n ** 3
+        st["k_hassemble"][1] += C * (8.0 * n * n + L * (npk + n * n) * 8.0)
         st["k_reduce"][0] += L * C * (10.0 / 3.0) * nb ** 3
         st["k_reduce"][1] += L * C * (npk + 6 * nb + 4 + 2 * nb * nb) * 8.0
         st["k_eig_init"][0] += nwin * C * 4.0 * nb * nb

@@ -332,3 +332,42 @@ def test_groundstate_over_several_devices():
     two = aks.groundstate(models, disc, alg, lh=lhs, nh=nhs, want_arrays=False, devices=[0, 1])
     assert [s.energies.Etot for s in one] == [s.energies.Etot for s in two]
     assert [s.niter for s in one] == [s.niter for s in two]
+
+
+def test_maximum_ionization_against_the_oracle_bisection():
+    """SURVEY 8(f) rank 2 (examples/periodic table/process.jl:12-86): the batched N-bisection front end against the SAME
+    bisection driven by the oracle, one atom and one trial at a time as the reference script does -- same bracket
+    [Z, Z + 1.2], same stability test (HOMO <= 0 and SCF converged to 1e-6 within 50 iterations, process.jl:77-82), same
+    ODA(0.4) / OptimizedAufbau(1e-2).  Every trial decision (bound / not bound) and the final N_max agree; the HOMO of
+    every converged trial agrees to 5e-6 Ha (runs that stop at scftol = 1e-6 end at different iterates near the same
+    fixed point: the levels carry an error of the order of the stopping criterion; measured worst 6e-7)."""
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200.sweep import maximum_ionization
+    from helpers import make_oracle, package_tables
+    mesh = ["exp", 0, 300, 30, 1.3]
+    basis, ops, quad = package_tables(mesh, 10, 1000)
+    disc = aks.KSEDiscretization(basis, None, lh=1, nh=6, nspin=1, fem_integration_method=quad, femops=ops)
+    zs = [1, 2, 3, 9]
+    precision = 1
+    trace = {}
+    got = maximum_ionization(zs, disc, precision=precision, lh=1, nh=6, trace=trace)
+    want = {}
+    for z in zs:
+        lo, hi = float(z), z + 1.2
+        k = 0
+        while hi - lo > 10.0 ** (-precision):
+            mid = (hi + lo) / 2
+            o = make_oracle({"Z": z, "N": mid, "lh": 1, "nh": 6, "ex": "lda_x", "ec": "lda_c_pw", "mesh": mesh, "p": 10,
+                             "scftol": 1e-6, "tinit": 0.4, "degen_tol": 1e-2})
+            st, _ = o.groundstate(maxiter=50)
+            homo = float(st.eps[st.n != 0].max())
+            stable = homo <= 0.0 and st.stop < 1e-6
+            g_mid, g_homo, g_stable = trace[z][k]
+            assert g_mid == mid and g_stable == stable, (z, k, mid, homo, g_homo, st.stop)
+            if st.stop < 1e-6:
+                assert abs(g_homo - homo) < 5e-6, (z, k, g_homo, homo)
+            lo, hi = (mid, hi) if stable else (lo, mid)
+            k += 1
+        want[z] = round(mid, precision)   # process.jl:85
+    assert got == want, (got, want)
+    print("[maximum ionization vs oracle bisection]", got)
