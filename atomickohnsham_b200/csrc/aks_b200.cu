@@ -36,6 +36,7 @@ struct aks_ctx {
   std::vector<cudaStream_t> stream_free;
   std::vector<cudaEvent_t> event_free;
   int check_every = 4;    // aks_scf_run reads the status words every this many steps (AKS_CHECK_EVERY)
+  bool dens_tc = true;    // cell densities by k_dens_cells_tc + k_fd (FP64 tensor cores; orders p <= 23) -- AKS_DENS_TC=0: k_dens_cells
   bool pot_tc = true;     // potential blocks by k_potential_tc (FP64 tensor cores; orders p <= 23) -- AKS_POTENTIAL_TC=0: k_potential
   bool use_graphs = true; // the step sequence of a lane is captured once and replayed as a CUDA graph (AKS_NO_GRAPH=1: off)
 };
@@ -179,7 +180,7 @@ static int set_kernel_attributes(aks_ctx* ctx) {
     CK(cudaFuncGetAttributes(&fa_, fn));                                                                      \
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa_.sharedSizeBytes)); \
   } while (0)
-  SMEM_MAX((k_potential<1, 4>)); SMEM_MAX((k_potential<2, 2>)); SMEM_MAX(k_potential_tc); SMEM_MAX(k_hassemble);
+  SMEM_MAX((k_potential<1, 4>)); SMEM_MAX((k_potential<2, 2>)); SMEM_MAX(k_potential_tc); SMEM_MAX(k_hassemble); SMEM_MAX(k_dens_cells_tc<1>); SMEM_MAX(k_dens_cells_tc<2>); SMEM_MAX(k_fd);
   SMEM_MAX(k_eig); SMEM_MAX(k_eig_cert);
   SMEM_MAX(k_reduce<8>); SMEM_MAX(k_reduce<12>); SMEM_MAX(k_reduce<20>); SMEM_MAX(k_reduce<28>);
   SMEM_MAX(k_eig_init); SMEM_MAX(k_eig_final); SMEM_MAX(k_poisson);
@@ -205,6 +206,7 @@ extern "C" int aks_ctx_create(int device, aks_ctx** out) {
   if (const char* e = getenv("AKS_CHECK_EVERY")) ctx->check_every = std::max(1, atoi(e));
   if (const char* e = getenv("AKS_NO_GRAPH")) ctx->use_graphs = !(e[0] == '1');
   if (const char* e = getenv("AKS_POTENTIAL_TC")) ctx->pot_tc = (e[0] != '0');
+  if (const char* e = getenv("AKS_DENS_TC")) ctx->dens_tc = (e[0] != '0');
   {
     // batches come and go (one per sweep / restart): their device arrays are taken from the device's
     // stream-ordered pool, which keeps freed memory instead of returning it to the OS
@@ -464,6 +466,19 @@ extern "C" int aks_disc_create(aks_ctx* ctx, const aks_disc_desc* D, aks_disc** 
   int rc;
 #define UP(vec, field)                                                                          \
   if ((rc = dev_upload(ctx, disc->allocs, vec, &dv.field)) != AKS_OK) { aks_disc_destroy(disc); return rc; }
+  std::vector<double> Pgc;
+  if (n <= POT_TC_ROWS) {
+    const int nchk = (Q + POT_QC - 1) / POT_QC;
+    Pgc.assign((size_t)nchk * POT_IMG_ROWS * POT_TC_QCS, 0.0);
+    for (int q = 0; q < Q; ++q) {
+      for (int g = 0; g < n; ++g)
+        Pgc[((size_t)(q / POT_QC) * POT_IMG_ROWS + g) * POT_TC_QCS + q % POT_QC] = Pg[(size_t)g * dv.Qs + q];
+      Pgc[((size_t)(q / POT_QC) * POT_IMG_ROWS + POT_TC_ROWS) * POT_TC_QCS + q % POT_QC] = D->x[q];
+    }
+  } else {
+    Pgc.assign(8, 0.0);
+  }
+  UP(Pgc, Pgc)
   UP(Pg, Pg) UP(wv, w) UP(xv, x) UP(inv1, inv1) UP(inv2, inv2) UP(Al, A_loc) UP(M0l, M0_loc) UP(M1l, Mm1_loc)
   UP(M2l, Mm2_loc) UP(M0pk, M0pk) UP(Fl, F_loc) UP(l2g, l2g) UP(yv, y) UP(wyv, wy) UP(ycell, ycell) UP(Pgy, Pgy)
   UP(lo_tab, lo_tab) UP(pk_tab, pk_tab) UP(Abbinv, Abb_inv) UP(XA, XA) UP(triD, triA_d) UP(triL, triA_l) UP(Linv, Linv)
@@ -909,6 +924,17 @@ static int launch_dens_cells(aks_batch* bt) {
   aks_ctx* ctx = bt->disc->ctx;
   const DiscDev& dv = bt->disc->dev;
   const dim3 grid(dv.C, bt->cur->B, 2);
+  if (ctx->dens_tc && dens_tc_ok(dv.n, dv.Q, dv.Qs)) {
+    const BatchDev& bd = bt->cur->dev;
+    const dim3 gtc((dv.C + DENS_TC_NC - 1) / DENS_TC_NC, bt->cur->B, 2);
+    if (bd.s == 1) k_dens_cells_tc<1><<<gtc, DENS_TC_NT, dens_tc_smem_bytes(), bt->cur->stream>>>(dv, bd);
+    else k_dens_cells_tc<2><<<gtc, DENS_TC_NT, dens_tc_smem_bytes(), bt->cur->stream>>>(dv, bd);
+    LAUNCH_CHECK();
+    ktick(bt, "k_dens_cells_tc");
+    k_fd<<<dim3(dv.C, (bt->cur->B + FD_NP - 1) / FD_NP, 2), AKS_NT, fd_smem_bytes(dv.n), bt->cur->stream>>>(dv, bt->cur->dev);
+    LAUNCH_CHECK();
+    ktick(bt, "k_fd");
+  } else {
   switch (bt->disc->nmax_tpl) {
     case 12: k_dens_cells<12><<<grid, DENS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
     case 24: k_dens_cells<24><<<grid, DENS_NT, bt->smem_dens, bt->cur->stream>>>(dv, bt->cur->dev); break;
@@ -916,6 +942,7 @@ static int launch_dens_cells(aks_batch* bt) {
   }
   LAUNCH_CHECK();
   ktick(bt, "k_dens_cells");
+  }
   const dim3 g2((dv.G + AKS_NT - 1) / AKS_NT, bt->cur->B, 2);
   switch (bt->disc->nmax_tpl) {
     case 12: k_dens_grid<12><<<g2, AKS_NT, 0, bt->cur->stream>>>(dv, bt->cur->dev); break;

@@ -16,6 +16,7 @@
 
 #define AKS_NT 256          // threads per CTA for the cell / eigen kernels
 #define AKS_NW (AKS_NT / 32)
+#define POT_IMG_ROWS 25     // rows of a 64-node chunk image of the generator table in DiscDev::Pgc (row 24: the nodes)
 #define AKS_MAXORB 96       // max orbitals (L*nh*nspin) per problem held in shared lists
 
 struct XcConsts {

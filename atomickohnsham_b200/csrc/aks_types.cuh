@@ -14,6 +14,9 @@ struct DiscDev {
   int p, n, nb, npk, C, Nh, Q, Qs, G, L, nh, nspin;
   double Rmax;
   const double* Pg;      // [n][Qs]   generator g at Gauss node q (row stride Qs)
+  const double* Pgc;     // [ceil(Q/64)][25][68]  the same table as shared-memory images of 64-node chunks (n <= 24 only): rows
+                         //   n..23, the 4 pad columns and the nodes >= Q are zero, row 24 holds the nodes x_q themselves -- one
+                         //   bulk copy per chunk (k_potential_tc: 24 rows, k_dens_cells_tc: 25)
   const double* w;       // [Q]
   const double* x;       // [Q]   Gauss nodes on [-1,1]
   const double* inv1;    // [C]  h/2

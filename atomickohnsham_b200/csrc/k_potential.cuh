@@ -451,15 +451,16 @@ k_potential_tc(DiscDev d, BatchDev b, int p0, int np, int force) {
 
   __shared__ __align__(8) uint64_t full_bar[ST], empty_bar[ST];
   const int nch = (Q + POT_QC - 1) / POT_QC;
-  // One lane of the producer warp (warp 8) issues a chunk: generator rows, then the f rows of the units with a functional.
-  // Bulk copies are warp-uniform instructions (UBLKCP, ~100 cycles each to issue): 25 per chunk would make a computing
-  // warp the straggler of its CTA, so the ninth warp does nothing else.
+  // One lane of the producer warp (warp 8) issues a chunk: its image of the generator table (DiscDev::Pgc: one 13 KB copy
+  // instead of n row copies of 512 B -- small bulk copies retire at ~1 per 60-100 cycles per SM), then the f rows of the units
+  // with a functional.  Bulk copies are warp-uniform instructions (UBLKCP): a computing warp that issued them would be the
+  // straggler of its CTA, so the ninth warp does nothing else.
   auto issue = [&](int ch) {
     const int st = ch % ST;
     double* dst = Gs + (size_t)st * STAGE;
     const int q0 = ch * POT_QC, len = min(POT_QC, Q - q0);
-    mbar_expect_tx(&full_bar[st], (uint32_t)((n + __popc(xmask)) * len * 8));
-    for (int g = 0; g < n; ++g) bulk_g2s(dst + g * QCS, d.Pg + (size_t)g * d.Qs + q0, (uint32_t)(len * 8), &full_bar[st]);
+    mbar_expect_tx(&full_bar[st], (uint32_t)(ROWS * QCS * 8 + __popc(xmask) * len * 8));
+    bulk_g2s(dst, d.Pgc + (size_t)ch * POT_IMG_ROWS * QCS, (uint32_t)(ROWS * QCS * 8), &full_bar[st]);   // the chunk image: one copy
 #pragma unroll
     for (int u = 0; u < NU; ++u)
       if (uxc(u)) {
@@ -477,16 +478,10 @@ k_potential_tc(DiscDev d, BatchDev b, int p0, int np, int force) {
       for (int st = 0; st < ST; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], AKS_NW); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // rows >= n of a chunk are never written by the copies: zero them once (rows of units without a functional are not read)
-    for (int idx = tid; idx < ST * (ROWS - n) * QCS; idx += POT_TC_NT) {
-      const int st = idx / ((ROWS - n) * QCS), r = idx - st * (ROWS - n) * QCS;
-      Gs[(size_t)st * STAGE + n * QCS + r] = 0.0;
-    }
     __syncthreads();
     POT_STAMP();
     if (warp == AKS_NW) {   // producer
       if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // zeros (generic proxy) before the bulk writes
         for (int ch = 0; ch < nch; ++ch) {
           if (ch >= ST) mbar_wait(&empty_bar[ch % ST], (uint32_t)(((ch - ST) / ST) & 1));   // all eight warps released it
           issue(ch);

@@ -2,6 +2,7 @@
 // representation the path needs, radial Poisson solve, energies + ODA line search, mixing
 // and the stopping rule.  Reference functions replaced are cited per kernel.
 #pragma once
+#include <type_traits>
 #include <float.h>
 
 #include "aks_device.cuh"
@@ -378,6 +379,281 @@ __global__ void __launch_bounds__(DENS_NT, 3) k_dens_cells(DiscDev d, BatchDev b
       if (m < n) {   // warp-uniform
         const double v = warp_sum(acc[j]);
         if (lane == 0) b.Bloc_new[(((size_t)p * 2 + slot) * C + c) * n + m] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_dens_cells_tc + k_fd: the same three outputs with the orbital values at the nodes on the FP64 tensor cores, for
+// orders p <= 23 (n <= 24 generators) and Q a multiple of 8.
+//
+//   psi[q][o] = sum_i G[i][q] us[o][i]  as  C(8 nodes x 8 orbitals) += A(8 nodes x 4 generators) B(4 generators x 8
+//   orbitals), mma.sync m8n8k4: six steps over the generators per 8-node group and 8-orbital tile.
+//
+// A CTA owns four cells of one (problem, slot): computing warp w owns cell c0 + w, a fifth warp streams the generator
+// table through shared memory in 64-node chunks (TMA row copies, DENS_TC_ST stages, full / empty mbarrier pair per stage;
+// the table is the same for every cell and problem, so one stream feeds the four cells).  The B fragments -- orbital
+// coefficients of the warp's cell, occupation folded in, 16 orbitals of one spin per sweep over the nodes (one sweep for
+// every atom of the periodic table without spin) -- are gathered from U straight into registers; the A fragments are
+// conflict-free shared loads (row stride 68).  Two node groups advance together (up to four independent DMMA chains).  A
+// lane ends a chain with psi[node lane / 4][orbitals 2 (lane % 4) + {0, 1}]: squares, two shuffles over lane % 4, then
+// lane % 4 = 0 / 1 finish the node of the first / second group: division by r^2, store, <Vxc[D_prev], D_new>.
+// Against k_dens_cells: no 48 generator values per thread (168 registers, 3 CTAs per SM), no reload of the table per cell.
+// The mass-tensor contraction B = F:D moves to k_fd, which reads F_c once for four problems.
+#define DENS_TC_ROWS 24
+#define DENS_TC_QC 64
+#define DENS_TC_QCS 68     // row stride of a node chunk: 4 mod 16 doubles
+#define DENS_TC_ST 3
+#define DENS_TC_NC 4       // cells (= computing warps) per CTA
+#define DENS_TC_NT (32 * DENS_TC_NC + 32)
+__host__ __device__ inline bool dens_tc_ok(int n, int Q, int Qs) { return n <= DENS_TC_ROWS && (Q % 8) == 0 && (Qs % 2) == 0; }
+#define DENS_TC_STAGE (POT_IMG_ROWS * DENS_TC_QCS + DENS_TC_NC * DENS_TC_QC)   // chunk image (table + nodes), then f of the 4 cells
+__host__ __device__ inline size_t dens_tc_smem_bytes() {
+  return sizeof(double) * ((size_t)DENS_TC_ST * DENS_TC_STAGE + 8);
+}
+template <int SP>   // nspin
+__global__ void __launch_bounds__(DENS_TC_NT, 4) k_dens_cells_tc(DiscDev d, BatchDev b) {
+  const int c0 = blockIdx.x * DENS_TC_NC, p = blockIdx.y, slot = blockIdx.z;
+  if (b.status[p] != 0) return;
+  if (slot == 1 && !b.degen[p]) return;
+  __shared__ OccList L;
+  __shared__ __align__(8) uint64_t full_bar[DENS_TC_ST], empty_bar[DENS_TC_ST];
+  extern __shared__ __align__(16) double sm_dc[];
+  constexpr int NR = DENS_TC_ROWS, QCS = DENS_TC_QCS, ST = DENS_TC_ST, QC = DENS_TC_QC;
+  const int n = d.n, Q = d.Q, C = d.C;
+  double* Gs = sm_dc;                                   // [ST][25 x 68 image | 4 x 64 f]
+  constexpr int STAGE = DENS_TC_STAGE;
+#ifdef AKS_DENS_TIMING   // cycle stamps of thread 0 (tools/gpu_dens_cycles.py); problems 0..63, slot 0
+  long long* stamp_ = b.eig_dbg + ((size_t)p * gridDim.x + blockIdx.x) * 8; int nstamp_ = 0;
+#define DENS_STAMP() do { if (threadIdx.x == 0 && p < 64 && slot == 0 && nstamp_ < 8) stamp_[nstamp_++] = clock64(); } while (0)
+#else
+#define DENS_STAMP() do { } while (0)
+#endif
+  DENS_STAMP();
+  build_occ_list(b, p, slot, &L);
+  const int cnt = L.count;
+  // the list is ordered by spin (density! order: sigma, k, l): orbitals [0, cnt_up) have sigma = 0
+  int cnt_up = cnt;
+  if (SP == 2)
+    for (int o = 0; o < cnt; ++o)
+      if (L.e[o] == 1) { cnt_up = o; break; }
+  // sweeps over the nodes: per spin, 16 orbitals each (at least one: a spin without electrons still writes rho = 0)
+  int nsw[2];
+  nsw[0] = max(1, (cnt_up + 15) >> 4);
+  nsw[1] = SP == 2 ? max(1, (cnt - cnt_up + 15) >> 4) : 0;
+  const int nch = (Q + QC - 1) / QC, nvalid = min(DENS_TC_NC, C - c0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int st = 0; st < ST; ++st) { mbar_init(&full_bar[st], 1); mbar_init(&empty_bar[st], nvalid); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  DENS_STAMP();
+  const bool has_xc = (b.ex[p] != 0) || (b.ec[p] != 0);
+  if (warp == DENS_TC_NC) {   // producer: (nsw[0] + nsw[1]) passes over the table: one bulk copy per chunk image, and in the
+    if (lane == 0) {          // last sweep of a spin the f rows of the four cells (<Vxc[D_prev], D_new>)
+      int it = 0;
+      for (int e = 0; e < SP; ++e)
+        for (int sw = 0; sw < nsw[e]; ++sw)
+          for (int ch = 0; ch < nch; ++ch, ++it) {
+            const int st = it % ST;
+            if (it >= ST) mbar_wait(&empty_bar[st], (uint32_t)(((it - ST) / ST) & 1));
+            const bool wf = has_xc && sw == nsw[e] - 1;
+            const int q0 = ch * QC, len = min(QC, Q - q0);
+            double* dst = Gs + (size_t)st * STAGE;
+            mbar_expect_tx(&full_bar[st], (uint32_t)(POT_IMG_ROWS * QCS * 8 + (wf ? nvalid * len * 8 : 0)));
+            bulk_g2s(dst, d.Pgc + (size_t)ch * POT_IMG_ROWS * QCS, (uint32_t)(POT_IMG_ROWS * QCS * 8), &full_bar[st]);
+            if (wf)
+              for (int u = 0; u < nvalid; ++u)
+                bulk_g2s(dst + POT_IMG_ROWS * QCS + u * QC, b.fxc + ((size_t)(p * SP + e) * C + c0 + u) * Q + q0, (uint32_t)(len * 8),
+                         &full_bar[st]);
+          }
+    }
+    return;
+  }
+  const int c = c0 + warp;
+  if (c >= C) return;
+  const int lr = lane >> 2, lk = lane & 3;
+  const double inv1 = d.inv1[c], inv2 = d.inv2[c];
+  int gi[6];   // global index of the generators 4 ks + lane % 4 of this cell (-1: none)
+#pragma unroll
+  for (int ks = 0; ks < 6; ++ks) gi[ks] = (4 * ks + lk < n) ? d.l2g[c * n + 4 * ks + lk] : -1;
+  double corr = 0.0;
+  int it = 0;   // chunk counter of the stream
+  for (int e = 0; e < SP; ++e) {
+    const int o0 = e == 0 ? 0 : cnt_up, o1 = e == 0 ? cnt_up : cnt;
+    double* out = b.rho_q_new + ((((size_t)p * 2 + slot) * SP + e) * C + c) * Q;
+    for (int sw = 0; sw < nsw[e]; ++sw) {
+      const bool first = sw == 0, last = sw == nsw[e] - 1;
+      // B fragments: us[o][i] = sqrt(n_o) U_o[i], orbital o0 + 16 sw + 8 t + lane / 4, generator 4 ks + lane % 4
+      double ba[6], bb[6];
+      const int oa = o0 + 16 * sw + lr, ob = oa + 8;
+      const bool two = o0 + 16 * sw + 8 < o1;
+      {
+        const double* Ua = oa < o1 ? b.U + orb_off(b, p, L.e[oa], L.l[oa], L.k[oa]) * d.Nh : nullptr;
+        const double* Ub = ob < o1 ? b.U + orb_off(b, p, L.e[ob], L.l[ob], L.k[ob]) * d.Nh : nullptr;
+        const double sa = oa < o1 ? sqrt(L.n[oa]) : 0.0, sb = ob < o1 ? sqrt(L.n[ob]) : 0.0;
+#pragma unroll
+        for (int ks = 0; ks < 6; ++ks) {
+          ba[ks] = (Ua && gi[ks] >= 0) ? Ua[gi[ks]] * sa : 0.0;
+          bb[ks] = (Ub && gi[ks] >= 0) ? Ub[gi[ks]] * sb : 0.0;
+        }
+      }
+      for (int ch = 0; ch < nch; ++ch, ++it) {
+        const int st = it % ST;
+        mbar_wait(&full_bar[st], (uint32_t)((it / ST) & 1));
+        const double* Gb = Gs + (size_t)st * STAGE + lk * QCS + lr;
+        const double* xs = Gs + (size_t)st * STAGE + NR * QCS;                       // nodes of the chunk (image row 24)
+        const double* fs = Gs + (size_t)st * STAGE + POT_IMG_ROWS * QCS + warp * QC;  // f of this warp's cell
+        const int q0 = ch * QC, ngr = min(QC, Q - q0) >> 3;
+        // eight independent DMMA chains per warp (a dependent DMMA waits ~300 cycles for its accumulator: with fewer chains the
+        // kernel is bound by that latency, not by the pipe): one orbital tile -> four node groups at a time, two tiles -> two
+        // groups; the even and the odd steps over the generators of a (group, tile) accumulate apart and are added at the end
+        auto run = [&](auto ng_c, auto nt_c) {
+          constexpr int NG = decltype(ng_c)::value, NTL = decltype(nt_c)::value;
+          for (int gp = 0; gp < ngr; gp += NG) {
+            // lane % 4 = k finishes node lane / 4 of group gp + k
+            const int q = q0 + 8 * (gp + lk) + lr;
+            const bool fin = lk < NG && gp + lk < ngr;
+            double fxv = 0.0, xq = 1.0, prev = 0.0;
+            if (fin) {
+              xq = xs[q - q0];
+              if (has_xc && last) fxv = fs[q - q0];
+              if (!first) prev = out[q];
+            }
+            double acc[NG][NTL][2][2];
+#pragma unroll
+            for (int g = 0; g < NG; ++g)
+#pragma unroll
+              for (int t = 0; t < NTL; ++t) acc[g][t][0][0] = acc[g][t][0][1] = acc[g][t][1][0] = acc[g][t][1][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 6; ++ks)
+#pragma unroll
+              for (int g = 0; g < NG; ++g) {
+                const double av = gp + g < ngr ? Gb[(4 * ks) * QCS + 8 * (gp + g)] : 0.0;
+                dmma_m8n8k4(acc[g][0][ks & 1], av, ba[ks]);
+                if (NTL == 2) dmma_m8n8k4(acc[g][NTL - 1][ks & 1], av, bb[ks]);
+              }
+            double myr = 0.0;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+              double r = 0.0;
+#pragma unroll
+              for (int t = 0; t < NTL; ++t) {
+                const double p0 = acc[g][t][0][0] + acc[g][t][1][0], p1 = acc[g][t][0][1] + acc[g][t][1][1];
+                r += fma(p0, p0, p1 * p1);
+              }
+              r += __shfl_xor_sync(0xffffffffu, r, 1);
+              r += __shfl_xor_sync(0xffffffffu, r, 2);
+              if (lk == g) myr = r;
+            }
+            if (fin) {
+              const double r = myr + prev;
+              if (last) {
+                const double X = inv1 * xq + inv2;
+                out[q] = (r / (X * X)) * c_xc.inv4pi;
+                corr = fma(fxv, r, corr);
+              } else {
+                out[q] = r;   // raw sum of the sweeps so far
+              }
+            }
+          }
+        };
+        if (two) run(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
+        else run(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{});
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+      }
+    }
+  }
+  DENS_STAMP();
+  corr = warp_sum(corr);
+  if (lane == 0) b.corr_part[((size_t)p * 2 + slot) * C + c] = corr * inv1;
+}
+
+// k_fd: the cell's share of the Hartree rhs, B_m = sum_ij F_c[m][ij] D_loc[ij] with D_loc = sum_o n_o u_o u_o^T on the cell
+// (tensor_matrix_dict!, src/utils/free allocation.jl:17-36).  One CTA per cell, slot and FD_NP problems: the (L2-resident)
+// tensor block F_c is read once for all of them.
+#define FD_NP 4
+__host__ __device__ inline size_t fd_smem_bytes(int n) {
+  return sizeof(double) * ((size_t)AKS_MAXORB * DENS_TC_ROWS + (size_t)FD_NP * n * n + 8);
+}
+__global__ void __launch_bounds__(AKS_NT) k_fd(DiscDev d, BatchDev b) {
+  const int c = blockIdx.x, pbase = blockIdx.y * FD_NP, slot = blockIdx.z;
+  __shared__ OccList L;
+  extern __shared__ __align__(16) double sm_dc[];
+  constexpr int NR = DENS_TC_ROWS;
+  const int n = d.n, C = d.C, nn = n * n;
+  double* us = sm_dc;                           // [cnt][24]
+  double* Dl = us + (size_t)AKS_MAXORB * NR;    // [FD_NP][n*n]
+  unsigned mask = 0;
+  for (int pp = 0; pp < FD_NP; ++pp) {
+    const int p = pbase + pp;
+    if (p < b.B && b.status[p] == 0 && (slot == 0 || b.degen[p]) && b.hartree[p] != 0.0) mask |= 1u << pp;
+  }
+  if (!mask) return;
+  for (int pp = 0; pp < FD_NP; ++pp) {
+    if (!((mask >> pp) & 1u)) {
+      for (int idx = threadIdx.x; idx < nn; idx += AKS_NT) Dl[pp * nn + idx] = 0.0;
+      continue;
+    }
+    const int p = pbase + pp;
+    __syncthreads();   // the previous problem's `us` and list are no longer read
+    build_occ_list(b, p, slot, &L);
+    const int cnt = L.count;
+    for (int idx = threadIdx.x; idx < cnt * NR; idx += AKS_NT) {
+      const int o = idx / NR, i = idx - o * NR;
+      double v = 0.0;
+      if (i < n) {
+        const int gi = d.l2g[c * n + i];
+        if (gi >= 0) v = b.U[orb_off(b, p, L.e[o], L.l[o], L.k[o]) * d.Nh + gi];
+      }
+      us[idx] = v * sqrt(L.n[o]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nn; idx += AKS_NT) {
+      const int i = idx / n, j = idx - i * n;
+      double v = 0.0;
+      for (int o = 0; o < cnt; ++o) v = fma(us[(size_t)o * NR + i], us[(size_t)o * NR + j], v);
+      Dl[pp * nn + idx] = v;
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* Fc = d.F_loc + (size_t)c * nn * n;
+  // a warp owns the rows m = warp, warp + 8, warp + 16: they advance together (three loads of F_c in flight per lane
+  // and step, every value used for the four problems)
+  constexpr int MPW = (DENS_TC_ROWS + AKS_NW - 1) / AKS_NW;
+  double acc[MPW][FD_NP];
+#pragma unroll
+  for (int j = 0; j < MPW; ++j)
+#pragma unroll
+    for (int pp = 0; pp < FD_NP; ++pp) acc[j][pp] = 0.0;
+#pragma unroll 2
+  for (int idx = lane; idx < nn; idx += 32) {
+    double dv[FD_NP];
+#pragma unroll
+    for (int pp = 0; pp < FD_NP; ++pp) dv[pp] = Dl[pp * nn + idx];
+#pragma unroll
+    for (int j = 0; j < MPW; ++j) {
+      const int m = warp + AKS_NW * j;
+      if (m < n) {
+        const double fv = Fc[(size_t)m * nn + idx];
+#pragma unroll
+        for (int pp = 0; pp < FD_NP; ++pp) acc[j][pp] = fma(dv[pp], fv, acc[j][pp]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MPW; ++j) {
+    const int m = warp + AKS_NW * j;
+    if (m < n) {   // warp-uniform
+#pragma unroll
+      for (int pp = 0; pp < FD_NP; ++pp) {
+        const double v = warp_sum(acc[j][pp]);
+        if (lane == 0 && ((mask >> pp) & 1u)) b.Bloc_new[(((size_t)(pbase + pp) * 2 + slot) * C + c) * n + m] = v;
       }
     }
   }

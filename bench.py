@@ -138,7 +138,7 @@ def workload_stats(lhs, nhs, states, eig_info):
     n, nb, C, Q, G, Nh = 21, 19, 40, 1000, 1000, 799
     npk = n * (n + 1) // 2
     st = {k: [0.0, 0.0] for k in ("k_xc", "k_potential", "k_potential_tc", "k_hassemble", "k_reduce", "k_eig_init", "k_eig", "k_eig_final", "k_eig_scale",
-                                  "k_aufbau", "k_eig_cert", "k_dens_cells", "k_dens_grid", "k_poisson", "k_linesearch",
+                                  "k_aufbau", "k_eig_cert", "k_dens_cells", "k_dens_cells_tc", "k_fd", "k_dens_grid", "k_poisson", "k_linesearch",
                                   "k_mix_state", "k_mix_dense", "k_finalize")}
     counts, rqi, _ = eig_info
     for i, (lh, nh) in enumerate(zip(lhs, nhs)):
@@ -168,6 +168,11 @@ def workload_stats(lhs, nhs, states, eig_info):
         st["k_eig_cert"][0] += L * 25.0 * nb * C
         st["k_dens_cells"][0] += C * (Q * (2.0 * n + 3.0) * nocc + 2.0 * n * n * nocc + 2.0 * n ** 3)
         st["k_dens_cells"][1] += C * Q * 16.0
+        # default path: orbital values at the nodes on the tensor cores; F:D in its own kernel (F_c read once per 4 problems)
+        st["k_dens_cells_tc"][0] += C * Q * (2.0 * n + 3.0) * nocc
+        st["k_dens_cells_tc"][1] += C * Q * 16.0
+        st["k_fd"][0] += C * (2.0 * n * n * nocc + 2.0 * n ** 3)
+        st["k_fd"][1] += C * n * 8.0 + nocc * Nh * 8.0
         st["k_dens_grid"][0] += G * (2.0 * n + 3.0) * nocc
         st["k_dens_grid"][1] += G * 8.0 + nocc * Nh * 8.0
         st["k_poisson"][0] += 2.0 * C * nb * nb + 8.0 * C * nb
