@@ -926,7 +926,7 @@ static int launch_dens_cells(aks_batch* bt) {
   const dim3 grid(dv.C, bt->cur->B, 2);
   if (ctx->dens_tc && dens_tc_ok(dv.n, dv.Q, dv.Qs)) {
     const BatchDev& bd = bt->cur->dev;
-    const dim3 gtc((dv.C + DENS_TC_NC - 1) / DENS_TC_NC, bt->cur->B, 2);
+    const dim3 gtc((dv.C + DENS_TC_NC - 1) / DENS_TC_NC, bt->cur->B, 1);   // both slots of a degenerate problem in one pass
     if (bd.s == 1) k_dens_cells_tc<1><<<gtc, DENS_TC_NT, dens_tc_smem_bytes(), bt->cur->stream>>>(dv, bd);
     else k_dens_cells_tc<2><<<gtc, DENS_TC_NT, dens_tc_smem_bytes(), bt->cur->stream>>>(dv, bd);
     LAUNCH_CHECK();

@@ -413,25 +413,61 @@ __host__ __device__ inline size_t dens_tc_smem_bytes() {
   return sizeof(double) * ((size_t)DENS_TC_ST * DENS_TC_STAGE + 8);
 }
 template <int SP>   // nspin
-__global__ void __launch_bounds__(DENS_TC_NT, 4) k_dens_cells_tc(DiscDev d, BatchDev b) {
-  const int c0 = blockIdx.x * DENS_TC_NC, p = blockIdx.y, slot = blockIdx.z;
+__global__ void __launch_bounds__(DENS_TC_NT, 3) k_dens_cells_tc(DiscDev d, BatchDev b) {
+  const int c0 = blockIdx.x * DENS_TC_NC, p = blockIdx.y;
   if (b.status[p] != 0) return;
-  if (slot == 1 && !b.degen[p]) return;
-  __shared__ OccList L;
+  const bool degen = b.degen[p] != 0;
+  __shared__ OccList L;                    // union of the orbitals of the two slots; L.n = occupations of slot 0
+  __shared__ double w1s[AKS_MAXORB];       // occupations of slot 1
   __shared__ __align__(8) uint64_t full_bar[DENS_TC_ST], empty_bar[DENS_TC_ST];
   extern __shared__ __align__(16) double sm_dc[];
   constexpr int NR = DENS_TC_ROWS, QCS = DENS_TC_QCS, ST = DENS_TC_ST, QC = DENS_TC_QC;
   const int n = d.n, Q = d.Q, C = d.C;
   double* Gs = sm_dc;                                   // [ST][25 x 68 image | 4 x 64 f]
   constexpr int STAGE = DENS_TC_STAGE;
-#ifdef AKS_DENS_TIMING   // cycle stamps of thread 0 (tools/gpu_dens_cycles.py); problems 0..63, slot 0
+#ifdef AKS_DENS_TIMING   // cycle stamps of thread 0 (tools/gpu_dens_cycles.py); problems 0..63
   long long* stamp_ = b.eig_dbg + ((size_t)p * gridDim.x + blockIdx.x) * 8; int nstamp_ = 0;
-#define DENS_STAMP() do { if (threadIdx.x == 0 && p < 64 && slot == 0 && nstamp_ < 8) stamp_[nstamp_++] = clock64(); } while (0)
+#define DENS_STAMP() do { if (threadIdx.x == 0 && p < 64 && nstamp_ < 8) stamp_[nstamp_++] = clock64(); } while (0)
 #else
 #define DENS_STAMP() do { } while (0)
 #endif
   DENS_STAMP();
-  build_occ_list(b, p, slot, &L);
+  // Both trial densities of a two-fold degenerate problem (slots 0 and 1: the two fillings of the degenerate pair,
+  // optimized.jl:205-262) come out of ONE pass: psi_o(q) is computed once, rho_slot = sum_o n_o^slot psi_o^2.
+  build_occ_list(b, p, 0, &L);
+  if (degen) {
+    if (threadIdx.x == 0) {
+      int cnt = L.count;
+      for (int o = 0; o < cnt; ++o) w1s[o] = 0.0;
+      const int cnt1 = b.occ_cnt[2 * p + 1];
+      const int* elk1 = b.occ_elk + ((size_t)p * 2 + 1) * AKS_MAXORB;
+      const double* n1 = b.occ_n + ((size_t)p * 2 + 1) * AKS_MAXORB;
+      bool appended = false;
+      for (int j = 0; j < cnt1; ++j) {
+        const int v = elk1[j];
+        int o = 0;
+        while (o < cnt && ((L.e[o] << 16) | (L.l[o] << 8) | L.k[o]) != v) ++o;
+        if (o == cnt && cnt < AKS_MAXORB) {
+          L.e[o] = v >> 16; L.l[o] = (v >> 8) & 0xff; L.k[o] = v & 0xff; L.n[o] = 0.0;
+          ++cnt; appended = true;
+        }
+        if (o < AKS_MAXORB) w1s[o] = n1[j];
+      }
+      if (SP == 2 && appended)   // keep the list ordered by spin (stable insertion sort on sigma)
+        for (int i = 1; i < cnt; ++i)
+          for (int j = i; j > 0 && L.e[j - 1] > L.e[j]; --j) {
+            int t;
+            double tn;
+            t = L.e[j]; L.e[j] = L.e[j - 1]; L.e[j - 1] = t;
+            t = L.l[j]; L.l[j] = L.l[j - 1]; L.l[j - 1] = t;
+            t = L.k[j]; L.k[j] = L.k[j - 1]; L.k[j - 1] = t;
+            tn = L.n[j]; L.n[j] = L.n[j - 1]; L.n[j - 1] = tn;
+            tn = w1s[j]; w1s[j] = w1s[j - 1]; w1s[j - 1] = tn;
+          }
+      L.count = cnt;
+    }
+    __syncthreads();
+  }
   const int cnt = L.count;
   // the list is ordered by spin (density! order: sigma, k, l): orbitals [0, cnt_up) have sigma = 0
   int cnt_up = cnt;
@@ -480,27 +516,37 @@ __global__ void __launch_bounds__(DENS_TC_NT, 4) k_dens_cells_tc(DiscDev d, Batc
   int gi[6];   // global index of the generators 4 ks + lane % 4 of this cell (-1: none)
 #pragma unroll
   for (int ks = 0; ks < 6; ++ks) gi[ks] = (4 * ks + lk < n) ? d.l2g[c * n + 4 * ks + lk] : -1;
-  double corr = 0.0;
+  double corr0 = 0.0, corr1 = 0.0;
   int it = 0;   // chunk counter of the stream
   for (int e = 0; e < SP; ++e) {
     const int o0 = e == 0 ? 0 : cnt_up, o1 = e == 0 ? cnt_up : cnt;
-    double* out = b.rho_q_new + ((((size_t)p * 2 + slot) * SP + e) * C + c) * Q;
+    double* out0 = b.rho_q_new + ((((size_t)p * 2 + 0) * SP + e) * C + c) * Q;
+    double* out1 = b.rho_q_new + ((((size_t)p * 2 + 1) * SP + e) * C + c) * Q;
     for (int sw = 0; sw < nsw[e]; ++sw) {
       const bool first = sw == 0, last = sw == nsw[e] - 1;
-      // B fragments: us[o][i] = sqrt(n_o) U_o[i], orbital o0 + 16 sw + 8 t + lane / 4, generator 4 ks + lane % 4
+      // B fragments: U_o[i], orbital o0 + 16 sw + 8 t + lane / 4, generator 4 ks + lane % 4
       double ba[6], bb[6];
       const int oa = o0 + 16 * sw + lr, ob = oa + 8;
       const bool two = o0 + 16 * sw + 8 < o1;
       {
         const double* Ua = oa < o1 ? b.U + orb_off(b, p, L.e[oa], L.l[oa], L.k[oa]) * d.Nh : nullptr;
         const double* Ub = ob < o1 ? b.U + orb_off(b, p, L.e[ob], L.l[ob], L.k[ob]) * d.Nh : nullptr;
-        const double sa = oa < o1 ? sqrt(L.n[oa]) : 0.0, sb = ob < o1 ? sqrt(L.n[ob]) : 0.0;
 #pragma unroll
         for (int ks = 0; ks < 6; ++ks) {
-          ba[ks] = (Ua && gi[ks] >= 0) ? Ua[gi[ks]] * sa : 0.0;
-          bb[ks] = (Ub && gi[ks] >= 0) ? Ub[gi[ks]] * sb : 0.0;
+          ba[ks] = (Ua && gi[ks] >= 0) ? Ua[gi[ks]] : 0.0;
+          bb[ks] = (Ub && gi[ks] >= 0) ? Ub[gi[ks]] : 0.0;
         }
       }
+      // occupations of the orbitals whose values this lane ends up with (columns 2 (lane % 4) + {0, 1} of the two tiles)
+      double w0[2][2], w1[2][2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int o = o0 + 16 * sw + 8 * t + 2 * lk + j;
+          w0[t][j] = o < o1 ? L.n[o] : 0.0;
+          w1[t][j] = (degen && o < o1) ? w1s[o] : 0.0;
+        }
       for (int ch = 0; ch < nch; ++ch, ++it) {
         const int st = it % ST;
         mbar_wait(&full_bar[st], (uint32_t)((it / ST) & 1));
@@ -508,21 +554,12 @@ __global__ void __launch_bounds__(DENS_TC_NT, 4) k_dens_cells_tc(DiscDev d, Batc
         const double* xs = Gs + (size_t)st * STAGE + NR * QCS;                       // nodes of the chunk (image row 24)
         const double* fs = Gs + (size_t)st * STAGE + POT_IMG_ROWS * QCS + warp * QC;  // f of this warp's cell
         const int q0 = ch * QC, ngr = min(QC, Q - q0) >> 3;
-        // eight independent DMMA chains per warp (a dependent DMMA waits ~300 cycles for its accumulator: with fewer chains the
-        // kernel is bound by that latency, not by the pipe): one orbital tile -> four node groups at a time, two tiles -> two
+        // sixteen independent DMMA chains per warp (a dependent DMMA waits ~300 cycles for its accumulator: with few chains the
+        // kernel is bound by that latency, not by the pipe): one orbital tile -> eight node groups at a time, two tiles -> four
         // groups; the even and the odd steps over the generators of a (group, tile) accumulate apart and are added at the end
         auto run = [&](auto ng_c, auto nt_c) {
-          constexpr int NG = decltype(ng_c)::value, NTL = decltype(nt_c)::value;
+          constexpr int NG = decltype(ng_c)::value, NTL = decltype(nt_c)::value, NH = (NG + 3) / 4;
           for (int gp = 0; gp < ngr; gp += NG) {
-            // lane % 4 = k finishes node lane / 4 of group gp + k
-            const int q = q0 + 8 * (gp + lk) + lr;
-            const bool fin = lk < NG && gp + lk < ngr;
-            double fxv = 0.0, xq = 1.0, prev = 0.0;
-            if (fin) {
-              xq = xs[q - q0];
-              if (has_xc && last) fxv = fs[q - q0];
-              if (!first) prev = out[q];
-            }
             double acc[NG][NTL][2][2];
 #pragma unroll
             for (int g = 0; g < NG; ++g)
@@ -536,41 +573,62 @@ __global__ void __launch_bounds__(DENS_TC_NT, 4) k_dens_cells_tc(DiscDev d, Batc
                 dmma_m8n8k4(acc[g][0][ks & 1], av, ba[ks]);
                 if (NTL == 2) dmma_m8n8k4(acc[g][NTL - 1][ks & 1], av, bb[ks]);
               }
-            double myr = 0.0;
+            // lane % 4 = k finishes node lane / 4 of the groups gp + k (+ 4)
+            double my0[NH], my1[NH];
+#pragma unroll
+            for (int h = 0; h < NH; ++h) my0[h] = my1[h] = 0.0;
 #pragma unroll
             for (int g = 0; g < NG; ++g) {
-              double r = 0.0;
+              double r0 = 0.0, r1 = 0.0;
 #pragma unroll
               for (int t = 0; t < NTL; ++t) {
                 const double p0 = acc[g][t][0][0] + acc[g][t][1][0], p1 = acc[g][t][0][1] + acc[g][t][1][1];
-                r += fma(p0, p0, p1 * p1);
+                const double s0 = p0 * p0, s1 = p1 * p1;
+                r0 = fma(w0[t][0], s0, fma(w0[t][1], s1, r0));
+                r1 = fma(w1[t][0], s0, fma(w1[t][1], s1, r1));
               }
-              r += __shfl_xor_sync(0xffffffffu, r, 1);
-              r += __shfl_xor_sync(0xffffffffu, r, 2);
-              if (lk == g) myr = r;
+              r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+              r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+              if (lk == (g & 3)) my0[g >> 2] = r0;
+              if (degen) {
+                r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+                r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+                if (lk == (g & 3)) my1[g >> 2] = r1;
+              }
             }
-            if (fin) {
-              const double r = myr + prev;
-              if (last) {
-                const double X = inv1 * xq + inv2;
-                out[q] = (r / (X * X)) * c_xc.inv4pi;
-                corr = fma(fxv, r, corr);
-              } else {
-                out[q] = r;   // raw sum of the sweeps so far
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              const int gq = gp + lk + 4 * h, j = 8 * gq + lr, q = q0 + j;
+              if (lk + 4 * h < NG && gq < ngr) {
+                const double X = inv1 * xs[j] + inv2;
+                const double sc = c_xc.inv4pi / (X * X);
+                const double fxv = (has_xc && last) ? fs[j] : 0.0;
+                double r = my0[h] + (first ? 0.0 : out0[q]);
+                out0[q] = last ? r * sc : r;          // not last: raw sum of the sweeps so far
+                corr0 = fma(fxv, r, corr0);
+                if (degen) {
+                  r = my1[h] + (first ? 0.0 : out1[q]);
+                  out1[q] = last ? r * sc : r;
+                  corr1 = fma(fxv, r, corr1);
+                }
               }
             }
           }
         };
-        if (two) run(std::integral_constant<int, 2>{}, std::integral_constant<int, 2>{});
-        else run(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{});
+        if (two) run(std::integral_constant<int, 4>{}, std::integral_constant<int, 2>{});
+        else run(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[st]);
       }
     }
   }
   DENS_STAMP();
-  corr = warp_sum(corr);
-  if (lane == 0) b.corr_part[((size_t)p * 2 + slot) * C + c] = corr * inv1;
+  corr0 = warp_sum(corr0);
+  corr1 = warp_sum(corr1);
+  if (lane == 0) {
+    b.corr_part[((size_t)p * 2 + 0) * C + c] = corr0 * inv1;
+    if (degen) b.corr_part[((size_t)p * 2 + 1) * C + c] = corr1 * inv1;
+  }
 }
 
 // k_fd: the cell's share of the Hartree rhs, B_m = sum_ij F_c[m][ij] D_loc[ij] with D_loc = sum_o n_o u_o u_o^T on the cell
