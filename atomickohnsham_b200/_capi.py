@@ -57,7 +57,7 @@ EXPORTS = ["aks_ctx_create", "aks_ctx_destroy", "aks_last_error", "aks_ctx_strea
            "aks_disc_create", "aks_disc_destroy", "aks_batch_create", "aks_batch_destroy",
            "aks_batch_set_oda", "aks_batch_set_oda_problem", "aks_batch_set_aufbau", "aks_batch_set_eig_window", "aks_batch_reset", "aks_scf_step", "aks_scf_run", "aks_get_state", "aks_get_state_all",
            "aks_set_density", "aks_assemble_hartree", "aks_assemble_vxc", "aks_eig_lowest",
-           "aks_density", "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak", "aks_measure_dmma_peak",
+           "aks_density", "aks_eval_grid", "aks_exc_energy", "aks_hartree_energy", "aks_launch_count", "aks_measure_fp64_peak", "aks_measure_dmma_peak",
            "aks_last_phase_ms", "aks_last_kernel_ms", "aks_debug_eig_info", "aks_debug_eig_cycles", "aks_debug_eig_refills",
            "aks_get_records_dd", "aks_dd_xc_eval", "aks_dd_gauss_legendre", "aks_dd_build_operators"]
 
@@ -98,6 +98,7 @@ def _load():
     lib.aks_density.argtypes = [vp, C.c_int32, _dp]
     lib.aks_assemble_vxc.argtypes = [vp, C.c_int32, _dp]
     lib.aks_eig_lowest.argtypes = [vp, C.c_int32, _dp, _dp, _dp]
+    lib.aks_eval_grid.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _dp, _dp]
     lib.aks_exc_energy.argtypes = [vp, C.c_int32, _dp]
     lib.aks_hartree_energy.argtypes = [vp, C.c_int32, _dp]
     lib.aks_launch_count.argtypes = [vp]

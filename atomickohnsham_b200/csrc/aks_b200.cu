@@ -1547,6 +1547,33 @@ extern "C" int aks_density(aks_batch* bt, int32_t prob, double* D) {
   return AKS_OK;
 }
 
+extern "C" int aks_eval_grid(aks_batch* bt, int32_t prob, int32_t kind, int32_t l, int32_t k, int32_t sigma, int64_t npts,
+                             const double* x, double* out) {
+  if (!bt || prob < 0 || prob >= bt->B || npts < 0 || (npts > 0 && (!x || !out))) return AKS_EINVAL;
+  GUARD(bt->disc->ctx);
+  DD_UNSUPPORTED(bt, "aks_eval_grid");
+  aks_ctx* ctx = bt->disc->ctx;
+  const DiscDev& dv = bt->disc->dev;
+  const BatchDev& b = bt->dev;
+  if (kind < 0 || kind > 5 || dv.n > EVAL_NMAX) { ctx->err = "aks_eval_grid: unknown kind (0..5) or order above 31"; return AKS_EINVAL; }
+  if ((kind == 0 || kind == 5) && (l < 0 || l >= b.Lmax || k < 0 || k >= b.nhmax || sigma < 0 || sigma >= b.s)) {
+    ctx->err = "aks_eval_grid: orbital (l, k, sigma) outside the batch"; return AKS_EINVAL;
+  }
+  if ((kind == 3 || kind == 4) && (sigma < 0 || sigma >= b.s)) { ctx->err = "aks_eval_grid: sigma outside 0..nspin-1"; return AKS_EINVAL; }
+  if (kind == 1 && sigma >= b.s) { ctx->err = "aks_eval_grid: sigma outside -1..nspin-1"; return AKS_EINVAL; }
+  if (npts == 0) return AKS_OK;
+  enter_main(bt);
+  double* dbuf = nullptr;
+  CK(cudaMallocAsync((void**)&dbuf, sizeof(double) * 2 * (size_t)npts, ctx->stream));
+  CK(cudaMemcpyAsync(dbuf, x, sizeof(double) * (size_t)npts, cudaMemcpyHostToDevice, ctx->stream));
+  k_eval_grid<<<(unsigned)((npts + 127) / 128), 128, 0, ctx->stream>>>(dv, b, prob, kind, l, k, sigma, (long long)npts, dbuf, dbuf + npts);
+  LAUNCH_CHECK();
+  CK(cudaMemcpyAsync(out, dbuf + npts, sizeof(double) * (size_t)npts, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaFreeAsync(dbuf, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return AKS_OK;
+}
+
 extern "C" int aks_exc_energy(aks_batch* bt, int32_t prob, double* Exc) {
   if (!bt || prob < 0 || prob >= bt->B || !Exc) return AKS_EINVAL;
   GUARD(bt->disc->ctx);

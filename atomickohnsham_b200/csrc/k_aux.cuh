@@ -195,3 +195,98 @@ __global__ void k_dmma_peak(double* out, int iters) {
   for (int t = 0; t < 8; ++t) s += c[t][0] + c[t][1];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+
+// ------------------------------------------------------------------------------------------
+// k_eval_grid: the solution of one problem on arbitrary radial points (post-processing on the device),
+// straight from the device state D, U, W -- nothing is copied to the host but the values asked for.
+//   kind 0  u_{k,l,sigma}(x) / x            eval_orbital             src/solution/postprocess.jl:34-62
+//   kind 5  u_{k,l,sigma}(x)                the H^1_0 function itself (h10 = true)
+//   kind 1  rho_sigma(x) (c = -1: spin sum) eval_density             postprocess.jl:81-182:  g^T D_loc g / (4 pi x^2)
+//   kind 2  W(x) / x + N / Rmax             eval_hartree             postprocess.jl:207-222
+//   kind 3  v_xc,sigma[rho](x)              eval_vxc                 postprocess.jl:328-352
+//   kind 4  -Z/x + l(l+1)/(2x^2) + hartree V_H + v_xc   eval_effective_potential   postprocess.jl:378-387
+// One thread per point: cell by bisection on the cell boundaries (findindex, src/fem/mesh.jl:64-75: right-owning at interior
+// nodes, the last node belongs to the last cell, 0 outside), generators by the Legendre three-term recurrence
+// (src/fem/generators.jl:79-138: 1 + xi, 1 - xi, (P_{k+1} - P_{k-1}) / (2k + 1)).  Only the lower triangle of D is kept
+// current during the iterations (k_mix_dense): D is read symmetrically.
+#define EVAL_NMAX 32
+__global__ void __launch_bounds__(128) k_eval_grid(DiscDev d, BatchDev b, int p, int kind, int qa, int qb, int qc,
+                                                   long long npts, const double* __restrict__ xs, double* __restrict__ out) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npts) return;
+  const double x = xs[t];
+  const int n = d.n, C = d.C, Nh = d.Nh, s = b.s;
+  // cell: last c with lower boundary <= x
+  int c = -1;
+  if (x >= d.inv2[0] - d.inv1[0] && x <= d.Rmax) {
+    int lo = 0, hi = C - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (d.inv2[mid] - d.inv1[mid] <= x) lo = mid; else hi = mid - 1;
+    }
+    c = lo;
+  }
+  double g[EVAL_NMAX];
+  int gi[EVAL_NMAX];
+  if (c >= 0) {
+    const double xi = (x - d.inv2[c]) / d.inv1[c];
+    g[0] = 1.0 + xi;
+    g[1] = 1.0 - xi;
+    double pm = 1.0, pk = xi;   // P_{k-1}, P_k
+    for (int k = 1; k + 1 < n; ++k) {
+      const double pn = ((2.0 * k + 1.0) * xi * pk - (double)k * pm) / (double)(k + 1);
+      g[k + 1] = (pn - pm) / (2.0 * k + 1.0);
+      pm = pk; pk = pn;
+    }
+    for (int i = 0; i < n; ++i) gi[i] = d.l2g[c * n + i];
+  }
+  auto fem = [&](const double* coef) {   // sum_i coef[global(i)] g_i(x)
+    double v = 0.0;
+    if (c >= 0)
+      for (int i = 0; i < n; ++i)
+        if (gi[i] >= 0) v = fma(coef[gi[i]], g[i], v);
+    return v;
+  };
+  auto dens = [&](int e) {   // rho_e(x)
+    double acc = 0.0;
+    if (c >= 0) {
+      const double* D = b.Dd + ((size_t)p * s + e) * Nh * Nh;
+      for (int i = 0; i < n; ++i) {
+        if (gi[i] < 0) continue;
+        double row = 0.0;
+        for (int j = 0; j < n; ++j) {
+          if (gi[j] < 0) continue;
+          const int r = gi[i] >= gi[j] ? gi[i] : gi[j], cc = gi[i] >= gi[j] ? gi[j] : gi[i];
+          row = fma(D[(size_t)r * Nh + cc], g[j], row);
+        }
+        acc = fma(g[i], row, acc);
+      }
+    }
+    return acc / (c_xc.fourpi * x * x);
+  };
+  auto hartree = [&]() {
+    const double bd = b.N[p] / d.Rmax;
+    return b.hartree[p] == 0.0 ? bd : fem(b.Wv + (size_t)p * Nh) / x + bd;
+  };
+  auto vxc = [&](int e) {
+    const int ex = b.ex[p], ec = b.ec[p];
+    if (ex == 0 && ec == 0) return 0.0;
+    if (s == 1) return xc_vrho_unpol(fmax(dens(0), 0.0), ex, ec);
+    double vu, vd;
+    xc_vrho_pol(fmax(dens(0), 0.0), fmax(dens(1), 0.0), ex, ec, vu, vd);
+    return e == 0 ? vu : vd;
+  };
+  double v = 0.0;
+  switch (kind) {
+    case 0: v = fem(b.U + orb_off(b, p, qc, qa, qb) * Nh) / x; break;
+    case 5: v = fem(b.U + orb_off(b, p, qc, qa, qb) * Nh); break;
+    case 1: v = qc < 0 ? (s == 2 ? dens(0) + dens(1) : dens(0)) : dens(qc); break;
+    case 2: v = hartree(); break;
+    case 3: v = vxc(qc); break;
+    default: {
+      const double l = (double)qa;
+      v = -b.Z[p] / x + l * (l + 1.0) / (2.0 * x * x) + b.hartree[p] * hartree() + vxc(qc);
+    }
+  }
+  out[t] = v;
+}

@@ -315,6 +315,43 @@ class Batch:
         return (eps.reshape((L, nh, s), order="F"), np.transpose(U, (3, 2, 1, 0)),
                 res.reshape((L, nh, s), order="F"))
 
+    # --- post-processing on the device (src/solution/postprocess.jl:34-387; host mirror: postprocess.py) -----------------
+    def _eval_grid(self, prob, kind, X, l=0, k=0, sigma=0):
+        X = np.ascontiguousarray(np.atleast_1d(np.asarray(X, dtype=np.float64)))
+        out = np.zeros(X.shape[0])
+        self.ctx.check(_capi.lib.aks_eval_grid(self.h, int(prob), int(kind), int(l), int(k), int(sigma), X.shape[0],
+                                                _capi.dptr(X), _capi.dptr(out)))
+        return out
+
+    def eval_orbital(self, prob, n, l, X, sigma=None, *, h10=False):
+        """u_{nl}(r)/r (or u itself, h10=True) of problem `prob` on X, from the device state (`eval_orbital`,
+        postprocess.jl:34-62; n is the principal quantum number, sigma 1 or 2 for spin-polarised batches)."""
+        if not 0 <= l <= n - 1:
+            raise ValueError("Wrong number quantum. You should have 0 <= l <= n-1.")
+        if self.disc.nspin == 2 and sigma is None:
+            raise ValueError("The discretization is spin-polarized. Please give a spin sigma.")
+        return self._eval_grid(prob, 5 if h10 else 0, X, l=l, k=n - l - 1, sigma=(sigma or 1) - 1)
+
+    def eval_density(self, prob, X, sigma=None):
+        """rho(X) = phi^T D phi / (4 pi X^2), spin-summed unless sigma (1 or 2) is given (`eval_density`, postprocess.jl:81-182)."""
+        return self._eval_grid(prob, 1, X, sigma=-1 if sigma is None else sigma - 1)
+
+    def eval_hartree(self, prob, X):
+        """V_H(X) = W(X)/X + N/Rmax (`eval_hartree`, postprocess.jl:207-222)."""
+        return self._eval_grid(prob, 2, X)
+
+    def eval_vxc(self, prob, X, sigma=None):
+        """v_xc[rho](X) of the problem's builtin LDA functionals (`eval_vxc`, postprocess.jl:328-352)."""
+        if self.disc.nspin == 2 and sigma is None:
+            raise ValueError("The discretization is spin-polarized. Please give a spin sigma.")
+        return self._eval_grid(prob, 3, X, sigma=(sigma or 1) - 1)
+
+    def eval_effective_potential(self, prob, l, X, sigma=None):
+        """-Z/r + l(l+1)/(2r^2) + hartree V_H + v_xc (`eval_effective_potential`, postprocess.jl:378-387)."""
+        if self.disc.nspin == 2 and sigma is None:
+            raise ValueError("The discretization is spin-polarized. Please give a spin sigma.")
+        return self._eval_grid(prob, 4, X, l=l, sigma=(sigma or 1) - 1)
+
     def exc_energy(self, prob=0):
         v = C.c_double()
         self.ctx.check(_capi.lib.aks_exc_energy(self.h, prob, C.byref(v)))

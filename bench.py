@@ -365,7 +365,13 @@ def b200_arm(args):
                 "traffic": top["traffic"], "kernel_ms": top["ms"], "share_of_step": top["share_of_step"],
                 "algorithmic_per_launch": top["algorithmic_flops"] if use_f else top["algorithmic_bytes"],
                 "note": "dominant kernel of the step (largest device time, one stream); `kernels` lists EVERY kernel of the "
-                        "step with its algorithmic flops and HBM bytes per launch (DESIGN.md section 5) against both peaks",
+                        "step with its algorithmic flops and HBM bytes per launch (DESIGN.md section 5) against both peaks. "
+                        "k_eig is counted on the work this design does (certified Rayleigh-quotient iteration on per-cell "
+                        "tridiagonal forms: sequential pivots, latency bound); by SURVEY 8(d)'s W_eig = L s 12 Nh^2 b (banded "
+                        "two-stage reduction) the eigensolve phase would read `eigensolve_phase_by_survey_W_eig` TFLOP/s",
+                "eigensolve_phase_by_survey_W_eig": {
+                    "tflops": sum((lh_ + 1) * 12.0 * 799.0 ** 2 * 39.0 for lh_ in lhs) / (phases["eigensolve"] * 1e-3) / 1e12,
+                    "phase_ms": phases["eigensolve"]},
                 "peak_source": {"fp64": "aks_measure_fp64_peak (register-resident DFMA chains, same run); MEASURED_PEAKS.json "
                                         "has no FP64 figure", "hbm": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650"},
                 "fp64_peak_tflops": fp64_peak, "hbm_peak_gbs": hbm_peak,

@@ -202,6 +202,18 @@ int aks_get_state_all(aks_batch* batch, double* eps, double* n, double* W);
 int aks_set_density(aks_batch* batch, int32_t prob, const double* D, const double* energies_prev,
                     int32_t niter);
 
+/* Post-processing on the device (src/solution/postprocess.jl:34-387): the solution of problem `prob`
+ * evaluated at npts radial points x (host array) straight from the device state, written to out (host array).
+ *   kind 0  u_{k,l,sigma}(x)/x   eval_orbital (l, k = radial index 0.., sigma = 0 / 1)       postprocess.jl:34-62
+ *   kind 5  u_{k,l,sigma}(x)     the H^1_0 function itself
+ *   kind 1  rho_sigma(x)         eval_density (sigma = -1: spin-summed)                      postprocess.jl:81-182
+ *   kind 2  V_H(x) = W(x)/x + N/Rmax                eval_hartree                             postprocess.jl:207-222
+ *   kind 3  v_xc,sigma(x)        eval_vxc (builtin LDA functionals of the problem)           postprocess.jl:328-352
+ *   kind 4  -Z/x + l(l+1)/(2x^2) + hartree V_H + v_xc   eval_effective_potential             postprocess.jl:378-387
+ * Points outside [0, Rmax] give the value of a vanishing solution.  Float64 batches only (AKS_ENOSYS for Double64). */
+int aks_eval_grid(aks_batch* batch, int32_t prob, int32_t kind, int32_t l, int32_t k, int32_t sigma, int64_t npts,
+                  const double* x, double* out);
+
 /* ---- step-level hooks (same device code as aks_scf_step; used by the parity tests) ------ */
 /* assemble_hartree!  (assemble.jl:63-83):   Har (Nh,Nh) of the problem's current D        */
 int aks_assemble_hartree(aks_batch* batch, int32_t prob, double* Har);

@@ -371,3 +371,58 @@ def test_maximum_ionization_against_the_oracle_bisection():
         want[z] = round(mid, precision)   # process.jl:85
     assert got == want, (got, want)
     print("[maximum ionization vs oracle bisection]", got)
+
+
+def test_postprocessing_on_the_device_matches_the_host_mirror():
+    """SURVEY 8(f) rank 4 (src/solution/postprocess.jl:34-387): `aks_eval_grid` evaluates orbitals, density, Hartree and XC
+    potentials and the effective potential on arbitrary radial points straight from the device state (D, U, W), against
+    the host mirror `postprocess.py` fed with the arrays `aks_get_state` returns -- 1e-11 relative to the largest value of
+    each curve (the device evaluates the generators by the double recurrence, the host in extended precision; D enters
+    with cancellation between its entries).  One closed-shell LDA atom on the order-20 discretization and one LSDA atom."""
+    import atomickohnsham_b200 as aks
+    from atomickohnsham_b200 import postprocess as pp
+    from atomickohnsham_b200.solver import Batch, _solution
+    from helpers import package_tables
+    X = np.concatenate([np.geomspace(1e-4, 250.0, 301), [0.5, 1.0, 299.0, 300.0, 301.0]])
+
+    def check(name, dev, host):
+        ok = np.isfinite(host)
+        scale = np.max(np.abs(host[ok]))
+        assert np.max(np.abs(dev[ok] - host[ok])) <= 1e-11 * scale, (name, np.max(np.abs(dev[ok] - host[ok])) / scale)
+
+    # (a) Neon, LDA, order 20
+    basis, ops, quad = package_tables(["exp", 0, 300, 41, 1.5], 20, 1000)
+    disc = aks.KSEDiscretization(basis, None, lh=1, nh=4, nspin=1, fem_integration_method=quad, femops=ops)
+    bt = Batch([aks.LDA(Z=10, N=10)], disc, aks.ODA(scftol=1e-10, tinit=0.6))
+    final, _ = bt.run(60)
+    sol = _solution(bt, 0, final[0])
+    for (n, l) in ((1, 0), (2, 0), (2, 1)):
+        check(f"orbital {n}{l}", bt.eval_orbital(0, n, l, X), pp.eval_orbital(sol, n, l, X))
+        check(f"orbital {n}{l} h10", bt.eval_orbital(0, n, l, X, h10=True), pp.eval_orbital(sol, n, l, X, h10=True))
+    check("density", bt.eval_density(0, X), pp.eval_density(sol, X))
+    check("hartree", bt.eval_hartree(0, X), pp.eval_hartree(sol, X))
+    check("vxc", bt.eval_vxc(0, X), pp.eval_vxc(sol, X))
+    check("veff l=1", bt.eval_effective_potential(0, 1, X), pp.eval_effective_potential(sol, 1, X))
+    assert bt.eval_density(0, np.array([301.0]))[0] == 0.0   # outside the mesh
+    # 4 pi int rho r^2 dr = N on a fine grid (trapezoid on the log grid)
+    r = np.geomspace(1e-6, 300.0, 20001)
+    rho = bt.eval_density(0, r)
+    assert abs(np.trapezoid(4 * np.pi * rho * r ** 3, np.log(r)) - 10.0) < 1e-5
+    bt.close()
+    # (b) Lithium, LSDA, order 10
+    basis, ops, quad = package_tables(["exp", 0, 100, 30, 1.4], 10, 200)
+    disc = aks.KSEDiscretization(basis, None, lh=0, nh=3, nspin=2, fem_integration_method=quad, femops=ops)
+    bt = Batch([aks.KSEModel(Z=3, N=3, ex=aks.BuiltinFunctional("lda_x", 2), ec=aks.BuiltinFunctional("lda_c_pw", 2))],
+               disc, aks.ODA(scftol=1e-9, tinit=0.6))
+    final, _ = bt.run(80)
+    sol = _solution(bt, 0, final[0])
+    Xs = X[X <= 100.0]
+    for sg in (1, 2):
+        check(f"orbital 1s sigma {sg}", bt.eval_orbital(0, 1, 0, Xs, sigma=sg), pp.eval_orbital(sol, 1, 0, Xs, sigma=sg))
+        check(f"density sigma {sg}", bt.eval_density(0, Xs, sigma=sg), pp.eval_density(sol, Xs, sigma=sg))
+        check(f"vxc sigma {sg}", bt.eval_vxc(0, Xs, sigma=sg), pp.eval_vxc(sol, Xs, sigma=sg))
+        check(f"veff sigma {sg}", bt.eval_effective_potential(0, 0, Xs, sigma=sg), pp.eval_effective_potential(sol, 0, Xs, sigma=sg))
+    check("density sum", bt.eval_density(0, Xs), pp.eval_density(sol, Xs))
+    with pytest.raises(ValueError):
+        bt.eval_vxc(0, Xs)
+    bt.close()

@@ -38,6 +38,10 @@ with open(out_csv, "w") as f:
     for name, r in last.items():
         st = sorted(((float(r[col[n]]), n.split("stalled_")[1].split("_per_")[0]) for n in stall if r[col[n]] not in ("", "n/a")), reverse=True)[:4]
         f.write('"%s",' % name + ",".join("%g" % num(r, n) for n in want) + "," + " ".join("%s=%.2f" % (b, a) for a, b in st) + "\n")
-traffic = {name: num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum") for name, r in last.items()}
+traffic = {"source": out_csv + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, 86 atoms, one lane)"}
+for name, r in last.items():
+    rd, wr = num(r, "dram__bytes_read.sum"), num(r, "dram__bytes_write.sum")
+    traffic[re.sub(r"<.*", "", name)] = {"dram_bytes_per_launch": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
+                                         "ncu_duration_us": num(r, "gpu__time_duration.sum")}
 json.dump(traffic, open(out_json, "w"), indent=1)
 print("wrote", out_csv, out_json, len(last), "kernels")
