@@ -36,6 +36,8 @@ struct aks_ctx {
   std::vector<cudaStream_t> stream_free;
   std::vector<cudaEvent_t> event_free;
   int check_every = 4;    // aks_scf_run reads the status words every this many steps (AKS_CHECK_EVERY)
+  bool mix_pipe = false;  // AKS_MIX_PIPE=1: dense mixing by persistent CTAs with a cp.async double buffer (measured slower)
+  int sm_count = 148;
   bool dens_tc = true;    // cell densities by k_dens_cells_tc + k_fd (FP64 tensor cores; orders p <= 23) -- AKS_DENS_TC=0: k_dens_cells
   bool pot_tc = true;     // potential blocks by k_potential_tc (FP64 tensor cores; orders p <= 23) -- AKS_POTENTIAL_TC=0: k_potential
   bool use_graphs = true; // the step sequence of a lane is captured once and replayed as a CUDA graph (AKS_NO_GRAPH=1: off)
@@ -180,7 +182,7 @@ static int set_kernel_attributes(aks_ctx* ctx) {
     CK(cudaFuncGetAttributes(&fa_, fn));                                                                      \
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa_.sharedSizeBytes)); \
   } while (0)
-  SMEM_MAX((k_potential<1, 4>)); SMEM_MAX((k_potential<2, 2>)); SMEM_MAX(k_potential_tc); SMEM_MAX(k_hassemble); SMEM_MAX(k_dens_cells_tc<1>); SMEM_MAX(k_dens_cells_tc<2>); SMEM_MAX(k_fd);
+  SMEM_MAX((k_potential<1, 4>)); SMEM_MAX((k_potential<2, 2>)); SMEM_MAX(k_potential_tc); SMEM_MAX(k_hassemble); SMEM_MAX(k_mix_dense_pipe); SMEM_MAX(k_dens_cells_tc<1>); SMEM_MAX(k_dens_cells_tc<2>); SMEM_MAX(k_fd);
   SMEM_MAX(k_eig); SMEM_MAX(k_eig_cert);
   SMEM_MAX(k_reduce<8>); SMEM_MAX(k_reduce<12>); SMEM_MAX(k_reduce<20>); SMEM_MAX(k_reduce<28>);
   SMEM_MAX(k_eig_init); SMEM_MAX(k_eig_final); SMEM_MAX(k_poisson);
@@ -207,6 +209,8 @@ extern "C" int aks_ctx_create(int device, aks_ctx** out) {
   if (const char* e = getenv("AKS_NO_GRAPH")) ctx->use_graphs = !(e[0] == '1');
   if (const char* e = getenv("AKS_POTENTIAL_TC")) ctx->pot_tc = (e[0] != '0');
   if (const char* e = getenv("AKS_DENS_TC")) ctx->dens_tc = (e[0] != '0');
+  if (const char* e = getenv("AKS_MIX_PIPE")) ctx->mix_pipe = (e[0] != '0');
+  { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
   {
     // batches come and go (one per sweep / restart): their device arrays are taken from the device's
     // stream-ordered pool, which keeps freed memory instead of returning it to the OS
@@ -1023,7 +1027,13 @@ static int step_segment(aks_batch* bt, int seg) {
       LAUNCH_CHECK();
       ktick(bt, "k_mix_state");
       TICK(9);
-      k_mix_dense<<<dim3(b.ntri, b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b);
+      if (ctx->mix_pipe) {
+        const long long items = (long long)b.ntri * b.s * bt->cur->B;
+        const int grid = (int)std::min<long long>(items, 2LL * ctx->sm_count);
+        k_mix_dense_pipe<<<grid, AKS_NT, mix_pipe_smem_bytes(), bt->cur->stream>>>(dv, b);
+      } else {
+        k_mix_dense<<<dim3(b.ntri, b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b);
+      }
       LAUNCH_CHECK();
       ktick(bt, "k_mix_dense");
       TICK(10);

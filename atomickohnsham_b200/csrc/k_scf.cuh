@@ -1236,6 +1236,129 @@ __global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense(DiscDev d, BatchDev b) 
   if (threadIdx.x == 0) b.norm_part[((size_t)p * b.s + e) * b.ntri + blockIdx.x] = (tr == tc) ? acc : 2.0 * acc;
 }
 
+// k_mix_dense_pipe: the same update by PERSISTENT CTAs (two per SM) that walk the (atom, spin, tile) list and keep the old
+// values of the NEXT tile in flight while the current one is updated.  k_mix_dense issues its 16 loads per thread, then
+// stages orbitals, computes, stores and reduces with nothing in flight: ncu shows 32 % of the DRAM throughput at
+// 2 CTAs per SM (126 registers), a CTA living ~12 k cycles for 64 KB of traffic.  Here the old values go through shared
+// memory by cp.async (8-byte copies: the rows of D have an odd stride, 16-byte alignment is not available): every thread
+// copies exactly the 16 entries it will consume, into its own slots of a double buffer, so the buffer needs no barrier --
+// only cp.async.wait_group -- and no registers while the copies fly.
+// MEASURED SLOWER than k_mix_dense (0.177 vs 0.159 ms alone, 1.198 vs 1.178 ms per 8-lane step): the 8-byte cp.async copies
+// cost an LSU instruction each like the loads they replace, the per-item barriers stay, and 124 registers still mean two
+// CTAs per SM.  Off by default (AKS_MIX_PIPE=1 selects it); kept as the record of the experiment.
+__host__ __device__ inline size_t mix_pipe_smem_bytes() {
+  return sizeof(double) * (2 * (size_t)MIX_TS * MIX_TS + 2 * (size_t)MIX_OCH * MIX_TS + AKS_NW + 8);
+}
+__global__ void __launch_bounds__(AKS_NT, 2) k_mix_dense_pipe(DiscDev d, BatchDev b) {
+  extern __shared__ __align__(16) double sm_mix[];
+  double* obuf = sm_mix;                                   // [2][64][64] old values, thread-private slots
+  double (*Ui)[MIX_TS] = reinterpret_cast<double (*)[MIX_TS]>(obuf + 2 * MIX_TS * MIX_TS);
+  double (*Uj)[MIX_TS] = Ui + MIX_OCH;
+  double* red = reinterpret_cast<double*>(Uj + MIX_OCH);
+  const int Nh = d.Nh, s = b.s, ntri = b.ntri;
+  const long long total = (long long)b.B * s * ntri;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // 16 x 16 threads, 4 x 4 entries each
+  // work item w -> (problem, spin, tile (tr, tc)); items of finished problems are skipped
+  auto decode = [&](long long w, int& p, int& e, int& tile, int& tr, int& tc) {
+    tile = (int)(w % ntri);
+    const long long r = w / ntri;
+    e = (int)(r % s);
+    p = (int)(r / s);
+    tr = (int)((sqrt(8.0 * (double)tile + 1.0) - 1.0) * 0.5);
+    while ((tr + 1) * (tr + 2) / 2 <= tile) ++tr;
+    while (tr * (tr + 1) / 2 > tile) --tr;
+    tc = tile - tr * (tr + 1) / 2;
+  };
+  auto next_item = [&](long long w) {   // first item >= w of a running problem
+    while (w < total && b.status[(int)(w / ((long long)s * ntri))] != 0) w += gridDim.x;
+    return w;
+  };
+  auto prefetch = [&](long long w, int buf) {   // cp.async of this thread's 16 old values
+    int p, e, tile, tr, tc;
+    decode(w, p, e, tile, tr, tc);
+    const double* D = b.Dd + ((size_t)p * s + e) * Nh * Nh;
+    const int r0 = tr * MIX_TS + 4 * ty, c0 = tc * MIX_TS + tx;
+    double* dst = obuf + (size_t)buf * MIX_TS * MIX_TS;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (r0 + a < Nh && c0 + 16 * c < Nh) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + (4 * ty + a) * MIX_TS + tx + 16 * c);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(D + (size_t)(r0 + a) * Nh + c0 + 16 * c) : "memory");
+        }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  long long w = next_item(blockIdx.x);
+  if (w >= total) return;
+  prefetch(w, 0);
+  for (int it = 0; w < total; ++it) {
+    const int buf = it & 1;
+    int p, e, tile, tr, tc;
+    decode(w, p, e, tile, tr, tc);
+    const long long wn = next_item(w + gridDim.x);
+    const int r0 = tr * MIX_TS + 4 * ty, c0 = tc * MIX_TS + tx;
+    double* D = b.Dd + ((size_t)p * s + e) * Nh * Nh;
+    // occupied orbitals of this spin (the compact list is ordered by spin)
+    const int tot = b.occ_cnt[2 * p];
+    const int* elk = b.occ_elk + ((size_t)p * 2) * AKS_MAXORB;
+    const double* nn = b.occ_n + ((size_t)p * 2) * AKS_MAXORB;
+    const int sp = ((int)threadIdx.x < tot) ? (elk[threadIdx.x] >> 16) : 99;
+    const int first = __syncthreads_count(sp < e);   // also: the previous item's Ui / Uj / red are no longer read
+    const int cnt = __syncthreads_count(sp == e);
+    const double* Ubase = b.U + (((size_t)p * s + e) * b.Lmax * b.nhmax) * Nh;
+    const double t = b.tmix[p];
+    double dn[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dn[a][c] = 0.0;
+    for (int o0 = 0; o0 < cnt || o0 == 0; o0 += MIX_OCH) {
+      const int oc = min(MIX_OCH, cnt - o0);
+      if (o0 > 0) __syncthreads();
+      for (int idx = threadIdx.x; idx < oc * MIX_TS; idx += AKS_NT) {
+        const int o = idx / MIX_TS, r = idx - o * MIX_TS;
+        const int v = elk[first + o0 + o];
+        const double* u = Ubase + (size_t)((((v >> 8) & 0xff) * b.nhmax) + (v & 0xff)) * Nh;
+        const int gi = tr * MIX_TS + r, gj = tc * MIX_TS + r;
+        Ui[o][r] = (gi < Nh) ? nn[first + o0 + o] * u[gi] : 0.0;   // occupation folded into the row factor
+        Uj[o][r] = (gj < Nh) ? u[gj] : 0.0;
+      }
+      // the old values of the NEXT item start their trip while this one is updated
+      if (o0 == 0 && wn < total) prefetch(wn, buf ^ 1);
+      __syncthreads();
+#pragma unroll 2
+      for (int o = 0; o < oc; ++o) {
+        const double a0 = Ui[o][4 * ty], a1 = Ui[o][4 * ty + 1], a2 = Ui[o][4 * ty + 2], a3 = Ui[o][4 * ty + 3];
+        const double b0 = Uj[o][tx], b1 = Uj[o][tx + 16], b2 = Uj[o][tx + 32], b3 = Uj[o][tx + 48];
+        dn[0][0] = fma(a0, b0, dn[0][0]); dn[0][1] = fma(a0, b1, dn[0][1]); dn[0][2] = fma(a0, b2, dn[0][2]); dn[0][3] = fma(a0, b3, dn[0][3]);
+        dn[1][0] = fma(a1, b0, dn[1][0]); dn[1][1] = fma(a1, b1, dn[1][1]); dn[1][2] = fma(a1, b2, dn[1][2]); dn[1][3] = fma(a1, b3, dn[1][3]);
+        dn[2][0] = fma(a2, b0, dn[2][0]); dn[2][1] = fma(a2, b1, dn[2][1]); dn[2][2] = fma(a2, b2, dn[2][2]); dn[2][3] = fma(a2, b3, dn[2][3]);
+        dn[3][0] = fma(a3, b0, dn[3][0]); dn[3][1] = fma(a3, b1, dn[3][1]); dn[3][2] = fma(a3, b2, dn[3][2]); dn[3][3] = fma(a3, b3, dn[3][3]);
+      }
+    }
+    // this item's old values have landed (the next item's group may still be in flight)
+    if (wn < total) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    const double* ob = obuf + (size_t)buf * MIX_TS * MIX_TS;
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (r0 + a < Nh && c0 + 16 * c < Nh) {
+          const double old = ob[(4 * ty + a) * MIX_TS + tx + 16 * c];
+          const double nv = t * dn[a][c] + (1.0 - t) * old;
+          D[(size_t)(r0 + a) * Nh + c0 + 16 * c] = nv;
+          const double df = nv - old;
+          acc = fma(df, df, acc);
+        }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) b.norm_part[((size_t)p * s + e) * ntri + tile] = (tr == tc) ? acc : 2.0 * acc;
+    w = wn;
+  }
+}
+
 // upper triangle of D from the lower one (see k_mix_dense); one CTA per 32 x 32 tile above the diagonal
 __global__ void __launch_bounds__(AKS_NT) k_mirror_dense(DiscDev d, BatchDev b, int p) {
   __shared__ double tile[32][33];
