@@ -1,5 +1,6 @@
-"""Summary of an `ncu --set full` capture: one row per kernel (the LAST launch of each name in the report) and the DRAM
-bytes per launch that bench.py copies into roofline.traffic.
+"""Summary of an `ncu --set full` capture of ONE step: one row per launch (a kernel that runs twice in a step -- the window
+pass and the refill pass of the eigensolver -- appears as `name` and `name (refill pass)`) and the DRAM bytes per launch
+that bench.py copies into roofline.traffic.
 
   ncu -i gpurun_out/r02_ncu_full.ncu-rep --page raw --csv > /tmp/ncu_raw.csv
   python tools/ncu_summarize.py /tmp/ncu_raw.csv profiles/r02_ncu_full_summary.csv profiles/r02_traffic.json "header text"
@@ -30,6 +31,12 @@ def num(r, n):
 last = {}
 for r in data:
     name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).strip()
+    if name.startswith("void "):
+        name = name[5:]
+    if name in last:
+        name += " (refill pass)"
+    if name in last:
+        continue   # a second step in the capture: the first one is kept
     last[name] = r
 with open(out_csv, "w") as f:
     if header:
