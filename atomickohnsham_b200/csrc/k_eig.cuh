@@ -1192,65 +1192,53 @@ k_eig_final(DiscDev d, BatchDev b, int mode) {
   const double ll = (double)(l * (l + 1));
   const size_t xs = (size_t)(nb * C + C);
   const int c0 = chunk * EIGC_CHUNK, nc = min(C, c0 + EIGC_CHUNK) - c0, nv = nhp - klo;
-  // one warp per (vector PAIR, cell) item; no staging and no CTA barrier: the blocks are read straight through L1 (rows
-  // are coalesced, and the warps of a CTA share the cells of its chunk).  Two vectors of the channel advance together:
-  // every block entry that is loaded feeds both (the kernel is bound by the latency and the number of these loads).
-  const int npair = (nv + 1) >> 1;
-  for (int item = warp; item < npair * nc; item += AKS_NW) {
-    const int k0 = klo + 2 * (item / nc), c = c0 + item % nc;
-    const bool two = k0 + 1 < nhp;
-    const int k1 = two ? k0 + 1 : k0;
+  // (two vectors per warp item -- every loaded block entry feeding both -- was measured SLOWER, 0.142 vs 0.127 ms: the kernel
+  // is bound by the latency of its loads, and half as many items means half as many warps hiding it)
+  // one warp per (vector, cell) item; no staging and no CTA barrier: the blocks are read straight
+  // through L1 (rows are coalesced, and the warps of a CTA share the cells of its chunk)
+  for (int item = warp; item < nv * nc; item += AKS_NW) {
+    const int k = klo + item / nc, c = c0 + item % nc;
     const double* __restrict__ Pc = b.Pm + (chan * C + c) * (size_t)nb * nb;
     const double* __restrict__ Mc = d.M0_loc + (size_t)c * n * n;
     const double* __restrict__ Hc = b.Hfull + (chan * C + c) * (size_t)n * n;
     const double* __restrict__ Ac = d.A_loc + (size_t)c * n * n;
     const double* __restrict__ M2c = d.Mm2_loc + (size_t)c * n * n;
     const double* __restrict__ M1c = d.Mm1_loc + (size_t)c * n * n;
-    const double* X0 = b.Xt + (chan * b.nhmax + k0) * xs;
-    const double* X1 = b.Xt + (chan * b.nhmax + k1) * xs;
+    const double* X = b.Xt + (chan * b.nhmax + k) * xs;
+    double* u = b.U + (chan * b.nhmax + k) * Nh;
     const int g0 = d.l2g[c * n + 2];
     const int gR = (c < C - 1) ? d.l2g[c * n] : -1;
+    const double xt = (lane < nb) ? X[(size_t)lane * C + c] : 0.0;
     const bool inb = lane < nb, inn = lane < n;
-    const double xt0 = inb ? X0[(size_t)lane * C + c] : 0.0;
-    const double xt1 = inb ? X1[(size_t)lane * C + c] : 0.0;
-    double xb0 = 0.0, xb1 = 0.0;   // x_b[lane] = sum_i P[i][lane] x~_i
+    double xb = 0.0;   // x_b[lane] = sum_i P[i][lane] x~_i
 #pragma unroll 4
     for (int i = 0; i < nb; ++i) {
       const double pv = inb ? Pc[i * nb + lane] : 0.0;
-      xb0 = fma(pv, __shfl_sync(0xffffffffu, xt0, i), xb0);
-      xb1 = fma(pv, __shfl_sync(0xffffffffu, xt1, i), xb1);
+      xb = fma(pv, __shfl_sync(0xffffffffu, xt, i), xb);
     }
-    // local vectors in generator order: lane 0 right hat, lane 1 left hat, lanes 2.. bubbles
-    double xl0 = __shfl_up_sync(0xffffffffu, xb0, 2), xl1 = __shfl_up_sync(0xffffffffu, xb1, 2);
-    if (lane == 0) { xl0 = (c < C - 1) ? X0[(size_t)nb * C + c] : 0.0; xl1 = (c < C - 1) ? X1[(size_t)nb * C + c] : 0.0; }
-    if (lane == 1) { xl0 = (c > 0) ? X0[(size_t)nb * C + c - 1] : 0.0; xl1 = (c > 0) ? X1[(size_t)nb * C + c - 1] : 0.0; }
-    if (!inn) { xl0 = 0.0; xl1 = 0.0; }
-    double mx0 = 0.0, hx0 = 0.0, kx0 = 0.0, cx0 = 0.0, mx1 = 0.0, hx1 = 0.0, kx1 = 0.0, cx1 = 0.0;
+    // local vector in generator order: lane 0 right hat, lane 1 left hat, lanes 2.. bubbles
+    double xl = __shfl_up_sync(0xffffffffu, xb, 2);
+    if (lane == 0) xl = (c < C - 1) ? X[(size_t)nb * C + c] : 0.0;
+    if (lane == 1) xl = (c > 0) ? X[(size_t)nb * C + c - 1] : 0.0;
+    if (!inn) xl = 0.0;
+    double mx = 0.0, hx = 0.0, kx = 0.0, cx = 0.0;
 #pragma unroll 3
     for (int a = 0; a < n; ++a) {
       const int o = a * n + lane;
       const double mv = inn ? Mc[o] : 0.0, hv = inn ? Hc[o] : 0.0, cv = inn ? M1c[o] : 0.0;
       const double av = inn ? Ac[o] : 0.0, m2 = (inn && l > 0) ? M2c[o] : 0.0;
-      const double kv = (av + ll * m2) / 2.0;
-      const double xa0 = __shfl_sync(0xffffffffu, xl0, a), xa1 = __shfl_sync(0xffffffffu, xl1, a);
-      mx0 = fma(mv, xa0, mx0); hx0 = fma(hv, xa0, hx0); cx0 = fma(cv, xa0, cx0); kx0 = fma(kv, xa0, kx0);
-      mx1 = fma(mv, xa1, mx1); hx1 = fma(hv, xa1, hx1); cx1 = fma(cv, xa1, cx1); kx1 = fma(kv, xa1, kx1);
+      const double xa = __shfl_sync(0xffffffffu, xl, a);
+      mx = fma(mv, xa, mx); hx = fma(hv, xa, hx); cx = fma(cv, xa, cx);
+      kx = fma((av + ll * m2) / 2.0, xa, kx);
     }
-    const bool owned = (lane >= 2 && inn) || (lane == 0 && gR >= 0);   // entries this cell owns
-    const int gdst = (lane >= 2) ? g0 + lane - 2 : gR;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (h == 1 && !two) break;
-      const int k = h ? k1 : k0;
-      const double xl = h ? xl1 : xl0, mx = h ? mx1 : mx0, hx = h ? hx1 : hx0, kx = h ? kx1 : kx0, cx = h ? cx1 : cx0;
-      double* u = b.U + (chan * b.nhmax + k) * Nh;
-      if (owned) u[gdst] = xl;
-      const double m = warp_sum(mx * xl), hh = warp_sum(hx * xl), sg = warp_sum(owned ? xl : 0.0);
-      const double kk = warp_sum(kx * xl), cc = warp_sum(cx * xl);
-      if (lane == 0) {
-        double* part = b.eig_part + ((chan * b.nhmax + k) * C + c) * 6;
-        part[0] = m; part[1] = hh; part[2] = sg; part[3] = kk; part[4] = cc;
-      }
+    if (lane >= 2 && inn) u[g0 + lane - 2] = xl;
+    if (lane == 0 && gR >= 0) u[gR] = xl;
+    const double own = ((lane >= 2 && inn) || (lane == 0 && gR >= 0)) ? xl : 0.0;   // entries this cell owns
+    const double m = warp_sum(mx * xl), h = warp_sum(hx * xl), sg = warp_sum(own);
+    const double kk = warp_sum(kx * xl), cc = warp_sum(cx * xl);
+    if (lane == 0) {
+      double* part = b.eig_part + ((chan * b.nhmax + k) * C + c) * 6;
+      part[0] = m; part[1] = h; part[2] = sg; part[3] = kk; part[4] = cc;
     }
   }
 }

@@ -33,10 +33,10 @@ for r in data:
     name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).strip()
     if name.startswith("void "):
         name = name[5:]
-    if name in last:
+    if name in last and (name.startswith("k_eig") or name.startswith("k_aufbau")):
         name += " (refill pass)"
     if name in last:
-        continue   # a second step in the capture: the first one is kept
+        continue   # a launch of the neighbouring step in the capture: the first one is kept
     last[name] = r
 with open(out_csv, "w") as f:
     if header:
