@@ -38,7 +38,8 @@ xc_id(f) = f isa AtomicKohnSham.NoFunctional ? Int32(0) :
 Drop-in for `groundstate` on one model or a vector of models sharing `disc`.  The tables are the ones
 `init_cache!` / `GaussLegendre` build on the host; every SCF iteration is one `aks_scf_step`.
 """
-function groundstate_b200(models::Vector{<:KSEModel}, disc, algs; maxiter = 100, callback = nothing, device = 0)
+function groundstate_b200(models::Vector{<:KSEModel}, disc, algs; maxiter = 100, callback = nothing, device = 0,
+                          plot_grid = nothing)
     # `algs` / `maxiter`: one ODA / Int for every model, or a vector with one entry per model (the reference picks
     # both per atom: examples/atomic density comparison/run.jl:74-76) -> aks_batch_set_oda_problem
     alg = algs isa AbstractVector ? first(algs) : algs
@@ -154,10 +155,34 @@ function groundstate_b200(models::Vector{<:KSEModel}, disc, algs; maxiter = 100,
             bh[], i - 1, fp(c.D), fp(c.U), fp(c.ϵ), fp(c.n), isempty(W) ? C_NULL : fp(W)))   # (hi, lo) pairs when T = Double64
         KSESolution(s, _solution_name(models[i]))
     end
+    # optional: the post-processing curves on a plot grid straight from the device state (aks_eval_grid: eval_density,
+    # eval_hartree, eval_vxc of src/solution/postprocess.jl:81-352) -- returned next to the solutions as (ρ, V_H, v_xc) per
+    # problem; the host functions of postprocess.jl keep working on the KSESolution objects above.
+    curves = nothing
+    if plot_grid !== nothing && dtype == 0
+        X = Vector{Float64}(plot_grid)
+        evalg(i, kind, σ) = (out = similar(X); check(ctx[], ccall((:aks_eval_grid, LIB), Cint,
+            (Ptr{Cvoid}, Int32, Int32, Int32, Int32, Int32, Int64, Ptr{Float64}, Ptr{Float64}),
+            bh[], i - 1, kind, 0, 0, σ, length(X), X, out)); out)
+        curves = [(ρ = evalg(i, 1, -1), VH = evalg(i, 2, 0), vxc = evalg(i, 3, 0)) for i in eachindex(models)]
+    end
     ccall((:aks_batch_destroy, LIB), Cvoid, (Ptr{Cvoid},), bh[])
     ccall((:aks_disc_destroy, LIB), Cvoid, (Ptr{Cvoid},), dh[])
     ccall((:aks_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
-    sols
+    curves === nothing ? sols : (sols, curves)
+end
+
+# Double64 tables built by the library on the device instead of QuadGK.gauss(Double64, n) + init_cache! on the host
+# (src/fem/integration methods.jl:46-70, src/discretization/discretization.jl:320-341); results are (hi, lo) pairs,
+# i.e. exactly the memory of a Vector{Double64}.
+function gauss_legendre_b200(n::Integer; device = 0)
+    ctx = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:aks_ctx_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, ctx))
+    x = Vector{Double64}(undef, n); w = Vector{Double64}(undef, n)
+    GC.@preserve x w check(ctx[], ccall((:aks_dd_gauss_legendre, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}),
+                                        ctx[], n, Ptr{Float64}(pointer(x)), Ptr{Float64}(pointer(w))))
+    ccall((:aks_ctx_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx[])
+    x, w
 end
 
 groundstate_b200(model::KSEModel, disc, alg; kw...) = only(groundstate_b200([model], disc, alg; kw...))
