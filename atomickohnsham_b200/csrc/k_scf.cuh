@@ -554,9 +554,12 @@ __global__ void __launch_bounds__(DENS_TC_NT, 3) k_dens_cells_tc(DiscDev d, Batc
         const double* xs = Gs + (size_t)st * STAGE + NR * QCS;                       // nodes of the chunk (image row 24)
         const double* fs = Gs + (size_t)st * STAGE + POT_IMG_ROWS * QCS + warp * QC;  // f of this warp's cell
         const int q0 = ch * QC, ngr = min(QC, Q - q0) >> 3;
-        // sixteen independent DMMA chains per warp (a dependent DMMA waits ~300 cycles for its accumulator: with few chains the
-        // kernel is bound by that latency, not by the pipe): one orbital tile -> eight node groups at a time, two tiles -> four
-        // groups; the even and the odd steps over the generators of a (group, tile) accumulate apart and are added at the end
+        // Eight node groups at a time for one orbital tile, four for two (sixteen accumulator chains per warp; the even and
+        // the odd steps over the generators of a (group, tile) accumulate apart and are added at the end).  With two groups
+        // per iteration the time per group did not depend on the number of DMMAs at all: it was the per-iteration work
+        // around them -- loop and address arithmetic, the two shuffles per group, a finalisation that kept 8 or 16 of 32 lanes
+        // busy -- that bound the kernel.  A batch of 8 / 4 groups shares that work and finishes one node per lane.  (A
+        // dependent DMMA costs 26 cycles and a warp issues one per 16-17.5, tools/micro/latency.cu: latency was never it.)
         auto run = [&](auto ng_c, auto nt_c) {
           constexpr int NG = decltype(ng_c)::value, NTL = decltype(nt_c)::value, NH = (NG + 3) / 4;
           for (int gp = 0; gp < ngr; gp += NG) {

@@ -38,6 +38,17 @@ __global__ void k(double* out, long long* cyc, int n, double a, double b) {
       y = x; x = pn * 1e-1;
   }
   if (MODE == 9) for (int i = 0; i < n; ++i) { double v = x; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); x = v * 1e-3 + a; }  // warp_sum chain
+  if (MODE == 10 || MODE == 11 || MODE == 12) {   // FP64 tensor-core tile update (mma.sync m8n8k4 -> DMMA.8x8x4)
+    double c[8][2];
+    for (int j = 0; j < 8; ++j) c[j][0] = c[j][1] = 0.0;
+    constexpr int NCH = MODE == 10 ? 1 : (MODE == 11 ? 4 : 8);   // independent accumulator chains
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+      for (int j = 0; j < NCH; ++j)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[j][0]), "+d"(c[j][1]) : "d"(a), "d"(b));
+    for (int j = 0; j < 8; ++j) x += c[j][0] + c[j][1];
+  }
   long long t1 = clock64();
   if (threadIdx.x == 0) { out[blockIdx.x] = x + y + z; cyc[blockIdx.x] = t1 - t0; }
 }
@@ -64,5 +75,10 @@ int main() {
   run<7>("LDL^T pivot step (eig_factor critical path)", 32, n);
   run<8>("product-form Sturm step", 32, n);
   run<9>("warp_sum (5 shuffles of a double) chain", 32, n);
+  run<10>("dependent DMMA m8n8k4 (1 chain, 1 warp)", 32, n);
+  run<11>("4 DMMA chains, 1 warp (per round of 4)", 32, n);
+  run<12>("8 DMMA chains, 1 warp (per round of 8)", 32, n);
+  run<12>("8 DMMA chains, 4 warps (per round of 8)", 128, n);
+  run<12>("8 DMMA chains, 16 warps (per round of 8)", 512, n);
   return 0;
 }
