@@ -404,8 +404,15 @@ def b200_arm(args):
     sweeps = {}
     for key, (mm, ll, kk), two_pass in (("c5_86_atoms", (c5m, c5l, c5k), True), ("atoms_x_ions_x_functionals", (bigm, bigl, bigk), False)):
         partitioned_sweep(mm[:8], ll[:8], kk[:8], disc, rank, world, local, False, barrier)   # warm-up (graph capture, pools)
-        secs, mine = partitioned_sweep(mm, ll, kk, disc, rank, world, local, two_pass, barrier)
-        tmax, = allreduce([secs], "MAX")
+        # three repetitions of the whole sweep (wall clock on the host: one run on a shared box can catch a hiccup -- a 2.4x
+        # outlier was seen once); the record is the repetition with the MEDIAN max-over-ranks time, all three are listed
+        reps = []
+        for _ in range(3):
+            secs_r, mine_r = partitioned_sweep(mm, ll, kk, disc, rank, world, local, two_pass, barrier)
+            tmax_r, = allreduce([secs_r], "MAX")
+            reps.append((tmax_r, secs_r, mine_r))
+        order = sorted(range(3), key=lambda i_: reps[i_][0])
+        tmax, secs, mine = reps[order[1]]
         per_rank = [secs]
         counts = [float(len(mine)), float(sum(1 for m_ in mine if m_[1] == "SUCCESS")), float(sum(m_[2] for m_ in mine)),
                   float(sum(1 for m_ in mine if m_[3] == 2))]
@@ -414,7 +421,8 @@ def b200_arm(args):
             dist.all_gather(alls, torch.tensor([secs], dtype=torch.float64, device=dev))
             per_rank = [float(x) for x in alls]
         counts = allreduce(counts, "SUM")
-        sweeps[key] = {"problems": int(counts[0]), "n_gpus": world, "seconds": tmax, "atoms_per_s": counts[0] / tmax,
+        sweeps[key] = {"problems": int(counts[0]), "n_gpus": world, "seconds": tmax, "seconds_each": [r_[0] for r_ in reps],
+                       "atoms_per_s": counts[0] / tmax,
                        "converged": int(counts[1]), "ended_in_a_defined_state": int(counts[0]), "iterations_total": int(counts[2]),
                        "second_pass_problems": int(counts[3]), "per_rank_seconds": per_rank,
                        "load_imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / len(per_rank)),
