@@ -51,6 +51,10 @@ def test_step_level_parity_identical_D(name):
     bt.set_density(0, st.D, [e.Etot, e.Ekin, e.Ecou, e.Ehar, e.Eexc], niter=st.niter)
     Har_o, Vxc_o, _ = o.hamiltonian_parts(st.D)
     assert rel(bt.assemble_hartree(0), Har_o) < 1e-13            # assemble_hartree!
+    if o.hartree != 0:
+        # postcomputations! (oda/loop.jl:51-54): W = A \\ (F:D) of the current D, directly against the oracle's CHOLMOD-style solve
+        W_o = o.assemble_hartree(st.D)[1]
+        assert rel(bt.state(0, want_D=False, want_U=False)["W"], W_o) < 1e-12
     if o.xc.active:
         assert rel(bt.assemble_vxc(0), Vxc_o) < 1e-13            # assemble_exc!
         assert abs(bt.exc_energy(0) - o.exc_energy(st.D)) < 1e-13 * abs(o.exc_energy(st.D))
