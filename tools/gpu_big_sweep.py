@@ -1,5 +1,8 @@
+"""The 1014-problem list (atoms x ions x functionals) of bench.py to convergence on one GPU, three times, and the split of one
+run into batch creation / run loop / state copy (what `sweeps_to_convergence.atoms_x_ions_x_functionals` times)."""
 import os, sys, time
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 from bench import build_disc, sweep_lists
 from atomickohnsham_b200.sweep import solve_sweep
