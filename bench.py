@@ -369,6 +369,13 @@ def b200_arm(args):
                         "k_eig is counted on the work this design does (certified Rayleigh-quotient iteration on per-cell "
                         "tridiagonal forms: sequential pivots, latency bound); by SURVEY 8(d)'s W_eig = L s 12 Nh^2 b (banded "
                         "two-stage reduction) the eigensolve phase would read `eigensolve_phase_by_survey_W_eig` TFLOP/s",
+                "named_kernels": {
+                    "B^T diag(w v) B contraction (north star): k_potential_tc, fraction of the measured FP64 peak":
+                        next((r_["frac_fp64_peak"] for r_ in rows if r_["kernel"] in ("k_potential_tc", "k_potential")), None),
+                    "density at the nodes: k_dens_cells_tc, fraction of the measured FP64 peak":
+                        next((r_["frac_fp64_peak"] for r_ in rows if r_["kernel"] in ("k_dens_cells_tc", "k_dens_cells")), None),
+                    "dense mixing + stopping norm: k_mix_dense, fraction of the measured HBM copy bandwidth":
+                        next((r_["frac_hbm_peak"] for r_ in rows if r_["kernel"] == "k_mix_dense"), None)},
                 "eigensolve_phase_by_survey_W_eig": {
                     "tflops": sum((lh_ + 1) * 12.0 * 799.0 ** 2 * 39.0 for lh_ in lhs) / (phases["eigensolve"] * 1e-3) / 1e12,
                     "phase_ms": phases["eigensolve"]},
