@@ -880,7 +880,7 @@ static int launch_eig_pass(aks_batch* bt, int mode) {
   LAUNCH_CHECK();
   ktick(bt, nm[mode][1]);
   const int nchunk = (dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK;
-  k_eig_final<<<dim3(nchunk, b.Lmax * b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b, mode);
+  k_eig_final<<<dim3(nchunk, b.Lmax * b.s, bt->cur->B), EIGF_NT, 0, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
   ktick(bt, nm[mode][2]);
   k_eig_scale<<<dim3(b.Lmax * b.s, bt->cur->B), AKS_NT, 0, bt->cur->stream>>>(dv, b, dv.C, mode);

@@ -1179,7 +1179,10 @@ k_eig_init(DiscDev d, BatchDev b, int mode) {
 // k_eig_scale then adds the shares in a fixed order: U = x / sqrt(x^T M0 x) with a fixed sign,
 // eps = x^T H x / x^T M0 x.  The kinetic and Coulomb blocks ride along (same staging, two more FMAs per
 // entry), which gives the per-orbital energies of energies.jl:47-87 without another pass over U.
-__global__ void __launch_bounds__(AKS_NT)
+#ifndef EIGF_NT
+#define EIGF_NT 128   // threads per CTA of k_eig_final: nv x EIGC_CHUNK warp items per CTA -- with 4 warps no warp idles for any nv
+#endif
+__global__ void __launch_bounds__(EIGF_NT)
 k_eig_final(DiscDev d, BatchDev b, int mode) {
   const int p = blockIdx.z, ch = blockIdx.y, chunk = blockIdx.x;
   const int e = ch / b.Lmax, l = ch - e * b.Lmax;
@@ -1196,7 +1199,7 @@ k_eig_final(DiscDev d, BatchDev b, int mode) {
   // is bound by the latency of its loads, and half as many items means half as many warps hiding it)
   // one warp per (vector, cell) item; no staging and no CTA barrier: the blocks are read straight
   // through L1 (rows are coalesced, and the warps of a CTA share the cells of its chunk)
-  for (int item = warp; item < nv * nc; item += AKS_NW) {
+  for (int item = warp; item < nv * nc; item += EIGF_NT / 32) {
     const int k = klo + item / nc, c = c0 + item % nc;
     const double* __restrict__ Pc = b.Pm + (chan * C + c) * (size_t)nb * nb;
     const double* __restrict__ Mc = d.M0_loc + (size_t)c * n * n;
