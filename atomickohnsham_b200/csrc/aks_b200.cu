@@ -873,7 +873,7 @@ static int launch_eig_pass(aks_batch* bt, int mode) {
   static const char* const nm[3][4] = {{"k_eig_init", "k_eig", "k_eig_final", "k_eig_scale"},
                                        {"k_eig_init (refill)", "k_eig (refill)", "k_eig_final (refill)", "k_eig_scale (refill)"},
                                        {"k_eig_init (completion)", "k_eig (completion)", "k_eig_final (completion)", "k_eig_scale (completion)"}};
-  k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->cur->B), AKS_NT, bt->smem_chan, bt->cur->stream>>>(dv, b, mode);
+  k_eig_init<<<dim3((dv.C + EIGC_CHUNK - 1) / EIGC_CHUNK, b.Lmax * b.s, bt->cur->B), EIGI_NT, bt->smem_chan, bt->cur->stream>>>(dv, b, mode);
   LAUNCH_CHECK();
   ktick(bt, nm[mode][0]);
   k_eig<<<dim3(b.nhmax, b.Lmax * b.s, bt->cur->B), EIG_NT, bt->smem_eig_main, bt->cur->stream>>>(dv, b, mode);

@@ -1124,7 +1124,10 @@ __host__ __device__ inline size_t eig_chan_smem_bytes(int n, int nb) {
   return sizeof(double) * ((size_t)nb * nb + 4 * (size_t)n * n + 8);
 }
 
-__global__ void __launch_bounds__(AKS_NT)
+#ifndef EIGI_NT
+#define EIGI_NT 128   // threads per CTA of k_eig_init (one warp per vector of the window: rarely more than four)
+#endif
+__global__ void __launch_bounds__(EIGI_NT)
 k_eig_init(DiscDev d, BatchDev b, int mode) {
   const int p = blockIdx.z, ch = blockIdx.y;
   if (b.warm[p] == 0 || !(b.stop[p] < 0.3)) return;
@@ -1150,7 +1153,7 @@ k_eig_init(DiscDev d, BatchDev b, int mode) {
     }
     __syncthreads();
     const int g0 = d.l2g[c * n + 2];
-    for (int k = klo + warp; k < nhp; k += AKS_NW) {
+    for (int k = klo + warp; k < nhp; k += EIGI_NT / 32) {
       const double* u = b.U + (chan * b.nhmax + k) * Nh;
       const double xb = (lane < nb) ? u[g0 + lane] : 0.0;
       double mb = 0.0;
