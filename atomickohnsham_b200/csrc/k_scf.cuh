@@ -878,6 +878,7 @@ __device__ double exc_grid(const DiscDev& d, const BatchDev& b, int p, double a,
 // evaluation is then pure arithmetic (rho(t) is linear in t) + one warp shuffle reduction + ONE pass through shared
 // memory with two barriers -- no global loads, no per-evaluation block_sum of 32 partials.
 #define LS_NT 512
+#define LS_RHO_MIN 1e-30   // densities at or below this are rounding noise of the orbital tails (see ls_exc)
 #define LS_MAXP 4   // grid points per thread held in registers: G <= LS_NT * LS_MAXP = 2048
 // MAXP points per thread (2 for G <= 1024, else 4), NS spins: compile-time so that the arrays live in registers
 template <int MAXP, int NS>
@@ -896,7 +897,16 @@ __device__ __forceinline__ double ls_exc(const LsGrid<MAXP, NS>& g, int G, int e
 #pragma unroll
   for (int j = 0; j < MAXP; ++j) {
     const int q = threadIdx.x + j * LS_NT;
-    if (q < G) {
+    // The energy grid is ONE Gauss rule on [0, Rmax] (quadrature.jl / integration methods.jl): 70-80 % of its nodes lie where
+    // the density of an atom has decayed to rounding noise.  A node whose three densities are all below LS_RHO_MIN adds
+    // less than 1e-33 to a sum of order 0.1 ... 1e3 -- nothing, in double precision -- and is skipped: the functional is
+    // evaluated where it matters (per evaluation ~250 nodes instead of 1000; whole warps of far-out nodes fall through).
+    bool live = q < G && fmax(fmax(fabs(g.n0u[j]), fabs(g.pru[j])), use1 ? fabs(g.n1u[j]) : 0.0) > LS_RHO_MIN;
+    if (s == 2) {
+      constexpr int jd2 = (NS == 2) ? 1 : 0;
+      live = live || (q < G && fmax(fmax(fabs(g.n0d[j * jd2]), fabs(g.prd[j * jd2])), use1 ? fabs(g.n1d[j * jd2]) : 0.0) > LS_RHO_MIN);
+    }
+    if (live) {
       double ru = a * g.n0u[j] + cq * g.pru[j];
       if (use1) ru += bq * g.n1u[j];
       double val;
@@ -968,6 +978,13 @@ template <int MAXP, int NS>
 __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
   const int p = blockIdx.x;
   if (b.status[p] != 0) return;
+#ifdef AKS_LS_TIMING   // cycle stamps of thread 0 (tools/gpu_ls_cycles.py)
+  long long* stamp_ = b.eig_dbg + (size_t)p * 8; int nstamp_ = 0;
+#define LS_STAMP() do { if (threadIdx.x == 0 && nstamp_ < 8) stamp_[nstamp_++] = clock64(); } while (0)
+#else
+#define LS_STAMP() do { } while (0)
+#endif
+  LS_STAMP();
   __shared__ double red[LS_NT / 32 + 2];
   __shared__ LsShared ls;
   __shared__ double sh[16];
@@ -1006,6 +1023,7 @@ __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
       g.y2[j] = yq * yq;
     }
   }
+  LS_STAMP();
   if (!in_regs) {   // never with the supported shapes (npoints <= 2048); keep the failure loud
     if (threadIdx.x == 0) b.status[p] = AKS_EINVAL;
     return;
@@ -1035,6 +1053,7 @@ __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
     sh[4 * slot + 0] = sne; sh[4 * slot + 1] = ek; sh[4 * slot + 2] = ecs; sh[4 * slot + 3] = corr;
   }
   __syncthreads();
+  LS_STAMP();
   const double* sc0 = b.scal + ((size_t)p * 2 + 0) * 4;
   const double* sc1 = b.scal + ((size_t)p * 2 + 1) * 4;
   double Ekin, Ecou, Ehar, Eexc, Etot, td = 1.0;
@@ -1077,6 +1096,7 @@ __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
     if (has_xc) { Eexc = ls_exc(g, G, ex, ec, 1.0, 0.0, 0.0, false, red); __syncthreads(); }
     Etot = has_xc ? (sh[0] - Ehar + Eexc - sh[3]) : (sh[0] - Ehar);
   }
+  LS_STAMP();
   // ---- ODA relaxation (niter > 0)
   const int niter = b.niter[p];
   const double* Ep = b.E + (size_t)p * 5;  // previous: Etot,Ekin,Ecou,Ehar,Eexc
@@ -1108,6 +1128,7 @@ __global__ void __launch_bounds__(LS_NT) k_linesearch(DiscDev d, BatchDev b) {
     Ekin = ekin_m; Ecou = ecou_m; Ehar = ehar_m; Eexc = eexc_m; Etot = etot_m;
     tmix = t;
   }
+  LS_STAMP();
   if (threadIdx.x == 0) {
     double* En = b.Enew + (size_t)p * 5;
     En[0] = Etot; En[1] = Ekin; En[2] = Ecou; En[3] = Ehar; En[4] = Eexc;
