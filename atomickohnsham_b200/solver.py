@@ -492,13 +492,26 @@ def _solution(batch: Batch, i: int, rec: dict, logbook=None, want_arrays=True):
 def _run_batch(models, discretization, alg, maxiter, lh, nh, want_arrays, history=True):
     """One device batch to convergence -> list of KSESolution (the body of the batched `groundstate`)."""
     per_problem = not np.isscalar(maxiter)
-    batch = Batch(models, discretization, alg, lh=lh, nh=nh, maxiter=maxiter if per_problem else None)
+    # problems are dealt over the library's stream lanes by cost (sweep.lane_balanced_order); the solutions come back in
+    # the caller's order
+    n = len(models)
+    order = list(range(n))
+    if n >= 16 and not isinstance(alg, (list, tuple)):   # (a per-problem alg list takes its shared options from entry 0)
+        from .sweep import lane_balanced_order
+        dl, dn = discretization.lh, discretization.nh
+        cost = [((lh[i] if lh is not None and not np.isscalar(lh) else (dl if lh is None else lh)) + 1.0)
+                * (nh[i] if nh is not None and not np.isscalar(nh) else (dn if nh is None else nh)) + 4.0 for i in range(n)]
+        order = lane_balanced_order(cost)
+    pick = lambda v: v if (v is None or np.isscalar(v)) else [v[i] for i in order]
+    algp = [alg[i] for i in order] if isinstance(alg, (list, tuple)) else alg
+    batch = Batch([models[i] for i in order], discretization, algp, lh=pick(lh), nh=pick(nh),
+                  maxiter=pick(maxiter) if per_problem else None)
     final, hist = batch.run(int(max(maxiter)) if per_problem else int(maxiter), history=history,
                             raise_on_problem_error=len(models) == 1)
-    sols = []
-    for i, rec in enumerate(final):
-        lb = LogBook([h["stop"] for h in hist[i]], [h["Etot"] for h in hist[i]]) if hist else None
-        sols.append(_solution(batch, i, rec, lb, want_arrays))
+    sols = [None] * n
+    for j, rec in enumerate(final):
+        lb = LogBook([h["stop"] for h in hist[j]], [h["Etot"] for h in hist[j]]) if hist else None
+        sols[order[j]] = _solution(batch, j, rec, lb, want_arrays)
     batch.close()
     return sols
 

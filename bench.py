@@ -241,6 +241,11 @@ def b200_arm(args):
     models, lhs, nhs = periodic_table_models(range(1, 87), ex=ex, ec=ec, charge=charge)
     if args.sweeps > 1:
         models, lhs, nhs = models * args.sweeps, lhs * args.sweeps, nhs * args.sweeps
+    # the atoms are dealt over the library's 8 stream lanes by cost, as groundstate(list) / solve_sweep do
+    # (sweep.lane_balanced_order): Z = 1..86 in order would put the light atoms into one lane and the heavy ones into another
+    from atomickohnsham_b200.sweep import lane_balanced_order
+    order = lane_balanced_order([(lhs[i] + 1.0) * nhs[i] + 4.0 for i in range(len(models))])
+    models, lhs, nhs = [models[i] for i in order], [lhs[i] for i in order], [nhs[i] for i in order]
     B = len(models)
     alg_fixed = aks.ODA(scftol=0.0, tinit=0.6, aufbau=aks.OptimizedAufbau(tol=1e-3))
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
@@ -461,6 +466,7 @@ def b200_arm(args):
                          "eig_window_margin": args.eig_margin, "eig_window_refills_in_run": refills,
                          "l2": "state per GPU (dense D: %.0f MB) exceeds the 126 MB L2; no explicit flush" % (B * 8 * 799 * 799 / 1e6),
                          "tables": "resident before the timed regions (setup is outside the reference's loop too)",
+                         "problem_order": "dealt over the stream lanes by cost (sweep.lane_balanced_order), as groundstate(list) does",
                          "launch": "8 stream lanes, plain launches (CUDA-graph replay is used for batches <= 32 problems, where "
                                    "launch latency matters); gpu_launches counts the kernels"},
             "clocks": clocks, "gpu_launches": launches, "per_rank_ms_per_step": [x / args.steps for x in per_rank_ms],
