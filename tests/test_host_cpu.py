@@ -221,3 +221,17 @@ def test_host_xc_matches_oracle():
     xu, xd = oxc.slater_vrho_pol(ru, rd)
     cu, cd = oxc.pw92_vrho_pol(ru, rd)
     assert np.allclose(vu, xu + cu, rtol=1e-11, atol=1e-300) and np.allclose(vd, xd + cd, rtol=1e-11, atol=1e-300)
+
+
+def test_lane_balanced_order_is_a_balanced_permutation():
+    """`sweep.lane_balanced_order` (host-side scheduling of a batch over the library's contiguous stream lanes): a
+    permutation of the problems whose eight contiguous ranges carry nearly equal cost."""
+    from atomickohnsham_b200.sweep import lane_balanced_order, periodic_table_models
+    _, lhs, nhs = periodic_table_models(range(1, 87))
+    costs = [(lhs[i] + 1.0) * nhs[i] + 4.0 for i in range(86)]
+    order = lane_balanced_order(costs)
+    assert sorted(order) == list(range(86))
+    per = [sum(costs[i] for i in order[k * 86 // 8:(k + 1) * 86 // 8]) for k in range(8)]
+    natural = [sum(costs[k * 86 // 8:(k + 1) * 86 // 8]) for k in range(8)]
+    assert max(per) / min(per) < 1.35 < max(natural) / min(natural)
+    assert lane_balanced_order([]) == [] and lane_balanced_order([3.0]) == [0]
